@@ -1,0 +1,154 @@
+/*
+ * vsb200.h -- C ABI of the B200-native 360-degree compose path (libvsb200.so).
+ *
+ * Drop-in boundary for the per-frame compose path of ultravideo/video-stitcher.  The reference has
+ * no FFI: its boundary is a set of C++ call sites.  Each entry point below names the
+ * reference interface it stands behind (paths relative to the reference root; A/ = 360_stitcher/,
+ * S/ = sources/modules/stitching/, CW/ = sources/modules/cudawarping/, CA/ = .../cudaarithm/).
+ *
+ * Conventions: plain C types only; every call returns an int status (VSB_OK = 0, negative = error,
+ * text via vsb_last_error()); no exceptions cross the ABI; device buffers are caller-owned or
+ * handle-owned, never returned; every per-frame call takes an explicit cudaStream_t (as void*) and is
+ * asynchronous on it; one handle per GPU; vsb_set_mesh may be called from a second host thread while
+ * another thread runs vsb_feed / vsb_blend / vsb_compose.
+ *
+ * There is NO CPU fallback: every compute entry point fails with VSB_ERR_CUDA when no device is present.
+ */
+#ifndef VSB200_H
+#define VSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSB_OK 0
+#define VSB_ERR_INVALID (-1) /* bad argument / call order (the reference would CV_Assert) */
+#define VSB_ERR_CUDA (-2)    /* CUDA runtime error (the reference would throw via cudaSafeCall) */
+#define VSB_ERR_NOMEM (-3)
+#define VSB_ERR_STATE (-4)   /* handle not fully calibrated for this call */
+
+#define VSB_MAX_VIEWS 16
+#define VSB_MAX_BANDS 7
+
+enum { VSB_PROJ_SPHERICAL = 0, VSB_PROJ_CYLINDRICAL = 1 };
+
+typedef struct vsb_stitcher vsb_stitcher;
+
+typedef struct vsb_config {
+    int num_views;     /* NUM_IMAGES, A/defs.h:37 (compile-time 6 in the reference; any 1..VSB_MAX_VIEWS here) */
+    int num_bands;     /* MultiBandBlender::setNumBands, S/include/opencv2/stitching/detail/blenders.hpp:132 */
+    int enable_local;  /* enable_local, A/defs.h:27 : CPW-mesh remap#2 on/off */
+    int max_batch;     /* frames per vsb_compose submission (>=1); the reference is 1 frame at a time */
+    int device;        /* CUDA device ordinal; -1 = current device (reference: cuda::setDevice(0), A/timed.cpp:496) */
+} vsb_config;
+
+const char *vsb_last_error(void);
+const char *vsb_version(void);
+int vsb_device_count(void);
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+int vsb_create(const vsb_config *cfg, vsb_stitcher **out);
+int vsb_destroy(vsb_stitcher *s);
+
+/* ---- B3: projection maps.  {Spherical,Cylindrical}WarperGpu::warpRoi / buildMaps,
+ *      S/src/warpers_cuda.cpp:210-231,255-277; kernel S/src/cuda/build_warp_maps.cu:88-152 ----------- */
+/* roi = {tl_x, tl_y, width, height}; width/height are the size of the maps buildMaps produces */
+int vsb_warp_roi(int projection, float scale, const float K[9], const float R[9], int src_w, int src_h, int roi[4]);
+/* d_xmap / d_ymap: device, roi[2] x roi[3] floats, pitch in bytes */
+int vsb_build_maps(int projection, float scale, const float K[9], const float R[9], int src_w, int src_h,
+                   float *d_xmap, float *d_ymap, size_t pitch_bytes, int roi[4], void *stream);
+
+/* ---- B6: static setup.  MultiBandBlender::prepare / init_gpu (S/src/blenders.cpp:237-295,344-461),
+ *      x_maps/y_maps (A/calibration.cpp:221), GainCompensator::gains (A/timed.cpp:94) ----------------- */
+int vsb_prepare(vsb_stitcher *s, const int *corners_xy, const int *sizes_wh);
+int vsb_get_roi(const vsb_stitcher *s, int roi_final[4], int roi_padded[4], int *num_bands);
+/* views must be initialised in order i = 0..num_views-1 exactly once after vsb_prepare (the reference push_backs).
+ * mask: CV_8U seam mask of the warped view (host or device memory), tl = corner of the warped view. */
+int vsb_init_view(vsb_stitcher *s, int i, const uint8_t *mask, int w, int h, size_t pitch_bytes,
+                  int tl_x, int tl_y, int mask_on_device);
+/* out8 = {top, bottom, left, right, x_tl, y_tl, x_br, y_br} (S/src/blenders.cpp:383-434) */
+int vsb_get_view_geometry(const vsb_stitcher *s, int i, int out8[8]);
+/* projection maps of remap #1 for view i (size must equal the view's mask size); src_w/src_h = camera frame size */
+int vsb_set_maps(vsb_stitcher *s, int i, const float *xmap, const float *ymap, int w, int h, size_t pitch_bytes,
+                 int maps_on_device, int src_w, int src_h);
+int vsb_set_gain(vsb_stitcher *s, int i, float gain);
+
+/* ---- fixed-rig calibration (the static half of the path): calibrateCameras + warpImages,
+ *      360_stitcher/calibration.cpp:28-249, generalised to N views (yaw_i = 2*pi*i/N, pitch = roll = 0), work_scale =
+ *      compose_scale = 1, sphere radius = pano_width / 2*pi.  Host-side, runs once; computes K/R, seam-scale Voronoi
+ *      masks (VoronoiSeamFinder, S/src/seam_finders.cpp:72-162), compose-scale ROIs and maps, then calls
+ *      vsb_prepare / vsb_init_view / vsb_set_maps / vsb_set_gain.  gains may be NULL (all 1). -------------------- */
+typedef struct vsb_rig_info {
+    int projection;
+    float scale;
+    int src_w, src_h, num_views, num_bands;
+    int roi_final[4], roi_padded[4];
+    int view_roi[VSB_MAX_VIEWS][4]; /* {tl_x, tl_y, w, h} of each warped view */
+} vsb_rig_info;
+int vsb_rig_camera(int n_views, int i, int src_w, int src_h, double hfov_deg, float K[9], float R[9]);
+int vsb_voronoi_seams(int n, const int *sizes_wh, const int *corners_xy, uint8_t *const *masks);
+int vsb_calibrate_rig(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg,
+                      const float *gains);
+int vsb_rig_info_get(const vsb_stitcher *s, vsb_rig_info *out);
+int vsb_get_config(const vsb_stitcher *s, vsb_config *out);
+
+/* ---- B1 + B2: custom_resize (A/resize.cu:9-45) and MeshWarper::convertMeshesToMap for one view
+ *      (A/meshwarper.cpp:823-886).  mesh_x/mesh_y: host, rows x cols floats (vertex positions).
+ *      Thread-safe w.r.t. feed/blend/compose; the new maps are used by the first compose submitted
+ *      after this call returns. ------------------------------------------------------------------------ */
+int vsb_set_mesh(vsb_stitcher *s, int i, const float *mesh_x, const float *mesh_y, int rows, int cols);
+int vsb_custom_resize(const float *d_in, int cols, int rows, size_t in_pitch_bytes,
+                      float *d_out, int tx, int ty, size_t out_pitch_bytes, void *stream);
+
+/* ---- B4: per-view feed = stitch_online minus the H2D upload (A/timed.cpp:56-121):
+ *      remap#1 -> gain -> remap#2 -> MultiBandBlender::feed_online (S/src/blenders.cpp:700-749) -------- */
+int vsb_feed(vsb_stitcher *s, int i, const uint8_t *d_bgr, size_t pitch_bytes, void *stream);
+/* ---- B5: MultiBandBlender::blend(dst, dst_mask, gpuOut, true) (S/src/blenders.cpp:758-832).
+ *      d_out: caller-owned CV_16SC3 of roi_final size. ------------------------------------------------- */
+int vsb_blend(vsb_stitcher *s, int16_t *d_out, size_t out_pitch_bytes, void *stream);
+/* ---- stitch_one (A/timed.cpp:123-152) for n_frames frames in one submission.
+ *      d_srcs[f*num_views + i] = device BGR frame of view i, frame f; d_outs[f] = device CV_16SC3 output. */
+int vsb_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch_bytes,
+                int16_t *const *d_outs, size_t out_pitch_bytes, void *stream);
+/* Same with HOST buffers (what A/timed.cpp:68 upload + the consumer's download do): H2D, compose, D2H;
+ * returns after the outputs are in host memory. */
+int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs, size_t src_pitch_bytes,
+                     int16_t *const *h_outs, size_t out_pitch_bytes);
+/* number of kernels the last vsb_compose / vsb_feed+vsb_blend submission launched */
+int vsb_last_launch_count(const vsb_stitcher *s);
+
+/* ---- B7: device-launcher layer (the .cpp -> .cu seam inside the reference's OpenCV), one primitive per
+ *      reference kernel, interleaved OpenCV layouts, pitches in bytes ---------------------------------- */
+/* cuda::remap LINEAR/BORDER_CONSTANT(0) on CV_8UC3: CW/src/cuda/remap.cu:56-86 */
+int vsb_remap_linear_u8c3(const uint8_t *d_src, int sw, int sh, size_t src_pitch,
+                          const float *d_xmap, const float *d_ymap, size_t map_pitch,
+                          uint8_t *d_dst, int dw, int dh, size_t dst_pitch, void *stream);
+/* GpuMat::convertTo(type, alpha) on CV_8U: CORE/src/cuda/gpu_mat.cu:488-512 */
+int vsb_gain_u8(uint8_t *d_buf, int width_bytes, int h, size_t pitch, float gain, void *stream);
+/* cuda::copyMakeBorder(BORDER_REFLECT)+convertTo(CV_16S): CA/src/cuda/copy_make_border.cu:92-124 */
+int vsb_border_reflect_u8c3_to_s16c3(const uint8_t *d_src, int w, int h, size_t src_pitch, int top, int bottom,
+                                     int left, int right, int16_t *d_dst, size_t dst_pitch, void *stream);
+/* cuda::pyrDown / cuda::pyrUp on CV_16SC3: CW/src/cuda/pyr_down.cu:55-188, pyr_up.cu:55-157 */
+int vsb_pyr_down_s16c3(const int16_t *d_src, int w, int h, size_t src_pitch, int16_t *d_dst, size_t dst_pitch, void *stream);
+int vsb_pyr_up_s16c3(const int16_t *d_src, int w, int h, size_t src_pitch, int16_t *d_dst, size_t dst_pitch, void *stream);
+/* cuda::pyrDown on CV_32FC1 (weight pyramids, S/src/blenders.cpp:422-423) */
+int vsb_pyr_down_f32(const float *d_src, int w, int h, size_t src_pitch, float *d_dst, size_t dst_pitch, void *stream);
+/* addSrcWeightGpu32F / normalizeUsingWeightMapGpu32F: S/src/cuda/multiband_blend.cu:36-60,85-108 */
+int vsb_add_src_weight_32f(const int16_t *d_src, size_t src_pitch, const float *d_w, size_t w_pitch,
+                           int16_t *d_dst, size_t dst_pitch, float *d_dst_w, size_t dst_w_pitch,
+                           int w, int h, void *stream);
+int vsb_normalize_32f(const float *d_w, size_t w_pitch, int16_t *d_src, size_t src_pitch, int w, int h, void *stream);
+
+/* ---- introspection for parity tests: copy an internal buffer of frame slot `frame` to host.
+ *      what: 0 = warped view Q (u8x3 interleaved, roi size), 1 = Gaussian level k (s16x3 interleaved, k>=0,
+ *      bordered size >> k), 2 = weight level k (f32), 3 = canvas weight sum level k (f32, view ignored),
+ *      4 = x mesh map (f32, roi size), 5 = y mesh map. `bytes` must match exactly. ---------------------- */
+int vsb_debug_read(vsb_stitcher *s, int what, int view, int level, int frame, void *h_dst, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSB200_H */

@@ -1,0 +1,211 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI) against oracle-G on identical seeded inputs.
+Bar: bit-exact (every stage is integer/byte work or fp32 with a pinned operation order)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _eq(a, b, what):
+    a = np.asarray(a); b = np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    if a.dtype.kind == "f":
+        same = (a == b) | (np.isnan(a) & np.isnan(b))
+    else:
+        same = a == b
+    assert same.all(), f"{what}: {np.count_nonzero(~same)} of {a.size} samples differ (max |d| = " \
+                       f"{np.nanmax(np.abs(a.astype(np.float64) - b.astype(np.float64)))})"
+
+
+# ------------------------------------------------------------------------------------------ B7 primitives
+@pytest.mark.parametrize("shape,dshape", [((120, 160), (90, 130)), ((33, 47), (64, 64)), ((1080, 1920), (200, 333))])
+def test_remap_linear_matches_oracle(cuda, og, vsb, shape, dshape):
+    # recipe of sources/modules/cudawarping/test/test_remap.cpp:158-177 (random image, maps reaching outside the image)
+    from tests.gpu_util import dev, host, stream
+    rng = np.random.default_rng(1)
+    src = rng.integers(0, 256, shape + (3,), dtype=np.uint8)
+    xm = (rng.random(dshape) * (shape[1] + 10) - 5).astype(np.float32)
+    ym = (rng.random(dshape) * (shape[0] + 10) - 5).astype(np.float32)
+    xm[0, 0] = np.nan; ym[1, 1] = np.nan; xm[2, 2] = -1; ym[2, 2] = -1; xm[3, 3] = 1e12
+    want = og.remap_linear_u8(src, xm, ym)
+    d_src, d_x, d_y = dev(src), dev(xm), dev(ym)
+    d_dst = cuda.zeros(dshape + (3,), dtype=cuda.uint8, device="cuda")
+    vsb.check(vsb.lib().vsb_remap_linear_u8c3(vsb._vp(d_src.data_ptr()), shape[1], shape[0], vsb.C.c_size_t(shape[1] * 3),
+                                              vsb._vp(d_x.data_ptr()), vsb._vp(d_y.data_ptr()), vsb.C.c_size_t(dshape[1] * 4),
+                                              vsb._vp(d_dst.data_ptr()), dshape[1], dshape[0], vsb.C.c_size_t(dshape[1] * 3), vsb._vp(stream())))
+    _eq(host(d_dst), want, "remap")
+
+
+@pytest.mark.parametrize("shape", [(64, 96), (160, 224), (33, 47), (20, 37), (640, 1184)])
+def test_pyramids_match_oracle(cuda, og, vsb, shape):
+    # sizes of sources/modules/cudawarping/test/test_pyramids.cpp plus the blender's CV_16SC3 type it omits
+    from tests.gpu_util import dev, host, stream
+    rng = np.random.default_rng(2)
+    a = rng.integers(-32768, 32768, shape + (3,)).astype(np.int16)
+    h, w = shape
+    d_a = dev(a)
+    dh, dw = (h + 1) // 2, (w + 1) // 2
+    d_dn = cuda.zeros((dh, dw, 3), dtype=cuda.int16, device="cuda")
+    vsb.check(vsb.lib().vsb_pyr_down_s16c3(vsb._vp(d_a.data_ptr()), w, h, vsb.C.c_size_t(w * 6), vsb._vp(d_dn.data_ptr()), vsb.C.c_size_t(dw * 6), vsb._vp(stream())))
+    _eq(host(d_dn), og.pyr_down_s16(a), "pyrDown s16c3")
+    d_up = cuda.zeros((2 * h, 2 * w, 3), dtype=cuda.int16, device="cuda")
+    vsb.check(vsb.lib().vsb_pyr_up_s16c3(vsb._vp(d_a.data_ptr()), w, h, vsb.C.c_size_t(w * 6), vsb._vp(d_up.data_ptr()), vsb.C.c_size_t(2 * w * 6), vsb._vp(stream())))
+    _eq(host(d_up), og.pyr_up_s16(a), "pyrUp s16c3")
+    f = rng.random(shape).astype(np.float32)
+    d_f = dev(f)
+    d_fd = cuda.zeros((dh, dw), dtype=cuda.float32, device="cuda")
+    vsb.check(vsb.lib().vsb_pyr_down_f32(vsb._vp(d_f.data_ptr()), w, h, vsb.C.c_size_t(w * 4), vsb._vp(d_fd.data_ptr()), vsb.C.c_size_t(dw * 4), vsb._vp(stream())))
+    _eq(host(d_fd), og.pyr_down_f32(f), "pyrDown f32")
+
+
+def test_border_gain_resize_weighted_add_match_oracle(cuda, og, vsb):
+    from tests.gpu_util import dev, host, stream
+    rng = np.random.default_rng(3)
+    L = vsb.lib(); vp = vsb._vp; sz = vsb.C.c_size_t
+    img = rng.integers(0, 256, (50, 70, 3), dtype=np.uint8)
+    for (t, b, l, r) in [(0, 13, 127, 97), (5, 0, 0, 1), (60, 3, 80, 2)]:
+        d = cuda.zeros((50 + t + b, 70 + l + r, 3), dtype=cuda.int16, device="cuda")
+        vsb.check(L.vsb_border_reflect_u8c3_to_s16c3(vp(dev(img).data_ptr()), 70, 50, sz(210), t, b, l, r, vp(d.data_ptr()), sz((70 + l + r) * 6), vp(stream())))
+        _eq(host(d), og.border_reflect_u8c3_to_s16(img, t, b, l, r), "copyMakeBorder REFLECT")
+    for g in (0.97, 1.0, 1.03, 1.7):
+        d = dev(img)
+        vsb.check(L.vsb_gain_u8(vp(d.data_ptr()), 210, 50, sz(210), vsb.C.c_float(g), vp(stream())))
+        _eq(host(d), og.gain_u8(img, np.float32(g)), "gain")
+    m = rng.random((10, 10)).astype(np.float32) * 100
+    d = cuda.zeros((627, 961), dtype=cuda.float32, device="cuda")
+    vsb.check(L.vsb_custom_resize(vp(dev(m).data_ptr()), 10, 10, sz(40), vp(d.data_ptr()), 961, 627, sz(961 * 4), vp(stream())))
+    _eq(host(d), og.custom_resize(m, 961, 627), "custom_resize")
+    # addSrcWeight / normalize: replay against the oracle blender arithmetic on one level
+    src = rng.integers(-300, 300, (40, 64, 3)).astype(np.int16)
+    w = rng.random((40, 64)).astype(np.float32)
+    w[rng.random((40, 64)) < 0.3] = 0
+    dst = rng.integers(-300, 300, (40, 64, 3)).astype(np.int16)
+    dw = rng.random((40, 64)).astype(np.float32)
+    d_dst, d_dw = dev(dst), dev(dw)
+    vsb.check(L.vsb_add_src_weight_32f(vp(dev(src).data_ptr()), sz(64 * 6), vp(dev(w).data_ptr()), sz(256), vp(d_dst.data_ptr()), sz(64 * 6), vp(d_dw.data_ptr()), sz(256), 64, 40, vp(stream())))
+    want = (dst.astype(np.int32) + np.trunc(src.astype(np.float32) * w[..., None]).astype(np.int32)).astype(np.int16)
+    _eq(host(d_dst), want, "addSrcWeight32F")
+    _eq(host(d_dw), dw + w, "addSrcWeight32F weights")
+    vsb.check(L.vsb_normalize_32f(vp(d_dw.data_ptr()), sz(256), vp(d_dst.data_ptr()), sz(64 * 6), 64, 40, vp(stream())))
+    want2 = np.trunc(want.astype(np.float32) / ((dw + w) + np.float32(1e-5))[..., None]).astype(np.int16)
+    _eq(host(d_dst), want2, "normalize32F")
+
+
+# ------------------------------------------------------------------------------------------ whole path
+CASES = {
+    "small4": dict(n_views=4, src_w=320, src_h=240, pano_width=1024, num_bands=3, enable_local=True),
+    "small6_nolocal": dict(n_views=6, src_w=320, src_h=180, pano_width=960, num_bands=5, enable_local=False),
+    "cyl5": dict(n_views=5, src_w=256, src_h=192, pano_width=800, num_bands=4, enable_local=True, projection=1),
+    "cfg2": dict(n_views=6, src_w=1920, src_h=1080, pano_width=3840, num_bands=5, enable_local=True),
+}
+
+
+def _rigs(case, inject, max_batch=1):
+    import vsb200
+    from oracle import pipeline as op
+    from tests.gpu_util import GpuRig
+    kw = dict(CASES[case])
+    gains = vsb200.synth.gains(kw["n_views"])
+    orig = op.OracleRig(gains=gains, **kw)
+    grig = GpuRig(gains=gains, max_batch=max_batch, oracle_rig=orig if inject else None, **kw)
+    if kw["enable_local"]:
+        for i in range(kw["n_views"]):
+            mx, my = vsb200.synth.mesh(*orig.sizes[i])
+            orig.set_mesh(i, mx, my)
+            grig.set_mesh(i, mx, my)
+    return orig, grig, kw
+
+
+@pytest.mark.parametrize("case", ["small4", "small6_nolocal", "cyl5", "cfg2"])
+def test_calibration_products_match_oracle(cuda, og, case):
+    orig, grig, kw = _rigs(case, inject=False)
+    assert grig.roi_final == orig.roi_final and grig.roi_padded == orig.roi_padded and grig.num_bands == orig.num_bands
+    for i in range(kw["n_views"]):
+        assert grig.geom[i] == orig.blender.view_geom(i), f"view {i} border geometry"
+        assert grig.sizes[i] == tuple(orig.sizes[i]) and grig.corners[i] == tuple(orig.corners[i])
+        for k in range(orig.num_bands + 1):
+            _eq(grig.weight(i, k), orig.blender.view_weight(i, k), f"weight pyramid view {i} level {k}")
+        # level-0 weight inside the un-bordered rect is mask/255: seam masks bit-exact
+        g = grig.geom[i]
+        w0 = grig.weight(i, 0)[g["top"]:g["top"] + orig.sizes[i][1], g["left"]:g["left"] + orig.sizes[i][0]]
+        _eq(np.rint(w0 * 255).astype(np.uint8), orig.masks[i], f"seam mask view {i}")
+        if kw["enable_local"]:
+            _eq(grig.mesh_map(i, 0), orig.mesh_maps[i][0], f"x mesh map view {i}")
+            _eq(grig.mesh_map(i, 1), orig.mesh_maps[i][1], f"y mesh map view {i}")
+
+
+@pytest.mark.parametrize("case,inject", [("small4", True), ("small4", False), ("small6_nolocal", False), ("cyl5", False),
+                                          ("cfg2", True), ("cfg2", False)])
+def test_compose_matches_oracle(cuda, og, case, inject):
+    import vsb200
+    orig, grig, kw = _rigs(case, inject)
+    frames = [vsb200.synth.frame(i, 0, kw["src_w"], kw["src_h"]) for i in range(kw["n_views"])]
+    want, want_mask = orig.compose(frames)
+    got = grig.compose([frames])[0]
+    # intermediates first so a failure names the stage
+    for i in range(kw["n_views"]):
+        _eq(grig.warped(i), orig.warp_view(i, frames[i]), f"warped view {i}")
+    for i in range(kw["n_views"]):
+        # oracle src_level holds Laplacians after feed; rebuild the Gaussian pyramid from the warped view
+        g = orig.blender.view_geom(i)
+        gk = og.border_reflect_u8c3_to_s16(orig.warp_view(i, frames[i]), g["top"], g["bottom"], g["left"], g["right"])
+        for k in range(orig.num_bands + 1):
+            _eq(grig.gauss_level(i, k), gk, f"gaussian level {k} view {i}")
+            gk = og.pyr_down_s16(gk)
+    _eq(got, want, "composed panorama (CV_16SC3)")
+    _eq((np.abs(got).sum(axis=2) > 0) | (want_mask > 0), want_mask > 0, "output mask support")
+    assert grig.st.last_launch_count() == 3 + orig.num_bands
+    # B4/B5 per-view entry points give the same frame
+    _eq(grig.feed_blend(frames), want, "feed + blend")
+
+
+def test_batched_compose_and_mesh_swap(cuda, og):
+    import vsb200
+    orig, grig, kw = _rigs("small4", inject=False, max_batch=3)
+    fr = [[vsb200.synth.frame(i, f, kw["src_w"], kw["src_h"]) for i in range(kw["n_views"])] for f in range(3)]
+    want = [orig.compose(f)[0] for f in fr]
+    got = grig.compose(fr)
+    for f in range(3):
+        _eq(got[f], want[f], f"batched frame {f}")
+    # install a different mesh (recalibration, config 5) and compose again
+    for i in range(kw["n_views"]):
+        mx, my = vsb200.synth.mesh(*orig.sizes[i], phase=0.7)
+        orig.set_mesh(i, mx, my)
+        grig.set_mesh(i, mx, my)
+    _eq(grig.compose([fr[1]])[0], orig.compose(fr[1])[0], "after mesh swap")
+    # and swap twice without a compose in between (re-uses the unpublished buffer)
+    for ph in (0.2, 1.1):
+        for i in range(kw["n_views"]):
+            mx, my = vsb200.synth.mesh(*orig.sizes[i], phase=ph)
+            orig.set_mesh(i, mx, my)
+            grig.set_mesh(i, mx, my)
+    _eq(grig.compose([fr[2]])[0], orig.compose(fr[2])[0], "after double mesh swap")
+
+
+def test_compose_host_roundtrip(cuda, og):
+    import vsb200
+    orig, grig, kw = _rigs("small4", inject=False, max_batch=2)
+    fr = [[vsb200.synth.frame(i, f, kw["src_w"], kw["src_h"]) for i in range(kw["n_views"])] for f in range(2)]
+    W, H = grig.roi_final[2], grig.roi_final[3]
+    outs = [np.zeros((H, W, 3), np.int16) for _ in range(2)]
+    grig.st.compose_host([a.ctypes.data for f in fr for a in f], kw["src_w"] * 3, [o.ctypes.data for o in outs], W * 6)
+    for f in range(2):
+        _eq(outs[f], orig.compose(fr[f])[0], f"host-buffer compose frame {f}")
+
+
+def test_error_behaviour(cuda, vsb):
+    # call-order and argument errors surface as status codes + text, never as crashes (the reference CV_Asserts)
+    st = vsb.Stitcher(2, 5, True, 1)
+    with pytest.raises(vsb.VsbError):
+        st.get_roi()
+    st.prepare([(0, 0), (50, 0)], [(64, 64), (64, 64)])
+    m = np.full((64, 64), 255, np.uint8)
+    with pytest.raises(vsb.VsbError):
+        st.init_view(1, m.ctypes.data, 64, 64, 64, (50, 0))  # out of order
+    st.init_view(0, m.ctypes.data, 64, 64, 64, (0, 0))
+    st.init_view(1, m.ctypes.data, 64, 64, 64, (50, 0))
+    with pytest.raises(vsb.VsbError):
+        st.feed(0, 1, 192)  # no maps yet
+    with pytest.raises(vsb.VsbError):
+        vsb.Stitcher(0)
+    assert b"num_views" in vsb.lib().vsb_last_error()

@@ -1,0 +1,187 @@
+"""ctypes binding of libvsb200.so (the C ABI declared in include/vsb200.h).
+
+Harness glue only: device memory, streams and process groups come from PyTorch in tests/ and bench.py;
+all compute happens inside the shared library.  There is no CPU fallback -- if the library or a CUDA
+device is missing the calls raise.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvsb200.so")
+
+OK = 0
+PROJ_SPHERICAL = 0
+PROJ_CYLINDRICAL = 1
+MAX_VIEWS = 16
+MAX_BANDS = 7
+
+# every symbol include/vsb200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "vsb_last_error", "vsb_version", "vsb_device_count", "vsb_create", "vsb_destroy", "vsb_warp_roi",
+    "vsb_build_maps", "vsb_prepare", "vsb_get_roi", "vsb_init_view", "vsb_get_view_geometry", "vsb_set_maps",
+    "vsb_set_gain", "vsb_set_mesh", "vsb_custom_resize", "vsb_feed", "vsb_blend", "vsb_compose",
+    "vsb_compose_host", "vsb_last_launch_count", "vsb_remap_linear_u8c3", "vsb_gain_u8",
+    "vsb_border_reflect_u8c3_to_s16c3", "vsb_pyr_down_s16c3", "vsb_pyr_up_s16c3", "vsb_pyr_down_f32",
+    "vsb_add_src_weight_32f", "vsb_normalize_32f", "vsb_debug_read",
+    "vsb_rig_camera", "vsb_voronoi_seams", "vsb_calibrate_rig", "vsb_rig_info_get", "vsb_get_config",
+]
+
+
+class VsbError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("num_views", C.c_int), ("num_bands", C.c_int), ("enable_local", C.c_int),
+                ("max_batch", C.c_int), ("device", C.c_int)]
+
+
+class RigInfo(C.Structure):
+    _fields_ = [("projection", C.c_int), ("scale", C.c_float), ("src_w", C.c_int), ("src_h", C.c_int),
+                ("num_views", C.c_int), ("num_bands", C.c_int),
+                ("roi_final", C.c_int * 4), ("roi_padded", C.c_int * 4),
+                ("view_roi", (C.c_int * 4) * MAX_VIEWS)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VsbError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no fallback path)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.vsb_last_error.restype = C.c_char_p
+        _lib.vsb_version.restype = C.c_char_p
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise VsbError(f"vsb error {rc}: {lib().vsb_last_error().decode()}")
+    return rc
+
+
+def _vp(x):
+    return C.c_void_p(int(x) if x is not None else 0)
+
+
+def _fp9(a):
+    return (C.c_float * 9)(*[float(v) for v in a])
+
+
+def warp_roi(projection, scale, K, R, src_w, src_h):
+    roi = (C.c_int * 4)()
+    check(lib().vsb_warp_roi(projection, C.c_float(scale), _fp9(K), _fp9(R), src_w, src_h, roi))
+    return tuple(roi)
+
+
+def rig_camera(n_views, i, src_w, src_h, hfov_deg=90.0):
+    K = (C.c_float * 9)()
+    R = (C.c_float * 9)()
+    check(lib().vsb_rig_camera(n_views, i, src_w, src_h, C.c_double(hfov_deg), K, R))
+    return list(K), list(R)
+
+
+class Stitcher:
+    """Thin RAII wrapper over a vsb_stitcher handle; pointer arguments are raw device/host addresses."""
+
+    def __init__(self, num_views, num_bands=5, enable_local=True, max_batch=1, device=-1):
+        self.cfg = Config(num_views, num_bands, int(bool(enable_local)), max_batch, device)
+        self._h = C.c_void_p()
+        check(lib().vsb_create(C.byref(self.cfg), C.byref(self._h)))
+        self.num_views = num_views
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().vsb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- static setup
+    def prepare(self, corners_xy, sizes_wh):
+        n = self.num_views
+        c = (C.c_int * (2 * n))(*[int(v) for p in corners_xy for v in p])
+        s = (C.c_int * (2 * n))(*[int(v) for p in sizes_wh for v in p])
+        check(lib().vsb_prepare(self._h, c, s))
+
+    def get_roi(self):
+        a, b, nb = (C.c_int * 4)(), (C.c_int * 4)(), C.c_int()
+        check(lib().vsb_get_roi(self._h, a, b, C.byref(nb)))
+        return tuple(a), tuple(b), nb.value
+
+    def init_view(self, i, mask_ptr, w, h, pitch, tl, on_device=False):
+        check(lib().vsb_init_view(self._h, i, _vp(mask_ptr), w, h, C.c_size_t(pitch), int(tl[0]), int(tl[1]), int(on_device)))
+
+    def view_geometry(self, i):
+        g = (C.c_int * 8)()
+        check(lib().vsb_get_view_geometry(self._h, i, g))
+        return dict(zip(["top", "bottom", "left", "right", "x_tl", "y_tl", "x_br", "y_br"], g))
+
+    def set_maps(self, i, xmap_ptr, ymap_ptr, w, h, pitch, src_w, src_h, on_device=False):
+        check(lib().vsb_set_maps(self._h, i, _vp(xmap_ptr), _vp(ymap_ptr), w, h, C.c_size_t(pitch), int(on_device), src_w, src_h))
+
+    def set_gain(self, i, gain):
+        check(lib().vsb_set_gain(self._h, i, C.c_float(gain)))
+
+    def set_mesh(self, i, mesh_x_ptr, mesh_y_ptr, rows, cols):
+        check(lib().vsb_set_mesh(self._h, i, _vp(mesh_x_ptr), _vp(mesh_y_ptr), rows, cols))
+
+    def calibrate_rig(self, projection, pano_width, src_w, src_h, hfov_deg=90.0, gains=None):
+        g = None
+        if gains is not None:
+            g = (C.c_float * self.num_views)(*[float(v) for v in gains])
+        check(lib().vsb_calibrate_rig(self._h, projection, pano_width, src_w, src_h, C.c_double(hfov_deg), g))
+
+    def rig_info(self):
+        info = RigInfo()
+        check(lib().vsb_rig_info_get(self._h, C.byref(info)))
+        return info
+
+    # ---- per frame
+    def feed(self, i, src_ptr, pitch, stream=0):
+        check(lib().vsb_feed(self._h, i, _vp(src_ptr), C.c_size_t(pitch), _vp(stream)))
+
+    def blend(self, out_ptr, out_pitch, stream=0):
+        check(lib().vsb_blend(self._h, _vp(out_ptr), C.c_size_t(out_pitch), _vp(stream)))
+
+    def compose(self, src_ptrs, src_pitch, out_ptrs, out_pitch, stream=0):
+        n_frames = len(out_ptrs)
+        assert len(src_ptrs) == n_frames * self.num_views
+        sp = (C.c_void_p * len(src_ptrs))(*[int(p) for p in src_ptrs])
+        op = (C.c_void_p * n_frames)(*[int(p) for p in out_ptrs])
+        check(lib().vsb_compose(self._h, n_frames, sp, C.c_size_t(src_pitch), op, C.c_size_t(out_pitch), _vp(stream)))
+
+    def make_compose_call(self, src_ptrs, src_pitch, out_ptrs, out_pitch, stream=0):
+        """Pre-marshalled compose call (keeps ctypes overhead out of timed loops)."""
+        n_frames = len(out_ptrs)
+        sp = (C.c_void_p * len(src_ptrs))(*[int(p) for p in src_ptrs])
+        op = (C.c_void_p * n_frames)(*[int(p) for p in out_ptrs])
+        fn, h, a, b, st = lib().vsb_compose, self._h, C.c_size_t(src_pitch), C.c_size_t(out_pitch), _vp(stream)
+
+        def call():
+            rc = fn(h, n_frames, sp, a, op, b, st)
+            if rc != OK:
+                check(rc)
+        call._keep = (sp, op)
+        return call
+
+    def compose_host(self, src_ptrs, src_pitch, out_ptrs, out_pitch):
+        n_frames = len(out_ptrs)
+        sp = (C.c_void_p * len(src_ptrs))(*[int(p) for p in src_ptrs])
+        op = (C.c_void_p * n_frames)(*[int(p) for p in out_ptrs])
+        check(lib().vsb_compose_host(self._h, n_frames, sp, C.c_size_t(src_pitch), op, C.c_size_t(out_pitch)))
+
+    def last_launch_count(self):
+        return lib().vsb_last_launch_count(self._h)
+
+    def debug_read(self, what, view, level, frame, host_ptr, nbytes):
+        check(lib().vsb_debug_read(self._h, what, view, level, frame, _vp(host_ptr), C.c_size_t(nbytes)))

@@ -1,0 +1,1076 @@
+// vsb_pipeline.cu -- the fused per-frame compose path (sm_100a) and the handle behind the C ABI.
+//
+// Reference path replaced: stitch_online x N -> MultiBandBlender::feed_online x N ->
+// MultiBandBlender::blend, ~190 kernel launches and ~1.1 GB of HBM traffic per frame in the reference
+// (360_stitcher/timed.cpp:56-152, sources/modules/stitching/src/blenders.cpp:700-832).
+//
+// Here one frame (or a batch of F frames) is
+//   K1 k_remap_stage1   src (u8x3)            -> P  = gain(remap#1(src))          u8x3 interleaved, ROI size
+//   K2 k_remap_stage2   P + CPW mesh maps     -> G0 = REFLECT-bordered remap#2(P) u8 planar, bordered size
+//   K3 k_pyr_down x nb  G(k)                  -> G(k+1)                            s16 planar
+//   K4 k_blend_collapse G(0..nb), W, sum(W)   -> out (CV_16SC3)
+// K4 fuses, per output tile and entirely on chip: pyrUp+subtract (Laplacian) of every contributing view,
+// the truncating weighted add, the normalisation by the static weight sum, the whole pyramid collapse
+// (pyrUp+add per level), the output mask and the crop.  The destination pyramid, the `ups` buffers and
+// the per-frame clears of the reference never exist.
+//
+// HBM layout: all per-view intermediates are PLANAR (one plane per colour channel) with the bordered
+// width (a multiple of 2^nb >= 32) as row length, so rows of every level start 16-byte aligned.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "vsb_internal.h"
+
+namespace vsb {
+
+constexpr int MAXV = VSB_MAX_VIEWS;
+constexpr int MAXL = VSB_MAX_BANDS + 1;
+constexpr int MAX_BATCH = 8;
+
+// ============================================================================================ device side
+
+struct TileMap {
+    int n;
+    int start[MAXV + 1];  // prefix sums of tiles per view
+    int tiles_x[MAXV];
+};
+
+__device__ __forceinline__ int find_view(const TileMap &tm, int tile)
+{
+    int v = 0;
+#pragma unroll 1
+    while (v + 1 < tm.n && tile >= tm.start[v + 1]) ++v;
+    return v;
+}
+
+// ---- K1: remap#1 (projection maps) + gain ------------------------------------------------------------
+struct Stage1View {
+    const float *xmap, *ymap;   // roi_w x roi_h, pitch map_pitch bytes
+    const uint8_t *lut;         // 256-entry gain table: sat_u8(rni(gain * v))
+    uint8_t *P;                 // frame 0
+    size_t map_pitch, p_pitch, p_frame_stride;
+    int w, h, src_w, src_h;
+};
+struct Stage1Params {
+    TileMap tm;
+    Stage1View v[MAXV];
+    const uint8_t *src[MAX_BATCH * MAXV];
+    size_t src_pitch;
+    int n_views;
+};
+
+constexpr int RM_BX = 32, RM_BY = 8, RM_PX = 4;  // 4 consecutive pixels per thread
+
+__global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage1(const __grid_constant__ Stage1Params p)
+{
+    const int vi = find_view(p.tm, blockIdx.x);
+    const Stage1View &V = p.v[vi];
+    const int t = blockIdx.x - p.tm.start[vi];
+    const int tx = t % p.tm.tiles_x[vi], ty = t / p.tm.tiles_x[vi];
+    const int x0 = (tx * RM_BX + threadIdx.x) * RM_PX, y = ty * RM_BY + threadIdx.y;
+    if (x0 >= V.w || y >= V.h) return;
+    const int f = blockIdx.y;
+    const uint8_t *src = p.src[f * p.n_views + vi];
+    const float *mx = (const float *)((const char *)V.xmap + (size_t)y * V.map_pitch) + x0;
+    const float *my = (const float *)((const char *)V.ymap + (size_t)y * V.map_pitch) + x0;
+    uint8_t *dst = V.P + (size_t)f * V.p_frame_stride + (size_t)y * V.p_pitch + (size_t)x0 * 3;
+    unsigned px[RM_PX];
+    const int n = min(RM_PX, V.w - x0);
+#pragma unroll
+    for (int i = 0; i < RM_PX; ++i) {
+        px[i] = 0;
+        if (i < n) {
+            const unsigned v = remap_px_u8c3(src, p.src_pitch, V.src_w, V.src_h, __ldg(mx + i), __ldg(my + i));
+            px[i] = (unsigned)__ldg(V.lut + (v & 0xff)) | ((unsigned)__ldg(V.lut + ((v >> 8) & 0xff)) << 8) |
+                    ((unsigned)__ldg(V.lut + ((v >> 16) & 0xff)) << 16);
+        }
+    }
+    if (n == RM_PX) {  // 12 bytes = three aligned 32-bit stores (p_pitch % 4 == 0, x0 % 4 == 0)
+        unsigned *d32 = (unsigned *)dst;
+        d32[0] = px[0] | (px[1] << 24);
+        d32[1] = (px[1] >> 8) | (px[2] << 16);
+        d32[2] = (px[2] >> 16) | (px[3] << 8);
+    } else {
+        for (int i = 0; i < n; ++i) { dst[3 * i] = px[i] & 0xff; dst[3 * i + 1] = (px[i] >> 8) & 0xff; dst[3 * i + 2] = (px[i] >> 16) & 0xff; }
+    }
+}
+
+// ---- K2: CPW-mesh remap#2 + REFLECT border + interleaved -> planar ------------------------------------
+struct Stage2View {
+    const uint8_t *P;
+    const float *xmesh, *ymesh;  // roi_w x roi_h (null when enable_local == 0)
+    uint8_t *G0;                 // planar 3 x (bw*bh), frame 0
+    size_t p_pitch, p_frame_stride, map_pitch, g0_frame_stride;
+    int w, h, bw, bh, top, left;
+};
+struct Stage2Params {
+    TileMap tm;
+    Stage2View v[MAXV];
+};
+
+__global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage2(const __grid_constant__ Stage2Params p)
+{
+    const int vi = find_view(p.tm, blockIdx.x);
+    const Stage2View &V = p.v[vi];
+    const int t = blockIdx.x - p.tm.start[vi];
+    const int tx = t % p.tm.tiles_x[vi], ty = t / p.tm.tiles_x[vi];
+    const int bx0 = (tx * RM_BX + threadIdx.x) * RM_PX, by = ty * RM_BY + threadIdx.y;
+    if (bx0 >= V.bw || by >= V.bh) return;  // bw % 4 == 0
+    const int f = blockIdx.y;
+    const uint8_t *P = V.P + (size_t)f * V.p_frame_stride;
+    const int y = reflect_idx(by - V.top, V.h);
+    unsigned c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+    for (int i = 0; i < RM_PX; ++i) {
+        const int x = reflect_idx(bx0 + i - V.left, V.w);
+        unsigned v;
+        if (V.xmesh) {
+            const float fx = __ldg((const float *)((const char *)V.xmesh + (size_t)y * V.map_pitch) + x);
+            const float fy = __ldg((const float *)((const char *)V.ymesh + (size_t)y * V.map_pitch) + x);
+            v = remap_px_u8c3(P, V.p_pitch, V.w, V.h, fx, fy);
+        } else {
+            const uint8_t *s = P + (size_t)y * V.p_pitch + (size_t)x * 3;
+            v = (unsigned)__ldg(s) | ((unsigned)__ldg(s + 1) << 8) | ((unsigned)__ldg(s + 2) << 16);
+        }
+        c0 |= (v & 0xff) << (8 * i);
+        c1 |= ((v >> 8) & 0xff) << (8 * i);
+        c2 |= ((v >> 16) & 0xff) << (8 * i);
+    }
+    const size_t plane = (size_t)V.bw * V.bh;
+    uint8_t *g = V.G0 + (size_t)f * V.g0_frame_stride + (size_t)by * V.bw + bx0;
+    *(unsigned *)g = c0;
+    *(unsigned *)(g + plane) = c1;
+    *(unsigned *)(g + 2 * plane) = c2;
+}
+
+// ---- K3: pyrDown on planes ----------------------------------------------------------------------------
+// out(y,x) = rhe( sum_{j,i} k5[j] k5[i] in(r101(2y+j-2), r101(2x+i-2)) / 256 ): the exact integer form of the
+// reference's fp32 vertical-then-horizontal 5-tap passes (every partial sum is exactly representable).
+struct PyrView {
+    const void *in;   // plane 0 of frame 0 (u8 when level 0, else s16)
+    int16_t *out;
+    size_t in_frame_stride, out_frame_stride;  // in elements
+    int w, h;                                  // input plane size
+};
+struct PyrParams {
+    TileMap tm;
+    PyrView v[MAXV];
+};
+
+constexpr int PD_TX = 32, PD_TY = 8;  // output tile per block (one thread per output sample)
+
+template <typename TIn>
+__global__ void __launch_bounds__(PD_TX *PD_TY) k_pyr_down(const __grid_constant__ PyrParams p)
+{
+    __shared__ int16_t tile[2 * PD_TY + 3][2 * PD_TX + 4];
+    const int vi = find_view(p.tm, blockIdx.x);
+    const PyrView &V = p.v[vi];
+    const int t = blockIdx.x - p.tm.start[vi];
+    const int tx = t % p.tm.tiles_x[vi], ty = t / p.tm.tiles_x[vi];
+    const int f = blockIdx.y, c = blockIdx.z;
+    const int w = V.w, h = V.h, ow = (w + 1) >> 1, oh = (h + 1) >> 1;
+    const TIn *in = (const TIn *)V.in + (size_t)f * V.in_frame_stride + (size_t)c * w * h;
+    const int ox0 = tx * PD_TX, oy0 = ty * PD_TY;
+    const int ix0 = 2 * ox0 - 2, iy0 = 2 * oy0 - 2;
+    const int tid = threadIdx.y * PD_TX + threadIdx.x;
+    for (int i = tid; i < (2 * PD_TY + 3) * (2 * PD_TX + 3); i += PD_TX * PD_TY) {
+        const int ly = i / (2 * PD_TX + 3), lx = i - ly * (2 * PD_TX + 3);
+        const int sy = r101_idx(iy0 + ly, h), sx = r101_idx(ix0 + lx, w);
+        tile[ly][lx] = (int16_t)in[(size_t)sy * w + sx];
+    }
+    __syncthreads();
+    const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
+    if (ox >= ow || oy >= oh) return;
+    int acc = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int16_t *r = &tile[2 * threadIdx.y + j][2 * threadIdx.x];
+        const int rs = r[0] + 4 * r[1] + 6 * r[2] + 4 * r[3] + r[4];
+        const int kj = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
+        acc += kj * rs;
+    }
+    V.out[(size_t)f * V.out_frame_stride + (size_t)c * ow * oh + (size_t)oy * ow + ox] = (int16_t)sat_s16(rhe_shift<8>(acc));
+}
+
+// ---- K4: fused Laplacian + weighted add + normalise + collapse + mask + crop ---------------------------
+struct BlendView {
+    const uint8_t *g0;       // level 0 planes (u8), frame 0
+    const int16_t *g[MAXL];  // level k >= 1 planes (s16), frame 0
+    const float *w[MAXL];    // static weight pyramid
+    size_t g0_frame_stride;
+    size_t g_frame_stride[MAXL];
+    int x_tl, y_tl, bw, bh;  // level-0 canvas rect origin and bordered size (multiples of 2^nb)
+};
+struct BlendPlan {
+    int n_views, nb;
+    int cw[MAXL], ch[MAXL];   // canvas (padded dst roi) size per level
+    const float *dw[MAXL];    // static sum of weights per level (accumulated in view order)
+    int out_w, out_h;         // dst_roi_final_
+    BlendView v[MAXV];
+};
+
+constexpr int BL_TW = 64, BL_TH = 32, BL_THREADS = 256;
+// region of level k needed by a BL_TW x BL_TH tile: r(k) = r(k-1)/2 + 3 (upper bound)
+constexpr int BL_R1W = BL_TW / 2 + 2, BL_R1H = BL_TH / 2 + 2;
+constexpr int BL_SMEM_ELEMS = BL_R1W * BL_R1H;  // largest stored region (level 1)
+
+// pyrUp (x4 gain folded) of one sample from a plane accessor
+template <typename Acc>
+__device__ __forceinline__ int pyr_up_sample(const Acc &a, int x, int y, int n_x, int n_y)
+{
+    const int ix = x >> 1, iy = y >> 1;
+    int acc;
+    if (((x | y) & 1) == 0) {
+        const int xm = up_idx(ix - 1, n_x), xc = ix, xp = up_idx(ix + 1, n_x);
+        const int ym = up_idx(iy - 1, n_y), yc = iy, yp = up_idx(iy + 1, n_y);
+        const int r0 = a(xm, ym) + 6 * a(xc, ym) + a(xp, ym);
+        const int r1 = a(xm, yc) + 6 * a(xc, yc) + a(xp, yc);
+        const int r2 = a(xm, yp) + 6 * a(xc, yp) + a(xp, yp);
+        acc = r0 + 6 * r1 + r2;
+    } else if ((y & 1) == 0) {  // x odd
+        const int xc = ix, xp = up_idx(ix + 1, n_x);
+        const int ym = up_idx(iy - 1, n_y), yc = iy, yp = up_idx(iy + 1, n_y);
+        acc = 4 * ((a(xc, ym) + a(xp, ym)) + 6 * (a(xc, yc) + a(xp, yc)) + (a(xc, yp) + a(xp, yp)));
+    } else if ((x & 1) == 0) {  // y odd
+        const int xm = up_idx(ix - 1, n_x), xc = ix, xp = up_idx(ix + 1, n_x);
+        const int yc = iy, yp = up_idx(iy + 1, n_y);
+        acc = 4 * ((a(xm, yc) + 6 * a(xc, yc) + a(xp, yc)) + (a(xm, yp) + 6 * a(xc, yp) + a(xp, yp)));
+    } else {
+        const int xc = ix, xp = up_idx(ix + 1, n_x);
+        const int yc = iy, yp = up_idx(iy + 1, n_y);
+        acc = 16 * (a(xc, yc) + a(xp, yc) + a(xc, yp) + a(xp, yp));
+    }
+    return sat_s16(rhe_shift<6>(acc));
+}
+
+struct GlobalS16Plane {
+    const int16_t *p;
+    int w;
+    __device__ __forceinline__ int operator()(int x, int y) const { return (int)__ldg(p + (size_t)y * w + x); }
+};
+struct SmemRegion {
+    const int16_t *p;
+    int x0, y0, w;
+    __device__ __forceinline__ int operator()(int x, int y) const { return (int)p[(y - y0) * w + (x - x0)]; }
+};
+
+struct OutPtrs { int16_t *out[MAX_BATCH]; };
+
+__global__ void __launch_bounds__(BL_THREADS) k_blend_collapse(const BlendPlan *__restrict__ plan, const __grid_constant__ OutPtrs outs, size_t out_pitch)
+{
+    __shared__ int16_t sD[2][3][BL_SMEM_ELEMS];
+    __shared__ BlendPlan P;
+    for (int i = threadIdx.x; i < (int)(sizeof(BlendPlan) / 4); i += BL_THREADS) ((int *)&P)[i] = ((const int *)plan)[i];
+    __syncthreads();
+    const int nb = P.nb, f = blockIdx.z;
+    int lo_x[MAXL], hi_x[MAXL], lo_y[MAXL], hi_y[MAXL];
+    lo_x[0] = blockIdx.x * BL_TW; hi_x[0] = min(lo_x[0] + BL_TW, P.cw[0]) - 1;
+    lo_y[0] = blockIdx.y * BL_TH; hi_y[0] = min(lo_y[0] + BL_TH, P.ch[0]) - 1;
+#pragma unroll
+    for (int k = 1; k < MAXL; ++k) {
+        if (k <= nb) {
+            lo_x[k] = max(0, (lo_x[k - 1] >> 1) - 1); hi_x[k] = min(P.cw[k] - 1, (hi_x[k - 1] >> 1) + 1);
+            lo_y[k] = max(0, (lo_y[k - 1] >> 1) - 1); hi_y[k] = min(P.ch[k] - 1, (hi_y[k - 1] >> 1) + 1);
+        }
+    }
+#pragma unroll 1
+    for (int k = nb; k >= 0; --k) {
+        const int rw = hi_x[k] - lo_x[k] + 1, rh = hi_y[k] - lo_y[k] + 1;
+        const int cwk = P.cw[k];
+        int16_t(*cur)[BL_SMEM_ELEMS] = sD[k & 1];
+        const int16_t(*prev)[BL_SMEM_ELEMS] = sD[(k + 1) & 1];
+#pragma unroll 1
+        for (int idx = threadIdx.x; idx < rw * rh; idx += BL_THREADS) {
+            const int ry = idx / rw, rx = idx - ry * rw;
+            const int px = lo_x[k] + rx, py = lo_y[k] + ry;
+            int a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 1
+            for (int vi = 0; vi < P.n_views; ++vi) {
+                const BlendView &V = P.v[vi];
+                const int bwk = V.bw >> k, bhk = V.bh >> k;
+                const int qx = px - (V.x_tl >> k), qy = py - (V.y_tl >> k);
+                if ((unsigned)qx >= (unsigned)bwk || (unsigned)qy >= (unsigned)bhk) continue;
+                const float wv = __ldg(V.w[k] + (size_t)qy * bwk + qx);
+                if (wv == 0.f) continue;  // (short)(L * 0) == 0 exactly: nothing to add
+                const size_t plane = (size_t)bwk * bhk;
+                int g[3];
+                if (k == 0) {
+                    const uint8_t *s = V.g0 + (size_t)f * V.g0_frame_stride + (size_t)qy * bwk + qx;
+                    g[0] = __ldg(s); g[1] = __ldg(s + plane); g[2] = __ldg(s + 2 * plane);
+                } else {
+                    const int16_t *s = V.g[k] + (size_t)f * V.g_frame_stride[k] + (size_t)qy * bwk + qx;
+                    g[0] = __ldg(s); g[1] = __ldg(s + plane); g[2] = __ldg(s + 2 * plane);
+                }
+                if (k < nb) {  // Laplacian: G_k - pyrUp(G_{k+1}), saturating
+                    const int nx = bwk >> 1, ny = bhk >> 1;
+                    const int16_t *up = V.g[k + 1] + (size_t)f * V.g_frame_stride[k + 1];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        GlobalS16Plane acc{up + (size_t)c * nx * ny, nx};
+                        g[c] = sat_s16(g[c] - pyr_up_sample(acc, qx, qy, nx, ny));
+                    }
+                }
+                a0 += rz_s16(__fmul_rn((float)g[0], wv));
+                a1 += rz_s16(__fmul_rn((float)g[1], wv));
+                a2 += rz_s16(__fmul_rn((float)g[2], wv));
+            }
+            // normalise (truncating) by the static weight sum
+            const float dwv = __ldg(P.dw[k] + (size_t)py * cwk + px);
+            const float den = __fadd_rn(dwv, 1e-5f);
+            int d[3] = {(int)(short)a0, (int)(short)a1, (int)(short)a2};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) d[c] = rz_s16(__fdiv_rn((float)d[c], den));
+            if (k < nb) {  // collapse: D_k += pyrUp(D_{k+1}), saturating
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    SmemRegion acc{prev[c], lo_x[k + 1], lo_y[k + 1], hi_x[k + 1] - lo_x[k + 1] + 1};
+                    d[c] = sat_s16(d[c] + pyr_up_sample(acc, px, py, P.cw[k + 1], P.ch[k + 1]));
+                }
+            }
+            if (k > 0) {
+                cur[0][idx] = (int16_t)d[0]; cur[1][idx] = (int16_t)d[1]; cur[2][idx] = (int16_t)d[2];
+            } else if (px < P.out_w && py < P.out_h) {
+                const bool m = dwv > 1e-5f;  // dst_mask = dst_band_weights_[0] > WEIGHT_EPS
+                int16_t *o = (int16_t *)((char *)outs.out[f] + (size_t)py * out_pitch) + (size_t)px * 3;
+                o[0] = m ? (int16_t)d[0] : (int16_t)0;
+                o[1] = m ? (int16_t)d[1] : (int16_t)0;
+                o[2] = m ? (int16_t)d[2] : (int16_t)0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- static setup kernels -------------------------------------------------------------------------------
+// weight level 0: copyMakeBorder(mask * (1/255), BORDER_CONSTANT 0) (sources/modules/stitching/src/blenders.cpp:410-421)
+__global__ void k_weight_level0(const uint8_t *__restrict__ mask, int mw, int mh, size_t mp, int top, int left, float *__restrict__ w0, int bw, int bh)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= bw || y >= bh) return;
+    const int sx = x - left, sy = y - top;
+    float v = 0.f;
+    if ((unsigned)sx < (unsigned)mw && (unsigned)sy < (unsigned)mh) v = __fmul_rn((float)(1. / 255.), (float)mask[(size_t)sy * mp + sx]);
+    w0[(size_t)y * bw + x] = v;
+}
+
+// dst_band_weights_[k](rc) += weight (the `dst_weight += w` half of addSrcWeightKernel32F), one view at a time
+__global__ void k_accum_weight(const float *__restrict__ w, int bw, int bh, float *dw, int cw, int x_tl, int y_tl)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= bw || y >= bh) return;
+    float *d = dw + (size_t)(y_tl + y) * cw + (x_tl + x);
+    *d = __fadd_rn(*d, w[(size_t)y * bw + x]);
+}
+
+// interleave / de-interleave helpers for vsb_debug_read
+__global__ void k_planar_to_interleaved_s16(const void *__restrict__ in, int is_u8, int w, int h, int16_t *__restrict__ out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const size_t plane = (size_t)w * h, o = (size_t)y * w + x;
+    for (int c = 0; c < 3; ++c)
+        out[o * 3 + c] = is_u8 ? (int16_t)((const uint8_t *)in)[c * plane + o] : ((const int16_t *)in)[c * plane + o];
+}
+
+// ---- CPW mesh -> backward map (360_stitcher/meshwarper.cpp:823-886) on the device ----------------------
+// m1+m2: forward-splat every pixel of the warped view into the half-resolution accumulators.  The sums are of
+// integer pixel coordinates (< 2^24) so fp32 atomics reproduce the CPU loop bit-exactly in any order.
+__global__ void k_mesh_splat(const float *__restrict__ mesh_x, const float *__restrict__ mesh_y, int mrows, int mcols,
+                             int W, int H, float *sum_x, float *sum_y, float *cnt)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float bx = custom_resize_at(mesh_x, mcols, mrows, (size_t)mcols * 4, W, H, x, y);
+    const float by = custom_resize_at(mesh_y, mcols, mrows, (size_t)mcols * 4, W, H, x, y);
+    if (!(fabsf(bx) < 2147483648.f) || !(fabsf(by) < 2147483648.f)) return;  // (int) of NaN / out of range fails the test below
+    const int x_ = (int)bx / 2, y_ = (int)by / 2;  // C cast (toward zero) then integer divide
+    const int hw = W / 2, hh = H / 2;
+    if (x_ >= 0 && y_ >= 0 && x_ < hw && y_ < hh) {
+        atomicAdd(sum_x + (size_t)y_ * hw + x_, (float)x);
+        atomicAdd(sum_y + (size_t)y_ * hw + x_, (float)y);
+        atomicAdd(cnt + (size_t)y_ * hw + x_, 1.f);
+    }
+}
+
+// m3: warp = sum / count (0/0 = NaN for empty cells, as in the reference)
+__global__ void k_mesh_divide(float *sum_x, float *sum_y, const float *__restrict__ cnt, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sum_x[i] = __fdiv_rn(sum_x[i], cnt[i]);
+    sum_y[i] = __fdiv_rn(sum_y[i], cnt[i]);
+}
+
+// m4: custom_resize of the half table back to W x H
+__global__ void k_mesh_upsample(const float *__restrict__ wx, const float *__restrict__ wy, int hw, int hh, int W, int H,
+                                float *mx, float *my, size_t pitch)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
+    if (u >= W || v >= H) return;
+    *((float *)((char *)mx + (size_t)v * pitch) + u) = custom_resize_at(wx, hw, hh, (size_t)hw * 4, W, H, u, v);
+    *((float *)((char *)my + (size_t)v * pitch) + u) = custom_resize_at(wy, hw, hh, (size_t)hw * 4, W, H, u, v);
+}
+
+// ============================================================================================ host side
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline dim3 grid2d(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }
+
+struct View {
+    bool inited = false, has_maps = false;
+    int roi_w = 0, roi_h = 0, tl_x = 0, tl_y = 0;
+    int top = 0, bottom = 0, left = 0, right = 0, x_tl = 0, y_tl = 0, x_br = 0, y_br = 0, bw = 0, bh = 0;
+    int src_w = 0, src_h = 0;
+    float gain = 1.f;
+    float *xmap = nullptr, *ymap = nullptr;
+    size_t map_pitch = 0;
+    float *mesh[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [buffer][x|y]
+    int mesh_cur = -1;                                              // buffer the compose path reads (-1: none yet)
+    int mesh_pending = -1;                                          // buffer published by vsb_set_mesh, not yet adopted
+    cudaEvent_t mesh_ready = nullptr;
+    float *mesh_scratch = nullptr;                                  // sum_x | sum_y | cnt (half res) + device copy of the vertex mesh
+    uint8_t *lut = nullptr;
+    float *weight[MAXL] = {};
+    uint8_t *P = nullptr;
+    size_t p_pitch = 0, p_frame_stride = 0;
+    uint8_t *G0 = nullptr;
+    size_t g0_frame_stride = 0;
+    int16_t *G[MAXL] = {};
+    size_t g_frame_stride[MAXL] = {};
+};
+
+}  // namespace vsb
+
+struct vsb_stitcher {
+    vsb_config cfg;
+    int device = 0;
+    bool prepared = false, finalized = false;
+    int nb = 0;
+    int roi_final[4] = {0, 0, 0, 0}, roi[4] = {0, 0, 0, 0};
+    int cw[vsb::MAXL] = {}, ch[vsb::MAXL] = {};
+    float *dw[vsb::MAXL] = {};
+    int views_inited = 0;
+    vsb::View v[vsb::MAXV];
+    vsb::BlendPlan *d_plan = nullptr;
+    cudaStream_t setup_stream = nullptr, mesh_stream = nullptr, io_stream = nullptr;
+    cudaEvent_t last_compose = nullptr;
+    bool last_compose_valid = false;
+    std::mutex mu;  // guards mesh publication
+    int launches = 0;
+    // vsb_feed / vsb_blend bookkeeping (frame slot 0)
+    // host-buffer path staging
+    uint8_t *stage_src = nullptr;
+    int16_t *stage_out = nullptr;
+    uint8_t *pin_src = nullptr;
+    int16_t *pin_out = nullptr;
+    size_t stage_src_pitch = 0, stage_src_frame = 0, stage_out_pitch = 0, stage_out_frame = 0;
+    int stage_src_w = 0, stage_src_h = 0;
+    int rig_projection = -1, rig_src_w = 0, rig_src_h = 0;
+    float rig_scale = 0.f;
+};
+
+namespace vsb {
+
+#define CK(expr) do { int _r = check_cuda((expr), #expr); if (_r != VSB_OK) return _r; } while (0)
+#define REQ(cond, code, ...) do { if (!(cond)) return fail((code), __VA_ARGS__); } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static void free_view(View &V)
+{
+    cudaFree(V.xmap); cudaFree(V.ymap);
+    for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) cudaFree(V.mesh[b][c]);
+    cudaFree(V.mesh_scratch); cudaFree(V.lut);
+    for (int k = 0; k < MAXL; ++k) { cudaFree(V.weight[k]); cudaFree(V.G[k]); }
+    cudaFree(V.P); cudaFree(V.G0);
+    if (V.mesh_ready) cudaEventDestroy(V.mesh_ready);
+    V = View();
+}
+
+static int upload_lut(vsb_stitcher *s, View &V)
+{
+    uint8_t lut[256];
+    for (int i = 0; i < 256; ++i) {
+        // sat_u8(rni(alpha * v)): Convertor, sources/modules/core/src/cuda/gpu_mat.cu:493-496 (host twin of cvt.rni.sat.u8.f32)
+        const float p = V.gain * (float)i;
+        float r = nearbyintf(p);
+        if (!(p == p)) r = 0.f;
+        lut[i] = (uint8_t)(r <= 0.f ? 0 : (r >= 255.f ? 255 : (int)r));
+    }
+    if (!V.lut) CK(cudaMalloc(&V.lut, 256));
+    CK(cudaMemcpyAsync(V.lut, lut, 256, cudaMemcpyHostToDevice, s->setup_stream));
+    CK(cudaStreamSynchronize(s->setup_stream));
+    return VSB_OK;
+}
+
+static int build_plan(vsb_stitcher *s)
+{
+    BlendPlan h;
+    std::memset(&h, 0, sizeof(h));
+    h.n_views = s->cfg.num_views; h.nb = s->nb;
+    h.out_w = s->roi_final[2]; h.out_h = s->roi_final[3];
+    for (int k = 0; k <= s->nb; ++k) { h.cw[k] = s->cw[k]; h.ch[k] = s->ch[k]; h.dw[k] = s->dw[k]; }
+    for (int i = 0; i < s->cfg.num_views; ++i) {
+        const View &V = s->v[i];
+        BlendView &B = h.v[i];
+        B.g0 = V.G0; B.g0_frame_stride = V.g0_frame_stride;
+        for (int k = 0; k <= s->nb; ++k) { B.g[k] = V.G[k]; B.w[k] = V.weight[k]; B.g_frame_stride[k] = V.g_frame_stride[k]; }
+        B.x_tl = V.x_tl; B.y_tl = V.y_tl; B.bw = V.bw; B.bh = V.bh;
+    }
+    if (!s->d_plan) CK(cudaMalloc(&s->d_plan, sizeof(BlendPlan)));
+    CK(cudaMemcpyAsync(s->d_plan, &h, sizeof(h), cudaMemcpyHostToDevice, s->setup_stream));
+    CK(cudaStreamSynchronize(s->setup_stream));
+    return VSB_OK;
+}
+
+// static weight sums, accumulated in view order like successive feed_online calls would
+static int finalize(vsb_stitcher *s)
+{
+    const dim3 b(32, 8);
+    for (int k = 0; k <= s->nb; ++k) CK(cudaMemsetAsync(s->dw[k], 0, sizeof(float) * s->cw[k] * s->ch[k], s->setup_stream));
+    for (int i = 0; i < s->cfg.num_views; ++i) {
+        const View &V = s->v[i];
+        for (int k = 0; k <= s->nb; ++k) {
+            const int bwk = V.bw >> k, bhk = V.bh >> k;
+            k_accum_weight<<<grid2d(bwk, bhk, b), b, 0, s->setup_stream>>>(V.weight[k], bwk, bhk, s->dw[k], s->cw[k], V.x_tl >> k, V.y_tl >> k);
+        }
+    }
+    int r = check_launch("k_accum_weight");
+    if (r != VSB_OK) return r;
+    r = build_plan(s);
+    if (r != VSB_OK) return r;
+    s->finalized = true;
+    return VSB_OK;
+}
+
+static int ready_for_frames(vsb_stitcher *s)
+{
+    REQ(s->finalized, VSB_ERR_STATE, "compose: prepare + init_view for every view must come first");
+    for (int i = 0; i < s->cfg.num_views; ++i) {
+        REQ(s->v[i].has_maps, VSB_ERR_STATE, "compose: view %d has no projection maps (vsb_set_maps)", i);
+        REQ(!s->cfg.enable_local || s->v[i].mesh_cur >= 0 || s->v[i].mesh_pending >= 0, VSB_ERR_STATE,
+            "compose: enable_local is set but view %d has no mesh (vsb_set_mesh)", i);
+    }
+    return VSB_OK;
+}
+
+// adopt meshes published by vsb_set_mesh: the compose stream waits for the builder's event, then flips buffers
+static int adopt_meshes(vsb_stitcher *s, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lk(s->mu);
+    for (int i = 0; i < s->cfg.num_views; ++i) {
+        View &V = s->v[i];
+        if (V.mesh_pending >= 0) {
+            CK(cudaStreamWaitEvent(st, V.mesh_ready, 0));
+            V.mesh_cur = V.mesh_pending;
+            V.mesh_pending = -1;
+        }
+    }
+    return VSB_OK;
+}
+
+static void fill_tilemap(TileMap &tm, int n, const int *w, const int *h, int tile_w, int tile_h)
+{
+    tm.n = n;
+    tm.start[0] = 0;
+    for (int i = 0; i < n; ++i) {
+        tm.tiles_x[i] = (w[i] + tile_w - 1) / tile_w;
+        tm.start[i + 1] = tm.start[i] + tm.tiles_x[i] * ((h[i] + tile_h - 1) / tile_h);
+    }
+}
+
+// remap stages + pyramid for views [v0, v1) of n_frames frames
+static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch, cudaStream_t st)
+{
+    const int n = v1 - v0;
+    int ws[MAXV], hs[MAXV];
+    {
+        Stage1Params p;
+        std::memset(&p, 0, sizeof(p));
+        for (int j = 0; j < n; ++j) {
+            const View &V = s->v[v0 + j];
+            Stage1View &S = p.v[j];
+            S.xmap = V.xmap; S.ymap = V.ymap; S.lut = V.lut; S.P = V.P;
+            S.map_pitch = V.map_pitch; S.p_pitch = V.p_pitch; S.p_frame_stride = V.p_frame_stride;
+            S.w = V.roi_w; S.h = V.roi_h; S.src_w = V.src_w; S.src_h = V.src_h;
+            ws[j] = V.roi_w; hs[j] = V.roi_h;
+        }
+        fill_tilemap(p.tm, n, ws, hs, RM_BX * RM_PX, RM_BY);
+        p.n_views = n; p.src_pitch = src_pitch;
+        for (int f = 0; f < n_frames; ++f) for (int j = 0; j < n; ++j) p.src[f * n + j] = d_srcs[f * n + j];
+        k_remap_stage1<<<dim3(p.tm.start[n], n_frames), dim3(RM_BX, RM_BY), 0, st>>>(p);
+        ++s->launches;
+    }
+    {
+        Stage2Params p;
+        std::memset(&p, 0, sizeof(p));
+        for (int j = 0; j < n; ++j) {
+            const View &V = s->v[v0 + j];
+            Stage2View &S = p.v[j];
+            S.P = V.P; S.G0 = V.G0;
+            if (s->cfg.enable_local) { S.xmesh = V.mesh[V.mesh_cur][0]; S.ymesh = V.mesh[V.mesh_cur][1]; }
+            S.p_pitch = V.p_pitch; S.p_frame_stride = V.p_frame_stride; S.map_pitch = V.map_pitch; S.g0_frame_stride = V.g0_frame_stride;
+            S.w = V.roi_w; S.h = V.roi_h; S.bw = V.bw; S.bh = V.bh; S.top = V.top; S.left = V.left;
+            ws[j] = V.bw; hs[j] = V.bh;
+        }
+        fill_tilemap(p.tm, n, ws, hs, RM_BX * RM_PX, RM_BY);
+        k_remap_stage2<<<dim3(p.tm.start[n], n_frames), dim3(RM_BX, RM_BY), 0, st>>>(p);
+        ++s->launches;
+    }
+    for (int k = 0; k < s->nb; ++k) {
+        PyrParams p;
+        std::memset(&p, 0, sizeof(p));
+        for (int j = 0; j < n; ++j) {
+            const View &V = s->v[v0 + j];
+            PyrView &S = p.v[j];
+            S.in = k == 0 ? (const void *)V.G0 : (const void *)V.G[k];
+            S.in_frame_stride = k == 0 ? V.g0_frame_stride : V.g_frame_stride[k];
+            S.out = V.G[k + 1]; S.out_frame_stride = V.g_frame_stride[k + 1];
+            S.w = V.bw >> k; S.h = V.bh >> k;
+            ws[j] = (S.w + 1) / 2; hs[j] = (S.h + 1) / 2;
+        }
+        fill_tilemap(p.tm, n, ws, hs, PD_TX, PD_TY);
+        const dim3 g(p.tm.start[n], n_frames, 3);
+        if (k == 0) k_pyr_down<uint8_t><<<g, dim3(PD_TX, PD_TY), 0, st>>>(p);
+        else k_pyr_down<int16_t><<<g, dim3(PD_TX, PD_TY), 0, st>>>(p);
+        ++s->launches;
+    }
+    return check_launch("front half (remap + pyramid)");
+}
+
+static int launch_back(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, size_t out_pitch, cudaStream_t st)
+{
+    OutPtrs o;
+    std::memset(&o, 0, sizeof(o));
+    for (int f = 0; f < n_frames; ++f) o.out[f] = d_outs[f];
+    const dim3 g((s->cw[0] + BL_TW - 1) / BL_TW, (s->ch[0] + BL_TH - 1) / BL_TH, n_frames);
+    k_blend_collapse<<<g, BL_THREADS, 0, st>>>(s->d_plan, o, out_pitch);
+    ++s->launches;
+    return check_launch("k_blend_collapse");
+}
+
+static int note_compose_done(vsb_stitcher *s, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lk(s->mu);
+    CK(cudaEventRecord(s->last_compose, st));
+    s->last_compose_valid = true;
+    return VSB_OK;
+}
+
+}  // namespace vsb
+
+using namespace vsb;
+
+extern "C" {
+
+int vsb_create(const vsb_config *cfg, vsb_stitcher **out)
+{
+    REQ(cfg && out, VSB_ERR_INVALID, "create: null argument");
+    REQ(cfg->num_views >= 1 && cfg->num_views <= VSB_MAX_VIEWS, VSB_ERR_INVALID, "create: num_views must be 1..%d", VSB_MAX_VIEWS);
+    REQ(cfg->num_bands >= 0 && cfg->num_bands <= VSB_MAX_BANDS, VSB_ERR_INVALID, "create: num_bands must be 0..%d", VSB_MAX_BANDS);
+    REQ(cfg->max_batch >= 1 && cfg->max_batch <= MAX_BATCH, VSB_ERR_INVALID, "create: max_batch must be 1..%d", MAX_BATCH);
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    REQ(ndev > 0, VSB_ERR_CUDA, "create: no CUDA device (this path has no CPU fallback)");
+    int dev = cfg->device;
+    if (dev < 0) CK(cudaGetDevice(&dev));
+    REQ(dev < ndev, VSB_ERR_INVALID, "create: device %d out of range", dev);
+    vsb_stitcher *s = new (std::nothrow) vsb_stitcher();
+    REQ(s, VSB_ERR_NOMEM, "create: out of host memory");
+    s->cfg = *cfg;
+    s->device = dev;
+    DeviceGuard g(dev);
+    cudaError_t e = cudaStreamCreateWithFlags(&s->setup_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->mesh_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->io_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->last_compose, cudaEventDisableTiming);
+    if (e != cudaSuccess) { vsb_destroy(s); return check_cuda(e, "create: streams"); }
+    *out = s;
+    return VSB_OK;
+}
+
+int vsb_destroy(vsb_stitcher *s)
+{
+    if (!s) return VSB_OK;
+    DeviceGuard g(s->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < MAXV; ++i) free_view(s->v[i]);
+    for (int k = 0; k < MAXL; ++k) cudaFree(s->dw[k]);
+    cudaFree(s->d_plan);
+    cudaFree(s->stage_src); cudaFree(s->stage_out);
+    cudaFreeHost(s->pin_src); cudaFreeHost(s->pin_out);
+    if (s->setup_stream) cudaStreamDestroy(s->setup_stream);
+    if (s->mesh_stream) cudaStreamDestroy(s->mesh_stream);
+    if (s->io_stream) cudaStreamDestroy(s->io_stream);
+    if (s->last_compose) cudaEventDestroy(s->last_compose);
+    cudaGetLastError();
+    delete s;
+    return VSB_OK;
+}
+
+// Blender::prepare(corners, sizes) -> resultRoi (sources/modules/stitching/src/util.cpp:125-138) ->
+// MultiBandBlender::prepare(Rect) (sources/modules/stitching/src/blenders.cpp:237-274)
+int vsb_prepare(vsb_stitcher *s, const int *corners_xy, const int *sizes_wh)
+{
+    REQ(s && corners_xy && sizes_wh, VSB_ERR_INVALID, "prepare: null argument");
+    DeviceGuard g(s->device);
+    const int n = s->cfg.num_views;
+    int tlx = INT32_MAX, tly = INT32_MAX, brx = INT32_MIN, bry = INT32_MIN;
+    for (int i = 0; i < n; ++i) {
+        REQ(sizes_wh[2 * i] > 0 && sizes_wh[2 * i + 1] > 0, VSB_ERR_INVALID, "prepare: view %d has an empty size", i);
+        tlx = std::min(tlx, corners_xy[2 * i]); tly = std::min(tly, corners_xy[2 * i + 1]);
+        brx = std::max(brx, corners_xy[2 * i] + sizes_wh[2 * i]); bry = std::max(bry, corners_xy[2 * i + 1] + sizes_wh[2 * i + 1]);
+    }
+    int W = brx - tlx, H = bry - tly;
+    s->roi_final[0] = tlx; s->roi_final[1] = tly; s->roi_final[2] = W; s->roi_final[3] = H;
+    const double max_len = (double)std::max(W, H);
+    s->nb = std::min(s->cfg.num_bands, (int)std::ceil(std::log(max_len) / std::log(2.0)));
+    const int m = 1 << s->nb;
+    W += (m - W % m) % m; H += (m - H % m) % m;
+    s->roi[0] = tlx; s->roi[1] = tly; s->roi[2] = W; s->roi[3] = H;
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < MAXV; ++i) free_view(s->v[i]);
+    for (int k = 0; k < MAXL; ++k) { cudaFree(s->dw[k]); s->dw[k] = nullptr; }
+    for (int k = 0; k <= s->nb; ++k) {
+        s->cw[k] = k == 0 ? W : (s->cw[k - 1] + 1) / 2;
+        s->ch[k] = k == 0 ? H : (s->ch[k - 1] + 1) / 2;
+        CK(cudaMalloc(&s->dw[k], sizeof(float) * s->cw[k] * s->ch[k]));
+    }
+    s->views_inited = 0; s->prepared = true; s->finalized = false;
+    return VSB_OK;
+}
+
+int vsb_get_roi(const vsb_stitcher *s, int roi_final[4], int roi_padded[4], int *num_bands)
+{
+    REQ(s && s->prepared, VSB_ERR_STATE, "get_roi: call vsb_prepare first");
+    if (roi_final) std::memcpy(roi_final, s->roi_final, sizeof(int) * 4);
+    if (roi_padded) std::memcpy(roi_padded, s->roi, sizeof(int) * 4);
+    if (num_bands) *num_bands = s->nb;
+    return VSB_OK;
+}
+
+// MultiBandBlender::init_gpu (sources/modules/stitching/src/blenders.cpp:344-434)
+int vsb_init_view(vsb_stitcher *s, int i, const uint8_t *mask, int mw, int mh, size_t pitch, int tl_x, int tl_y, int on_device)
+{
+    REQ(s && mask, VSB_ERR_INVALID, "init_view: null argument");
+    REQ(s->prepared, VSB_ERR_STATE, "init_view: call vsb_prepare first");
+    REQ(i == s->views_inited && i < s->cfg.num_views, VSB_ERR_INVALID, "init_view: views must be initialised in order (expected %d, got %d)", s->views_inited, i);
+    REQ(mw > 0 && mh > 0 && pitch >= (size_t)mw, VSB_ERR_INVALID, "init_view: bad mask size");
+    DeviceGuard g(s->device);
+    View &V = s->v[i];
+    const int nb = s->nb, m = 1 << nb;
+    const int rx = s->roi[0], ry = s->roi[1], rbx = s->roi[0] + s->roi[2], rby = s->roi[1] + s->roi[3];
+    const int gap = 3 * m;
+    int tnx = std::max(rx, tl_x - gap), tny = std::max(ry, tl_y - gap);
+    int bnx = std::min(rbx, tl_x + mw + gap), bny = std::min(rby, tl_y + mh + gap);
+    tnx = rx + (((tnx - rx) >> nb) << nb);
+    tny = ry + (((tny - ry) >> nb) << nb);
+    int width = bnx - tnx, height = bny - tny;
+    width += (m - width % m) % m;
+    height += (m - height % m) % m;
+    bnx = tnx + width; bny = tny + height;
+    const int dy = std::max(bny - rby, 0), dx = std::max(bnx - rbx, 0);
+    tnx -= dx; bnx -= dx; tny -= dy; bny -= dy;
+    V.top = tl_y - tny; V.left = tl_x - tnx; V.bottom = bny - tl_y - mh; V.right = bnx - tl_x - mw;
+    REQ(V.top >= 0 && V.left >= 0 && V.bottom >= 0 && V.right >= 0, VSB_ERR_INVALID, "init_view: view %d lies outside the prepared roi", i);
+    V.y_tl = tny - ry; V.y_br = bny - ry; V.x_tl = tnx - rx; V.x_br = bnx - rx;
+    V.bw = width; V.bh = height; V.roi_w = mw; V.roi_h = mh; V.tl_x = tl_x; V.tl_y = tl_y;
+
+    // static weight pyramid
+    uint8_t *d_mask = nullptr;
+    size_t d_pitch = pitch;
+    if (!on_device) {
+        CK(cudaMalloc(&d_mask, (size_t)mw * mh));
+        CK(cudaMemcpy2D(d_mask, mw, mask, pitch, mw, mh, cudaMemcpyHostToDevice));
+        d_pitch = mw;
+    }
+    const dim3 b(32, 8);
+    CK(cudaMalloc(&V.weight[0], sizeof(float) * width * height));
+    k_weight_level0<<<grid2d(width, height, b), b, 0, s->setup_stream>>>(on_device ? mask : d_mask, mw, mh, d_pitch, V.top, V.left, V.weight[0], width, height);
+    for (int k = 0; k < nb; ++k) {
+        const int w = width >> k, h = height >> k;
+        CK(cudaMalloc(&V.weight[k + 1], sizeof(float) * (w / 2) * (h / 2)));
+        int r = vsb_pyr_down_f32(V.weight[k], w, h, (size_t)w * 4, V.weight[k + 1], (size_t)(w / 2) * 4, s->setup_stream);
+        if (r != VSB_OK) return r;
+    }
+    CK(cudaStreamSynchronize(s->setup_stream));
+    cudaFree(d_mask);
+    int r = check_launch("init_view weights");
+    if (r != VSB_OK) return r;
+
+    // per-frame buffers of this view
+    const int F = s->cfg.max_batch;
+    V.p_pitch = align_up((size_t)mw * 3, 16);
+    V.p_frame_stride = V.p_pitch * mh;
+    CK(cudaMalloc(&V.P, V.p_frame_stride * F));
+    V.g0_frame_stride = (size_t)3 * width * height;
+    CK(cudaMalloc(&V.G0, V.g0_frame_stride * F));
+    for (int k = 1; k <= nb; ++k) {
+        V.g_frame_stride[k] = (size_t)3 * (width >> k) * (height >> k);
+        CK(cudaMalloc(&V.G[k], sizeof(int16_t) * V.g_frame_stride[k] * F));
+    }
+    V.map_pitch = align_up((size_t)mw * 4, 16);
+    CK(cudaEventCreateWithFlags(&V.mesh_ready, cudaEventDisableTiming));
+    r = upload_lut(s, V);
+    if (r != VSB_OK) return r;
+    V.inited = true;
+    s->views_inited++;
+    if (s->views_inited == s->cfg.num_views) return finalize(s);
+    return VSB_OK;
+}
+
+int vsb_get_view_geometry(const vsb_stitcher *s, int i, int out8[8])
+{
+    REQ(s && out8 && i >= 0 && i < s->cfg.num_views && s->v[i].inited, VSB_ERR_INVALID, "get_view_geometry: view not initialised");
+    const View &V = s->v[i];
+    const int g[8] = {V.top, V.bottom, V.left, V.right, V.x_tl, V.y_tl, V.x_br, V.y_br};
+    std::memcpy(out8, g, sizeof(g));
+    return VSB_OK;
+}
+
+int vsb_set_maps(vsb_stitcher *s, int i, const float *xmap, const float *ymap, int w, int h, size_t pitch, int on_device, int src_w, int src_h)
+{
+    REQ(s && xmap && ymap, VSB_ERR_INVALID, "set_maps: null argument");
+    REQ(i >= 0 && i < s->cfg.num_views && s->v[i].inited, VSB_ERR_STATE, "set_maps: view %d is not initialised", i);
+    View &V = s->v[i];
+    REQ(w == V.roi_w && h == V.roi_h, VSB_ERR_INVALID, "set_maps: maps are %dx%d but the view's mask is %dx%d", w, h, V.roi_w, V.roi_h);
+    REQ(src_w > 0 && src_h > 0 && pitch >= (size_t)w * 4, VSB_ERR_INVALID, "set_maps: bad sizes");
+    DeviceGuard g(s->device);
+    CK(cudaDeviceSynchronize());
+    if (!V.xmap) { CK(cudaMalloc(&V.xmap, V.map_pitch * h)); CK(cudaMalloc(&V.ymap, V.map_pitch * h)); }
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CK(cudaMemcpy2D(V.xmap, V.map_pitch, xmap, pitch, (size_t)w * 4, h, kind));
+    CK(cudaMemcpy2D(V.ymap, V.map_pitch, ymap, pitch, (size_t)w * 4, h, kind));
+    V.src_w = src_w; V.src_h = src_h; V.has_maps = true;
+    return VSB_OK;
+}
+
+int vsb_set_gain(vsb_stitcher *s, int i, float gain)
+{
+    REQ(s && i >= 0 && i < s->cfg.num_views && s->v[i].inited, VSB_ERR_STATE, "set_gain: view %d is not initialised", i);
+    DeviceGuard g(s->device);
+    CK(cudaDeviceSynchronize());
+    s->v[i].gain = gain;
+    return upload_lut(s, s->v[i]);
+}
+
+// MeshWarper::convertMeshesToMap for one view (360_stitcher/meshwarper.cpp:823-886), entirely on the device
+int vsb_set_mesh(vsb_stitcher *s, int i, const float *mesh_x, const float *mesh_y, int rows, int cols)
+{
+    REQ(s && mesh_x && mesh_y, VSB_ERR_INVALID, "set_mesh: null argument");
+    REQ(i >= 0 && i < s->cfg.num_views && s->v[i].inited, VSB_ERR_STATE, "set_mesh: view %d is not initialised", i);
+    REQ(rows >= 2 && cols >= 2 && rows * cols <= 4096, VSB_ERR_INVALID, "set_mesh: mesh must be between 2x2 and 4096 vertices");
+    DeviceGuard g(s->device);
+    View &V = s->v[i];
+    const int W = V.roi_w, H = V.roi_h, hw = W / 2, hh = H / 2;
+    REQ(hw >= 2 && hh >= 2, VSB_ERR_INVALID, "set_mesh: view too small");
+    cudaStream_t st = s->mesh_stream;
+    int target;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        // write into the buffer the compose path is NOT reading; if a previous publication was never adopted, reuse it
+        target = V.mesh_pending >= 0 ? V.mesh_pending : (V.mesh_cur < 0 ? 0 : 1 - V.mesh_cur);
+        V.mesh_pending = -1;
+        // frames already submitted may still read `target` (it was `cur` two publications ago): order after them
+        if (s->last_compose_valid) CK(cudaStreamWaitEvent(st, s->last_compose, 0));
+    }
+    const size_t half = (size_t)hw * hh;
+    if (!V.mesh_scratch) CK(cudaMalloc(&V.mesh_scratch, sizeof(float) * (3 * half + 2 * 4096)));
+    for (int c = 0; c < 2; ++c)
+        if (!V.mesh[target][c]) CK(cudaMalloc(&V.mesh[target][c], V.map_pitch * H));
+    float *sum_x = V.mesh_scratch, *sum_y = sum_x + half, *cnt = sum_y + half, *d_mx = cnt + half, *d_my = d_mx + 4096;
+    CK(cudaMemcpyAsync(d_mx, mesh_x, sizeof(float) * rows * cols, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_my, mesh_y, sizeof(float) * rows * cols, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(sum_x, 0, sizeof(float) * 3 * half, st));
+    const dim3 b(32, 8);
+    k_mesh_splat<<<grid2d(W, H, b), b, 0, st>>>(d_mx, d_my, rows, cols, W, H, sum_x, sum_y, cnt);
+    k_mesh_divide<<<(unsigned)((half + 255) / 256), 256, 0, st>>>(sum_x, sum_y, cnt, (int)half);
+    k_mesh_upsample<<<grid2d(W, H, b), b, 0, st>>>(sum_x, sum_y, hw, hh, W, H, V.mesh[target][0], V.mesh[target][1], V.map_pitch);
+    int r = check_launch("set_mesh kernels");
+    if (r != VSB_OK) return r;
+    CK(cudaEventRecord(V.mesh_ready, st));
+    CK(cudaStreamSynchronize(st));  // host mesh arrays may be reused by the caller after return (pageable H2D)
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        V.mesh_pending = target;
+    }
+    return VSB_OK;
+}
+
+int vsb_feed(vsb_stitcher *s, int i, const uint8_t *d_bgr, size_t pitch, void *stream)
+{
+    REQ(s && d_bgr, VSB_ERR_INVALID, "feed: null argument");
+    REQ(i >= 0 && i < s->cfg.num_views, VSB_ERR_INVALID, "feed: view index out of range");
+    int r = ready_for_frames(s);
+    if (r != VSB_OK) return r;
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (i == 0) s->launches = 0;
+    r = adopt_meshes(s, st);
+    if (r != VSB_OK) return r;
+    const uint8_t *srcs[1] = {d_bgr};
+    return launch_front(s, i, i + 1, 1, srcs, pitch, st);
+}
+
+int vsb_blend(vsb_stitcher *s, int16_t *d_out, size_t out_pitch, void *stream)
+{
+    REQ(s && d_out, VSB_ERR_INVALID, "blend: null argument");
+    int r = ready_for_frames(s);
+    if (r != VSB_OK) return r;
+    DeviceGuard g(s->device);
+    int16_t *outs[1] = {d_out};
+    r = launch_back(s, 1, outs, out_pitch, (cudaStream_t)stream);
+    if (r != VSB_OK) return r;
+    return note_compose_done(s, (cudaStream_t)stream);
+}
+
+int vsb_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch, int16_t *const *d_outs, size_t out_pitch, void *stream)
+{
+    REQ(s && d_srcs && d_outs, VSB_ERR_INVALID, "compose: null argument");
+    REQ(n_frames >= 1 && n_frames <= s->cfg.max_batch, VSB_ERR_INVALID, "compose: n_frames must be 1..max_batch (%d)", s->cfg.max_batch);
+    int r = ready_for_frames(s);
+    if (r != VSB_OK) return r;
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    s->launches = 0;
+    r = adopt_meshes(s, st);
+    if (r != VSB_OK) return r;
+    r = launch_front(s, 0, s->cfg.num_views, n_frames, d_srcs, src_pitch, st);
+    if (r != VSB_OK) return r;
+    r = launch_back(s, n_frames, d_outs, out_pitch, st);
+    if (r != VSB_OK) return r;
+    return note_compose_done(s, st);
+}
+
+int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs, size_t src_pitch, int16_t *const *h_outs, size_t out_pitch)
+{
+    REQ(s && h_srcs && h_outs, VSB_ERR_INVALID, "compose_host: null argument");
+    REQ(n_frames >= 1 && n_frames <= s->cfg.max_batch, VSB_ERR_INVALID, "compose_host: n_frames must be 1..max_batch (%d)", s->cfg.max_batch);
+    int r = ready_for_frames(s);
+    if (r != VSB_OK) return r;
+    DeviceGuard g(s->device);
+    const int n = s->cfg.num_views, F = s->cfg.max_batch;
+    const int sw = s->v[0].src_w, sh = s->v[0].src_h;
+    for (int i = 1; i < n; ++i) REQ(s->v[i].src_w == sw && s->v[i].src_h == sh, VSB_ERR_INVALID, "compose_host: all views must share one source size");
+    REQ(src_pitch >= (size_t)sw * 3 && out_pitch >= (size_t)s->roi_final[2] * 6, VSB_ERR_INVALID, "compose_host: pitch too small");
+    if (!s->stage_src) {
+        s->stage_src_pitch = align_up((size_t)sw * 3, 256);
+        s->stage_src_frame = s->stage_src_pitch * sh;
+        s->stage_out_pitch = align_up((size_t)s->roi_final[2] * 6, 256);
+        s->stage_out_frame = s->stage_out_pitch * s->roi_final[3];
+        CK(cudaMalloc(&s->stage_src, s->stage_src_frame * n * F));
+        CK(cudaMalloc(&s->stage_out, s->stage_out_frame * F));
+    }
+    cudaStream_t st = s->io_stream;
+    const uint8_t *d_srcs[MAX_BATCH * MAXV];
+    int16_t *d_outs[MAX_BATCH];
+    for (int f = 0; f < n_frames; ++f) {
+        for (int i = 0; i < n; ++i) {
+            uint8_t *d = s->stage_src + s->stage_src_frame * (size_t)(f * n + i);
+            CK(cudaMemcpy2DAsync(d, s->stage_src_pitch, h_srcs[f * n + i], src_pitch, (size_t)sw * 3, sh, cudaMemcpyHostToDevice, st));
+            d_srcs[f * n + i] = d;
+        }
+        d_outs[f] = (int16_t *)((char *)s->stage_out + s->stage_out_frame * f);
+    }
+    r = vsb_compose(s, n_frames, d_srcs, s->stage_src_pitch, d_outs, s->stage_out_pitch, st);
+    if (r != VSB_OK) return r;
+    for (int f = 0; f < n_frames; ++f)
+        CK(cudaMemcpy2DAsync(h_outs[f], out_pitch, d_outs[f], s->stage_out_pitch, (size_t)s->roi_final[2] * 6, s->roi_final[3], cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return VSB_OK;
+}
+
+int vsb_last_launch_count(const vsb_stitcher *s) { return s ? s->launches : 0; }
+
+int vsb_get_config(const vsb_stitcher *s, vsb_config *out)
+{
+    REQ(s && out, VSB_ERR_INVALID, "get_config: null argument");
+    *out = s->cfg;
+    return VSB_OK;
+}
+
+int vsb_note_rig(vsb_stitcher *s, int projection, float scale, int src_w, int src_h)
+{
+    s->rig_projection = projection; s->rig_scale = scale; s->rig_src_w = src_w; s->rig_src_h = src_h;
+    return VSB_OK;
+}
+
+int vsb_rig_info_get(const vsb_stitcher *s, vsb_rig_info *out)
+{
+    REQ(s && out, VSB_ERR_INVALID, "rig_info: null argument");
+    REQ(s->finalized, VSB_ERR_STATE, "rig_info: not calibrated");
+    std::memset(out, 0, sizeof(*out));
+    out->projection = s->rig_projection; out->scale = s->rig_scale; out->src_w = s->rig_src_w; out->src_h = s->rig_src_h;
+    out->num_views = s->cfg.num_views; out->num_bands = s->nb;
+    std::memcpy(out->roi_final, s->roi_final, sizeof(int) * 4);
+    std::memcpy(out->roi_padded, s->roi, sizeof(int) * 4);
+    for (int i = 0; i < s->cfg.num_views; ++i) {
+        out->view_roi[i][0] = s->v[i].tl_x; out->view_roi[i][1] = s->v[i].tl_y;
+        out->view_roi[i][2] = s->v[i].roi_w; out->view_roi[i][3] = s->v[i].roi_h;
+    }
+    return VSB_OK;
+}
+
+int vsb_debug_read(vsb_stitcher *s, int what, int view, int level, int frame, void *h_dst, size_t bytes)
+{
+    REQ(s && h_dst, VSB_ERR_INVALID, "debug_read: null argument");
+    REQ(s->finalized, VSB_ERR_STATE, "debug_read: not calibrated");
+    REQ(frame >= 0 && frame < s->cfg.max_batch && level >= 0 && level <= s->nb, VSB_ERR_INVALID, "debug_read: bad frame/level");
+    REQ(what == 3 || (view >= 0 && view < s->cfg.num_views), VSB_ERR_INVALID, "debug_read: bad view");
+    DeviceGuard g(s->device);
+    CK(cudaDeviceSynchronize());
+    const View &V = s->v[what == 3 ? 0 : view];
+    switch (what) {
+    case 0: {  // warped view (after remap #2): crop of G0 planes -> interleaved u8
+        REQ(bytes == (size_t)V.roi_w * V.roi_h * 3, VSB_ERR_INVALID, "debug_read: size mismatch");
+        std::vector<uint8_t> tmp(V.g0_frame_stride);
+        CK(cudaMemcpy(tmp.data(), V.G0 + V.g0_frame_stride * frame, tmp.size(), cudaMemcpyDeviceToHost));
+        uint8_t *o = (uint8_t *)h_dst;
+        const size_t plane = (size_t)V.bw * V.bh;
+        for (int y = 0; y < V.roi_h; ++y)
+            for (int x = 0; x < V.roi_w; ++x)
+                for (int c = 0; c < 3; ++c) o[((size_t)y * V.roi_w + x) * 3 + c] = tmp[c * plane + (size_t)(y + V.top) * V.bw + (x + V.left)];
+        return VSB_OK;
+    }
+    case 1: {
+        const int w = V.bw >> level, h = V.bh >> level;
+        REQ(bytes == (size_t)w * h * 6, VSB_ERR_INVALID, "debug_read: size mismatch");
+        int16_t *d_tmp = nullptr;
+        CK(cudaMalloc(&d_tmp, bytes));
+        const void *in = level == 0 ? (const void *)(V.G0 + V.g0_frame_stride * frame) : (const void *)(V.G[level] + V.g_frame_stride[level] * frame);
+        const dim3 b(32, 8);
+        k_planar_to_interleaved_s16<<<grid2d(w, h, b), b>>>(in, level == 0, w, h, d_tmp);
+        cudaError_t e = cudaMemcpy(h_dst, d_tmp, bytes, cudaMemcpyDeviceToHost);
+        cudaFree(d_tmp);
+        return check_cuda(e, "debug_read level");
+    }
+    case 2: {
+        const int w = V.bw >> level, h = V.bh >> level;
+        REQ(bytes == (size_t)w * h * 4, VSB_ERR_INVALID, "debug_read: size mismatch");
+        return check_cuda(cudaMemcpy(h_dst, V.weight[level], bytes, cudaMemcpyDeviceToHost), "debug_read weight");
+    }
+    case 3:
+        REQ(bytes == (size_t)s->cw[level] * s->ch[level] * 4, VSB_ERR_INVALID, "debug_read: size mismatch");
+        return check_cuda(cudaMemcpy(h_dst, s->dw[level], bytes, cudaMemcpyDeviceToHost), "debug_read dw");
+    case 4:
+    case 5: {
+        int buf;
+        { std::lock_guard<std::mutex> lk(s->mu); buf = V.mesh_pending >= 0 ? V.mesh_pending : V.mesh_cur; }
+        REQ(buf >= 0, VSB_ERR_STATE, "debug_read: no mesh set");
+        REQ(bytes == (size_t)V.roi_w * V.roi_h * 4, VSB_ERR_INVALID, "debug_read: size mismatch");
+        return check_cuda(cudaMemcpy2D(h_dst, (size_t)V.roi_w * 4, V.mesh[buf][what - 4], V.map_pitch, (size_t)V.roi_w * 4, V.roi_h, cudaMemcpyDeviceToHost), "debug_read mesh");
+    }
+    default:
+        return fail(VSB_ERR_INVALID, "debug_read: unknown selector %d", what);
+    }
+}
+
+}  // extern "C"
