@@ -32,6 +32,7 @@ extern "C" {
 
 #define VSB_MAX_VIEWS 16
 #define VSB_MAX_BANDS 7
+#define VSB_MAX_STAGES 16
 
 enum { VSB_PROJ_SPHERICAL = 0, VSB_PROJ_CYLINDRICAL = 1 };
 
@@ -119,6 +120,13 @@ int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs
                      int16_t *const *h_outs, size_t out_pitch_bytes);
 /* number of kernels the last vsb_compose / vsb_feed+vsb_blend submission launched */
 int vsb_last_launch_count(const vsb_stitcher *s);
+
+/* ---- measurement: with profiling on, CUDA events bracket every kernel of a submission on the caller's stream
+ *      (the reference keeps std::chrono stamps per stage in times[5], A/timed.cpp:43-44,61-63).  vsb_get_profile
+ *      returns, for the last submission, each kernel's name, its device time and its ALGORITHMIC bytes (its own
+ *      compulsory input + output, static tables excluded). ------------------------------- */
+int vsb_set_profiling(vsb_stitcher *s, int on);
+int vsb_get_profile(vsb_stitcher *s, int max_stages, int *n_stages, const char **names, float *ms, double *bytes);
 
 /* ---- B7: device-launcher layer (the .cpp -> .cu seam inside the reference's OpenCV), one primitive per
  *      reference kernel, interleaved OpenCV layouts, pitches in bytes ---------------------------------- */

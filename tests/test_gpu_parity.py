@@ -63,9 +63,10 @@ def test_border_gain_resize_weighted_add_match_oracle(cuda, og, vsb):
     rng = np.random.default_rng(3)
     L = vsb.lib(); vp = vsb._vp; sz = vsb.C.c_size_t
     img = rng.integers(0, 256, (50, 70, 3), dtype=np.uint8)
+    d_img = dev(img)
     for (t, b, l, r) in [(0, 13, 127, 97), (5, 0, 0, 1), (60, 3, 80, 2)]:
         d = cuda.zeros((50 + t + b, 70 + l + r, 3), dtype=cuda.int16, device="cuda")
-        vsb.check(L.vsb_border_reflect_u8c3_to_s16c3(vp(dev(img).data_ptr()), 70, 50, sz(210), t, b, l, r, vp(d.data_ptr()), sz((70 + l + r) * 6), vp(stream())))
+        vsb.check(L.vsb_border_reflect_u8c3_to_s16c3(vp(d_img.data_ptr()), 70, 50, sz(210), t, b, l, r, vp(d.data_ptr()), sz((70 + l + r) * 6), vp(stream())))
         _eq(host(d), og.border_reflect_u8c3_to_s16(img, t, b, l, r), "copyMakeBorder REFLECT")
     for g in (0.97, 1.0, 1.03, 1.7):
         d = dev(img)
@@ -73,7 +74,8 @@ def test_border_gain_resize_weighted_add_match_oracle(cuda, og, vsb):
         _eq(host(d), og.gain_u8(img, np.float32(g)), "gain")
     m = rng.random((10, 10)).astype(np.float32) * 100
     d = cuda.zeros((627, 961), dtype=cuda.float32, device="cuda")
-    vsb.check(L.vsb_custom_resize(vp(dev(m).data_ptr()), 10, 10, sz(40), vp(d.data_ptr()), 961, 627, sz(961 * 4), vp(stream())))
+    d_m = dev(m)
+    vsb.check(L.vsb_custom_resize(vp(d_m.data_ptr()), 10, 10, sz(40), vp(d.data_ptr()), 961, 627, sz(961 * 4), vp(stream())))
     _eq(host(d), og.custom_resize(m, 961, 627), "custom_resize")
     # addSrcWeight / normalize: replay against the oracle blender arithmetic on one level
     src = rng.integers(-300, 300, (40, 64, 3)).astype(np.int16)
@@ -81,13 +83,14 @@ def test_border_gain_resize_weighted_add_match_oracle(cuda, og, vsb):
     w[rng.random((40, 64)) < 0.3] = 0
     dst = rng.integers(-300, 300, (40, 64, 3)).astype(np.int16)
     dw = rng.random((40, 64)).astype(np.float32)
-    d_dst, d_dw = dev(dst), dev(dw)
-    vsb.check(L.vsb_add_src_weight_32f(vp(dev(src).data_ptr()), sz(64 * 6), vp(dev(w).data_ptr()), sz(256), vp(d_dst.data_ptr()), sz(64 * 6), vp(d_dw.data_ptr()), sz(256), 64, 40, vp(stream())))
+    d_dst, d_dw, d_s, d_w = dev(dst), dev(dw), dev(src), dev(w)
+    vsb.check(L.vsb_add_src_weight_32f(vp(d_s.data_ptr()), sz(64 * 6), vp(d_w.data_ptr()), sz(256), vp(d_dst.data_ptr()), sz(64 * 6), vp(d_dw.data_ptr()), sz(256), 64, 40, vp(stream())))
     want = (dst.astype(np.int32) + np.trunc(src.astype(np.float32) * w[..., None]).astype(np.int32)).astype(np.int16)
     _eq(host(d_dst), want, "addSrcWeight32F")
     _eq(host(d_dw), dw + w, "addSrcWeight32F weights")
     vsb.check(L.vsb_normalize_32f(vp(d_dw.data_ptr()), sz(256), vp(d_dst.data_ptr()), sz(64 * 6), 64, 40, vp(stream())))
-    want2 = np.trunc(want.astype(np.float32) / ((dw + w) + np.float32(1e-5))[..., None]).astype(np.int16)
+    # static_cast<short>(float) on the device is cvt.rzi.s16.f32: truncates and saturates
+    want2 = np.clip(np.trunc(want.astype(np.float32) / ((dw + w) + np.float32(1e-5))[..., None]), -32768, 32767).astype(np.int16)
     _eq(host(d_dst), want2, "normalize32F")
 
 

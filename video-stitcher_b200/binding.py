@@ -24,7 +24,7 @@ SYMBOLS = [
     "vsb_compose_host", "vsb_last_launch_count", "vsb_remap_linear_u8c3", "vsb_gain_u8",
     "vsb_border_reflect_u8c3_to_s16c3", "vsb_pyr_down_s16c3", "vsb_pyr_up_s16c3", "vsb_pyr_down_f32",
     "vsb_add_src_weight_32f", "vsb_normalize_32f", "vsb_debug_read",
-    "vsb_rig_camera", "vsb_voronoi_seams", "vsb_calibrate_rig", "vsb_rig_info_get", "vsb_get_config",
+    "vsb_rig_camera", "vsb_voronoi_seams", "vsb_calibrate_rig", "vsb_rig_info_get", "vsb_get_config", "vsb_set_profiling", "vsb_get_profile",
 ]
 
 
@@ -182,6 +182,17 @@ class Stitcher:
 
     def last_launch_count(self):
         return lib().vsb_last_launch_count(self._h)
+
+    def set_profiling(self, on):
+        check(lib().vsb_set_profiling(self._h, int(bool(on))))
+
+    def get_profile(self):
+        n = C.c_int()
+        names = (C.c_char_p * 16)()
+        ms = (C.c_float * 16)()
+        nbytes = (C.c_double * 16)()
+        check(lib().vsb_get_profile(self._h, 16, C.byref(n), names, ms, nbytes))
+        return [(names[i].decode(), float(ms[i]), float(nbytes[i])) for i in range(n.value)]
 
     def debug_read(self, what, view, level, frame, host_ptr, nbytes):
         check(lib().vsb_debug_read(self._h, what, view, level, frame, _vp(host_ptr), C.c_size_t(nbytes)))

@@ -471,6 +471,12 @@ struct vsb_stitcher {
     int stage_src_w = 0, stage_src_h = 0;
     int rig_projection = -1, rig_src_w = 0, rig_src_h = 0;
     float rig_scale = 0.f;
+    // optional per-kernel timing (vsb_set_profiling): events bracket every launch of the last submission
+    bool profiling = false;
+    int n_stages = 0;
+    cudaEvent_t prof_ev[VSB_MAX_STAGES + 1] = {};
+    const char *stage_name[VSB_MAX_STAGES] = {};
+    double stage_bytes[VSB_MAX_STAGES] = {};
 };
 
 namespace vsb {
@@ -577,6 +583,22 @@ static int adopt_meshes(vsb_stitcher *s, cudaStream_t st)
     return VSB_OK;
 }
 
+// profiling: record an event before the first kernel and after every kernel of a submission
+static void prof_begin(vsb_stitcher *s, cudaStream_t st)
+{
+    if (!s->profiling) return;
+    s->n_stages = 0;
+    cudaEventRecord(s->prof_ev[0], st);
+}
+static void prof_stage(vsb_stitcher *s, cudaStream_t st, const char *name, double bytes)
+{
+    if (!s->profiling || s->n_stages >= VSB_MAX_STAGES) return;
+    s->stage_name[s->n_stages] = name;
+    s->stage_bytes[s->n_stages] = bytes;
+    ++s->n_stages;
+    cudaEventRecord(s->prof_ev[s->n_stages], st);
+}
+
 static void fill_tilemap(TileMap &tm, int n, const int *w, const int *h, int tile_w, int tile_h)
 {
     tm.n = n;
@@ -608,6 +630,9 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
         for (int f = 0; f < n_frames; ++f) for (int j = 0; j < n; ++j) p.src[f * n + j] = d_srcs[f * n + j];
         k_remap_stage1<<<dim3(p.tm.start[n], n_frames), dim3(RM_BX, RM_BY), 0, st>>>(p);
         ++s->launches;
+        double bytes = 0;  // algorithmic: every source pixel once + P once
+        for (int j = 0; j < n; ++j) { const View &V = s->v[v0 + j]; bytes += 3.0 * V.src_w * V.src_h + 3.0 * V.roi_w * V.roi_h; }
+        prof_stage(s, st, "remap_stage1", bytes * n_frames);
     }
     {
         Stage2Params p;
@@ -624,6 +649,9 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
         fill_tilemap(p.tm, n, ws, hs, RM_BX * RM_PX, RM_BY);
         k_remap_stage2<<<dim3(p.tm.start[n], n_frames), dim3(RM_BX, RM_BY), 0, st>>>(p);
         ++s->launches;
+        double bytes = 0;  // P once + bordered planar G0 once
+        for (int j = 0; j < n; ++j) { const View &V = s->v[v0 + j]; bytes += 3.0 * V.roi_w * V.roi_h + 3.0 * V.bw * V.bh; }
+        prof_stage(s, st, "remap_stage2", bytes * n_frames);
     }
     for (int k = 0; k < s->nb; ++k) {
         PyrParams p;
@@ -642,6 +670,13 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
         if (k == 0) k_pyr_down<uint8_t><<<g, dim3(PD_TX, PD_TY), 0, st>>>(p);
         else k_pyr_down<int16_t><<<g, dim3(PD_TX, PD_TY), 0, st>>>(p);
         ++s->launches;
+        double bytes = 0;  // level k in once + level k+1 out once
+        for (int j = 0; j < n; ++j) {
+            const View &V = s->v[v0 + j];
+            bytes += 3.0 * (V.bw >> k) * (V.bh >> k) * (k == 0 ? 1 : 2) + 3.0 * (V.bw >> (k + 1)) * (V.bh >> (k + 1)) * 2;
+        }
+        static const char *names[VSB_MAX_BANDS] = {"pyr_down_0", "pyr_down_1", "pyr_down_2", "pyr_down_3", "pyr_down_4", "pyr_down_5", "pyr_down_6"};
+        prof_stage(s, st, names[k], bytes * n_frames);
     }
     return check_launch("front half (remap + pyramid)");
 }
@@ -654,6 +689,13 @@ static int launch_back(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, si
     const dim3 g((s->cw[0] + BL_TW - 1) / BL_TW, (s->ch[0] + BL_TH - 1) / BL_TH, n_frames);
     k_blend_collapse<<<g, BL_THREADS, 0, st>>>(s->d_plan, o, out_pitch);
     ++s->launches;
+    double bytes = 6.0 * s->roi_final[2] * s->roi_final[3];  // every Gaussian level of every view once + the CV_16SC3 pano once
+    for (int i = 0; i < s->cfg.num_views; ++i) {
+        const View &V = s->v[i];
+        bytes += 3.0 * V.bw * V.bh;
+        for (int k = 1; k <= s->nb; ++k) bytes += 6.0 * (V.bw >> k) * (V.bh >> k);
+    }
+    prof_stage(s, st, "blend_collapse", bytes * n_frames);
     return check_launch("k_blend_collapse");
 }
 
@@ -711,6 +753,7 @@ int vsb_destroy(vsb_stitcher *s)
     if (s->mesh_stream) cudaStreamDestroy(s->mesh_stream);
     if (s->io_stream) cudaStreamDestroy(s->io_stream);
     if (s->last_compose) cudaEventDestroy(s->last_compose);
+    for (int i = 0; i <= VSB_MAX_STAGES; ++i) if (s->prof_ev[i]) cudaEventDestroy(s->prof_ev[i]);
     cudaGetLastError();
     delete s;
     return VSB_OK;
@@ -789,7 +832,9 @@ int vsb_init_view(vsb_stitcher *s, int i, const uint8_t *mask, int mw, int mh, s
     size_t d_pitch = pitch;
     if (!on_device) {
         CK(cudaMalloc(&d_mask, (size_t)mw * mh));
-        CK(cudaMemcpy2D(d_mask, mw, mask, pitch, mw, mh, cudaMemcpyHostToDevice));
+        // stream-ordered: a blocking cudaMemcpy2D from pageable memory may return before its DMA lands, and the
+        // non-blocking setup stream does not serialise with the NULL stream
+        CK(cudaMemcpy2DAsync(d_mask, mw, mask, pitch, mw, mh, cudaMemcpyHostToDevice, s->setup_stream));
         d_pitch = mw;
     }
     const dim3 b(32, 8);
@@ -847,8 +892,9 @@ int vsb_set_maps(vsb_stitcher *s, int i, const float *xmap, const float *ymap, i
     CK(cudaDeviceSynchronize());
     if (!V.xmap) { CK(cudaMalloc(&V.xmap, V.map_pitch * h)); CK(cudaMalloc(&V.ymap, V.map_pitch * h)); }
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    CK(cudaMemcpy2D(V.xmap, V.map_pitch, xmap, pitch, (size_t)w * 4, h, kind));
-    CK(cudaMemcpy2D(V.ymap, V.map_pitch, ymap, pitch, (size_t)w * 4, h, kind));
+    CK(cudaMemcpy2DAsync(V.xmap, V.map_pitch, xmap, pitch, (size_t)w * 4, h, kind, s->setup_stream));
+    CK(cudaMemcpy2DAsync(V.ymap, V.map_pitch, ymap, pitch, (size_t)w * 4, h, kind, s->setup_stream));
+    CK(cudaStreamSynchronize(s->setup_stream));
     V.src_w = src_w; V.src_h = src_h; V.has_maps = true;
     return VSB_OK;
 }
@@ -913,7 +959,7 @@ int vsb_feed(vsb_stitcher *s, int i, const uint8_t *d_bgr, size_t pitch, void *s
     if (r != VSB_OK) return r;
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (i == 0) s->launches = 0;
+    if (i == 0) { s->launches = 0; prof_begin(s, st); }
     r = adopt_meshes(s, st);
     if (r != VSB_OK) return r;
     const uint8_t *srcs[1] = {d_bgr};
@@ -943,6 +989,7 @@ int vsb_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, siz
     s->launches = 0;
     r = adopt_meshes(s, st);
     if (r != VSB_OK) return r;
+    prof_begin(s, st);
     r = launch_front(s, 0, s->cfg.num_views, n_frames, d_srcs, src_pitch, st);
     if (r != VSB_OK) return r;
     r = launch_back(s, n_frames, d_outs, out_pitch, st);
@@ -989,6 +1036,33 @@ int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs
 }
 
 int vsb_last_launch_count(const vsb_stitcher *s) { return s ? s->launches : 0; }
+
+int vsb_set_profiling(vsb_stitcher *s, int on)
+{
+    REQ(s, VSB_ERR_INVALID, "set_profiling: null handle");
+    DeviceGuard g(s->device);
+    if (on && !s->prof_ev[0])
+        for (int i = 0; i <= VSB_MAX_STAGES; ++i) CK(cudaEventCreate(&s->prof_ev[i]));
+    s->profiling = on != 0;
+    s->n_stages = 0;
+    return VSB_OK;
+}
+
+int vsb_get_profile(vsb_stitcher *s, int max_stages, int *n_stages, const char **names, float *ms, double *bytes)
+{
+    REQ(s && n_stages && names && ms && bytes, VSB_ERR_INVALID, "get_profile: null argument");
+    REQ(s->profiling, VSB_ERR_STATE, "get_profile: profiling is off");
+    DeviceGuard g(s->device);
+    const int n = std::min(max_stages, s->n_stages);
+    if (n > 0) CK(cudaEventSynchronize(s->prof_ev[s->n_stages]));
+    for (int i = 0; i < n; ++i) {
+        CK(cudaEventElapsedTime(&ms[i], s->prof_ev[i], s->prof_ev[i + 1]));
+        names[i] = s->stage_name[i];
+        bytes[i] = s->stage_bytes[i];
+    }
+    *n_stages = n;
+    return VSB_OK;
+}
 
 int vsb_get_config(const vsb_stitcher *s, vsb_config *out)
 {
