@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- stitched frames/s of the per-frame 360-degree compose path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch F] [--impl ours|reference]
+
+A step = one vsb_compose submission of F frames of the workload (config 2 of BASELINE.json: 6 x 1080p ->
+3840-wide spherical panorama, CPW mesh remap on, 5-band blend).  Source frames live in a ring of frame sets
+larger than L2, so every step reads its inputs from HBM.
+  value  : frames/s, inputs already resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e    : frames/s through vsb_compose_host (pinned HOST buffers, H2D + D2H inside the timed region)
+  roofline : dominant kernel, algorithmic bytes / mean device time from per-kernel CUDA events (vsb_get_profile)
+  cpu_baseline : oracle-G (the CPU port of the reference arithmetic) on the box's host cores, bounded sample
+N > 1 (torchrun): frame-level replicas, one process per GPU, no data-path collective ("weak" scaling).
+--impl reference : the CPU implementation on all host cores, same config/metric (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1] (and [4] without the recalibration thread)
+    "cfg2": dict(n_views=6, src_w=1920, src_h=1080, pano_width=3840, num_bands=5, enable_local=True, projection=0,
+                 name="6x1080p->3840 spherical, CPW on, 5 bands"),
+    "cfg3": dict(n_views=6, src_w=1920, src_h=1080, pano_width=7680, num_bands=5, enable_local=True, projection=0,
+                 name="6x1080p->7680 spherical, CPW on, 5 bands"),
+    "tiny": dict(n_views=4, src_w=320, src_h=240, pano_width=1024, num_bands=3, enable_local=True, projection=0,
+                 name="4x320x240->1024 (debug)"),
+}
+RING = 8  # distinct frame sets resident in HBM (8 x 37 MB = 299 MB > 126 MB L2 at cfg2)
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._stop_evt, self.proc = gpu_index, [], threading.Event(), None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+                if self._stop_evt.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def make_frames(cfg, n_sets):
+    import vsb200
+    S = vsb200.synth
+    return [[S.frame(i, f, cfg["src_w"], cfg["src_h"]) for i in range(cfg["n_views"])] for f in range(n_sets)]
+
+
+def cpu_reference_run(cfg, frames, steps, warmup, threads):
+    """Times the CPU implementation (oracle-G port of the reference arithmetic) on `threads` host threads."""
+    import vsb200
+    from oracle import oracle as og
+    from oracle import pipeline as op
+    og.set_num_threads(threads)
+    rig = op.OracleRig(cfg["n_views"], cfg["src_w"], cfg["src_h"], cfg["pano_width"], cfg["projection"], cfg["num_bands"],
+                       cfg["enable_local"], vsb200.synth.gains(cfg["n_views"]))
+    if cfg["enable_local"]:
+        for i in range(cfg["n_views"]):
+            rig.set_mesh(i, *vsb200.synth.mesh(*rig.sizes[i]))
+    for w in range(warmup):
+        rig.compose(frames[w % len(frames)])
+    t0 = time.perf_counter()
+    for k in range(steps):
+        rig.compose(frames[k % len(frames)])
+    dt = time.perf_counter() - t0
+    return steps / dt, dt
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    threads = host_cores()
+    steps, warmup = max(1, min(args.steps, 40)), max(1, min(args.warmup, 3))
+    frames = make_frames(cfg, min(RING, steps))
+    fps, dt = cpu_reference_run(cfg, frames, steps, warmup, threads)
+    sample = f"{steps} frames of the full {cfg['name']} workload (1 frame per step), oracle-G CPU port, OpenMP over rows"
+    line = {
+        "impl": "reference", "metric": "stitched equirect frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/s16 (fp32 taps)", "data": "synthetic",
+        "config": {"workload": cfg["name"], "frames_per_step": 1, "inputs": "host memory"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--batch", type=int, default=1, help="frames per vsb_compose submission (F)")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    cfg = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import vsb200
+    B, S = vsb200.binding, vsb200.synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the compose path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    F, K, W = args.batch, args.steps, max(args.warmup, 3)
+    n = cfg["n_views"]
+    st = B.Stitcher(n, cfg["num_bands"], cfg["enable_local"], F)
+    st.calibrate_rig(cfg["projection"], cfg["pano_width"], cfg["src_w"], cfg["src_h"], 90.0, S.gains(n))
+    info = st.rig_info()
+    if cfg["enable_local"]:
+        for i in range(n):
+            mx, my = S.mesh(info.view_roi[i][2], info.view_roi[i][3])
+            st.set_mesh(i, mx.ctypes.data, my.ctypes.data, mx.shape[0], mx.shape[1])
+    roi, _, nb = st.get_roi()
+    OW, OH = roi[2], roi[3]
+    src_pitch, out_pitch = cfg["src_w"] * 3, OW * 6
+
+    # ring of RING frame sets (each rank gets different frames: frame-level data parallelism)
+    n_sets = max(RING, F)
+    host_sets = []
+    for f in range(n_sets):
+        host_sets.append([torch.from_numpy(S.frame(i, f + rank * n_sets, cfg["src_w"], cfg["src_h"])).pin_memory() for i in range(n)])
+    dev_sets = [[t.cuda(non_blocking=True) for t in fs] for fs in host_sets]
+    outs = [torch.empty((OH, OW, 3), dtype=torch.int16, device="cuda") for _ in range(F)]
+    stream = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+
+    calls = []
+    for s0 in range(0, n_sets):
+        srcs = [dev_sets[(s0 + j) % n_sets][i].data_ptr() for j in range(F) for i in range(n)]
+        calls.append(st.make_compose_call(srcs, src_pitch, [o.data_ptr() for o in outs], out_pitch, stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(W):
+        calls[w % n_sets]()
+    launches_per_step = st.last_launch_count()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for k in range(K):
+        calls[k % n_sets]()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # keep sampling for a moment on very short runs so at least a few samples land under load
+    if t_wall1 - t_wall0 < 0.5:
+        t_end = time.time() + 0.6
+        while time.time() < t_end:
+            calls[0]()
+        torch.cuda.synchronize()
+        t_wall1 = time.time()
+    sampler.stop()
+    clocks = sampler.summary(t_wall0, t_wall1)
+    fps = world * F * K / (ms / 1000.0)
+
+    # ---- per-kernel device times over K steps (events on the launching stream), dominant kernel roofline
+    st.set_profiling(True)
+    acc = {}
+    prof_steps = min(K, 50)
+    for k in range(prof_steps):
+        calls[k % n_sets]()
+        for name, t_ms, nbytes in st.get_profile():
+            a = acc.setdefault(name, [0.0, nbytes])
+            a[0] += t_ms
+    st.set_profiling(False)
+    kernels = {name: {"ms": a[0] / prof_steps, "alg_bytes": a[1], "GBps": a[1] / (a[0] / prof_steps) / 1e6} for name, a in acc.items()}
+    top = max(kernels, key=lambda k_: kernels[k_]["ms"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s"
+    b_io = n * cfg["src_w"] * cfg["src_h"] * 3 + OW * OH * 6  # sources once + CV_16SC3 pano once
+    roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[top]["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": kernels[top]["alg_bytes"], "ms_per_launch": kernels[top]["ms"],
+                "share_of_step": kernels[top]["ms"] / sum(v["ms"] for v in kernels.values())}
+    roofline_path = {"alg_bytes_per_frame": b_io, "achieved": b_io * fps / world / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": b_io * fps / world / 1e9 / peak, "note": "whole path, B_io = sources once + pano once (SURVEY.md 8d)"}
+
+    # ---- e2e through the host-buffer entry point (pinned host memory in, host memory out)
+    e2e = None
+    if not args.no_e2e:
+        h_outs = [torch.empty((OH, OW, 3), dtype=torch.int16).pin_memory() for _ in range(F)]
+        def host_call(s0):
+            srcs = [host_sets[(s0 + j) % n_sets][i].data_ptr() for j in range(F) for i in range(n)]
+            st.compose_host(srcs, src_pitch, [o.data_ptr() for o in h_outs], out_pitch)
+        for w in range(3):
+            host_call(w)
+        Ke = max(3, min(K, 60))
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(Ke):
+            host_call(k % n_sets)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * F * Ke / dt, "unit": "frames/s", "h2d_bytes_per_step": F * n * cfg["src_w"] * cfg["src_h"] * 3,
+               "d2h_bytes_per_step": F * OW * OH * 6, "steps": Ke, "api": "vsb_compose_host (pinned host buffers, H2D+D2H inside)"}
+
+    # ---- CPU baseline: oracle-G port on the host cores, rank 0 at N=1 only, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = host_cores()
+        frames_np = [[t.numpy() for t in fs] for fs in host_sets[:4]]
+        n_cpu = 12
+        cfps, cdt = cpu_reference_run(cfg, frames_np, n_cpu, 1, threads)
+        cpu = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"{n_cpu} frames of the same workload, oracle-G (C, OpenMP over rows), {cdt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "stitched equirect frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/s16 (fp32 taps)", "data": "synthetic",
+            "config": {"workload": cfg["name"], "frames_per_step": F, "ring_frame_sets": n_sets,
+                       "l2_policy": f"inputs larger than L2: ring of {n_sets} frame sets = {n_sets * n * cfg['src_w'] * cfg['src_h'] * 3 / 1e6:.0f} MB",
+                       "pano": f"{OW}x{OH} CV_16SC3", "bands": nb, "multi_gpu": "frame-level replicas, no collective" if world > 1 else "single GPU"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
+            "roofline": roofline, "roofline_path": roofline_path, "kernels": kernels, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
