@@ -198,6 +198,14 @@ def pyr_up_s16_int(src):
     return _pyr(lib().og_pyr_up_s16_int, src, True)
 
 
+def pyr_down_s16_halfup(src):
+    return _pyr(lib().og_pyr_down_s16_halfup, src, False)
+
+
+def pyr_up_s16_halfup(src):
+    return _pyr(lib().og_pyr_up_s16_halfup, src, True)
+
+
 def pyr_down_f32(src):
     src = _f32(src)
     h, w = src.shape
@@ -255,6 +263,13 @@ class Blender:
         assert r >= 0
         self.n_views += 1
         return r
+
+    def set_cpu_pyramids(self, on):
+        lib().og_blender_set_cpu_pyramids(self._h, int(bool(on)))
+
+    def set_view_weight(self, i, level, w):
+        w = _f32(w)
+        lib().og_blender_set_view_weight(self._h, i, level, _p(w, C.c_float))
 
     def view_geom(self, i):
         g = (C.c_int * 8)()

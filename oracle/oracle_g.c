@@ -549,6 +549,47 @@ void og_pyr_up_s16_int(const int16_t *src, int w, int h, int cn, int16_t *dst)
             }
 }
 
+/* CPU-rounding twins: the vendored CPU cv::pyrDown / cv::pyrUp on CV_16S are exact integer sums with round-half-UP
+ * (FixPtCast<short,8>: (v + 128) >> 8, FixPtCast<short,6>: (v + 32) >> 6; IMG/src/pyramids.cpp:52-57,1375,1483).  They
+ * differ from the CUDA fp32 + cvt.rni forms above only on exact .5 ties.  Used to pin the blender restatement
+ * bit-exactly against oracle/_ref (tests/test_oracle_pin.py). */
+void og_pyr_down_s16_halfup(const int16_t *src, int w, int h, int cn, int16_t *dst)
+{
+    static const int K5[5] = {1, 4, 6, 4, 1};
+    int dw = (w + 1) / 2, dh = (h + 1) / 2;
+    for (int y = 0; y < dh; ++y)
+        for (int x = 0; x < dw; ++x)
+            for (int c = 0; c < cn; ++c) {
+                int s = 0;
+                for (int j = 0; j < 5; ++j) {
+                    int sy = r101(2 * y + j - 2, h);
+                    for (int i = 0; i < 5; ++i) {
+                        int sx = r101(2 * x + i - 2, w);
+                        s += K5[j] * K5[i] * src[((size_t)sy * w + sx) * cn + c];
+                    }
+                }
+                dst[((size_t)y * dw + x) * cn + c] = sat_s16_i((s + 128) >> 8);
+            }
+}
+
+void og_pyr_up_s16_halfup(const int16_t *src, int w, int h, int cn, int16_t *dst)
+{
+    int dw = 2 * w, dh = 2 * h;
+    for (int y = 0; y < dh; ++y)
+        for (int x = 0; x < dw; ++x)
+            for (int c = 0; c < cn; ++c) {
+                int iy = y >> 1, ix = x >> 1;
+                int wy[3], wx[3];
+                if ((y & 1) == 0) { wy[0] = 1; wy[1] = 6; wy[2] = 1; } else { wy[0] = 0; wy[1] = 4; wy[2] = 4; }
+                if ((x & 1) == 0) { wx[0] = 1; wx[1] = 6; wx[2] = 1; } else { wx[0] = 0; wx[1] = 4; wx[2] = 4; }
+                int s = 0;
+                for (int j = 0; j < 3; ++j)
+                    for (int i = 0; i < 3; ++i)
+                        s += wy[j] * wx[i] * src[((size_t)up_idx(iy + j - 1, h) * w + up_idx(ix + i - 1, w)) * cn + c];
+                dst[((size_t)y * dw + x) * cn + c] = sat_s16_i((s + 32) >> 6);
+            }
+}
+
 /* cuda::pyrDown<float, BrdReflect101> for the weight pyramids (S/src/blenders.cpp:422-423): not exact in fp32,
  * so nvcc's contraction pattern matters: sum = 0.0625f*a; sum = fma(0.25f,b,sum); ... */
 void og_pyr_down_f32(const float *src, int w, int h, float *dst)
@@ -691,6 +732,7 @@ struct og_blender {
     int16_t *dst[OG_MAX_LEVELS];   /* gpu_dst_pyr_laplace_ */
     float *dstw[OG_MAX_LEVELS];    /* gpu_dst_band_weights_ */
     int n_views;
+    int cpu_pyramids;              /* test hook: half-up integer pyramids (the CPU twins) instead of fp32 + rni */
     og_view views[OG_MAX_VIEWS];
 };
 
@@ -746,6 +788,16 @@ int og_blender_prepare(og_blender *b, int n, const int *corners_xy, const int *s
 }
 
 int og_blender_num_bands(const og_blender *b) { return b->num_bands; }
+
+static void level_size(int w0, int h0, int k, int *w, int *h);
+/* test hooks (tests/test_oracle_pin.py): CPU-rounding pyramids, and injection of a weight level computed elsewhere */
+void og_blender_set_cpu_pyramids(og_blender *b, int on) { b->cpu_pyramids = on; }
+void og_blender_set_view_weight(og_blender *b, int i, int level, const float *w)
+{
+    int lw, lh;
+    level_size(b->views[i].bw, b->views[i].bh, level, &lw, &lh);
+    memcpy(b->views[i].weight[level], w, sizeof(float) * lw * lh);
+}
 
 void og_blender_dst_roi(const og_blender *b, int roi_final[4], int roi_padded[4])
 {
@@ -843,10 +895,10 @@ void og_blender_feed_online(og_blender *b, int i, const uint8_t *img, int w, int
         if (!v->lap[k]) v->lap[k] = (int16_t *)malloc(sizeof(int16_t) * 3 * lw[k] * lh[k]);
     }
     og_border_reflect_u8c3_to_s16(img, w, h, step, v->top, v->bottom, v->left, v->right, v->lap[0]);
-    for (int k = 0; k < nb; ++k) og_pyr_down_s16(v->lap[k], lw[k], lh[k], 3, v->lap[k + 1]);
+    for (int k = 0; k < nb; ++k) (b->cpu_pyramids ? og_pyr_down_s16_halfup : og_pyr_down_s16)(v->lap[k], lw[k], lh[k], 3, v->lap[k + 1]);
     for (int k = 0; k < nb; ++k) {
         int16_t *up = (int16_t *)malloc(sizeof(int16_t) * 3 * lw[k] * lh[k]);
-        og_pyr_up_s16(v->lap[k + 1], lw[k + 1], lh[k + 1], 3, up);
+        (b->cpu_pyramids ? og_pyr_up_s16_halfup : og_pyr_up_s16)(v->lap[k + 1], lw[k + 1], lh[k + 1], 3, up);
         size_t n = (size_t)3 * lw[k] * lh[k];
         for (size_t j = 0; j < n; ++j) v->lap[k][j] = sat_s16_i((int)v->lap[k][j] - (int)up[j]);
         free(up);
@@ -884,7 +936,7 @@ void og_blender_blend(og_blender *b, int16_t *out, uint8_t *mask_out)
     for (int k = nb; k > 0; --k) {
         size_t n = (size_t)3 * b->lw[k - 1] * b->lh[k - 1];
         int16_t *up = (int16_t *)malloc(sizeof(int16_t) * n);
-        og_pyr_up_s16(b->dst[k], b->lw[k], b->lh[k], 3, up);
+        (b->cpu_pyramids ? og_pyr_up_s16_halfup : og_pyr_up_s16)(b->dst[k], b->lw[k], b->lh[k], 3, up);
         for (size_t j = 0; j < n; ++j) b->dst[k - 1][j] = sat_s16_i((int)up[j] + (int)b->dst[k - 1][j]);
         free(up);
     }

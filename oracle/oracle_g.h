@@ -59,6 +59,9 @@ void og_pyr_down_f32(const float *src, int w, int h, float *dst);
 /* exact-integer twins used to prove the fp32 forms are rounding-order independent on s16 data */
 void og_pyr_down_s16_int(const int16_t *src, int w, int h, int cn, int16_t *dst);
 void og_pyr_up_s16_int(const int16_t *src, int w, int h, int cn, int16_t *dst);
+/* round-half-up twins = the vendored CPU cv::pyrDown / cv::pyrUp on CV_16S (IMG/src/pyramids.cpp:52-57) */
+void og_pyr_down_s16_halfup(const int16_t *src, int w, int h, int cn, int16_t *dst);
+void og_pyr_up_s16_halfup(const int16_t *src, int w, int h, int cn, int16_t *dst);
 
 /* ---------------------------------------------------------------- seam masks */
 void og_voronoi_find(int n, const int *sizes_wh, const int *corners_xy, uint8_t **masks);
@@ -70,6 +73,8 @@ void og_blender_destroy(og_blender *b);
 /* prepare(corners, sizes): returns 0; fills geometry */
 int og_blender_prepare(og_blender *b, int n, const int *corners_xy, const int *sizes_wh);
 int og_blender_num_bands(const og_blender *b);
+void og_blender_set_cpu_pyramids(og_blender *b, int on);
+void og_blender_set_view_weight(og_blender *b, int i, int level, const float *w);
 void og_blender_dst_roi(const og_blender *b, int roi_final[4], int roi_padded[4]);
 /* init_gpu(mask, tl): views must be added in order */
 int og_blender_init_view(og_blender *b, const uint8_t *mask, int mw, int mh, size_t mstep, int tl_x, int tl_y);

@@ -1,0 +1,106 @@
+"""CPU-only tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/vsb200.h declares, and
+its HOST-side calibration logic (no device work) matches the oracle and the reference golden vectors.  No compute entry
+point is exercised here -- those are the -m gpu tests."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vsb200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vsb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(vsb):
+    lib = vsb.lib()
+    names = _declared()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"libvsb200.so does not export {missing}"
+    assert sorted(set(vsb.SYMBOLS)) == names, set(vsb.SYMBOLS) ^ set(names)
+
+
+def test_cpp_adapter_header_compiles():
+    """include/vsb200.hpp (the C++ adapter with the reference's class/function names) is self-contained C++11."""
+    import shutil
+    import subprocess
+    import tempfile
+    gxx = shutil.which("g++", path="/usr/bin") or shutil.which("g++")
+    if not gxx or not os.path.exists(os.path.join(ROOT, "include", "vsb200.hpp")):
+        pytest.skip("no g++ or adapter header")
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.cpp")
+        open(src, "w").write('#include "vsb200.hpp"\nint main() { return 0; }\n')
+        subprocess.check_call([gxx, "-std=c++11", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src])
+
+
+def test_no_device_fails_loudly(vsb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    assert vsb.lib().vsb_device_count() == 0
+    with pytest.raises(vsb.VsbError) as e:
+        vsb.Stitcher(2, 3, True, 1)
+    assert "vsb error -2" in str(e.value) or "no CUDA device" in str(e.value)
+
+
+def test_bad_arguments_are_rejected_without_a_device(vsb):
+    lib = vsb.lib()
+    roi = (C.c_int * 4)()
+    K = (C.c_float * 9)(*([1, 0, 0, 0, 1, 0, 0, 0, 1]))
+    assert lib.vsb_warp_roi(7, C.c_float(100.0), K, K, 10, 10, roi) == -1
+    assert b"warp_roi" in lib.vsb_last_error()
+    assert lib.vsb_warp_roi(0, C.c_float(-1.0), K, K, 10, 10, roi) == -1
+    assert lib.vsb_rig_camera(0, 0, 10, 10, C.c_double(90.0), K, K) == -1
+    assert lib.vsb_create(None, None) == -1
+    assert lib.vsb_destroy(None) == 0
+
+
+@pytest.mark.parametrize("rig", [(6, 1920, 1080, 3840), (4, 320, 240, 1024), (12, 3840, 2160, 15360), (5, 640, 480, 2000)])
+def test_host_geometry_matches_oracle_and_reference(vsb, og, rig):
+    n, sw, sh, pano = rig
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_cpu.npz"))["warp_roi"]
+    scale = np.float32(pano / (2.0 * 3.1415926535897932384626))
+    for i in range(n):
+        K, R = vsb.rig_camera(n, i, sw, sh)
+        Ko, Ro = og.rig_camera(n, i, sw, sh)
+        assert np.array_equal(np.float32(K), Ko.reshape(9)) and np.array_equal(np.float32(R), Ro.reshape(9))
+        for proj in (0, 1):
+            roi = vsb.warp_roi(proj, float(scale), K, R, sw, sh)
+            assert roi == og.warp_roi(proj, scale, Ko, Ro, sw, sh)
+            row = gold[(gold[:, 0] == n) & (gold[:, 3] == pano) & (gold[:, 4] == proj) & (gold[:, 5] == i)]
+            assert len(row) == 1 and roi == tuple(int(v) for v in row[0, 6:])   # = the reference's warpRoi
+
+
+def test_host_voronoi_matches_reference(vsb, og):
+    from tests.golden import make_golden as G
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_cpu.npz"))
+    n, sw, sh, pano, proj = G.SEAM_RIGS[0]
+    masks, corners, sizes = G.seam_inputs(og, n, sw, sh, pano, proj)
+    s = np.ascontiguousarray(np.array(sizes, np.int32).reshape(-1))
+    c = np.ascontiguousarray(np.array(corners, np.int32).reshape(-1))
+    ptrs = (C.c_void_p * n)(*[m.ctypes.data for m in masks])
+    vsb.check(vsb.lib().vsb_voronoi_seams(n, s.ctypes.data_as(C.POINTER(C.c_int)), c.ctypes.data_as(C.POINTER(C.c_int)), ptrs))
+    for i, m in enumerate(masks):
+        assert np.array_equal(np.packbits(m > 0, axis=1), gold[f"voronoi_{n}_{pano}_{proj}_{i}"])
+
+
+def test_product_never_touches_the_oracle():
+    """The product path must not import, link or execute anything under oracle/ (nor fall back to the CPU)."""
+    pkg = os.path.join(ROOT, "video-stitcher_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.replace("no oracle dependency", ""), f"{f} mentions the oracle"
+    for f in ("vsb200.h", "vsb200.hpp"):
+        p = os.path.join(ROOT, "include", f)
+        if os.path.exists(p):
+            assert "oracle/" not in open(p).read()
