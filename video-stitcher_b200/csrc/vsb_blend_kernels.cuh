@@ -1,0 +1,569 @@
+// vsb_blend_kernels.cuh -- the back half of the per-frame compose path (sm_100a): Gaussian pyramid, Laplacian,
+// seam-masked weighted add, normalisation, pyramid collapse, output mask and crop in THREE kernels.
+//
+// Reference stages replaced: MultiBandBlender::feed_online's pyrDown x nb, (pyrUp, subtract) x nb,
+// addSrcWeightGpu32F x (nb+1) per view (sources/modules/stitching/src/blenders.cpp:713-746) and MultiBandBlender::blend's
+// normalizeUsingWeightMapGpu32F x (nb+1), (pyrUp, add) x nb, compare, setTo, crop-copy and per-frame clears (:767-831) --
+// ~23 launches per view + 32 per frame there.
+//
+//   k_down2   per view      G0 (u8 planes, bordered)  -> G2                       two pyrDown levels per CTA, G1 stays on chip
+//   k_coarse  per canvas    G2 of every view          -> C2 = collapsed levels 2..nb of the blended, normalised pyramid
+//   k_blend   per canvas    G0, G2, masks, C2         -> CV_16SC3 panorama        levels 0 and 1 + final collapse + mask + crop
+//
+// Facts the design rests on (all exact):
+//   * every Gaussian level of a u8 image stays in [0, 255] (convex taps + round-half-even), so G_k is stored as u8 and the
+//     5x5 binomial taps are evaluated with __dp4a on packed bytes; the integer sum / 256 rounded half-even IS the reference's
+//     fp32 vertical-then-horizontal pass followed by cvt.rni (every partial sum is exactly representable in fp32);
+//   * dst += (short)(L * w) is arithmetic mod 2^16, hence order independent: a canvas tile sums its views in registers /
+//     shared memory and the destination pyramid of the reference never exists in HBM;
+//   * weights are static, so which views touch which tile is a table built once (vsb_pipeline.cu: build_plan);
+//     the per-level weight sums of levels 0 and 1 are re-accumulated in view order (bit-identical to dst_band_weights_).
+#pragma once
+#include "vsb_internal.h"
+
+namespace vsb {
+
+constexpr int MAXV = VSB_MAX_VIEWS;
+constexpr int MAXL = VSB_MAX_BANDS + 1;
+constexpr int MAX_BATCH = 8;
+
+struct OutPtrs { int16_t *out[MAX_BATCH]; };
+
+__device__ __forceinline__ unsigned ldg_u8(const uint8_t *p) { return (unsigned)__ldg(p); }
+
+// 5x5 binomial taps on packed bytes.  `row` points at a 4-byte aligned word of a u8 row; the five taps start at byte
+// offset 0 (ALIGNED) or 2 (!ALIGNED) of row[0] and spill into row[1].  `kj` is the vertical tap weight (1, 4, 6).
+template <bool ALIGNED>
+__device__ __forceinline__ unsigned taps5(unsigned w0, unsigned w1, unsigned kj, unsigned acc)
+{
+    // byte weights (little endian): ALIGNED: w0 = {1,4,6,4}, w1 = {1,0,0,0};  else: w0 = {0,0,1,4}, w1 = {6,4,1,0}
+    const unsigned a0 = ALIGNED ? 0x04060401u : 0x04010000u;
+    const unsigned a1 = ALIGNED ? 0x00000001u : 0x00010406u;
+    acc = __dp4a(w0, a0 * kj, acc);
+    return __dp4a(w1, a1 * kj, acc);
+}
+
+// pyrUp (x4 gain folded) of one sample from a plane accessor a(x, y) defined on level-(k+1) PLANE indices
+template <typename Acc>
+__device__ __forceinline__ int pyr_up_sample(const Acc &a, int x, int y, int n_x, int n_y)
+{
+    const int ix = x >> 1, iy = y >> 1;
+    int acc;
+    if (((x | y) & 1) == 0) {
+        const int xm = up_idx(ix - 1, n_x), xc = ix, xp = up_idx(ix + 1, n_x);
+        const int ym = up_idx(iy - 1, n_y), yc = iy, yp = up_idx(iy + 1, n_y);
+        const int r0 = a(xm, ym) + 6 * a(xc, ym) + a(xp, ym);
+        const int r1 = a(xm, yc) + 6 * a(xc, yc) + a(xp, yc);
+        const int r2 = a(xm, yp) + 6 * a(xc, yp) + a(xp, yp);
+        acc = r0 + 6 * r1 + r2;
+    } else if ((y & 1) == 0) {  // x odd
+        const int xc = ix, xp = up_idx(ix + 1, n_x);
+        const int ym = up_idx(iy - 1, n_y), yc = iy, yp = up_idx(iy + 1, n_y);
+        acc = 4 * ((a(xc, ym) + a(xp, ym)) + 6 * (a(xc, yc) + a(xp, yc)) + (a(xc, yp) + a(xp, yp)));
+    } else if ((x & 1) == 0) {  // y odd
+        const int xm = up_idx(ix - 1, n_x), xc = ix, xp = up_idx(ix + 1, n_x);
+        const int yc = iy, yp = up_idx(iy + 1, n_y);
+        acc = 4 * ((a(xm, yc) + 6 * a(xc, yc) + a(xp, yc)) + (a(xm, yp) + 6 * a(xc, yp) + a(xp, yp)));
+    } else {
+        const int xc = ix, xp = up_idx(ix + 1, n_x);
+        const int yc = iy, yp = up_idx(iy + 1, n_y);
+        acc = 16 * (a(xc, yc) + a(xp, yc) + a(xc, yp) + a(xp, yp));
+    }
+    return sat_s16(rhe_shift<6>(acc));
+}
+
+// pyrUp of the 8 consecutive samples x0 .. x0+7 (x0 even) of row y; same integers as pyr_up_sample, columns shared.
+template <typename Acc>
+__device__ __forceinline__ void pyr_up_row8(const Acc &a, int x0, int y, int n_x, int n_y, int out[8])
+{
+    const int ix0 = x0 >> 1, iy = y >> 1;
+    int col[6];
+    if (y & 1) {
+        const int yc = iy, yp = up_idx(iy + 1, n_y);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { const int cx = up_idx(ix0 - 1 + i, n_x); col[i] = 4 * (a(cx, yc) + a(cx, yp)); }
+    } else {
+        const int ym = up_idx(iy - 1, n_y), yc = iy, yp = up_idx(iy + 1, n_y);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { const int cx = up_idx(ix0 - 1 + i, n_x); col[i] = a(cx, ym) + 6 * a(cx, yc) + a(cx, yp); }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        out[2 * p] = sat_s16(rhe_shift<6>(col[p] + 6 * col[p + 1] + col[p + 2]));
+        out[2 * p + 1] = sat_s16(rhe_shift<6>(4 * (col[p + 1] + col[p + 2])));
+    }
+}
+
+// Loads one 4-byte word of a u8 plane row whose column gx may fall outside [0, w): BORDER_REFLECT_101 per byte there.
+__device__ __forceinline__ unsigned load_word_r101(const uint8_t *__restrict__ row, int gx, int w)
+{
+    if (gx >= 0 && gx + 3 < w && (((size_t)(row + gx)) & 3) == 0) return __ldg((const unsigned *)(row + gx));
+    unsigned v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) v |= ldg_u8(row + r101_idx(gx + b, w)) << (8 * b);
+    return v;
+}
+
+// =========================================================================================================== k_down2
+// G2 = pyrDown(pyrDown(G0)) for one 32x16 tile of one colour plane of one view; G1 lives in shared memory only.
+constexpr int D2_TW = 32, D2_TH = 16, D2_THREADS = 256;
+constexpr int D2_R1W = 2 * D2_TW + 3, D2_R1H = 2 * D2_TH + 3;  // G1 region 67 x 35: origin (2*X0 - 2, 2*Y0 - 2)
+constexpr int D2_R0WORDS = 35, D2_R0H = 4 * D2_TH + 9;          // G0 region 140 B x 73: origin (4*X0 - 8, 4*Y0 - 6)
+
+struct Down2View {
+    const uint8_t *g0;  // frame 0, plane 0
+    uint8_t *g2;
+    size_t g0_fs, g2_fs;  // frame strides (bytes)
+    int bw, bh;           // level-0 plane size
+};
+struct Down2Params {
+    const uint32_t *tiles;  // view | tile_x << 8 | tile_y << 20
+    Down2View v[MAXV];
+};
+
+__global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Down2Params P)
+{
+    __shared__ __align__(16) unsigned s0[D2_R0H][D2_R0WORDS + 1];
+    __shared__ uint8_t s1[D2_R1H][D2_R1W + 1];
+    const unsigned tile = __ldg(P.tiles + blockIdx.x);
+    const Down2View &V = P.v[tile & 0xff];
+    const int X0 = ((tile >> 8) & 0xfff) * D2_TW, Y0 = (tile >> 20) * D2_TH;
+    const int c = blockIdx.y, f = blockIdx.z, t = threadIdx.x;
+    const int w0 = V.bw, h0 = V.bh, w1 = w0 >> 1, h1 = h0 >> 1, w2 = w0 >> 2, h2 = h0 >> 2;
+    const uint8_t *g0 = V.g0 + (size_t)f * V.g0_fs + (size_t)c * w0 * h0;
+    const int gx0 = 4 * X0 - 8, gy0 = 4 * Y0 - 6;
+    for (int i = t; i < D2_R0H * D2_R0WORDS; i += D2_THREADS) {
+        const int r = i / D2_R0WORDS, m = i - r * D2_R0WORDS;
+        s0[r][m] = load_word_r101(g0 + (size_t)r101_idx(gy0 + r, h0) * w0, gx0 + 4 * m, w0);
+    }
+    __syncthreads();
+    // G1 over the region, at true in-plane positions only (nested reflection does not commute at the high edge)
+    for (int i = t; i < D2_R1H * D2_R1W; i += D2_THREADS) {
+        const int r1 = i / D2_R1W, c1 = i - r1 * D2_R1W;
+        const int y1 = 2 * Y0 - 2 + r1, x1 = 2 * X0 - 2 + c1;
+        if ((unsigned)y1 >= (unsigned)h1 || (unsigned)x1 >= (unsigned)w1) continue;
+        const int b = 2 * c1 + 2;  // first tap, byte offset inside the region row
+        const unsigned *row = &s0[2 * r1][b >> 2];
+        unsigned acc = 0;
+        if (c1 & 1) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) acc = taps5<true>(row[j * (D2_R0WORDS + 1)], row[j * (D2_R0WORDS + 1) + 1], j == 2 ? 6u : ((j & 1) ? 4u : 1u), acc);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) acc = taps5<false>(row[j * (D2_R0WORDS + 1)], row[j * (D2_R0WORDS + 1) + 1], j == 2 ? 6u : ((j & 1) ? 4u : 1u), acc);
+        }
+        s1[r1][c1] = (uint8_t)rhe_shift<8>((int)acc);
+    }
+    __syncthreads();
+    uint8_t *g2 = V.g2 + (size_t)f * V.g2_fs + (size_t)c * w2 * h2;
+    for (int i = t; i < D2_TW * D2_TH; i += D2_THREADS) {
+        const int x2 = X0 + (i & (D2_TW - 1)), y2 = Y0 + i / D2_TW;
+        if (x2 >= w2 || y2 >= h2) continue;
+        int acc = 0;
+        const int ry = 2 * (y2 - Y0), rx = 2 * (x2 - X0);  // region position of tap (0, 0)
+        if (2 * y2 - 2 >= 0 && 2 * y2 + 2 < h1 && 2 * x2 - 2 >= 0 && 2 * x2 + 2 < w1) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const uint8_t *r = &s1[ry + j][rx];
+                acc += (j == 2 ? 6 : ((j & 1) ? 4 : 1)) * (r[0] + 4 * r[1] + 6 * r[2] + 4 * r[3] + r[4]);
+            }
+        } else {
+            int cc[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) cc[j] = r101_idx(2 * x2 - 2 + j, w1) - (2 * X0 - 2);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const uint8_t *r = s1[r101_idx(2 * y2 - 2 + j, h1) - (2 * Y0 - 2)];
+                acc += (j == 2 ? 6 : ((j & 1) ? 4 : 1)) * (r[cc[0]] + 4 * r[cc[1]] + 6 * r[cc[2]] + 4 * r[cc[3]] + r[cc[4]]);
+            }
+        }
+        g2[(size_t)y2 * w2 + x2] = (uint8_t)rhe_shift<8>(acc);
+    }
+}
+
+// ========================================================================================================== k_coarse
+// Levels 2..nb for one 64x64 (level-2) canvas tile of one colour plane: for every view that has weight there, the
+// Gaussian levels 3..nb, the Laplacian bands, the truncating weighted add into shared-memory accumulators; then the
+// normalisation by the static weight sums and the collapse nb -> 2.  Output: C2 = D2 + up(D3 + up(... Dnb)).
+constexpr int CT = 64, C_MAXJ = 6, C_THREADS = 256;
+
+struct CoarseGeo {  // tile-independent offsets, relative to (X0 >> j, Y0 >> j); same for x and y (square tiles)
+    int nlev;                         // levels 2 .. nb  ->  nb - 1
+    int a_lo[C_MAXJ], a_n[C_MAXJ];    // accumulation / collapse region of level 2 + j
+    int g_lo[C_MAXJ], g_n[C_MAXJ];    // Gaussian region of level 2 + j (g_lo[0] is a multiple of 4)
+    int a_off[C_MAXJ], g_off[C_MAXJ]; // shared-memory offsets: A in int16 units, G in bytes (after the A area)
+    int g_pitch[C_MAXJ];              // bytes (g_pitch[0] is a multiple of 4)
+    int a_total;                      // int16 elements
+};
+struct CoarseView {
+    const uint8_t *g2;
+    const float *w[C_MAXJ];  // static weight level 2 + j
+    size_t g2_fs;
+    int x_tl, y_tl, bw, bh;  // level-0 canvas origin and size of the bordered view
+};
+struct CoarseParams {
+    CoarseGeo geo;
+    int cw[C_MAXJ], ch[C_MAXJ];  // canvas size of level 2 + j
+    const float *dw[C_MAXJ];     // static weight sums of level 2 + j
+    int16_t *c2;                 // frame 0, plane 0: [3][ch2][cw2]
+    size_t c2_fs;                // elements
+    const uint32_t *tile_views;  // bit v: view v has weight in this tile (any level >= 2)
+    int tiles_x;
+    CoarseView v[MAXV];
+};
+
+__global__ void __launch_bounds__(C_THREADS) k_coarse(const __grid_constant__ CoarseParams P)
+{
+    extern __shared__ __align__(16) uint8_t c_smem[];
+    const CoarseGeo &Gm = P.geo;
+    int16_t *A = (int16_t *)c_smem;
+    uint8_t *G = c_smem + (size_t)Gm.a_total * 2;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, c = blockIdx.y, f = blockIdx.z, nlev = Gm.nlev;
+    const int X0 = (blockIdx.x % P.tiles_x) * CT, Y0 = (blockIdx.x / P.tiles_x) * CT;
+    for (int i = t; i < Gm.a_total; i += C_THREADS) A[i] = 0;
+    unsigned views = __ldg(P.tile_views + blockIdx.x);
+    while (views) {
+        const int vi = __ffs(views) - 1;
+        views &= views - 1;
+        const CoarseView &V = P.v[vi];
+        __syncthreads();
+        {   // G2 region of this view (words; BORDER_REFLECT_101 relative to the view's plane)
+            const int w = V.bw >> 2, h = V.bh >> 2, ox = V.x_tl >> 2, oy = V.y_tl >> 2;
+            const uint8_t *g2 = V.g2 + (size_t)f * V.g2_fs + (size_t)c * w * h;
+            const int n = Gm.g_n[0], words = Gm.g_pitch[0] >> 2;
+            const int vx0 = X0 + Gm.g_lo[0] - ox, vy0 = Y0 + Gm.g_lo[0] - oy;
+            unsigned *dst = (unsigned *)(G + Gm.g_off[0]);
+            for (int r = warp; r < n; r += C_THREADS / 32) {
+                const uint8_t *row = g2 + (size_t)r101_idx(vy0 + r, h) * w;
+                for (int m = lane; m < words; m += 32) dst[r * words + m] = load_word_r101(row, vx0 + 4 * m, w);
+            }
+        }
+        __syncthreads();
+        for (int j = 0; j + 1 < nlev; ++j) {  // G(j+1) = pyrDown(G(j)) at in-plane positions of its region
+            const int k = 2 + j;
+            const int ws = V.bw >> k, hs = V.bh >> k, wd = ws >> 1, hd = hs >> 1;
+            const int sx0 = (X0 >> j) + Gm.g_lo[j] - (V.x_tl >> k), sy0 = (Y0 >> j) + Gm.g_lo[j] - (V.y_tl >> k);
+            const int dx0 = (X0 >> (j + 1)) + Gm.g_lo[j + 1] - (V.x_tl >> (k + 1)), dy0 = (Y0 >> (j + 1)) + Gm.g_lo[j + 1] - (V.y_tl >> (k + 1));
+            const uint8_t *src = G + Gm.g_off[j];
+            uint8_t *dst = G + Gm.g_off[j + 1];
+            const int sp = Gm.g_pitch[j], dp = Gm.g_pitch[j + 1], n = Gm.g_n[j + 1];
+            for (int r = warp; r < n; r += C_THREADS / 32) {
+                const int y = dy0 + r;  // plane coordinates at level k + 1
+                if ((unsigned)y >= (unsigned)hd) continue;
+                const bool yin = 2 * y - 2 >= 0 && 2 * y + 2 < hs;
+                for (int q = lane; q < n; q += 32) {
+                    const int x = dx0 + q;
+                    if ((unsigned)x >= (unsigned)wd) continue;
+                    int acc = 0;
+                    if (yin && 2 * x - 2 >= 0 && 2 * x + 2 < ws) {
+                        const uint8_t *rp = src + (2 * y - 2 - sy0) * sp + (2 * x - 2 - sx0);
+#pragma unroll
+                        for (int e = 0; e < 5; ++e, rp += sp) acc += (e == 2 ? 6 : ((e & 1) ? 4 : 1)) * (rp[0] + 4 * rp[1] + 6 * rp[2] + 4 * rp[3] + rp[4]);
+                    } else {
+                        int cc[5];
+#pragma unroll
+                        for (int e = 0; e < 5; ++e) cc[e] = r101_idx(2 * x - 2 + e, ws) - sx0;
+#pragma unroll
+                        for (int e = 0; e < 5; ++e) {
+                            const uint8_t *rp = src + (r101_idx(2 * y - 2 + e, hs) - sy0) * sp;
+                            acc += (e == 2 ? 6 : ((e & 1) ? 4 : 1)) * (rp[cc[0]] + 4 * rp[cc[1]] + 6 * rp[cc[2]] + 4 * rp[cc[3]] + rp[cc[4]]);
+                        }
+                    }
+                    dst[r * dp + q] = (uint8_t)rhe_shift<8>(acc);
+                }
+            }
+            __syncthreads();
+        }
+        for (int j = 0; j < nlev; ++j) {  // A(j) += trunc(L(j) * W(j))
+            const int k = 2 + j;
+            const int wv = V.bw >> k, hv = V.bh >> k;
+            const int ax0 = (X0 >> j) + Gm.a_lo[j] - (V.x_tl >> k), ay0 = (Y0 >> j) + Gm.a_lo[j] - (V.y_tl >> k);
+            const int gx0 = (X0 >> j) + Gm.g_lo[j] - (V.x_tl >> k), gy0 = (Y0 >> j) + Gm.g_lo[j] - (V.y_tl >> k);
+            const uint8_t *gs = G + Gm.g_off[j];
+            const int gp = Gm.g_pitch[j], n = Gm.a_n[j];
+            int16_t *Aj = A + Gm.a_off[j];
+            const float *wgt = V.w[j];
+            const bool top = j + 1 == nlev;
+            const uint8_t *gu = top ? nullptr : G + Gm.g_off[j + 1];
+            const int up = top ? 0 : Gm.g_pitch[j + 1];
+            const int ux0 = top ? 0 : (X0 >> (j + 1)) + Gm.g_lo[j + 1] - (V.x_tl >> (k + 1));
+            const int uy0 = top ? 0 : (Y0 >> (j + 1)) + Gm.g_lo[j + 1] - (V.y_tl >> (k + 1));
+            for (int r = warp; r < n; r += C_THREADS / 32) {
+                const int y = ay0 + r;
+                if ((unsigned)y >= (unsigned)hv) continue;
+                for (int q = lane; q < n; q += 32) {
+                    const int x = ax0 + q;
+                    if ((unsigned)x >= (unsigned)wv) continue;
+                    const float wv_ = __ldg(wgt + (size_t)y * wv + x);
+                    if (wv_ == 0.f) continue;  // (short)(L * 0) == 0
+                    int L = gs[(y - gy0) * gp + (x - gx0)];
+                    if (!top) {
+                        auto acc = [&](int xi, int yi) { return (int)gu[(yi - uy0) * up + (xi - ux0)]; };
+                        L -= pyr_up_sample(acc, x, y, wv >> 1, hv >> 1);
+                    }
+                    Aj[r * n + q] = (int16_t)(Aj[r * n + q] + rz_s16(__fmul_rn((float)L, wv_)));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = nlev - 1; j >= 0; --j) {  // normalise, then C(j) = D(j) + up(C(j+1)), saturating
+        const int cwj = P.cw[j], chj = P.ch[j], n = Gm.a_n[j];
+        const int x0 = (X0 >> j) + Gm.a_lo[j], y0 = (Y0 >> j) + Gm.a_lo[j];
+        int16_t *Aj = A + Gm.a_off[j];
+        const bool top = j + 1 == nlev;
+        const int16_t *Au = top ? nullptr : A + Gm.a_off[j + 1];
+        const int un = top ? 0 : Gm.a_n[j + 1];
+        const int ux0 = top ? 0 : (X0 >> (j + 1)) + Gm.a_lo[j + 1], uy0 = top ? 0 : (Y0 >> (j + 1)) + Gm.a_lo[j + 1];
+        const int cwu = top ? 0 : P.cw[j + 1], chu = top ? 0 : P.ch[j + 1];
+        const float *dw = P.dw[j];
+        for (int r = warp; r < n; r += C_THREADS / 32) {
+            const int y = y0 + r;
+            if ((unsigned)y >= (unsigned)chj) continue;
+            for (int q = lane; q < n; q += 32) {
+                const int x = x0 + q;
+                if ((unsigned)x >= (unsigned)cwj) continue;
+                const float den = __fadd_rn(__ldg(dw + (size_t)y * cwj + x), 1e-5f);
+                int d = rz_s16(__fdiv_rn((float)Aj[r * n + q], den));
+                if (!top) {
+                    auto acc = [&](int xi, int yi) { return (int)Au[(yi - uy0) * un + (xi - ux0)]; };
+                    d = sat_s16(d + pyr_up_sample(acc, x, y, cwu, chu));
+                }
+                Aj[r * n + q] = (int16_t)d;
+            }
+        }
+        __syncthreads();
+    }
+    {
+        const int cw2 = P.cw[0], ch2 = P.ch[0];
+        int16_t *o = P.c2 + (size_t)f * P.c2_fs + (size_t)c * cw2 * ch2;
+        for (int i = t; i < CT * CT; i += C_THREADS) {
+            const int y = Y0 + i / CT, x = X0 + (i & (CT - 1));
+            if (y < ch2 && x < cw2) o[(size_t)y * cw2 + x] = A[Gm.a_off[0] + i];
+        }
+    }
+}
+
+// =========================================================================================================== k_blend
+// Levels 0 and 1, the final collapse, the output mask and the crop for one 64x32 canvas tile (all three channels).
+constexpr int BL_TW = 64, BL_TH = 32, BL_THREADS = 256;
+constexpr int BL_R1W = BL_TW / 2 + 2, BL_R1H = BL_TH / 2 + 2;   // level-1 region 34 x 18, origin (tx0/2 - 1, ty0/2 - 1)
+constexpr int BL_G0WORDS = 18, BL_G0H = BL_TH + 7;              // level-0 region 72 B x 39, origin (tx0 - 4, ty0 - 4)
+constexpr int BL_R2W = BL_TW / 4 + 4, BL_R2H = BL_TH / 4 + 4;   // level-2 region 20 x 12, origin (tx0/4 - 2, ty0/4 - 2)
+constexpr int BL_L1PT = (BL_R1W * BL_R1H + BL_THREADS - 1) / BL_THREADS;  // level-1 samples per thread (3)
+
+struct BlendView {
+    const uint8_t *g0, *g2;  // frame 0
+    const uint8_t *m0;       // bordered seam mask (u8, 0 in the border): W0 = m0 * (1/255)
+    const float *w1;         // static weight level 1
+    size_t g0_fs, g2_fs;
+    int x_tl, y_tl, bw, bh;
+};
+struct BlendParams {
+    int nb, tiles_x;
+    int cw0, ch0, cw1, ch1, cw2, ch2;
+    int out_w, out_h;
+    const int16_t *c2;
+    size_t c2_fs;
+    const uint32_t *tile_views;  // bit v: view v has level-0 or level-1 weight in this tile
+    BlendView v[MAXV];
+};
+
+__global__ void __launch_bounds__(BL_THREADS) k_blend(const __grid_constant__ BlendParams P, const __grid_constant__ OutPtrs outs, size_t out_pitch)
+{
+    __shared__ __align__(16) unsigned sG0[3][BL_G0H][BL_G0WORDS + 1];
+    __shared__ uint8_t sG1[3][BL_R1H][BL_R1W + 2];
+    __shared__ uint8_t sG2[3][BL_R2H][BL_R2W];
+    __shared__ int16_t sC2[3][BL_R2H][BL_R2W];
+    __shared__ int16_t sD1[3][BL_R1H][BL_R1W];
+    __shared__ __align__(16) int16_t sOut[BL_TH][BL_TW * 3];
+    const int t = threadIdx.x, f = blockIdx.z, nb = P.nb;
+    const int tx0 = blockIdx.x * BL_TW, ty0 = blockIdx.y * BL_TH;
+    const int lx = (t & 7) * 8, ly = t >> 3;  // this thread's 8 consecutive level-0 samples
+    const int px0 = tx0 + lx, py = ty0 + ly;
+    int acc0[3][8], acc1[3][BL_L1PT];
+    float dw0[8], dw1[BL_L1PT];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dw0[i] = 0.f; acc0[0][i] = acc0[1][i] = acc0[2][i] = 0; }
+#pragma unroll
+    for (int q = 0; q < BL_L1PT; ++q) { dw1[q] = 0.f; acc1[0][q] = acc1[1][q] = acc1[2][q] = 0; }
+
+    unsigned views = __ldg(P.tile_views + blockIdx.y * P.tiles_x + blockIdx.x);
+    while (views) {
+        const int vi = __ffs(views) - 1;  // ascending view order: the weight sums below add in the reference's order
+        views &= views - 1;
+        const BlendView &V = P.v[vi];
+        const int w0 = V.bw, h0 = V.bh, w1 = w0 >> 1, h1 = h0 >> 1, w2 = w0 >> 2, h2 = h0 >> 2;
+        __syncthreads();
+        {
+            const uint8_t *g0 = V.g0 + (size_t)f * V.g0_fs;
+            const int vx0 = tx0 - 4 - V.x_tl, vy0 = ty0 - 4 - V.y_tl;
+            for (int i = t; i < 3 * BL_G0H * BL_G0WORDS; i += BL_THREADS) {
+                const int c = i / (BL_G0H * BL_G0WORDS), rem = i - c * (BL_G0H * BL_G0WORDS);
+                const int r = rem / BL_G0WORDS, m = rem - r * BL_G0WORDS;
+                sG0[c][r][m] = load_word_r101(g0 + ((size_t)c * h0 + r101_idx(vy0 + r, h0)) * w0, vx0 + 4 * m, w0);
+            }
+            if (nb >= 2) {
+                const uint8_t *g2 = V.g2 + (size_t)f * V.g2_fs;
+                const int ux0 = (tx0 >> 2) - 2 - (V.x_tl >> 2), uy0 = (ty0 >> 2) - 2 - (V.y_tl >> 2);
+                for (int i = t; i < 3 * BL_R2H * BL_R2W; i += BL_THREADS) {
+                    const int c = i / (BL_R2H * BL_R2W), rem = i - c * (BL_R2H * BL_R2W);
+                    const int r = rem / BL_R2W, q = rem - r * BL_R2W;
+                    sG2[c][r][q] = (uint8_t)ldg_u8(g2 + ((size_t)c * h2 + up_idx(uy0 + r, h2)) * w2 + up_idx(ux0 + q, w2));
+                }
+            }
+        }
+        __syncthreads();
+        const int v1x0 = (tx0 >> 1) - 1 - (V.x_tl >> 1), v1y0 = (ty0 >> 1) - 1 - (V.y_tl >> 1);  // plane coords of region (0,0)
+        if (nb >= 1) {
+            for (int i = t; i < 3 * BL_R1H * BL_R1W; i += BL_THREADS) {
+                const int c = i / (BL_R1H * BL_R1W), rem = i - c * (BL_R1H * BL_R1W);
+                const int r1 = rem / BL_R1W, c1 = rem - r1 * BL_R1W;
+                if ((unsigned)(v1y0 + r1) >= (unsigned)h1 || (unsigned)(v1x0 + c1) >= (unsigned)w1) continue;
+                const unsigned *row = &sG0[c][2 * r1][c1 >> 1];  // first tap at region byte 2*c1
+                unsigned acc = 0;
+                if (c1 & 1) {
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) acc = taps5<false>(row[j * (BL_G0WORDS + 1)], row[j * (BL_G0WORDS + 1) + 1], j == 2 ? 6u : ((j & 1) ? 4u : 1u), acc);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) acc = taps5<true>(row[j * (BL_G0WORDS + 1)], row[j * (BL_G0WORDS + 1) + 1], j == 2 ? 6u : ((j & 1) ? 4u : 1u), acc);
+                }
+                sG1[c][r1][c1] = (uint8_t)rhe_shift<8>((int)acc);
+            }
+            __syncthreads();
+        }
+        // ---- level 0: this thread's 8 samples
+        const int qx0 = px0 - V.x_tl, qy = py - V.y_tl;
+        if ((unsigned)qx0 < (unsigned)w0 && (unsigned)qy < (unsigned)h0) {
+            const uint2 mm = __ldg((const uint2 *)(V.m0 + (size_t)qy * w0 + qx0));
+            float wv[8];
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const unsigned m = ((i < 4 ? mm.x : mm.y) >> (8 * (i & 3))) & 0xff;
+                wv[i] = __fmul_rn((float)(1. / 255.), (float)m);
+                dw0[i] = __fadd_rn(dw0[i], wv[i]);
+                any |= m != 0;
+            }
+            if (any) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const unsigned ga = sG0[c][ly + 4][(lx + 4) >> 2], gb = sG0[c][ly + 4][((lx + 4) >> 2) + 1];
+                    int up[8];
+                    if (nb >= 1) {
+                        auto a = [&](int xi, int yi) { return (int)sG1[c][yi - v1y0][xi - v1x0]; };
+                        pyr_up_row8(a, qx0, qy, w1, h1, up);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) up[i] = 0;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int g = ((i < 4 ? ga : gb) >> (8 * (i & 3))) & 0xff;
+                        acc0[c][i] += rz_s16(__fmul_rn((float)(g - up[i]), wv[i]));
+                    }
+                }
+            }
+        }
+        // ---- level 1: up to BL_L1PT samples of the 34 x 18 region
+        if (nb >= 1) {
+            const int u2x0 = (tx0 >> 2) - 2 - (V.x_tl >> 2), u2y0 = (ty0 >> 2) - 2 - (V.y_tl >> 2);
+#pragma unroll
+            for (int q = 0; q < BL_L1PT; ++q) {
+                const int i = t + q * BL_THREADS;
+                if (i >= BL_R1W * BL_R1H) continue;
+                const int r1 = i / BL_R1W, c1 = i - r1 * BL_R1W;
+                const int x = v1x0 + c1, y = v1y0 + r1;
+                if ((unsigned)x >= (unsigned)w1 || (unsigned)y >= (unsigned)h1) continue;
+                const float wq = __ldg(V.w1 + (size_t)y * w1 + x);
+                dw1[q] = __fadd_rn(dw1[q], wq);
+                if (wq == 0.f) continue;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    int L = sG1[c][r1][c1];
+                    if (nb >= 2) {
+                        auto a = [&](int xi, int yi) { return (int)sG2[c][yi - u2y0][xi - u2x0]; };
+                        L -= pyr_up_sample(a, x, y, w2, h2);
+                    }
+                    acc1[c][q] += rz_s16(__fmul_rn((float)L, wq));
+                }
+            }
+        }
+    }
+    // ---- collapse: C2 (global) -> D1 (shared) -> D0 -> output
+    if (nb >= 2) {
+        const int16_t *c2 = P.c2 + (size_t)f * P.c2_fs;
+        const int ux0 = (tx0 >> 2) - 2, uy0 = (ty0 >> 2) - 2;
+        for (int i = t; i < 3 * BL_R2H * BL_R2W; i += BL_THREADS) {
+            const int c = i / (BL_R2H * BL_R2W), rem = i - c * (BL_R2H * BL_R2W);
+            const int r = rem / BL_R2W, q = rem - r * BL_R2W;
+            sC2[c][r][q] = __ldg(c2 + ((size_t)c * P.ch2 + up_idx(uy0 + r, P.ch2)) * P.cw2 + up_idx(ux0 + q, P.cw2));
+        }
+        __syncthreads();
+    }
+    if (nb >= 1) {
+        const int X1 = (tx0 >> 1) - 1, Y1 = (ty0 >> 1) - 1, ux0 = (tx0 >> 2) - 2, uy0 = (ty0 >> 2) - 2;
+#pragma unroll
+        for (int q = 0; q < BL_L1PT; ++q) {
+            const int i = t + q * BL_THREADS;
+            if (i >= BL_R1W * BL_R1H) continue;
+            const int r1 = i / BL_R1W, c1 = i - r1 * BL_R1W;
+            const int x = X1 + c1, y = Y1 + r1;
+            if ((unsigned)x >= (unsigned)P.cw1 || (unsigned)y >= (unsigned)P.ch1) continue;
+            const float den = __fadd_rn(dw1[q], 1e-5f);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                int d = rz_s16(__fdiv_rn((float)(int)(short)acc1[c][q], den));
+                if (nb >= 2) {
+                    auto a = [&](int xi, int yi) { return (int)sC2[c][yi - uy0][xi - ux0]; };
+                    d = sat_s16(d + pyr_up_sample(a, x, y, P.cw2, P.ch2));
+                }
+                sD1[c][r1][c1] = (int16_t)d;
+            }
+        }
+        __syncthreads();
+    }
+    if (px0 < P.cw0 && py < P.ch0) {
+        const int X1 = (tx0 >> 1) - 1, Y1 = (ty0 >> 1) - 1;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int up[8];
+            if (nb >= 1) {
+                auto a = [&](int xi, int yi) { return (int)sD1[c][yi - Y1][xi - X1]; };
+                pyr_up_row8(a, px0, py, P.cw1, P.ch1, up);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) up[i] = 0;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int d = rz_s16(__fdiv_rn((float)(int)(short)acc0[c][i], __fadd_rn(dw0[i], 1e-5f)));
+                d = sat_s16(d + up[i]);
+                sOut[ly][(lx + i) * 3 + c] = dw0[i] > 1e-5f ? (int16_t)d : (int16_t)0;  // dst_mask = dst_band_weights_[0] > WEIGHT_EPS
+            }
+        }
+    }
+    __syncthreads();
+    // ---- cropped, interleaved CV_16SC3 store: 16-byte vectors where the caller's buffer allows
+    const int n_px = min(BL_TW, P.out_w - tx0), n_rows = min(BL_TH, P.out_h - ty0);
+    if (n_px <= 0 || n_rows <= 0) return;
+    char *obase = (char *)outs.out[f] + (size_t)tx0 * 6;
+    const bool vec_ok = ((((size_t)obase) | out_pitch) & 15) == 0;
+    const int row_bytes = n_px * 6;
+    for (int i = t; i < n_rows * (BL_TW * 6 / 16); i += BL_THREADS) {
+        const int r = i / (BL_TW * 6 / 16), ck = i - r * (BL_TW * 6 / 16);
+        const int b0 = ck * 16;
+        if (b0 >= row_bytes) continue;
+        char *o = obase + (size_t)(ty0 + r) * out_pitch + b0;
+        const int16_t *s = &sOut[r][ck * 8];
+        if (vec_ok && b0 + 16 <= row_bytes) {
+            *(uint4 *)o = *(const uint4 *)s;
+        } else {
+            const int n = min(8, (row_bytes - b0) >> 1);
+            for (int e = 0; e < n; ++e) ((int16_t *)o)[e] = s[e];
+        }
+    }
+}
+
+}  // namespace vsb

@@ -51,11 +51,16 @@ __device__ __forceinline__ int reflect_idx(int i, int len)
 }
 
 // BORDER_REFLECT_101 as used by pyrDown: sources/modules/core/include/opencv2/core/cuda/border_interpolate.hpp:351-380
+//   idx_low(i) = abs(i) % len, idx_high(i) = abs(last - abs(last - i)) % len, idx = idx_low(idx_high(i)).
+// Within one fold (-(len-1) <= i <= 2*(len-1)) that is the plain mirror below; the modulo only matters for planes
+// smaller than the tap reach, handled by the (rare) second branch so the common case costs four instructions.
 __device__ __forceinline__ int r101_idx(int i, int len)
 {
     const int last = len - 1;
-    int j = abs(last - abs(last - i)) % len;
-    return abs(j) % len;
+    int j = abs(i);
+    j = j > last ? 2 * last - j : j;
+    if ((unsigned)j > (unsigned)last) j = abs(abs(last - abs(last - i)) % len) % len;
+    return j;
 }
 
 // pyrUp source index: abs() at the low edge, clamp at the high edge (sources/modules/cudawarping/src/cuda/pyr_up.cu:70-74)

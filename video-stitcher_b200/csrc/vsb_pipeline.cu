@@ -4,18 +4,18 @@
 // MultiBandBlender::blend, ~190 kernel launches and ~1.1 GB of HBM traffic per frame in the reference
 // (360_stitcher/timed.cpp:56-152, sources/modules/stitching/src/blenders.cpp:700-832).
 //
-// Here one frame (or a batch of F frames) is
+// Here one frame (or a batch of F frames) is five launches (num_bands >= 3):
 //   K1 k_remap_stage1   src (u8x3)            -> P  = gain(remap#1(src))          u8x3 interleaved, ROI size
 //   K2 k_remap_stage2   P + CPW mesh maps     -> G0 = REFLECT-bordered remap#2(P) u8 planar, bordered size
-//   K3 k_pyr_down x nb  G(k)                  -> G(k+1)                            s16 planar
-//   K4 k_blend_collapse G(0..nb), W, sum(W)   -> out (CV_16SC3)
-// K4 fuses, per output tile and entirely on chip: pyrUp+subtract (Laplacian) of every contributing view,
-// the truncating weighted add, the normalisation by the static weight sum, the whole pyramid collapse
-// (pyrUp+add per level), the output mask and the crop.  The destination pyramid, the `ups` buffers and
-// the per-frame clears of the reference never exist.
+//   K3 k_down2          G0                    -> G2 (two pyrDown levels, G1 on chip)              vsb_blend_kernels.cuh
+//   K4 k_coarse         G2 of every view      -> C2 = collapsed blended levels 2..nb (canvas)     vsb_blend_kernels.cuh
+//   K5 k_blend          G0, G2, masks, C2     -> out (CV_16SC3): levels 0/1, collapse, mask, crop vsb_blend_kernels.cuh
+// The destination pyramid, the per-view Laplacian pyramids, the `ups` buffers and the per-frame clears of the
+// reference never exist; which view touches which tile is a static table (build_plan).
+// num_bands < 3 (bordered sizes not multiples of 8) takes the generic per-level kernels further below.
 //
-// HBM layout: all per-view intermediates are PLANAR (one plane per colour channel) with the bordered
-// width (a multiple of 2^nb >= 32) as row length, so rows of every level start 16-byte aligned.
+// HBM layout: all per-view intermediates are PLANAR u8 (one plane per colour channel) with the bordered
+// width (a multiple of 2^nb) as row length, so rows of every level start word aligned.
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -24,12 +24,9 @@
 #include <vector>
 
 #include "vsb_internal.h"
+#include "vsb_blend_kernels.cuh"
 
 namespace vsb {
-
-constexpr int MAXV = VSB_MAX_VIEWS;
-constexpr int MAXL = VSB_MAX_BANDS + 1;
-constexpr int MAX_BATCH = 8;
 
 // ============================================================================================ device side
 
@@ -197,7 +194,7 @@ __global__ void __launch_bounds__(PD_TX *PD_TY) k_pyr_down(const __grid_constant
 }
 
 // ---- K4: fused Laplacian + weighted add + normalise + collapse + mask + crop ---------------------------
-struct BlendView {
+struct LgBlendView {
     const uint8_t *g0;       // level 0 planes (u8), frame 0
     const int16_t *g[MAXL];  // level k >= 1 planes (s16), frame 0
     const float *w[MAXL];    // static weight pyramid
@@ -205,47 +202,18 @@ struct BlendView {
     size_t g_frame_stride[MAXL];
     int x_tl, y_tl, bw, bh;  // level-0 canvas rect origin and bordered size (multiples of 2^nb)
 };
-struct BlendPlan {
+struct LgBlendPlan {
     int n_views, nb;
     int cw[MAXL], ch[MAXL];   // canvas (padded dst roi) size per level
     const float *dw[MAXL];    // static sum of weights per level (accumulated in view order)
     int out_w, out_h;         // dst_roi_final_
-    BlendView v[MAXV];
+    LgBlendView v[MAXV];
 };
 
-constexpr int BL_TW = 64, BL_TH = 32, BL_THREADS = 256;
-// region of level k needed by a BL_TW x BL_TH tile: r(k) = r(k-1)/2 + 3 (upper bound)
-constexpr int BL_R1W = BL_TW / 2 + 2, BL_R1H = BL_TH / 2 + 2;
-constexpr int BL_SMEM_ELEMS = BL_R1W * BL_R1H;  // largest stored region (level 1)
-
-// pyrUp (x4 gain folded) of one sample from a plane accessor
-template <typename Acc>
-__device__ __forceinline__ int pyr_up_sample(const Acc &a, int x, int y, int n_x, int n_y)
-{
-    const int ix = x >> 1, iy = y >> 1;
-    int acc;
-    if (((x | y) & 1) == 0) {
-        const int xm = up_idx(ix - 1, n_x), xc = ix, xp = up_idx(ix + 1, n_x);
-        const int ym = up_idx(iy - 1, n_y), yc = iy, yp = up_idx(iy + 1, n_y);
-        const int r0 = a(xm, ym) + 6 * a(xc, ym) + a(xp, ym);
-        const int r1 = a(xm, yc) + 6 * a(xc, yc) + a(xp, yc);
-        const int r2 = a(xm, yp) + 6 * a(xc, yp) + a(xp, yp);
-        acc = r0 + 6 * r1 + r2;
-    } else if ((y & 1) == 0) {  // x odd
-        const int xc = ix, xp = up_idx(ix + 1, n_x);
-        const int ym = up_idx(iy - 1, n_y), yc = iy, yp = up_idx(iy + 1, n_y);
-        acc = 4 * ((a(xc, ym) + a(xp, ym)) + 6 * (a(xc, yc) + a(xp, yc)) + (a(xc, yp) + a(xp, yp)));
-    } else if ((x & 1) == 0) {  // y odd
-        const int xm = up_idx(ix - 1, n_x), xc = ix, xp = up_idx(ix + 1, n_x);
-        const int yc = iy, yp = up_idx(iy + 1, n_y);
-        acc = 4 * ((a(xm, yc) + 6 * a(xc, yc) + a(xp, yc)) + (a(xm, yp) + 6 * a(xc, yp) + a(xp, yp)));
-    } else {
-        const int xc = ix, xp = up_idx(ix + 1, n_x);
-        const int yc = iy, yp = up_idx(iy + 1, n_y);
-        acc = 16 * (a(xc, yc) + a(xp, yc) + a(xc, yp) + a(xp, yp));
-    }
-    return sat_s16(rhe_shift<6>(acc));
-}
+constexpr int LG_TW = 64, LG_TH = 32, LG_THREADS = 256;
+// region of level k needed by a LG_TW x LG_TH tile: r(k) = r(k-1)/2 + 3 (upper bound)
+constexpr int LG_R1W = LG_TW / 2 + 2, LG_R1H = LG_TH / 2 + 2;
+constexpr int LG_SMEM_ELEMS = LG_R1W * LG_R1H;  // largest stored region (level 1)
 
 struct GlobalS16Plane {
     const int16_t *p;
@@ -258,18 +226,16 @@ struct SmemRegion {
     __device__ __forceinline__ int operator()(int x, int y) const { return (int)p[(y - y0) * w + (x - x0)]; }
 };
 
-struct OutPtrs { int16_t *out[MAX_BATCH]; };
-
-__global__ void __launch_bounds__(BL_THREADS) k_blend_collapse(const BlendPlan *__restrict__ plan, const __grid_constant__ OutPtrs outs, size_t out_pitch)
+__global__ void __launch_bounds__(LG_THREADS) k_legacy_blend_collapse(const LgBlendPlan *__restrict__ plan, const __grid_constant__ OutPtrs outs, size_t out_pitch)
 {
-    __shared__ int16_t sD[2][3][BL_SMEM_ELEMS];
-    __shared__ BlendPlan P;
-    for (int i = threadIdx.x; i < (int)(sizeof(BlendPlan) / 4); i += BL_THREADS) ((int *)&P)[i] = ((const int *)plan)[i];
+    __shared__ int16_t sD[2][3][LG_SMEM_ELEMS];
+    __shared__ LgBlendPlan P;
+    for (int i = threadIdx.x; i < (int)(sizeof(LgBlendPlan) / 4); i += LG_THREADS) ((int *)&P)[i] = ((const int *)plan)[i];
     __syncthreads();
     const int nb = P.nb, f = blockIdx.z;
     int lo_x[MAXL], hi_x[MAXL], lo_y[MAXL], hi_y[MAXL];
-    lo_x[0] = blockIdx.x * BL_TW; hi_x[0] = min(lo_x[0] + BL_TW, P.cw[0]) - 1;
-    lo_y[0] = blockIdx.y * BL_TH; hi_y[0] = min(lo_y[0] + BL_TH, P.ch[0]) - 1;
+    lo_x[0] = blockIdx.x * LG_TW; hi_x[0] = min(lo_x[0] + LG_TW, P.cw[0]) - 1;
+    lo_y[0] = blockIdx.y * LG_TH; hi_y[0] = min(lo_y[0] + LG_TH, P.ch[0]) - 1;
 #pragma unroll
     for (int k = 1; k < MAXL; ++k) {
         if (k <= nb) {
@@ -281,16 +247,16 @@ __global__ void __launch_bounds__(BL_THREADS) k_blend_collapse(const BlendPlan *
     for (int k = nb; k >= 0; --k) {
         const int rw = hi_x[k] - lo_x[k] + 1, rh = hi_y[k] - lo_y[k] + 1;
         const int cwk = P.cw[k];
-        int16_t(*cur)[BL_SMEM_ELEMS] = sD[k & 1];
-        const int16_t(*prev)[BL_SMEM_ELEMS] = sD[(k + 1) & 1];
+        int16_t(*cur)[LG_SMEM_ELEMS] = sD[k & 1];
+        const int16_t(*prev)[LG_SMEM_ELEMS] = sD[(k + 1) & 1];
 #pragma unroll 1
-        for (int idx = threadIdx.x; idx < rw * rh; idx += BL_THREADS) {
+        for (int idx = threadIdx.x; idx < rw * rh; idx += LG_THREADS) {
             const int ry = idx / rw, rx = idx - ry * rw;
             const int px = lo_x[k] + rx, py = lo_y[k] + ry;
             int a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll 1
             for (int vi = 0; vi < P.n_views; ++vi) {
-                const BlendView &V = P.v[vi];
+                const LgBlendView &V = P.v[vi];
                 const int bwk = V.bw >> k, bhk = V.bh >> k;
                 const int qx = px - (V.x_tl >> k), qy = py - (V.y_tl >> k);
                 if ((unsigned)qx >= (unsigned)bwk || (unsigned)qy >= (unsigned)bhk) continue;
@@ -347,14 +313,16 @@ __global__ void __launch_bounds__(BL_THREADS) k_blend_collapse(const BlendPlan *
 
 // ---- static setup kernels -------------------------------------------------------------------------------
 // weight level 0: copyMakeBorder(mask * (1/255), BORDER_CONSTANT 0) (sources/modules/stitching/src/blenders.cpp:410-421)
-__global__ void k_weight_level0(const uint8_t *__restrict__ mask, int mw, int mh, size_t mp, int top, int left, float *__restrict__ w0, int bw, int bh)
+__global__ void k_weight_level0(const uint8_t *__restrict__ mask, int mw, int mh, size_t mp, int top, int left, float *__restrict__ w0,
+                                uint8_t *__restrict__ m0, int bw, int bh)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= bw || y >= bh) return;
     const int sx = x - left, sy = y - top;
-    float v = 0.f;
-    if ((unsigned)sx < (unsigned)mw && (unsigned)sy < (unsigned)mh) v = __fmul_rn((float)(1. / 255.), (float)mask[(size_t)sy * mp + sx]);
-    w0[(size_t)y * bw + x] = v;
+    uint8_t m = 0;
+    if ((unsigned)sx < (unsigned)mw && (unsigned)sy < (unsigned)mh) m = mask[(size_t)sy * mp + sx];
+    w0[(size_t)y * bw + x] = m ? __fmul_rn((float)(1. / 255.), (float)m) : 0.f;
+    m0[(size_t)y * bw + x] = m;  // k_blend recomputes W0 from this byte (same product)
 }
 
 // dst_band_weights_[k](rc) += weight (the `dst_weight += w` half of addSrcWeightKernel32F), one view at a time
@@ -439,8 +407,13 @@ struct View {
     size_t p_pitch = 0, p_frame_stride = 0;
     uint8_t *G0 = nullptr;
     size_t g0_frame_stride = 0;
-    int16_t *G[MAXL] = {};
+    int16_t *G[MAXL] = {};              // generic path (num_bands < 3) only: s16 Gaussian levels >= 1
     size_t g_frame_stride[MAXL] = {};
+    uint8_t *G2 = nullptr;              // fast path: u8 Gaussian level 2
+    size_t g2_frame_stride = 0;
+    uint8_t *M0 = nullptr;              // bordered seam mask (u8, bw x bh): W0 = M0 * (1/255)
+    std::vector<uint8_t> g2_needed;     // per k_down2 tile: computed (1) or skipped (0); host copy for vsb_debug_read
+    int d2_tiles_x = 0, d2_tiles_y = 0;
 };
 
 }  // namespace vsb
@@ -455,7 +428,15 @@ struct vsb_stitcher {
     float *dw[vsb::MAXL] = {};
     int views_inited = 0;
     vsb::View v[vsb::MAXV];
-    vsb::BlendPlan *d_plan = nullptr;
+    vsb::LgBlendPlan *d_plan = nullptr;  // generic path
+    // fast path (num_bands >= 3): static tile tables + per-frame canvas buffer
+    bool fast = false;
+    vsb::CoarseGeo cgeo;
+    size_t coarse_smem = 0;
+    uint32_t *d_blend_views = nullptr, *d_coarse_views = nullptr, *d_down2_tiles = nullptr;
+    int blend_tiles_x = 0, blend_tiles_y = 0, coarse_tiles_x = 0, coarse_tiles_y = 0, n_down2_tiles = 0;
+    int16_t *C2 = nullptr;
+    size_t c2_frame_stride = 0;
     cudaStream_t setup_stream = nullptr, mesh_stream = nullptr, io_stream = nullptr;
     cudaEvent_t last_compose = nullptr;
     bool last_compose_valid = false;
@@ -496,7 +477,7 @@ static void free_view(View &V)
     for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) cudaFree(V.mesh[b][c]);
     cudaFree(V.mesh_scratch); cudaFree(V.lut);
     for (int k = 0; k < MAXL; ++k) { cudaFree(V.weight[k]); cudaFree(V.G[k]); }
-    cudaFree(V.P); cudaFree(V.G0);
+    cudaFree(V.P); cudaFree(V.G0); cudaFree(V.G2); cudaFree(V.M0);
     if (V.mesh_ready) cudaEventDestroy(V.mesh_ready);
     V = View();
 }
@@ -519,21 +500,159 @@ static int upload_lut(vsb_stitcher *s, View &V)
 
 static int build_plan(vsb_stitcher *s)
 {
-    BlendPlan h;
+    LgBlendPlan h;
     std::memset(&h, 0, sizeof(h));
     h.n_views = s->cfg.num_views; h.nb = s->nb;
     h.out_w = s->roi_final[2]; h.out_h = s->roi_final[3];
     for (int k = 0; k <= s->nb; ++k) { h.cw[k] = s->cw[k]; h.ch[k] = s->ch[k]; h.dw[k] = s->dw[k]; }
     for (int i = 0; i < s->cfg.num_views; ++i) {
         const View &V = s->v[i];
-        BlendView &B = h.v[i];
+        LgBlendView &B = h.v[i];
         B.g0 = V.G0; B.g0_frame_stride = V.g0_frame_stride;
         for (int k = 0; k <= s->nb; ++k) { B.g[k] = V.G[k]; B.w[k] = V.weight[k]; B.g_frame_stride[k] = V.g_frame_stride[k]; }
         B.x_tl = V.x_tl; B.y_tl = V.y_tl; B.bw = V.bw; B.bh = V.bh;
     }
-    if (!s->d_plan) CK(cudaMalloc(&s->d_plan, sizeof(BlendPlan)));
+    if (!s->d_plan) CK(cudaMalloc(&s->d_plan, sizeof(LgBlendPlan)));
     CK(cudaMemcpyAsync(s->d_plan, &h, sizeof(h), cudaMemcpyHostToDevice, s->setup_stream));
     CK(cudaStreamSynchronize(s->setup_stream));
+    return VSB_OK;
+}
+
+
+// ---- fast path (num_bands >= 3): static tables -------------------------------------------------------------------
+static inline int fdiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }  // floor(v / 2)
+
+// region offsets of k_coarse, relative to the tile origin at each level (see vsb_blend_kernels.cuh)
+static void coarse_geometry(int nb, CoarseGeo &g)
+{
+    std::memset(&g, 0, sizeof(g));
+    const int nlev = nb - 1;
+    g.nlev = nlev;
+    int a_lo[C_MAXJ], a_hi[C_MAXJ], g_lo[C_MAXJ], g_hi[C_MAXJ];
+    a_lo[0] = 0; a_hi[0] = CT - 1;
+    for (int j = 1; j < nlev; ++j) { a_lo[j] = fdiv2(a_lo[j - 1]) - 1; a_hi[j] = fdiv2(a_hi[j - 1]) + 1; }
+    g_lo[nlev - 1] = a_lo[nlev - 1]; g_hi[nlev - 1] = a_hi[nlev - 1];
+    for (int j = nlev - 2; j >= 0; --j) { g_lo[j] = std::min(a_lo[j], 2 * g_lo[j + 1] - 2); g_hi[j] = std::max(a_hi[j], 2 * g_hi[j + 1] + 2); }
+    g_lo[0] = -(int)align_up((size_t)(-g_lo[0]), 4);
+    int a_total = 0, g_total = 0;
+    for (int j = 0; j < nlev; ++j) {
+        g.a_lo[j] = a_lo[j]; g.a_n[j] = a_hi[j] - a_lo[j] + 1;
+        g.g_lo[j] = g_lo[j]; g.g_n[j] = g_hi[j] - g_lo[j] + 1;
+        g.g_pitch[j] = (int)align_up((size_t)g.g_n[j], 4);
+        g.a_off[j] = a_total; a_total += (int)align_up((size_t)g.a_n[j] * g.a_n[j], 8);
+        g.g_off[j] = g_total; g_total += (int)align_up((size_t)g.g_pitch[j] * g.g_n[j], 16);
+    }
+    g.a_total = a_total;
+}
+static size_t coarse_smem_bytes(const CoarseGeo &g)
+{
+    const int j = g.nlev - 1;
+    return (size_t)g.a_total * 2 + g.g_off[j] + align_up((size_t)g.g_pitch[j] * g.g_n[j], 16);
+}
+
+struct HostWeights {  // nonzero structure of one view's static weight pyramid
+    std::vector<std::vector<uint8_t>> nz;  // [level][h * w]: weight != 0
+    int w[MAXL], h[MAXL];
+    bool any(int k, int x0, int y0, int x1, int y1) const  // half-open plane rect, clipped here
+    {
+        x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, w[k]); y1 = std::min(y1, h[k]);
+        for (int y = y0; y < y1; ++y) {
+            const uint8_t *r = nz[k].data() + (size_t)y * w[k];
+            for (int x = x0; x < x1; ++x) if (r[x]) return true;
+        }
+        return false;
+    }
+};
+
+static int build_fast_plan(vsb_stitcher *s)
+{
+    const int n = s->cfg.num_views, nb = s->nb, F = s->cfg.max_batch;
+    // nonzero structure of every weight level (read back once; calibration time)
+    std::vector<HostWeights> hw(n);
+    for (int i = 0; i < n; ++i) {
+        const View &V = s->v[i];
+        hw[i].nz.resize(nb + 1);
+        for (int k = 0; k <= nb; ++k) {
+            const int w = V.bw >> k, h = V.bh >> k;
+            hw[i].w[k] = w; hw[i].h[k] = h;
+            std::vector<float> tmp((size_t)w * h);
+            CK(cudaMemcpy(tmp.data(), V.weight[k], tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            hw[i].nz[k].resize(tmp.size());
+            for (size_t j = 0; j < tmp.size(); ++j) hw[i].nz[k][j] = tmp[j] != 0.f;
+        }
+    }
+    // ---- k_blend: views with level-0 / level-1 weight per 64 x 32 canvas tile
+    s->blend_tiles_x = (s->cw[0] + BL_TW - 1) / BL_TW; s->blend_tiles_y = (s->ch[0] + BL_TH - 1) / BL_TH;
+    std::vector<uint32_t> bviews((size_t)s->blend_tiles_x * s->blend_tiles_y, 0);
+    for (int ty = 0; ty < s->blend_tiles_y; ++ty)
+        for (int tx = 0; tx < s->blend_tiles_x; ++tx)
+            for (int i = 0; i < n; ++i) {
+                const View &V = s->v[i];
+                const int x0 = tx * BL_TW - V.x_tl, y0 = ty * BL_TH - V.y_tl;
+                const int x1 = fdiv2(tx * BL_TW) - 1 - (V.x_tl >> 1), y1 = fdiv2(ty * BL_TH) - 1 - (V.y_tl >> 1);
+                if (hw[i].any(0, x0, y0, x0 + BL_TW, y0 + BL_TH) || hw[i].any(1, x1, y1, x1 + BL_R1W, y1 + BL_R1H))
+                    bviews[(size_t)ty * s->blend_tiles_x + tx] |= 1u << i;
+            }
+    // ---- k_coarse: views with weight at any level >= 2 per 64 x 64 level-2 canvas tile
+    coarse_geometry(nb, s->cgeo);
+    s->coarse_smem = coarse_smem_bytes(s->cgeo);
+    s->coarse_tiles_x = (s->cw[2] + CT - 1) / CT; s->coarse_tiles_y = (s->ch[2] + CT - 1) / CT;
+    std::vector<uint32_t> cviews((size_t)s->coarse_tiles_x * s->coarse_tiles_y, 0);
+    for (int ty = 0; ty < s->coarse_tiles_y; ++ty)
+        for (int tx = 0; tx < s->coarse_tiles_x; ++tx)
+            for (int i = 0; i < n; ++i) {
+                const View &V = s->v[i];
+                bool any = false;
+                for (int j = 0; j < s->cgeo.nlev && !any; ++j) {
+                    const int k = 2 + j;
+                    const int x0 = ((tx * CT) >> j) + s->cgeo.a_lo[j] - (V.x_tl >> k), y0 = ((ty * CT) >> j) + s->cgeo.a_lo[j] - (V.y_tl >> k);
+                    any = hw[i].any(k, x0, y0, x0 + s->cgeo.a_n[j], y0 + s->cgeo.a_n[j]);
+                }
+                if (any) cviews[(size_t)ty * s->coarse_tiles_x + tx] |= 1u << i;
+            }
+    // ---- k_down2: the G2 tiles some k_coarse / k_blend tile reads
+    std::vector<uint32_t> d2tiles;
+    for (int i = 0; i < n; ++i) {
+        View &V = s->v[i];
+        const int w2 = V.bw >> 2, h2 = V.bh >> 2;
+        V.d2_tiles_x = (w2 + D2_TW - 1) / D2_TW; V.d2_tiles_y = (h2 + D2_TH - 1) / D2_TH;
+        V.g2_needed.assign((size_t)V.d2_tiles_x * V.d2_tiles_y, 0);
+        auto mark = [&](int x0, int y0, int x1, int y1) {  // half-open rect in level-2 plane coordinates
+            x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, w2); y1 = std::min(y1, h2);
+            if (x0 >= x1 || y0 >= y1) return;
+            for (int ty = y0 / D2_TH; ty <= (y1 - 1) / D2_TH; ++ty)
+                for (int tx = x0 / D2_TW; tx <= (x1 - 1) / D2_TW; ++tx) V.g2_needed[(size_t)ty * V.d2_tiles_x + tx] = 1;
+        };
+        for (int ty = 0; ty < s->coarse_tiles_y; ++ty)
+            for (int tx = 0; tx < s->coarse_tiles_x; ++tx)
+                if (cviews[(size_t)ty * s->coarse_tiles_x + tx] >> i & 1) {
+                    // the region is read through BORDER_REFLECT_101 (at most 2 samples beyond the loaded range fold back inside it)
+                    const int x0 = tx * CT + s->cgeo.g_lo[0] - (V.x_tl >> 2), y0 = ty * CT + s->cgeo.g_lo[0] - (V.y_tl >> 2);
+                    mark(x0, y0, x0 + s->cgeo.g_pitch[0], y0 + s->cgeo.g_n[0]);
+                }
+        for (int ty = 0; ty < s->blend_tiles_y; ++ty)
+            for (int tx = 0; tx < s->blend_tiles_x; ++tx)
+                if (bviews[(size_t)ty * s->blend_tiles_x + tx] >> i & 1) {
+                    const int x0 = fdiv2(fdiv2(tx * BL_TW)) - 2 - (V.x_tl >> 2), y0 = fdiv2(fdiv2(ty * BL_TH)) - 2 - (V.y_tl >> 2);
+                    mark(x0, y0, x0 + BL_R2W, y0 + BL_R2H);
+                }
+        for (int ty = 0; ty < V.d2_tiles_y; ++ty)
+            for (int tx = 0; tx < V.d2_tiles_x; ++tx)
+                if (V.g2_needed[(size_t)ty * V.d2_tiles_x + tx]) d2tiles.push_back((uint32_t)i | ((uint32_t)tx << 8) | ((uint32_t)ty << 20));
+    }
+    s->n_down2_tiles = (int)d2tiles.size();
+    cudaFree(s->d_blend_views); cudaFree(s->d_coarse_views); cudaFree(s->d_down2_tiles); cudaFree(s->C2);
+    s->d_blend_views = s->d_coarse_views = s->d_down2_tiles = nullptr; s->C2 = nullptr;
+    CK(cudaMalloc(&s->d_blend_views, bviews.size() * 4));
+    CK(cudaMalloc(&s->d_coarse_views, cviews.size() * 4));
+    CK(cudaMalloc(&s->d_down2_tiles, std::max<size_t>(d2tiles.size(), 1) * 4));
+    CK(cudaMemcpy(s->d_blend_views, bviews.data(), bviews.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->d_coarse_views, cviews.data(), cviews.size() * 4, cudaMemcpyHostToDevice));
+    if (!d2tiles.empty()) CK(cudaMemcpy(s->d_down2_tiles, d2tiles.data(), d2tiles.size() * 4, cudaMemcpyHostToDevice));
+    s->c2_frame_stride = (size_t)3 * s->cw[2] * s->ch[2];
+    CK(cudaMalloc(&s->C2, s->c2_frame_stride * sizeof(int16_t) * F));
+    if (s->coarse_smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(k_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->coarse_smem));
     return VSB_OK;
 }
 
@@ -551,7 +670,9 @@ static int finalize(vsb_stitcher *s)
     }
     int r = check_launch("k_accum_weight");
     if (r != VSB_OK) return r;
-    r = build_plan(s);
+    CK(cudaStreamSynchronize(s->setup_stream));
+    s->fast = s->nb >= 3;
+    r = s->fast ? build_fast_plan(s) : build_plan(s);
     if (r != VSB_OK) return r;
     s->finalized = true;
     return VSB_OK;
@@ -609,6 +730,84 @@ static void fill_tilemap(TileMap &tm, int n, const int *w, const int *h, int til
     }
 }
 
+
+// K3: G0 -> G2 for the needed tiles of views [v0, v1)
+static int launch_down2(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStream_t st)
+{
+    Down2Params p;
+    std::memset(&p, 0, sizeof(p));
+    for (int i = 0; i < s->cfg.num_views; ++i) {
+        const View &V = s->v[i];
+        p.v[i].g0 = V.G0; p.v[i].g2 = V.G2; p.v[i].g0_fs = V.g0_frame_stride; p.v[i].g2_fs = V.g2_frame_stride;
+        p.v[i].bw = V.bw; p.v[i].bh = V.bh;
+    }
+    // the tile list is sorted by view: launch the sub-range that belongs to [v0, v1)
+    int first = 0, count = 0;
+    double bytes = 0;
+    for (int i = 0; i < s->cfg.num_views; ++i) {
+        int nt = 0;
+        for (uint8_t b : s->v[i].g2_needed) nt += b;
+        if (i < v0) first += nt;
+        else if (i < v1) { count += nt; bytes += (double)nt * 3 * (16.0 * D2_TW * D2_TH + D2_TW * D2_TH); }
+    }
+    p.tiles = s->d_down2_tiles + first;
+    if (count > 0) k_down2<<<dim3(count, 3, n_frames), D2_THREADS, 0, st>>>(p);
+    ++s->launches;
+    prof_stage(s, st, "down2", bytes * n_frames);  // G0 of the needed tiles in once + G2 out once
+    return check_launch("k_down2");
+}
+
+// K4 + K5
+static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, size_t out_pitch, cudaStream_t st)
+{
+    const int n = s->cfg.num_views, nb = s->nb;
+    {
+        CoarseParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.geo = s->cgeo;
+        for (int j = 0; j < s->cgeo.nlev; ++j) { p.cw[j] = s->cw[2 + j]; p.ch[j] = s->ch[2 + j]; p.dw[j] = s->dw[2 + j]; }
+        p.c2 = s->C2; p.c2_fs = s->c2_frame_stride; p.tile_views = s->d_coarse_views; p.tiles_x = s->coarse_tiles_x;
+        double bytes = 0;
+        for (int i = 0; i < n; ++i) {
+            const View &V = s->v[i];
+            CoarseView &C = p.v[i];
+            C.g2 = V.G2; C.g2_fs = V.g2_frame_stride;
+            for (int j = 0; j < s->cgeo.nlev; ++j) C.w[j] = V.weight[2 + j];
+            C.x_tl = V.x_tl; C.y_tl = V.y_tl; C.bw = V.bw; C.bh = V.bh;
+            int nt = 0;
+            for (uint8_t b : V.g2_needed) nt += b;
+            bytes += 3.0 * nt * D2_TW * D2_TH;
+        }
+        bytes += 6.0 * s->cw[2] * s->ch[2];  // needed G2 in once + C2 (s16 x 3) out once
+        k_coarse<<<dim3(s->coarse_tiles_x * s->coarse_tiles_y, 3, n_frames), C_THREADS, s->coarse_smem, st>>>(p);
+        ++s->launches;
+        prof_stage(s, st, "coarse", bytes * n_frames);
+    }
+    {
+        BlendParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.nb = nb; p.tiles_x = s->blend_tiles_x;
+        p.cw0 = s->cw[0]; p.ch0 = s->ch[0]; p.cw1 = s->cw[1]; p.ch1 = s->ch[1]; p.cw2 = s->cw[2]; p.ch2 = s->ch[2];
+        p.out_w = s->roi_final[2]; p.out_h = s->roi_final[3];
+        p.c2 = s->C2; p.c2_fs = s->c2_frame_stride; p.tile_views = s->d_blend_views;
+        double bytes = 6.0 * s->roi_final[2] * s->roi_final[3] + 6.0 * s->cw[2] * s->ch[2];
+        for (int i = 0; i < n; ++i) {
+            const View &V = s->v[i];
+            BlendView &B = p.v[i];
+            B.g0 = V.G0; B.g2 = V.G2; B.m0 = V.M0; B.w1 = V.weight[1]; B.g0_fs = V.g0_frame_stride; B.g2_fs = V.g2_frame_stride;
+            B.x_tl = V.x_tl; B.y_tl = V.y_tl; B.bw = V.bw; B.bh = V.bh;
+            bytes += 3.0 * V.bw * V.bh + 3.0 * (V.bw >> 2) * (V.bh >> 2);
+        }
+        OutPtrs o;
+        std::memset(&o, 0, sizeof(o));
+        for (int f = 0; f < n_frames; ++f) o.out[f] = d_outs[f];
+        k_blend<<<dim3(s->blend_tiles_x, s->blend_tiles_y, n_frames), BL_THREADS, 0, st>>>(p, o, out_pitch);
+        ++s->launches;
+        prof_stage(s, st, "blend", bytes * n_frames);  // G0 + G2 of every view once, C2 once, CV_16SC3 pano out once
+    }
+    return check_launch("k_coarse / k_blend");
+}
+
 // remap stages + pyramid for views [v0, v1) of n_frames frames
 static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch, cudaStream_t st)
 {
@@ -653,6 +852,7 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
         for (int j = 0; j < n; ++j) { const View &V = s->v[v0 + j]; bytes += 3.0 * V.roi_w * V.roi_h + 3.0 * V.bw * V.bh; }
         prof_stage(s, st, "remap_stage2", bytes * n_frames);
     }
+    if (s->fast) return launch_down2(s, v0, v1, n_frames, st);
     for (int k = 0; k < s->nb; ++k) {
         PyrParams p;
         std::memset(&p, 0, sizeof(p));
@@ -683,11 +883,12 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
 
 static int launch_back(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, size_t out_pitch, cudaStream_t st)
 {
+    if (s->fast) return launch_back_fast(s, n_frames, d_outs, out_pitch, st);
     OutPtrs o;
     std::memset(&o, 0, sizeof(o));
     for (int f = 0; f < n_frames; ++f) o.out[f] = d_outs[f];
-    const dim3 g((s->cw[0] + BL_TW - 1) / BL_TW, (s->ch[0] + BL_TH - 1) / BL_TH, n_frames);
-    k_blend_collapse<<<g, BL_THREADS, 0, st>>>(s->d_plan, o, out_pitch);
+    const dim3 g((s->cw[0] + LG_TW - 1) / LG_TW, (s->ch[0] + LG_TH - 1) / LG_TH, n_frames);
+    k_legacy_blend_collapse<<<g, LG_THREADS, 0, st>>>(s->d_plan, o, out_pitch);
     ++s->launches;
     double bytes = 6.0 * s->roi_final[2] * s->roi_final[3];  // every Gaussian level of every view once + the CV_16SC3 pano once
     for (int i = 0; i < s->cfg.num_views; ++i) {
@@ -696,7 +897,7 @@ static int launch_back(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, si
         for (int k = 1; k <= s->nb; ++k) bytes += 6.0 * (V.bw >> k) * (V.bh >> k);
     }
     prof_stage(s, st, "blend_collapse", bytes * n_frames);
-    return check_launch("k_blend_collapse");
+    return check_launch("k_legacy_blend_collapse");
 }
 
 static int note_compose_done(vsb_stitcher *s, cudaStream_t st)
@@ -747,6 +948,7 @@ int vsb_destroy(vsb_stitcher *s)
     for (int i = 0; i < MAXV; ++i) free_view(s->v[i]);
     for (int k = 0; k < MAXL; ++k) cudaFree(s->dw[k]);
     cudaFree(s->d_plan);
+    cudaFree(s->d_blend_views); cudaFree(s->d_coarse_views); cudaFree(s->d_down2_tiles); cudaFree(s->C2);
     cudaFree(s->stage_src); cudaFree(s->stage_out);
     cudaFreeHost(s->pin_src); cudaFreeHost(s->pin_out);
     if (s->setup_stream) cudaStreamDestroy(s->setup_stream);
@@ -839,7 +1041,8 @@ int vsb_init_view(vsb_stitcher *s, int i, const uint8_t *mask, int mw, int mh, s
     }
     const dim3 b(32, 8);
     CK(cudaMalloc(&V.weight[0], sizeof(float) * width * height));
-    k_weight_level0<<<grid2d(width, height, b), b, 0, s->setup_stream>>>(on_device ? mask : d_mask, mw, mh, d_pitch, V.top, V.left, V.weight[0], width, height);
+    CK(cudaMalloc(&V.M0, (size_t)width * height));
+    k_weight_level0<<<grid2d(width, height, b), b, 0, s->setup_stream>>>(on_device ? mask : d_mask, mw, mh, d_pitch, V.top, V.left, V.weight[0], V.M0, width, height);
     for (int k = 0; k < nb; ++k) {
         const int w = width >> k, h = height >> k;
         CK(cudaMalloc(&V.weight[k + 1], sizeof(float) * (w / 2) * (h / 2)));
@@ -858,9 +1061,15 @@ int vsb_init_view(vsb_stitcher *s, int i, const uint8_t *mask, int mw, int mh, s
     CK(cudaMalloc(&V.P, V.p_frame_stride * F));
     V.g0_frame_stride = (size_t)3 * width * height;
     CK(cudaMalloc(&V.G0, V.g0_frame_stride * F));
-    for (int k = 1; k <= nb; ++k) {
-        V.g_frame_stride[k] = (size_t)3 * (width >> k) * (height >> k);
-        CK(cudaMalloc(&V.G[k], sizeof(int16_t) * V.g_frame_stride[k] * F));
+    if (nb >= 3) {  // fast path keeps only G0 and G2 (u8)
+        V.g2_frame_stride = (size_t)3 * (width >> 2) * (height >> 2);
+        CK(cudaMalloc(&V.G2, V.g2_frame_stride * F));
+        CK(cudaMemsetAsync(V.G2, 0, V.g2_frame_stride * F, s->setup_stream));  // skipped tiles stay defined
+    } else {
+        for (int k = 1; k <= nb; ++k) {
+            V.g_frame_stride[k] = (size_t)3 * (width >> k) * (height >> k);
+            CK(cudaMalloc(&V.G[k], sizeof(int16_t) * V.g_frame_stride[k] * F));
+        }
     }
     V.map_pitch = align_up((size_t)mw * 4, 16);
     CK(cudaEventCreateWithFlags(&V.mesh_ready, cudaEventDisableTiming));
@@ -1119,9 +1328,11 @@ int vsb_debug_read(vsb_stitcher *s, int what, int view, int level, int frame, vo
         REQ(bytes == (size_t)w * h * 6, VSB_ERR_INVALID, "debug_read: size mismatch");
         int16_t *d_tmp = nullptr;
         CK(cudaMalloc(&d_tmp, bytes));
-        const void *in = level == 0 ? (const void *)(V.G0 + V.g0_frame_stride * frame) : (const void *)(V.G[level] + V.g_frame_stride[level] * frame);
+        if (s->fast && level != 0 && level != 2) { cudaFree(d_tmp); return fail(VSB_ERR_STATE, "debug_read: Gaussian level %d is never materialised (only 0 and 2 are)", level); }
+        const void *in = level == 0 ? (const void *)(V.G0 + V.g0_frame_stride * frame)
+                         : (s->fast ? (const void *)(V.G2 + V.g2_frame_stride * frame) : (const void *)(V.G[level] + V.g_frame_stride[level] * frame));
         const dim3 b(32, 8);
-        k_planar_to_interleaved_s16<<<grid2d(w, h, b), b>>>(in, level == 0, w, h, d_tmp);
+        k_planar_to_interleaved_s16<<<grid2d(w, h, b), b>>>(in, level == 0 || s->fast, w, h, d_tmp);
         cudaError_t e = cudaMemcpy(h_dst, d_tmp, bytes, cudaMemcpyDeviceToHost);
         cudaFree(d_tmp);
         return check_cuda(e, "debug_read level");
@@ -1141,6 +1352,15 @@ int vsb_debug_read(vsb_stitcher *s, int what, int view, int level, int frame, vo
         REQ(buf >= 0, VSB_ERR_STATE, "debug_read: no mesh set");
         REQ(bytes == (size_t)V.roi_w * V.roi_h * 4, VSB_ERR_INVALID, "debug_read: size mismatch");
         return check_cuda(cudaMemcpy2D(h_dst, (size_t)V.roi_w * 4, V.mesh[buf][what - 4], V.map_pitch, (size_t)V.roi_w * 4, V.roi_h, cudaMemcpyDeviceToHost), "debug_read mesh");
+    }
+    case 6: {  // which level-2 samples k_down2 computes (1) / skips because no tile reads them (0)
+        REQ(s->fast, VSB_ERR_STATE, "debug_read: the generic path computes every level");
+        const int w = V.bw >> 2, h = V.bh >> 2;
+        REQ(bytes == (size_t)w * h, VSB_ERR_INVALID, "debug_read: size mismatch");
+        uint8_t *o = (uint8_t *)h_dst;
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) o[(size_t)y * w + x] = V.g2_needed[(size_t)(y / D2_TH) * V.d2_tiles_x + x / D2_TW];
+        return VSB_OK;
     }
     default:
         return fail(VSB_ERR_INVALID, "debug_read: unknown selector %d", what);
