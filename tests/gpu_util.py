@@ -87,6 +87,12 @@ class GpuRig:
         bw, bh = (g["x_br"] - g["x_tl"]) >> k, (g["y_br"] - g["y_tl"]) >> k
         return self.read(1, i, k, (bh, bw, 3), np.int16, frame)
 
+    def g0_computed(self, i):
+        """1 where k_remap_stage2 computes the bordered level-0 sample, 0 where its tile is skipped (nothing reads it)."""
+        g = self.geom[i]
+        bw, bh = g["x_br"] - g["x_tl"], g["y_br"] - g["y_tl"]
+        return self.read(7, i, 0, (bh, bw), np.uint8)
+
     def g2_computed(self, i):
         """1 where k_down2 computes the level-2 sample, 0 where its tile is skipped (nothing reads it)."""
         g = self.geom[i]

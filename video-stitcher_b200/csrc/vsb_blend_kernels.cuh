@@ -94,6 +94,39 @@ __device__ __forceinline__ void pyr_up_row8(const Acc &a, int x0, int y, int n_x
     }
 }
 
+
+// pyrUp of the 2x2 quad {x0, x0+1} x {y0, y0+1} with x0 and y0 ODD (x0 = -1 allowed: only the valid samples are used).
+// out[0] = (x0, y0), out[1] = (x0+1, y0), out[2] = (x0, y0+1), out[3] = (x0+1, y0+1); same integers as pyr_up_sample,
+// the 3x3 source neighbourhood is read once and no lane diverges on parity.
+template <typename Acc>
+__device__ __forceinline__ void pyr_up_quad_odd(const Acc &a, int x0, int y0, int n_x, int n_y, int out[4])
+{
+    const int m = x0 >> 1, n = y0 >> 1;
+    const int c0 = up_idx(m, n_x), c1 = up_idx(m + 1, n_x), c2 = up_idx(m + 2, n_x);
+    int h[3], p[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int r = up_idx(n + i, n_y);
+        const int s0 = a(c0, r), s1 = a(c1, r), s2 = a(c2, r);
+        h[i] = s0 + 6 * s1 + s2;
+        p[i] = s0 + s1;
+    }
+    out[0] = sat_s16(rhe_shift<6>(16 * (p[0] + p[1])));
+    out[1] = sat_s16(rhe_shift<6>(4 * (h[0] + h[1])));
+    out[2] = sat_s16(rhe_shift<6>(4 * (p[0] + 6 * p[1] + p[2])));
+    out[3] = sat_s16(rhe_shift<6>(h[0] + 6 * h[1] + h[2]));
+}
+
+// (short)(acc / (weight_sum + WEIGHT_EPS)) of normalizeUsingWeightKernel32F; `acc` is the wrapped 16-bit accumulator.
+// For weight_sum == 1 (one view, full weight: most of the panorama) the quotient acc / 1.00001f truncates to
+// acc - sign(acc) for every 16-bit acc (checked exhaustively, tests/test_abi_host.py), which skips the IEEE division.
+__device__ __forceinline__ int normalize_s16(int acc, float dw)
+{
+    const int a = (int)(short)acc;
+    if (dw == 1.0f) return a - (a > 0) + (a < 0);
+    return rz_s16(__fdiv_rn((float)a, __fadd_rn(dw, 1e-5f)));
+}
+
 // Loads one 4-byte word of a u8 plane row whose column gx may fall outside [0, w): BORDER_REFLECT_101 per byte there.
 __device__ __forceinline__ unsigned load_word_r101(const uint8_t *__restrict__ row, int gx, int w)
 {
@@ -181,25 +214,73 @@ __global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Do
     }
 }
 
+// ============================================================================================================ k_down1
+// One more pyrDown level on u8 planes (levels 2 -> 3 -> ... -> nb): these planes are 1/16 of the image and smaller, so a
+// plain one-thread-per-sample kernel over every view is enough (taps come from L1/L2; interior samples skip the reflection).
+constexpr int D1_TX = 32, D1_TY = 8;
+struct Down1View {
+    const uint8_t *src;
+    uint8_t *dst;
+    size_t src_fs, dst_fs;
+    int w, h;  // source plane size
+};
+struct Down1Params {
+    int n;
+    int start[MAXV + 1];  // prefix sums of tiles per view
+    int tiles_x[MAXV];
+    Down1View v[MAXV];
+};
+
+__global__ void __launch_bounds__(D1_TX *D1_TY) k_down1(const __grid_constant__ Down1Params P)
+{
+    int vi = 0;
+    while (vi + 1 < P.n && (int)blockIdx.x >= P.start[vi + 1]) ++vi;
+    const Down1View &V = P.v[vi];
+    const int tl = blockIdx.x - P.start[vi];
+    const int x = (tl % P.tiles_x[vi]) * D1_TX + threadIdx.x, y = (tl / P.tiles_x[vi]) * D1_TY + threadIdx.y;
+    const int ws = V.w, hs = V.h, wd = ws >> 1, hd = hs >> 1;
+    if (x >= wd || y >= hd) return;
+    const int c = blockIdx.z, f = blockIdx.y;
+    const uint8_t *src = V.src + (size_t)f * V.src_fs + (size_t)c * ws * hs;
+    int acc = 0;
+    if (2 * y - 2 >= 0 && 2 * y + 2 < hs && 2 * x - 2 >= 0 && 2 * x + 2 < ws) {
+        const uint8_t *rp = src + (size_t)(2 * y - 2) * ws + (2 * x - 2);
+#pragma unroll
+        for (int e = 0; e < 5; ++e, rp += ws)
+            acc += (e == 2 ? 6 : ((e & 1) ? 4 : 1)) * ((int)ldg_u8(rp) + 4 * (int)ldg_u8(rp + 1) + 6 * (int)ldg_u8(rp + 2) + 4 * (int)ldg_u8(rp + 3) + (int)ldg_u8(rp + 4));
+    } else {
+        int cc[5];
+#pragma unroll
+        for (int e = 0; e < 5; ++e) cc[e] = r101_idx(2 * x - 2 + e, ws);
+#pragma unroll
+        for (int e = 0; e < 5; ++e) {
+            const uint8_t *rp = src + (size_t)r101_idx(2 * y - 2 + e, hs) * ws;
+            acc += (e == 2 ? 6 : ((e & 1) ? 4 : 1)) * ((int)ldg_u8(rp + cc[0]) + 4 * (int)ldg_u8(rp + cc[1]) + 6 * (int)ldg_u8(rp + cc[2]) + 4 * (int)ldg_u8(rp + cc[3]) + (int)ldg_u8(rp + cc[4]));
+        }
+    }
+    V.dst[(size_t)f * V.dst_fs + ((size_t)c * hd + y) * wd + x] = (uint8_t)rhe_shift<8>(acc);
+}
+
 // ========================================================================================================== k_coarse
 // Levels 2..nb for one 64x64 (level-2) canvas tile of one colour plane: for every view that has weight there, the
-// Gaussian levels 3..nb, the Laplacian bands, the truncating weighted add into shared-memory accumulators; then the
+// Laplacian bands from the stored Gaussian levels, the truncating weighted add into shared-memory accumulators; then the
 // normalisation by the static weight sums and the collapse nb -> 2.  Output: C2 = D2 + up(D3 + up(... Dnb)).
+// Every level is processed as 2x2 quads (one thread each): the 3x3 neighbourhood of the coarser level is read once and
+// no lane diverges on the pyrUp phase.
 constexpr int CT = 64, C_MAXJ = 6, C_THREADS = 256;
 
 struct CoarseGeo {  // tile-independent offsets, relative to (X0 >> j, Y0 >> j); same for x and y (square tiles)
     int nlev;                         // levels 2 .. nb  ->  nb - 1
-    int a_lo[C_MAXJ], a_n[C_MAXJ];    // accumulation / collapse region of level 2 + j
-    int g_lo[C_MAXJ], g_n[C_MAXJ];    // Gaussian region of level 2 + j (g_lo[0] is a multiple of 4)
-    int a_off[C_MAXJ], g_off[C_MAXJ]; // shared-memory offsets: A in int16 units, G in bytes (after the A area)
-    int g_pitch[C_MAXJ];              // bytes (g_pitch[0] is a multiple of 4)
+    int a_lo[C_MAXJ], a_n[C_MAXJ];    // region of level 2 + j the tile accumulates / collapses (a_n even)
+    int g_lo[C_MAXJ], g_n[C_MAXJ];    // host only: support of the tile in Gaussian level 2 + j (marks the G2 tiles k_down2 must compute)
+    int a_off[C_MAXJ], g_off[C_MAXJ]; // shared-memory offsets: A in int16 units, G (u8 copy of the a-region) in bytes after A
     int a_total;                      // int16 elements
 };
 struct CoarseView {
-    const uint8_t *g2;
-    const float *w[C_MAXJ];  // static weight level 2 + j
-    size_t g2_fs;
-    int x_tl, y_tl, bw, bh;  // level-0 canvas origin and size of the bordered view
+    const uint8_t *g[C_MAXJ];  // Gaussian level 2 + j, frame 0
+    const float *w[C_MAXJ];    // static weight level 2 + j
+    size_t g_fs[C_MAXJ];
+    int x_tl, y_tl, bw, bh;    // level-0 canvas origin and size of the bordered view
 };
 struct CoarseParams {
     CoarseGeo geo;
@@ -209,8 +290,31 @@ struct CoarseParams {
     size_t c2_fs;                // elements
     const uint32_t *tile_views;  // bit v: view v has weight in this tile (any level >= 2)
     int tiles_x;
-    CoarseView v[MAXV];
+    const CoarseView *views;     // device array [n_views]
 };
+
+// pyrUp of the 2x2 quad {x0, x0+1} x {y0, y0+1} (any parity; uniform per call site in practice) from a plane accessor.
+// out[0] = (x0, y0), out[1] = (x0+1, y0), out[2] = (x0, y0+1), out[3] = (x0+1, y0+1); same integers as pyr_up_sample.
+template <typename Acc>
+__device__ __forceinline__ void pyr_up_quad(const Acc &a, int x0, int y0, int n_x, int n_y, int out[4])
+{
+    const int px = x0 & 1, py = y0 & 1;
+    const int cb = (x0 >> 1) - 1 + px, rb = (y0 >> 1) - 1 + py;
+    const int c0 = up_idx(cb, n_x), c1 = up_idx(cb + 1, n_x), c2 = up_idx(cb + 2, n_x);
+    int h0[3], h1[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int r = up_idx(rb + i, n_y);
+        const int s0 = a(c0, r), s1 = a(c1, r), s2 = a(c2, r);
+        const int tri = s0 + 6 * s1 + s2;
+        h0[i] = px ? 4 * (s0 + s1) : tri;
+        h1[i] = px ? tri : 4 * (s1 + s2);
+    }
+    out[0] = sat_s16(rhe_shift<6>(py ? 4 * (h0[0] + h0[1]) : h0[0] + 6 * h0[1] + h0[2]));
+    out[1] = sat_s16(rhe_shift<6>(py ? 4 * (h1[0] + h1[1]) : h1[0] + 6 * h1[1] + h1[2]));
+    out[2] = sat_s16(rhe_shift<6>(py ? h0[0] + 6 * h0[1] + h0[2] : 4 * (h0[1] + h0[2])));
+    out[3] = sat_s16(rhe_shift<6>(py ? h1[0] + 6 * h1[1] + h1[2] : 4 * (h1[1] + h1[2])));
+}
 
 __global__ void __launch_bounds__(C_THREADS) k_coarse(const __grid_constant__ CoarseParams P)
 {
@@ -225,113 +329,83 @@ __global__ void __launch_bounds__(C_THREADS) k_coarse(const __grid_constant__ Co
     while (views) {
         const int vi = __ffs(views) - 1;
         views &= views - 1;
-        const CoarseView &V = P.v[vi];
+        const CoarseView &V = P.views[vi];
         __syncthreads();
-        {   // G2 region of this view (words; BORDER_REFLECT_101 relative to the view's plane)
-            const int w = V.bw >> 2, h = V.bh >> 2, ox = V.x_tl >> 2, oy = V.y_tl >> 2;
-            const uint8_t *g2 = V.g2 + (size_t)f * V.g2_fs + (size_t)c * w * h;
-            const int n = Gm.g_n[0], words = Gm.g_pitch[0] >> 2;
-            const int vx0 = X0 + Gm.g_lo[0] - ox, vy0 = Y0 + Gm.g_lo[0] - oy;
-            unsigned *dst = (unsigned *)(G + Gm.g_off[0]);
+        for (int j = 0; j < nlev; ++j) {  // copy of the a-region of Gaussian level 2 + j (coordinates clamped into the plane)
+            const int k = 2 + j, w = V.bw >> k, h = V.bh >> k, n = Gm.a_n[j];
+            const uint8_t *g = V.g[j] + (size_t)f * V.g_fs[j] + (size_t)c * w * h;
+            const int vx0 = (X0 >> j) + Gm.a_lo[j] - (V.x_tl >> k), vy0 = (Y0 >> j) + Gm.a_lo[j] - (V.y_tl >> k);
+            uint8_t *dst = G + Gm.g_off[j];
             for (int r = warp; r < n; r += C_THREADS / 32) {
-                const uint8_t *row = g2 + (size_t)r101_idx(vy0 + r, h) * w;
-                for (int m = lane; m < words; m += 32) dst[r * words + m] = load_word_r101(row, vx0 + 4 * m, w);
+                const uint8_t *row = g + (size_t)min(max(vy0 + r, 0), h - 1) * w;
+                for (int q = lane; q < n; q += 32) dst[r * n + q] = (uint8_t)ldg_u8(row + min(max(vx0 + q, 0), w - 1));
             }
         }
         __syncthreads();
-        for (int j = 0; j + 1 < nlev; ++j) {  // G(j+1) = pyrDown(G(j)) at in-plane positions of its region
-            const int k = 2 + j;
-            const int ws = V.bw >> k, hs = V.bh >> k, wd = ws >> 1, hd = hs >> 1;
-            const int sx0 = (X0 >> j) + Gm.g_lo[j] - (V.x_tl >> k), sy0 = (Y0 >> j) + Gm.g_lo[j] - (V.y_tl >> k);
-            const int dx0 = (X0 >> (j + 1)) + Gm.g_lo[j + 1] - (V.x_tl >> (k + 1)), dy0 = (Y0 >> (j + 1)) + Gm.g_lo[j + 1] - (V.y_tl >> (k + 1));
-            const uint8_t *src = G + Gm.g_off[j];
-            uint8_t *dst = G + Gm.g_off[j + 1];
-            const int sp = Gm.g_pitch[j], dp = Gm.g_pitch[j + 1], n = Gm.g_n[j + 1];
-            for (int r = warp; r < n; r += C_THREADS / 32) {
-                const int y = dy0 + r;  // plane coordinates at level k + 1
-                if ((unsigned)y >= (unsigned)hd) continue;
-                const bool yin = 2 * y - 2 >= 0 && 2 * y + 2 < hs;
-                for (int q = lane; q < n; q += 32) {
-                    const int x = dx0 + q;
-                    if ((unsigned)x >= (unsigned)wd) continue;
-                    int acc = 0;
-                    if (yin && 2 * x - 2 >= 0 && 2 * x + 2 < ws) {
-                        const uint8_t *rp = src + (2 * y - 2 - sy0) * sp + (2 * x - 2 - sx0);
-#pragma unroll
-                        for (int e = 0; e < 5; ++e, rp += sp) acc += (e == 2 ? 6 : ((e & 1) ? 4 : 1)) * (rp[0] + 4 * rp[1] + 6 * rp[2] + 4 * rp[3] + rp[4]);
-                    } else {
-                        int cc[5];
-#pragma unroll
-                        for (int e = 0; e < 5; ++e) cc[e] = r101_idx(2 * x - 2 + e, ws) - sx0;
-#pragma unroll
-                        for (int e = 0; e < 5; ++e) {
-                            const uint8_t *rp = src + (r101_idx(2 * y - 2 + e, hs) - sy0) * sp;
-                            acc += (e == 2 ? 6 : ((e & 1) ? 4 : 1)) * (rp[cc[0]] + 4 * rp[cc[1]] + 6 * rp[cc[2]] + 4 * rp[cc[3]] + rp[cc[4]]);
-                        }
-                    }
-                    dst[r * dp + q] = (uint8_t)rhe_shift<8>(acc);
-                }
-            }
-            __syncthreads();
-        }
-        for (int j = 0; j < nlev; ++j) {  // A(j) += trunc(L(j) * W(j))
-            const int k = 2 + j;
-            const int wv = V.bw >> k, hv = V.bh >> k;
+        for (int j = 0; j < nlev; ++j) {  // A(j) += trunc(L(j) * W(j)), one 2x2 quad per thread
+            const int k = 2 + j, wv = V.bw >> k, hv = V.bh >> k, n = Gm.a_n[j], nq = n >> 1;
             const int ax0 = (X0 >> j) + Gm.a_lo[j] - (V.x_tl >> k), ay0 = (Y0 >> j) + Gm.a_lo[j] - (V.y_tl >> k);
-            const int gx0 = (X0 >> j) + Gm.g_lo[j] - (V.x_tl >> k), gy0 = (Y0 >> j) + Gm.g_lo[j] - (V.y_tl >> k);
             const uint8_t *gs = G + Gm.g_off[j];
-            const int gp = Gm.g_pitch[j], n = Gm.a_n[j];
             int16_t *Aj = A + Gm.a_off[j];
             const float *wgt = V.w[j];
             const bool top = j + 1 == nlev;
-            const uint8_t *gu = top ? nullptr : G + Gm.g_off[j + 1];
-            const int up = top ? 0 : Gm.g_pitch[j + 1];
-            const int ux0 = top ? 0 : (X0 >> (j + 1)) + Gm.g_lo[j + 1] - (V.x_tl >> (k + 1));
-            const int uy0 = top ? 0 : (Y0 >> (j + 1)) + Gm.g_lo[j + 1] - (V.y_tl >> (k + 1));
-            for (int r = warp; r < n; r += C_THREADS / 32) {
-                const int y = ay0 + r;
-                if ((unsigned)y >= (unsigned)hv) continue;
-                for (int q = lane; q < n; q += 32) {
-                    const int x = ax0 + q;
-                    if ((unsigned)x >= (unsigned)wv) continue;
-                    const float wv_ = __ldg(wgt + (size_t)y * wv + x);
-                    if (wv_ == 0.f) continue;  // (short)(L * 0) == 0
-                    int L = gs[(y - gy0) * gp + (x - gx0)];
-                    if (!top) {
-                        auto acc = [&](int xi, int yi) { return (int)gu[(yi - uy0) * up + (xi - ux0)]; };
-                        L -= pyr_up_sample(acc, x, y, wv >> 1, hv >> 1);
+            const uint8_t *gu = top ? gs : G + Gm.g_off[j + 1];
+            const int un = top ? 0 : Gm.a_n[j + 1];
+            const int ux0 = top ? 0 : (X0 >> (j + 1)) + Gm.a_lo[j + 1] - (V.x_tl >> (k + 1));
+            const int uy0 = top ? 0 : (Y0 >> (j + 1)) + Gm.a_lo[j + 1] - (V.y_tl >> (k + 1));
+            for (int qr = warp; qr < nq; qr += C_THREADS / 32)
+                for (int qc = lane; qc < nq; qc += 32) {
+                    const int x0 = ax0 + 2 * qc, y0 = ay0 + 2 * qr;
+                    float wq[4];
+                    bool any = false;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int x = x0 + (q & 1), y = y0 + (q >> 1);
+                        wq[q] = ((unsigned)x < (unsigned)wv && (unsigned)y < (unsigned)hv) ? __ldg(wgt + (size_t)y * wv + x) : 0.f;
+                        any |= wq[q] != 0.f;
                     }
-                    Aj[r * n + q] = (int16_t)(Aj[r * n + q] + rz_s16(__fmul_rn((float)L, wv_)));
+                    if (!any) continue;  // (short)(L * 0) == 0
+                    int up4[4] = {0, 0, 0, 0};
+                    if (!top) {
+                        auto acc = [&](int xi, int yi) { return (int)gu[(yi - uy0) * un + (xi - ux0)]; };
+                        pyr_up_quad(acc, x0, y0, wv >> 1, hv >> 1, up4);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (wq[q] == 0.f) continue;
+                        const int o = (2 * qr + (q >> 1)) * n + 2 * qc + (q & 1);
+                        Aj[o] = (int16_t)(Aj[o] + rz_s16(__fmul_rn((float)((int)gs[o] - up4[q]), wq[q])));
+                    }
                 }
-            }
         }
     }
     __syncthreads();
     for (int j = nlev - 1; j >= 0; --j) {  // normalise, then C(j) = D(j) + up(C(j+1)), saturating
-        const int cwj = P.cw[j], chj = P.ch[j], n = Gm.a_n[j];
-        const int x0 = (X0 >> j) + Gm.a_lo[j], y0 = (Y0 >> j) + Gm.a_lo[j];
+        const int cwj = P.cw[j], chj = P.ch[j], n = Gm.a_n[j], nq = n >> 1;
+        const int x00 = (X0 >> j) + Gm.a_lo[j], y00 = (Y0 >> j) + Gm.a_lo[j];
         int16_t *Aj = A + Gm.a_off[j];
         const bool top = j + 1 == nlev;
-        const int16_t *Au = top ? nullptr : A + Gm.a_off[j + 1];
+        const int16_t *Au = top ? Aj : A + Gm.a_off[j + 1];
         const int un = top ? 0 : Gm.a_n[j + 1];
         const int ux0 = top ? 0 : (X0 >> (j + 1)) + Gm.a_lo[j + 1], uy0 = top ? 0 : (Y0 >> (j + 1)) + Gm.a_lo[j + 1];
-        const int cwu = top ? 0 : P.cw[j + 1], chu = top ? 0 : P.ch[j + 1];
+        const int cwu = top ? 1 : P.cw[j + 1], chu = top ? 1 : P.ch[j + 1];
         const float *dw = P.dw[j];
-        for (int r = warp; r < n; r += C_THREADS / 32) {
-            const int y = y0 + r;
-            if ((unsigned)y >= (unsigned)chj) continue;
-            for (int q = lane; q < n; q += 32) {
-                const int x = x0 + q;
-                if ((unsigned)x >= (unsigned)cwj) continue;
-                const float den = __fadd_rn(__ldg(dw + (size_t)y * cwj + x), 1e-5f);
-                int d = rz_s16(__fdiv_rn((float)Aj[r * n + q], den));
+        for (int qr = warp; qr < nq; qr += C_THREADS / 32)
+            for (int qc = lane; qc < nq; qc += 32) {
+                const int x0 = x00 + 2 * qc, y0 = y00 + 2 * qr;
+                int up4[4] = {0, 0, 0, 0};
                 if (!top) {
                     auto acc = [&](int xi, int yi) { return (int)Au[(yi - uy0) * un + (xi - ux0)]; };
-                    d = sat_s16(d + pyr_up_sample(acc, x, y, cwu, chu));
+                    pyr_up_quad(acc, x0, y0, cwu, chu, up4);
                 }
-                Aj[r * n + q] = (int16_t)d;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int x = x0 + (q & 1), y = y0 + (q >> 1);
+                    if ((unsigned)x >= (unsigned)cwj || (unsigned)y >= (unsigned)chj) continue;
+                    const int o = (2 * qr + (q >> 1)) * n + 2 * qc + (q & 1);
+                    Aj[o] = (int16_t)sat_s16(normalize_s16(Aj[o], __ldg(dw + (size_t)y * cwj + x)) + up4[q]);
+                }
             }
-        }
         __syncthreads();
     }
     {
@@ -350,7 +424,7 @@ constexpr int BL_TW = 64, BL_TH = 32, BL_THREADS = 256;
 constexpr int BL_R1W = BL_TW / 2 + 2, BL_R1H = BL_TH / 2 + 2;   // level-1 region 34 x 18, origin (tx0/2 - 1, ty0/2 - 1)
 constexpr int BL_G0WORDS = 18, BL_G0H = BL_TH + 7;              // level-0 region 72 B x 39, origin (tx0 - 4, ty0 - 4)
 constexpr int BL_R2W = BL_TW / 4 + 4, BL_R2H = BL_TH / 4 + 4;   // level-2 region 20 x 12, origin (tx0/4 - 2, ty0/4 - 2)
-constexpr int BL_L1PT = (BL_R1W * BL_R1H + BL_THREADS - 1) / BL_THREADS;  // level-1 samples per thread (3)
+constexpr int BL_QW = BL_R1W / 2, BL_QH = BL_R1H / 2, BL_NQ = BL_QW * BL_QH;  // level-1 region as 17 x 9 quads, one thread each
 
 struct BlendView {
     const uint8_t *g0, *g2;  // frame 0
@@ -369,7 +443,7 @@ struct BlendParams {
     BlendView v[MAXV];
 };
 
-__global__ void __launch_bounds__(BL_THREADS) k_blend(const __grid_constant__ BlendParams P, const __grid_constant__ OutPtrs outs, size_t out_pitch)
+__global__ void __launch_bounds__(BL_THREADS, 3) k_blend(const __grid_constant__ BlendParams P, const __grid_constant__ OutPtrs outs, size_t out_pitch)
 {
     __shared__ __align__(16) unsigned sG0[3][BL_G0H][BL_G0WORDS + 1];
     __shared__ uint8_t sG1[3][BL_R1H][BL_R1W + 2];
@@ -381,12 +455,13 @@ __global__ void __launch_bounds__(BL_THREADS) k_blend(const __grid_constant__ Bl
     const int tx0 = blockIdx.x * BL_TW, ty0 = blockIdx.y * BL_TH;
     const int lx = (t & 7) * 8, ly = t >> 3;  // this thread's 8 consecutive level-0 samples
     const int px0 = tx0 + lx, py = ty0 + ly;
-    int acc0[3][8], acc1[3][BL_L1PT];
-    float dw0[8], dw1[BL_L1PT];
+    int acc0[3][8], acc1[3][4];
+    float dw0[8], dw1[4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { dw0[i] = 0.f; acc0[0][i] = acc0[1][i] = acc0[2][i] = 0; }
 #pragma unroll
-    for (int q = 0; q < BL_L1PT; ++q) { dw1[q] = 0.f; acc1[0][q] = acc1[1][q] = acc1[2][q] = 0; }
+    for (int q = 0; q < 4; ++q) { dw1[q] = 0.f; acc1[0][q] = acc1[1][q] = acc1[2][q] = 0; }
+    const int qr1 = 2 * (t / BL_QW), qc1 = 2 * (t % BL_QW);  // this thread's level-1 quad (threads < BL_NQ)
 
     unsigned views = __ldg(P.tile_views + blockIdx.y * P.tiles_x + blockIdx.x);
     while (views) {
@@ -466,27 +541,33 @@ __global__ void __launch_bounds__(BL_THREADS) k_blend(const __grid_constant__ Bl
                 }
             }
         }
-        // ---- level 1: up to BL_L1PT samples of the 34 x 18 region
-        if (nb >= 1) {
+        // ---- level 1: one 2x2 quad of the 34 x 18 region per thread
+        if (nb >= 1 && t < BL_NQ) {
             const int u2x0 = (tx0 >> 2) - 2 - (V.x_tl >> 2), u2y0 = (ty0 >> 2) - 2 - (V.y_tl >> 2);
+            const int x0 = v1x0 + qc1, y0 = v1y0 + qr1;  // plane coordinates, both odd
+            float wq[4];
+            bool any = false;
 #pragma unroll
-            for (int q = 0; q < BL_L1PT; ++q) {
-                const int i = t + q * BL_THREADS;
-                if (i >= BL_R1W * BL_R1H) continue;
-                const int r1 = i / BL_R1W, c1 = i - r1 * BL_R1W;
-                const int x = v1x0 + c1, y = v1y0 + r1;
-                if ((unsigned)x >= (unsigned)w1 || (unsigned)y >= (unsigned)h1) continue;
-                const float wq = __ldg(V.w1 + (size_t)y * w1 + x);
-                dw1[q] = __fadd_rn(dw1[q], wq);
-                if (wq == 0.f) continue;
+            for (int q = 0; q < 4; ++q) {
+                const int x = x0 + (q & 1), y = y0 + (q >> 1);
+                wq[q] = 0.f;
+                if ((unsigned)x < (unsigned)w1 && (unsigned)y < (unsigned)h1) {
+                    wq[q] = __ldg(V.w1 + (size_t)y * w1 + x);
+                    dw1[q] = __fadd_rn(dw1[q], wq[q]);
+                    any |= wq[q] != 0.f;
+                }
+            }
+            if (any) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    int L = sG1[c][r1][c1];
+                    int up4[4] = {0, 0, 0, 0};
                     if (nb >= 2) {
                         auto a = [&](int xi, int yi) { return (int)sG2[c][yi - u2y0][xi - u2x0]; };
-                        L -= pyr_up_sample(a, x, y, w2, h2);
+                        pyr_up_quad_odd(a, x0, y0, w2, h2, up4);
                     }
-                    acc1[c][q] += rz_s16(__fmul_rn((float)L, wq));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (wq[q] != 0.f) acc1[c][q] += rz_s16(__fmul_rn((float)((int)sG1[c][qr1 + (q >> 1)][qc1 + (q & 1)] - up4[q]), wq[q]));
                 }
             }
         }
@@ -503,23 +584,22 @@ __global__ void __launch_bounds__(BL_THREADS) k_blend(const __grid_constant__ Bl
         __syncthreads();
     }
     if (nb >= 1) {
-        const int X1 = (tx0 >> 1) - 1, Y1 = (ty0 >> 1) - 1, ux0 = (tx0 >> 2) - 2, uy0 = (ty0 >> 2) - 2;
-#pragma unroll
-        for (int q = 0; q < BL_L1PT; ++q) {
-            const int i = t + q * BL_THREADS;
-            if (i >= BL_R1W * BL_R1H) continue;
-            const int r1 = i / BL_R1W, c1 = i - r1 * BL_R1W;
-            const int x = X1 + c1, y = Y1 + r1;
-            if ((unsigned)x >= (unsigned)P.cw1 || (unsigned)y >= (unsigned)P.ch1) continue;
-            const float den = __fadd_rn(dw1[q], 1e-5f);
+        if (t < BL_NQ) {
+            const int ux0 = (tx0 >> 2) - 2, uy0 = (ty0 >> 2) - 2;
+            const int x0 = (tx0 >> 1) - 1 + qc1, y0 = (ty0 >> 1) - 1 + qr1;  // canvas coordinates, both odd
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                int d = rz_s16(__fdiv_rn((float)(int)(short)acc1[c][q], den));
+                int up4[4] = {0, 0, 0, 0};
                 if (nb >= 2) {
                     auto a = [&](int xi, int yi) { return (int)sC2[c][yi - uy0][xi - ux0]; };
-                    d = sat_s16(d + pyr_up_sample(a, x, y, P.cw2, P.ch2));
+                    pyr_up_quad_odd(a, x0, y0, P.cw2, P.ch2, up4);
                 }
-                sD1[c][r1][c1] = (int16_t)d;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int x = x0 + (q & 1), y = y0 + (q >> 1);
+                    if ((unsigned)x < (unsigned)P.cw1 && (unsigned)y < (unsigned)P.ch1)
+                        sD1[c][qr1 + (q >> 1)][qc1 + (q & 1)] = (int16_t)sat_s16(normalize_s16(acc1[c][q], dw1[q]) + up4[q]);
+                }
             }
         }
         __syncthreads();
@@ -538,8 +618,7 @@ __global__ void __launch_bounds__(BL_THREADS) k_blend(const __grid_constant__ Bl
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                int d = rz_s16(__fdiv_rn((float)(int)(short)acc0[c][i], __fadd_rn(dw0[i], 1e-5f)));
-                d = sat_s16(d + up[i]);
+                const int d = sat_s16(normalize_s16(acc0[c][i], dw0[i]) + up[i]);
                 sOut[ly][(lx + i) * 3 + c] = dw0[i] > 1e-5f ? (int16_t)d : (int16_t)0;  // dst_mask = dst_band_weights_[0] > WEIGHT_EPS
             }
         }
@@ -551,17 +630,16 @@ __global__ void __launch_bounds__(BL_THREADS) k_blend(const __grid_constant__ Bl
     char *obase = (char *)outs.out[f] + (size_t)tx0 * 6;
     const bool vec_ok = ((((size_t)obase) | out_pitch) & 15) == 0;
     const int row_bytes = n_px * 6;
-    for (int i = t; i < n_rows * (BL_TW * 6 / 16); i += BL_THREADS) {
-        const int r = i / (BL_TW * 6 / 16), ck = i - r * (BL_TW * 6 / 16);
-        const int b0 = ck * 16;
-        if (b0 >= row_bytes) continue;
+    for (int r = t >> 5; r < n_rows; r += BL_THREADS / 32) {  // one warp per row: 24 chunks of 16 bytes
+        const int ck = t & 31, b0 = ck * 16;
+        if (ck >= BL_TW * 6 / 16 || b0 >= row_bytes) continue;
         char *o = obase + (size_t)(ty0 + r) * out_pitch + b0;
-        const int16_t *s = &sOut[r][ck * 8];
+        const int16_t *sp = &sOut[r][ck * 8];
         if (vec_ok && b0 + 16 <= row_bytes) {
-            *(uint4 *)o = *(const uint4 *)s;
+            *(uint4 *)o = *(const uint4 *)sp;
         } else {
             const int n = min(8, (row_bytes - b0) >> 1);
-            for (int e = 0; e < n; ++e) ((int16_t *)o)[e] = s[e];
+            for (int e = 0; e < n; ++e) ((int16_t *)o)[e] = sp[e];
         }
     }
 }

@@ -43,11 +43,18 @@ __device__ __forceinline__ int rhe_shift(int v)
 }
 
 // BORDER_REFLECT (fedcba|abcdefgh|hgfedcb): sources/modules/cudev/include/opencv2/cudev/ptr2d/extrapolation.hpp:171-183
+//   idx_high(i) = last - abs(last - i) + (i > last), idx_low(j) = (abs(j) - (j < 0)) % len.
+// Within one fold (-len <= i <= 2*len - 1) that is the mirror below; the modulo form only runs for borders wider than
+// the image (the reference's formula, not OpenCV's CPU borderInterpolate, is what the CUDA path computes there).
 __device__ __forceinline__ int reflect_idx(int i, int len)
 {
     const int last = len - 1;
-    int j = last - abs(last - i) + (i > last);
-    return (abs(j) - (j < 0)) % len;
+    int j = i < 0 ? -i - 1 : (i > last ? 2 * last - i + 1 : i);
+    if ((unsigned)j > (unsigned)last) {
+        j = last - abs(last - i) + (i > last);
+        j = (abs(j) - (j < 0)) % len;
+    }
+    return j;
 }
 
 // BORDER_REFLECT_101 as used by pyrDown: sources/modules/core/include/opencv2/core/cuda/border_interpolate.hpp:351-380
@@ -57,10 +64,9 @@ __device__ __forceinline__ int reflect_idx(int i, int len)
 __device__ __forceinline__ int r101_idx(int i, int len)
 {
     const int last = len - 1;
-    int j = abs(i);
-    j = j > last ? 2 * last - j : j;
-    if ((unsigned)j > (unsigned)last) j = abs(abs(last - abs(last - i)) % len) % len;
-    return j;
+    if ((unsigned)(i + last) > (unsigned)(3 * last)) return abs(abs(last - abs(last - i)) % len) % len;  // beyond one fold (or len == 1)
+    const int j = abs(i);
+    return j > last ? 2 * last - j : j;
 }
 
 // pyrUp source index: abs() at the low edge, clamp at the high edge (sources/modules/cudawarping/src/cuda/pyr_up.cu:70-74)
@@ -112,6 +118,75 @@ __device__ __forceinline__ unsigned remap_px_u8c3(const uint8_t *__restrict__ sr
 #pragma unroll
     for (int c = 0; c < 3; ++c) out |= rni_sat_u8(bilerp(s11[c], s12[c], s21[c], s22[c], t)) << (8 * c);
     return out;
+}
+
+
+// ---- fast exact bilinear tap machinery (same fp32 operations in the same order as remap_px_u8c3 above) ---------------
+// u8 -> fp32 without the conversion pipe: PRMT builds 0x4B0000xx (= 2^23 + xx), one FADD removes the bias (exact).
+__device__ __forceinline__ float u8_to_f32(unsigned packed, int byte)
+{
+    return __fsub_rn(__uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7540u | (unsigned)byte)), 8388608.f);
+}
+// cvt.rni of a value known to lie in [0, 2^22): adding 1.5 * 2^23 rounds to nearest-even in the mantissa's low bits
+__device__ __forceinline__ float rni_biased(float v) { return __fadd_rn(v, 12582912.f); }
+
+// six consecutive bytes (two interleaved BGR pixels) starting at an arbitrary address, as lo = bytes 0..3, hi = bytes 4..5
+__device__ __forceinline__ void load6(const uint8_t *__restrict__ p, bool bytewise, unsigned &lo, unsigned &hi)
+{
+    if (bytewise) {  // the last bytes of the image: never touch memory past the caller's buffer
+        lo = (unsigned)__ldg(p) | ((unsigned)__ldg(p + 1) << 8) | ((unsigned)__ldg(p + 2) << 16) | ((unsigned)__ldg(p + 3) << 24);
+        hi = (unsigned)__ldg(p + 4) | ((unsigned)__ldg(p + 5) << 8);
+        return;
+    }
+    const size_t a = (size_t)p & ~(size_t)3;
+    const unsigned sh = ((unsigned)(size_t)p & 3u) * 8u;
+    const unsigned w0 = __ldg((const unsigned *)a), w1 = __ldg((const unsigned *)(a + 4));
+    const unsigned w2 = sh == 24u ? __ldg((const unsigned *)(a + 8)) : 0u;
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = __funnelshift_r(w1, w2, sh);
+}
+
+// remap LINEAR / BORDER_CONSTANT(0) of one interleaved u8x3 pixel followed by the gain convertTo:
+//   p = sat_u8(rni(gain * sat_u8(rni(bilinear))))   (360_stitcher/timed.cpp:90-94); gain = 1 gives the plain remap.
+// Returns b | g << 8 | r << 16.  Requires sw >= 2.  Bit-identical to remap_px_u8c3 + rni_sat_u8(gain * v): the taps,
+// weights and the fmul/fma chain are the same; only the u8<->fp32 conversions take a cheaper route.
+template <bool GAIN>
+__device__ __forceinline__ unsigned remap_gain_px(const uint8_t *__restrict__ src, size_t pitch, int sw, int sh, float x, float y, float gain)
+{
+    const int x1 = __float2int_rd(x), y1 = __float2int_rd(y);
+    // no tap in range (or NaN coordinates: every product is NaN and cvt.sat gives 0)
+    if (x1 < -1 || x1 >= sw || y1 < -1 || y1 >= sh || !(x == x) || !(y == y)) return 0u;
+    const float fx2 = __fsub_rn((float)(x1 + 1), x), fx1 = __fsub_rn(x, (float)x1);
+    const float fy2 = __fsub_rn((float)(y1 + 1), y), fy1 = __fsub_rn(y, (float)y1);
+    const float w11 = __fmul_rn(fx2, fy2), w12 = __fmul_rn(fx1, fy2), w21 = __fmul_rn(fx2, fy1), w22 = __fmul_rn(fx1, fy1);
+    const int xs = min(max(x1, 0), sw - 2);
+    unsigned l1 = 0, r1 = 0, l2 = 0, r2 = 0;  // 24-bit BGR of the four taps
+    const uint8_t *row = src + (size_t)max(y1, 0) * pitch + (size_t)xs * 3;
+    const bool tail = xs + 4 >= sw;  // word loads could run up to 3 bytes past the end of the last row
+    if (y1 >= 0) {
+        unsigned lo, hi;
+        load6(row, tail && y1 == sh - 1, lo, hi);
+        l1 = lo & 0xffffffu; r1 = (lo >> 24) | ((hi & 0xffffu) << 8);
+    }
+    if (y1 + 1 < sh) {
+        unsigned lo, hi;
+        load6(y1 >= 0 ? row + pitch : row, tail && y1 + 1 == sh - 1, lo, hi);
+        l2 = lo & 0xffffffu; r2 = (lo >> 24) | ((hi & 0xffffu) << 8);
+    }
+    if (x1 != xs) {  // x1 == -1: left taps are outside; x1 == sw - 1: right taps are outside
+        if (x1 < 0) { r1 = l1; r2 = l2; l1 = l2 = 0u; } else { l1 = r1; l2 = r2; r1 = r2 = 0u; }
+    }
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float v = __fmul_rn(u8_to_f32(l1, c), w11);
+        v = __fmaf_rn(u8_to_f32(r1, c), w12, v);
+        v = __fmaf_rn(u8_to_f32(l2, c), w21, v);
+        v = __fmaf_rn(u8_to_f32(r2, c), w22, v);
+        v = __fsub_rn(rni_biased(v), 12582912.f);                      // sat_u8(rni(.)) as a float: 0 <= v < 255.5
+        o[c] = GAIN ? rni_biased(fminf(__fmul_rn(gain, v), 255.f)) : __fadd_rn(v, 12582912.f);  // sat_u8(rni(gain * v)); integer in the low byte
+    }
+    return __byte_perm(__byte_perm(__float_as_uint(o[0]), __float_as_uint(o[1]), 0x0040u), __float_as_uint(o[2]), 0x0410u) & 0xffffffu;
 }
 
 }  // namespace vsb

@@ -45,47 +45,51 @@ __device__ __forceinline__ int find_view(const TileMap &tm, int tile)
 }
 
 // ---- K1: remap#1 (projection maps) + gain ------------------------------------------------------------
+// One CTA = one 128 x 8 tile of one view's warped ROI (4 consecutive pixels per thread).  Tiles whose maps address
+// nothing inside the camera frame are not in the list: P is zeroed once and stays 0 there, which is what the
+// reference's BORDER_CONSTANT remap writes every frame.
 struct Stage1View {
     const float *xmap, *ymap;   // roi_w x roi_h, pitch map_pitch bytes
-    const uint8_t *lut;         // 256-entry gain table: sat_u8(rni(gain * v))
     uint8_t *P;                 // frame 0
     size_t map_pitch, p_pitch, p_frame_stride;
     int w, h, src_w, src_h;
+    float gain;
 };
 struct Stage1Params {
-    TileMap tm;
+    const uint32_t *tiles;      // view | tile_x << 8 | tile_y << 20
     Stage1View v[MAXV];
-    const uint8_t *src[MAX_BATCH * MAXV];
+    const uint8_t *src[MAX_BATCH * MAXV];  // [frame][view - v0]
     size_t src_pitch;
-    int n_views;
+    int v0, n_views;
 };
 
 constexpr int RM_BX = 32, RM_BY = 8, RM_PX = 4;  // 4 consecutive pixels per thread
 
 __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage1(const __grid_constant__ Stage1Params p)
 {
-    const int vi = find_view(p.tm, blockIdx.x);
+    const unsigned tile = __ldg(p.tiles + blockIdx.x);
+    const int vi = tile & 0xff;
     const Stage1View &V = p.v[vi];
-    const int t = blockIdx.x - p.tm.start[vi];
-    const int tx = t % p.tm.tiles_x[vi], ty = t / p.tm.tiles_x[vi];
-    const int x0 = (tx * RM_BX + threadIdx.x) * RM_PX, y = ty * RM_BY + threadIdx.y;
+    const int x0 = ((int)((tile >> 8) & 0xfff) * RM_BX + threadIdx.x) * RM_PX, y = (int)(tile >> 20) * RM_BY + threadIdx.y;
     if (x0 >= V.w || y >= V.h) return;
     const int f = blockIdx.y;
-    const uint8_t *src = p.src[f * p.n_views + vi];
+    const uint8_t *src = p.src[f * p.n_views + vi - p.v0];
     const float *mx = (const float *)((const char *)V.xmap + (size_t)y * V.map_pitch) + x0;
     const float *my = (const float *)((const char *)V.ymap + (size_t)y * V.map_pitch) + x0;
     uint8_t *dst = V.P + (size_t)f * V.p_frame_stride + (size_t)y * V.p_pitch + (size_t)x0 * 3;
-    unsigned px[RM_PX];
     const int n = min(RM_PX, V.w - x0);
+    float fx[RM_PX], fy[RM_PX];
+    if (n == RM_PX) {  // map rows are 16-byte aligned and x0 % 4 == 0
+        const float4 a = __ldg((const float4 *)mx), b = __ldg((const float4 *)my);
+        fx[0] = a.x; fx[1] = a.y; fx[2] = a.z; fx[3] = a.w;
+        fy[0] = b.x; fy[1] = b.y; fy[2] = b.z; fy[3] = b.w;
+    } else {
 #pragma unroll
-    for (int i = 0; i < RM_PX; ++i) {
-        px[i] = 0;
-        if (i < n) {
-            const unsigned v = remap_px_u8c3(src, p.src_pitch, V.src_w, V.src_h, __ldg(mx + i), __ldg(my + i));
-            px[i] = (unsigned)__ldg(V.lut + (v & 0xff)) | ((unsigned)__ldg(V.lut + ((v >> 8) & 0xff)) << 8) |
-                    ((unsigned)__ldg(V.lut + ((v >> 16) & 0xff)) << 16);
-        }
+        for (int i = 0; i < RM_PX; ++i) { fx[i] = i < n ? __ldg(mx + i) : -1.f; fy[i] = i < n ? __ldg(my + i) : -1.f; }
     }
+    unsigned px[RM_PX];
+#pragma unroll
+    for (int i = 0; i < RM_PX; ++i) px[i] = remap_gain_px<true>(src, p.src_pitch, V.src_w, V.src_h, fx[i], fy[i], V.gain);
     if (n == RM_PX) {  // 12 bytes = three aligned 32-bit stores (p_pitch % 4 == 0, x0 % 4 == 0)
         unsigned *d32 = (unsigned *)dst;
         d32[0] = px[0] | (px[1] << 24);
@@ -97,6 +101,7 @@ __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage1(const __grid_cons
 }
 
 // ---- K2: CPW-mesh remap#2 + REFLECT border + interleaved -> planar ------------------------------------
+// One CTA = one 128 x 8 tile of one view's BORDERED plane; only tiles some later kernel reads are in the list.
 struct Stage2View {
     const uint8_t *P;
     const float *xmesh, *ymesh;  // roi_w x roi_h (null when enable_local == 0)
@@ -105,30 +110,30 @@ struct Stage2View {
     int w, h, bw, bh, top, left;
 };
 struct Stage2Params {
-    TileMap tm;
+    const uint32_t *tiles;
     Stage2View v[MAXV];
 };
 
 __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage2(const __grid_constant__ Stage2Params p)
 {
-    const int vi = find_view(p.tm, blockIdx.x);
-    const Stage2View &V = p.v[vi];
-    const int t = blockIdx.x - p.tm.start[vi];
-    const int tx = t % p.tm.tiles_x[vi], ty = t / p.tm.tiles_x[vi];
-    const int bx0 = (tx * RM_BX + threadIdx.x) * RM_PX, by = ty * RM_BY + threadIdx.y;
-    if (bx0 >= V.bw || by >= V.bh) return;  // bw % 4 == 0
+    const unsigned tile = __ldg(p.tiles + blockIdx.x);
+    const Stage2View &V = p.v[tile & 0xff];
+    const int bx0 = ((int)((tile >> 8) & 0xfff) * RM_BX + threadIdx.x) * RM_PX, by = (int)(tile >> 20) * RM_BY + threadIdx.y;
+    if (bx0 >= V.bw || by >= V.bh) return;
     const int f = blockIdx.y;
     const uint8_t *P = V.P + (size_t)f * V.p_frame_stride;
     const int y = reflect_idx(by - V.top, V.h);
+    const int n = min(RM_PX, V.bw - bx0);
     unsigned c0 = 0, c1 = 0, c2 = 0;
 #pragma unroll
     for (int i = 0; i < RM_PX; ++i) {
+        if (i >= n) break;
         const int x = reflect_idx(bx0 + i - V.left, V.w);
         unsigned v;
         if (V.xmesh) {
             const float fx = __ldg((const float *)((const char *)V.xmesh + (size_t)y * V.map_pitch) + x);
             const float fy = __ldg((const float *)((const char *)V.ymesh + (size_t)y * V.map_pitch) + x);
-            v = remap_px_u8c3(P, V.p_pitch, V.w, V.h, fx, fy);
+            v = remap_gain_px<false>(P, V.p_pitch, V.w, V.h, fx, fy, 1.f);
         } else {
             const uint8_t *s = P + (size_t)y * V.p_pitch + (size_t)x * 3;
             v = (unsigned)__ldg(s) | ((unsigned)__ldg(s + 1) << 8) | ((unsigned)__ldg(s + 2) << 16);
@@ -139,9 +144,13 @@ __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage2(const __grid_cons
     }
     const size_t plane = (size_t)V.bw * V.bh;
     uint8_t *g = V.G0 + (size_t)f * V.g0_frame_stride + (size_t)by * V.bw + bx0;
-    *(unsigned *)g = c0;
-    *(unsigned *)(g + plane) = c1;
-    *(unsigned *)(g + 2 * plane) = c2;
+    if (n == RM_PX && (V.bw & 3) == 0) {
+        *(unsigned *)g = c0;
+        *(unsigned *)(g + plane) = c1;
+        *(unsigned *)(g + 2 * plane) = c2;
+    } else {
+        for (int i = 0; i < n; ++i) { g[i] = (c0 >> (8 * i)) & 0xff; g[plane + i] = (c1 >> (8 * i)) & 0xff; g[2 * plane + i] = (c2 >> (8 * i)) & 0xff; }
+    }
 }
 
 // ---- K3: pyrDown on planes ----------------------------------------------------------------------------
@@ -401,7 +410,6 @@ struct View {
     int mesh_pending = -1;                                          // buffer published by vsb_set_mesh, not yet adopted
     cudaEvent_t mesh_ready = nullptr;
     float *mesh_scratch = nullptr;                                  // sum_x | sum_y | cnt (half res) + device copy of the vertex mesh
-    uint8_t *lut = nullptr;
     float *weight[MAXL] = {};
     uint8_t *P = nullptr;
     size_t p_pitch = 0, p_frame_stride = 0;
@@ -411,9 +419,12 @@ struct View {
     size_t g_frame_stride[MAXL] = {};
     uint8_t *G2 = nullptr;              // fast path: u8 Gaussian level 2
     size_t g2_frame_stride = 0;
+    uint8_t *Gu[MAXL] = {};             // fast path: u8 Gaussian levels 3..nb (Gu[2] aliases G2)
+    size_t gu_frame_stride[MAXL] = {};
     uint8_t *M0 = nullptr;              // bordered seam mask (u8, bw x bh): W0 = M0 * (1/255)
     std::vector<uint8_t> g2_needed;     // per k_down2 tile: computed (1) or skipped (0); host copy for vsb_debug_read
     int d2_tiles_x = 0, d2_tiles_y = 0;
+    std::vector<uint32_t> s1_tiles, s2_tiles;  // 128 x 8 tiles k_remap_stage1 / k_remap_stage2 compute (packed view|tx|ty)
 };
 
 }  // namespace vsb
@@ -437,6 +448,9 @@ struct vsb_stitcher {
     int blend_tiles_x = 0, blend_tiles_y = 0, coarse_tiles_x = 0, coarse_tiles_y = 0, n_down2_tiles = 0;
     int16_t *C2 = nullptr;
     size_t c2_frame_stride = 0;
+    uint32_t *d_s1_tiles = nullptr, *d_s2_tiles = nullptr;  // concatenated per-view lists, view order
+    vsb::CoarseView *d_coarse_desc = nullptr;
+    bool tiles_dirty = true;
     cudaStream_t setup_stream = nullptr, mesh_stream = nullptr, io_stream = nullptr;
     cudaEvent_t last_compose = nullptr;
     bool last_compose_valid = false;
@@ -475,27 +489,12 @@ static void free_view(View &V)
 {
     cudaFree(V.xmap); cudaFree(V.ymap);
     for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) cudaFree(V.mesh[b][c]);
-    cudaFree(V.mesh_scratch); cudaFree(V.lut);
+    cudaFree(V.mesh_scratch);
     for (int k = 0; k < MAXL; ++k) { cudaFree(V.weight[k]); cudaFree(V.G[k]); }
     cudaFree(V.P); cudaFree(V.G0); cudaFree(V.G2); cudaFree(V.M0);
+    for (int k = 3; k < MAXL; ++k) cudaFree(V.Gu[k]);
     if (V.mesh_ready) cudaEventDestroy(V.mesh_ready);
     V = View();
-}
-
-static int upload_lut(vsb_stitcher *s, View &V)
-{
-    uint8_t lut[256];
-    for (int i = 0; i < 256; ++i) {
-        // sat_u8(rni(alpha * v)): Convertor, sources/modules/core/src/cuda/gpu_mat.cu:493-496 (host twin of cvt.rni.sat.u8.f32)
-        const float p = V.gain * (float)i;
-        float r = nearbyintf(p);
-        if (!(p == p)) r = 0.f;
-        lut[i] = (uint8_t)(r <= 0.f ? 0 : (r >= 255.f ? 255 : (int)r));
-    }
-    if (!V.lut) CK(cudaMalloc(&V.lut, 256));
-    CK(cudaMemcpyAsync(V.lut, lut, 256, cudaMemcpyHostToDevice, s->setup_stream));
-    CK(cudaStreamSynchronize(s->setup_stream));
-    return VSB_OK;
 }
 
 static int build_plan(vsb_stitcher *s)
@@ -533,21 +532,19 @@ static void coarse_geometry(int nb, CoarseGeo &g)
     for (int j = 1; j < nlev; ++j) { a_lo[j] = fdiv2(a_lo[j - 1]) - 1; a_hi[j] = fdiv2(a_hi[j - 1]) + 1; }
     g_lo[nlev - 1] = a_lo[nlev - 1]; g_hi[nlev - 1] = a_hi[nlev - 1];
     for (int j = nlev - 2; j >= 0; --j) { g_lo[j] = std::min(a_lo[j], 2 * g_lo[j + 1] - 2); g_hi[j] = std::max(a_hi[j], 2 * g_hi[j + 1] + 2); }
-    g_lo[0] = -(int)align_up((size_t)(-g_lo[0]), 4);
     int a_total = 0, g_total = 0;
     for (int j = 0; j < nlev; ++j) {
-        g.a_lo[j] = a_lo[j]; g.a_n[j] = a_hi[j] - a_lo[j] + 1;
+        g.a_lo[j] = a_lo[j]; g.a_n[j] = a_hi[j] - a_lo[j] + 1;   // even by construction (64, 34, 20, 12, 8, 6)
         g.g_lo[j] = g_lo[j]; g.g_n[j] = g_hi[j] - g_lo[j] + 1;
-        g.g_pitch[j] = (int)align_up((size_t)g.g_n[j], 4);
         g.a_off[j] = a_total; a_total += (int)align_up((size_t)g.a_n[j] * g.a_n[j], 8);
-        g.g_off[j] = g_total; g_total += (int)align_up((size_t)g.g_pitch[j] * g.g_n[j], 16);
+        g.g_off[j] = g_total; g_total += (int)align_up((size_t)g.a_n[j] * g.a_n[j], 16);
     }
     g.a_total = a_total;
 }
 static size_t coarse_smem_bytes(const CoarseGeo &g)
 {
     const int j = g.nlev - 1;
-    return (size_t)g.a_total * 2 + g.g_off[j] + align_up((size_t)g.g_pitch[j] * g.g_n[j], 16);
+    return (size_t)g.a_total * 2 + g.g_off[j] + align_up((size_t)g.a_n[j] * g.a_n[j], 16);
 }
 
 struct HostWeights {  // nonzero structure of one view's static weight pyramid
@@ -628,7 +625,7 @@ static int build_fast_plan(vsb_stitcher *s)
                 if (cviews[(size_t)ty * s->coarse_tiles_x + tx] >> i & 1) {
                     // the region is read through BORDER_REFLECT_101 (at most 2 samples beyond the loaded range fold back inside it)
                     const int x0 = tx * CT + s->cgeo.g_lo[0] - (V.x_tl >> 2), y0 = ty * CT + s->cgeo.g_lo[0] - (V.y_tl >> 2);
-                    mark(x0, y0, x0 + s->cgeo.g_pitch[0], y0 + s->cgeo.g_n[0]);
+                    mark(x0, y0, x0 + s->cgeo.g_n[0], y0 + s->cgeo.g_n[0]);
                 }
         for (int ty = 0; ty < s->blend_tiles_y; ++ty)
             for (int tx = 0; tx < s->blend_tiles_x; ++tx)
@@ -640,6 +637,31 @@ static int build_fast_plan(vsb_stitcher *s)
             for (int tx = 0; tx < V.d2_tiles_x; ++tx)
                 if (V.g2_needed[(size_t)ty * V.d2_tiles_x + tx]) d2tiles.push_back((uint32_t)i | ((uint32_t)tx << 8) | ((uint32_t)ty << 20));
     }
+    // ---- k_remap_stage2: the 128 x 8 tiles of G0 that a computed k_down2 tile or a k_blend tile reads
+    for (int i = 0; i < n; ++i) {
+        View &V = s->v[i];
+        const int tw = RM_BX * RM_PX, ntx = (V.bw + tw - 1) / tw, nty = (V.bh + RM_BY - 1) / RM_BY;
+        std::vector<uint8_t> need((size_t)ntx * nty, 0);
+        auto mark = [&](int x0, int y0, int x1, int y1) {  // half-open rect in level-0 plane coordinates
+            x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, V.bw); y1 = std::min(y1, V.bh);
+            if (x0 >= x1 || y0 >= y1) return;
+            for (int ty = y0 / RM_BY; ty <= (y1 - 1) / RM_BY; ++ty)
+                for (int tx = x0 / tw; tx <= (x1 - 1) / tw; ++tx) need[(size_t)ty * ntx + tx] = 1;
+        };
+        for (int ty = 0; ty < V.d2_tiles_y; ++ty)
+            for (int tx = 0; tx < V.d2_tiles_x; ++tx)
+                if (V.g2_needed[(size_t)ty * V.d2_tiles_x + tx])
+                    mark(4 * tx * D2_TW - 8, 4 * ty * D2_TH - 6, 4 * tx * D2_TW - 8 + 4 * D2_R0WORDS, 4 * ty * D2_TH - 6 + D2_R0H);
+        for (int ty = 0; ty < s->blend_tiles_y; ++ty)
+            for (int tx = 0; tx < s->blend_tiles_x; ++tx)
+                if (bviews[(size_t)ty * s->blend_tiles_x + tx] >> i & 1)
+                    mark(tx * BL_TW - 4 - V.x_tl, ty * BL_TH - 4 - V.y_tl, tx * BL_TW - 4 - V.x_tl + 4 * BL_G0WORDS, ty * BL_TH - 4 - V.y_tl + BL_G0H);
+        V.s2_tiles.clear();
+        for (int ty = 0; ty < nty; ++ty)
+            for (int tx = 0; tx < ntx; ++tx)
+                if (need[(size_t)ty * ntx + tx]) V.s2_tiles.push_back((uint32_t)i | ((uint32_t)tx << 8) | ((uint32_t)ty << 20));
+    }
+    s->tiles_dirty = true;
     s->n_down2_tiles = (int)d2tiles.size();
     cudaFree(s->d_blend_views); cudaFree(s->d_coarse_views); cudaFree(s->d_down2_tiles); cudaFree(s->C2);
     s->d_blend_views = s->d_coarse_views = s->d_down2_tiles = nullptr; s->C2 = nullptr;
@@ -653,6 +675,16 @@ static int build_fast_plan(vsb_stitcher *s)
     CK(cudaMalloc(&s->C2, s->c2_frame_stride * sizeof(int16_t) * F));
     if (s->coarse_smem > 48 * 1024)
         CK(cudaFuncSetAttribute(k_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->coarse_smem));
+    std::vector<CoarseView> desc(n);
+    std::memset(desc.data(), 0, sizeof(CoarseView) * n);
+    for (int i = 0; i < n; ++i) {
+        const View &V = s->v[i];
+        for (int j = 0; j < s->cgeo.nlev; ++j) { desc[i].g[j] = V.Gu[2 + j]; desc[i].g_fs[j] = V.gu_frame_stride[2 + j]; desc[i].w[j] = V.weight[2 + j]; }
+        desc[i].x_tl = V.x_tl; desc[i].y_tl = V.y_tl; desc[i].bw = V.bw; desc[i].bh = V.bh;
+    }
+    cudaFree(s->d_coarse_desc); s->d_coarse_desc = nullptr;
+    CK(cudaMalloc(&s->d_coarse_desc, sizeof(CoarseView) * n));
+    CK(cudaMemcpy(s->d_coarse_desc, desc.data(), sizeof(CoarseView) * n, cudaMemcpyHostToDevice));
     return VSB_OK;
 }
 
@@ -731,6 +763,35 @@ static void fill_tilemap(TileMap &tm, int n, const int *w, const int *h, int til
 }
 
 
+
+// (re)uploads the concatenated stage-1 / stage-2 tile lists after calibration changed them
+static int sync_tile_lists(vsb_stitcher *s)
+{
+    if (!s->tiles_dirty) return VSB_OK;
+    std::vector<uint32_t> a, b;
+    for (int i = 0; i < s->cfg.num_views; ++i) {
+        a.insert(a.end(), s->v[i].s1_tiles.begin(), s->v[i].s1_tiles.end());
+        b.insert(b.end(), s->v[i].s2_tiles.begin(), s->v[i].s2_tiles.end());
+    }
+    CK(cudaDeviceSynchronize());
+    cudaFree(s->d_s1_tiles); cudaFree(s->d_s2_tiles);
+    s->d_s1_tiles = s->d_s2_tiles = nullptr;
+    CK(cudaMalloc(&s->d_s1_tiles, std::max<size_t>(a.size(), 1) * 4));
+    CK(cudaMalloc(&s->d_s2_tiles, std::max<size_t>(b.size(), 1) * 4));
+    if (!a.empty()) CK(cudaMemcpy(s->d_s1_tiles, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
+    if (!b.empty()) CK(cudaMemcpy(s->d_s2_tiles, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    s->tiles_dirty = false;
+    return VSB_OK;
+}
+
+// every 128 x 8 tile of a w x h plane
+static void all_tiles(int view, int w, int h, std::vector<uint32_t> &out)
+{
+    out.clear();
+    for (int ty = 0; ty < (h + RM_BY - 1) / RM_BY; ++ty)
+        for (int tx = 0; tx < (w + RM_BX * RM_PX - 1) / (RM_BX * RM_PX); ++tx) out.push_back((uint32_t)view | ((uint32_t)tx << 8) | ((uint32_t)ty << 20));
+}
+
 // K3: G0 -> G2 for the needed tiles of views [v0, v1)
 static int launch_down2(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStream_t st)
 {
@@ -761,24 +822,35 @@ static int launch_down2(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
 static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, size_t out_pitch, cudaStream_t st)
 {
     const int n = s->cfg.num_views, nb = s->nb;
+    for (int k = 2; k < nb; ++k) {  // Gaussian levels 3..nb of every view (tiny planes)
+        Down1Params p;
+        std::memset(&p, 0, sizeof(p));
+        p.n = n;
+        double bytes = 0;
+        for (int i = 0; i < n; ++i) {
+            const View &V = s->v[i];
+            p.v[i].src = V.Gu[k]; p.v[i].dst = V.Gu[k + 1]; p.v[i].src_fs = V.gu_frame_stride[k]; p.v[i].dst_fs = V.gu_frame_stride[k + 1];
+            p.v[i].w = V.bw >> k; p.v[i].h = V.bh >> k;
+            const int wd = V.bw >> (k + 1), hd = V.bh >> (k + 1);
+            p.tiles_x[i] = (wd + D1_TX - 1) / D1_TX;
+            p.start[i + 1] = p.start[i] + p.tiles_x[i] * ((hd + D1_TY - 1) / D1_TY);
+            bytes += 3.0 * (V.bw >> k) * (V.bh >> k) + 3.0 * wd * hd;
+        }
+        k_down1<<<dim3(p.start[n], n_frames, 3), dim3(D1_TX, D1_TY), 0, st>>>(p);
+        ++s->launches;
+        static const char *names[MAXL] = {"", "", "down1_L3", "down1_L4", "down1_L5", "down1_L6", "down1_L7", ""};
+        prof_stage(s, st, names[k], bytes * n_frames);
+    }
     {
         CoarseParams p;
         std::memset(&p, 0, sizeof(p));
         p.geo = s->cgeo;
         for (int j = 0; j < s->cgeo.nlev; ++j) { p.cw[j] = s->cw[2 + j]; p.ch[j] = s->ch[2 + j]; p.dw[j] = s->dw[2 + j]; }
         p.c2 = s->C2; p.c2_fs = s->c2_frame_stride; p.tile_views = s->d_coarse_views; p.tiles_x = s->coarse_tiles_x;
-        double bytes = 0;
-        for (int i = 0; i < n; ++i) {
-            const View &V = s->v[i];
-            CoarseView &C = p.v[i];
-            C.g2 = V.G2; C.g2_fs = V.g2_frame_stride;
-            for (int j = 0; j < s->cgeo.nlev; ++j) C.w[j] = V.weight[2 + j];
-            C.x_tl = V.x_tl; C.y_tl = V.y_tl; C.bw = V.bw; C.bh = V.bh;
-            int nt = 0;
-            for (uint8_t b : V.g2_needed) nt += b;
-            bytes += 3.0 * nt * D2_TW * D2_TH;
-        }
-        bytes += 6.0 * s->cw[2] * s->ch[2];  // needed G2 in once + C2 (s16 x 3) out once
+        p.views = s->d_coarse_desc;
+        double bytes = 6.0 * s->cw[2] * s->ch[2];  // Gaussian levels >= 2 of every view in once + C2 (s16 x 3) out once
+        for (int i = 0; i < n; ++i)
+            for (int k = 2; k <= nb; ++k) bytes += 3.0 * (s->v[i].bw >> k) * (s->v[i].bh >> k);
         k_coarse<<<dim3(s->coarse_tiles_x * s->coarse_tiles_y, 3, n_frames), C_THREADS, s->coarse_smem, st>>>(p);
         ++s->launches;
         prof_stage(s, st, "coarse", bytes * n_frames);
@@ -813,43 +885,47 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
 {
     const int n = v1 - v0;
     int ws[MAXV], hs[MAXV];
+    int r = sync_tile_lists(s);
+    if (r != VSB_OK) return r;
     {
         Stage1Params p;
         std::memset(&p, 0, sizeof(p));
-        for (int j = 0; j < n; ++j) {
-            const View &V = s->v[v0 + j];
-            Stage1View &S = p.v[j];
-            S.xmap = V.xmap; S.ymap = V.ymap; S.lut = V.lut; S.P = V.P;
+        int first = 0, count = 0;
+        double bytes = 0;  // algorithmic: every source pixel once + P once
+        for (int i = 0; i < s->cfg.num_views; ++i) {
+            const View &V = s->v[i];
+            Stage1View &S = p.v[i];
+            S.xmap = V.xmap; S.ymap = V.ymap; S.P = V.P; S.gain = V.gain;
             S.map_pitch = V.map_pitch; S.p_pitch = V.p_pitch; S.p_frame_stride = V.p_frame_stride;
             S.w = V.roi_w; S.h = V.roi_h; S.src_w = V.src_w; S.src_h = V.src_h;
-            ws[j] = V.roi_w; hs[j] = V.roi_h;
+            if (i < v0) first += (int)V.s1_tiles.size();
+            else if (i < v1) { count += (int)V.s1_tiles.size(); bytes += 3.0 * V.src_w * V.src_h + 3.0 * V.roi_w * V.roi_h; }
         }
-        fill_tilemap(p.tm, n, ws, hs, RM_BX * RM_PX, RM_BY);
-        p.n_views = n; p.src_pitch = src_pitch;
+        p.tiles = s->d_s1_tiles + first;
+        p.v0 = v0; p.n_views = n; p.src_pitch = src_pitch;
         for (int f = 0; f < n_frames; ++f) for (int j = 0; j < n; ++j) p.src[f * n + j] = d_srcs[f * n + j];
-        k_remap_stage1<<<dim3(p.tm.start[n], n_frames), dim3(RM_BX, RM_BY), 0, st>>>(p);
+        if (count > 0) k_remap_stage1<<<dim3(count, n_frames), dim3(RM_BX, RM_BY), 0, st>>>(p);
         ++s->launches;
-        double bytes = 0;  // algorithmic: every source pixel once + P once
-        for (int j = 0; j < n; ++j) { const View &V = s->v[v0 + j]; bytes += 3.0 * V.src_w * V.src_h + 3.0 * V.roi_w * V.roi_h; }
         prof_stage(s, st, "remap_stage1", bytes * n_frames);
     }
     {
         Stage2Params p;
         std::memset(&p, 0, sizeof(p));
-        for (int j = 0; j < n; ++j) {
-            const View &V = s->v[v0 + j];
-            Stage2View &S = p.v[j];
+        int first = 0, count = 0;
+        double bytes = 0;  // P once + bordered planar G0 once
+        for (int i = 0; i < s->cfg.num_views; ++i) {
+            const View &V = s->v[i];
+            Stage2View &S = p.v[i];
             S.P = V.P; S.G0 = V.G0;
-            if (s->cfg.enable_local) { S.xmesh = V.mesh[V.mesh_cur][0]; S.ymesh = V.mesh[V.mesh_cur][1]; }
+            if (s->cfg.enable_local && V.mesh_cur >= 0) { S.xmesh = V.mesh[V.mesh_cur][0]; S.ymesh = V.mesh[V.mesh_cur][1]; }
             S.p_pitch = V.p_pitch; S.p_frame_stride = V.p_frame_stride; S.map_pitch = V.map_pitch; S.g0_frame_stride = V.g0_frame_stride;
             S.w = V.roi_w; S.h = V.roi_h; S.bw = V.bw; S.bh = V.bh; S.top = V.top; S.left = V.left;
-            ws[j] = V.bw; hs[j] = V.bh;
+            if (i < v0) first += (int)V.s2_tiles.size();
+            else if (i < v1) { count += (int)V.s2_tiles.size(); bytes += 3.0 * V.roi_w * V.roi_h + 3.0 * V.bw * V.bh; }
         }
-        fill_tilemap(p.tm, n, ws, hs, RM_BX * RM_PX, RM_BY);
-        k_remap_stage2<<<dim3(p.tm.start[n], n_frames), dim3(RM_BX, RM_BY), 0, st>>>(p);
+        p.tiles = s->d_s2_tiles + first;
+        if (count > 0) k_remap_stage2<<<dim3(count, n_frames), dim3(RM_BX, RM_BY), 0, st>>>(p);
         ++s->launches;
-        double bytes = 0;  // P once + bordered planar G0 once
-        for (int j = 0; j < n; ++j) { const View &V = s->v[v0 + j]; bytes += 3.0 * V.roi_w * V.roi_h + 3.0 * V.bw * V.bh; }
         prof_stage(s, st, "remap_stage2", bytes * n_frames);
     }
     if (s->fast) return launch_down2(s, v0, v1, n_frames, st);
@@ -1065,6 +1141,11 @@ int vsb_init_view(vsb_stitcher *s, int i, const uint8_t *mask, int mw, int mh, s
         V.g2_frame_stride = (size_t)3 * (width >> 2) * (height >> 2);
         CK(cudaMalloc(&V.G2, V.g2_frame_stride * F));
         CK(cudaMemsetAsync(V.G2, 0, V.g2_frame_stride * F, s->setup_stream));  // skipped tiles stay defined
+        V.Gu[2] = V.G2; V.gu_frame_stride[2] = V.g2_frame_stride;
+        for (int k = 3; k <= nb; ++k) {
+            V.gu_frame_stride[k] = (size_t)3 * (width >> k) * (height >> k);
+            CK(cudaMalloc(&V.Gu[k], V.gu_frame_stride[k] * F));
+        }
     } else {
         for (int k = 1; k <= nb; ++k) {
             V.g_frame_stride[k] = (size_t)3 * (width >> k) * (height >> k);
@@ -1073,8 +1154,11 @@ int vsb_init_view(vsb_stitcher *s, int i, const uint8_t *mask, int mw, int mh, s
     }
     V.map_pitch = align_up((size_t)mw * 4, 16);
     CK(cudaEventCreateWithFlags(&V.mesh_ready, cudaEventDisableTiming));
-    r = upload_lut(s, V);
-    if (r != VSB_OK) return r;
+    CK(cudaMemsetAsync(V.P, 0, V.p_frame_stride * F, s->setup_stream));  // tiles outside the camera frame are never written
+    CK(cudaStreamSynchronize(s->setup_stream));
+    all_tiles(i, V.bw, V.bh, V.s2_tiles);   // narrowed by build_fast_plan once every view is known
+    V.s1_tiles.clear();                      // filled by vsb_set_maps
+    s->tiles_dirty = true;
     V.inited = true;
     s->views_inited++;
     if (s->views_inited == s->cfg.num_views) return finalize(s);
@@ -1096,14 +1180,32 @@ int vsb_set_maps(vsb_stitcher *s, int i, const float *xmap, const float *ymap, i
     REQ(i >= 0 && i < s->cfg.num_views && s->v[i].inited, VSB_ERR_STATE, "set_maps: view %d is not initialised", i);
     View &V = s->v[i];
     REQ(w == V.roi_w && h == V.roi_h, VSB_ERR_INVALID, "set_maps: maps are %dx%d but the view's mask is %dx%d", w, h, V.roi_w, V.roi_h);
-    REQ(src_w > 0 && src_h > 0 && pitch >= (size_t)w * 4, VSB_ERR_INVALID, "set_maps: bad sizes");
+    REQ(src_w >= 2 && src_h >= 1 && pitch >= (size_t)w * 4, VSB_ERR_INVALID, "set_maps: bad sizes");
     DeviceGuard g(s->device);
     CK(cudaDeviceSynchronize());
     if (!V.xmap) { CK(cudaMalloc(&V.xmap, V.map_pitch * h)); CK(cudaMalloc(&V.ymap, V.map_pitch * h)); }
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     CK(cudaMemcpy2DAsync(V.xmap, V.map_pitch, xmap, pitch, (size_t)w * 4, h, kind, s->setup_stream));
     CK(cudaMemcpy2DAsync(V.ymap, V.map_pitch, ymap, pitch, (size_t)w * 4, h, kind, s->setup_stream));
+    CK(cudaMemsetAsync(V.P, 0, V.p_frame_stride * s->cfg.max_batch, s->setup_stream));
     CK(cudaStreamSynchronize(s->setup_stream));
+    // static tile table of remap #1: tiles in which at least one pixel has a tap inside the camera frame
+    std::vector<float> hx((size_t)w * h), hy((size_t)w * h);
+    CK(cudaMemcpy2D(hx.data(), (size_t)w * 4, V.xmap, V.map_pitch, (size_t)w * 4, h, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy2D(hy.data(), (size_t)w * 4, V.ymap, V.map_pitch, (size_t)w * 4, h, cudaMemcpyDeviceToHost));
+    V.s1_tiles.clear();
+    const int tw = RM_BX * RM_PX;
+    for (int ty = 0; ty < (h + RM_BY - 1) / RM_BY; ++ty)
+        for (int tx = 0; tx < (w + tw - 1) / tw; ++tx) {
+            bool any = false;
+            for (int y = ty * RM_BY; y < std::min(h, (ty + 1) * RM_BY) && !any; ++y)
+                for (int x = tx * tw; x < std::min(w, (tx + 1) * tw); ++x) {
+                    const float fx = hx[(size_t)y * w + x], fy = hy[(size_t)y * w + x];
+                    if (fx >= -1.f && fx < (float)src_w && fy >= -1.f && fy < (float)src_h) { any = true; break; }
+                }
+            if (any) V.s1_tiles.push_back((uint32_t)i | ((uint32_t)tx << 8) | ((uint32_t)ty << 20));
+        }
+    s->tiles_dirty = true;
     V.src_w = src_w; V.src_h = src_h; V.has_maps = true;
     return VSB_OK;
 }
@@ -1111,10 +1213,11 @@ int vsb_set_maps(vsb_stitcher *s, int i, const float *xmap, const float *ymap, i
 int vsb_set_gain(vsb_stitcher *s, int i, float gain)
 {
     REQ(s && i >= 0 && i < s->cfg.num_views && s->v[i].inited, VSB_ERR_STATE, "set_gain: view %d is not initialised", i);
+    REQ(gain >= 0.f && gain < 1e6f, VSB_ERR_INVALID, "set_gain: gain must be a finite non-negative number");
     DeviceGuard g(s->device);
     CK(cudaDeviceSynchronize());
     s->v[i].gain = gain;
-    return upload_lut(s, s->v[i]);
+    return VSB_OK;
 }
 
 // MeshWarper::convertMeshesToMap for one view (360_stitcher/meshwarper.cpp:823-886), entirely on the device
@@ -1360,6 +1463,17 @@ int vsb_debug_read(vsb_stitcher *s, int what, int view, int level, int frame, vo
         uint8_t *o = (uint8_t *)h_dst;
         for (int y = 0; y < h; ++y)
             for (int x = 0; x < w; ++x) o[(size_t)y * w + x] = V.g2_needed[(size_t)(y / D2_TH) * V.d2_tiles_x + x / D2_TW];
+        return VSB_OK;
+    }
+    case 7: {  // which bordered level-0 samples k_remap_stage2 computes (1) / skips because nothing reads them (0)
+        REQ(bytes == (size_t)V.bw * V.bh, VSB_ERR_INVALID, "debug_read: size mismatch");
+        std::memset(h_dst, 0, bytes);
+        uint8_t *o = (uint8_t *)h_dst;
+        for (uint32_t tl : V.s2_tiles) {
+            const int x0 = (int)((tl >> 8) & 0xfff) * RM_BX * RM_PX, y0 = (int)(tl >> 20) * RM_BY;
+            for (int y = y0; y < std::min(V.bh, y0 + RM_BY); ++y)
+                for (int x = x0; x < std::min(V.bw, x0 + RM_BX * RM_PX); ++x) o[(size_t)y * V.bw + x] = 1;
+        }
         return VSB_OK;
     }
     default:

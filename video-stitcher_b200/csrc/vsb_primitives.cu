@@ -16,7 +16,8 @@ __global__ void k_remap_linear_u8c3(const uint8_t *__restrict__ src, int sw, int
     if (x >= dw || y >= dh) return;
     const float fx = *(const float *)((const char *)xmap + (size_t)y * mp + (size_t)x * 4);
     const float fy = *(const float *)((const char *)ymap + (size_t)y * mp + (size_t)x * 4);
-    const unsigned v = remap_px_u8c3(src, sp, sw, sh, fx, fy);
+    // the fused path's tap routine (word loads, biased conversions); the plain byte-wise form for 1-pixel-wide sources
+    const unsigned v = sw >= 2 ? remap_gain_px<false>(src, sp, sw, sh, fx, fy, 1.f) : remap_px_u8c3(src, sp, sw, sh, fx, fy);
     uint8_t *d = dst + (size_t)y * dp + (size_t)x * 3;
     d[0] = v & 0xff; d[1] = (v >> 8) & 0xff; d[2] = (v >> 16) & 0xff;
 }
