@@ -1,17 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- stitched frames/s of the per-frame 360-degree compose path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch F] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch F] [--workload cfg2] [--impl ours|reference]
 
-A step = one vsb_compose submission of F frames of the workload (config 2 of BASELINE.json: 6 x 1080p ->
-3840-wide spherical panorama, CPW mesh remap on, 5-band blend).  Source frames live in a ring of frame sets
-larger than L2, so every step reads its inputs from HBM.
-  value  : frames/s, inputs already resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e    : frames/s through vsb_compose_host (pinned HOST buffers, H2D + D2H inside the timed region)
-  roofline : dominant kernel, algorithmic bytes / mean device time from per-kernel CUDA events (vsb_get_profile)
-  cpu_baseline : oracle-G (the CPU port of the reference arithmetic) on the box's host cores, bounded sample
-N > 1 (torchrun): frame-level replicas, one process per GPU, no data-path collective ("weak" scaling).
---impl reference : the CPU implementation on all host cores, same config/metric (rank 0 only).
+A step = one vsb_compose submission of F frames (default 8) of the workload (BASELINE.json configs[1]: 6 x 1080p ->
+3840-wide spherical panorama, CPW mesh remap on, 5-band blend).  Source frames live in a ring of frame sets larger than
+L2, so every step reads its inputs from HBM.
+  value        frames/s with inputs resident in HBM; CUDA events on the launching stream; max over ranks
+  e2e          frames/s through vsb_compose_host: pinned HOST frames in, host panoramas out, H2D + D2H inside the timed region
+  roofline     the dominant kernel: algorithmic bytes / mean device time, from CUDA events around every kernel of the
+               timed submissions (vsb_set_profiling); `traffic` = DRAM bytes of the committed ncu capture (profiles/)
+  roofline_path  the whole path against B_io = sources once + CV_16SC3 panorama once
+  cpu_baseline the reference's own vendored OpenCV 3.4.0 CPU code (oracle/_ref, kind "reference") -- or the oracle-G port
+               when that library is absent -- timed on this box's host cores on a bounded sample of the same workload
+N > 1 (torchrun): every rank composes its own frame stream (frame-level replicas, no data-path collective; "weak").
+--impl reference : the CPU implementation alone, all host threads, same config / metric (rank 0 only).
 """
 import argparse
 import json
@@ -30,10 +33,13 @@ WORKLOADS = {
                  name="6x1080p->3840 spherical, CPW on, 5 bands"),
     "cfg3": dict(n_views=6, src_w=1920, src_h=1080, pano_width=7680, num_bands=5, enable_local=True, projection=0,
                  name="6x1080p->7680 spherical, CPW on, 5 bands"),
+    "cfg1": dict(n_views=2, src_w=1280, src_h=720, pano_width=4021, num_bands=5, enable_local=False, projection=0,
+                 name="2x720p->4021 spherical, CPW off, 5 bands"),
     "tiny": dict(n_views=4, src_w=320, src_h=240, pano_width=1024, num_bands=3, enable_local=True, projection=0,
                  name="4x320x240->1024 (debug)"),
 }
 RING = 8  # distinct frame sets resident in HBM (8 x 37 MB = 299 MB > 126 MB L2 at cfg2)
+METRIC = "stitched equirect frames/sec"
 
 
 class ClockSampler(threading.Thread):
@@ -88,62 +94,102 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def make_frames(cfg, n_sets):
+def make_frames(cfg, n_sets, first=0):
     import vsb200
     S = vsb200.synth
-    return [[S.frame(i, f, cfg["src_w"], cfg["src_h"]) for i in range(cfg["n_views"])] for f in range(n_sets)]
+    return [[S.frame(i, first + f, cfg["src_w"], cfg["src_h"]) for i in range(cfg["n_views"])] for f in range(n_sets)]
 
 
-def cpu_reference_run(cfg, frames, steps, warmup, threads):
-    """Times the CPU implementation (oracle-G port of the reference arithmetic) on `threads` host threads."""
+def cpu_compose_run(cfg, frames, budget_s, threads):
+    """Times the CPU implementation of the path on `threads` host threads for about `budget_s` seconds.
+
+    Preferred: oracle/_ref (the reference's vendored OpenCV 3.4.0 CPU primitives + the CPU branch of its MultiBandBlender),
+    in its two honest configurations -- views in sequence with OpenCV's own parallel_for_ threads, and one thread per view
+    (cv::pyrDown / pyrUp are single-threaded in this OpenCV) -- the faster one is reported.  Fallback: the oracle-G port.
+    Static inputs (maps, seam masks, mesh maps, gains) are the oracle's, shared by every implementation."""
     import vsb200
     from oracle import oracle as og
     from oracle import pipeline as op
+    from oracle import ref as vr
     og.set_num_threads(threads)
     rig = op.OracleRig(cfg["n_views"], cfg["src_w"], cfg["src_h"], cfg["pano_width"], cfg["projection"], cfg["num_bands"],
                        cfg["enable_local"], vsb200.synth.gains(cfg["n_views"]))
     if cfg["enable_local"]:
         for i in range(cfg["n_views"]):
             rig.set_mesh(i, *vsb200.synth.mesh(*rig.sizes[i]))
-    for w in range(warmup):
-        rig.compose(frames[w % len(frames)])
-    t0 = time.perf_counter()
-    for k in range(steps):
-        rig.compose(frames[k % len(frames)])
-    dt = time.perf_counter() - t0
-    return steps / dt, dt
+    runs = []
+    if vr.available():
+        cpu = vr.RigC(rig)
+        modes = [("views in sequence, OpenCV parallel_for_ threads", False), ("one thread per view (OpenMP)", True)]
+        kind = "reference"
+        def step(k, par):
+            cpu.compose(frames[k % len(frames)], parallel_views=par)
+    else:
+        modes = [("oracle-G C port, OpenMP over rows", False)]
+        kind = "port"
+        def step(k, par):
+            rig.compose(frames[k % len(frames)])
+    for label, par in modes:
+        if kind == "reference":
+            vr.set_num_threads(1 if par else threads)
+        step(0, par)  # warm-up (allocations, thread pool)
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            step(n, par)
+            n += 1
+            dt = time.perf_counter() - t0
+            if dt >= budget_s / len(modes) or n >= 400:
+                break
+        runs.append((n / dt, n, dt, label))
+    best = max(runs)
+    used = min(threads, cfg["n_views"]) if best[3].startswith("one thread") else threads
+    sample = (f"{best[1]} frames of the full {cfg['name']} workload in {best[2]:.1f} s; {best[3]}; "
+              + "; ".join(f"{lab}: {fps:.2f} fps" for fps, _, _, lab in runs))
+    return best[0], kind, used, sample
 
 
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
     threads = host_cores()
-    steps, warmup = max(1, min(args.steps, 40)), max(1, min(args.warmup, 3))
-    frames = make_frames(cfg, min(RING, steps))
-    fps, dt = cpu_reference_run(cfg, frames, steps, warmup, threads)
-    sample = f"{steps} frames of the full {cfg['name']} workload (1 frame per step), oracle-G CPU port, OpenMP over rows"
+    frames = make_frames(cfg, 4)
+    budget = min(90.0, max(8.0, 2.0 * max(1, args.steps) / 10.0))
+    fps, kind, used, sample = cpu_compose_run(cfg, frames, budget, threads)
     line = {
-        "impl": "reference", "metric": "stitched equirect frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/s16 (fp32 taps)", "data": "synthetic",
-        "config": {"workload": cfg["name"], "frames_per_step": 1, "inputs": "host memory"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": cfg["name"], "frames_per_step": 1, "inputs": "host memory", "host_threads": threads},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": used, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(kernel, frames_per_launch):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json), scaled to
+    this run's frames per launch; None when no capture of that kernel is on file."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = t["kernels"][kernel]
+        return e["dram_bytes_per_launch"] * frames_per_launch / e["frames_per_launch"]
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--batch", type=int, default=1, help="frames per vsb_compose submission (F)")
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=8, help="frames per vsb_compose submission (F)")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=16.0, help="CPU baseline sample budget")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -177,7 +223,8 @@ def main():
             st.set_mesh(i, mx.ctypes.data, my.ctypes.data, mx.shape[0], mx.shape[1])
     roi, _, nb = st.get_roi()
     OW, OH = roi[2], roi[3]
-    src_pitch, out_pitch = cfg["src_w"] * 3, OW * 6
+    src_pitch = cfg["src_w"] * 3
+    out_pitch = (OW * 6 + 255) // 256 * 256  # pitched rows like cv::cuda::GpuMat (cudaMallocPitch): 16-byte vector stores
 
     # ring of RING frame sets (each rank gets different frames: frame-level data parallelism)
     n_sets = max(RING, F)
@@ -185,7 +232,7 @@ def main():
     for f in range(n_sets):
         host_sets.append([torch.from_numpy(S.frame(i, f + rank * n_sets, cfg["src_w"], cfg["src_h"])).pin_memory() for i in range(n)])
     dev_sets = [[t.cuda(non_blocking=True) for t in fs] for fs in host_sets]
-    outs = [torch.empty((OH, OW, 3), dtype=torch.int16, device="cuda") for _ in range(F)]
+    outs = [torch.empty((OH, out_pitch // 2), dtype=torch.int16, device="cuda") for _ in range(F)]
     stream = torch.cuda.current_stream().cuda_stream
     torch.cuda.synchronize()
 
@@ -231,7 +278,7 @@ def main():
     clocks = sampler.summary(t_wall0, t_wall1)
     fps = world * F * K / (ms / 1000.0)
 
-    # ---- per-kernel device times over K steps (events on the launching stream), dominant kernel roofline
+    # ---- per-kernel device times (events on the launching stream around every kernel), dominant kernel roofline
     st.set_profiling(True)
     acc = {}
     prof_steps = min(K, 50)
@@ -252,7 +299,7 @@ def main():
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s"
     b_io = n * cfg["src_w"] * cfg["src_h"] * 3 + OW * OH * 6  # sources once + CV_16SC3 pano once
     roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[top]["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": kernels[top]["GBps"] / peak, "traffic": ncu_traffic(top, F), "peak_source": peak_src,
                 "alg_bytes_per_launch": kernels[top]["alg_bytes"], "ms_per_launch": kernels[top]["ms"],
                 "share_of_step": kernels[top]["ms"] / sum(v["ms"] for v in kernels.values())}
     roofline_path = {"alg_bytes_per_frame": b_io, "achieved": b_io * fps / world / 1e9, "peak": peak, "unit": "GB/s",
@@ -264,10 +311,10 @@ def main():
         h_outs = [torch.empty((OH, OW, 3), dtype=torch.int16).pin_memory() for _ in range(F)]
         def host_call(s0):
             srcs = [host_sets[(s0 + j) % n_sets][i].data_ptr() for j in range(F) for i in range(n)]
-            st.compose_host(srcs, src_pitch, [o.data_ptr() for o in h_outs], out_pitch)
+            st.compose_host(srcs, src_pitch, [o.data_ptr() for o in h_outs], OW * 6)
         for w in range(3):
             host_call(w)
-        Ke = max(3, min(K, 60))
+        Ke = max(3, min(K, 40))
         barrier()
         t0 = time.perf_counter()
         for k in range(Ke):
@@ -279,21 +326,20 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": world * F * Ke / dt, "unit": "frames/s", "h2d_bytes_per_step": F * n * cfg["src_w"] * cfg["src_h"] * 3,
-               "d2h_bytes_per_step": F * OW * OH * 6, "steps": Ke, "api": "vsb_compose_host (pinned host buffers, H2D+D2H inside)"}
+               "d2h_bytes_per_step": F * OW * OH * 6, "steps": Ke,
+               "api": "vsb_compose_host: pinned host frames in, host panoramas out; upload / compose / download pipelined per frame"}
 
-    # ---- CPU baseline: oracle-G port on the host cores, rank 0 at N=1 only, bounded sample
+    # ---- CPU baseline on the host cores, rank 0 at N=1 only, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_cores()
         frames_np = [[t.numpy() for t in fs] for fs in host_sets[:4]]
-        n_cpu = 12
-        cfps, cdt = cpu_reference_run(cfg, frames_np, n_cpu, 1, threads)
-        cpu = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": f"{n_cpu} frames of the same workload, oracle-G (C, OpenMP over rows), {cdt:.1f} s"}
+        cfps, kind, used, sample = cpu_compose_run(cfg, frames_np, args.cpu_seconds, threads)
+        cpu = {"value": cfps, "unit": "frames/s", "cores": used, "kind": kind, "sample": sample}
 
     if rank == 0:
         line = {
-            "metric": "stitched equirect frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/s16 (fp32 taps)", "data": "synthetic",
             "config": {"workload": cfg["name"], "frames_per_step": F, "ring_frame_sets": n_sets,

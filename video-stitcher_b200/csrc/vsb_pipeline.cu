@@ -451,7 +451,8 @@ struct vsb_stitcher {
     uint32_t *d_s1_tiles = nullptr, *d_s2_tiles = nullptr;  // concatenated per-view lists, view order
     vsb::CoarseView *d_coarse_desc = nullptr;
     bool tiles_dirty = true;
-    cudaStream_t setup_stream = nullptr, mesh_stream = nullptr, io_stream = nullptr;
+    cudaStream_t setup_stream = nullptr, mesh_stream = nullptr, io_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+    cudaEvent_t ev_in[vsb::MAX_BATCH] = {}, ev_done[vsb::MAX_BATCH] = {};
     cudaEvent_t last_compose = nullptr;
     bool last_compose_valid = false;
     std::mutex mu;  // guards mesh publication
@@ -1030,6 +1031,9 @@ int vsb_destroy(vsb_stitcher *s)
     if (s->setup_stream) cudaStreamDestroy(s->setup_stream);
     if (s->mesh_stream) cudaStreamDestroy(s->mesh_stream);
     if (s->io_stream) cudaStreamDestroy(s->io_stream);
+    if (s->in_stream) cudaStreamDestroy(s->in_stream);
+    if (s->out_stream) cudaStreamDestroy(s->out_stream);
+    for (int f = 0; f < MAX_BATCH; ++f) { if (s->ev_in[f]) cudaEventDestroy(s->ev_in[f]); if (s->ev_done[f]) cudaEventDestroy(s->ev_done[f]); }
     if (s->last_compose) cudaEventDestroy(s->last_compose);
     for (int i = 0; i <= VSB_MAX_STAGES; ++i) if (s->prof_ev[i]) cudaEventDestroy(s->prof_ev[i]);
     cudaGetLastError();
@@ -1065,6 +1069,7 @@ int vsb_prepare(vsb_stitcher *s, const int *corners_xy, const int *sizes_wh)
         s->ch[k] = k == 0 ? H : (s->ch[k - 1] + 1) / 2;
         CK(cudaMalloc(&s->dw[k], sizeof(float) * s->cw[k] * s->ch[k]));
     }
+    cudaFree(s->stage_src); cudaFree(s->stage_out); s->stage_src = nullptr; s->stage_out = nullptr;  // sized per calibration
     s->views_inited = 0; s->prepared = true; s->finalized = false;
     return VSB_OK;
 }
@@ -1321,29 +1326,45 @@ int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs
     for (int i = 1; i < n; ++i) REQ(s->v[i].src_w == sw && s->v[i].src_h == sh, VSB_ERR_INVALID, "compose_host: all views must share one source size");
     REQ(src_pitch >= (size_t)sw * 3 && out_pitch >= (size_t)s->roi_final[2] * 6, VSB_ERR_INVALID, "compose_host: pitch too small");
     if (!s->stage_src) {
-        s->stage_src_pitch = align_up((size_t)sw * 3, 256);
-        s->stage_src_frame = s->stage_src_pitch * sh;
+        s->stage_src_pitch = align_up((size_t)sw * 3, 4);  // tight rows: a packed host frame moves as ONE contiguous DMA
+        s->stage_src_frame = align_up(s->stage_src_pitch * sh + 16, 256);
         s->stage_out_pitch = align_up((size_t)s->roi_final[2] * 6, 256);
         s->stage_out_frame = s->stage_out_pitch * s->roi_final[3];
         CK(cudaMalloc(&s->stage_src, s->stage_src_frame * n * F));
         CK(cudaMalloc(&s->stage_out, s->stage_out_frame * F));
     }
-    cudaStream_t st = s->io_stream;
-    const uint8_t *d_srcs[MAX_BATCH * MAXV];
-    int16_t *d_outs[MAX_BATCH];
+    if (!s->in_stream) {
+        CK(cudaStreamCreateWithFlags(&s->in_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s->out_stream, cudaStreamNonBlocking));
+        for (int f = 0; f < MAX_BATCH; ++f) {
+            CK(cudaEventCreateWithFlags(&s->ev_in[f], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s->ev_done[f], cudaEventDisableTiming));
+        }
+    }
+    // Three-stage pipeline over the frames of the submission: upload (copy engine, in_stream) -> compose (io_stream) ->
+    // download (second copy engine, out_stream).  Frame f+1 uploads while frame f composes and frame f-1 downloads.
+    // (The reference uploads pageable memory on the compute stream and downloads in the consumer thread, A/timed.cpp:68,252.)
     for (int f = 0; f < n_frames; ++f) {
+        const uint8_t *d_srcs[MAXV];
         for (int i = 0; i < n; ++i) {
             uint8_t *d = s->stage_src + s->stage_src_frame * (size_t)(f * n + i);
-            CK(cudaMemcpy2DAsync(d, s->stage_src_pitch, h_srcs[f * n + i], src_pitch, (size_t)sw * 3, sh, cudaMemcpyHostToDevice, st));
-            d_srcs[f * n + i] = d;
+            if (src_pitch == s->stage_src_pitch)
+                CK(cudaMemcpyAsync(d, h_srcs[f * n + i], src_pitch * sh, cudaMemcpyHostToDevice, s->in_stream));
+            else
+                CK(cudaMemcpy2DAsync(d, s->stage_src_pitch, h_srcs[f * n + i], src_pitch, (size_t)sw * 3, sh, cudaMemcpyHostToDevice, s->in_stream));
+            d_srcs[i] = d;
         }
-        d_outs[f] = (int16_t *)((char *)s->stage_out + s->stage_out_frame * f);
+        CK(cudaEventRecord(s->ev_in[f], s->in_stream));
+        CK(cudaStreamWaitEvent(s->io_stream, s->ev_in[f], 0));
+        int16_t *d_out = (int16_t *)((char *)s->stage_out + s->stage_out_frame * f);
+        r = vsb_compose(s, 1, d_srcs, s->stage_src_pitch, &d_out, s->stage_out_pitch, s->io_stream);
+        if (r != VSB_OK) { cudaDeviceSynchronize(); return r; }
+        CK(cudaEventRecord(s->ev_done[f], s->io_stream));
+        CK(cudaStreamWaitEvent(s->out_stream, s->ev_done[f], 0));
+        CK(cudaMemcpy2DAsync(h_outs[f], out_pitch, d_out, s->stage_out_pitch, (size_t)s->roi_final[2] * 6, s->roi_final[3], cudaMemcpyDeviceToHost, s->out_stream));
     }
-    r = vsb_compose(s, n_frames, d_srcs, s->stage_src_pitch, d_outs, s->stage_out_pitch, st);
-    if (r != VSB_OK) return r;
-    for (int f = 0; f < n_frames; ++f)
-        CK(cudaMemcpy2DAsync(h_outs[f], out_pitch, d_outs[f], s->stage_out_pitch, (size_t)s->roi_final[2] * 6, s->roi_final[3], cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(s->out_stream));
+    CK(cudaStreamSynchronize(s->io_stream));
     return VSB_OK;
 }
 
