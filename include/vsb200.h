@@ -107,6 +107,10 @@ int vsb_custom_resize(const float *d_in, int cols, int rows, size_t in_pitch_byt
 /* ---- B4: per-view feed = stitch_online minus the H2D upload (A/timed.cpp:56-121):
  *      remap#1 -> gain -> remap#2 -> MultiBandBlender::feed_online (S/src/blenders.cpp:700-749) -------- */
 int vsb_feed(vsb_stitcher *s, int i, const uint8_t *d_bgr, size_t pitch_bytes, void *stream);
+/* ---- B4, inner boundary: MultiBandBlender::feed_online(cuda::GpuMat &gpu_img, int img_num, cuda::Stream &stream)
+ *      (S/include/opencv2/stitching/detail/blenders.hpp:138, S/src/blenders.cpp:700-749) for callers that keep their own
+ *      cuda::remap calls: d_warped = the warped CV_8UC3 view, size = the view's seam mask size. ------------------ */
+int vsb_feed_warped(vsb_stitcher *s, int i, const uint8_t *d_warped, size_t pitch_bytes, void *stream);
 /* ---- B5: MultiBandBlender::blend(dst, dst_mask, gpuOut, true) (S/src/blenders.cpp:758-832).
  *      d_out: caller-owned CV_16SC3 of roi_final size. ------------------------------------------------- */
 int vsb_blend(vsb_stitcher *s, int16_t *d_out, size_t out_pitch_bytes, void *stream);

@@ -1,0 +1,206 @@
+/*
+ * vsb200.hpp -- C++ adapter over the C ABI (vsb200.h) that mirrors the reference's own class / function names and call
+ * order for the per-frame compose path, so host code shaped like 360_stitcher/timed.cpp + calibration.cpp keeps its
+ * structure (the north star: "host code stays C++").  Header-only; needs nothing but libvsb200.so.
+ *
+ * Reference interfaces mirrored (paths relative to the reference root):
+ *   cv::detail::MultiBandBlender   sources/modules/stitching/include/opencv2/stitching/detail/blenders.hpp:126-176
+ *       MultiBandBlender(try_gpu, num_bands, weight_type) / setNumBands / prepare / init_gpu / feed_online / blend
+ *   stitch_online / stitch_one     360_stitcher/timed.cpp:56-152
+ *   custom_resize                  360_stitcher/resize.cu:30-45 (decl 360_stitcher/calibration.h:15)
+ *   MeshWarper::convertMeshesToMap 360_stitcher/meshwarper.h:34-36, meshwarper.cpp:823-886
+ *   {Spherical,Cylindrical}WarperGpu::warpRoi / buildMaps   .../detail/warpers.hpp:489-550
+ *
+ * Types: the reference passes cv::cuda::GpuMat / cv::cuda::Stream.  This header does not depend on OpenCV: DeviceMat is
+ * the (data, step, rows, cols) quadruple of a GpuMat / PtrStepSz and Stream is a cudaStream_t.  When OpenCV's core/cuda.hpp
+ * has been included first, from_gpumat() / from_stream() convert without copying.
+ *
+ * Errors: the reference throws cv::Exception from CV_Assert / cudaSafeCall (core/cuda/common.hpp:66-74); here every
+ * non-zero status of the C ABI is re-thrown as vsb::Error (std::runtime_error) carrying vsb_last_error().
+ */
+#ifndef VSB200_HPP
+#define VSB200_HPP
+
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "vsb200.h"
+
+namespace vsb {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &what) : std::runtime_error(what), code(c) {}
+};
+inline void check(int rc)
+{
+    if (rc != VSB_OK) throw Error(rc, std::string("vsb200: ") + vsb_last_error());
+}
+
+typedef void *Stream;  /* cudaStream_t */
+
+struct Point { int x, y; Point(int x_ = 0, int y_ = 0) : x(x_), y(y_) {} };
+struct Size { int width, height; Size(int w = 0, int h = 0) : width(w), height(h) {} };
+struct Rect { int x, y, width, height; Rect(int x_ = 0, int y_ = 0, int w = 0, int h = 0) : x(x_), y(y_), width(w), height(h) {} };
+
+/* a pitched device matrix the caller owns (what a cv::cuda::GpuMat header describes) */
+struct DeviceMat {
+    void *data;
+    size_t step;  /* bytes */
+    int rows, cols;
+    DeviceMat() : data(0), step(0), rows(0), cols(0) {}
+    DeviceMat(void *d, size_t s, int r, int c) : data(d), step(s), rows(r), cols(c) {}
+};
+#ifdef OPENCV_CORE_CUDA_HPP
+inline DeviceMat from_gpumat(const cv::cuda::GpuMat &m) { return DeviceMat(m.data, m.step, m.rows, m.cols); }
+#endif
+
+/* ---- rotation warpers: warpRoi / buildMaps (static inputs of remap #1) -------------------------------------------- */
+class RotationWarperGpu {
+public:
+    RotationWarperGpu(int projection, float scale) : projection_(projection), scale_(scale) {}
+    /* Rect warpRoi(Size src_size, InputArray K, InputArray R): K, R = 3x3 CV_32F, row major */
+    Rect warpRoi(Size src, const float K[9], const float R[9]) const
+    {
+        int roi[4];
+        check(vsb_warp_roi(projection_, scale_, K, R, src.width, src.height, roi));
+        return Rect(roi[0], roi[1], roi[2], roi[3]);
+    }
+    /* Rect buildMaps(Size, K, R, GpuMat &xmap, GpuMat &ymap): the maps must be roi-sized CV_32FC1 device matrices */
+    Rect buildMaps(Size src, const float K[9], const float R[9], DeviceMat xmap, DeviceMat ymap, Stream stream = 0) const
+    {
+        int roi[4];
+        if (xmap.step != ymap.step) throw Error(VSB_ERR_INVALID, "vsb200: buildMaps: xmap and ymap must share one pitch");
+        check(vsb_build_maps(projection_, scale_, K, R, src.width, src.height, (float *)xmap.data, (float *)ymap.data, xmap.step, roi, stream));
+        return Rect(roi[0], roi[1], roi[2], roi[3]);
+    }
+private:
+    int projection_;
+    float scale_;
+};
+struct SphericalWarperGpu : RotationWarperGpu { explicit SphericalWarperGpu(float scale) : RotationWarperGpu(VSB_PROJ_SPHERICAL, scale) {} };
+struct CylindricalWarperGpu : RotationWarperGpu { explicit CylindricalWarperGpu(float scale) : RotationWarperGpu(VSB_PROJ_CYLINDRICAL, scale) {} };
+
+/* ---- extern void custom_resize(GpuMat &in, GpuMat &out, Size t_size), 360_stitcher/resize.cu:30 --------------------
+ * `out` must already be a t_size CV_32FC1 device matrix (the reference creates it); asynchronous on `stream` instead of
+ * the reference's cudaDeviceSynchronize(). */
+inline void custom_resize(const DeviceMat &in, DeviceMat &out, Size t_size, Stream stream = 0)
+{
+    if (out.cols != t_size.width || out.rows != t_size.height) throw Error(VSB_ERR_INVALID, "vsb200: custom_resize: out must be t_size");
+    check(vsb_custom_resize((const float *)in.data, in.cols, in.rows, in.step, (float *)out.data, t_size.width, t_size.height, out.step, stream));
+}
+
+/* ---- MultiBandBlender (the authors' GPU variant) + the stitch_online / stitch_one drivers ------------------------- */
+class MultiBandBlender {
+public:
+    /* MultiBandBlender(int try_gpu = false, int num_bands = 5, int weight_type = CV_32F): only the CV_32F weights the
+     * application uses exist here; try_gpu is implied.  num_views replaces the reference's hard-coded vector<...>(6). */
+    explicit MultiBandBlender(int num_views, int num_bands = 5, bool enable_local = true, int max_batch = 1, int device = -1)
+        : h_(0), n_(num_views), next_view_(0)
+    {
+        cfg_.num_views = num_views; cfg_.num_bands = num_bands; cfg_.enable_local = enable_local ? 1 : 0;
+        cfg_.max_batch = max_batch; cfg_.device = device;
+        check(vsb_create(&cfg_, &h_));
+    }
+    ~MultiBandBlender() { vsb_destroy(h_); }
+
+    int numBands() const { return cfg_.num_bands; }
+    /* setNumBands must precede prepare(), as in the reference (calibration.cpp:193-196) */
+    void setNumBands(int val)
+    {
+        cfg_.num_bands = val;
+        vsb_destroy(h_); h_ = 0; next_view_ = 0;
+        check(vsb_create(&cfg_, &h_));
+    }
+    /* Blender::prepare(const std::vector<Point> &corners, const std::vector<Size> &sizes) */
+    void prepare(const std::vector<Point> &corners, const std::vector<Size> &sizes)
+    {
+        if ((int)corners.size() != n_ || (int)sizes.size() != n_) throw Error(VSB_ERR_INVALID, "vsb200: prepare: one corner and one size per view");
+        std::vector<int> c(2 * n_), s(2 * n_);
+        for (int i = 0; i < n_; ++i) { c[2 * i] = corners[i].x; c[2 * i + 1] = corners[i].y; s[2 * i] = sizes[i].width; s[2 * i + 1] = sizes[i].height; }
+        check(vsb_prepare(h_, c.data(), s.data()));
+        next_view_ = 0;
+    }
+    /* void init_gpu(GpuMat img (unused by the reference), GpuMat mask, Point tl): views in push_back order */
+    void init_gpu(const DeviceMat &mask, Point tl)
+    {
+        check(vsb_init_view(h_, next_view_, (const uint8_t *)mask.data, mask.cols, mask.rows, mask.step, tl.x, tl.y, 1));
+        ++next_view_;
+    }
+    void init_host_mask(const uint8_t *mask, int w, int h, size_t step, Point tl)
+    {
+        check(vsb_init_view(h_, next_view_, mask, w, h, step, tl.x, tl.y, 0));
+        ++next_view_;
+    }
+    /* static inputs of stitch_online: x_maps[i] / y_maps[i] (calibration.cpp:221), gains (timed.cpp:94) */
+    void setMaps(int i, const DeviceMat &xmap, const DeviceMat &ymap, Size src)
+    {
+        if (xmap.step != ymap.step) throw Error(VSB_ERR_INVALID, "vsb200: setMaps: xmap and ymap must share one pitch");
+        check(vsb_set_maps(h_, i, (const float *)xmap.data, (const float *)ymap.data, xmap.cols, xmap.rows, xmap.step, 1, src.width, src.height));
+    }
+    void setGain(int i, double gain) { check(vsb_set_gain(h_, i, (float)gain)); }
+
+    /* void feed_online(cuda::GpuMat &gpu_img, int img_num, cuda::Stream &stream): gpu_img = warped CV_8UC3 view */
+    void feed_online(const DeviceMat &gpu_img, int img_num, Stream stream)
+    {
+        check(vsb_feed_warped(h_, img_num, (const uint8_t *)gpu_img.data, gpu_img.step, stream));
+    }
+    /* stitch_online(compose_scale, img, x_map, y_map, x_mesh, y_mesh, ..., mb, gc, thread_num) minus the H2D upload:
+     * remap #1 -> gain -> remap #2 -> feed_online in one call, from the camera frame already on the device */
+    void stitch_online(const DeviceMat &bgr_frame, int img_num, Stream stream)
+    {
+        check(vsb_feed(h_, img_num, (const uint8_t *)bgr_frame.data, bgr_frame.step, stream));
+    }
+    /* void blend(InputOutputArray dst, InputOutputArray dst_mask, cuda::GpuMat &gpuOut, bool outputGpu = true): gpuOut is
+     * CV_16SC3 of resultRoi() size, CALLER-owned here (the reference allocates it and moves it into its result queue) */
+    void blend(DeviceMat &gpuOut, Stream stream)
+    {
+        check(vsb_blend(h_, (int16_t *)gpuOut.data, gpuOut.step, stream));
+    }
+    /* stitch_one for a batch of frames: srcs[f * num_views + i] */
+    void stitch(const std::vector<DeviceMat> &srcs, std::vector<DeviceMat> &outs, Stream stream)
+    {
+        if (outs.empty() || srcs.size() != outs.size() * (size_t)n_) throw Error(VSB_ERR_INVALID, "vsb200: stitch: need num_views sources per output");
+        std::vector<const uint8_t *> sp(srcs.size());
+        std::vector<int16_t *> op(outs.size());
+        for (size_t k = 0; k < srcs.size(); ++k) { sp[k] = (const uint8_t *)srcs[k].data; if (srcs[k].step != srcs[0].step) throw Error(VSB_ERR_INVALID, "vsb200: stitch: sources must share one pitch"); }
+        for (size_t k = 0; k < outs.size(); ++k) { op[k] = (int16_t *)outs[k].data; if (outs[k].step != outs[0].step) throw Error(VSB_ERR_INVALID, "vsb200: stitch: outputs must share one pitch"); }
+        check(vsb_compose(h_, (int)outs.size(), sp.data(), srcs[0].step, op.data(), outs[0].step, stream));
+    }
+    /* dst_roi_final_ (the Rect `blend` crops to) and the padded dst_roi_ */
+    Rect resultRoi() const { int a[4], b[4], nb; check(vsb_get_roi(h_, a, b, &nb)); return Rect(a[0], a[1], a[2], a[3]); }
+    Rect paddedRoi() const { int a[4], b[4], nb; check(vsb_get_roi(h_, a, b, &nb)); return Rect(b[0], b[1], b[2], b[3]); }
+
+    /* calibrateCameras + warpImages for the fixed rig (calibration.cpp:28-249), N-generic */
+    void calibrateRig(int projection, int pano_width, Size src, double hfov_deg = 90.0, const float *gains = 0)
+    {
+        check(vsb_calibrate_rig(h_, projection, pano_width, src.width, src.height, hfov_deg, gains));
+        next_view_ = n_;
+    }
+    Size viewSize(int i) const { vsb_rig_info info; check(vsb_rig_info_get(h_, &info)); return Size(info.view_roi[i][2], info.view_roi[i][3]); }
+
+    vsb_stitcher *handle() { return h_; }
+private:
+    MultiBandBlender(const MultiBandBlender &);
+    MultiBandBlender &operator=(const MultiBandBlender &);
+    vsb_stitcher *h_;
+    vsb_config cfg_;
+    int n_, next_view_;
+};
+
+/* ---- MeshWarper::convertMeshesToMap(mesh_x, mesh_y, map_x, map_y, mesh_sizes), 360_stitcher/meshwarper.cpp:823-886 ---
+ * mesh_x[i] / mesh_y[i]: N x M vertex positions (host, row major).  The maps live inside the blender handle (double
+ * buffered; the reference rewrites the live maps under LockableVector mutexes): callable from the recalibration thread
+ * while another thread composes. */
+struct MeshCpu { const float *x, *y; int rows, cols; };
+inline void convertMeshesToMap(MultiBandBlender &mb, const std::vector<MeshCpu> &meshes)
+{
+    for (size_t i = 0; i < meshes.size(); ++i) check(vsb_set_mesh(mb.handle(), (int)i, meshes[i].x, meshes[i].y, meshes[i].rows, meshes[i].cols));
+}
+
+}  /* namespace vsb */
+#endif /* VSB200_HPP */

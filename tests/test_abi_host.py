@@ -92,6 +92,15 @@ def test_host_voronoi_matches_reference(vsb, og):
         assert np.array_equal(np.packbits(m > 0, axis=1), gold[f"voronoi_{n}_{pano}_{proj}_{i}"])
 
 
+def test_unit_weight_normalisation_shortcut_is_exact():
+    """k_blend / k_coarse replace trunc(acc / (1 + 1e-5f)) by acc - sign(acc) when the weight sum is exactly 1
+    (vsb_blend_kernels.cuh normalize_s16): exhaustive over the 16-bit accumulator range, in fp32."""
+    a = np.arange(-32768, 32768, dtype=np.int32)
+    den = np.float32(1.0) + np.float32(1e-5)
+    q = np.trunc(a.astype(np.float32) / den).astype(np.int32)
+    assert np.array_equal(q, a - np.sign(a))
+
+
 def test_product_never_touches_the_oracle():
     """The product path must not import, link or execute anything under oracle/ (nor fall back to the CPU)."""
     pkg = os.path.join(ROOT, "video-stitcher_b200")

@@ -228,6 +228,69 @@ def test_compose_host_roundtrip(cuda, og):
         _eq(outs[f], orig.compose(fr[f])[0], f"host-buffer compose frame {f}")
 
 
+def test_feed_online_boundary_and_pitched_output(cuda, og):
+    """B4 inner boundary: MultiBandBlender::feed_online takes the WARPED view (the caller keeps its own remaps); and a pitched
+    (16-byte aligned) output buffer takes the vector-store path of k_blend."""
+    import torch
+    import vsb200
+    from tests.gpu_util import dev, host, stream
+    orig, grig, kw = _rigs("small4", inject=False)
+    frames = [vsb200.synth.frame(i, 3, kw["src_w"], kw["src_h"]) for i in range(kw["n_views"])]
+    want, _ = orig.compose(frames)
+    W, H = grig.roi_final[2], grig.roi_final[3]
+    pitch = (W * 6 + 255) // 256 * 256
+    out = torch.full((H, pitch // 2), -12345, dtype=torch.int16, device="cuda")
+    warped = [dev(orig.warp_view(i, frames[i])) for i in range(kw["n_views"])]
+    for i, t in enumerate(warped):
+        grig.st.feed_warped(i, t.data_ptr(), t.shape[1] * 3, stream())
+    grig.st.blend(out.data_ptr(), pitch, stream())
+    got = host(out)
+    _eq(got[:, :W * 3].reshape(H, W, 3), want, "feed_online(warped) + blend, pitched output")
+    assert (got[:, W * 3:] == -12345).all(), "row padding must stay untouched"
+    # batched compose into pitched outputs
+    srcs = [dev(f) for f in frames]
+    out2 = torch.full((H, pitch // 2), -12345, dtype=torch.int16, device="cuda")
+    grig.st.compose([t.data_ptr() for t in srcs], kw["src_w"] * 3, [out2.data_ptr()], pitch, stream())
+    _eq(host(out2)[:, :W * 3].reshape(H, W, 3), want, "compose, pitched output")
+
+
+def test_cpp_host_demo_matches_oracle(cuda, og, tmp_path):
+    """Host code stays C++: examples/stitch_demo.cpp (timed.cpp-shaped, on include/vsb200.hpp) gives the oracle's panoramas."""
+    import math
+    import os
+    import subprocess
+    import vsb200
+    from oracle import pipeline as op
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "stitch_demo")
+    if not os.path.exists(exe):
+        import __graft_entry__ as ge
+        ge.build_examples()
+    n, sw, sh, pano, nb, nf = 4, 320, 240, 1024, 3, 2
+    gains = [1.0 + 0.03 * ((i % 3) - 1) for i in range(n)]
+    orig = op.OracleRig(n, sw, sh, pano, num_bands=nb, enable_local=True, gains=[float(np.float32(g)) for g in gains])
+    for v in range(n):
+        W, H = orig.sizes[v]
+        mx, my = vsb200.synth.identity_mesh(W, H)
+        for i in range(10):
+            for j in range(10):  # libm sin/cos in double, like the C++ demo
+                mx[i, j] = np.float32(mx[i, j] + np.float32(6.0 * math.sin(math.pi * i / 9) * math.cos(math.pi * j / 9)))
+                my[i, j] = np.float32(my[i, j] + np.float32(4.0 * math.sin(math.pi * j / 9)))
+        orig.set_mesh(v, mx, my)
+    frames = [[vsb200.synth.frame(i, f, sw, sh) for i in range(n)] for f in range(nf)]
+    fin, fout = tmp_path / "frames.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as fh:
+        for fr in frames:
+            for a in fr:
+                fh.write(a.tobytes())
+    r = subprocess.run([exe, str(n), str(sw), str(sh), str(pano), str(nb), str(nf), str(fin), str(fout)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    W, H = orig.roi_final[2], orig.roi_final[3]
+    got = np.fromfile(fout, np.int16).reshape(nf, H, W, 3)
+    for f in range(nf):
+        _eq(got[f], orig.compose(frames[f])[0], f"C++ demo frame {f}")
+
+
 def test_error_behaviour(cuda, vsb):
     # call-order and argument errors surface as status codes + text, never as crashes (the reference CV_Asserts)
     st = vsb.Stitcher(2, 5, True, 1)

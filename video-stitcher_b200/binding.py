@@ -20,7 +20,7 @@ MAX_BANDS = 7
 SYMBOLS = [
     "vsb_last_error", "vsb_version", "vsb_device_count", "vsb_create", "vsb_destroy", "vsb_warp_roi",
     "vsb_build_maps", "vsb_prepare", "vsb_get_roi", "vsb_init_view", "vsb_get_view_geometry", "vsb_set_maps",
-    "vsb_set_gain", "vsb_set_mesh", "vsb_custom_resize", "vsb_feed", "vsb_blend", "vsb_compose",
+    "vsb_set_gain", "vsb_set_mesh", "vsb_custom_resize", "vsb_feed", "vsb_feed_warped", "vsb_blend", "vsb_compose",
     "vsb_compose_host", "vsb_last_launch_count", "vsb_remap_linear_u8c3", "vsb_gain_u8",
     "vsb_border_reflect_u8c3_to_s16c3", "vsb_pyr_down_s16c3", "vsb_pyr_up_s16c3", "vsb_pyr_down_f32",
     "vsb_add_src_weight_32f", "vsb_normalize_32f", "vsb_debug_read",
@@ -149,6 +149,9 @@ class Stitcher:
     # ---- per frame
     def feed(self, i, src_ptr, pitch, stream=0):
         check(lib().vsb_feed(self._h, i, _vp(src_ptr), C.c_size_t(pitch), _vp(stream)))
+
+    def feed_warped(self, i, warped_ptr, pitch, stream=0):
+        check(lib().vsb_feed_warped(self._h, i, _vp(warped_ptr), C.c_size_t(pitch), _vp(stream)))
 
     def blend(self, out_ptr, out_pitch, stream=0):
         check(lib().vsb_blend(self._h, _vp(out_ptr), C.c_size_t(out_pitch), _vp(stream)))

@@ -882,13 +882,14 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
 }
 
 // remap stages + pyramid for views [v0, v1) of n_frames frames
-static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch, cudaStream_t st)
+static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch, cudaStream_t st,
+                        const uint8_t *warped = nullptr)
 {
     const int n = v1 - v0;
     int ws[MAXV], hs[MAXV];
     int r = sync_tile_lists(s);
     if (r != VSB_OK) return r;
-    {
+    if (!warped) {
         Stage1Params p;
         std::memset(&p, 0, sizeof(p));
         int first = 0, count = 0;
@@ -918,8 +919,9 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
             const View &V = s->v[i];
             Stage2View &S = p.v[i];
             S.P = V.P; S.G0 = V.G0;
-            if (s->cfg.enable_local && V.mesh_cur >= 0) { S.xmesh = V.mesh[V.mesh_cur][0]; S.ymesh = V.mesh[V.mesh_cur][1]; }
-            S.p_pitch = V.p_pitch; S.p_frame_stride = V.p_frame_stride; S.map_pitch = V.map_pitch; S.g0_frame_stride = V.g0_frame_stride;
+            if (s->cfg.enable_local && V.mesh_cur >= 0 && !warped) { S.xmesh = V.mesh[V.mesh_cur][0]; S.ymesh = V.mesh[V.mesh_cur][1]; }
+            S.p_pitch = V.p_pitch; S.p_frame_stride = V.p_frame_stride;
+            if (warped && i == v0) { S.P = warped; S.p_pitch = src_pitch; S.p_frame_stride = 0; }  // feed_online: the caller's warped view S.map_pitch = V.map_pitch; S.g0_frame_stride = V.g0_frame_stride;
             S.w = V.roi_w; S.h = V.roi_h; S.bw = V.bw; S.bh = V.bh; S.top = V.top; S.left = V.left;
             if (i < v0) first += (int)V.s2_tiles.size();
             else if (i < v1) { count += (int)V.s2_tiles.size(); bytes += 3.0 * V.roi_w * V.roi_h + 3.0 * V.bw * V.bh; }
@@ -1283,11 +1285,25 @@ int vsb_feed(vsb_stitcher *s, int i, const uint8_t *d_bgr, size_t pitch, void *s
     return launch_front(s, i, i + 1, 1, srcs, pitch, st);
 }
 
+// MultiBandBlender::feed_online(gpu_img, img_num, stream) itself (sources/modules/stitching/src/blenders.cpp:700-749):
+// the caller has already warped the view (its own cuda::remap calls); border + pyramid + weighted add from there.
+int vsb_feed_warped(vsb_stitcher *s, int i, const uint8_t *d_warped, size_t pitch, void *stream)
+{
+    REQ(s && d_warped, VSB_ERR_INVALID, "feed_warped: null argument");
+    REQ(i >= 0 && i < s->cfg.num_views, VSB_ERR_INVALID, "feed_warped: view index out of range");
+    REQ(s->finalized, VSB_ERR_STATE, "feed_warped: prepare + init_view for every view must come first");
+    REQ(pitch >= (size_t)s->v[i].roi_w * 3, VSB_ERR_INVALID, "feed_warped: pitch too small for a %d-pixel-wide CV_8UC3 view", s->v[i].roi_w);
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (i == 0) { s->launches = 0; prof_begin(s, st); }
+    return launch_front(s, i, i + 1, 1, nullptr, pitch, st, d_warped);
+}
+
 int vsb_blend(vsb_stitcher *s, int16_t *d_out, size_t out_pitch, void *stream)
 {
     REQ(s && d_out, VSB_ERR_INVALID, "blend: null argument");
-    int r = ready_for_frames(s);
-    if (r != VSB_OK) return r;
+    REQ(s->finalized, VSB_ERR_STATE, "blend: prepare + init_view for every view must come first");
+    int r;
     DeviceGuard g(s->device);
     int16_t *outs[1] = {d_out};
     r = launch_back(s, 1, outs, out_pitch, (cudaStream_t)stream);
