@@ -921,7 +921,8 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
             S.P = V.P; S.G0 = V.G0;
             if (s->cfg.enable_local && V.mesh_cur >= 0 && !warped) { S.xmesh = V.mesh[V.mesh_cur][0]; S.ymesh = V.mesh[V.mesh_cur][1]; }
             S.p_pitch = V.p_pitch; S.p_frame_stride = V.p_frame_stride;
-            if (warped && i == v0) { S.P = warped; S.p_pitch = src_pitch; S.p_frame_stride = 0; }  // feed_online: the caller's warped view S.map_pitch = V.map_pitch; S.g0_frame_stride = V.g0_frame_stride;
+            S.map_pitch = V.map_pitch; S.g0_frame_stride = V.g0_frame_stride;
+            if (warped && i == v0) { S.P = warped; S.p_pitch = src_pitch; S.p_frame_stride = 0; }  // feed_online: the caller's warped view
             S.w = V.roi_w; S.h = V.roi_h; S.bw = V.bw; S.bh = V.bh; S.top = V.top; S.left = V.left;
             if (i < v0) first += (int)V.s2_tiles.size();
             else if (i < v1) { count += (int)V.s2_tiles.size(); bytes += 3.0 * V.roi_w * V.roi_h + 3.0 * V.bw * V.bh; }
