@@ -230,7 +230,7 @@ def main():
     n_sets = max(RING, F)
     host_sets = []
     for f in range(n_sets):
-        host_sets.append([torch.from_numpy(S.frame(i, f + rank * n_sets, cfg["src_w"], cfg["src_h"])).pin_memory() for i in range(n)])
+        host_sets.append([torch.from_numpy(S.frame(i, f + vsb200.dist.ring_seed_offset(rank, n_sets), cfg["src_w"], cfg["src_h"])).pin_memory() for i in range(n)])
     dev_sets = [[t.cuda(non_blocking=True) for t in fs] for fs in host_sets]
     outs = [torch.empty((OH, out_pitch // 2), dtype=torch.int16, device="cuda") for _ in range(F)]
     stream = torch.cuda.current_stream().cuda_stream
@@ -262,11 +262,7 @@ def main():
     e1.record()
     barrier()
     t_wall1 = time.time()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = vsb200.dist.reduce_step_time(e0.elapsed_time(e1), dist if world > 1 else None, "cuda")  # MAX over ranks
     # keep sampling for a moment on very short runs so at least a few samples land under load
     if t_wall1 - t_wall0 < 0.5:
         t_end = time.time() + 0.6
@@ -320,11 +316,7 @@ def main():
         for k in range(Ke):
             host_call(k % n_sets)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = vsb200.dist.reduce_step_time(time.perf_counter() - t0, dist if world > 1 else None, "cuda")
         e2e = {"value": world * F * Ke / dt, "unit": "frames/s", "h2d_bytes_per_step": F * n * cfg["src_w"] * cfg["src_h"] * 3,
                "d2h_bytes_per_step": F * OW * OH * 6, "steps": Ke,
                "api": "vsb_compose_host: pinned host frames in, host panoramas out; upload / compose / download pipelined per frame"}

@@ -19,3 +19,4 @@ def _load(name):
 
 binding = _load("binding")
 synth = _load("synth")
+dist = _load("dist")
