@@ -95,6 +95,33 @@ __device__ __forceinline__ void pyr_up_row8(const Acc &a, int x0, int y, int n_x
 }
 
 
+// pyr_up_row8 on a shared-memory region `reg` (row pitch PITCH elements) whose element (0, 0) is plane sample (ox, oy).
+// Interior threads (no index clamps) read their 6 x 3 neighbourhood through one base pointer and immediate offsets.
+template <typename T, int PITCH>
+__device__ __forceinline__ void pyr_up_row8_region(const T *reg, int ox, int oy, int x0, int y, int n_x, int n_y, int out[8])
+{
+    const int ix0 = x0 >> 1, iy = y >> 1;
+    if (ix0 >= 1 && ix0 + 4 < n_x && iy >= 1 && iy + 1 < n_y) {
+        const T *p = reg + (iy - 1 - oy) * PITCH + (ix0 - 1 - ox);
+        int col[6];
+        if (y & 1) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) col[i] = 4 * ((int)p[PITCH + i] + (int)p[2 * PITCH + i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) col[i] = (int)p[i] + 6 * (int)p[PITCH + i] + (int)p[2 * PITCH + i];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            out[2 * q] = sat_s16(rhe_shift<6>(col[q] + 6 * col[q + 1] + col[q + 2]));
+            out[2 * q + 1] = sat_s16(rhe_shift<6>(4 * (col[q + 1] + col[q + 2])));
+        }
+    } else {
+        auto a = [&](int xi, int yi) { return (int)reg[(yi - oy) * PITCH + (xi - ox)]; };
+        pyr_up_row8(a, x0, y, n_x, n_y, out);
+    }
+}
+
 // pyrUp of the 2x2 quad {x0, x0+1} x {y0, y0+1} with x0 and y0 ODD (x0 = -1 allowed: only the valid samples are used).
 // out[0] = (x0, y0), out[1] = (x0+1, y0), out[2] = (x0, y0+1), out[3] = (x0+1, y0+1); same integers as pyr_up_sample,
 // the 3x3 source neighbourhood is read once and no lane diverges on parity.
@@ -138,16 +165,19 @@ __device__ __forceinline__ unsigned load_word_r101(const uint8_t *__restrict__ r
 }
 
 // =========================================================================================================== k_down2
-// G2 = pyrDown(pyrDown(G0)) for one 32x16 tile of one colour plane of one view; G1 lives in shared memory only.
+// G1 = pyrDown(G0) and G2 = pyrDown(G1) for one 32x16 (level-2) tile of one colour plane of one view.  The G0 region goes
+// to shared memory as 16-byte vectors, G1 is computed there with __dp4a, the tile's own 64x32 block of G1 and its 32x16
+// block of G2 are written out (u8).
 constexpr int D2_TW = 32, D2_TH = 16, D2_THREADS = 256;
 constexpr int D2_R1W = 2 * D2_TW + 3, D2_R1H = 2 * D2_TH + 3;  // G1 region 67 x 35: origin (2*X0 - 2, 2*Y0 - 2)
-constexpr int D2_R0WORDS = 35, D2_R0H = 4 * D2_TH + 9;          // G0 region 140 B x 73: origin (4*X0 - 8, 4*Y0 - 6)
+constexpr int D2_R0VEC = 10, D2_R0H = 4 * D2_TH + 9;            // G0 region 160 B x 73: origin (4*X0 - 16, 4*Y0 - 6)
+constexpr int D2_S1OFF = 2, D2_S1PITCH = 72;                    // G1 column c1 lives at byte c1 + 2: the owned block is word aligned
 
 struct Down2View {
     const uint8_t *g0;  // frame 0, plane 0
-    uint8_t *g2;
-    size_t g0_fs, g2_fs;  // frame strides (bytes)
-    int bw, bh;           // level-0 plane size
+    uint8_t *g1, *g2;
+    size_t g0_fs, g1_fs, g2_fs;  // frame strides (bytes)
+    int bw, bh;                  // level-0 plane size
 };
 struct Down2Params {
     const uint32_t *tiles;  // view | tile_x << 8 | tile_y << 20
@@ -156,18 +186,27 @@ struct Down2Params {
 
 __global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Down2Params P)
 {
-    __shared__ __align__(16) unsigned s0[D2_R0H][D2_R0WORDS + 1];
-    __shared__ uint8_t s1[D2_R1H][D2_R1W + 1];
+    __shared__ __align__(16) unsigned s0[D2_R0H][D2_R0VEC * 4];
+    __shared__ __align__(16) uint8_t s1[D2_R1H][D2_S1PITCH];
     const unsigned tile = __ldg(P.tiles + blockIdx.x);
     const Down2View &V = P.v[tile & 0xff];
     const int X0 = ((tile >> 8) & 0xfff) * D2_TW, Y0 = (tile >> 20) * D2_TH;
     const int c = blockIdx.y, f = blockIdx.z, t = threadIdx.x;
     const int w0 = V.bw, h0 = V.bh, w1 = w0 >> 1, h1 = h0 >> 1, w2 = w0 >> 2, h2 = h0 >> 2;
     const uint8_t *g0 = V.g0 + (size_t)f * V.g0_fs + (size_t)c * w0 * h0;
-    const int gx0 = 4 * X0 - 8, gy0 = 4 * Y0 - 6;
-    for (int i = t; i < D2_R0H * D2_R0WORDS; i += D2_THREADS) {
-        const int r = i / D2_R0WORDS, m = i - r * D2_R0WORDS;
-        s0[r][m] = load_word_r101(g0 + (size_t)r101_idx(gy0 + r, h0) * w0, gx0 + 4 * m, w0);
+    const int gx0 = 4 * X0 - 16, gy0 = 4 * Y0 - 6;
+    for (int i = t; i < D2_R0H * D2_R0VEC; i += D2_THREADS) {
+        const int r = i / D2_R0VEC, m = i - r * D2_R0VEC;
+        const uint8_t *row = g0 + (size_t)r101_idx(gy0 + r, h0) * w0;
+        const int gx = gx0 + 16 * m;
+        uint4 v;
+        if (gx >= 0 && gx + 15 < w0 && (((size_t)(row + gx)) & 15) == 0) {
+            v = __ldg((const uint4 *)(row + gx));
+        } else {
+            v.x = load_word_r101(row, gx, w0); v.y = load_word_r101(row, gx + 4, w0);
+            v.z = load_word_r101(row, gx + 8, w0); v.w = load_word_r101(row, gx + 12, w0);
+        }
+        *(uint4 *)&s0[r][4 * m] = v;
     }
     __syncthreads();
     // G1 over the region, at true in-plane positions only (nested reflection does not commute at the high edge)
@@ -175,25 +214,34 @@ __global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Do
         const int r1 = i / D2_R1W, c1 = i - r1 * D2_R1W;
         const int y1 = 2 * Y0 - 2 + r1, x1 = 2 * X0 - 2 + c1;
         if ((unsigned)y1 >= (unsigned)h1 || (unsigned)x1 >= (unsigned)w1) continue;
-        const int b = 2 * c1 + 2;  // first tap, byte offset inside the region row
+        const int b = 2 * c1 + 10;  // first tap, byte offset inside the region row
         const unsigned *row = &s0[2 * r1][b >> 2];
         unsigned acc = 0;
         if (c1 & 1) {
 #pragma unroll
-            for (int j = 0; j < 5; ++j) acc = taps5<true>(row[j * (D2_R0WORDS + 1)], row[j * (D2_R0WORDS + 1) + 1], j == 2 ? 6u : ((j & 1) ? 4u : 1u), acc);
+            for (int j = 0; j < 5; ++j) acc = taps5<true>(row[j * (D2_R0VEC * 4)], row[j * (D2_R0VEC * 4) + 1], j == 2 ? 6u : ((j & 1) ? 4u : 1u), acc);
         } else {
 #pragma unroll
-            for (int j = 0; j < 5; ++j) acc = taps5<false>(row[j * (D2_R0WORDS + 1)], row[j * (D2_R0WORDS + 1) + 1], j == 2 ? 6u : ((j & 1) ? 4u : 1u), acc);
+            for (int j = 0; j < 5; ++j) acc = taps5<false>(row[j * (D2_R0VEC * 4)], row[j * (D2_R0VEC * 4) + 1], j == 2 ? 6u : ((j & 1) ? 4u : 1u), acc);
         }
-        s1[r1][c1] = (uint8_t)rhe_shift<8>((int)acc);
+        s1[r1][c1 + D2_S1OFF] = (uint8_t)rhe_shift<8>((int)acc);
     }
     __syncthreads();
+    {   // the tile's own 64 x 32 block of G1 (region rows 2..33, columns 2..65), one word per thread and pass
+        uint8_t *g1 = V.g1 + (size_t)f * V.g1_fs + (size_t)c * w1 * h1;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int rr = (t >> 4) + 16 * pass, wq = t & 15;
+            const int y1 = 2 * Y0 + rr, x1 = 2 * X0 + 4 * wq;
+            if (y1 < h1 && x1 + 3 < w1) *(unsigned *)(g1 + (size_t)y1 * w1 + x1) = *(const unsigned *)&s1[rr + 2][4 + 4 * wq];
+        }
+    }
     uint8_t *g2 = V.g2 + (size_t)f * V.g2_fs + (size_t)c * w2 * h2;
     for (int i = t; i < D2_TW * D2_TH; i += D2_THREADS) {
         const int x2 = X0 + (i & (D2_TW - 1)), y2 = Y0 + i / D2_TW;
         if (x2 >= w2 || y2 >= h2) continue;
         int acc = 0;
-        const int ry = 2 * (y2 - Y0), rx = 2 * (x2 - X0);  // region position of tap (0, 0)
+        const int ry = 2 * (y2 - Y0), rx = 2 * (x2 - X0) + D2_S1OFF;  // region position of tap (0, 0)
         if (2 * y2 - 2 >= 0 && 2 * y2 + 2 < h1 && 2 * x2 - 2 >= 0 && 2 * x2 + 2 < w1) {
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
@@ -203,7 +251,7 @@ __global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Do
         } else {
             int cc[5];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) cc[j] = r101_idx(2 * x2 - 2 + j, w1) - (2 * X0 - 2);
+            for (int j = 0; j < 5; ++j) cc[j] = r101_idx(2 * x2 - 2 + j, w1) - (2 * X0 - 2) + D2_S1OFF;
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
                 const uint8_t *r = s1[r101_idx(2 * y2 - 2 + j, h1) - (2 * Y0 - 2)];
@@ -422,15 +470,14 @@ __global__ void __launch_bounds__(C_THREADS) k_coarse(const __grid_constant__ Co
 // Levels 0 and 1, the final collapse, the output mask and the crop for one 64x32 canvas tile (all three channels).
 constexpr int BL_TW = 64, BL_TH = 32, BL_THREADS = 256;
 constexpr int BL_R1W = BL_TW / 2 + 2, BL_R1H = BL_TH / 2 + 2;   // level-1 region 34 x 18, origin (tx0/2 - 1, ty0/2 - 1)
-constexpr int BL_G0WORDS = 18, BL_G0H = BL_TH + 7;              // level-0 region 72 B x 39, origin (tx0 - 4, ty0 - 4)
 constexpr int BL_R2W = BL_TW / 4 + 4, BL_R2H = BL_TH / 4 + 4;   // level-2 region 20 x 12, origin (tx0/4 - 2, ty0/4 - 2)
 constexpr int BL_QW = BL_R1W / 2, BL_QH = BL_R1H / 2, BL_NQ = BL_QW * BL_QH;  // level-1 region as 17 x 9 quads, one thread each
 
 struct BlendView {
-    const uint8_t *g0, *g2;  // frame 0
+    const uint8_t *g0, *g1, *g2;  // frame 0
     const uint8_t *m0;       // bordered seam mask (u8, 0 in the border): W0 = m0 * (1/255)
     const float *w1;         // static weight level 1
-    size_t g0_fs, g2_fs;
+    size_t g0_fs, g1_fs, g2_fs;
     int x_tl, y_tl, bw, bh;
 };
 struct BlendParams {
@@ -445,7 +492,6 @@ struct BlendParams {
 
 __global__ void __launch_bounds__(BL_THREADS, 3) k_blend(const __grid_constant__ BlendParams P, const __grid_constant__ OutPtrs outs, size_t out_pitch)
 {
-    __shared__ __align__(16) unsigned sG0[3][BL_G0H][BL_G0WORDS + 1];
     __shared__ uint8_t sG1[3][BL_R1H][BL_R1W + 2];
     __shared__ uint8_t sG2[3][BL_R2H][BL_R2W];
     __shared__ int16_t sC2[3][BL_R2H][BL_R2W];
@@ -469,14 +515,14 @@ __global__ void __launch_bounds__(BL_THREADS, 3) k_blend(const __grid_constant__
         views &= views - 1;
         const BlendView &V = P.v[vi];
         const int w0 = V.bw, h0 = V.bh, w1 = w0 >> 1, h1 = h0 >> 1, w2 = w0 >> 2, h2 = h0 >> 2;
+        const int v1x0 = (tx0 >> 1) - 1 - (V.x_tl >> 1), v1y0 = (ty0 >> 1) - 1 - (V.y_tl >> 1);  // plane coords of region (0,0)
         __syncthreads();
-        {
-            const uint8_t *g0 = V.g0 + (size_t)f * V.g0_fs;
-            const int vx0 = tx0 - 4 - V.x_tl, vy0 = ty0 - 4 - V.y_tl;
-            for (int i = t; i < 3 * BL_G0H * BL_G0WORDS; i += BL_THREADS) {
-                const int c = i / (BL_G0H * BL_G0WORDS), rem = i - c * (BL_G0H * BL_G0WORDS);
-                const int r = rem / BL_G0WORDS, m = rem - r * BL_G0WORDS;
-                sG0[c][r][m] = load_word_r101(g0 + ((size_t)c * h0 + r101_idx(vy0 + r, h0)) * w0, vx0 + 4 * m, w0);
+        if (nb >= 1) {  // G1 region 34 x 18 (written by k_down2) and G2 region 20 x 12, coordinates clamped like pyrUp does
+            const uint8_t *g1 = V.g1 + (size_t)f * V.g1_fs;
+            for (int i = t; i < 3 * BL_R1H * BL_R1W; i += BL_THREADS) {
+                const int c = i / (BL_R1H * BL_R1W), rem = i - c * (BL_R1H * BL_R1W);
+                const int r = rem / BL_R1W, q = rem - r * BL_R1W;
+                sG1[c][r][q] = (uint8_t)ldg_u8(g1 + ((size_t)c * h1 + up_idx(v1y0 + r, h1)) * w1 + up_idx(v1x0 + q, w1));
             }
             if (nb >= 2) {
                 const uint8_t *g2 = V.g2 + (size_t)f * V.g2_fs;
@@ -489,25 +535,6 @@ __global__ void __launch_bounds__(BL_THREADS, 3) k_blend(const __grid_constant__
             }
         }
         __syncthreads();
-        const int v1x0 = (tx0 >> 1) - 1 - (V.x_tl >> 1), v1y0 = (ty0 >> 1) - 1 - (V.y_tl >> 1);  // plane coords of region (0,0)
-        if (nb >= 1) {
-            for (int i = t; i < 3 * BL_R1H * BL_R1W; i += BL_THREADS) {
-                const int c = i / (BL_R1H * BL_R1W), rem = i - c * (BL_R1H * BL_R1W);
-                const int r1 = rem / BL_R1W, c1 = rem - r1 * BL_R1W;
-                if ((unsigned)(v1y0 + r1) >= (unsigned)h1 || (unsigned)(v1x0 + c1) >= (unsigned)w1) continue;
-                const unsigned *row = &sG0[c][2 * r1][c1 >> 1];  // first tap at region byte 2*c1
-                unsigned acc = 0;
-                if (c1 & 1) {
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) acc = taps5<false>(row[j * (BL_G0WORDS + 1)], row[j * (BL_G0WORDS + 1) + 1], j == 2 ? 6u : ((j & 1) ? 4u : 1u), acc);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) acc = taps5<true>(row[j * (BL_G0WORDS + 1)], row[j * (BL_G0WORDS + 1) + 1], j == 2 ? 6u : ((j & 1) ? 4u : 1u), acc);
-                }
-                sG1[c][r1][c1] = (uint8_t)rhe_shift<8>((int)acc);
-            }
-            __syncthreads();
-        }
         // ---- level 0: this thread's 8 samples
         const int qx0 = px0 - V.x_tl, qy = py - V.y_tl;
         if ((unsigned)qx0 < (unsigned)w0 && (unsigned)qy < (unsigned)h0) {
@@ -524,11 +551,11 @@ __global__ void __launch_bounds__(BL_THREADS, 3) k_blend(const __grid_constant__
             if (any) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const unsigned ga = sG0[c][ly + 4][(lx + 4) >> 2], gb = sG0[c][ly + 4][((lx + 4) >> 2) + 1];
+                    const uint2 gg = __ldg((const uint2 *)(V.g0 + (size_t)f * V.g0_fs + ((size_t)c * h0 + qy) * w0 + qx0));
+                    const unsigned ga = gg.x, gb = gg.y;
                     int up[8];
                     if (nb >= 1) {
-                        auto a = [&](int xi, int yi) { return (int)sG1[c][yi - v1y0][xi - v1x0]; };
-                        pyr_up_row8(a, qx0, qy, w1, h1, up);
+                        pyr_up_row8_region<uint8_t, BL_R1W + 2>(&sG1[c][0][0], v1x0, v1y0, qx0, qy, w1, h1, up);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) up[i] = 0;
@@ -610,8 +637,7 @@ __global__ void __launch_bounds__(BL_THREADS, 3) k_blend(const __grid_constant__
         for (int c = 0; c < 3; ++c) {
             int up[8];
             if (nb >= 1) {
-                auto a = [&](int xi, int yi) { return (int)sD1[c][yi - Y1][xi - X1]; };
-                pyr_up_row8(a, px0, py, P.cw1, P.ch1, up);
+                pyr_up_row8_region<int16_t, BL_R1W>(&sD1[c][0][0], X1, Y1, px0, py, P.cw1, P.ch1, up);
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) up[i] = 0;

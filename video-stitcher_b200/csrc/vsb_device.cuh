@@ -150,8 +150,9 @@ __device__ __forceinline__ void load6(const uint8_t *__restrict__ p, bool bytewi
 //   p = sat_u8(rni(gain * sat_u8(rni(bilinear))))   (360_stitcher/timed.cpp:90-94); gain = 1 gives the plain remap.
 // Returns b | g << 8 | r << 16.  Requires sw >= 2.  Bit-identical to remap_px_u8c3 + rni_sat_u8(gain * v): the taps,
 // weights and the fmul/fma chain are the same; only the u8<->fp32 conversions take a cheaper route.
+// General form: any coordinate (taps outside the image read 0, NaN gives 0, the last bytes of the image are read bytewise).
 template <bool GAIN>
-__device__ __forceinline__ unsigned remap_gain_px(const uint8_t *__restrict__ src, size_t pitch, int sw, int sh, float x, float y, float gain)
+__device__ __noinline__ unsigned remap_gain_px_edge(const uint8_t *__restrict__ src, size_t pitch, int sw, int sh, float x, float y, float gain)
 {
     const int x1 = __float2int_rd(x), y1 = __float2int_rd(y);
     // no tap in range (or NaN coordinates: every product is NaN and cvt.sat gives 0)
@@ -183,8 +184,49 @@ __device__ __forceinline__ unsigned remap_gain_px(const uint8_t *__restrict__ sr
         v = __fmaf_rn(u8_to_f32(r1, c), w12, v);
         v = __fmaf_rn(u8_to_f32(l2, c), w21, v);
         v = __fmaf_rn(u8_to_f32(r2, c), w22, v);
-        v = __fsub_rn(rni_biased(v), 12582912.f);                      // sat_u8(rni(.)) as a float: 0 <= v < 255.5
-        o[c] = GAIN ? rni_biased(fminf(__fmul_rn(gain, v), 255.f)) : __fadd_rn(v, 12582912.f);  // sat_u8(rni(gain * v)); integer in the low byte
+        v = rni_biased(v);                                                 // sat_u8(rni(.)): integer in the low mantissa bits
+        o[c] = GAIN ? rni_biased(fminf(__fmul_rn(gain, __fsub_rn(v, 12582912.f)), 255.f)) : v;  // sat_u8(rni(gain * v))
+    }
+    return __byte_perm(__byte_perm(__float_as_uint(o[0]), __float_as_uint(o[1]), 0x0040u), __float_as_uint(o[2]), 0x0410u) & 0xffffffu;
+}
+
+// Hot form: all four taps inside the image and away from its last bytes -- no selects, no per-row conditions; the
+// byte -> fp32 conversions pick their bytes straight out of the funnel-shifted words.  Anything else takes the general form.
+template <bool GAIN>
+__device__ __forceinline__ unsigned remap_gain_px(const uint8_t *__restrict__ src, size_t pitch, int sw, int sh, float x, float y, float gain)
+{
+    const int x1 = __float2int_rd(x), y1 = __float2int_rd(y);
+    const bool interior = (unsigned)x1 < (unsigned)(sw - 1) && (unsigned)y1 < (unsigned)(sh - 1) && x == x && y == y &&
+                          !(y1 == sh - 2 && x1 + 5 >= sw);
+    if (!interior) return remap_gain_px_edge<GAIN>(src, pitch, sw, sh, x, y, gain);
+    const float fx2 = __fsub_rn((float)(x1 + 1), x), fx1 = __fsub_rn(x, (float)x1);
+    const float fy2 = __fsub_rn((float)(y1 + 1), y), fy1 = __fsub_rn(y, (float)y1);
+    const float w11 = __fmul_rn(fx2, fy2), w12 = __fmul_rn(fx1, fy2), w21 = __fmul_rn(fx2, fy1), w22 = __fmul_rn(fx1, fy1);
+    const uint8_t *p1 = src + (size_t)y1 * pitch + (size_t)x1 * 3, *p2 = p1 + pitch;
+    unsigned lo1, hi1, lo2, hi2;
+    {
+        const size_t a = (size_t)p1 & ~(size_t)3;
+        const unsigned s8 = ((unsigned)(size_t)p1 & 3u) * 8u;
+        const unsigned w0 = __ldg((const unsigned *)a), w1 = __ldg((const unsigned *)(a + 4));
+        const unsigned w2 = s8 == 24u ? __ldg((const unsigned *)(a + 8)) : 0u;
+        lo1 = __funnelshift_r(w0, w1, s8); hi1 = __funnelshift_r(w1, w2, s8);
+    }
+    {
+        const size_t a = (size_t)p2 & ~(size_t)3;
+        const unsigned s8 = ((unsigned)(size_t)p2 & 3u) * 8u;
+        const unsigned w0 = __ldg((const unsigned *)a), w1 = __ldg((const unsigned *)(a + 4));
+        const unsigned w2 = s8 == 24u ? __ldg((const unsigned *)(a + 8)) : 0u;
+        lo2 = __funnelshift_r(w0, w1, s8); hi2 = __funnelshift_r(w1, w2, s8);
+    }
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {  // left pixel = bytes 0..2 of lo, right pixel = byte 3 of lo, bytes 0..1 of hi
+        float v = __fmul_rn(u8_to_f32(lo1, c), w11);
+        v = __fmaf_rn(c == 0 ? u8_to_f32(lo1, 3) : u8_to_f32(hi1, c - 1), w12, v);
+        v = __fmaf_rn(u8_to_f32(lo2, c), w21, v);
+        v = __fmaf_rn(c == 0 ? u8_to_f32(lo2, 3) : u8_to_f32(hi2, c - 1), w22, v);
+        v = rni_biased(v);
+        o[c] = GAIN ? rni_biased(fminf(__fmul_rn(gain, __fsub_rn(v, 12582912.f)), 255.f)) : v;
     }
     return __byte_perm(__byte_perm(__float_as_uint(o[0]), __float_as_uint(o[1]), 0x0040u), __float_as_uint(o[2]), 0x0410u) & 0xffffffu;
 }

@@ -124,24 +124,26 @@ __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage2(const __grid_cons
     const uint8_t *P = V.P + (size_t)f * V.p_frame_stride;
     const int y = reflect_idx(by - V.top, V.h);
     const int n = min(RM_PX, V.bw - bx0);
-    unsigned c0 = 0, c1 = 0, c2 = 0;
+    const bool inside = bx0 >= V.left && bx0 + RM_PX <= V.left + V.w;  // no reflection in x for this thread's pixels
+    unsigned px[RM_PX];
 #pragma unroll
     for (int i = 0; i < RM_PX; ++i) {
-        if (i >= n) break;
-        const int x = reflect_idx(bx0 + i - V.left, V.w);
-        unsigned v;
+        px[i] = 0u;
+        if (i >= n) continue;
+        const int x = inside ? bx0 + i - V.left : reflect_idx(bx0 + i - V.left, V.w);
         if (V.xmesh) {
             const float fx = __ldg((const float *)((const char *)V.xmesh + (size_t)y * V.map_pitch) + x);
             const float fy = __ldg((const float *)((const char *)V.ymesh + (size_t)y * V.map_pitch) + x);
-            v = remap_gain_px<false>(P, V.p_pitch, V.w, V.h, fx, fy, 1.f);
+            px[i] = remap_gain_px<false>(P, V.p_pitch, V.w, V.h, fx, fy, 1.f);
         } else {
             const uint8_t *s = P + (size_t)y * V.p_pitch + (size_t)x * 3;
-            v = (unsigned)__ldg(s) | ((unsigned)__ldg(s + 1) << 8) | ((unsigned)__ldg(s + 2) << 16);
+            px[i] = (unsigned)__ldg(s) | ((unsigned)__ldg(s + 1) << 8) | ((unsigned)__ldg(s + 2) << 16);
         }
-        c0 |= (v & 0xff) << (8 * i);
-        c1 |= ((v >> 8) & 0xff) << (8 * i);
-        c2 |= ((v >> 16) & 0xff) << (8 * i);
     }
+    // interleaved -> planar: byte c of the four pixels
+    const unsigned lo01 = __byte_perm(px[0], px[1], 0x5140u), lo23 = __byte_perm(px[2], px[3], 0x5140u);  // b0 b1 g0 g1 | b2 b3 g2 g3
+    const unsigned c0 = __byte_perm(lo01, lo23, 0x5410u), c1 = __byte_perm(lo01, lo23, 0x7632u);
+    const unsigned c2 = __byte_perm(__byte_perm(px[0], px[1], 0x0062u), __byte_perm(px[2], px[3], 0x0062u), 0x5410u);
     const size_t plane = (size_t)V.bw * V.bh;
     uint8_t *g = V.G0 + (size_t)f * V.g0_frame_stride + (size_t)by * V.bw + bx0;
     if (n == RM_PX && (V.bw & 3) == 0) {
@@ -419,6 +421,8 @@ struct View {
     size_t g_frame_stride[MAXL] = {};
     uint8_t *G2 = nullptr;              // fast path: u8 Gaussian level 2
     size_t g2_frame_stride = 0;
+    uint8_t *G1 = nullptr;              // fast path: u8 Gaussian level 1 (written by k_down2, read by k_blend)
+    size_t g1_frame_stride = 0;
     uint8_t *Gu[MAXL] = {};             // fast path: u8 Gaussian levels 3..nb (Gu[2] aliases G2)
     size_t gu_frame_stride[MAXL] = {};
     uint8_t *M0 = nullptr;              // bordered seam mask (u8, bw x bh): W0 = M0 * (1/255)
@@ -492,7 +496,7 @@ static void free_view(View &V)
     for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) cudaFree(V.mesh[b][c]);
     cudaFree(V.mesh_scratch);
     for (int k = 0; k < MAXL; ++k) { cudaFree(V.weight[k]); cudaFree(V.G[k]); }
-    cudaFree(V.P); cudaFree(V.G0); cudaFree(V.G2); cudaFree(V.M0);
+    cudaFree(V.P); cudaFree(V.G0); cudaFree(V.G1); cudaFree(V.G2); cudaFree(V.M0);
     for (int k = 3; k < MAXL; ++k) cudaFree(V.Gu[k]);
     if (V.mesh_ready) cudaEventDestroy(V.mesh_ready);
     V = View();
@@ -652,11 +656,11 @@ static int build_fast_plan(vsb_stitcher *s)
         for (int ty = 0; ty < V.d2_tiles_y; ++ty)
             for (int tx = 0; tx < V.d2_tiles_x; ++tx)
                 if (V.g2_needed[(size_t)ty * V.d2_tiles_x + tx])
-                    mark(4 * tx * D2_TW - 8, 4 * ty * D2_TH - 6, 4 * tx * D2_TW - 8 + 4 * D2_R0WORDS, 4 * ty * D2_TH - 6 + D2_R0H);
+                    mark(4 * tx * D2_TW - 16, 4 * ty * D2_TH - 6, 4 * tx * D2_TW - 16 + 16 * D2_R0VEC, 4 * ty * D2_TH - 6 + D2_R0H);
         for (int ty = 0; ty < s->blend_tiles_y; ++ty)
             for (int tx = 0; tx < s->blend_tiles_x; ++tx)
                 if (bviews[(size_t)ty * s->blend_tiles_x + tx] >> i & 1)
-                    mark(tx * BL_TW - 4 - V.x_tl, ty * BL_TH - 4 - V.y_tl, tx * BL_TW - 4 - V.x_tl + 4 * BL_G0WORDS, ty * BL_TH - 4 - V.y_tl + BL_G0H);
+                    mark(tx * BL_TW - V.x_tl, ty * BL_TH - V.y_tl, (tx + 1) * BL_TW - V.x_tl, (ty + 1) * BL_TH - V.y_tl);
         V.s2_tiles.clear();
         for (int ty = 0; ty < nty; ++ty)
             for (int tx = 0; tx < ntx; ++tx)
@@ -800,7 +804,8 @@ static int launch_down2(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
     std::memset(&p, 0, sizeof(p));
     for (int i = 0; i < s->cfg.num_views; ++i) {
         const View &V = s->v[i];
-        p.v[i].g0 = V.G0; p.v[i].g2 = V.G2; p.v[i].g0_fs = V.g0_frame_stride; p.v[i].g2_fs = V.g2_frame_stride;
+        p.v[i].g0 = V.G0; p.v[i].g1 = V.G1; p.v[i].g2 = V.G2;
+        p.v[i].g0_fs = V.g0_frame_stride; p.v[i].g1_fs = V.g1_frame_stride; p.v[i].g2_fs = V.g2_frame_stride;
         p.v[i].bw = V.bw; p.v[i].bh = V.bh;
     }
     // the tile list is sorted by view: launch the sub-range that belongs to [v0, v1)
@@ -810,12 +815,12 @@ static int launch_down2(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
         int nt = 0;
         for (uint8_t b : s->v[i].g2_needed) nt += b;
         if (i < v0) first += nt;
-        else if (i < v1) { count += nt; bytes += (double)nt * 3 * (16.0 * D2_TW * D2_TH + D2_TW * D2_TH); }
+        else if (i < v1) { count += nt; bytes += (double)nt * 3 * (16.0 * D2_TW * D2_TH + 4.0 * D2_TW * D2_TH + D2_TW * D2_TH); }
     }
     p.tiles = s->d_down2_tiles + first;
     if (count > 0) k_down2<<<dim3(count, 3, n_frames), D2_THREADS, 0, st>>>(p);
     ++s->launches;
-    prof_stage(s, st, "down2", bytes * n_frames);  // G0 of the needed tiles in once + G2 out once
+    prof_stage(s, st, "down2", bytes * n_frames);  // G0 of the needed tiles in once + G1 and G2 out once
     return check_launch("k_down2");
 }
 
@@ -867,16 +872,17 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
         for (int i = 0; i < n; ++i) {
             const View &V = s->v[i];
             BlendView &B = p.v[i];
-            B.g0 = V.G0; B.g2 = V.G2; B.m0 = V.M0; B.w1 = V.weight[1]; B.g0_fs = V.g0_frame_stride; B.g2_fs = V.g2_frame_stride;
+            B.g0 = V.G0; B.g1 = V.G1; B.g2 = V.G2; B.m0 = V.M0; B.w1 = V.weight[1];
+            B.g0_fs = V.g0_frame_stride; B.g1_fs = V.g1_frame_stride; B.g2_fs = V.g2_frame_stride;
             B.x_tl = V.x_tl; B.y_tl = V.y_tl; B.bw = V.bw; B.bh = V.bh;
-            bytes += 3.0 * V.bw * V.bh + 3.0 * (V.bw >> 2) * (V.bh >> 2);
+            bytes += 3.0 * V.bw * V.bh + 3.0 * (V.bw >> 1) * (V.bh >> 1) + 3.0 * (V.bw >> 2) * (V.bh >> 2);
         }
         OutPtrs o;
         std::memset(&o, 0, sizeof(o));
         for (int f = 0; f < n_frames; ++f) o.out[f] = d_outs[f];
         k_blend<<<dim3(s->blend_tiles_x, s->blend_tiles_y, n_frames), BL_THREADS, 0, st>>>(p, o, out_pitch);
         ++s->launches;
-        prof_stage(s, st, "blend", bytes * n_frames);  // G0 + G2 of every view once, C2 once, CV_16SC3 pano out once
+        prof_stage(s, st, "blend", bytes * n_frames);  // G0 + G1 + G2 of every view once, C2 once, CV_16SC3 pano out once
     }
     return check_launch("k_coarse / k_blend");
 }
@@ -1149,6 +1155,9 @@ int vsb_init_view(vsb_stitcher *s, int i, const uint8_t *mask, int mw, int mh, s
         V.g2_frame_stride = (size_t)3 * (width >> 2) * (height >> 2);
         CK(cudaMalloc(&V.G2, V.g2_frame_stride * F));
         CK(cudaMemsetAsync(V.G2, 0, V.g2_frame_stride * F, s->setup_stream));  // skipped tiles stay defined
+        V.g1_frame_stride = (size_t)3 * (width >> 1) * (height >> 1);
+        CK(cudaMalloc(&V.G1, V.g1_frame_stride * F));
+        CK(cudaMemsetAsync(V.G1, 0, V.g1_frame_stride * F, s->setup_stream));
         V.Gu[2] = V.G2; V.gu_frame_stride[2] = V.g2_frame_stride;
         for (int k = 3; k <= nb; ++k) {
             V.gu_frame_stride[k] = (size_t)3 * (width >> k) * (height >> k);
