@@ -190,19 +190,31 @@ __device__ __noinline__ unsigned remap_gain_px_edge(const uint8_t *__restrict__ 
     return __byte_perm(__byte_perm(__float_as_uint(o[0]), __float_as_uint(o[1]), 0x0040u), __float_as_uint(o[2]), 0x0410u) & 0xffffffu;
 }
 
-// Hot form: all four taps inside the image and away from its last bytes -- no selects, no per-row conditions; the
-// byte -> fp32 conversions pick their bytes straight out of the funnel-shifted words.  Anything else takes the general form.
+// Hot form.  Taps outside the image contribute exactly +0 in the reference (0 * w with w >= 0), which is what a ZERO
+// WEIGHT on a clamped, in-bounds tap gives too -- so image borders need no selects on the pixel data: a short, rarely
+// taken block zeroes the 1-D fractions and clamps the row pointers.  Only the few pixels whose byte window would leave
+// the caller's buffer (first / last bytes of the image) take the general form above.  (The kernels are bound by the
+// ALU pipe, so the floor / int->float conversions deliberately stay on the otherwise idle conversion unit.)
 template <bool GAIN>
 __device__ __forceinline__ unsigned remap_gain_px(const uint8_t *__restrict__ src, size_t pitch, int sw, int sh, float x, float y, float gain)
 {
     const int x1 = __float2int_rd(x), y1 = __float2int_rd(y);
-    const bool interior = (unsigned)x1 < (unsigned)(sw - 1) && (unsigned)y1 < (unsigned)(sh - 1) && x == x && y == y &&
-                          !(y1 == sh - 2 && x1 + 5 >= sw);
-    if (!interior) return remap_gain_px_edge<GAIN>(src, pitch, sw, sh, x, y, gain);
-    const float fx2 = __fsub_rn((float)(x1 + 1), x), fx1 = __fsub_rn(x, (float)x1);
-    const float fy2 = __fsub_rn((float)(y1 + 1), y), fy1 = __fsub_rn(y, (float)y1);
+    // no tap in range: x1 outside [-1, sw - 1] or y1 outside [-1, sh - 1]; NaN coordinates give 0 as well
+    if ((unsigned)(x1 + 1) > (unsigned)sw || (unsigned)(y1 + 1) > (unsigned)sh || !(x == x) || !(y == y)) return 0u;
+    float fx2 = __fsub_rn((float)(x1 + 1), x), fx1 = __fsub_rn(x, (float)x1);
+    float fy2 = __fsub_rn((float)(y1 + 1), y), fy1 = __fsub_rn(y, (float)y1);
+    const uint8_t *p1 = src + (ptrdiff_t)y1 * (ptrdiff_t)pitch + (ptrdiff_t)x1 * 3, *p2 = p1 + pitch;
+    if ((unsigned)x1 >= (unsigned)(sw - 1) || (unsigned)y1 >= (unsigned)(sh - 2)) {  // a tap outside, or the last image row
+        const int ya = max(y1, 0), yb = min(y1 + 1, sh - 1);
+        if ((ya == 0 && x1 < 0) || (yb == sh - 1 && x1 + 5 >= sw)) return remap_gain_px_edge<GAIN>(src, pitch, sw, sh, x, y, gain);
+        fx2 = x1 >= 0 ? fx2 : 0.f;
+        fx1 = x1 + 1 < sw ? fx1 : 0.f;
+        fy2 = y1 >= 0 ? fy2 : 0.f;
+        fy1 = y1 + 1 < sh ? fy1 : 0.f;
+        p1 = src + (size_t)ya * pitch + (ptrdiff_t)x1 * 3;
+        p2 = src + (size_t)yb * pitch + (ptrdiff_t)x1 * 3;
+    }
     const float w11 = __fmul_rn(fx2, fy2), w12 = __fmul_rn(fx1, fy2), w21 = __fmul_rn(fx2, fy1), w22 = __fmul_rn(fx1, fy1);
-    const uint8_t *p1 = src + (size_t)y1 * pitch + (size_t)x1 * 3, *p2 = p1 + pitch;
     unsigned lo1, hi1, lo2, hi2;
     {
         const size_t a = (size_t)p1 & ~(size_t)3;
