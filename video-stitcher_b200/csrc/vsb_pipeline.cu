@@ -1354,9 +1354,15 @@ int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs
     if (!s->stage_src) {
         s->stage_src_pitch = align_up((size_t)sw * 3, 4);  // tight rows: a packed host frame moves as ONE contiguous DMA
         s->stage_src_frame = align_up(s->stage_src_pitch * sh + 16, 256);
-        s->stage_out_pitch = align_up((size_t)s->roi_final[2] * 6, 256);
-        s->stage_out_frame = s->stage_out_pitch * s->roi_final[3];
         CK(cudaMalloc(&s->stage_src, s->stage_src_frame * n * F));
+    }
+    // the device-side panorama staging uses the HOST pitch, so each download is one contiguous DMA (a 2-D copy of 600+
+    // rows whose pitches differ by a few bytes runs at a fraction of the link rate)
+    if (!s->stage_out || s->stage_out_pitch != out_pitch) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(s->stage_out); s->stage_out = nullptr;
+        s->stage_out_pitch = out_pitch;
+        s->stage_out_frame = align_up(out_pitch * s->roi_final[3], 256);
         CK(cudaMalloc(&s->stage_out, s->stage_out_frame * F));
     }
     if (!s->in_stream) {
@@ -1387,7 +1393,10 @@ int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs
         if (r != VSB_OK) { cudaDeviceSynchronize(); return r; }
         CK(cudaEventRecord(s->ev_done[f], s->io_stream));
         CK(cudaStreamWaitEvent(s->out_stream, s->ev_done[f], 0));
-        CK(cudaMemcpy2DAsync(h_outs[f], out_pitch, d_out, s->stage_out_pitch, (size_t)s->roi_final[2] * 6, s->roi_final[3], cudaMemcpyDeviceToHost, s->out_stream));
+        if (out_pitch == (size_t)s->roi_final[2] * 6)  // packed host rows: one contiguous DMA
+            CK(cudaMemcpyAsync(h_outs[f], d_out, out_pitch * (size_t)s->roi_final[3], cudaMemcpyDeviceToHost, s->out_stream));
+        else                                            // padded host rows: leave the caller's padding untouched
+            CK(cudaMemcpy2DAsync(h_outs[f], out_pitch, d_out, s->stage_out_pitch, (size_t)s->roi_final[2] * 6, s->roi_final[3], cudaMemcpyDeviceToHost, s->out_stream));
     }
     CK(cudaStreamSynchronize(s->out_stream));
     CK(cudaStreamSynchronize(s->io_stream));
