@@ -122,6 +122,16 @@ int vsb_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, siz
  * returns after the outputs are in host memory. */
 int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs, size_t src_pitch_bytes,
                      int16_t *const *h_outs, size_t out_pitch_bytes);
+/* ---- view-sharded multi-GPU mode (the reference is single-GPU, A/timed.cpp:495-496).  One process and
+ *      one calibrated handle per GPU.  Rank r owns a canvas strip (its part of `blend`) and the views whose seam masks lie
+ *      mostly inside it (their `stitch_online`).  Per frame: vsb_feed the owned views -> exchange the Gaussian sub-planes
+ *      vsb_shard_rect lists (u8; NCCL send/recv by the caller, video-stitcher_b200/dist.py) -> vsb_blend writes the strip. */
+int vsb_shard_set(vsb_stitcher *s, int rank, int world);
+int vsb_shard_info(const vsb_stitcher *s, int *strip_x0, int *strip_x1, unsigned *owned_view_mask);
+/* rect = {x0, y0, w, h} of Gaussian level `level` of `view` (plane coordinates) that rank dst_rank reads; w = 0: nothing */
+int vsb_shard_rect(const vsb_stitcher *s, int dst_rank, int view, int level, int rect[4]);
+/* device address of Gaussian level `level` (0, 1, 2..num_bands) of `view`, frame slot `frame`: [3][h][w] u8 */
+int vsb_get_plane(vsb_stitcher *s, int view, int level, int frame, void **ptr, int *w, int *h);
 /* number of kernels the last vsb_compose / vsb_feed+vsb_blend submission launched */
 int vsb_last_launch_count(const vsb_stitcher *s);
 

@@ -1,0 +1,76 @@
+"""torchrun worker for the view-sharded mode on >= 2 GPUs: every rank calibrates the same rig, feeds its views, exchanges
+Gaussian sub-planes over NCCL, blends its canvas strip; the strips are summed and rank 0 checks them against the oracle."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import vsb200
+
+
+def main():
+    case = json.loads(sys.argv[1])
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    B, S, D = vsb200.binding, vsb200.synth, vsb200.dist
+    n, sw, sh = case["n_views"], case["src_w"], case["src_h"]
+    gains = S.gains(n)
+    st = B.Stitcher(n, case["num_bands"], True, 1)
+    st.calibrate_rig(0, case["pano_width"], sw, sh, 90.0, gains)
+    info = st.rig_info()
+    for i in range(n):
+        mx, my = S.mesh(info.view_roi[i][2], info.view_roi[i][3])
+        st.set_mesh(i, mx.ctypes.data, my.ctypes.data, mx.shape[0], mx.shape[1])
+    roi, _, nb = st.get_roi()
+    W, H = roi[2], roi[3]
+    sh_st = D.ShardedStitcher(st, dist, torch)
+    frames = [S.frame(i, 0, sw, sh) for i in range(n)]
+    d_src = [torch.from_numpy(f).cuda() for f in frames]
+    pitch = (W * 6 + 255) // 256 * 256
+    out = torch.zeros((H, pitch // 2), dtype=torch.int16, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    sh_st.compose([t.data_ptr() for t in d_src], sw * 3, out.data_ptr(), pitch, stream)
+    torch.cuda.synchronize()
+    full = out.to(torch.int32)
+    dist.all_reduce(full)  # strips are disjoint and the rest of every rank's buffer is zero
+    res = {"rank": rank, "strip": [sh_st.strip_x0, sh_st.strip_x1], "owned": sh_st.owned,
+           "send_bytes": D.exchange_bytes(sh_st.sends), "recv_bytes": D.exchange_bytes(sh_st.recvs)}
+    if steps > 0:
+        for _ in range(3):
+            sh_st.compose([t.data_ptr() for t in d_src], sw * 3, out.data_ptr(), pitch, stream)
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            sh_st.compose([t.data_ptr() for t in d_src], sw * 3, out.data_ptr(), pitch, stream)
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        res["fps"] = steps / (D.reduce_step_time(e0.elapsed_time(e1), dist, "cuda") / 1000.0)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)
+    if rank == 0:
+        from oracle import oracle as og
+        from oracle import pipeline as op
+        og.set_num_threads(min(8, os.cpu_count() or 1))
+        orig = op.OracleRig(n, sw, sh, case["pano_width"], num_bands=case["num_bands"], enable_local=True, gains=gains)
+        for i in range(n):
+            orig.set_mesh(i, *S.mesh(*orig.sizes[i]))
+        want, _ = orig.compose(frames)
+        got = full.cpu().numpy()[:, :W * 3].reshape(H, W, 3).astype(np.int16)
+        bad = int(np.count_nonzero(got != want))
+        print(json.dumps({"world": world, "bad": bad, "size": int(want.size), "ranks": gathered}), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,7 @@ SYMBOLS = [
     "vsb_compose_host", "vsb_last_launch_count", "vsb_remap_linear_u8c3", "vsb_gain_u8",
     "vsb_border_reflect_u8c3_to_s16c3", "vsb_pyr_down_s16c3", "vsb_pyr_up_s16c3", "vsb_pyr_down_f32",
     "vsb_add_src_weight_32f", "vsb_normalize_32f", "vsb_debug_read",
+    "vsb_shard_set", "vsb_shard_info", "vsb_shard_rect", "vsb_get_plane",
     "vsb_rig_camera", "vsb_voronoi_seams", "vsb_calibrate_rig", "vsb_rig_info_get", "vsb_get_config", "vsb_set_profiling", "vsb_get_profile",
 ]
 
@@ -182,6 +183,25 @@ class Stitcher:
         sp = (C.c_void_p * len(src_ptrs))(*[int(p) for p in src_ptrs])
         op = (C.c_void_p * n_frames)(*[int(p) for p in out_ptrs])
         check(lib().vsb_compose_host(self._h, n_frames, sp, C.c_size_t(src_pitch), op, C.c_size_t(out_pitch)))
+
+    # ---- view-sharded mode
+    def shard_set(self, rank, world):
+        check(lib().vsb_shard_set(self._h, rank, world))
+
+    def shard_info(self):
+        a, b, m = C.c_int(), C.c_int(), C.c_uint()
+        check(lib().vsb_shard_info(self._h, C.byref(a), C.byref(b), C.byref(m)))
+        return a.value, b.value, [i for i in range(self.num_views) if m.value >> i & 1]
+
+    def shard_rect(self, dst_rank, view, level):
+        r = (C.c_int * 4)()
+        check(lib().vsb_shard_rect(self._h, dst_rank, view, level, r))
+        return tuple(r)
+
+    def get_plane(self, view, level, frame=0):
+        p, w, h = C.c_void_p(), C.c_int(), C.c_int()
+        check(lib().vsb_get_plane(self._h, view, level, frame, C.byref(p), C.byref(w), C.byref(h)))
+        return p.value, w.value, h.value
 
     def last_launch_count(self):
         return lib().vsb_last_launch_count(self._h)

@@ -372,8 +372,9 @@ __global__ void __launch_bounds__(C_THREADS) k_coarse(const __grid_constant__ Co
     uint8_t *G = c_smem + (size_t)Gm.a_total * 2;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31, c = blockIdx.y, f = blockIdx.z, nlev = Gm.nlev;
     const int X0 = (blockIdx.x % P.tiles_x) * CT, Y0 = (blockIdx.x / P.tiles_x) * CT;
-    for (int i = t; i < Gm.a_total; i += C_THREADS) A[i] = 0;
     unsigned views = __ldg(P.tile_views + blockIdx.x);
+    if (views & 0x80000000u) return;  // view-sharded mode: another rank owns this canvas strip
+    for (int i = t; i < Gm.a_total; i += C_THREADS) A[i] = 0;
     while (views) {
         const int vi = __ffs(views) - 1;
         views &= views - 1;
@@ -510,6 +511,7 @@ __global__ void __launch_bounds__(BL_THREADS, 3) k_blend(const __grid_constant__
     const int qr1 = 2 * (t / BL_QW), qc1 = 2 * (t % BL_QW);  // this thread's level-1 quad (threads < BL_NQ)
 
     unsigned views = __ldg(P.tile_views + blockIdx.y * P.tiles_x + blockIdx.x);
+    if (views & 0x80000000u) return;  // view-sharded mode: another rank owns this canvas strip
     while (views) {
         const int vi = __ffs(views) - 1;  // ascending view order: the weight sums below add in the reference's order
         views &= views - 1;

@@ -429,6 +429,7 @@ struct View {
     std::vector<uint8_t> g2_needed;     // per k_down2 tile: computed (1) or skipped (0); host copy for vsb_debug_read
     int d2_tiles_x = 0, d2_tiles_y = 0;
     std::vector<uint32_t> s1_tiles, s2_tiles;  // 128 x 8 tiles k_remap_stage1 / k_remap_stage2 compute (packed view|tx|ty)
+    std::vector<int> w0_cols;                  // per plane column: number of non-zero level-0 weights (view -> strip ownership)
 };
 
 }  // namespace vsb
@@ -454,6 +455,11 @@ struct vsb_stitcher {
     size_t c2_frame_stride = 0;
     uint32_t *d_s1_tiles = nullptr, *d_s2_tiles = nullptr;  // concatenated per-view lists, view order
     vsb::CoarseView *d_coarse_desc = nullptr;
+    // view-sharded mode (vsb_shard_set): this rank's views and canvas strip; host copies of the tile tables
+    std::vector<uint32_t> h_bviews, h_cviews;
+    int shard_rank = -1, shard_world = 1, strip_w = 0;
+    bool owned[vsb::MAXV] = {};
+    uint32_t *d_blend_views_all = nullptr, *d_coarse_views_all = nullptr;  // unsharded tables (d_*_views point at the active ones)
     bool tiles_dirty = true;
     cudaStream_t setup_stream = nullptr, mesh_stream = nullptr, io_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
     cudaEvent_t ev_in[vsb::MAX_BATCH] = {}, ev_done[vsb::MAX_BATCH] = {};
@@ -583,6 +589,12 @@ static int build_fast_plan(vsb_stitcher *s)
             for (size_t j = 0; j < tmp.size(); ++j) hw[i].nz[k][j] = tmp[j] != 0.f;
         }
     }
+    for (int i = 0; i < n; ++i) {
+        View &V = s->v[i];
+        V.w0_cols.assign(V.bw, 0);
+        for (int y = 0; y < V.bh; ++y)
+            for (int x = 0; x < V.bw; ++x) V.w0_cols[x] += hw[i].nz[0][(size_t)y * V.bw + x];
+    }
     // ---- k_blend: views with level-0 / level-1 weight per 64 x 32 canvas tile
     s->blend_tiles_x = (s->cw[0] + BL_TW - 1) / BL_TW; s->blend_tiles_y = (s->ch[0] + BL_TH - 1) / BL_TH;
     std::vector<uint32_t> bviews((size_t)s->blend_tiles_x * s->blend_tiles_y, 0);
@@ -673,6 +685,8 @@ static int build_fast_plan(vsb_stitcher *s)
     CK(cudaMalloc(&s->d_blend_views, bviews.size() * 4));
     CK(cudaMalloc(&s->d_coarse_views, cviews.size() * 4));
     CK(cudaMalloc(&s->d_down2_tiles, std::max<size_t>(d2tiles.size(), 1) * 4));
+    s->h_bviews = bviews; s->h_cviews = cviews; s->shard_rank = -1; s->shard_world = 1;
+    for (int i = 0; i < MAXV; ++i) s->owned[i] = i < n;
     CK(cudaMemcpy(s->d_blend_views, bviews.data(), bviews.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->d_coarse_views, cviews.data(), cviews.size() * 4, cudaMemcpyHostToDevice));
     if (!d2tiles.empty()) CK(cudaMemcpy(s->d_down2_tiles, d2tiles.data(), d2tiles.size() * 4, cudaMemcpyHostToDevice));
@@ -831,18 +845,21 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
     for (int k = 2; k < nb; ++k) {  // Gaussian levels 3..nb of every view (tiny planes)
         Down1Params p;
         std::memset(&p, 0, sizeof(p));
-        p.n = n;
         double bytes = 0;
+        int m = 0;  // views this rank owns (all of them unless vsb_shard_set was called)
         for (int i = 0; i < n; ++i) {
+            if (!s->owned[i]) continue;
             const View &V = s->v[i];
-            p.v[i].src = V.Gu[k]; p.v[i].dst = V.Gu[k + 1]; p.v[i].src_fs = V.gu_frame_stride[k]; p.v[i].dst_fs = V.gu_frame_stride[k + 1];
-            p.v[i].w = V.bw >> k; p.v[i].h = V.bh >> k;
+            p.v[m].src = V.Gu[k]; p.v[m].dst = V.Gu[k + 1]; p.v[m].src_fs = V.gu_frame_stride[k]; p.v[m].dst_fs = V.gu_frame_stride[k + 1];
+            p.v[m].w = V.bw >> k; p.v[m].h = V.bh >> k;
             const int wd = V.bw >> (k + 1), hd = V.bh >> (k + 1);
-            p.tiles_x[i] = (wd + D1_TX - 1) / D1_TX;
-            p.start[i + 1] = p.start[i] + p.tiles_x[i] * ((hd + D1_TY - 1) / D1_TY);
+            p.tiles_x[m] = (wd + D1_TX - 1) / D1_TX;
+            p.start[m + 1] = p.start[m] + p.tiles_x[m] * ((hd + D1_TY - 1) / D1_TY);
             bytes += 3.0 * (V.bw >> k) * (V.bh >> k) + 3.0 * wd * hd;
+            ++m;
         }
-        k_down1<<<dim3(p.start[n], n_frames, 3), dim3(D1_TX, D1_TY), 0, st>>>(p);
+        p.n = m;
+        if (m > 0) k_down1<<<dim3(p.start[m], n_frames, 3), dim3(D1_TX, D1_TY), 0, st>>>(p);
         ++s->launches;
         static const char *names[MAXL] = {"", "", "down1_L3", "down1_L4", "down1_L5", "down1_L6", "down1_L7", ""};
         prof_stage(s, st, names[k], bytes * n_frames);
@@ -1325,6 +1342,7 @@ int vsb_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, siz
 {
     REQ(s && d_srcs && d_outs, VSB_ERR_INVALID, "compose: null argument");
     REQ(n_frames >= 1 && n_frames <= s->cfg.max_batch, VSB_ERR_INVALID, "compose: n_frames must be 1..max_batch (%d)", s->cfg.max_batch);
+    REQ(s->shard_rank < 0, VSB_ERR_STATE, "compose: handle is view-sharded; feed the owned views, exchange, then blend");
     int r = ready_for_frames(s);
     if (r != VSB_OK) return r;
     DeviceGuard g(s->device);
@@ -1400,6 +1418,103 @@ int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs
     }
     CK(cudaStreamSynchronize(s->out_stream));
     CK(cudaStreamSynchronize(s->io_stream));
+    return VSB_OK;
+}
+
+
+// ---- view-sharded multi-GPU mode: one process per GPU, every rank calibrates the same rig ---------
+// Rank r owns (1) the canvas strip [r * strip_w, (r + 1) * strip_w) -- its k_coarse / k_blend tiles -- and (2) the views
+// whose level-0 weight lies mostly inside that strip -- their remap / pyramid front half.  Between the two halves the
+// ranks exchange the Gaussian sub-planes (u8) that foreign strips read; vsb_shard_rect names them, the transport is the
+// caller's (NCCL send/recv in video-stitcher_b200/dist.py).
+int vsb_shard_set(vsb_stitcher *s, int rank, int world)
+{
+    REQ(s, VSB_ERR_INVALID, "shard_set: null handle");
+    REQ(s->finalized && s->fast, VSB_ERR_STATE, "shard_set: needs a calibrated handle with num_bands >= 3");
+    REQ(world >= 1 && rank >= 0 && rank < world, VSB_ERR_INVALID, "shard_set: bad rank / world");
+    DeviceGuard g(s->device);
+    CK(cudaDeviceSynchronize());
+    const int n = s->cfg.num_views, cw0 = s->cw[0];
+    const int unit = CT * 4;  // k_coarse tiles are 256 level-0 columns wide
+    s->strip_w = (int)(align_up((size_t)(cw0 + world - 1) / world, unit));
+    s->shard_rank = rank; s->shard_world = world;
+    for (int i = 0; i < n; ++i) {
+        const View &V = s->v[i];
+        std::vector<long long> per(world, 0);
+        for (int x = 0; x < V.bw; ++x) per[std::min((V.x_tl + x) / s->strip_w, world - 1)] += V.w0_cols[x];
+        int best = 0;
+        for (int r = 1; r < world; ++r) if (per[r] > per[best]) best = r;
+        s->owned[i] = best == rank;
+    }
+    std::vector<uint32_t> b = s->h_bviews, c = s->h_cviews;
+    for (int ty = 0; ty < s->blend_tiles_y; ++ty)
+        for (int tx = 0; tx < s->blend_tiles_x; ++tx)
+            if (std::min(tx * BL_TW / s->strip_w, world - 1) != rank) b[(size_t)ty * s->blend_tiles_x + tx] = 0x80000000u;
+    for (int ty = 0; ty < s->coarse_tiles_y; ++ty)
+        for (int tx = 0; tx < s->coarse_tiles_x; ++tx)
+            if (std::min(tx * unit / s->strip_w, world - 1) != rank) c[(size_t)ty * s->coarse_tiles_x + tx] = 0x80000000u;
+    CK(cudaMemcpy(s->d_blend_views, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->d_coarse_views, c.data(), c.size() * 4, cudaMemcpyHostToDevice));
+    return VSB_OK;
+}
+
+int vsb_shard_info(const vsb_stitcher *s, int *strip_x0, int *strip_x1, unsigned *owned_mask)
+{
+    REQ(s && s->shard_rank >= 0, VSB_ERR_STATE, "shard_info: vsb_shard_set first");
+    if (strip_x0) *strip_x0 = s->shard_rank * s->strip_w;
+    if (strip_x1) *strip_x1 = std::min((s->shard_rank + 1) * s->strip_w, s->cw[0]);
+    if (owned_mask) { *owned_mask = 0; for (int i = 0; i < s->cfg.num_views; ++i) if (s->owned[i]) *owned_mask |= 1u << i; }
+    return VSB_OK;
+}
+
+// Bounding box {x0, y0, w, h} (plane coordinates of `level`) of what rank `dst_rank`'s tiles read from Gaussian level
+// `level` of `view`; w = h = 0 when nothing.  Pure function of the static tables: every rank computes every rank's needs.
+int vsb_shard_rect(const vsb_stitcher *s, int dst_rank, int view, int level, int rect[4])
+{
+    REQ(s && rect, VSB_ERR_INVALID, "shard_rect: null argument");
+    REQ(s->shard_rank >= 0, VSB_ERR_STATE, "shard_rect: vsb_shard_set first");
+    REQ(dst_rank >= 0 && dst_rank < s->shard_world && view >= 0 && view < s->cfg.num_views && level >= 0 && level <= s->nb, VSB_ERR_INVALID, "shard_rect: bad argument");
+    const View &V = s->v[view];
+    const int pw = V.bw >> level, ph = V.bh >> level, world = s->shard_world, unit = CT * 4;
+    int x0 = INT32_MAX, y0 = INT32_MAX, x1 = INT32_MIN, y1 = INT32_MIN;
+    auto add = [&](int ax0, int ay0, int w, int h) {  // plane coordinates, clipped
+        const int bx0 = std::max(ax0, 0), by0 = std::max(ay0, 0), bx1 = std::min(ax0 + w, pw), by1 = std::min(ay0 + h, ph);
+        if (bx0 >= bx1 || by0 >= by1) return;
+        x0 = std::min(x0, bx0); y0 = std::min(y0, by0); x1 = std::max(x1, bx1); y1 = std::max(y1, by1);
+    };
+    if (level <= 2)
+        for (int ty = 0; ty < s->blend_tiles_y; ++ty)
+            for (int tx = 0; tx < s->blend_tiles_x; ++tx) {
+                if (std::min(tx * BL_TW / s->strip_w, world - 1) != dst_rank || !(s->h_bviews[(size_t)ty * s->blend_tiles_x + tx] >> view & 1)) continue;
+                if (level == 0) add(tx * BL_TW - V.x_tl, ty * BL_TH - V.y_tl, BL_TW, BL_TH);
+                else if (level == 1) add((tx * BL_TW >> 1) - 1 - (V.x_tl >> 1), (ty * BL_TH >> 1) - 1 - (V.y_tl >> 1), BL_R1W, BL_R1H);
+                else add((tx * BL_TW >> 2) - 2 - (V.x_tl >> 2), (ty * BL_TH >> 2) - 2 - (V.y_tl >> 2), BL_R2W, BL_R2H);
+            }
+    if (level >= 2) {
+        const int j = level - 2;
+        for (int ty = 0; ty < s->coarse_tiles_y; ++ty)
+            for (int tx = 0; tx < s->coarse_tiles_x; ++tx) {
+                if (std::min(tx * unit / s->strip_w, world - 1) != dst_rank || !(s->h_cviews[(size_t)ty * s->coarse_tiles_x + tx] >> view & 1)) continue;
+                add(((tx * CT) >> j) + s->cgeo.a_lo[j] - (V.x_tl >> level), ((ty * CT) >> j) + s->cgeo.a_lo[j] - (V.y_tl >> level), s->cgeo.a_n[j], s->cgeo.a_n[j]);
+            }
+    }
+    if (x0 > x1) { rect[0] = rect[1] = rect[2] = rect[3] = 0; return VSB_OK; }
+    rect[0] = x0; rect[1] = y0; rect[2] = x1 - x0; rect[3] = y1 - y0;
+    return VSB_OK;
+}
+
+// device address of plane 0 of Gaussian level `level` of `view` in frame slot `frame` ([3][h][w] u8, rows of w bytes)
+int vsb_get_plane(vsb_stitcher *s, int view, int level, int frame, void **ptr, int *w, int *h)
+{
+    REQ(s && ptr, VSB_ERR_INVALID, "get_plane: null argument");
+    REQ(s->finalized && s->fast, VSB_ERR_STATE, "get_plane: needs a calibrated handle with num_bands >= 3");
+    REQ(view >= 0 && view < s->cfg.num_views && level >= 0 && level <= s->nb && frame >= 0 && frame < s->cfg.max_batch, VSB_ERR_INVALID, "get_plane: bad argument");
+    const View &V = s->v[view];
+    if (level == 0) *ptr = V.G0 + V.g0_frame_stride * frame;
+    else if (level == 1) *ptr = V.G1 + V.g1_frame_stride * frame;
+    else *ptr = V.Gu[level] + V.gu_frame_stride[level] * frame;
+    if (w) *w = V.bw >> level;
+    if (h) *h = V.bh >> level;
     return VSB_OK;
 }
 

@@ -36,3 +36,95 @@ def reduce_step_time(ms_local, dist=None, device=None):
     t = torch.tensor([ms_local], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# View-sharded mode: rank r composes its views' front half and its canvas strip's back half; in between
+# the ranks exchange the Gaussian sub-planes (u8) that foreign strips read.  The plan is a pure function of the static
+# calibration tables (vsb_shard_rect), identical on every rank; the transport is grouped point-to-point over
+# torch.distributed (NCCL send/recv on NVLink for CUDA tensors, gloo for the CPU tests).
+
+def build_exchange_plan(rect_fn, owners, rank, world, levels):
+    """rect_fn(dst_rank, view, level) -> (x0, y0, w, h) of what dst_rank reads of that plane (w == 0: nothing).
+    Returns (sends, recvs): lists of (view, level, rect, peer), both sorted by (peer, view, level) so that the k-th send
+    to a peer pairs with that peer's k-th receive."""
+    sends, recvs = [], []
+    for v, owner in enumerate(owners):
+        for k in levels:
+            if owner == rank:
+                for dst in range(world):
+                    if dst != rank:
+                        r = tuple(rect_fn(dst, v, k))
+                        if r[2] > 0 and r[3] > 0:
+                            sends.append((v, k, r, dst))
+            else:
+                r = tuple(rect_fn(rank, v, k))
+                if r[2] > 0 and r[3] > 0:
+                    recvs.append((v, k, r, owner))
+    key = lambda e: (e[3], e[0], e[1])
+    return sorted(sends, key=key), sorted(recvs, key=key)
+
+
+def exchange_bytes(plan_half):
+    return sum(3 * r[2] * r[3] for _, _, r, _ in plan_half)
+
+
+def run_exchange(dist, torch, plane_fn, sends, recvs):
+    """plane_fn(view, level) -> uint8 tensor [3, h, w] aliasing that Gaussian plane.  One grouped batch of isend / irecv,
+    then the received blocks are written into the local copies of the foreign planes."""
+    ops, landing = [], []
+    for v, k, (x0, y0, w, h), dst in sends:
+        ops.append(dist.P2POp(dist.isend, plane_fn(v, k)[:, y0:y0 + h, x0:x0 + w].contiguous(), dst))
+    for v, k, (x0, y0, w, h), src in recvs:
+        p = plane_fn(v, k)
+        buf = torch.empty((3, h, w), dtype=p.dtype, device=p.device)
+        ops.append(dist.P2POp(dist.irecv, buf, src))
+        landing.append((p, x0, y0, w, h, buf))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for p, x0, y0, w, h, buf in landing:
+        p[:, y0:y0 + h, x0:x0 + w].copy_(buf)
+
+
+class _DeviceArray:
+    """Zero-copy view of handle-owned device memory for torch.as_tensor (CUDA array interface, version 2)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "|u1", "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+class ShardedStitcher:
+    """One per rank, around a calibrated binding.Stitcher (every rank calibrates the same rig)."""
+
+    def __init__(self, st, dist, torch):
+        self.st, self.dist, self.torch = st, dist, torch
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        st.shard_set(self.rank, self.world)
+        self.strip_x0, self.strip_x1, self.owned = st.shard_info()
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, self.owned)
+        self.owners = [None] * st.num_views
+        for r, views in enumerate(gathered):
+            for v in views:
+                self.owners[v] = r
+        assert None not in self.owners, "every view needs exactly one owner"
+        _, _, nb = st.get_roi()
+        self.levels = list(range(nb + 1))
+        self.sends, self.recvs = build_exchange_plan(st.shard_rect, self.owners, self.rank, self.world, self.levels)
+        self._planes = {}
+
+    def plane(self, view, level):
+        key = (view, level)
+        if key not in self._planes:
+            ptr, w, h = self.st.get_plane(view, level, 0)
+            self._planes[key] = self.torch.as_tensor(_DeviceArray(ptr, (3, h, w)), device="cuda")
+        return self._planes[key]
+
+    def compose(self, src_ptrs, src_pitch, out_ptr, out_pitch, stream):
+        """src_ptrs: device BGR frames of ALL views (only the owned ones are read).  Writes this rank's strip of the
+        CV_16SC3 panorama into out_ptr (full-size buffer)."""
+        for v in self.owned:
+            self.st.feed(v, src_ptrs[v], src_pitch, stream)
+        run_exchange(self.dist, self.torch, self.plane, self.sends, self.recvs)
+        self.st.blend(out_ptr, out_pitch, stream)
