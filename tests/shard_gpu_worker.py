@@ -43,7 +43,29 @@ def main():
     torch.cuda.synchronize()
     full = out.to(torch.int32)
     dist.all_reduce(full)  # strips are disjoint and the rest of every rank's buffer is zero
-    res = {"rank": rank, "strip": [sh_st.strip_x0, sh_st.strip_x1], "owned": sh_st.owned,
+    debug = {}
+    if os.environ.get("VSB_SHARD_DEBUG"):
+        # (1) transport check: owners broadcast their full planes; compare inside the planned rectangles
+        # (2) coverage check: overwrite local copies of foreign planes with the full truth, blend again
+        bad_transport = 0
+        for v in range(n):
+            for k in sh_st.levels:
+                mine = sh_st.plane(v, k)
+                truth = mine.clone()
+                dist.broadcast(truth, src=sh_st.owners[v])
+                if sh_st.owners[v] != rank:
+                    x0, y0, w, h = st.shard_rect(rank, v, k)
+                    if w > 0:
+                        bad_transport += int((mine[:, y0:y0 + h, x0:x0 + w] != truth[:, y0:y0 + h, x0:x0 + w]).sum().item())
+                    mine.copy_(truth)
+        out2 = torch.zeros_like(out)
+        st.blend(out2.data_ptr(), pitch, stream)
+        torch.cuda.synchronize()
+        full2 = out2.to(torch.int32)
+        dist.all_reduce(full2)
+        debug = {"bad_transport": bad_transport, "diff_after_full_planes": int((full2 != full).sum().item())}
+        full = full2 if os.environ.get("VSB_SHARD_DEBUG") == "2" else full
+    res = {"rank": rank, "strip": [sh_st.strip_x0, sh_st.strip_x1], "owned": sh_st.owned, "debug": debug,
            "send_bytes": D.exchange_bytes(sh_st.sends), "recv_bytes": D.exchange_bytes(sh_st.recvs)}
     if steps > 0:
         for _ in range(3):
@@ -68,7 +90,12 @@ def main():
         want, _ = orig.compose(frames)
         got = full.cpu().numpy()[:, :W * 3].reshape(H, W, 3).astype(np.int16)
         bad = int(np.count_nonzero(got != want))
-        print(json.dumps({"world": world, "bad": bad, "size": int(want.size), "ranks": gathered}), flush=True)
+        diag = None
+        if bad:
+            cols = np.nonzero((got != want).any(axis=(0, 2)))[0]
+            bins = sorted(set(int(c) // 64 for c in cols))
+            diag = {"first_col": int(cols.min()), "last_col": int(cols.max()), "bins64": bins[:80], "max_abs": int(np.abs(got.astype(int) - want.astype(int)).max())}
+        print(json.dumps({"world": world, "bad": bad, "size": int(want.size), "diag": diag, "ranks": gathered}), flush=True)
     dist.destroy_process_group()
 
 

@@ -838,17 +838,16 @@ static int launch_down2(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
     return check_launch("k_down2");
 }
 
-// K4 + K5
-static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, size_t out_pitch, cudaStream_t st)
+// K3b: Gaussian levels 3..nb of views [v0, v1) (tiny planes), one launch per level
+static int launch_down1(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStream_t st)
 {
-    const int n = s->cfg.num_views, nb = s->nb;
-    for (int k = 2; k < nb; ++k) {  // Gaussian levels 3..nb of every view (tiny planes)
+    const int nb = s->nb;
+    for (int k = 2; k < nb; ++k) {
         Down1Params p;
         std::memset(&p, 0, sizeof(p));
         double bytes = 0;
-        int m = 0;  // views this rank owns (all of them unless vsb_shard_set was called)
-        for (int i = 0; i < n; ++i) {
-            if (!s->owned[i]) continue;
+        int m = 0;
+        for (int i = v0; i < v1; ++i) {
             const View &V = s->v[i];
             p.v[m].src = V.Gu[k]; p.v[m].dst = V.Gu[k + 1]; p.v[m].src_fs = V.gu_frame_stride[k]; p.v[m].dst_fs = V.gu_frame_stride[k + 1];
             p.v[m].w = V.bw >> k; p.v[m].h = V.bh >> k;
@@ -864,6 +863,13 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
         static const char *names[MAXL] = {"", "", "down1_L3", "down1_L4", "down1_L5", "down1_L6", "down1_L7", ""};
         prof_stage(s, st, names[k], bytes * n_frames);
     }
+    return check_launch("k_down1");
+}
+
+// K4 + K5
+static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, size_t out_pitch, cudaStream_t st)
+{
+    const int n = s->cfg.num_views, nb = s->nb;
     {
         CoarseParams p;
         std::memset(&p, 0, sizeof(p));
@@ -955,7 +961,10 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
         ++s->launches;
         prof_stage(s, st, "remap_stage2", bytes * n_frames);
     }
-    if (s->fast) return launch_down2(s, v0, v1, n_frames, st);
+    if (s->fast) {
+        r = launch_down2(s, v0, v1, n_frames, st);
+        return r != VSB_OK ? r : launch_down1(s, v0, v1, n_frames, st);
+    }
     for (int k = 0; k < s->nb; ++k) {
         PyrParams p;
         std::memset(&p, 0, sizeof(p));
@@ -1427,6 +1436,14 @@ int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs
 // whose level-0 weight lies mostly inside that strip -- their remap / pyramid front half.  Between the two halves the
 // ranks exchange the Gaussian sub-planes (u8) that foreign strips read; vsb_shard_rect names them, the transport is the
 // caller's (NCCL send/recv in video-stitcher_b200/dist.py).
+// k_blend tiles read C2 two level-2 samples (8 level-0 columns) beyond their own columns, so a rank also runs the k_coarse
+// tiles that touch its strip widened by that margin (the neighbour computes the same tile for itself).
+static bool coarse_tile_of_rank(const vsb_stitcher *s, int tx, int rank)
+{
+    const int unit = vsb::CT * 4, x0 = rank * s->strip_w - 8, x1 = std::min((rank + 1) * s->strip_w, s->cw[0]) + 8;
+    return tx * unit < x1 && (tx + 1) * unit > x0;
+}
+
 int vsb_shard_set(vsb_stitcher *s, int rank, int world)
 {
     REQ(s, VSB_ERR_INVALID, "shard_set: null handle");
@@ -1452,7 +1469,7 @@ int vsb_shard_set(vsb_stitcher *s, int rank, int world)
             if (std::min(tx * BL_TW / s->strip_w, world - 1) != rank) b[(size_t)ty * s->blend_tiles_x + tx] = 0x80000000u;
     for (int ty = 0; ty < s->coarse_tiles_y; ++ty)
         for (int tx = 0; tx < s->coarse_tiles_x; ++tx)
-            if (std::min(tx * unit / s->strip_w, world - 1) != rank) c[(size_t)ty * s->coarse_tiles_x + tx] = 0x80000000u;
+            if (!coarse_tile_of_rank(s, tx, rank)) c[(size_t)ty * s->coarse_tiles_x + tx] = 0x80000000u;
     CK(cudaMemcpy(s->d_blend_views, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->d_coarse_views, c.data(), c.size() * 4, cudaMemcpyHostToDevice));
     return VSB_OK;
@@ -1475,7 +1492,7 @@ int vsb_shard_rect(const vsb_stitcher *s, int dst_rank, int view, int level, int
     REQ(s->shard_rank >= 0, VSB_ERR_STATE, "shard_rect: vsb_shard_set first");
     REQ(dst_rank >= 0 && dst_rank < s->shard_world && view >= 0 && view < s->cfg.num_views && level >= 0 && level <= s->nb, VSB_ERR_INVALID, "shard_rect: bad argument");
     const View &V = s->v[view];
-    const int pw = V.bw >> level, ph = V.bh >> level, world = s->shard_world, unit = CT * 4;
+    const int pw = V.bw >> level, ph = V.bh >> level, world = s->shard_world;
     int x0 = INT32_MAX, y0 = INT32_MAX, x1 = INT32_MIN, y1 = INT32_MIN;
     auto add = [&](int ax0, int ay0, int w, int h) {  // plane coordinates, clipped
         const int bx0 = std::max(ax0, 0), by0 = std::max(ay0, 0), bx1 = std::min(ax0 + w, pw), by1 = std::min(ay0 + h, ph);
@@ -1494,7 +1511,7 @@ int vsb_shard_rect(const vsb_stitcher *s, int dst_rank, int view, int level, int
         const int j = level - 2;
         for (int ty = 0; ty < s->coarse_tiles_y; ++ty)
             for (int tx = 0; tx < s->coarse_tiles_x; ++tx) {
-                if (std::min(tx * unit / s->strip_w, world - 1) != dst_rank || !(s->h_cviews[(size_t)ty * s->coarse_tiles_x + tx] >> view & 1)) continue;
+                if (!coarse_tile_of_rank(s, tx, dst_rank) || !(s->h_cviews[(size_t)ty * s->coarse_tiles_x + tx] >> view & 1)) continue;
                 add(((tx * CT) >> j) + s->cgeo.a_lo[j] - (V.x_tl >> level), ((ty * CT) >> j) + s->cgeo.a_lo[j] - (V.y_tl >> level), s->cgeo.a_n[j], s->cgeo.a_n[j]);
             }
     }
