@@ -168,6 +168,68 @@ def run_reference(args, cfg, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_sharded(args, cfg, rank, world, local_rank):
+    """View-sharded mode: all ranks work on the SAME frame (strong scaling of one stream); one frame per step."""
+    import torch
+    import torch.distributed as dist
+    import vsb200
+    B, S, D = vsb200.binding, vsb200.synth, vsb200.dist
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29655", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
+    n, K, W = cfg["n_views"], args.steps, max(args.warmup, 3)
+    st = B.Stitcher(n, cfg["num_bands"], cfg["enable_local"], 1)
+    st.calibrate_rig(cfg["projection"], cfg["pano_width"], cfg["src_w"], cfg["src_h"], 90.0, S.gains(n))
+    info = st.rig_info()
+    if cfg["enable_local"]:
+        for i in range(n):
+            mx, my = S.mesh(info.view_roi[i][2], info.view_roi[i][3])
+            st.set_mesh(i, mx.ctypes.data, my.ctypes.data, mx.shape[0], mx.shape[1])
+    roi, _, nb = st.get_roi()
+    OW, OH = roi[2], roi[3]
+    sh = D.ShardedStitcher(st, dist, torch)
+    sets = [[torch.from_numpy(S.frame(i, f, cfg["src_w"], cfg["src_h"])).cuda() for i in range(n)] for f in range(RING)]
+    out_pitch = (OW * 6 + 255) // 256 * 256
+    out = torch.zeros((OH, out_pitch // 2), dtype=torch.int16, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    def step(k):
+        sh.compose([t.data_ptr() for t in sets[k % RING]], cfg["src_w"] * 3, out.data_ptr(), out_pitch, stream)
+    for w in range(W):
+        step(w)
+    dist.barrier(); torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank); sampler.start(); time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time(); e0.record()
+    for k in range(K):
+        step(k)
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    t1 = time.time()
+    ms = D.reduce_step_time(e0.elapsed_time(e1), dist, "cuda")
+    sampler.stop()
+    launches = st.last_launch_count()
+    stats = [None] * world
+    dist.all_gather_object(stats, {"rank": rank, "views": sh.owned, "strip": [sh.strip_x0, sh.strip_x1],
+                                   "send_bytes_per_frame": D.exchange_bytes(sh.sends), "launches_per_frame": launches})
+    if rank == 0:
+        fps = K / (ms / 1000.0)
+        b_io = n * cfg["src_w"] * cfg["src_h"] * 3 + OW * OH * 6
+        peak = 6541.5
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
+        print(json.dumps({
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/s16 (fp32 taps)", "data": "synthetic",
+            "config": {"workload": cfg["name"], "frames_per_step": 1, "pano": f"{OW}x{OH} CV_16SC3", "bands": nb,
+                       "multi_gpu": "view-sharded: views + canvas strips per rank, one NCCL send/recv exchange of Gaussian u8 sub-planes per frame",
+                       "l2_policy": f"ring of {RING} frame sets"},
+            "clocks": sampler.summary(t0, t1), "e2e": None, "gpu_launches": sum(s_["launches_per_frame"] for s_ in stats) * K,
+            "roofline_path": {"alg_bytes_per_frame": b_io, "achieved": b_io * fps / world / 1e9, "peak": peak, "unit": "GB/s", "frac": b_io * fps / world / 1e9 / peak},
+            "shards": stats, "exchange_bytes_per_frame": sum(s_["send_bytes_per_frame"] for s_ in stats)}), flush=True)
+    dist.destroy_process_group()
+
+
 def ncu_traffic(kernel, frames_per_launch):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json), scaled to
     this run's frames per launch; None when no capture of that kernel is on file."""
@@ -190,6 +252,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=16.0, help="CPU baseline sample budget")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "shard"],
+                    help="N > 1: replicas = every rank composes its own frames (default); shard = ONE frame stream, views and canvas "
+                         "strips split across ranks with an NCCL exchange of Gaussian sub-planes (SURVEY.md 8e)")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -212,6 +277,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    if args.mode == "shard":
+        run_sharded(args, cfg, rank, world, local_rank)
+        return
     F, K, W = args.batch, args.steps, max(args.warmup, 3)
     n = cfg["n_views"]
     st = B.Stitcher(n, cfg["num_bands"], cfg["enable_local"], F)

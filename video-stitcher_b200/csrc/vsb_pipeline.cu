@@ -466,7 +466,7 @@ struct vsb_stitcher {
     cudaEvent_t last_compose = nullptr;
     bool last_compose_valid = false;
     std::mutex mu;  // guards mesh publication
-    int launches = 0;
+    int launches = 0, launches_last = 0;  // running count of the submission in flight / count of the last finished one
     // vsb_feed / vsb_blend bookkeeping (frame slot 0)
     // host-buffer path staging
     uint8_t *stage_src = nullptr;
@@ -1014,6 +1014,8 @@ static int launch_back(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, si
 
 static int note_compose_done(vsb_stitcher *s, cudaStream_t st)
 {
+    s->launches_last = s->launches;
+    s->launches = 0;
     std::lock_guard<std::mutex> lk(s->mu);
     CK(cudaEventRecord(s->last_compose, st));
     s->last_compose_valid = true;
@@ -1314,7 +1316,7 @@ int vsb_feed(vsb_stitcher *s, int i, const uint8_t *d_bgr, size_t pitch, void *s
     if (r != VSB_OK) return r;
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (i == 0) { s->launches = 0; prof_begin(s, st); }
+    if (s->launches == 0) prof_begin(s, st);
     r = adopt_meshes(s, st);
     if (r != VSB_OK) return r;
     const uint8_t *srcs[1] = {d_bgr};
@@ -1331,7 +1333,7 @@ int vsb_feed_warped(vsb_stitcher *s, int i, const uint8_t *d_warped, size_t pitc
     REQ(pitch >= (size_t)s->v[i].roi_w * 3, VSB_ERR_INVALID, "feed_warped: pitch too small for a %d-pixel-wide CV_8UC3 view", s->v[i].roi_w);
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (i == 0) { s->launches = 0; prof_begin(s, st); }
+    if (s->launches == 0) prof_begin(s, st);
     return launch_front(s, i, i + 1, 1, nullptr, pitch, st, d_warped);
 }
 
@@ -1535,7 +1537,7 @@ int vsb_get_plane(vsb_stitcher *s, int view, int level, int frame, void **ptr, i
     return VSB_OK;
 }
 
-int vsb_last_launch_count(const vsb_stitcher *s) { return s ? s->launches : 0; }
+int vsb_last_launch_count(const vsb_stitcher *s) { return s ? s->launches_last : 0; }
 
 int vsb_set_profiling(vsb_stitcher *s, int on)
 {
