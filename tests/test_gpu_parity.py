@@ -217,6 +217,25 @@ def test_batched_compose_and_mesh_swap(cuda, og):
     _eq(grig.compose([fr[2]])[0], orig.compose(fr[2])[0], "after double mesh swap")
 
 
+@pytest.mark.parametrize("variant,pad", [(-1, 0), (0, 0), (1, 0), (2, 0), (3, 0), (1, 1), (1, 4)])
+def test_remap_kernel_variants(cuda, og, tmp_path, variant, pad):
+    """Every form of the remap kernels (coordinate-driven, table-driven scalar / packed-pair / conversion-unit mixes) gives the
+    oracle's frames; pad = 1 makes the caller's rows unaligned (falls back to the coordinate-driven kernels)."""
+    import os
+    import subprocess
+    import sys
+    import vsb200
+    orig, _, kw = _rigs("small4", inject=False)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "v.npz")
+    env = dict(os.environ, VSB_REMAP_VARIANT=str(variant))
+    subprocess.run([sys.executable, os.path.join(root, "tests", "variant_gpu_worker.py"), out, str(pad)], check=True, env=env, timeout=600)
+    got = np.load(out)
+    for f in range(2):
+        frames = [vsb200.synth.frame(i, f, kw["src_w"], kw["src_h"]) for i in range(kw["n_views"])]
+        _eq(got[f"pano{f}"], orig.compose(frames)[0], f"variant {variant} pad {pad} frame {f}")
+
+
 def test_compose_host_roundtrip(cuda, og):
     import vsb200
     orig, grig, kw = _rigs("small4", inject=False, max_batch=2)

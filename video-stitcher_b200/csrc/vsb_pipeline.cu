@@ -18,6 +18,7 @@
 // width (a multiple of 2^nb) as row length, so rows of every level start word aligned.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -152,6 +153,176 @@ __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage2(const __grid_cons
         *(unsigned *)(g + 2 * plane) = c2;
     } else {
         for (int i = 0; i < n; ++i) { g[i] = (c0 >> (8 * i)) & 0xff; g[plane + i] = (c1 >> (8 * i)) & 0xff; g[2 * plane + i] = (c2 >> (8 * i)) & 0xff; }
+    }
+}
+
+// ---- K1 / K2, table-driven form (the one the compose path runs whenever the caller's frames are 4-byte aligned) -------
+// Tap tables: per pixel one int32 window offset + four fp32 weights, stored as five planes of `tab_pitch` elements per
+// row (16-byte aligned rows: one 128-bit load per plane and thread).  Built by k_build_taps1 when the projection maps or
+// the caller's row pitch change, by k_build_taps2 when a CPW mesh is published (vsb_set_mesh, double buffered with it).
+struct TapTable {
+    const int *off;     // [rows][tab_pitch]
+    const float *w;     // [4][rows][tab_pitch]
+    size_t plane;       // elements per weight plane
+    int tab_pitch;
+};
+
+// One thread per table entry of remap #1.  Entries whose 32-bit window loads would leave the caller's image buffer
+// (last bytes of the last row) are marked TAP_SLOW and take the coordinate-driven edge routine in the frame kernel.
+__global__ void k_build_taps1(const float *__restrict__ xmap, const float *__restrict__ ymap, size_t map_pitch, int w, int h,
+                              int sw, int sh, unsigned pitch, int *__restrict__ off, float *__restrict__ wgt, size_t plane, int tab_pitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= tab_pitch || y >= h) return;
+    TapEntry e;
+    e.off = 0; e.wa = e.wb = e.wc = e.wd = 0.f;
+    if (x < w) {
+        const float fx = *((const float *)((const char *)xmap + (size_t)y * map_pitch) + x);
+        const float fy = *((const float *)((const char *)ymap + (size_t)y * map_pitch) + x);
+        e = make_tap_entry(fx, fy, sw, sh, pitch, 0u, false);
+        const unsigned p2 = (unsigned)e.off + pitch;                       // second row of the window
+        const unsigned end = (p2 & ~3u) + ((p2 & 3u) == 3u ? 12u : 8u);    // one past the last byte the word loads touch
+        if (end > (unsigned)(sh - 1) * pitch + (unsigned)sw * 3u) e.off = TAP_SLOW;
+    }
+    const size_t i = (size_t)y * tab_pitch + x;
+    off[i] = e.off; wgt[i] = e.wa; wgt[plane + i] = e.wb; wgt[2 * plane + i] = e.wc; wgt[3 * plane + i] = e.wd;
+}
+
+// One thread per BORDERED pixel of remap #2: the REFLECT border is resolved here, the taps address the zero-framed P.
+__global__ void k_build_taps2(const float *__restrict__ xmesh, const float *__restrict__ ymesh, size_t map_pitch, int w, int h,
+                              int bw, int bh, int top, int left, unsigned p_pitch, unsigned origin,
+                              int *__restrict__ off, float *__restrict__ wgt, size_t plane, int tab_pitch)
+{
+    const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
+    if (bx >= tab_pitch || by >= bh) return;
+    TapEntry e;
+    e.off = (int)origin; e.wa = e.wb = e.wc = e.wd = 0.f;
+    if (bx < bw) {
+        const int x = reflect_idx(bx - left, w), y = reflect_idx(by - top, h);
+        const float fx = *((const float *)((const char *)xmesh + (size_t)y * map_pitch) + x);
+        const float fy = *((const float *)((const char *)ymesh + (size_t)y * map_pitch) + x);
+        e = make_tap_entry(fx, fy, w, h, p_pitch, origin, true);
+    }
+    const size_t i = (size_t)by * tab_pitch + bx;
+    off[i] = e.off; wgt[i] = e.wa; wgt[plane + i] = e.wb; wgt[2 * plane + i] = e.wc; wgt[3 * plane + i] = e.wd;
+}
+
+struct Stage1TabView {
+    TapTable tab;
+    const float *xmap, *ymap;   // only for TAP_SLOW entries
+    uint8_t *P;
+    size_t map_pitch, p_pitch, p_frame_stride;
+    int w, h, src_w, src_h;
+    float gain;
+};
+struct Stage1TabParams {
+    const uint32_t *tiles;
+    Stage1TabView v[MAXV];
+    const uint8_t *src[MAX_BATCH * MAXV];  // [frame][view - v0]
+    unsigned src_pitch;
+    int v0, n_views, n_frames, frame_shift;  // block = tile << frame_shift | frame: the frames of a tile run back to back (table stays in L2)
+};
+
+// VAR: 0 = scalar chain, 1..3 = packed pairs with 0 / 1 / 2 taps per channel converted on the conversion unit (remap_tab_px2)
+template <int VAR>
+__global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage1_tab(const __grid_constant__ Stage1TabParams p)
+{
+    const int f = blockIdx.x & ((1 << p.frame_shift) - 1);
+    if (f >= p.n_frames) return;
+    const unsigned tile = __ldg(p.tiles + (blockIdx.x >> p.frame_shift));
+    const int vi = tile & 0xff;
+    const Stage1TabView &V = p.v[vi];
+    const int x0 = ((int)((tile >> 8) & 0xfff) * RM_BX + threadIdx.x) * RM_PX, y = (int)(tile >> 20) * RM_BY + threadIdx.y;
+    if (x0 >= V.w || y >= V.h) return;
+    const uint8_t *src = p.src[f * p.n_views + vi - p.v0];
+    const size_t i = (size_t)y * V.tab.tab_pitch + x0;
+    const int4 o = __ldg((const int4 *)(V.tab.off + i));
+    const float4 A = __ldg((const float4 *)(V.tab.w + i)), B = __ldg((const float4 *)(V.tab.w + V.tab.plane + i));
+    const float4 C = __ldg((const float4 *)(V.tab.w + 2 * V.tab.plane + i)), D = __ldg((const float4 *)(V.tab.w + 3 * V.tab.plane + i));
+    const int off[RM_PX] = {o.x, o.y, o.z, o.w};
+    unsigned px[RM_PX];
+    if (VAR == 0) {
+        const float wa[RM_PX] = {A.x, A.y, A.z, A.w}, wb[RM_PX] = {B.x, B.y, B.z, B.w}, wc[RM_PX] = {C.x, C.y, C.z, C.w}, wd[RM_PX] = {D.x, D.y, D.z, D.w};
+#pragma unroll
+        for (int k = 0; k < RM_PX; ++k) px[k] = remap_tab_px<true>(src, p.src_pitch, (unsigned)off[k] & 0x7fffffffu, wa[k], wb[k], wc[k], wd[k], V.gain);
+    } else {
+        constexpr int NXU = VAR > 0 ? VAR - 1 : 0;
+        remap_tab_px2<true, NXU>(src, p.src_pitch, (unsigned)o.x, (unsigned)o.y, make_float2(A.x, A.y), make_float2(B.x, B.y), make_float2(C.x, C.y), make_float2(D.x, D.y), V.gain, px[0], px[1]);
+        remap_tab_px2<true, NXU>(src, p.src_pitch, (unsigned)o.z, (unsigned)o.w, make_float2(A.z, A.w), make_float2(B.z, B.w), make_float2(C.z, C.w), make_float2(D.z, D.w), V.gain, px[2], px[3]);
+    }
+    if ((o.x | o.y | o.z | o.w) < 0) {  // TAP_SLOW entries: the window loads above were redirected to offset 0, the result comes from the coordinates
+#pragma unroll 1
+        for (int k = 0; k < RM_PX; ++k) {
+            if (off[k] >= 0) continue;
+            const float fx = __ldg((const float *)((const char *)V.xmap + (size_t)y * V.map_pitch) + x0 + k);
+            const float fy = __ldg((const float *)((const char *)V.ymap + (size_t)y * V.map_pitch) + x0 + k);
+            px[k] = remap_gain_px_edge<true>(src, p.src_pitch, V.src_w, V.src_h, fx, fy, V.gain);
+        }
+    }
+    uint8_t *dst = V.P + (size_t)f * V.p_frame_stride + (size_t)y * V.p_pitch + (size_t)x0 * 3;
+    const int n = min(RM_PX, V.w - x0);
+    if (n == RM_PX) {  // 12 bytes = three aligned 32-bit stores
+        unsigned *d32 = (unsigned *)dst;
+        d32[0] = px[0] | (px[1] << 24);
+        d32[1] = (px[1] >> 8) | (px[2] << 16);
+        d32[2] = (px[2] >> 16) | (px[3] << 8);
+    } else {
+        for (int k = 0; k < n; ++k) { dst[3 * k] = px[k] & 0xff; dst[3 * k + 1] = (px[k] >> 8) & 0xff; dst[3 * k + 2] = (px[k] >> 16) & 0xff; }
+    }
+}
+
+struct Stage2TabView {
+    TapTable tab;
+    const uint8_t *Pbase;        // frame 0 of the zero-framed P allocation (table offsets are relative to it)
+    uint8_t *G0;
+    size_t p_frame_stride, g0_frame_stride;
+    unsigned p_pitch;
+    int bw, bh;
+};
+struct Stage2TabParams {
+    const uint32_t *tiles;
+    Stage2TabView v[MAXV];
+    int n_frames, frame_shift;
+};
+
+template <int VAR>
+__global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage2_tab(const __grid_constant__ Stage2TabParams p)
+{
+    const int f = blockIdx.x & ((1 << p.frame_shift) - 1);
+    if (f >= p.n_frames) return;
+    const unsigned tile = __ldg(p.tiles + (blockIdx.x >> p.frame_shift));
+    const Stage2TabView &V = p.v[tile & 0xff];
+    const int bx0 = ((int)((tile >> 8) & 0xfff) * RM_BX + threadIdx.x) * RM_PX, by = (int)(tile >> 20) * RM_BY + threadIdx.y;
+    if (bx0 >= V.bw || by >= V.bh) return;
+    const uint8_t *P = V.Pbase + (size_t)f * V.p_frame_stride;
+    const size_t i = (size_t)by * V.tab.tab_pitch + bx0;
+    const int4 o = __ldg((const int4 *)(V.tab.off + i));
+    const float4 A = __ldg((const float4 *)(V.tab.w + i)), B = __ldg((const float4 *)(V.tab.w + V.tab.plane + i));
+    const float4 C = __ldg((const float4 *)(V.tab.w + 2 * V.tab.plane + i)), D = __ldg((const float4 *)(V.tab.w + 3 * V.tab.plane + i));
+    unsigned px[RM_PX];
+    if (VAR == 0) {
+        px[0] = remap_tab_px<false>(P, V.p_pitch, (unsigned)o.x, A.x, B.x, C.x, D.x, 1.f);
+        px[1] = remap_tab_px<false>(P, V.p_pitch, (unsigned)o.y, A.y, B.y, C.y, D.y, 1.f);
+        px[2] = remap_tab_px<false>(P, V.p_pitch, (unsigned)o.z, A.z, B.z, C.z, D.z, 1.f);
+        px[3] = remap_tab_px<false>(P, V.p_pitch, (unsigned)o.w, A.w, B.w, C.w, D.w, 1.f);
+    } else {
+        constexpr int NXU = VAR > 0 ? VAR - 1 : 0;
+        remap_tab_px2<false, NXU>(P, V.p_pitch, (unsigned)o.x, (unsigned)o.y, make_float2(A.x, A.y), make_float2(B.x, B.y), make_float2(C.x, C.y), make_float2(D.x, D.y), 1.f, px[0], px[1]);
+        remap_tab_px2<false, NXU>(P, V.p_pitch, (unsigned)o.z, (unsigned)o.w, make_float2(A.z, A.w), make_float2(B.z, B.w), make_float2(C.z, C.w), make_float2(D.z, D.w), 1.f, px[2], px[3]);
+    }
+    // interleaved -> planar: byte c of the four pixels
+    const unsigned lo01 = __byte_perm(px[0], px[1], 0x5140u), lo23 = __byte_perm(px[2], px[3], 0x5140u);
+    const unsigned c0 = __byte_perm(lo01, lo23, 0x5410u), c1 = __byte_perm(lo01, lo23, 0x7632u);
+    const unsigned c2 = __byte_perm(__byte_perm(px[0], px[1], 0x0062u), __byte_perm(px[2], px[3], 0x0062u), 0x5410u);
+    const size_t plane = (size_t)V.bw * V.bh;
+    uint8_t *g = V.G0 + (size_t)f * V.g0_frame_stride + (size_t)by * V.bw + bx0;
+    const int n = min(RM_PX, V.bw - bx0);
+    if (n == RM_PX && (V.bw & 3) == 0) {
+        *(unsigned *)g = c0;
+        *(unsigned *)(g + plane) = c1;
+        *(unsigned *)(g + 2 * plane) = c2;
+    } else {
+        for (int k = 0; k < n; ++k) { g[k] = (c0 >> (8 * k)) & 0xff; g[plane + k] = (c1 >> (8 * k)) & 0xff; g[2 * plane + k] = (c2 >> (8 * k)) & 0xff; }
     }
 }
 
@@ -413,8 +584,13 @@ struct View {
     cudaEvent_t mesh_ready = nullptr;
     float *mesh_scratch = nullptr;                                  // sum_x | sum_y | cnt (half res) + device copy of the vertex mesh
     float *weight[MAXL] = {};
-    uint8_t *P = nullptr;
+    uint8_t *P = nullptr;               // pixel (0, 0) of frame 0 inside P_alloc
+    uint8_t *P_alloc = nullptr;         // P with a zero frame (1 row above / below, 4 px left, >= 1 px right): taps of remap #2 just outside read 0
     size_t p_pitch = 0, p_frame_stride = 0;
+    unsigned p_origin = 0;              // P - P_alloc
+    // tap tables (see TapTable): remap #1, valid for caller row pitch t1_src_pitch; remap #2, one per mesh buffer
+    int *t1_off = nullptr; float *t1_w = nullptr; size_t t1_plane = 0; int t1_pitch = 0; size_t t1_src_pitch = 0;
+    int *t2_off[2] = {nullptr, nullptr}; float *t2_w[2] = {nullptr, nullptr}; size_t t2_plane = 0; int t2_pitch = 0;
     uint8_t *G0 = nullptr;
     size_t g0_frame_stride = 0;
     int16_t *G[MAXL] = {};              // generic path (num_bands < 3) only: s16 Gaussian levels >= 1
@@ -502,7 +678,9 @@ static void free_view(View &V)
     for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) cudaFree(V.mesh[b][c]);
     cudaFree(V.mesh_scratch);
     for (int k = 0; k < MAXL; ++k) { cudaFree(V.weight[k]); cudaFree(V.G[k]); }
-    cudaFree(V.P); cudaFree(V.G0); cudaFree(V.G1); cudaFree(V.G2); cudaFree(V.M0);
+    cudaFree(V.P_alloc); cudaFree(V.G0); cudaFree(V.G1); cudaFree(V.G2); cudaFree(V.M0);
+    cudaFree(V.t1_off); cudaFree(V.t1_w);
+    for (int b = 0; b < 2; ++b) { cudaFree(V.t2_off[b]); cudaFree(V.t2_w[b]); }
     for (int k = 3; k < MAXL; ++k) cudaFree(V.Gu[k]);
     if (V.mesh_ready) cudaEventDestroy(V.mesh_ready);
     V = View();
@@ -910,6 +1088,34 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
     return check_launch("k_coarse / k_blend");
 }
 
+// which form of the remap kernels runs (all bit-identical): VSB_REMAP_VARIANT = 0..3 picks the instruction mix of the
+// table-driven kernels (see k_remap_stage1_tab), -1 the coordinate-driven kernels that also serve unaligned caller frames
+static int remap_variant()
+{
+    static int v = -2;
+    if (v < -1) { const char *e = std::getenv("VSB_REMAP_VARIANT"); v = e ? std::max(-1, std::min(3, std::atoi(e))) : 0; }
+    return v;
+}
+
+// (re)builds the remap #1 tap table of view i for the caller's row pitch; stream-ordered before the kernels that read it
+static int build_taps1(vsb_stitcher *s, int i, size_t src_pitch, cudaStream_t st)
+{
+    View &V = s->v[i];
+    if (V.t1_src_pitch == src_pitch) return VSB_OK;
+    if (V.t1_src_pitch != 0) CK(cudaDeviceSynchronize());  // an earlier submission on another stream may still read the old table
+    if (!V.t1_off) {
+        V.t1_pitch = (int)align_up((size_t)V.roi_w, 4);
+        V.t1_plane = (size_t)V.t1_pitch * V.roi_h;
+        CK(cudaMalloc(&V.t1_off, V.t1_plane * sizeof(int)));
+        CK(cudaMalloc(&V.t1_w, V.t1_plane * 4 * sizeof(float)));
+    }
+    const dim3 b(32, 8);
+    k_build_taps1<<<grid2d(V.t1_pitch, V.roi_h, b), b, 0, st>>>(V.xmap, V.ymap, V.map_pitch, V.roi_w, V.roi_h, V.src_w, V.src_h,
+                                                                (unsigned)src_pitch, V.t1_off, V.t1_w, V.t1_plane, V.t1_pitch);
+    V.t1_src_pitch = src_pitch;
+    return check_launch("k_build_taps1");
+}
+
 // remap stages + pyramid for views [v0, v1) of n_frames frames
 static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch, cudaStream_t st,
                         const uint8_t *warped = nullptr)
@@ -918,46 +1124,115 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
     int ws[MAXV], hs[MAXV];
     int r = sync_tile_lists(s);
     if (r != VSB_OK) return r;
+    int frame_shift = 0;
+    while ((1 << frame_shift) < n_frames) ++frame_shift;
     if (!warped) {
-        Stage1Params p;
-        std::memset(&p, 0, sizeof(p));
+        // table-driven remap #1 whenever the caller's frames allow aligned 32-bit window loads
+        bool tab = remap_variant() >= 0 && src_pitch % 4 == 0;
+        for (int i = v0; i < v1 && tab; ++i) tab = s->v[i].src_h >= 2 && (unsigned long long)src_pitch * s->v[i].src_h < 0x7fffffffull;
+        for (int j = 0; j < n * n_frames && tab; ++j) tab = ((size_t)d_srcs[j] & 3) == 0;
         int first = 0, count = 0;
         double bytes = 0;  // algorithmic: every source pixel once + P once
         for (int i = 0; i < s->cfg.num_views; ++i) {
             const View &V = s->v[i];
-            Stage1View &S = p.v[i];
-            S.xmap = V.xmap; S.ymap = V.ymap; S.P = V.P; S.gain = V.gain;
-            S.map_pitch = V.map_pitch; S.p_pitch = V.p_pitch; S.p_frame_stride = V.p_frame_stride;
-            S.w = V.roi_w; S.h = V.roi_h; S.src_w = V.src_w; S.src_h = V.src_h;
             if (i < v0) first += (int)V.s1_tiles.size();
             else if (i < v1) { count += (int)V.s1_tiles.size(); bytes += 3.0 * V.src_w * V.src_h + 3.0 * V.roi_w * V.roi_h; }
         }
-        p.tiles = s->d_s1_tiles + first;
-        p.v0 = v0; p.n_views = n; p.src_pitch = src_pitch;
-        for (int f = 0; f < n_frames; ++f) for (int j = 0; j < n; ++j) p.src[f * n + j] = d_srcs[f * n + j];
-        if (count > 0) k_remap_stage1<<<dim3(count, n_frames), dim3(RM_BX, RM_BY), 0, st>>>(p);
+        if (tab) {
+            for (int i = v0; i < v1; ++i) {
+                r = build_taps1(s, i, src_pitch, st);
+                if (r != VSB_OK) return r;
+            }
+            Stage1TabParams p;
+            std::memset(&p, 0, sizeof(p));
+            for (int i = 0; i < s->cfg.num_views; ++i) {
+                const View &V = s->v[i];
+                Stage1TabView &S = p.v[i];
+                S.tab.off = V.t1_off; S.tab.w = V.t1_w; S.tab.plane = V.t1_plane; S.tab.tab_pitch = V.t1_pitch;
+                S.xmap = V.xmap; S.ymap = V.ymap; S.P = V.P; S.gain = V.gain;
+                S.map_pitch = V.map_pitch; S.p_pitch = V.p_pitch; S.p_frame_stride = V.p_frame_stride;
+                S.w = V.roi_w; S.h = V.roi_h; S.src_w = V.src_w; S.src_h = V.src_h;
+            }
+            p.tiles = s->d_s1_tiles + first;
+            p.v0 = v0; p.n_views = n; p.src_pitch = (unsigned)src_pitch; p.n_frames = n_frames; p.frame_shift = frame_shift;
+            for (int f = 0; f < n_frames; ++f) for (int j = 0; j < n; ++j) p.src[f * n + j] = d_srcs[f * n + j];
+            if (count > 0) {
+                const unsigned g = (unsigned)count << frame_shift;
+                const dim3 b(RM_BX, RM_BY);
+                switch (remap_variant()) {
+                case 0: k_remap_stage1_tab<0><<<g, b, 0, st>>>(p); break;
+                case 2: k_remap_stage1_tab<2><<<g, b, 0, st>>>(p); break;
+                case 3: k_remap_stage1_tab<3><<<g, b, 0, st>>>(p); break;
+                default: k_remap_stage1_tab<1><<<g, b, 0, st>>>(p); break;
+                }
+            }
+        } else {
+            Stage1Params p;
+            std::memset(&p, 0, sizeof(p));
+            for (int i = 0; i < s->cfg.num_views; ++i) {
+                const View &V = s->v[i];
+                Stage1View &S = p.v[i];
+                S.xmap = V.xmap; S.ymap = V.ymap; S.P = V.P; S.gain = V.gain;
+                S.map_pitch = V.map_pitch; S.p_pitch = V.p_pitch; S.p_frame_stride = V.p_frame_stride;
+                S.w = V.roi_w; S.h = V.roi_h; S.src_w = V.src_w; S.src_h = V.src_h;
+            }
+            p.tiles = s->d_s1_tiles + first;
+            p.v0 = v0; p.n_views = n; p.src_pitch = src_pitch;
+            for (int f = 0; f < n_frames; ++f) for (int j = 0; j < n; ++j) p.src[f * n + j] = d_srcs[f * n + j];
+            if (count > 0) k_remap_stage1<<<dim3(count, n_frames), dim3(RM_BX, RM_BY), 0, st>>>(p);
+        }
         ++s->launches;
         prof_stage(s, st, "remap_stage1", bytes * n_frames);
     }
     {
-        Stage2Params p;
-        std::memset(&p, 0, sizeof(p));
         int first = 0, count = 0;
         double bytes = 0;  // P once + bordered planar G0 once
+        bool tab = remap_variant() >= 0 && s->cfg.enable_local && !warped;
         for (int i = 0; i < s->cfg.num_views; ++i) {
             const View &V = s->v[i];
-            Stage2View &S = p.v[i];
-            S.P = V.P; S.G0 = V.G0;
-            if (s->cfg.enable_local && V.mesh_cur >= 0 && !warped) { S.xmesh = V.mesh[V.mesh_cur][0]; S.ymesh = V.mesh[V.mesh_cur][1]; }
-            S.p_pitch = V.p_pitch; S.p_frame_stride = V.p_frame_stride;
-            S.map_pitch = V.map_pitch; S.g0_frame_stride = V.g0_frame_stride;
-            if (warped && i == v0) { S.P = warped; S.p_pitch = src_pitch; S.p_frame_stride = 0; }  // feed_online: the caller's warped view
-            S.w = V.roi_w; S.h = V.roi_h; S.bw = V.bw; S.bh = V.bh; S.top = V.top; S.left = V.left;
             if (i < v0) first += (int)V.s2_tiles.size();
-            else if (i < v1) { count += (int)V.s2_tiles.size(); bytes += 3.0 * V.roi_w * V.roi_h + 3.0 * V.bw * V.bh; }
+            else if (i < v1) {
+                count += (int)V.s2_tiles.size(); bytes += 3.0 * V.roi_w * V.roi_h + 3.0 * V.bw * V.bh;
+                tab = tab && V.mesh_cur >= 0 && V.t2_off[V.mesh_cur] != nullptr;
+            }
         }
-        p.tiles = s->d_s2_tiles + first;
-        if (count > 0) k_remap_stage2<<<dim3(count, n_frames), dim3(RM_BX, RM_BY), 0, st>>>(p);
+        if (tab) {
+            Stage2TabParams p;
+            std::memset(&p, 0, sizeof(p));
+            for (int i = v0; i < v1; ++i) {
+                const View &V = s->v[i];
+                Stage2TabView &S = p.v[i];
+                S.tab.off = V.t2_off[V.mesh_cur]; S.tab.w = V.t2_w[V.mesh_cur]; S.tab.plane = V.t2_plane; S.tab.tab_pitch = V.t2_pitch;
+                S.Pbase = V.P_alloc; S.G0 = V.G0; S.p_frame_stride = V.p_frame_stride; S.g0_frame_stride = V.g0_frame_stride;
+                S.p_pitch = (unsigned)V.p_pitch; S.bw = V.bw; S.bh = V.bh;
+            }
+            p.tiles = s->d_s2_tiles + first; p.n_frames = n_frames; p.frame_shift = frame_shift;
+            if (count > 0) {
+                const unsigned g = (unsigned)count << frame_shift;
+                const dim3 b(RM_BX, RM_BY);
+                switch (remap_variant()) {
+                case 0: k_remap_stage2_tab<0><<<g, b, 0, st>>>(p); break;
+                case 2: k_remap_stage2_tab<2><<<g, b, 0, st>>>(p); break;
+                case 3: k_remap_stage2_tab<3><<<g, b, 0, st>>>(p); break;
+                default: k_remap_stage2_tab<1><<<g, b, 0, st>>>(p); break;
+                }
+            }
+        } else {
+            Stage2Params p;
+            std::memset(&p, 0, sizeof(p));
+            for (int i = 0; i < s->cfg.num_views; ++i) {
+                const View &V = s->v[i];
+                Stage2View &S = p.v[i];
+                S.P = V.P; S.G0 = V.G0;
+                if (s->cfg.enable_local && V.mesh_cur >= 0 && !warped) { S.xmesh = V.mesh[V.mesh_cur][0]; S.ymesh = V.mesh[V.mesh_cur][1]; }
+                S.p_pitch = V.p_pitch; S.p_frame_stride = V.p_frame_stride;
+                S.map_pitch = V.map_pitch; S.g0_frame_stride = V.g0_frame_stride;
+                if (warped && i == v0) { S.P = warped; S.p_pitch = src_pitch; S.p_frame_stride = 0; }  // feed_online: the caller's warped view
+                S.w = V.roi_w; S.h = V.roi_h; S.bw = V.bw; S.bh = V.bh; S.top = V.top; S.left = V.left;
+            }
+            p.tiles = s->d_s2_tiles + first;
+            if (count > 0) k_remap_stage2<<<dim3(count, n_frames), dim3(RM_BX, RM_BY), 0, st>>>(p);
+        }
         ++s->launches;
         prof_stage(s, st, "remap_stage2", bytes * n_frames);
     }
@@ -1174,9 +1449,11 @@ int vsb_init_view(vsb_stitcher *s, int i, const uint8_t *mask, int mw, int mh, s
 
     // per-frame buffers of this view
     const int F = s->cfg.max_batch;
-    V.p_pitch = align_up((size_t)mw * 3, 16);
-    V.p_frame_stride = V.p_pitch * mh;
-    CK(cudaMalloc(&V.P, V.p_frame_stride * F));
+    V.p_pitch = align_up((size_t)(mw + 5) * 3 + 8, 16);
+    V.p_frame_stride = align_up(V.p_pitch * (mh + 2) + 16, 16);
+    V.p_origin = (unsigned)(V.p_pitch + 12);
+    CK(cudaMalloc(&V.P_alloc, V.p_frame_stride * F));
+    V.P = V.P_alloc + V.p_origin;
     V.g0_frame_stride = (size_t)3 * width * height;
     CK(cudaMalloc(&V.G0, V.g0_frame_stride * F));
     if (nb >= 3) {  // fast path keeps only G0 and G2 (u8)
@@ -1199,7 +1476,7 @@ int vsb_init_view(vsb_stitcher *s, int i, const uint8_t *mask, int mw, int mh, s
     }
     V.map_pitch = align_up((size_t)mw * 4, 16);
     CK(cudaEventCreateWithFlags(&V.mesh_ready, cudaEventDisableTiming));
-    CK(cudaMemsetAsync(V.P, 0, V.p_frame_stride * F, s->setup_stream));  // tiles outside the camera frame are never written
+    CK(cudaMemsetAsync(V.P_alloc, 0, V.p_frame_stride * F, s->setup_stream));  // tiles outside the camera frame and the zero frame are never written
     CK(cudaStreamSynchronize(s->setup_stream));
     all_tiles(i, V.bw, V.bh, V.s2_tiles);   // narrowed by build_fast_plan once every view is known
     V.s1_tiles.clear();                      // filled by vsb_set_maps
@@ -1232,8 +1509,9 @@ int vsb_set_maps(vsb_stitcher *s, int i, const float *xmap, const float *ymap, i
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     CK(cudaMemcpy2DAsync(V.xmap, V.map_pitch, xmap, pitch, (size_t)w * 4, h, kind, s->setup_stream));
     CK(cudaMemcpy2DAsync(V.ymap, V.map_pitch, ymap, pitch, (size_t)w * 4, h, kind, s->setup_stream));
-    CK(cudaMemsetAsync(V.P, 0, V.p_frame_stride * s->cfg.max_batch, s->setup_stream));
+    CK(cudaMemsetAsync(V.P_alloc, 0, V.p_frame_stride * s->cfg.max_batch, s->setup_stream));
     CK(cudaStreamSynchronize(s->setup_stream));
+    V.t1_src_pitch = 0;  // the remap #1 tap table follows the maps: rebuilt by the next compose
     // static tile table of remap #1: tiles in which at least one pixel has a tap inside the camera frame
     std::vector<float> hx((size_t)w * h), hy((size_t)w * h);
     CK(cudaMemcpy2D(hx.data(), (size_t)w * 4, V.xmap, V.map_pitch, (size_t)w * 4, h, cudaMemcpyDeviceToHost));
@@ -1297,6 +1575,16 @@ int vsb_set_mesh(vsb_stitcher *s, int i, const float *mesh_x, const float *mesh_
     k_mesh_splat<<<grid2d(W, H, b), b, 0, st>>>(d_mx, d_my, rows, cols, W, H, sum_x, sum_y, cnt);
     k_mesh_divide<<<(unsigned)((half + 255) / 256), 256, 0, st>>>(sum_x, sum_y, cnt, (int)half);
     k_mesh_upsample<<<grid2d(W, H, b), b, 0, st>>>(sum_x, sum_y, hw, hh, W, H, V.mesh[target][0], V.mesh[target][1], V.map_pitch);
+    {   // tap table of remap #2 for this mesh buffer (REFLECT border resolved, offsets into the zero-framed P)
+        if (!V.t2_off[target]) {
+            V.t2_pitch = (int)align_up((size_t)V.bw, 4);
+            V.t2_plane = (size_t)V.t2_pitch * V.bh;
+            CK(cudaMalloc(&V.t2_off[target], V.t2_plane * sizeof(int)));
+            CK(cudaMalloc(&V.t2_w[target], V.t2_plane * 4 * sizeof(float)));
+        }
+        k_build_taps2<<<grid2d(V.t2_pitch, V.bh, b), b, 0, st>>>(V.mesh[target][0], V.mesh[target][1], V.map_pitch, W, H, V.bw, V.bh, V.top, V.left,
+                                                                 (unsigned)V.p_pitch, V.p_origin, V.t2_off[target], V.t2_w[target], V.t2_plane, V.t2_pitch);
+    }
     int r = check_launch("set_mesh kernels");
     if (r != VSB_OK) return r;
     CK(cudaEventRecord(V.mesh_ready, st));
