@@ -171,6 +171,7 @@ __device__ __forceinline__ unsigned load_word_r101(const uint8_t *__restrict__ r
 constexpr int D2_TW = 32, D2_TH = 16, D2_THREADS = 256;
 constexpr int D2_R1W = 2 * D2_TW + 3, D2_R1H = 2 * D2_TH + 3;  // G1 region 67 x 35: origin (2*X0 - 2, 2*Y0 - 2)
 constexpr int D2_R0VEC = 10, D2_R0H = 4 * D2_TH + 9;            // G0 region 160 B x 73: origin (4*X0 - 16, 4*Y0 - 6)
+constexpr int D2_R1PAIRS = (D2_R1W + 1) / 2;                      // G1 region columns are computed in pairs (2m, 2m + 1)
 constexpr int D2_S1OFF = 2, D2_S1PITCH = 72;                    // G1 column c1 lives at byte c1 + 2: the owned block is word aligned
 
 struct Down2View {
@@ -209,22 +210,26 @@ __global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Do
         *(uint4 *)&s0[r][4 * m] = v;
     }
     __syncthreads();
-    // G1 over the region, at true in-plane positions only (nested reflection does not commute at the high edge)
-    for (int i = t; i < D2_R1H * D2_R1W; i += D2_THREADS) {
-        const int r1 = i / D2_R1W, c1 = i - r1 * D2_R1W;
-        const int y1 = 2 * Y0 - 2 + r1, x1 = 2 * X0 - 2 + c1;
-        if ((unsigned)y1 >= (unsigned)h1 || (unsigned)x1 >= (unsigned)w1) continue;
-        const int b = 2 * c1 + 10;  // first tap, byte offset inside the region row
-        const unsigned *row = &s0[2 * r1][b >> 2];
-        unsigned acc = 0;
-        if (c1 & 1) {
+    // G1 over the region, at true in-plane positions only (nested reflection does not commute at the high edge).
+    // One thread computes the column pair (2m, 2m + 1): the two 5-tap windows start at byte 2 of word m + 2 and byte 0 of
+    // word m + 3 of the region row, so no lane diverges on the alignment and the three words per row are loaded once.
+    for (int i = t; i < D2_R1H * D2_R1PAIRS; i += D2_THREADS) {
+        const int r1 = i / D2_R1PAIRS, m = i - r1 * D2_R1PAIRS;
+        const int y1 = 2 * Y0 - 2 + r1, x1 = 2 * X0 - 2 + 2 * m;
+        if ((unsigned)y1 >= (unsigned)h1) continue;
+        const unsigned *row = &s0[2 * r1][m + 2];
+        unsigned acc_e = 0, acc_o = 0;
 #pragma unroll
-            for (int j = 0; j < 5; ++j) acc = taps5<true>(row[j * (D2_R0VEC * 4)], row[j * (D2_R0VEC * 4) + 1], j == 2 ? 6u : ((j & 1) ? 4u : 1u), acc);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 5; ++j) acc = taps5<false>(row[j * (D2_R0VEC * 4)], row[j * (D2_R0VEC * 4) + 1], j == 2 ? 6u : ((j & 1) ? 4u : 1u), acc);
+        for (int j = 0; j < 5; ++j) {
+            const unsigned kj = j == 2 ? 6u : ((j & 1) ? 4u : 1u);
+            const unsigned a = row[j * (D2_R0VEC * 4)], b = row[j * (D2_R0VEC * 4) + 1], c2 = row[j * (D2_R0VEC * 4) + 2];
+            acc_e = taps5<false>(a, b, kj, acc_e);
+            acc_o = taps5<true>(b, c2, kj, acc_o);
         }
-        s1[r1][c1 + D2_S1OFF] = (uint8_t)rhe_shift<8>((int)acc);
+        const unsigned ge = (unsigned)rhe_shift<8>((int)acc_e), go = (unsigned)rhe_shift<8>((int)acc_o);
+        // column c1 lives at byte c1 + D2_S1OFF: the pair is one aligned 16-bit store; out-of-plane columns are never read
+        if ((unsigned)x1 < (unsigned)w1) *(uint16_t *)&s1[r1][2 * m + D2_S1OFF] = (uint16_t)(ge | (go << 8));
+        else if ((unsigned)(x1 + 1) < (unsigned)w1) s1[r1][2 * m + 1 + D2_S1OFF] = (uint8_t)go;
     }
     __syncthreads();
     {   // the tile's own 64 x 32 block of G1 (region rows 2..33, columns 2..65), one word per thread and pass
@@ -237,28 +242,38 @@ __global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Do
         }
     }
     uint8_t *g2 = V.g2 + (size_t)f * V.g2_fs + (size_t)c * w2 * h2;
-    for (int i = t; i < D2_TW * D2_TH; i += D2_THREADS) {
-        const int x2 = X0 + (i & (D2_TW - 1)), y2 = Y0 + i / D2_TW;
+    // G2: one thread per column pair (2n, 2n + 1) of the 32 x 16 tile; taps of column X0 + q start at region byte 2q + D2_S1OFF
+    for (int i = t; i < (D2_TW / 2) * D2_TH; i += D2_THREADS) {
+        const int n = i & (D2_TW / 2 - 1), ry2 = i / (D2_TW / 2);
+        const int x2 = X0 + 2 * n, y2 = Y0 + ry2;
         if (x2 >= w2 || y2 >= h2) continue;
-        int acc = 0;
-        const int ry = 2 * (y2 - Y0), rx = 2 * (x2 - X0) + D2_S1OFF;  // region position of tap (0, 0)
-        if (2 * y2 - 2 >= 0 && 2 * y2 + 2 < h1 && 2 * x2 - 2 >= 0 && 2 * x2 + 2 < w1) {
+        if (2 * y2 - 2 >= 0 && 2 * y2 + 2 < h1 && 2 * x2 - 2 >= 0 && 2 * x2 + 4 < w1) {  // both windows inside the plane
+            const unsigned *row = (const unsigned *)&s1[2 * ry2][4 * n];  // byte 4n + 2 = first tap of the even column
+            unsigned acc_e = 0, acc_o = 0;
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
-                const uint8_t *r = &s1[ry + j][rx];
-                acc += (j == 2 ? 6 : ((j & 1) ? 4 : 1)) * (r[0] + 4 * r[1] + 6 * r[2] + 4 * r[3] + r[4]);
+                const unsigned kj = j == 2 ? 6u : ((j & 1) ? 4u : 1u);
+                const unsigned a = row[j * (D2_S1PITCH / 4)], b = row[j * (D2_S1PITCH / 4) + 1], c2 = row[j * (D2_S1PITCH / 4) + 2];
+                acc_e = taps5<false>(a, b, kj, acc_e);
+                acc_o = taps5<true>(b, c2, kj, acc_o);
             }
+            *(uint16_t *)(g2 + (size_t)y2 * w2 + x2) = (uint16_t)((unsigned)rhe_shift<8>((int)acc_e) | ((unsigned)rhe_shift<8>((int)acc_o) << 8));
         } else {
-            int cc[5];
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q) {
+                const int xx = x2 + q;
+                if (xx >= w2) break;
+                int cc[5], acc = 0;
 #pragma unroll
-            for (int j = 0; j < 5; ++j) cc[j] = r101_idx(2 * x2 - 2 + j, w1) - (2 * X0 - 2) + D2_S1OFF;
+                for (int j = 0; j < 5; ++j) cc[j] = r101_idx(2 * xx - 2 + j, w1) - (2 * X0 - 2) + D2_S1OFF;
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const uint8_t *r = s1[r101_idx(2 * y2 - 2 + j, h1) - (2 * Y0 - 2)];
-                acc += (j == 2 ? 6 : ((j & 1) ? 4 : 1)) * (r[cc[0]] + 4 * r[cc[1]] + 6 * r[cc[2]] + 4 * r[cc[3]] + r[cc[4]]);
+                for (int j = 0; j < 5; ++j) {
+                    const uint8_t *r = s1[r101_idx(2 * y2 - 2 + j, h1) - (2 * Y0 - 2)];
+                    acc += (j == 2 ? 6 : ((j & 1) ? 4 : 1)) * (r[cc[0]] + 4 * r[cc[1]] + 6 * r[cc[2]] + 4 * r[cc[3]] + r[cc[4]]);
+                }
+                g2[(size_t)y2 * w2 + xx] = (uint8_t)rhe_shift<8>(acc);
             }
         }
-        g2[(size_t)y2 * w2 + x2] = (uint8_t)rhe_shift<8>(acc);
     }
 }
 
@@ -488,10 +503,11 @@ struct BlendParams {
     const int16_t *c2;
     size_t c2_fs;
     const uint32_t *tile_views;  // bit v: view v has level-0 or level-1 weight in this tile
+    const float *dw0, *dw1;      // static weight sums of canvas levels 0 and 1 (accumulated in view order at calibration)
     BlendView v[MAXV];
 };
 
-__global__ void __launch_bounds__(BL_THREADS, 3) k_blend(const __grid_constant__ BlendParams P, const __grid_constant__ OutPtrs outs, size_t out_pitch)
+__global__ void __launch_bounds__(BL_THREADS, 3) k_blend_v1(const __grid_constant__ BlendParams P, const __grid_constant__ OutPtrs outs, size_t out_pitch)
 {
     __shared__ uint8_t sG1[3][BL_R1H][BL_R1W + 2];
     __shared__ uint8_t sG2[3][BL_R2H][BL_R2W];
@@ -663,6 +679,324 @@ __global__ void __launch_bounds__(BL_THREADS, 3) k_blend(const __grid_constant__
         if (ck >= BL_TW * 6 / 16 || b0 >= row_bytes) continue;
         char *o = obase + (size_t)(ty0 + r) * out_pitch + b0;
         const int16_t *sp = &sOut[r][ck * 8];
+        if (vec_ok && b0 + 16 <= row_bytes) {
+            *(uint4 *)o = *(const uint4 *)sp;
+        } else {
+            const int n = min(8, (row_bytes - b0) >> 1);
+            for (int e = 0; e < n; ++e) ((int16_t *)o)[e] = sp[e];
+        }
+    }
+}
+
+// ======================================================================================================== k_blend (v2)
+// Same result as k_blend_v1, restructured around what the profile showed (56 % issue utilisation, 80 registers, the two
+// pyrUp evaluations per output sample dominating):
+//   * the level-1 / level-2 regions are staged ONCE per view as fp32 (clamped like pyrUp's index rules, so the readers
+//     need no edge cases) and every pyrUp is evaluated in fp32: all partial sums are integers below 2^24, the final
+//     scale is a power of two and one fused multiply-add onto 1.5 * 2^23 rounds half-to-even at integer granularity --
+//     the same integer as rhe_shift<6>, without the four-instruction integer rounding per sample;
+//   * two passes over the tile's views -- level 1 first (accumulators: 8 registers), then level 0 (24 registers) -- instead
+//     of carrying both sets plus the weight sums through one loop; the weight sums come from the static tables;
+//   * a warp covers rows of ONE parity, so the vertical pyrUp phase never diverges; rows are read as 16-byte vectors;
+//   * the level-1 work is 3 x 153 (channel, quad) items spread over all 256 threads.
+constexpr int B2_G1P = 44, B2_G1OFF = 4;    // fp32 level-1 region: row pitch (floats) and index of region column 0
+constexpr int B2_G2P = 24, B2_G2OFF = 2;    // fp32 level-2 region
+constexpr int B2_G1F = 3 * BL_R1H * B2_G1P, B2_G2F = 3 * BL_R2H * B2_G2P;  // floats per staged region
+constexpr int B2_ITEMS = 3 * BL_NQ;         // (channel, level-1 quad) work items
+constexpr float B2_MAGIC = 12582912.f;      // 1.5 * 2^23
+constexpr int B2_MAGIC_BITS = 0x4B400000;
+
+// pyrUp of the quad {x0, x0+1} x {y0, y0+1}, x0 and y0 odd, from an fp32 region; p points at (row y0 >> 1, column x0 >> 1).
+// r[q] = value + 1.5 * 2^23 (the integer sits in the low mantissa bits); same integers as pyr_up_quad_odd.
+__device__ __forceinline__ void up_quad_odd_f(const float *p, int pitch, float r[4])
+{
+    float h[3], s[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float s0 = p[i * pitch], s1 = p[i * pitch + 1], s2 = p[i * pitch + 2];
+        h[i] = __fadd_rn(__fmaf_rn(s1, 6.f, s0), s2);
+        s[i] = __fadd_rn(s0, s1);
+    }
+    r[0] = __fmaf_rn(__fadd_rn(s[0], s[1]), 0.25f, B2_MAGIC);
+    r[1] = __fmaf_rn(__fadd_rn(h[0], h[1]), 0.0625f, B2_MAGIC);
+    r[2] = __fmaf_rn(__fadd_rn(__fmaf_rn(s[1], 6.f, s[0]), s[2]), 0.0625f, B2_MAGIC);
+    r[3] = __fmaf_rn(__fadd_rn(__fmaf_rn(h[1], 6.f, h[0]), h[2]), 0.015625f, B2_MAGIC);
+}
+
+// pyrUp of 8 consecutive samples (first one at an even column) of one row from an fp32 region; p points at the region
+// sample (row (y >> 1) - 1, column (x0 >> 1) - 1), 16-byte aligned.  ODD = parity of the destination row.
+template <bool ODD>
+__device__ __forceinline__ void up_row8_f(const float *p, float r[8])
+{
+    float col[6];
+    const float4 m4 = *(const float4 *)(p + B2_G1P), b4 = *(const float4 *)(p + 2 * B2_G1P);
+    const float2 m2 = *(const float2 *)(p + B2_G1P + 4), b2 = *(const float2 *)(p + 2 * B2_G1P + 4);
+    const float mid[6] = {m4.x, m4.y, m4.z, m4.w, m2.x, m2.y}, bot[6] = {b4.x, b4.y, b4.z, b4.w, b2.x, b2.y};
+    if (ODD) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) col[i] = __fadd_rn(mid[i], bot[i]);
+    } else {
+        const float4 t4 = *(const float4 *)p;
+        const float2 t2 = *(const float2 *)(p + 4);
+        const float top[6] = {t4.x, t4.y, t4.z, t4.w, t2.x, t2.y};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) col[i] = __fadd_rn(__fmaf_rn(mid[i], 6.f, top[i]), bot[i]);
+    }
+    const float ke = ODD ? 0.0625f : 0.015625f, ko = ODD ? 0.25f : 0.0625f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        r[2 * q] = __fmaf_rn(__fadd_rn(__fmaf_rn(col[q + 1], 6.f, col[q]), col[q + 2]), ke, B2_MAGIC);
+        r[2 * q + 1] = __fmaf_rn(__fadd_rn(col[q + 1], col[q + 2]), ko, B2_MAGIC);
+    }
+}
+
+// the same 8 samples through pyrUp's index rules (abs at the low edge, clamp at the high edge) for threads at the canvas border;
+// reg(0, 0) is plane sample (ox, oy) and sits at reg[B2_G1OFF]
+__device__ __noinline__ void up_row8_f_edge(const float *reg, int ox, int oy, int x0, int y, int n_x, int n_y, float r[8])
+{
+    const int ix0 = x0 >> 1, iy = y >> 1;
+    float col[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int cx = up_idx(ix0 - 1 + i, n_x) - ox + B2_G1OFF;
+        const float mid = reg[(iy - oy) * B2_G1P + cx], bot = reg[(up_idx(iy + 1, n_y) - oy) * B2_G1P + cx];
+        col[i] = (y & 1) ? __fadd_rn(mid, bot) : __fadd_rn(__fmaf_rn(mid, 6.f, reg[(up_idx(iy - 1, n_y) - oy) * B2_G1P + cx]), bot);
+    }
+    const float ke = (y & 1) ? 0.0625f : 0.015625f, ko = (y & 1) ? 0.25f : 0.0625f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        r[2 * q] = __fmaf_rn(__fadd_rn(__fmaf_rn(col[q + 1], 6.f, col[q]), col[q + 2]), ke, B2_MAGIC);
+        r[2 * q + 1] = __fmaf_rn(__fadd_rn(col[q + 1], col[q + 2]), ko, B2_MAGIC);
+    }
+}
+
+__global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__ BlendParams P, const __grid_constant__ OutPtrs outs, size_t out_pitch)
+{
+    // staging area: fp32 G1 and G2 regions of the current view; re-used for the interleaved output tile at the end
+    __shared__ __align__(16) float sStage[B2_G1F + B2_G2F];
+    __shared__ __align__(16) float sC2f[B2_G2F];
+    __shared__ __align__(16) float sD1f[B2_G1F];
+    float *sG1f = sStage, *sG2f = sStage + B2_G1F;
+    static_assert(sizeof(float) * (B2_G1F + B2_G2F) >= sizeof(int16_t) * BL_TH * BL_TW * 3, "output tile must fit the staging area");
+    const int t = threadIdx.x, f = blockIdx.z;
+    const int tx0 = blockIdx.x * BL_TW, ty0 = blockIdx.y * BL_TH;
+    const unsigned views_all = __ldg(P.tile_views + blockIdx.y * P.tiles_x + blockIdx.x);
+    if (views_all & 0x80000000u) return;  // view-sharded mode: another rank owns this canvas strip
+    // level-0 mapping: a warp holds four rows of one parity, a thread 8 consecutive samples
+    const int warp = t >> 5, lane = t & 31;
+    const int ly = (warp >> 1) * 8 + (lane >> 3) * 2 + (warp & 1), lx = (lane & 7) * 8;
+    const int px0 = tx0 + lx, py = ty0 + ly;
+    const bool row_odd = warp & 1;
+    const int reg_off = (ly >> 1) * B2_G1P + (lx >> 1) + B2_G1OFF;  // region sample (row (y>>1) - 1, column (x0>>1) - 1) of this thread
+    // level-1 mapping: up to two (channel, quad) items per thread
+    int it_c[2], it_qr[2], it_qc[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int it = t + k * BL_THREADS;
+        it_c[k] = it < B2_ITEMS ? it / BL_NQ : -1;
+        const int quad = it - (it / BL_NQ) * BL_NQ;
+        it_qr[k] = 2 * (quad / BL_QW); it_qc[k] = 2 * (quad % BL_QW);
+    }
+    int acc1[2][4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) acc1[k][0] = acc1[k][1] = acc1[k][2] = acc1[k][3] = 0;
+
+    auto stage_view = [&](const BlendView &V, bool with_g2) {
+        const int w1 = V.bw >> 1, h1 = V.bh >> 1, w2 = V.bw >> 2, h2 = V.bh >> 2;
+        const int v1x0 = (tx0 >> 1) - 1 - (V.x_tl >> 1), v1y0 = (ty0 >> 1) - 1 - (V.y_tl >> 1);
+        const uint8_t *g1 = V.g1 + (size_t)f * V.g1_fs;
+        for (int i = t; i < 3 * BL_R1H * 10; i += BL_THREADS) {  // 10 aligned words per region row: plane columns v1x0 - 3 .. v1x0 + 36
+            const int c = i / (BL_R1H * 10), rem = i - c * (BL_R1H * 10);
+            const int r = rem / 10, k = rem - r * 10;
+            const uint8_t *row = g1 + ((size_t)c * h1 + up_idx(v1y0 + r, h1)) * w1;
+            const int col0 = v1x0 - 3 + 4 * k;
+            unsigned word;
+            if (col0 >= 0 && col0 + 3 < w1 && (((size_t)(row + col0)) & 3) == 0) {
+                word = __ldg((const unsigned *)(row + col0));
+            } else {
+                word = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) word |= ldg_u8(row + up_idx(col0 + b, w1)) << (8 * b);
+            }
+            float *d = sG1f + (c * BL_R1H + r) * B2_G1P + 1 + 4 * k;
+            d[0] = (float)(word & 0xffu); d[1] = (float)((word >> 8) & 0xffu); d[2] = (float)((word >> 16) & 0xffu); d[3] = (float)(word >> 24);
+        }
+        if (with_g2) {
+            const uint8_t *g2 = V.g2 + (size_t)f * V.g2_fs;
+            const int ux0 = (tx0 >> 2) - 2 - (V.x_tl >> 2), uy0 = (ty0 >> 2) - 2 - (V.y_tl >> 2);
+            for (int i = t; i < 3 * BL_R2H * 6; i += BL_THREADS) {  // 6 aligned words per row: plane columns ux0 - 2 .. ux0 + 21
+                const int c = i / (BL_R2H * 6), rem = i - c * (BL_R2H * 6);
+                const int r = rem / 6, k = rem - r * 6;
+                const uint8_t *row = g2 + ((size_t)c * h2 + up_idx(uy0 + r, h2)) * w2;
+                const int col0 = ux0 - 2 + 4 * k;
+                unsigned word;
+                if (col0 >= 0 && col0 + 3 < w2 && (((size_t)(row + col0)) & 3) == 0) {  // rows are word aligned from num_bands >= 4 on
+                    word = __ldg((const unsigned *)(row + col0));
+                } else {
+                    word = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) word |= ldg_u8(row + up_idx(col0 + b, w2)) << (8 * b);
+                }
+                *(float4 *)(sG2f + (c * BL_R2H + r) * B2_G2P + 4 * k) =
+                    make_float4((float)(word & 0xffu), (float)((word >> 8) & 0xffu), (float)((word >> 16) & 0xffu), (float)(word >> 24));
+            }
+        }
+    };
+
+    // ---- pass 1: level 1.  C2 region (canvas level 2, s16) -> fp32 once per tile
+    {
+        const int16_t *c2 = P.c2 + (size_t)f * P.c2_fs;
+        const int ux0 = (tx0 >> 2) - 2, uy0 = (ty0 >> 2) - 2;
+        for (int i = t; i < 3 * BL_R2H * 6; i += BL_THREADS) {
+            const int c = i / (BL_R2H * 6), rem = i - c * (BL_R2H * 6);
+            const int r = rem / 6, k = rem - r * 6;
+            const int16_t *row = c2 + ((size_t)c * P.ch2 + up_idx(uy0 + r, P.ch2)) * P.cw2;
+            const int col0 = ux0 - 2 + 4 * k;
+            float4 v;
+            if (col0 >= 0 && col0 + 3 < P.cw2 && (((size_t)(row + col0)) & 7) == 0) {
+                const uint2 w = __ldg((const uint2 *)(row + col0));
+                v = make_float4((float)(short)(w.x & 0xffffu), (float)(short)(w.x >> 16), (float)(short)(w.y & 0xffffu), (float)(short)(w.y >> 16));
+            } else {
+                v = make_float4((float)__ldg(row + up_idx(col0, P.cw2)), (float)__ldg(row + up_idx(col0 + 1, P.cw2)),
+                                (float)__ldg(row + up_idx(col0 + 2, P.cw2)), (float)__ldg(row + up_idx(col0 + 3, P.cw2)));
+            }
+            *(float4 *)(sC2f + (c * BL_R2H + r) * B2_G2P + 4 * k) = v;
+        }
+    }
+    const bool single = (views_all & (views_all - 1)) == 0;  // at most one view: its staged G1 region survives into pass 2
+    for (unsigned views = views_all; views;) {
+        const int vi = __ffs(views) - 1;
+        views &= views - 1;
+        const BlendView &V = P.v[vi];
+        __syncthreads();
+        stage_view(V, true);
+        __syncthreads();
+        const int w1 = V.bw >> 1, h1 = V.bh >> 1;
+        const int v1x0 = (tx0 >> 1) - 1 - (V.x_tl >> 1), v1y0 = (ty0 >> 1) - 1 - (V.y_tl >> 1);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (it_c[k] < 0) continue;
+            const int qr1 = it_qr[k], qc1 = it_qc[k], c = it_c[k];
+            const int x0 = v1x0 + qc1, y0 = v1y0 + qr1;  // plane coordinates, both odd
+            float wq[4];
+            bool any = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int x = x0 + (q & 1), y = y0 + (q >> 1);
+                wq[q] = ((unsigned)x < (unsigned)w1 && (unsigned)y < (unsigned)h1) ? __ldg(V.w1 + (size_t)y * w1 + x) : 0.f;
+                any |= wq[q] != 0.f;
+            }
+            if (!any) continue;
+            float up[4];
+            up_quad_odd_f(sG2f + (c * BL_R2H + 1 + (qr1 >> 1)) * B2_G2P + B2_G2OFF + 1 + (qc1 >> 1), B2_G2P, up);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float g = sG1f[(c * BL_R1H + qr1 + (q >> 1)) * B2_G1P + B2_G1OFF + qc1 + (q & 1)];
+                const float lap = __fsub_rn(__fadd_rn(g, B2_MAGIC), up[q]);  // G1 - pyrUp(G2), exact
+                acc1[k][q] += rz_s16(__fmul_rn(lap, wq[q]));
+            }
+        }
+    }
+    if (views_all == 0) __syncthreads();  // sC2f complete (the loop above did not run)
+    // D1 = normalised level 1 + pyrUp(C2), saturating, as fp32 into sD1f (in-canvas samples only)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (it_c[k] < 0) continue;
+        const int qr1 = it_qr[k], qc1 = it_qc[k], c = it_c[k];
+        const int x0 = (tx0 >> 1) - 1 + qc1, y0 = (ty0 >> 1) - 1 + qr1;  // canvas level-1 coordinates, both odd
+        float up[4];
+        up_quad_odd_f(sC2f + (c * BL_R2H + 1 + (qr1 >> 1)) * B2_G2P + B2_G2OFF + 1 + (qc1 >> 1), B2_G2P, up);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int x = x0 + (q & 1), y = y0 + (q >> 1);
+            if ((unsigned)x >= (unsigned)P.cw1 || (unsigned)y >= (unsigned)P.ch1) continue;
+            const float dw = __ldg(P.dw1 + (size_t)y * P.cw1 + x);
+            const int d = sat_s16(normalize_s16(acc1[k][q], dw) + (__float_as_int(up[q]) - B2_MAGIC_BITS));
+            sD1f[(c * BL_R1H + qr1 + (q >> 1)) * B2_G1P + B2_G1OFF + qc1 + (q & 1)] = (float)d;
+        }
+    }
+
+    // ---- pass 2: level 0
+    int acc0[3][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc0[0][i] = acc0[1][i] = acc0[2][i] = 0;
+    for (unsigned views = views_all; views;) {
+        const int vi = __ffs(views) - 1;
+        views &= views - 1;
+        const BlendView &V = P.v[vi];
+        if (!single) {
+            __syncthreads();
+            stage_view(V, false);
+            __syncthreads();
+        }
+        const int w0 = V.bw, h0 = V.bh;
+        const int qx0 = px0 - V.x_tl, qy = py - V.y_tl;
+        if ((unsigned)qx0 >= (unsigned)w0 || (unsigned)qy >= (unsigned)h0) continue;
+        const uint2 mm = __ldg((const uint2 *)(V.m0 + (size_t)qy * w0 + qx0));
+        if ((mm.x | mm.y) == 0u) continue;  // (short)(L * 0) == 0
+        float wv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wv[i] = __fmul_rn((float)(1. / 255.), (float)(((i < 4 ? mm.x : mm.y) >> (8 * (i & 3))) & 0xffu));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint2 gg = __ldg((const uint2 *)(V.g0 + (size_t)f * V.g0_fs + ((size_t)c * h0 + qy) * w0 + qx0));
+            float up[8];
+            const float *rp = sG1f + c * (BL_R1H * B2_G1P) + reg_off;
+            if (row_odd) up_row8_f<true>(rp, up); else up_row8_f<false>(rp, up);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float gb = __uint_as_float(__byte_perm(i < 4 ? gg.x : gg.y, (unsigned)B2_MAGIC_BITS, 0x7650u | (unsigned)(i & 3)));  // G0 + 1.5 * 2^23
+                acc0[c][i] += rz_s16(__fmul_rn(__fsub_rn(gb, up[i]), wv[i]));
+            }
+        }
+    }
+    __syncthreads();  // sD1f complete; every reader of the staging area is done (the output tile re-uses it)
+    int16_t *sOut = (int16_t *)sStage;
+    if (px0 < P.cw0 && py < P.ch0) {
+        const float4 da = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0)), db = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0 + 4));
+        const float dw[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+        const int ix0 = px0 >> 1, iy = py >> 1;
+        const bool interior = ix0 >= 1 && ix0 + 4 < P.cw1 && iy >= 1 && iy + 1 < P.ch1;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float up[8];
+            if (interior) {
+                const float *rp = sD1f + c * (BL_R1H * B2_G1P) + reg_off;
+                if (row_odd) up_row8_f<true>(rp, up); else up_row8_f<false>(rp, up);
+            } else {
+                up_row8_f_edge(sD1f + c * (BL_R1H * B2_G1P), (tx0 >> 1) - 1, (ty0 >> 1) - 1, px0, py, P.cw1, P.ch1, up);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int d = sat_s16(normalize_s16(acc0[c][i], dw[i]) + (__float_as_int(up[i]) - B2_MAGIC_BITS));
+                acc0[c][i] = dw[i] > 1e-5f ? d : 0;  // dst_mask = dst_band_weights_[0] > WEIGHT_EPS
+            }
+        }
+        // 8 pixels x 3 channels of CV_16SC3 = 48 contiguous bytes: element e = 3 * i + c
+        uint4 *o4 = (uint4 *)(sOut + ly * (BL_TW * 3) + lx * 3);
+#pragma unroll
+        for (int v4 = 0; v4 < 3; ++v4) {
+            unsigned w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int e0 = 8 * v4 + 2 * k, e1 = e0 + 1;
+                w[k] = __byte_perm((unsigned)acc0[e0 % 3][e0 / 3], (unsigned)acc0[e1 % 3][e1 / 3], 0x5410u);
+            }
+            o4[v4] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    __syncthreads();
+    // ---- cropped, interleaved CV_16SC3 store: 16-byte vectors where the caller's buffer allows
+    const int n_px = min(BL_TW, P.out_w - tx0), n_rows = min(BL_TH, P.out_h - ty0);
+    if (n_px <= 0 || n_rows <= 0) return;
+    char *obase = (char *)outs.out[f] + (size_t)tx0 * 6;
+    const bool vec_ok = ((((size_t)obase) | out_pitch) & 15) == 0;
+    const int row_bytes = n_px * 6;
+    for (int r = t >> 5; r < n_rows; r += BL_THREADS / 32) {  // one warp per row: 24 chunks of 16 bytes
+        const int ck = t & 31, b0 = ck * 16;
+        if (ck >= BL_TW * 6 / 16 || b0 >= row_bytes) continue;
+        char *o = obase + (size_t)(ty0 + r) * out_pitch + b0;
+        const int16_t *sp = sOut + r * (BL_TW * 3) + ck * 8;
         if (vec_ok && b0 + 16 <= row_bytes) {
             *(uint4 *)o = *(const uint4 *)sp;
         } else {

@@ -1069,6 +1069,7 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
         p.cw0 = s->cw[0]; p.ch0 = s->ch[0]; p.cw1 = s->cw[1]; p.ch1 = s->ch[1]; p.cw2 = s->cw[2]; p.ch2 = s->ch[2];
         p.out_w = s->roi_final[2]; p.out_h = s->roi_final[3];
         p.c2 = s->C2; p.c2_fs = s->c2_frame_stride; p.tile_views = s->d_blend_views;
+        p.dw0 = s->dw[0]; p.dw1 = s->dw[1];
         double bytes = 6.0 * s->roi_final[2] * s->roi_final[3] + 6.0 * s->cw[2] * s->ch[2];
         for (int i = 0; i < n; ++i) {
             const View &V = s->v[i];
@@ -1081,7 +1082,9 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
         OutPtrs o;
         std::memset(&o, 0, sizeof(o));
         for (int f = 0; f < n_frames; ++f) o.out[f] = d_outs[f];
-        k_blend<<<dim3(s->blend_tiles_x, s->blend_tiles_y, n_frames), BL_THREADS, 0, st>>>(p, o, out_pitch);
+        static const bool v1 = std::getenv("VSB_BLEND_V1") != nullptr;  // A/B switch for the previous kernel (same results)
+        if (v1) k_blend_v1<<<dim3(s->blend_tiles_x, s->blend_tiles_y, n_frames), BL_THREADS, 0, st>>>(p, o, out_pitch);
+        else k_blend<<<dim3(s->blend_tiles_x, s->blend_tiles_y, n_frames), BL_THREADS, 0, st>>>(p, o, out_pitch);
         ++s->launches;
         prof_stage(s, st, "blend", bytes * n_frames);  // G0 + G1 + G2 of every view once, C2 once, CV_16SC3 pano out once
     }
