@@ -788,6 +788,12 @@ __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__
     const int px0 = tx0 + lx, py = ty0 + ly;
     const bool row_odd = warp & 1;
     const int reg_off = (ly >> 1) * B2_G1P + (lx >> 1) + B2_G1OFF;  // region sample (row (y>>1) - 1, column (x0>>1) - 1) of this thread
+    // static weight sum of this thread's 8 samples: exactly 1 on most of the panorama (one view, full weight)
+    bool dw_all_one = false;
+    if (px0 < P.cw0 && py < P.ch0) {
+        const float4 da = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0)), db = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0 + 4));
+        dw_all_one = da.x == 1.f && da.y == 1.f && da.z == 1.f && da.w == 1.f && db.x == 1.f && db.y == 1.f && db.z == 1.f && db.w == 1.f;
+    }
     // level-1 mapping: up to two (channel, quad) items per thread
     int it_c[2], it_qr[2], it_qc[2];
 #pragma unroll
@@ -805,21 +811,33 @@ __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__
         const int w1 = V.bw >> 1, h1 = V.bh >> 1, w2 = V.bw >> 2, h2 = V.bh >> 2;
         const int v1x0 = (tx0 >> 1) - 1 - (V.x_tl >> 1), v1y0 = (ty0 >> 1) - 1 - (V.y_tl >> 1);
         const uint8_t *g1 = V.g1 + (size_t)f * V.g1_fs;
-        for (int i = t; i < 3 * BL_R1H * 10; i += BL_THREADS) {  // 10 aligned words per region row: plane columns v1x0 - 3 .. v1x0 + 36
-            const int c = i / (BL_R1H * 10), rem = i - c * (BL_R1H * 10);
-            const int r = rem / 10, k = rem - r * 10;
-            const uint8_t *row = g1 + ((size_t)c * h1 + up_idx(v1y0 + r, h1)) * w1;
-            const int col0 = v1x0 - 3 + 4 * k;
-            unsigned word;
-            if (col0 >= 0 && col0 + 3 < w1 && (((size_t)(row + col0)) & 3) == 0) {
-                word = __ldg((const unsigned *)(row + col0));
-            } else {
-                word = 0;
+        {   // 10 aligned words per region row (plane columns v1x0 - 3 .. v1x0 + 36); all loads are issued before the first conversion
+            constexpr int N = 3 * BL_R1H * 10, ROUNDS = (N + BL_THREADS - 1) / BL_THREADS;
+            unsigned word[ROUNDS];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) word |= ldg_u8(row + up_idx(col0 + b, w1)) << (8 * b);
+            for (int it = 0; it < ROUNDS; ++it) {
+                const int i = t + it * BL_THREADS;
+                word[it] = 0;
+                if (i >= N) continue;
+                const int c = i / (BL_R1H * 10), rem = i - c * (BL_R1H * 10);
+                const int r = rem / 10, k = rem - r * 10;
+                const uint8_t *row = g1 + ((size_t)c * h1 + up_idx(v1y0 + r, h1)) * w1;
+                const int col0 = v1x0 - 3 + 4 * k;
+                if (col0 >= 0 && col0 + 3 < w1 && (((size_t)(row + col0)) & 3) == 0) {
+                    word[it] = __ldg((const unsigned *)(row + col0));
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) word[it] |= ldg_u8(row + up_idx(col0 + b, w1)) << (8 * b);
+                }
             }
-            float *d = sG1f + (c * BL_R1H + r) * B2_G1P + 1 + 4 * k;
-            d[0] = (float)(word & 0xffu); d[1] = (float)((word >> 8) & 0xffu); d[2] = (float)((word >> 16) & 0xffu); d[3] = (float)(word >> 24);
+#pragma unroll
+            for (int it = 0; it < ROUNDS; ++it) {
+                const int i = t + it * BL_THREADS;
+                if (i >= N) continue;
+                const int rk = i / 10, k = i - rk * 10;  // rk = c * BL_R1H + r
+                float *d = sG1f + rk * B2_G1P + 1 + 4 * k;
+                d[0] = (float)(word[it] & 0xffu); d[1] = (float)((word[it] >> 8) & 0xffu); d[2] = (float)((word[it] >> 16) & 0xffu); d[3] = (float)(word[it] >> 24);
+            }
         }
         if (with_g2) {
             const uint8_t *g2 = V.g2 + (size_t)f * V.g2_fs;
@@ -911,8 +929,8 @@ __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__
             const int x = x0 + (q & 1), y = y0 + (q >> 1);
             if ((unsigned)x >= (unsigned)P.cw1 || (unsigned)y >= (unsigned)P.ch1) continue;
             const float dw = __ldg(P.dw1 + (size_t)y * P.cw1 + x);
-            const int d = sat_s16(normalize_s16(acc1[k][q], dw) + (__float_as_int(up[q]) - B2_MAGIC_BITS));
-            sD1f[(c * BL_R1H + qr1 + (q >> 1)) * B2_G1P + B2_G1OFF + qc1 + (q & 1)] = (float)d;
+            const int d = max(B2_MAGIC_BITS - 32768, min(B2_MAGIC_BITS + 32767, normalize_s16(acc1[k][q], dw) + __float_as_int(up[q])));  // biased, see pass 2
+            sD1f[(c * BL_R1H + qr1 + (q >> 1)) * B2_G1P + B2_G1OFF + qc1 + (q & 1)] = __fsub_rn(__int_as_float(d), B2_MAGIC);
         }
     }
 
@@ -934,18 +952,20 @@ __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__
         if ((unsigned)qx0 >= (unsigned)w0 || (unsigned)qy >= (unsigned)h0) continue;
         const uint2 mm = __ldg((const uint2 *)(V.m0 + (size_t)qy * w0 + qx0));
         if ((mm.x | mm.y) == 0u) continue;  // (short)(L * 0) == 0
+        uint2 gg[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gg[c] = __ldg((const uint2 *)(V.g0 + (size_t)f * V.g0_fs + ((size_t)c * h0 + qy) * w0 + qx0));
         float wv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) wv[i] = __fmul_rn((float)(1. / 255.), (float)(((i < 4 ? mm.x : mm.y) >> (8 * (i & 3))) & 0xffu));
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const uint2 gg = __ldg((const uint2 *)(V.g0 + (size_t)f * V.g0_fs + ((size_t)c * h0 + qy) * w0 + qx0));
             float up[8];
             const float *rp = sG1f + c * (BL_R1H * B2_G1P) + reg_off;
             if (row_odd) up_row8_f<true>(rp, up); else up_row8_f<false>(rp, up);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float gb = __uint_as_float(__byte_perm(i < 4 ? gg.x : gg.y, (unsigned)B2_MAGIC_BITS, 0x7650u | (unsigned)(i & 3)));  // G0 + 1.5 * 2^23
+                const float gb = __uint_as_float(__byte_perm(i < 4 ? gg[c].x : gg[c].y, (unsigned)B2_MAGIC_BITS, 0x7650u | (unsigned)(i & 3)));  // G0 + 1.5 * 2^23
                 acc0[c][i] += rz_s16(__fmul_rn(__fsub_rn(gb, up[i]), wv[i]));
             }
         }
@@ -953,10 +973,11 @@ __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__
     __syncthreads();  // sD1f complete; every reader of the staging area is done (the output tile re-uses it)
     int16_t *sOut = (int16_t *)sStage;
     if (px0 < P.cw0 && py < P.ch0) {
-        const float4 da = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0)), db = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0 + 4));
-        const float dw[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
         const int ix0 = px0 >> 1, iy = py >> 1;
         const bool interior = ix0 >= 1 && ix0 + 4 < P.cw1 && iy >= 1 && iy + 1 < P.ch1;
+        // Outputs keep the 1.5 * 2^23 bias of the pyrUp result (bits 0x4B400000 + value): its low 16 bits are zero, so the
+        // CV_16SC3 sample is simply the low half-word.  Saturation bounds are shifted by the same constant.
+        constexpr int LO = B2_MAGIC_BITS - 32768, HI = B2_MAGIC_BITS + 32767;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float up[8];
@@ -966,10 +987,20 @@ __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__
             } else {
                 up_row8_f_edge(sD1f + c * (BL_R1H * B2_G1P), (tx0 >> 1) - 1, (ty0 >> 1) - 1, px0, py, P.cw1, P.ch1, up);
             }
+            if (dw_all_one) {  // one view with full weight (most of the panorama): acc / 1.00001f truncates to acc - sign(acc)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int d = sat_s16(normalize_s16(acc0[c][i], dw[i]) + (__float_as_int(up[i]) - B2_MAGIC_BITS));
-                acc0[c][i] = dw[i] > 1e-5f ? d : 0;  // dst_mask = dst_band_weights_[0] > WEIGHT_EPS
+                for (int i = 0; i < 8; ++i) {
+                    const int a = acc0[c][i];
+                    acc0[c][i] = max(LO, min(HI, a - max(-1, min(1, a)) + __float_as_int(up[i])));
+                }
+            } else {
+                const float4 da = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0)), db = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0 + 4));
+                const float dw[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int d = max(LO, min(HI, normalize_s16(acc0[c][i], dw[i]) + __float_as_int(up[i])));
+                    acc0[c][i] = dw[i] > 1e-5f ? d : 0;  // dst_mask = dst_band_weights_[0] > WEIGHT_EPS
+                }
             }
         }
         // 8 pixels x 3 channels of CV_16SC3 = 48 contiguous bytes: element e = 3 * i + c
