@@ -305,85 +305,4 @@ __device__ __forceinline__ unsigned remap_tab_px(const uint8_t *__restrict__ bas
     return __byte_perm(__byte_perm(__float_as_uint(o[0]), __float_as_uint(o[1]), 0x0040u), __float_as_uint(o[2]), 0x0410u) & 0xffffffu;
 }
 
-// ---- packed fp32 pairs (sm_100a FADD2 / FMUL2 / FFMA2): two IEEE operations per issued instruction, bit-identical to
-// the scalar _rn intrinsics (no .ftz, round-to-nearest-even) -----------------------------------------------------------
-__device__ __forceinline__ float2 add2(float2 a, float2 b)
-{
-    float2 r;
-    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
-        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return r;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b)
-{
-    float2 r;
-    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
-        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return r;
-}
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
-{
-    float2 r;
-    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }"
-        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-    return r;
-}
-
-// byte `b` of `word` as a float still carrying the 2^23 bias (PRMT only); remove with one (paired) add of -2^23
-__device__ __forceinline__ float u8_biased(unsigned word, int b) { return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | (unsigned)b)); }
-
-// the 2x2 window of one table entry as byte-aligned words: lo = bytes 0..3, hi = bytes 4..5 of each window row
-struct TapWindow { unsigned lo1, hi1, lo2, hi2; };
-__device__ __forceinline__ TapWindow load_tap_window(const uint8_t *__restrict__ base, unsigned pitch, unsigned off)
-{
-    const uint8_t *a = base + (off & 0x7ffffffcu);
-    const unsigned s8 = (off & 3u) * 8u;
-    const unsigned t0 = __ldg((const unsigned *)a), t1 = __ldg((const unsigned *)(a + 4));
-    const unsigned u0 = __ldg((const unsigned *)(a + pitch)), u1 = __ldg((const unsigned *)(a + pitch + 4));
-    unsigned t2 = 0u, u2 = 0u;
-    if (s8 == 24u) { t2 = __ldg((const unsigned *)(a + 8)); u2 = __ldg((const unsigned *)(a + pitch + 8)); }
-    TapWindow w;
-    w.lo1 = __funnelshift_r(t0, t1, s8); w.hi1 = __funnelshift_r(t1, t2, s8);
-    w.lo2 = __funnelshift_r(u0, u1, s8); w.hi2 = __funnelshift_r(u1, u2, s8);
-    return w;
-}
-
-// Two pixels from two table entries with the fmul / fma chain, both roundings and the gain step issued as packed pairs
-// (lane x = first pixel, lane y = second).  NXU of the four taps per channel are converted by I2F.U8 (conversion unit,
-// no bias) instead of PRMT + packed add: spreads the work over one more pipe.  Same operations in the same order as
-// remap_tab_px, hence bit-identical.
-template <bool GAIN, int NXU>
-__device__ __forceinline__ void remap_tab_px2(const uint8_t *__restrict__ base, unsigned pitch, unsigned off0, unsigned off1,
-                                              float2 wa, float2 wb, float2 wc, float2 wd, float gain, unsigned &out0, unsigned &out1)
-{
-    const TapWindow p = load_tap_window(base, pitch, off0), q = load_tap_window(base, pitch, off1);
-    const float2 unbias = make_float2(-8388608.f, -8388608.f), magic = make_float2(12582912.f, 12582912.f);
-    float2 o[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        // tap t of channel c sits in word (lo | hi) at byte: t even -> byte c of lo; t odd -> byte 3 of lo (c == 0) or byte c - 1 of hi
-        float2 s[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const unsigned wp = (t & 1) ? (c == 0 ? (t < 2 ? p.lo1 : p.lo2) : (t < 2 ? p.hi1 : p.hi2)) : (t < 2 ? p.lo1 : p.lo2);
-            const unsigned wq = (t & 1) ? (c == 0 ? (t < 2 ? q.lo1 : q.lo2) : (t < 2 ? q.hi1 : q.hi2)) : (t < 2 ? q.lo1 : q.lo2);
-            const int b = (t & 1) ? (c == 0 ? 3 : c - 1) : c;
-            if (t >= 4 - NXU) s[t] = make_float2((float)((wp >> (8 * b)) & 0xffu), (float)((wq >> (8 * b)) & 0xffu));
-            else s[t] = add2(make_float2(u8_biased(wp, b), u8_biased(wq, b)), unbias);
-        }
-        float2 v = mul2(s[0], wa);
-        v = fma2(s[1], wb, v);
-        v = fma2(s[2], wc, v);
-        v = fma2(s[3], wd, v);
-        v = add2(v, magic);                                   // sat_u8(rni(.)): integer in the low mantissa bits
-        if (GAIN) {
-            v = mul2(make_float2(gain, gain), add2(v, make_float2(-12582912.f, -12582912.f)));
-            v = add2(make_float2(fminf(v.x, 255.f), fminf(v.y, 255.f)), magic);  // sat_u8(rni(gain * v))
-        }
-        o[c] = v;
-    }
-    out0 = __byte_perm(__byte_perm(__float_as_uint(o[0].x), __float_as_uint(o[1].x), 0x0040u), __float_as_uint(o[2].x), 0x0410u) & 0xffffffu;
-    out1 = __byte_perm(__byte_perm(__float_as_uint(o[0].y), __float_as_uint(o[1].y), 0x0040u), __float_as_uint(o[2].y), 0x0410u) & 0xffffffu;
-}
-
 }  // namespace vsb

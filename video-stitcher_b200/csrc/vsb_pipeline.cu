@@ -220,54 +220,50 @@ struct Stage1TabParams {
     Stage1TabView v[MAXV];
     const uint8_t *src[MAX_BATCH * MAXV];  // [frame][view - v0]
     unsigned src_pitch;
-    int v0, n_views, n_frames, frame_shift;  // block = tile << frame_shift | frame: the frames of a tile run back to back (table stays in L2)
+    int v0, n_views, n_frames;
 };
 
-// VAR: 0 = scalar chain, 1..3 = packed pairs with 0 / 1 / 2 taps per channel converted on the conversion unit (remap_tab_px2)
-template <int VAR>
+// One CTA = one 128 x 8 tile for ALL frames of the submission: the table entries of the thread's 4 pixels are loaded once
+// and stay in registers while the frames stream through (window loads -> fmul / fma chain -> 12-byte store per frame).
 __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage1_tab(const __grid_constant__ Stage1TabParams p)
 {
-    const int f = blockIdx.x & ((1 << p.frame_shift) - 1);
-    if (f >= p.n_frames) return;
-    const unsigned tile = __ldg(p.tiles + (blockIdx.x >> p.frame_shift));
+    const unsigned tile = __ldg(p.tiles + blockIdx.x);
     const int vi = tile & 0xff;
     const Stage1TabView &V = p.v[vi];
     const int x0 = ((int)((tile >> 8) & 0xfff) * RM_BX + threadIdx.x) * RM_PX, y = (int)(tile >> 20) * RM_BY + threadIdx.y;
     if (x0 >= V.w || y >= V.h) return;
-    const uint8_t *src = p.src[f * p.n_views + vi - p.v0];
     const size_t i = (size_t)y * V.tab.tab_pitch + x0;
     const int4 o = __ldg((const int4 *)(V.tab.off + i));
     const float4 A = __ldg((const float4 *)(V.tab.w + i)), B = __ldg((const float4 *)(V.tab.w + V.tab.plane + i));
     const float4 C = __ldg((const float4 *)(V.tab.w + 2 * V.tab.plane + i)), D = __ldg((const float4 *)(V.tab.w + 3 * V.tab.plane + i));
     const int off[RM_PX] = {o.x, o.y, o.z, o.w};
-    unsigned px[RM_PX];
-    if (VAR == 0) {
-        const float wa[RM_PX] = {A.x, A.y, A.z, A.w}, wb[RM_PX] = {B.x, B.y, B.z, B.w}, wc[RM_PX] = {C.x, C.y, C.z, C.w}, wd[RM_PX] = {D.x, D.y, D.z, D.w};
+    const float wa[RM_PX] = {A.x, A.y, A.z, A.w}, wb[RM_PX] = {B.x, B.y, B.z, B.w}, wc[RM_PX] = {C.x, C.y, C.z, C.w}, wd[RM_PX] = {D.x, D.y, D.z, D.w};
+    const bool slow = (o.x | o.y | o.z | o.w) < 0;
+    const int n = min(RM_PX, V.w - x0);
+    uint8_t *dst = V.P + (size_t)y * V.p_pitch + (size_t)x0 * 3;
+#pragma unroll 1
+    for (int f = 0; f < p.n_frames; ++f, dst += V.p_frame_stride) {
+        const uint8_t *src = p.src[f * p.n_views + vi - p.v0];
+        unsigned px[RM_PX];
 #pragma unroll
         for (int k = 0; k < RM_PX; ++k) px[k] = remap_tab_px<true>(src, p.src_pitch, (unsigned)off[k] & 0x7fffffffu, wa[k], wb[k], wc[k], wd[k], V.gain);
-    } else {
-        constexpr int NXU = VAR > 0 ? VAR - 1 : 0;
-        remap_tab_px2<true, NXU>(src, p.src_pitch, (unsigned)o.x, (unsigned)o.y, make_float2(A.x, A.y), make_float2(B.x, B.y), make_float2(C.x, C.y), make_float2(D.x, D.y), V.gain, px[0], px[1]);
-        remap_tab_px2<true, NXU>(src, p.src_pitch, (unsigned)o.z, (unsigned)o.w, make_float2(A.z, A.w), make_float2(B.z, B.w), make_float2(C.z, C.w), make_float2(D.z, D.w), V.gain, px[2], px[3]);
-    }
-    if ((o.x | o.y | o.z | o.w) < 0) {  // TAP_SLOW entries: the window loads above were redirected to offset 0, the result comes from the coordinates
+        if (slow) {  // TAP_SLOW entries: the window loads above were redirected to offset 0, the result comes from the coordinates
 #pragma unroll 1
-        for (int k = 0; k < RM_PX; ++k) {
-            if (off[k] >= 0) continue;
-            const float fx = __ldg((const float *)((const char *)V.xmap + (size_t)y * V.map_pitch) + x0 + k);
-            const float fy = __ldg((const float *)((const char *)V.ymap + (size_t)y * V.map_pitch) + x0 + k);
-            px[k] = remap_gain_px_edge<true>(src, p.src_pitch, V.src_w, V.src_h, fx, fy, V.gain);
+            for (int k = 0; k < RM_PX; ++k) {
+                if (off[k] >= 0) continue;
+                const float fx = __ldg((const float *)((const char *)V.xmap + (size_t)y * V.map_pitch) + x0 + k);
+                const float fy = __ldg((const float *)((const char *)V.ymap + (size_t)y * V.map_pitch) + x0 + k);
+                px[k] = remap_gain_px_edge<true>(src, p.src_pitch, V.src_w, V.src_h, fx, fy, V.gain);
+            }
         }
-    }
-    uint8_t *dst = V.P + (size_t)f * V.p_frame_stride + (size_t)y * V.p_pitch + (size_t)x0 * 3;
-    const int n = min(RM_PX, V.w - x0);
-    if (n == RM_PX) {  // 12 bytes = three aligned 32-bit stores
-        unsigned *d32 = (unsigned *)dst;
-        d32[0] = px[0] | (px[1] << 24);
-        d32[1] = (px[1] >> 8) | (px[2] << 16);
-        d32[2] = (px[2] >> 16) | (px[3] << 8);
-    } else {
-        for (int k = 0; k < n; ++k) { dst[3 * k] = px[k] & 0xff; dst[3 * k + 1] = (px[k] >> 8) & 0xff; dst[3 * k + 2] = (px[k] >> 16) & 0xff; }
+        if (n == RM_PX) {  // 12 bytes = three aligned 32-bit stores
+            unsigned *d32 = (unsigned *)dst;
+            d32[0] = px[0] | (px[1] << 24);
+            d32[1] = (px[1] >> 8) | (px[2] << 16);
+            d32[2] = (px[2] >> 16) | (px[3] << 8);
+        } else {
+            for (int k = 0; k < n; ++k) { dst[3 * k] = px[k] & 0xff; dst[3 * k + 1] = (px[k] >> 8) & 0xff; dst[3 * k + 2] = (px[k] >> 16) & 0xff; }
+        }
     }
 }
 
@@ -282,47 +278,42 @@ struct Stage2TabView {
 struct Stage2TabParams {
     const uint32_t *tiles;
     Stage2TabView v[MAXV];
-    int n_frames, frame_shift;
+    int n_frames;
 };
 
-template <int VAR>
 __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage2_tab(const __grid_constant__ Stage2TabParams p)
 {
-    const int f = blockIdx.x & ((1 << p.frame_shift) - 1);
-    if (f >= p.n_frames) return;
-    const unsigned tile = __ldg(p.tiles + (blockIdx.x >> p.frame_shift));
+    const unsigned tile = __ldg(p.tiles + blockIdx.x);
     const Stage2TabView &V = p.v[tile & 0xff];
     const int bx0 = ((int)((tile >> 8) & 0xfff) * RM_BX + threadIdx.x) * RM_PX, by = (int)(tile >> 20) * RM_BY + threadIdx.y;
     if (bx0 >= V.bw || by >= V.bh) return;
-    const uint8_t *P = V.Pbase + (size_t)f * V.p_frame_stride;
     const size_t i = (size_t)by * V.tab.tab_pitch + bx0;
     const int4 o = __ldg((const int4 *)(V.tab.off + i));
     const float4 A = __ldg((const float4 *)(V.tab.w + i)), B = __ldg((const float4 *)(V.tab.w + V.tab.plane + i));
     const float4 C = __ldg((const float4 *)(V.tab.w + 2 * V.tab.plane + i)), D = __ldg((const float4 *)(V.tab.w + 3 * V.tab.plane + i));
-    unsigned px[RM_PX];
-    if (VAR == 0) {
+    const size_t plane = (size_t)V.bw * V.bh;
+    const int n = min(RM_PX, V.bw - bx0);
+    const bool vec = n == RM_PX && (V.bw & 3) == 0;
+    const uint8_t *P = V.Pbase;
+    uint8_t *g = V.G0 + (size_t)by * V.bw + bx0;
+#pragma unroll 1
+    for (int f = 0; f < p.n_frames; ++f, P += V.p_frame_stride, g += V.g0_frame_stride) {
+        unsigned px[RM_PX];
         px[0] = remap_tab_px<false>(P, V.p_pitch, (unsigned)o.x, A.x, B.x, C.x, D.x, 1.f);
         px[1] = remap_tab_px<false>(P, V.p_pitch, (unsigned)o.y, A.y, B.y, C.y, D.y, 1.f);
         px[2] = remap_tab_px<false>(P, V.p_pitch, (unsigned)o.z, A.z, B.z, C.z, D.z, 1.f);
         px[3] = remap_tab_px<false>(P, V.p_pitch, (unsigned)o.w, A.w, B.w, C.w, D.w, 1.f);
-    } else {
-        constexpr int NXU = VAR > 0 ? VAR - 1 : 0;
-        remap_tab_px2<false, NXU>(P, V.p_pitch, (unsigned)o.x, (unsigned)o.y, make_float2(A.x, A.y), make_float2(B.x, B.y), make_float2(C.x, C.y), make_float2(D.x, D.y), 1.f, px[0], px[1]);
-        remap_tab_px2<false, NXU>(P, V.p_pitch, (unsigned)o.z, (unsigned)o.w, make_float2(A.z, A.w), make_float2(B.z, B.w), make_float2(C.z, C.w), make_float2(D.z, D.w), 1.f, px[2], px[3]);
-    }
-    // interleaved -> planar: byte c of the four pixels
-    const unsigned lo01 = __byte_perm(px[0], px[1], 0x5140u), lo23 = __byte_perm(px[2], px[3], 0x5140u);
-    const unsigned c0 = __byte_perm(lo01, lo23, 0x5410u), c1 = __byte_perm(lo01, lo23, 0x7632u);
-    const unsigned c2 = __byte_perm(__byte_perm(px[0], px[1], 0x0062u), __byte_perm(px[2], px[3], 0x0062u), 0x5410u);
-    const size_t plane = (size_t)V.bw * V.bh;
-    uint8_t *g = V.G0 + (size_t)f * V.g0_frame_stride + (size_t)by * V.bw + bx0;
-    const int n = min(RM_PX, V.bw - bx0);
-    if (n == RM_PX && (V.bw & 3) == 0) {
-        *(unsigned *)g = c0;
-        *(unsigned *)(g + plane) = c1;
-        *(unsigned *)(g + 2 * plane) = c2;
-    } else {
-        for (int k = 0; k < n; ++k) { g[k] = (c0 >> (8 * k)) & 0xff; g[plane + k] = (c1 >> (8 * k)) & 0xff; g[2 * plane + k] = (c2 >> (8 * k)) & 0xff; }
+        // interleaved -> planar: byte c of the four pixels
+        const unsigned lo01 = __byte_perm(px[0], px[1], 0x5140u), lo23 = __byte_perm(px[2], px[3], 0x5140u);
+        const unsigned c0 = __byte_perm(lo01, lo23, 0x5410u), c1 = __byte_perm(lo01, lo23, 0x7632u);
+        const unsigned c2 = __byte_perm(__byte_perm(px[0], px[1], 0x0062u), __byte_perm(px[2], px[3], 0x0062u), 0x5410u);
+        if (vec) {
+            *(unsigned *)g = c0;
+            *(unsigned *)(g + plane) = c1;
+            *(unsigned *)(g + 2 * plane) = c2;
+        } else {
+            for (int k = 0; k < n; ++k) { g[k] = (c0 >> (8 * k)) & 0xff; g[plane + k] = (c1 >> (8 * k)) & 0xff; g[2 * plane + k] = (c2 >> (8 * k)) & 0xff; }
+        }
     }
 }
 
@@ -1091,8 +1082,8 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
     return check_launch("k_coarse / k_blend");
 }
 
-// which form of the remap kernels runs (all bit-identical): VSB_REMAP_VARIANT = 0..3 picks the instruction mix of the
-// table-driven kernels (see k_remap_stage1_tab), -1 the coordinate-driven kernels that also serve unaligned caller frames
+// which form of the remap kernels runs (both bit-identical): VSB_REMAP_VARIANT = -1 forces the coordinate-driven kernels
+// that also serve unaligned caller frames, anything else the table-driven ones
 static int remap_variant()
 {
     static int v = -2;
@@ -1127,8 +1118,6 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
     int ws[MAXV], hs[MAXV];
     int r = sync_tile_lists(s);
     if (r != VSB_OK) return r;
-    int frame_shift = 0;
-    while ((1 << frame_shift) < n_frames) ++frame_shift;
     if (!warped) {
         // table-driven remap #1 whenever the caller's frames allow aligned 32-bit window loads
         bool tab = remap_variant() >= 0 && src_pitch % 4 == 0;
@@ -1157,17 +1146,10 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
                 S.w = V.roi_w; S.h = V.roi_h; S.src_w = V.src_w; S.src_h = V.src_h;
             }
             p.tiles = s->d_s1_tiles + first;
-            p.v0 = v0; p.n_views = n; p.src_pitch = (unsigned)src_pitch; p.n_frames = n_frames; p.frame_shift = frame_shift;
+            p.v0 = v0; p.n_views = n; p.src_pitch = (unsigned)src_pitch; p.n_frames = n_frames;
             for (int f = 0; f < n_frames; ++f) for (int j = 0; j < n; ++j) p.src[f * n + j] = d_srcs[f * n + j];
             if (count > 0) {
-                const unsigned g = (unsigned)count << frame_shift;
-                const dim3 b(RM_BX, RM_BY);
-                switch (remap_variant()) {
-                case 0: k_remap_stage1_tab<0><<<g, b, 0, st>>>(p); break;
-                case 2: k_remap_stage1_tab<2><<<g, b, 0, st>>>(p); break;
-                case 3: k_remap_stage1_tab<3><<<g, b, 0, st>>>(p); break;
-                default: k_remap_stage1_tab<1><<<g, b, 0, st>>>(p); break;
-                }
+                k_remap_stage1_tab<<<(unsigned)count, dim3(RM_BX, RM_BY), 0, st>>>(p);
             }
         } else {
             Stage1Params p;
@@ -1209,16 +1191,9 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
                 S.Pbase = V.P_alloc; S.G0 = V.G0; S.p_frame_stride = V.p_frame_stride; S.g0_frame_stride = V.g0_frame_stride;
                 S.p_pitch = (unsigned)V.p_pitch; S.bw = V.bw; S.bh = V.bh;
             }
-            p.tiles = s->d_s2_tiles + first; p.n_frames = n_frames; p.frame_shift = frame_shift;
+            p.tiles = s->d_s2_tiles + first; p.n_frames = n_frames;
             if (count > 0) {
-                const unsigned g = (unsigned)count << frame_shift;
-                const dim3 b(RM_BX, RM_BY);
-                switch (remap_variant()) {
-                case 0: k_remap_stage2_tab<0><<<g, b, 0, st>>>(p); break;
-                case 2: k_remap_stage2_tab<2><<<g, b, 0, st>>>(p); break;
-                case 3: k_remap_stage2_tab<3><<<g, b, 0, st>>>(p); break;
-                default: k_remap_stage2_tab<1><<<g, b, 0, st>>>(p); break;
-                }
+                k_remap_stage2_tab<<<(unsigned)count, dim3(RM_BX, RM_BY), 0, st>>>(p);
             }
         } else {
             Stage2Params p;
