@@ -189,7 +189,7 @@ def test_compose_matches_oracle(cuda, og, case, inject):
             gk = og.pyr_down_s16(gk)
     _eq(got, want, "composed panorama (CV_16SC3)")
     _eq((np.abs(got).sum(axis=2) > 0) | (want_mask > 0), want_mask > 0, "output mask support")
-    assert grig.st.last_launch_count() == (5 + orig.num_bands - 2 if orig.num_bands >= 3 else 3 + orig.num_bands)
+    assert grig.st.last_launch_count() == (6 if orig.num_bands >= 3 else 3 + orig.num_bands)  # K1 K2 down2 down_tail coarse blend
     # B4/B5 per-view entry points give the same frame
     _eq(grig.feed_blend(frames), want, "feed + blend")
 

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvsb200.so")
+LIB_PATH = os.environ.get("VSB200_LIB") or os.path.join(_HERE, "libvsb200.so")  # VSB200_LIB: an alternative build of the same ABI (kernel A/B runs)
 
 OK = 0
 PROJ_SPHERICAL = 0

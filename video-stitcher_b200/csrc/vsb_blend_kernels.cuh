@@ -324,6 +324,98 @@ __global__ void __launch_bounds__(D1_TX *D1_TY) k_down1(const __grid_constant__ 
     V.dst[(size_t)f * V.dst_fs + ((size_t)c * hd + y) * wd + x] = (uint8_t)rhe_shift<8>(acc);
 }
 
+// ======================================================================================================== k_down_tail
+// Gaussian levels 3 .. nb of one colour plane of one view in ONE launch: these planes are 1/64 of the image and smaller, so
+// one CTA keeps every level it produces in shared memory (level k + 1 is computed from the shared copy of level k) and
+// writes each level out once.  Replaces nb - 2 k_down1 launches whose cost was launch latency, not work.
+struct DownTailView {
+    const uint8_t *g2;           // level 2, frame 0
+    uint8_t *g[MAXL];            // level k (3 .. nb), frame 0
+    size_t g2_fs, fs[MAXL];      // frame strides (bytes)
+    int w2, h2;
+};
+struct DownTailParams {
+    int nb;
+    DownTailView v[MAXV];
+};
+constexpr int DT_TX = 32, DT_TY = 32;
+
+// one pyrDown level of a u8 plane (ws x hs -> ws/2 x hs/2) by the whole CTA (32 x 32 threads, no index divisions); a thread
+// produces the column pair (2n, 2n + 1) from three aligned words per source row (__dp4a taps), samples near the plane
+// border take the reflecting scalar form.  GLOBAL_SRC: the source is the level-2 plane in HBM / L2, else the shared copy.
+template <bool GLOBAL_SRC>
+__device__ __forceinline__ void down_plane_cta(const uint8_t *__restrict__ src, int ws, int hs, uint8_t *__restrict__ dst_s, uint8_t *__restrict__ dst_g)
+{
+    const int wd = ws >> 1, hd = hs >> 1, npair = (wd + 1) >> 1, wsw = ws >> 2;
+    const bool words = (ws & 3) == 0 && (((size_t)src) & 3) == 0;
+    for (int y = threadIdx.y; y < hd; y += DT_TY) {
+        if (words && ws >= 8) {
+            // reflect-101 rows are an index computation; the two border column pairs synthesise their out-of-plane word from
+            // the neighbouring ones (columns -2, -1 mirror 2, 1; column ws mirrors ws - 2), so no lane leaves this path
+            const unsigned *rowp[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) rowp[j] = (const unsigned *)(src + (size_t)r101_idx(2 * y - 2 + j, hs) * ws);
+            for (int n = threadIdx.x; n < npair; n += DT_TX) {
+                unsigned acc_e = 0, acc_o = 0;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const unsigned kj = j == 2 ? 6u : ((j & 1) ? 4u : 1u);
+                    const unsigned *row = rowp[j] + n;
+                    unsigned a, b, c;
+                    if (GLOBAL_SRC) { b = __ldg(row); a = n >= 1 ? __ldg(row - 1) : 0u; c = n + 1 < wsw ? __ldg(row + 1) : 0u; }
+                    else { b = row[0]; a = n >= 1 ? row[-1] : 0u; c = n + 1 < wsw ? row[1] : 0u; }
+                    if (n == 0) a = __byte_perm(b, c, 0x1234u);            // columns -4 .. -1  <-  4, 3, 2, 1
+                    if (n + 1 >= wsw) c = __byte_perm(b, 0u, 0x2222u);     // column ws  <-  ws - 2
+                    acc_e = taps5<false>(a, b, kj, acc_e);
+                    acc_o = taps5<true>(b, c, kj, acc_o);
+                }
+                const unsigned pair = (unsigned)rhe_shift<8>((int)acc_e) | ((unsigned)rhe_shift<8>((int)acc_o) << 8);
+                *(uint16_t *)(dst_s + y * wd + 2 * n) = (uint16_t)pair;   // wd is even here
+                *(uint16_t *)(dst_g + (size_t)y * wd + 2 * n) = (uint16_t)pair;
+            }
+            continue;
+        }
+        for (int n = threadIdx.x; n < npair; n += DT_TX) {
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q) {
+                const int xx = 2 * n + q;
+                if (xx >= wd) break;
+                int cc[5], acc = 0;
+#pragma unroll
+                for (int e = 0; e < 5; ++e) cc[e] = r101_idx(2 * xx - 2 + e, ws);
+#pragma unroll
+                for (int e = 0; e < 5; ++e) {
+                    const uint8_t *rp = src + (size_t)r101_idx(2 * y - 2 + e, hs) * ws;
+                    acc += (e == 2 ? 6 : ((e & 1) ? 4 : 1)) * ((int)rp[cc[0]] + 4 * (int)rp[cc[1]] + 6 * (int)rp[cc[2]] + 4 * (int)rp[cc[3]] + (int)rp[cc[4]]);
+                }
+                const uint8_t v = (uint8_t)rhe_shift<8>(acc);
+                dst_s[y * wd + xx] = v;
+                dst_g[(size_t)y * wd + xx] = v;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(DT_TX *DT_TY) k_down_tail(const __grid_constant__ DownTailParams P)
+{
+    extern __shared__ __align__(16) uint8_t dt_smem[];
+    const DownTailView &V = P.v[blockIdx.x];
+    const int c = blockIdx.y, f = blockIdx.z;
+    int w = V.w2, h = V.h2;
+    uint8_t *level = dt_smem;
+    const uint8_t *src = V.g2 + (size_t)f * V.g2_fs + (size_t)c * w * h;
+    for (int k = 2; k < P.nb; ++k) {
+        const int wd = w >> 1, hd = h >> 1;
+        uint8_t *dst_g = V.g[k + 1] + (size_t)f * V.fs[k + 1] + (size_t)c * wd * hd;
+        if (k == 2) down_plane_cta<true>(src, w, h, level, dst_g);
+        else down_plane_cta<false>(src, w, h, level, dst_g);
+        __syncthreads();
+        src = level;
+        level += ((size_t)wd * hd + 15) & ~(size_t)15;
+        w = wd; h = hd;
+    }
+}
+
 // ========================================================================================================== k_coarse
 // Levels 2..nb for one 64x64 (level-2) canvas tile of one colour plane: for every view that has weight there, the
 // Laplacian bands from the stored Gaussian levels, the truncating weighted add into shared-memory accumulators; then the

@@ -615,7 +615,7 @@ struct vsb_stitcher {
     // fast path (num_bands >= 3): static tile tables + per-frame canvas buffer
     bool fast = false;
     vsb::CoarseGeo cgeo;
-    size_t coarse_smem = 0;
+    size_t coarse_smem = 0, down_tail_smem = 48 * 1024;
     uint32_t *d_blend_views = nullptr, *d_coarse_views = nullptr, *d_down2_tiles = nullptr;
     int blend_tiles_x = 0, blend_tiles_y = 0, coarse_tiles_x = 0, coarse_tiles_y = 0, n_down2_tiles = 0;
     int16_t *C2 = nullptr;
@@ -1011,6 +1011,36 @@ static int launch_down2(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
 static int launch_down1(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStream_t st)
 {
     const int nb = s->nb;
+    {   // every level of a plane fits in shared memory (true up to ~8k-wide panoramas): one launch, one CTA per plane
+        size_t smem = 0;
+        double bytes = 0;
+        for (int i = v0; i < v1; ++i) {
+            size_t need = 0;
+            for (int k = 3; k <= nb; ++k) need += align_up((size_t)(s->v[i].bw >> k) * (s->v[i].bh >> k), 16);
+            smem = std::max(smem, need);
+            bytes += 3.0 * (s->v[i].bw >> 2) * (s->v[i].bh >> 2);
+            for (int k = 3; k <= nb; ++k) bytes += 3.0 * (s->v[i].bw >> k) * (s->v[i].bh >> k);
+        }
+        if (smem <= 200 * 1024 && v1 > v0) {
+            if (smem > s->down_tail_smem) {
+                CK(cudaFuncSetAttribute(k_down_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                s->down_tail_smem = smem;
+            }
+            DownTailParams p;
+            std::memset(&p, 0, sizeof(p));
+            p.nb = nb;
+            for (int i = v0; i < v1; ++i) {
+                const View &V = s->v[i];
+                DownTailView &D = p.v[i - v0];
+                D.g2 = V.G2; D.g2_fs = V.g2_frame_stride; D.w2 = V.bw >> 2; D.h2 = V.bh >> 2;
+                for (int k = 3; k <= nb; ++k) { D.g[k] = V.Gu[k]; D.fs[k] = V.gu_frame_stride[k]; }
+            }
+            k_down_tail<<<dim3(v1 - v0, 3, n_frames), dim3(DT_TX, DT_TY), smem, st>>>(p);
+            ++s->launches;
+            prof_stage(s, st, "down_tail", bytes * n_frames);  // level 2 in once, levels 3..nb out once
+            return check_launch("k_down_tail");
+        }
+    }
     for (int k = 2; k < nb; ++k) {
         Down1Params p;
         std::memset(&p, 0, sizeof(p));
