@@ -203,6 +203,12 @@ __global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Do
         uint4 v;
         if (gx >= 0 && gx + 15 < w0 && (((size_t)(row + gx)) & 15) == 0) {
             v = __ldg((const uint4 *)(row + gx));
+        } else if ((w0 & 15) == 0 && gx < 0) {
+            // left of the plane: G1 exists from column 0 on, so only columns -2 and -1 are ever tapped; they mirror 2 and 1
+            v = make_uint4(0u, 0u, 0u, __byte_perm(__ldg((const unsigned *)row), 0u, 0x1234u));
+        } else if ((w0 & 15) == 0 && gx >= w0) {
+            // right of the plane: the last G1 column taps column w0 at most; it mirrors w0 - 2
+            v = make_uint4(ldg_u8(row + w0 - 2), 0u, 0u, 0u);
         } else {
             v.x = load_word_r101(row, gx, w0); v.y = load_word_r101(row, gx + 4, w0);
             v.z = load_word_r101(row, gx + 8, w0); v.w = load_word_r101(row, gx + 12, w0);
@@ -241,13 +247,27 @@ __global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Do
             if (y1 < h1 && x1 + 3 < w1) *(unsigned *)(g1 + (size_t)y1 * w1 + x1) = *(const unsigned *)&s1[rr + 2][4 + 4 * wq];
         }
     }
+    // Tiles on the plane border: give the out-of-plane G1 positions the value BORDER_REFLECT_101 would read (the mirrored
+    // in-plane sample, which lies inside the region), so that the G2 taps below need no index arithmetic.
+    const bool reflect_ok = 2 * X0 - 2 >= 0 && 2 * X0 - 2 + D2_R1W - 1 < w1 && 2 * Y0 - 2 >= 0 && 2 * Y0 - 2 + D2_R1H - 1 < h1;
+    if (!reflect_ok && w1 >= 6 && h1 >= 6) {
+        for (int i = t; i < D2_R1H * D2_R1W; i += D2_THREADS) {
+            const int r1 = i / D2_R1W, c1 = i - r1 * D2_R1W;
+            const int y1 = 2 * Y0 - 2 + r1, x1 = 2 * X0 - 2 + c1;
+            if ((unsigned)y1 < (unsigned)h1 && (unsigned)x1 < (unsigned)w1) continue;
+            if (y1 < -2 || y1 > h1 || x1 < -2 || x1 > w1) continue;  // never tapped
+            const int my = r101_idx(y1, h1) - (2 * Y0 - 2), mx = r101_idx(x1, w1) - (2 * X0 - 2);
+            if ((unsigned)my < (unsigned)D2_R1H && (unsigned)mx < (unsigned)D2_R1W) s1[r1][c1 + D2_S1OFF] = s1[my][mx + D2_S1OFF];
+        }
+        __syncthreads();
+    }
     uint8_t *g2 = V.g2 + (size_t)f * V.g2_fs + (size_t)c * w2 * h2;
     // G2: one thread per column pair (2n, 2n + 1) of the 32 x 16 tile; taps of column X0 + q start at region byte 2q + D2_S1OFF
     for (int i = t; i < (D2_TW / 2) * D2_TH; i += D2_THREADS) {
         const int n = i & (D2_TW / 2 - 1), ry2 = i / (D2_TW / 2);
         const int x2 = X0 + 2 * n, y2 = Y0 + ry2;
         if (x2 >= w2 || y2 >= h2) continue;
-        if (2 * y2 - 2 >= 0 && 2 * y2 + 2 < h1 && 2 * x2 - 2 >= 0 && 2 * x2 + 4 < w1) {  // both windows inside the plane
+        if ((w1 >= 6 && h1 >= 6 && x2 + 1 < w2) || (2 * y2 - 2 >= 0 && 2 * y2 + 2 < h1 && 2 * x2 - 2 >= 0 && 2 * x2 + 4 < w1)) {  // windows inside the plane, or mirrored above
             const unsigned *row = (const unsigned *)&s1[2 * ry2][4 * n];  // byte 4n + 2 = first tap of the even column
             unsigned acc_e = 0, acc_o = 0;
 #pragma unroll
