@@ -19,6 +19,8 @@
 //   * weights are static, so which views touch which tile is a table built once (vsb_pipeline.cu: build_plan);
 //     the per-level weight sums of levels 0 and 1 are re-accumulated in view order (bit-identical to dst_band_weights_).
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
+
 #include "vsb_internal.h"
 
 namespace vsb {
@@ -184,11 +186,43 @@ struct Down2Params {
     const uint32_t *tiles;  // view | tile_x << 8 | tile_y << 20
     Down2View v[MAXV];
 };
+// TMA descriptors of the G0 buffers, one per view: 3-D u8 tensor {bw, bh, 3 * max_batch}, box {160, 73, 1} (= one k_down2 region)
+struct Down2Maps { CUtensorMap g0[MAXV]; };
 
-__global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Down2Params P)
+// ---- TMA / mbarrier primitives (sm_100a PTX) ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
 {
-    __shared__ __align__(16) unsigned s0[D2_R0H][D2_R0VEC * 4];
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a descriptor / byte-count mistake must trap, not hang the device
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned phase)
+{
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; ++spins) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+        if (!done && spins > (1u << 24)) __trap();
+    }
+}
+// one box of a 3-D tensor -> shared memory, completion counted in bytes on `bar`; out-of-range elements arrive as 0
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+template <bool TMA>
+__global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Down2Params P, const __grid_constant__ Down2Maps M)
+{
+    __shared__ __align__(128) unsigned s0[D2_R0H][D2_R0VEC * 4];
     __shared__ __align__(16) uint8_t s1[D2_R1H][D2_S1PITCH];
+    __shared__ __align__(8) uint64_t bar;
     const unsigned tile = __ldg(P.tiles + blockIdx.x);
     const Down2View &V = P.v[tile & 0xff];
     const int X0 = ((tile >> 8) & 0xfff) * D2_TW, Y0 = (tile >> 20) * D2_TH;
@@ -196,6 +230,37 @@ __global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Do
     const int w0 = V.bw, h0 = V.bh, w1 = w0 >> 1, h1 = h0 >> 1, w2 = w0 >> 2, h2 = h0 >> 2;
     const uint8_t *g0 = V.g0 + (size_t)f * V.g0_fs + (size_t)c * w0 * h0;
     const int gx0 = 4 * X0 - 16, gy0 = 4 * Y0 - 6;
+    if (TMA) {
+        // The 160 x 73 byte region arrives as ONE tensor copy issued by one thread (rows outside the plane arrive as zeros);
+        // requires 16-byte aligned plane rows, i.e. num_bands >= 4 (the host picks the instantiation).
+        if (t == 0) {
+            mbar_init(&bar, 1);
+            mbar_expect_tx(&bar, D2_R0H * D2_R0VEC * 16);
+            tma_load_3d(&s0[0][0], &M.g0[tile & 0xff], gx0, gy0, f * 3 + c, &bar);
+        }
+        __syncthreads();  // the barrier is initialised before anybody polls it
+        mbar_wait(&bar, 0);
+        // Border tiles: BORDER_REFLECT_101 of the few out-of-plane samples the G1 taps reach (rows -2, -1, h0; columns -2, -1, w0)
+        const bool rows_out = gy0 < 0 || gy0 + D2_R0H > h0, cols_out = gx0 < 0 || gx0 + D2_R0VEC * 16 > w0;
+        if (rows_out) {
+            for (int i = t; i < 3 * D2_R0VEC * 4; i += D2_THREADS) {
+                const int which = i / (D2_R0VEC * 4), wd = i - which * (D2_R0VEC * 4);
+                const int y = which == 0 ? -2 : (which == 1 ? -1 : h0);        // plane row to synthesise
+                const int r = y - gy0, rs = r101_idx(y, h0) - gy0;              // region rows: destination, mirrored source
+                if ((unsigned)r < (unsigned)D2_R0H && (unsigned)rs < (unsigned)D2_R0H) s0[r][wd] = s0[rs][wd];
+            }
+            __syncthreads();
+        }
+        if (cols_out) {
+            uint8_t *b0 = (uint8_t *)&s0[0][0];
+            for (int r = t; r < D2_R0H; r += D2_THREADS) {
+                uint8_t *row = b0 + r * (D2_R0VEC * 16);
+                if (gx0 < 0) { row[-2 - gx0] = row[2 - gx0]; row[-1 - gx0] = row[1 - gx0]; }
+                if (w0 - gx0 < D2_R0VEC * 16) row[w0 - gx0] = row[w0 - 2 - gx0];
+            }
+        }
+        __syncthreads();
+    } else {
     for (int i = t; i < D2_R0H * D2_R0VEC; i += D2_THREADS) {
         const int r = i / D2_R0VEC, m = i - r * D2_R0VEC;
         const uint8_t *row = g0 + (size_t)r101_idx(gy0 + r, h0) * w0;
@@ -216,6 +281,7 @@ __global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Do
         *(uint4 *)&s0[r][4 * m] = v;
     }
     __syncthreads();
+    }
     // G1 over the region, at true in-plane positions only (nested reflection does not commute at the high edge).
     // One thread computes the column pair (2m, 2m + 1): the two 5-tap windows start at byte 2 of word m + 2 and byte 0 of
     // word m + 3 of the region row, so no lane diverges on the alignment and the three words per row are loaded once.

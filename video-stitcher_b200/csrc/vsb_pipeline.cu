@@ -584,6 +584,8 @@ struct View {
     int *t2_off[2] = {nullptr, nullptr}; float *t2_w[2] = {nullptr, nullptr}; size_t t2_plane = 0; int t2_pitch = 0;
     uint8_t *G0 = nullptr;
     size_t g0_frame_stride = 0;
+    CUtensorMap g0_map;                 // TMA descriptor of G0 for k_down2 (valid when g0_map_ok)
+    bool g0_map_ok = false;
     int16_t *G[MAXL] = {};              // generic path (num_bands < 3) only: s16 Gaussian levels >= 1
     size_t g_frame_stride[MAXL] = {};
     uint8_t *G2 = nullptr;              // fast path: u8 Gaussian level 2
@@ -675,6 +677,38 @@ static void free_view(View &V)
     for (int k = 3; k < MAXL; ++k) cudaFree(V.Gu[k]);
     if (V.mesh_ready) cudaEventDestroy(V.mesh_ready);
     V = View();
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// G0 of one view as a 3-D u8 tensor {bw, bh, 3 * F}; the box is one k_down2 region.  Needs 16-byte aligned rows.
+static void make_g0_map(View &V, int F)
+{
+    V.g0_map_ok = false;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || (V.bw & 15) != 0 || std::getenv("VSB_NO_TMA")) return;
+    const cuuint64_t dims[3] = {(cuuint64_t)V.bw, (cuuint64_t)V.bh, (cuuint64_t)3 * F};
+    const cuuint64_t strides[2] = {(cuuint64_t)V.bw, (cuuint64_t)V.bw * V.bh};
+    const cuuint32_t box[3] = {(cuuint32_t)(D2_R0VEC * 16), (cuuint32_t)D2_R0H, 1u}, estr[3] = {1u, 1u, 1u};
+    if (V.bw < (int)box[0] || V.bh < (int)box[1]) return;  // planes smaller than one region keep the plain loads
+    const CUresult r = enc(&V.g0_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, V.G0, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    V.g0_map_ok = r == CUDA_SUCCESS;
 }
 
 static int build_plan(vsb_stitcher *s)
@@ -1001,7 +1035,14 @@ static int launch_down2(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
         else if (i < v1) { count += nt; bytes += (double)nt * 3 * (16.0 * D2_TW * D2_TH + 4.0 * D2_TW * D2_TH + D2_TW * D2_TH); }
     }
     p.tiles = s->d_down2_tiles + first;
-    if (count > 0) k_down2<<<dim3(count, 3, n_frames), D2_THREADS, 0, st>>>(p);
+    bool tma = true;
+    Down2Maps maps;
+    std::memset(&maps, 0, sizeof(maps));
+    for (int i = v0; i < v1; ++i) { tma = tma && s->v[i].g0_map_ok; maps.g0[i] = s->v[i].g0_map; }
+    if (count > 0) {
+        if (tma) k_down2<true><<<dim3(count, 3, n_frames), D2_THREADS, 0, st>>>(p, maps);
+        else k_down2<false><<<dim3(count, 3, n_frames), D2_THREADS, 0, st>>>(p, maps);
+    }
     ++s->launches;
     prof_stage(s, st, "down2", bytes * n_frames);  // G0 of the needed tiles in once + G1 and G2 out once
     return check_launch("k_down2");
@@ -1464,6 +1505,7 @@ int vsb_init_view(vsb_stitcher *s, int i, const uint8_t *mask, int mw, int mh, s
     V.P = V.P_alloc + V.p_origin;
     V.g0_frame_stride = (size_t)3 * width * height;
     CK(cudaMalloc(&V.G0, V.g0_frame_stride * F));
+    make_g0_map(V, F);
     if (nb >= 3) {  // fast path keeps only G0 and G2 (u8)
         V.g2_frame_stride = (size_t)3 * (width >> 2) * (height >> 2);
         CK(cudaMalloc(&V.G2, V.g2_frame_stride * F));
