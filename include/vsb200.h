@@ -122,6 +122,17 @@ int vsb_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, siz
  * returns after the outputs are in host memory. */
 int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs, size_t src_pitch_bytes,
                      int16_t *const *h_outs, size_t out_pitch_bytes);
+/* ---- wire format in, consumer format out (both default to the reference's stage boundary).
+ *      VSB_IN_NV12: the source pointers of vsb_feed / vsb_compose / vsb_compose_host are NV12 frames as the capture
+ *      boards send them (A/defs.h:10-17: h rows of Y then h/2 rows of interleaved U,V; `pitch` = row pitch of both) and
+ *      cv::cvtColor(mat, mat, CV_YUV2BGR_NV12) (A/networking.cpp:46) runs on the device, bit-exact.
+ *      VSB_OUT_U8C3: the consumer's mat.convertTo(mat_8u, CV_8U) (A/timed.cpp:250) is fused into the final store; the
+ *      output pointers are then CV_8UC3 buffers (pitch >= 3 * width; pass them cast to int16_t*). ---------------- */
+enum { VSB_IN_BGR8 = 0, VSB_IN_NV12 = 1 };
+enum { VSB_OUT_S16C3 = 0, VSB_OUT_U8C3 = 1 };
+int vsb_set_formats(vsb_stitcher *s, int input_format, int output_format);
+/* cv::cvtColor(CV_YUV2BGR_NV12) on device buffers: IMG/src/color.cpp:8759-8819 (YUV420sp2RGB888Invoker<0,0>) */
+int vsb_nv12_to_bgr(const uint8_t *d_nv12, int w, int h, size_t pitch, uint8_t *d_bgr, size_t bgr_pitch, void *stream);
 /* ---- view-sharded multi-GPU mode (the reference is single-GPU, A/timed.cpp:495-496).  One process and
  *      one calibrated handle per GPU.  Rank r owns a canvas strip (its part of `blend`) and the views whose seam masks lie
  *      mostly inside it (their `stitch_online`).  Per frame: vsb_feed the owned views -> exchange the Gaussian sub-planes

@@ -119,6 +119,22 @@ def gain_u8(img, gain):
     return out
 
 
+def nv12_to_bgr(nv12, w, h):
+    """nv12: (h * 3 // 2, w) uint8 (Y plane then interleaved UV) -> (h, w, 3) BGR"""
+    nv12 = np.ascontiguousarray(nv12, np.uint8)
+    assert nv12.shape == (h * 3 // 2, w) and w % 2 == 0 and h % 2 == 0
+    dst = np.empty((h, w, 3), np.uint8)
+    lib().og_nv12_to_bgr(_p(nv12, C.c_uint8), w, h, C.c_size_t(w), _p(dst, C.c_uint8), C.c_size_t(w * 3))
+    return dst
+
+
+def s16_to_u8(a):
+    a = np.ascontiguousarray(a, np.int16)
+    dst = np.empty(a.shape, np.uint8)
+    lib().og_s16_to_u8(_p(a, C.c_int16), C.c_size_t(a.size), _p(dst, C.c_uint8))
+    return dst
+
+
 def resize_linear_u8c1(src, dw, dh):
     src = np.ascontiguousarray(src, np.uint8)
     sh, sw = src.shape

@@ -279,6 +279,37 @@ void og_gain_u8(uint8_t *buf, size_t n, float gain)
     for (size_t i = 0; i < n; ++i) buf[i] = lut[buf[i]];
 }
 
+/* The capture boards send NV12; the reference converts every received frame with cv::cvtColor(mat, mat, CV_YUV2BGR_NV12)
+ * (360_stitcher/networking.cpp:46).  Integer BT.601 arithmetic of YUV420sp2RGB888Invoker<bIdx = 0, uIdx = 0>:
+ * sources/modules/imgproc/src/color.cpp:8741-8746 (constants), :8793-8818 (per 2x2 block). */
+static uint8_t sat_u8_int(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+void og_nv12_to_bgr(const uint8_t *nv12, int w, int h, size_t step, uint8_t *bgr, size_t bgr_step)
+{
+    const int CY = 1220542, CUB = 2116026, CUG = -409993, CVG = -852492, CVR = 1673527, SHIFT = 20;
+    const uint8_t *uvp = nv12 + step * (size_t)h;
+    for (int j = 0; j < h; ++j) {
+        const uint8_t *yr = nv12 + step * (size_t)j, *uv = uvp + step * (size_t)(j / 2);
+        uint8_t *o = bgr + bgr_step * (size_t)j;
+        for (int i = 0; i < w; ++i) {
+            const int u = (int)uv[(i & ~1)] - 128, v = (int)uv[(i & ~1) + 1] - 128;
+            const int ruv = (1 << (SHIFT - 1)) + CVR * v;
+            const int guv = (1 << (SHIFT - 1)) + CVG * v + CUG * u;
+            const int buv = (1 << (SHIFT - 1)) + CUB * u;
+            const int yy = ((int)yr[i] - 16 > 0 ? (int)yr[i] - 16 : 0) * CY;
+            o[3 * i + 0] = sat_u8_int((yy + buv) >> SHIFT);
+            o[3 * i + 1] = sat_u8_int((yy + guv) >> SHIFT);
+            o[3 * i + 2] = sat_u8_int((yy + ruv) >> SHIFT);
+        }
+    }
+}
+
+/* consumer: mat.convertTo(mat_8u, CV_8U) before the download (360_stitcher/timed.cpp:250); cuda convertTo without scale is
+ * saturate_cast<uchar>(short) (sources/modules/core/include/opencv2/core/cuda/saturate_cast.hpp) */
+void og_s16_to_u8(const int16_t *src, size_t n, uint8_t *dst)
+{
+    for (size_t i = 0; i < n; ++i) dst[i] = sat_u8_int(src[i]);
+}
+
 /* cuda::resize INTER_LINEAR on CV_8UC1: CW/src/cuda/resize.cu:71-106, host CW/src/resize.cpp:76-105 */
 void og_resize_linear_u8c1(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh)
 {

@@ -41,6 +41,12 @@ void og_gain_u8(uint8_t *buf, size_t n, float gain);
 void og_resize_linear_u8c1(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh);
 void og_dilate3x3_u8c1(const uint8_t *src, int w, int h, uint8_t *dst);
 
+/* ---------------------------------------------------------------- wire format in / consumer format out */
+/* cv::cvtColor(CV_YUV2BGR_NV12): h rows of Y (step bytes apart) followed by h/2 rows of interleaved U,V; w and h even */
+void og_nv12_to_bgr(const uint8_t *nv12, int w, int h, size_t step, uint8_t *bgr, size_t bgr_step);
+/* GpuMat::convertTo(CV_8U) of the CV_16SC3 panorama: saturate_cast<uchar>(short) */
+void og_s16_to_u8(const int16_t *src, size_t n, uint8_t *dst);
+
 /* ---------------------------------------------------------------- CPW mesh -> backward map */
 void og_custom_resize(const float *in, int cols, int rows, float *out, int tx, int ty);
 /* half-res table (W/2 x H/2) of step m1-m3; then og_custom_resize gives the full map (m4) */

@@ -108,6 +108,21 @@ def gain_u8(img, gain):
     return out
 
 
+def cvt_nv12_bgr(nv12, w, h):
+    nv12 = np.ascontiguousarray(nv12, np.uint8)
+    dst = np.empty((h, w, 3), np.uint8)
+    lib().vr_cvt_nv12_bgr(_p(nv12), w, h, _p(dst))
+    return dst
+
+
+def convert_s16_u8(a):
+    a = np.ascontiguousarray(a, np.int16)
+    h, w, cn = a.shape
+    dst = np.empty(a.shape, np.uint8)
+    lib().vr_convert_s16_u8(_p(a), w, h, cn, _p(dst))
+    return dst
+
+
 def resize_linear_u8c1(src, dw, dh):
     src = np.ascontiguousarray(src, np.uint8)
     sh, sw = src.shape

@@ -161,6 +161,18 @@ void vr_gain_u8(uint8_t *buf, size_t n, float gain)
     Mat m(1, (int)n, CV_8U, buf);
     m.convertTo(m, CV_8U, gain);
 }
+void vr_cvt_nv12_bgr(const uint8_t *nv12, int w, int h, uint8_t *bgr)
+{
+    Mat s(h * 3 / 2, w, CV_8UC1, const_cast<uint8_t *>(nv12)), d(h, w, CV_8UC3, bgr), o;
+    cvtColor(s, o, COLOR_YUV2BGR_NV12);  // 360_stitcher/networking.cpp:46
+    o.copyTo(d);
+}
+void vr_convert_s16_u8(const int16_t *src, int w, int h, int cn, uint8_t *dst)
+{
+    Mat s(h, w, CV_16SC(cn), const_cast<int16_t *>(src)), d(h, w, CV_8UC(cn), dst), o;
+    s.convertTo(o, CV_8U);  // 360_stitcher/timed.cpp:250 (CPU twin of GpuMat::convertTo)
+    o.copyTo(d);
+}
 void vr_resize_linear_u8c1(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh)
 {
     Mat s(sh, sw, CV_8U, const_cast<uint8_t *>(src)), d(dh, dw, CV_8U, dst), o;

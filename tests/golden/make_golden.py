@@ -54,6 +54,19 @@ def remap_input(seed=3):
     return src, xm, ym
 
 
+def nv12_input(w=64, h=48, seed=17):
+    """Random NV12 frame (Y plane then interleaved UV) covering the full byte range, incl. the saturating branches."""
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, (h * 3 // 2, w), dtype=np.uint8), w, h
+
+
+def s16_input(seed=19):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(-600, 900, (24, 40, 3)).astype(np.int16)
+    a[0, 0] = (-32768, 32767, 255); a[0, 1] = (256, -1, 0)
+    return a
+
+
 def blend_recipe(size=128, seed=5):
     """Upstream MultiBandBlender.CanBlendTwoImages recipe (sources/modules/stitching/test/test_blenders.cpp:57-72):
     two images, left/right half masks, 5 bands -- on seeded synthetic images because baboon/lena are not vendored."""
@@ -166,6 +179,10 @@ def main():
         for i in range(2):
             for k in range(b.num_bands + 1):
                 out[f"blend_{name}_w_{i}_{k}"] = b.view_weight(i, k)
+    # 10. wire / consumer formats: cvtColor(CV_YUV2BGR_NV12) (A/networking.cpp:46), convertTo(CV_8U) (A/timed.cpp:250)
+    nv, w, h = nv12_input()
+    out["nv12_bgr"] = vr.cvt_nv12_bgr(nv, w, h)
+    out["s16_to_u8"] = vr.convert_s16_u8(s16_input())
     path = os.path.join(HERE, "reference_cpu.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")

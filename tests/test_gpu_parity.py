@@ -236,6 +236,70 @@ def test_remap_kernel_variants(cuda, og, tmp_path, variant, pad):
         _eq(got[f"pano{f}"], orig.compose(frames)[0], f"variant {variant} pad {pad} frame {f}")
 
 
+def test_nv12_primitive_matches_oracle(cuda, og, vsb):
+    """B-row 'wire format': vsb_nv12_to_bgr = cv::cvtColor(CV_YUV2BGR_NV12), bit-exact, aligned and unaligned pitches."""
+    import ctypes as C
+    import torch
+    import vsb200
+    from tests.gpu_util import host, stream
+    L = vsb.lib()
+    for (w, h, pitch) in ((320, 240, 320), (322, 242, 331), (1920, 1080, 2048)):
+        nv = vsb200.synth.frame_nv12(1, 0, w, h)
+        buf = torch.zeros((h * 3 // 2, pitch), dtype=torch.uint8, device="cuda")
+        buf[:, :w] = torch.from_numpy(nv).cuda()
+        out = torch.full((h, w * 3 + 5), 7, dtype=torch.uint8, device="cuda")
+        vsb.check(L.vsb_nv12_to_bgr(C.c_void_p(buf.data_ptr()), w, h, C.c_size_t(pitch), C.c_void_p(out.data_ptr()), C.c_size_t(w * 3 + 5), C.c_void_p(stream())))
+        got = host(out)
+        _eq(got[:, :w * 3].reshape(h, w, 3), og.nv12_to_bgr(nv, w, h), f"nv12 -> bgr {w}x{h} pitch {pitch}")
+        assert (got[:, w * 3:] == 7).all()
+
+
+@pytest.mark.parametrize("case", ["small4", "bands6"])
+def test_nv12_input_and_u8_output(cuda, og, case):
+    """SURVEY 8f rows 2-3 fused into the path: NV12 frames in (cvtColor on the device), CV_8UC3 panorama out (convertTo fused
+    into the blend store); device and host entry points, batched."""
+    import torch
+    import vsb200
+    from tests.gpu_util import dev, host, stream
+    B = vsb200.binding
+    orig, grig, kw = _rigs(case, inject=False, max_batch=2)
+    n, sw, sh = kw["n_views"], kw["src_w"], kw["src_h"]
+    nv = [[vsb200.synth.frame_nv12(i, f, sw, sh) for i in range(n)] for f in range(2)]
+    want16 = [orig.compose([og.nv12_to_bgr(a, sw, sh) for a in fr])[0] for fr in nv]
+    want8 = [og.s16_to_u8(w) for w in want16]
+    W, H = grig.roi_final[2], grig.roi_final[3]
+    srcs = [dev(a) for fr in nv for a in fr]
+    # NV12 in, CV_16SC3 out
+    grig.st.set_formats(B.IN_NV12, B.OUT_S16C3)
+    outs = [torch.full((H, W, 3), -12345, dtype=torch.int16, device="cuda") for _ in range(2)]
+    grig.st.compose([t.data_ptr() for t in srcs], sw, [o.data_ptr() for o in outs], W * 6, stream())
+    for f in range(2):
+        _eq(host(outs[f]), want16[f], f"NV12 in, frame {f}")
+    # NV12 in, CV_8UC3 out, pitched output
+    grig.st.set_formats(B.IN_NV12, B.OUT_U8C3)
+    pitch = (W * 3 + 63) // 64 * 64
+    outs8 = [torch.full((H, pitch), 99, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    grig.st.compose([t.data_ptr() for t in srcs], sw, [o.data_ptr() for o in outs8], pitch, stream())
+    for f in range(2):
+        got = host(outs8[f])
+        _eq(got[:, :W * 3].reshape(H, W, 3), want8[f], f"NV12 in, CV_8UC3 out, frame {f}")
+        assert (got[:, W * 3:] == 99).all(), "row padding must stay untouched"
+    # host entry point with both formats
+    houts = [np.zeros((H, W, 3), np.uint8) for _ in range(2)]
+    grig.st.compose_host([a.ctypes.data for fr in nv for a in fr], sw, [o.ctypes.data for o in houts], W * 3)
+    for f in range(2):
+        _eq(houts[f], want8[f], f"host path NV12 -> CV_8UC3 frame {f}")
+    # BGR in, CV_8UC3 out through feed + blend
+    grig.st.set_formats(B.IN_BGR8, B.OUT_U8C3)
+    bgr = [og.nv12_to_bgr(a, sw, sh) for a in nv[1]]
+    d_bgr = [dev(a) for a in bgr]
+    out1 = torch.zeros((H, W, 3), dtype=torch.uint8, device="cuda")
+    for i, t_ in enumerate(d_bgr):
+        grig.st.feed(i, t_.data_ptr(), sw * 3, stream())
+    grig.st.blend(out1.data_ptr(), W * 3, stream())
+    _eq(host(out1), want8[1], "feed + blend, CV_8UC3 out")
+
+
 def test_compose_host_roundtrip(cuda, og):
     import vsb200
     orig, grig, kw = _rigs("small4", inject=False, max_batch=2)

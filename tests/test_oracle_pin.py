@@ -49,6 +49,13 @@ def test_pyramids_vs_reference_cpu(og, gold, shape):
     np.testing.assert_allclose(og.pyr_down_f32(w), gold[f"pyr_down_f32_{key}"], rtol=0, atol=1e-6)
 
 
+def test_wire_and_consumer_formats_exact(og, gold):
+    """cvtColor(CV_YUV2BGR_NV12) (A/networking.cpp:46) and convertTo(CV_8U) (A/timed.cpp:250): integer work, bit-exact."""
+    nv, w, h = G.nv12_input()
+    assert np.array_equal(og.nv12_to_bgr(nv, w, h), gold["nv12_bgr"])
+    assert np.array_equal(og.s16_to_u8(G.s16_input()), gold["s16_to_u8"])
+
+
 def test_border_gain_dilate_distance_exact(og, gold):
     img = G.pyr_input((20, 37)).astype(np.uint8)
     assert np.array_equal(og.border_reflect_u8c3_to_s16(img, 17, 19, 30, 3), gold["border_reflect"].astype(np.int16))
@@ -154,6 +161,13 @@ def test_live_golden_file_is_current(gold):
     assert np.array_equal(vr.pyr_down(a, vr.T_S16C3), gold["pyr_down_s16_33x47"])
     src, xm, ym = G.remap_input()
     assert np.array_equal(vr.remap_u8(src, xm, ym), gold["remap_linear"])
+
+
+def test_live_nv12_full_frame(og):
+    vr = _vr()
+    import vsb200
+    nv = vsb200.synth.frame_nv12(2, 1, 320, 240)
+    assert np.array_equal(og.nv12_to_bgr(nv, 320, 240), vr.cvt_nv12_bgr(nv, 320, 240))
 
 
 def test_live_pyramids_bordered_size(og):

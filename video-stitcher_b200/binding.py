@@ -26,7 +26,10 @@ SYMBOLS = [
     "vsb_add_src_weight_32f", "vsb_normalize_32f", "vsb_debug_read",
     "vsb_shard_set", "vsb_shard_info", "vsb_shard_rect", "vsb_get_plane",
     "vsb_rig_camera", "vsb_voronoi_seams", "vsb_calibrate_rig", "vsb_rig_info_get", "vsb_get_config", "vsb_set_profiling", "vsb_get_profile",
+    "vsb_set_formats", "vsb_nv12_to_bgr",
 ]
+IN_BGR8, IN_NV12 = 0, 1
+OUT_S16C3, OUT_U8C3 = 0, 1
 
 
 class VsbError(RuntimeError):
@@ -205,6 +208,10 @@ class Stitcher:
 
     def last_launch_count(self):
         return lib().vsb_last_launch_count(self._h)
+
+    def set_formats(self, input_format=IN_BGR8, output_format=OUT_S16C3):
+        """NV12 frames in (cvtColor on the device) and / or CV_8UC3 panoramas out (convertTo(CV_8U) fused into the blend)."""
+        check(lib().vsb_set_formats(self._h, int(input_format), int(output_format)))
 
     def set_profiling(self, on):
         check(lib().vsb_set_profiling(self._h, int(bool(on))))

@@ -948,6 +948,9 @@ __device__ __noinline__ void up_row8_f_edge(const float *reg, int ox, int oy, in
     }
 }
 
+// U8: the consumer's `mat.convertTo(mat_8u, CV_8U)` (360_stitcher/timed.cpp:250) is applied in the final store: the
+// panorama leaves as CV_8UC3 (saturate_cast<uchar> of the CV_16SC3 sample) -- half the bytes to write and to download.
+template <bool U8>
 __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__ BlendParams P, const __grid_constant__ OutPtrs outs, size_t out_pitch)
 {
     // staging area: fp32 G1 and G2 regions of the current view; re-used for the interleaved output tile at the end
@@ -1155,7 +1158,7 @@ __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__
         const bool interior = ix0 >= 1 && ix0 + 4 < P.cw1 && iy >= 1 && iy + 1 < P.ch1;
         // Outputs keep the 1.5 * 2^23 bias of the pyrUp result (bits 0x4B400000 + value): its low 16 bits are zero, so the
         // CV_16SC3 sample is simply the low half-word.  Saturation bounds are shifted by the same constant.
-        constexpr int LO = B2_MAGIC_BITS - 32768, HI = B2_MAGIC_BITS + 32767;
+        constexpr int LO = U8 ? B2_MAGIC_BITS : B2_MAGIC_BITS - 32768, HI = U8 ? B2_MAGIC_BITS + 255 : B2_MAGIC_BITS + 32767;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float up[8];
@@ -1181,36 +1184,53 @@ __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__
                 }
             }
         }
-        // 8 pixels x 3 channels of CV_16SC3 = 48 contiguous bytes: element e = 3 * i + c
-        uint4 *o4 = (uint4 *)(sOut + ly * (BL_TW * 3) + lx * 3);
+        // 8 pixels x 3 channels, element e = 3 * i + c: 48 contiguous bytes of CV_16SC3 or 24 of CV_8UC3
+        if (U8) {
+            uint2 *o2 = (uint2 *)((uint8_t *)sStage + ly * (BL_TW * 3) + lx * 3);
 #pragma unroll
-        for (int v4 = 0; v4 < 3; ++v4) {
-            unsigned w[4];
+            for (int v2 = 0; v2 < 3; ++v2) {
+                unsigned w[2];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int e0 = 8 * v4 + 2 * k, e1 = e0 + 1;
-                w[k] = __byte_perm((unsigned)acc0[e0 % 3][e0 / 3], (unsigned)acc0[e1 % 3][e1 / 3], 0x5410u);
+                for (int k = 0; k < 2; ++k) {
+                    const int e = 8 * v2 + 4 * k;
+                    const unsigned lo = __byte_perm((unsigned)acc0[e % 3][e / 3], (unsigned)acc0[(e + 1) % 3][(e + 1) / 3], 0x0040u);
+                    const unsigned hi = __byte_perm((unsigned)acc0[(e + 2) % 3][(e + 2) / 3], (unsigned)acc0[(e + 3) % 3][(e + 3) / 3], 0x0040u);
+                    w[k] = __byte_perm(lo, hi, 0x5410u);
+                }
+                o2[v2] = make_uint2(w[0], w[1]);
             }
-            o4[v4] = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            uint4 *o4 = (uint4 *)(sOut + ly * (BL_TW * 3) + lx * 3);
+#pragma unroll
+            for (int v4 = 0; v4 < 3; ++v4) {
+                unsigned w[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int e0 = 8 * v4 + 2 * k, e1 = e0 + 1;
+                    w[k] = __byte_perm((unsigned)acc0[e0 % 3][e0 / 3], (unsigned)acc0[e1 % 3][e1 / 3], 0x5410u);
+                }
+                o4[v4] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
         }
     }
     __syncthreads();
-    // ---- cropped, interleaved CV_16SC3 store: 16-byte vectors where the caller's buffer allows
+    // ---- cropped, interleaved store: 16-byte vectors where the caller's buffer allows
+    constexpr int PXB = U8 ? 3 : 6;  // bytes per output pixel
     const int n_px = min(BL_TW, P.out_w - tx0), n_rows = min(BL_TH, P.out_h - ty0);
     if (n_px <= 0 || n_rows <= 0) return;
-    char *obase = (char *)outs.out[f] + (size_t)tx0 * 6;
+    char *obase = (char *)outs.out[f] + (size_t)tx0 * PXB;
     const bool vec_ok = ((((size_t)obase) | out_pitch) & 15) == 0;
-    const int row_bytes = n_px * 6;
-    for (int r = t >> 5; r < n_rows; r += BL_THREADS / 32) {  // one warp per row: 24 chunks of 16 bytes
+    const int row_bytes = n_px * PXB;
+    for (int r = t >> 5; r < n_rows; r += BL_THREADS / 32) {  // one warp per row: 16-byte chunks
         const int ck = t & 31, b0 = ck * 16;
-        if (ck >= BL_TW * 6 / 16 || b0 >= row_bytes) continue;
+        if (ck >= BL_TW * PXB / 16 || b0 >= row_bytes) continue;
         char *o = obase + (size_t)(ty0 + r) * out_pitch + b0;
-        const int16_t *sp = sOut + r * (BL_TW * 3) + ck * 8;
+        const char *sp = (const char *)sStage + r * (BL_TW * PXB) + b0;
         if (vec_ok && b0 + 16 <= row_bytes) {
             *(uint4 *)o = *(const uint4 *)sp;
         } else {
-            const int n = min(8, (row_bytes - b0) >> 1);
-            for (int e = 0; e < n; ++e) ((int16_t *)o)[e] = sp[e];
+            const int n = min(16, row_bytes - b0);
+            for (int e = 0; e < n; ++e) o[e] = sp[e];
         }
     }
 }

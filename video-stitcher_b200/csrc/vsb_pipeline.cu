@@ -317,6 +317,65 @@ __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage2_tab(const __grid_
     }
 }
 
+// ---- K0 (optional): NV12 wire format -> BGR ------------------------------------------------------------------------------
+// The capture boards send NV12 and the reference converts every received frame on the CPU with
+// cv::cvtColor(mat, mat, CV_YUV2BGR_NV12) before the upload (360_stitcher/networking.cpp:46, A/defs.h:10-17).  Here the NV12
+// frame is what crosses PCIe (half the bytes) and this kernel restates the integer BT.601 arithmetic of
+// YUV420sp2RGB888Invoker<bIdx = 0, uIdx = 0> (sources/modules/imgproc/src/color.cpp:8741-8746, 8793-8818) bit for bit.
+// One thread = 4 pixels x 2 rows (two chroma pairs): three 32-bit loads, six 32-bit stores.
+struct Nv12Params {
+    const uint8_t *src[MAX_BATCH * MAXV];  // NV12 frames: h rows of Y, then h / 2 rows of interleaved U, V; rows `pitch` bytes apart
+    uint8_t *dst[MAX_BATCH * MAXV];        // BGR staging image of each frame
+    size_t pitch, dst_pitch;
+    int w, h;
+};
+
+__device__ __forceinline__ unsigned nv12_px(int y, int ruv, int guv, int buv)
+{
+    const int yy = max(0, y - 16) * 1220542;
+    const int b = min(255, max(0, (yy + buv) >> 20)), g = min(255, max(0, (yy + guv) >> 20)), r = min(255, max(0, (yy + ruv) >> 20));
+    return (unsigned)b | ((unsigned)g << 8) | ((unsigned)r << 16);
+}
+
+__global__ void __launch_bounds__(256) k_nv12_to_bgr(const __grid_constant__ Nv12Params p)
+{
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
+    if (x0 >= p.w || y0 >= p.h) return;
+    const uint8_t *src = p.src[blockIdx.z];
+    const uint8_t *y1 = src + (size_t)y0 * p.pitch + x0, *uv = src + (size_t)p.h * p.pitch + (size_t)(y0 >> 1) * p.pitch + x0;
+    uint8_t *d = p.dst[blockIdx.z] + (size_t)y0 * p.dst_pitch + (size_t)x0 * 3;
+    const int n = min(4, p.w - x0);  // w is even: n is 2 or 4
+    unsigned ya, yb, c;
+    if (n == 4 && ((((size_t)src) | p.pitch) & 3) == 0) {
+        ya = __ldg((const unsigned *)y1); yb = __ldg((const unsigned *)(y1 + p.pitch)); c = __ldg((const unsigned *)uv);
+    } else {
+        ya = yb = c = 0;
+        for (int i = 0; i < n; ++i) { ya |= (unsigned)__ldg(y1 + i) << (8 * i); yb |= (unsigned)__ldg(y1 + p.pitch + i) << (8 * i); c |= (unsigned)__ldg(uv + i) << (8 * i); }
+    }
+    unsigned pa[4], pb[4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int u = (int)((c >> (16 * k)) & 0xff) - 128, v = (int)((c >> (16 * k + 8)) & 0xff) - 128;
+        const int ruv = (1 << 19) + 1673527 * v, guv = (1 << 19) - 852492 * v - 409993 * u, buv = (1 << 19) + 2116026 * u;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            pa[2 * k + q] = nv12_px((int)((ya >> (8 * (2 * k + q))) & 0xff), ruv, guv, buv);
+            pb[2 * k + q] = nv12_px((int)((yb >> (8 * (2 * k + q))) & 0xff), ruv, guv, buv);
+        }
+    }
+    if (n == 4 && (p.dst_pitch & 3) == 0) {  // 12 bytes per row = three aligned words (staging rows are 16-byte aligned)
+        unsigned *d0 = (unsigned *)d, *d1 = (unsigned *)(d + p.dst_pitch);
+        d0[0] = pa[0] | (pa[1] << 24); d0[1] = (pa[1] >> 8) | (pa[2] << 16); d0[2] = (pa[2] >> 16) | (pa[3] << 8);
+        d1[0] = pb[0] | (pb[1] << 24); d1[1] = (pb[1] >> 8) | (pb[2] << 16); d1[2] = (pb[2] >> 16) | (pb[3] << 8);
+    } else {
+        for (int i = 0; i < n; ++i) {
+            d[3 * i] = pa[i] & 0xff; d[3 * i + 1] = (pa[i] >> 8) & 0xff; d[3 * i + 2] = (pa[i] >> 16) & 0xff;
+            uint8_t *e = d + p.dst_pitch;
+            e[3 * i] = pb[i] & 0xff; e[3 * i + 1] = (pb[i] >> 8) & 0xff; e[3 * i + 2] = (pb[i] >> 16) & 0xff;
+        }
+    }
+}
+
 // ---- K3: pyrDown on planes ----------------------------------------------------------------------------
 // out(y,x) = rhe( sum_{j,i} k5[j] k5[i] in(r101(2y+j-2), r101(2x+i-2)) / 256 ): the exact integer form of the
 // reference's fp32 vertical-then-horizontal 5-tap passes (every partial sum is exactly representable).
@@ -646,6 +705,13 @@ struct vsb_stitcher {
     int stage_src_w = 0, stage_src_h = 0;
     int rig_projection = -1, rig_src_w = 0, rig_src_h = 0;
     float rig_scale = 0.f;
+    // wire / consumer formats (vsb_set_formats): NV12 input goes through k_nv12_to_bgr into nv_bgr; CV_8UC3 output is k_blend<true>
+    int in_format = VSB_IN_BGR8, out_format = VSB_OUT_S16C3;
+    uint8_t *nv_bgr = nullptr;          // [max_batch][num_views] BGR images, rows nv_pitch bytes apart
+    size_t nv_pitch = 0, nv_stride = 0;
+    int nv_w = 0, nv_h = 0;
+    uint8_t *stage_nv12 = nullptr;      // host path: device copy of the caller's NV12 frames
+    size_t stage_nv12_frame = 0;
     // optional per-kernel timing (vsb_set_profiling): events bracket every launch of the last submission
     bool profiling = false;
     int n_stages = 0;
@@ -1132,7 +1198,7 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
         p.out_w = s->roi_final[2]; p.out_h = s->roi_final[3];
         p.c2 = s->C2; p.c2_fs = s->c2_frame_stride; p.tile_views = s->d_blend_views;
         p.dw0 = s->dw[0]; p.dw1 = s->dw[1];
-        double bytes = 6.0 * s->roi_final[2] * s->roi_final[3] + 6.0 * s->cw[2] * s->ch[2];
+        double bytes = (s->out_format == VSB_OUT_U8C3 ? 3.0 : 6.0) * s->roi_final[2] * s->roi_final[3] + 6.0 * s->cw[2] * s->ch[2];
         for (int i = 0; i < n; ++i) {
             const View &V = s->v[i];
             BlendView &B = p.v[i];
@@ -1144,9 +1210,9 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
         OutPtrs o;
         std::memset(&o, 0, sizeof(o));
         for (int f = 0; f < n_frames; ++f) o.out[f] = d_outs[f];
-        static const bool v1 = std::getenv("VSB_BLEND_V1") != nullptr;  // A/B switch for the previous kernel (same results)
-        if (v1) k_blend_v1<<<dim3(s->blend_tiles_x, s->blend_tiles_y, n_frames), BL_THREADS, 0, st>>>(p, o, out_pitch);
-        else k_blend<<<dim3(s->blend_tiles_x, s->blend_tiles_y, n_frames), BL_THREADS, 0, st>>>(p, o, out_pitch);
+        const dim3 g(s->blend_tiles_x, s->blend_tiles_y, n_frames);
+        if (s->out_format == VSB_OUT_U8C3) k_blend<true><<<g, BL_THREADS, 0, st>>>(p, o, out_pitch);
+        else k_blend<false><<<g, BL_THREADS, 0, st>>>(p, o, out_pitch);
         ++s->launches;
         prof_stage(s, st, "blend", bytes * n_frames);  // G0 + G1 + G2 of every view once, C2 once, CV_16SC3 pano out once
     }
@@ -1160,6 +1226,38 @@ static int remap_variant()
     static int v = -2;
     if (v < -1) { const char *e = std::getenv("VSB_REMAP_VARIANT"); v = e ? std::max(-1, std::min(3, std::atoi(e))) : 0; }
     return v;
+}
+
+// NV12 input: converts the caller's frames of views [v0, v1) into the handle's BGR staging and returns pointers to it
+static int launch_nv12(vsb_stitcher *s, int v0, int v1, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch, cudaStream_t st,
+                       const uint8_t **bgr_ptrs)
+{
+    const int n = v1 - v0, nv = s->cfg.num_views;
+    const int w = s->v[v0].src_w, h = s->v[v0].src_h;
+    for (int i = v0; i < v1; ++i) REQ(s->v[i].src_w == w && s->v[i].src_h == h, VSB_ERR_INVALID, "NV12 input: all views must share one source size");
+    REQ((w & 1) == 0 && (h & 1) == 0, VSB_ERR_INVALID, "NV12 input: source width and height must be even (got %dx%d)", w, h);
+    REQ(src_pitch >= (size_t)w, VSB_ERR_INVALID, "NV12 input: pitch is the Y-plane row pitch and must be >= width");
+    if (!s->nv_bgr || s->nv_w != w || s->nv_h != h) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(s->nv_bgr); s->nv_bgr = nullptr;
+        s->nv_pitch = align_up((size_t)w * 3, 16);
+        s->nv_stride = align_up(s->nv_pitch * h + 16, 256);
+        CK(cudaMalloc(&s->nv_bgr, s->nv_stride * nv * s->cfg.max_batch));
+        s->nv_w = w; s->nv_h = h;
+    }
+    Nv12Params p;
+    std::memset(&p, 0, sizeof(p));
+    for (int f = 0; f < n_frames; ++f)
+        for (int j = 0; j < n; ++j) {
+            p.src[f * n + j] = d_srcs[f * n + j];
+            p.dst[f * n + j] = s->nv_bgr + s->nv_stride * ((size_t)f * nv + v0 + j);
+            bgr_ptrs[f * n + j] = p.dst[f * n + j];
+        }
+    p.pitch = src_pitch; p.dst_pitch = s->nv_pitch; p.w = w; p.h = h;
+    k_nv12_to_bgr<<<dim3(((w + 3) / 4 + 31) / 32, (h / 2 + 7) / 8, n * n_frames), dim3(32, 8), 0, st>>>(p);
+    ++s->launches;
+    prof_stage(s, st, "nv12_to_bgr", (1.5 + 3.0) * w * h * n * n_frames);  // NV12 in once, BGR out once
+    return check_launch("k_nv12_to_bgr");
 }
 
 // (re)builds the remap #1 tap table of view i for the caller's row pitch; stream-ordered before the kernels that read it
@@ -1189,6 +1287,12 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
     int ws[MAXV], hs[MAXV];
     int r = sync_tile_lists(s);
     if (r != VSB_OK) return r;
+    const uint8_t *bgr_ptrs[MAX_BATCH * MAXV];
+    if (!warped && s->in_format == VSB_IN_NV12) {
+        r = launch_nv12(s, v0, v1, n_frames, d_srcs, src_pitch, st, bgr_ptrs);
+        if (r != VSB_OK) return r;
+        d_srcs = bgr_ptrs; src_pitch = s->nv_pitch;
+    }
     if (!warped) {
         // table-driven remap #1 whenever the caller's frames allow aligned 32-bit window loads
         bool tab = remap_variant() >= 0 && src_pitch % 4 == 0;
@@ -1387,7 +1491,7 @@ int vsb_destroy(vsb_stitcher *s)
     for (int k = 0; k < MAXL; ++k) cudaFree(s->dw[k]);
     cudaFree(s->d_plan);
     cudaFree(s->d_blend_views); cudaFree(s->d_coarse_views); cudaFree(s->d_down2_tiles); cudaFree(s->C2);
-    cudaFree(s->stage_src); cudaFree(s->stage_out);
+    cudaFree(s->stage_src); cudaFree(s->stage_out); cudaFree(s->nv_bgr); cudaFree(s->stage_nv12);
     cudaFreeHost(s->pin_src); cudaFreeHost(s->pin_out);
     if (s->setup_stream) cudaStreamDestroy(s->setup_stream);
     if (s->mesh_stream) cudaStreamDestroy(s->mesh_stream);
@@ -1646,6 +1750,29 @@ int vsb_set_mesh(vsb_stitcher *s, int i, const float *mesh_x, const float *mesh_
     return VSB_OK;
 }
 
+int vsb_set_formats(vsb_stitcher *s, int input_format, int output_format)
+{
+    REQ(s, VSB_ERR_INVALID, "set_formats: null handle");
+    REQ(input_format == VSB_IN_BGR8 || input_format == VSB_IN_NV12, VSB_ERR_INVALID, "set_formats: unknown input format %d", input_format);
+    REQ(output_format == VSB_OUT_S16C3 || output_format == VSB_OUT_U8C3, VSB_ERR_INVALID, "set_formats: unknown output format %d", output_format);
+    REQ(output_format == VSB_OUT_S16C3 || !s->finalized || s->fast, VSB_ERR_STATE, "set_formats: CV_8UC3 output needs num_bands >= 3");
+    DeviceGuard g(s->device);
+    CK(cudaDeviceSynchronize());
+    s->in_format = input_format; s->out_format = output_format;
+    return VSB_OK;
+}
+
+int vsb_nv12_to_bgr(const uint8_t *d_nv12, int w, int h, size_t pitch, uint8_t *d_bgr, size_t bgr_pitch, void *stream)
+{
+    REQ(d_nv12 && d_bgr, VSB_ERR_INVALID, "nv12_to_bgr: null argument");
+    REQ(w > 0 && h > 0 && (w & 1) == 0 && (h & 1) == 0 && pitch >= (size_t)w && bgr_pitch >= (size_t)w * 3, VSB_ERR_INVALID, "nv12_to_bgr: bad sizes");
+    Nv12Params p;
+    std::memset(&p, 0, sizeof(p));
+    p.src[0] = d_nv12; p.dst[0] = d_bgr; p.pitch = pitch; p.dst_pitch = bgr_pitch; p.w = w; p.h = h;
+    k_nv12_to_bgr<<<dim3(((w + 3) / 4 + 31) / 32, (h / 2 + 7) / 8, 1), dim3(32, 8), 0, (cudaStream_t)stream>>>(p);
+    return check_launch("k_nv12_to_bgr");
+}
+
 int vsb_feed(vsb_stitcher *s, int i, const uint8_t *d_bgr, size_t pitch, void *stream)
 {
     REQ(s && d_bgr, VSB_ERR_INVALID, "feed: null argument");
@@ -1680,6 +1807,8 @@ int vsb_blend(vsb_stitcher *s, int16_t *d_out, size_t out_pitch, void *stream)
     REQ(s && d_out, VSB_ERR_INVALID, "blend: null argument");
     REQ(s->finalized, VSB_ERR_STATE, "blend: prepare + init_view for every view must come first");
     int r;
+    REQ(s->out_format == VSB_OUT_S16C3 || s->fast, VSB_ERR_STATE, "blend: CV_8UC3 output needs num_bands >= 3");
+    REQ(out_pitch >= (size_t)s->roi_final[2] * (s->out_format == VSB_OUT_U8C3 ? 3 : 6), VSB_ERR_INVALID, "blend: output pitch too small");
     DeviceGuard g(s->device);
     int16_t *outs[1] = {d_out};
     r = launch_back(s, 1, outs, out_pitch, (cudaStream_t)stream);
@@ -1692,6 +1821,8 @@ int vsb_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, siz
     REQ(s && d_srcs && d_outs, VSB_ERR_INVALID, "compose: null argument");
     REQ(n_frames >= 1 && n_frames <= s->cfg.max_batch, VSB_ERR_INVALID, "compose: n_frames must be 1..max_batch (%d)", s->cfg.max_batch);
     REQ(s->shard_rank < 0, VSB_ERR_STATE, "compose: handle is view-sharded; feed the owned views, exchange, then blend");
+    REQ(s->out_format == VSB_OUT_S16C3 || s->fast, VSB_ERR_STATE, "compose: CV_8UC3 output needs num_bands >= 3");
+    REQ(out_pitch >= (size_t)s->roi_final[2] * (s->out_format == VSB_OUT_U8C3 ? 3 : 6), VSB_ERR_INVALID, "compose: output pitch too small");
     int r = ready_for_frames(s);
     if (r != VSB_OK) return r;
     DeviceGuard g(s->device);
@@ -1717,12 +1848,23 @@ int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs
     const int n = s->cfg.num_views, F = s->cfg.max_batch;
     const int sw = s->v[0].src_w, sh = s->v[0].src_h;
     for (int i = 1; i < n; ++i) REQ(s->v[i].src_w == sw && s->v[i].src_h == sh, VSB_ERR_INVALID, "compose_host: all views must share one source size");
-    REQ(src_pitch >= (size_t)sw * 3 && out_pitch >= (size_t)s->roi_final[2] * 6, VSB_ERR_INVALID, "compose_host: pitch too small");
-    if (!s->stage_src) {
+    const bool nv12 = s->in_format == VSB_IN_NV12;
+    const size_t opx = s->out_format == VSB_OUT_U8C3 ? 3 : 6;     // bytes per output pixel
+    const size_t src_row = nv12 ? (size_t)sw : (size_t)sw * 3;    // bytes per source row, rows per source frame
+    const int src_rows = nv12 ? sh * 3 / 2 : sh;
+    REQ(src_pitch >= src_row && out_pitch >= (size_t)s->roi_final[2] * opx, VSB_ERR_INVALID, "compose_host: pitch too small");
+    REQ(!nv12 || ((sw | sh) & 1) == 0, VSB_ERR_INVALID, "compose_host: NV12 needs even source sizes");
+    if (!nv12 && !s->stage_src) {
         s->stage_src_pitch = align_up((size_t)sw * 3, 4);  // tight rows: a packed host frame moves as ONE contiguous DMA
         s->stage_src_frame = align_up(s->stage_src_pitch * sh + 16, 256);
         CK(cudaMalloc(&s->stage_src, s->stage_src_frame * n * F));
     }
+    if (nv12 && !s->stage_nv12) {
+        s->stage_nv12_frame = align_up(align_up((size_t)sw, 4) * src_rows + 16, 256);
+        CK(cudaMalloc(&s->stage_nv12, s->stage_nv12_frame * n * F));
+    }
+    const size_t st_pitch = nv12 ? align_up((size_t)sw, 4) : s->stage_src_pitch, st_frame = nv12 ? s->stage_nv12_frame : s->stage_src_frame;
+    uint8_t *st_base = nv12 ? s->stage_nv12 : s->stage_src;
     // the device-side panorama staging uses the HOST pitch, so each download is one contiguous DMA (a 2-D copy of 600+
     // rows whose pitches differ by a few bytes runs at a fraction of the link rate)
     if (!s->stage_out || s->stage_out_pitch != out_pitch) {
@@ -1746,24 +1888,24 @@ int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs
     for (int f = 0; f < n_frames; ++f) {
         const uint8_t *d_srcs[MAXV];
         for (int i = 0; i < n; ++i) {
-            uint8_t *d = s->stage_src + s->stage_src_frame * (size_t)(f * n + i);
-            if (src_pitch == s->stage_src_pitch)
-                CK(cudaMemcpyAsync(d, h_srcs[f * n + i], src_pitch * sh, cudaMemcpyHostToDevice, s->in_stream));
+            uint8_t *d = st_base + st_frame * (size_t)(f * n + i);
+            if (src_pitch == st_pitch)
+                CK(cudaMemcpyAsync(d, h_srcs[f * n + i], src_pitch * src_rows, cudaMemcpyHostToDevice, s->in_stream));
             else
-                CK(cudaMemcpy2DAsync(d, s->stage_src_pitch, h_srcs[f * n + i], src_pitch, (size_t)sw * 3, sh, cudaMemcpyHostToDevice, s->in_stream));
+                CK(cudaMemcpy2DAsync(d, st_pitch, h_srcs[f * n + i], src_pitch, src_row, src_rows, cudaMemcpyHostToDevice, s->in_stream));
             d_srcs[i] = d;
         }
         CK(cudaEventRecord(s->ev_in[f], s->in_stream));
         CK(cudaStreamWaitEvent(s->io_stream, s->ev_in[f], 0));
         int16_t *d_out = (int16_t *)((char *)s->stage_out + s->stage_out_frame * f);
-        r = vsb_compose(s, 1, d_srcs, s->stage_src_pitch, &d_out, s->stage_out_pitch, s->io_stream);
+        r = vsb_compose(s, 1, d_srcs, st_pitch, &d_out, s->stage_out_pitch, s->io_stream);
         if (r != VSB_OK) { cudaDeviceSynchronize(); return r; }
         CK(cudaEventRecord(s->ev_done[f], s->io_stream));
         CK(cudaStreamWaitEvent(s->out_stream, s->ev_done[f], 0));
-        if (out_pitch == (size_t)s->roi_final[2] * 6)  // packed host rows: one contiguous DMA
+        if (out_pitch == (size_t)s->roi_final[2] * opx)  // packed host rows: one contiguous DMA
             CK(cudaMemcpyAsync(h_outs[f], d_out, out_pitch * (size_t)s->roi_final[3], cudaMemcpyDeviceToHost, s->out_stream));
-        else                                            // padded host rows: leave the caller's padding untouched
-            CK(cudaMemcpy2DAsync(h_outs[f], out_pitch, d_out, s->stage_out_pitch, (size_t)s->roi_final[2] * 6, s->roi_final[3], cudaMemcpyDeviceToHost, s->out_stream));
+        else                                              // padded host rows: leave the caller's padding untouched
+            CK(cudaMemcpy2DAsync(h_outs[f], out_pitch, d_out, s->stage_out_pitch, (size_t)s->roi_final[2] * opx, s->roi_final[3], cudaMemcpyDeviceToHost, s->out_stream));
     }
     CK(cudaStreamSynchronize(s->out_stream));
     CK(cudaStreamSynchronize(s->io_stream));

@@ -39,3 +39,18 @@ def mesh(W, H, rows=10, cols=10, phase=0.0):
     dx = 6.0 * np.sin(math.pi * i / 9 + phase) * np.cos(math.pi * j / 9)
     dy = 4.0 * np.sin(math.pi * j / 9 + phase) * np.ones_like(i)
     return (mx + dx.astype(np.float32)).astype(np.float32), (my + dy.astype(np.float32)).astype(np.float32)
+
+
+def frame_nv12(view, frame_idx, w, h):
+    """Synthetic NV12 wire frame (A/defs.h:10-17): (h * 3 // 2, w) uint8 -- luma from frame(), smooth chroma plus noise, with
+    values outside the nominal [16, 235] / [16, 240] ranges so the saturating branches of the conversion are exercised."""
+    rng = np.random.default_rng(4321 + 1000 * frame_idx + view)
+    bgr = frame(view, frame_idx, w, h)
+    out = np.empty((h * 3 // 2, w), np.uint8)
+    out[:h] = np.clip(bgr[..., 1].astype(np.int32) + rng.integers(-40, 41, (h, w)), 0, 255).astype(np.uint8)
+    yy, xx = np.mgrid[0:h // 2, 0:w // 2]
+    u = 128 + 100 * np.sin(xx / 37.0 + view) + rng.integers(-30, 31, (h // 2, w // 2))
+    v = 128 + 100 * np.cos(yy / 29.0 - view) + rng.integers(-30, 31, (h // 2, w // 2))
+    out[h:, 0::2] = np.clip(u, 0, 255).astype(np.uint8)
+    out[h:, 1::2] = np.clip(v, 0, 255).astype(np.uint8)
+    return out
