@@ -33,6 +33,8 @@ WORKLOADS = {
                  name="6x1080p->3840 spherical, CPW on, 5 bands"),
     "cfg3": dict(n_views=6, src_w=1920, src_h=1080, pano_width=7680, num_bands=5, enable_local=True, projection=0,
                  name="6x1080p->7680 spherical, CPW on, 5 bands"),
+    "cfg4": dict(n_views=12, src_w=3840, src_h=2160, pano_width=15360, num_bands=5, enable_local=True, projection=0,
+                 name="12x2160p->15360 spherical, CPW on, 5 bands"),
     "cfg1": dict(n_views=2, src_w=1280, src_h=720, pano_width=4021, num_bands=5, enable_local=False, projection=0,
                  name="2x720p->4021 spherical, CPW off, 5 bands"),
     "tiny": dict(n_views=4, src_w=320, src_h=240, pano_width=1024, num_bands=3, enable_local=True, projection=0,
@@ -389,6 +391,41 @@ def main():
                "d2h_bytes_per_step": F * OW * OH * 6, "steps": Ke,
                "api": "vsb_compose_host: pinned host frames in, host panoramas out; upload / compose / download pipelined per frame"}
 
+    # ---- the same through the wire / consumer formats: NV12 frames in as the capture boards send them
+    #      (the reference converts them on the CPU before its upload, A/networking.cpp:46), CV_8UC3 panoramas out (the reference
+    #      converts on the GPU before its download, A/timed.cpp:250-251): half the bytes in each direction over PCIe
+    e2e_wire = None
+    if not args.no_e2e and cfg["src_w"] % 2 == 0 and cfg["src_h"] % 2 == 0 and nb >= 3:
+        sw_, sh_ = cfg["src_w"], cfg["src_h"]
+        nv_sets = []
+        for fs in host_sets:
+            one = []
+            for t in fs:
+                nvf = torch.empty((sh_ * 3 // 2, sw_), dtype=torch.uint8)
+                nvf[:sh_] = t[..., 1]
+                nvf[sh_:, 0::2] = t[::2, ::2, 0]
+                nvf[sh_:, 1::2] = t[::2, ::2, 2]
+                one.append(nvf.pin_memory())
+            nv_sets.append(one)
+        h_outs8 = [torch.empty((OH, OW, 3), dtype=torch.uint8).pin_memory() for _ in range(F)]
+        st.set_formats(B.IN_NV12, B.OUT_U8C3)
+        def wire_call(s0):
+            srcs = [nv_sets[(s0 + j) % n_sets][i].data_ptr() for j in range(F) for i in range(n)]
+            st.compose_host(srcs, sw_, [o.data_ptr() for o in h_outs8], OW * 3)
+        for w in range(3):
+            wire_call(w)
+        Ke = max(3, min(K, 40))
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(Ke):
+            wire_call(k % n_sets)
+        torch.cuda.synchronize()
+        dt = vsb200.dist.reduce_step_time(time.perf_counter() - t0, dist if world > 1 else None, "cuda")
+        st.set_formats(B.IN_BGR8, B.OUT_S16C3)
+        e2e_wire = {"value": world * F * Ke / dt, "unit": "frames/s", "h2d_bytes_per_step": F * n * sw_ * sh_ * 3 // 2,
+                    "d2h_bytes_per_step": F * OW * OH * 3, "steps": Ke,
+                    "api": "vsb_set_formats(VSB_IN_NV12, VSB_OUT_U8C3) + vsb_compose_host: NV12 host frames in, CV_8UC3 host panoramas out"}
+
     # ---- CPU baseline on the host cores, rank 0 at N=1 only, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -405,7 +442,7 @@ def main():
             "config": {"workload": cfg["name"], "frames_per_step": F, "ring_frame_sets": n_sets,
                        "l2_policy": f"inputs larger than L2: ring of {n_sets} frame sets = {n_sets * n * cfg['src_w'] * cfg['src_h'] * 3 / 1e6:.0f} MB",
                        "pano": f"{OW}x{OH} CV_16SC3", "bands": nb, "multi_gpu": "frame-level replicas, no collective" if world > 1 else "single GPU"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
+            "clocks": clocks, "e2e": e2e, "e2e_wire": e2e_wire, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
             "roofline": roofline, "roofline_path": roofline_path, "kernels": kernels, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -194,6 +194,21 @@ def test_compose_matches_oracle(cuda, og, case, inject):
     _eq(grig.feed_blend(frames), want, "feed + blend")
 
 
+def test_full_size_config4_compose(cuda, og):
+    """BASELINE.json configs[3] at full size: 12 x 3840x2160 -> 15360-wide spherical panorama, CPW on, 5 bands (maximum sizes:
+    ~125 MPx of warped views per frame).  One frame, bit-exact against oracle-G."""
+    import vsb200
+    kw = dict(n_views=12, src_w=3840, src_h=2160, pano_width=15360, num_bands=5, enable_local=True)
+    CASES["cfg4"] = kw
+    orig, grig, _ = _rigs("cfg4", inject=False)
+    assert grig.roi_final == orig.roi_final and grig.roi_final[2] >= 15359
+    frames = [vsb200.synth.frame(i, 0, kw["src_w"], kw["src_h"]) for i in range(kw["n_views"])]
+    want, want_mask = orig.compose(frames)
+    got = grig.compose([frames])[0]
+    _eq(got, want, "config 4 panorama (CV_16SC3)")
+    assert grig.st.last_launch_count() == 7  # K1 K2 down2 down1(L3: too large for shared memory) down_tail coarse blend
+
+
 def test_batched_compose_and_mesh_swap(cuda, og):
     import vsb200
     orig, grig, kw = _rigs("small4", inject=False, max_batch=3)

@@ -415,13 +415,13 @@ __global__ void __launch_bounds__(D1_TX *D1_TY) k_down1(const __grid_constant__ 
 // one CTA keeps every level it produces in shared memory (level k + 1 is computed from the shared copy of level k) and
 // writes each level out once.  Replaces nb - 2 k_down1 launches whose cost was launch latency, not work.
 struct DownTailView {
-    const uint8_t *g2;           // level 2, frame 0
-    uint8_t *g[MAXL];            // level k (3 .. nb), frame 0
+    const uint8_t *g2;           // level k0 (the first level this launch reads; 2 unless the planes are very large), frame 0
+    uint8_t *g[MAXL];            // level k (k0 + 1 .. nb), frame 0
     size_t g2_fs, fs[MAXL];      // frame strides (bytes)
-    int w2, h2;
+    int w2, h2;                  // size of level k0
 };
 struct DownTailParams {
-    int nb;
+    int nb, k0;
     DownTailView v[MAXV];
 };
 constexpr int DT_TX = 32, DT_TY = 32;
@@ -490,10 +490,10 @@ __global__ void __launch_bounds__(DT_TX *DT_TY) k_down_tail(const __grid_constan
     int w = V.w2, h = V.h2;
     uint8_t *level = dt_smem;
     const uint8_t *src = V.g2 + (size_t)f * V.g2_fs + (size_t)c * w * h;
-    for (int k = 2; k < P.nb; ++k) {
+    for (int k = P.k0; k < P.nb; ++k) {
         const int wd = w >> 1, hd = h >> 1;
         uint8_t *dst_g = V.g[k + 1] + (size_t)f * V.fs[k + 1] + (size_t)c * wd * hd;
-        if (k == 2) down_plane_cta<true>(src, w, h, level, dst_g);
+        if (k == P.k0) down_plane_cta<true>(src, w, h, level, dst_g);
         else down_plane_cta<false>(src, w, h, level, dst_g);
         __syncthreads();
         src = level;

@@ -1114,41 +1114,10 @@ static int launch_down2(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
     return check_launch("k_down2");
 }
 
-// K3b: Gaussian levels 3..nb of views [v0, v1) (tiny planes), one launch per level
-static int launch_down1(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStream_t st)
+// one more pyrDown level (k -> k + 1) of views [v0, v1) on the u8 planes
+static int launch_down1_level(vsb_stitcher *s, int k, int v0, int v1, int n_frames, cudaStream_t st)
 {
-    const int nb = s->nb;
-    {   // every level of a plane fits in shared memory (true up to ~8k-wide panoramas): one launch, one CTA per plane
-        size_t smem = 0;
-        double bytes = 0;
-        for (int i = v0; i < v1; ++i) {
-            size_t need = 0;
-            for (int k = 3; k <= nb; ++k) need += align_up((size_t)(s->v[i].bw >> k) * (s->v[i].bh >> k), 16);
-            smem = std::max(smem, need);
-            bytes += 3.0 * (s->v[i].bw >> 2) * (s->v[i].bh >> 2);
-            for (int k = 3; k <= nb; ++k) bytes += 3.0 * (s->v[i].bw >> k) * (s->v[i].bh >> k);
-        }
-        if (smem <= 200 * 1024 && v1 > v0) {
-            if (smem > s->down_tail_smem) {
-                CK(cudaFuncSetAttribute(k_down_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                s->down_tail_smem = smem;
-            }
-            DownTailParams p;
-            std::memset(&p, 0, sizeof(p));
-            p.nb = nb;
-            for (int i = v0; i < v1; ++i) {
-                const View &V = s->v[i];
-                DownTailView &D = p.v[i - v0];
-                D.g2 = V.G2; D.g2_fs = V.g2_frame_stride; D.w2 = V.bw >> 2; D.h2 = V.bh >> 2;
-                for (int k = 3; k <= nb; ++k) { D.g[k] = V.Gu[k]; D.fs[k] = V.gu_frame_stride[k]; }
-            }
-            k_down_tail<<<dim3(v1 - v0, 3, n_frames), dim3(DT_TX, DT_TY), smem, st>>>(p);
-            ++s->launches;
-            prof_stage(s, st, "down_tail", bytes * n_frames);  // level 2 in once, levels 3..nb out once
-            return check_launch("k_down_tail");
-        }
-    }
-    for (int k = 2; k < nb; ++k) {
+    {
         Down1Params p;
         std::memset(&p, 0, sizeof(p));
         double bytes = 0;
@@ -1168,6 +1137,57 @@ static int launch_down1(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
         ++s->launches;
         static const char *names[MAXL] = {"", "", "down1_L3", "down1_L4", "down1_L5", "down1_L6", "down1_L7", ""};
         prof_stage(s, st, names[k], bytes * n_frames);
+    }
+    return VSB_OK;
+}
+
+// K3b: Gaussian levels 3..nb of views [v0, v1) (tiny planes), one launch per level
+static int launch_down1(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStream_t st)
+{
+    const int nb = s->nb;
+    // Levels whose outputs fit in shared memory together (all of them up to ~8k-wide panoramas, all but level 3 at 16k) are
+    // produced by ONE k_down_tail launch starting at level k0; the levels before it take one k_down1 launch each.
+    int k0 = 2;
+    size_t smem = 0;
+    for (; k0 < nb; ++k0) {
+        smem = 0;
+        for (int i = v0; i < v1; ++i) {
+            size_t need = 0;
+            for (int k = k0 + 1; k <= nb; ++k) need += align_up((size_t)(s->v[i].bw >> k) * (s->v[i].bh >> k), 16);
+            smem = std::max(smem, need);
+        }
+        if (smem <= 200 * 1024) break;
+    }
+    if (k0 < nb && v1 > v0) {
+        double bytes = 0;
+        for (int i = v0; i < v1; ++i)
+            for (int k = k0; k <= nb; ++k) bytes += 3.0 * (s->v[i].bw >> k) * (s->v[i].bh >> k);
+        if (smem > s->down_tail_smem) {
+            CK(cudaFuncSetAttribute(k_down_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            s->down_tail_smem = smem;
+        }
+        DownTailParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.nb = nb; p.k0 = k0;
+        for (int i = v0; i < v1; ++i) {
+            const View &V = s->v[i];
+            DownTailView &D = p.v[i - v0];
+            D.g2 = V.Gu[k0]; D.g2_fs = V.gu_frame_stride[k0]; D.w2 = V.bw >> k0; D.h2 = V.bh >> k0;
+            for (int k = k0 + 1; k <= nb; ++k) { D.g[k] = V.Gu[k]; D.fs[k] = V.gu_frame_stride[k]; }
+        }
+        // stream order: the k_down1 launches for levels 2 .. k0 - 1 (below) come first
+        for (int k = 2; k < k0; ++k) {
+            int r = launch_down1_level(s, k, v0, v1, n_frames, st);
+            if (r != VSB_OK) return r;
+        }
+        k_down_tail<<<dim3(v1 - v0, 3, n_frames), dim3(DT_TX, DT_TY), smem, st>>>(p);
+        ++s->launches;
+        prof_stage(s, st, "down_tail", bytes * n_frames);  // level k0 in once, levels k0 + 1 .. nb out once
+        return check_launch("k_down_tail");
+    }
+    for (int k = 2; k < nb; ++k) {
+        int r = launch_down1_level(s, k, v0, v1, n_frames, st);
+        if (r != VSB_OK) return r;
     }
     return check_launch("k_down1");
 }
