@@ -232,7 +232,7 @@ def test_batched_compose_and_mesh_swap(cuda, og):
     _eq(grig.compose([fr[2]])[0], orig.compose(fr[2])[0], "after double mesh swap")
 
 
-@pytest.mark.parametrize("variant,pad", [(-1, 0), (0, 0), (0, 1), (0, 4)])
+@pytest.mark.parametrize("variant,pad", [(-1, 0), (0, 0), (1, 0), (0, 1), (1, 4)])
 def test_remap_kernel_variants(cuda, og, tmp_path, variant, pad):
     """Every form of the remap kernels (coordinate-driven, table-driven scalar / packed-pair / conversion-unit mixes) gives the
     oracle's frames; pad = 1 makes the caller's rows unaligned (falls back to the coordinate-driven kernels)."""

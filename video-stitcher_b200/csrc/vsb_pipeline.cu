@@ -224,23 +224,55 @@ struct Stage1TabParams {
 };
 
 // One CTA = one 128 x 8 tile for ALL frames of the submission: the table entries of the thread's 4 pixels are loaded once
-// and stay in registers while the frames stream through (window loads -> fmul / fma chain -> 12-byte store per frame).
-__global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage1_tab(const __grid_constant__ Stage1TabParams p)
+// and stay in registers while the frames stream through (window loads -> fmul / fma chain -> store per frame).
+// LANES = false: a thread owns 4 consecutive pixels (128-bit table loads, one 12-byte store).
+// LANES = true : a thread owns pixels lane, lane + 32, lane + 64, lane + 96 of the tile row, so the 32 window loads of one
+//                instruction are ONE source-pixel step apart instead of four and fall into two or three cache lines instead
+//                of five or six (the kernel is bound by L1 wavefronts, not by issue slots); the row is transposed through
+//                shared memory so that the stores stay full, coalesced words.
+#ifndef VSB_RM1_MINB
+#define VSB_RM1_MINB 4
+#endif
+template <bool LANES>
+__global__ void __launch_bounds__(RM_BX *RM_BY, VSB_RM1_MINB) k_remap_stage1_tab(const __grid_constant__ Stage1TabParams p)
 {
+    __shared__ unsigned sP[LANES ? RM_BY : 1][LANES ? RM_BX * RM_PX + 1 : 1];
     const unsigned tile = __ldg(p.tiles + blockIdx.x);
     const int vi = tile & 0xff;
     const Stage1TabView &V = p.v[vi];
-    const int x0 = ((int)((tile >> 8) & 0xfff) * RM_BX + threadIdx.x) * RM_PX, y = (int)(tile >> 20) * RM_BY + threadIdx.y;
-    if (x0 >= V.w || y >= V.h) return;
+    const int tx0 = (int)((tile >> 8) & 0xfff) * (RM_BX * RM_PX), y = (int)(tile >> 20) * RM_BY + threadIdx.y;
+    const int x0 = LANES ? tx0 + threadIdx.x : tx0 + threadIdx.x * RM_PX;
+    constexpr int XSTEP = LANES ? RM_BX : 1;
+    if (y >= V.h || (!LANES && x0 >= V.w)) return;  // LANES: the whole warp stays for the shared-memory transpose
     const size_t i = (size_t)y * V.tab.tab_pitch + x0;
-    const int4 o = __ldg((const int4 *)(V.tab.off + i));
-    const float4 A = __ldg((const float4 *)(V.tab.w + i)), B = __ldg((const float4 *)(V.tab.w + V.tab.plane + i));
-    const float4 C = __ldg((const float4 *)(V.tab.w + 2 * V.tab.plane + i)), D = __ldg((const float4 *)(V.tab.w + 3 * V.tab.plane + i));
-    const int off[RM_PX] = {o.x, o.y, o.z, o.w};
-    const float wa[RM_PX] = {A.x, A.y, A.z, A.w}, wb[RM_PX] = {B.x, B.y, B.z, B.w}, wc[RM_PX] = {C.x, C.y, C.z, C.w}, wd[RM_PX] = {D.x, D.y, D.z, D.w};
-    const bool slow = (o.x | o.y | o.z | o.w) < 0;
+    int off[RM_PX];
+    float wa[RM_PX], wb[RM_PX], wc[RM_PX], wd[RM_PX];
+    if (LANES) {
+#pragma unroll
+        for (int k = 0; k < RM_PX; ++k) {
+            const bool in = x0 + k * XSTEP < V.tab.tab_pitch;
+            off[k] = in ? __ldg(V.tab.off + i + k * XSTEP) : 0;
+            wa[k] = in ? __ldg(V.tab.w + i + k * XSTEP) : 0.f;
+            wb[k] = in ? __ldg(V.tab.w + V.tab.plane + i + k * XSTEP) : 0.f;
+            wc[k] = in ? __ldg(V.tab.w + 2 * V.tab.plane + i + k * XSTEP) : 0.f;
+            wd[k] = in ? __ldg(V.tab.w + 3 * V.tab.plane + i + k * XSTEP) : 0.f;
+        }
+    } else {
+        const int4 o = __ldg((const int4 *)(V.tab.off + i));
+        const float4 A = __ldg((const float4 *)(V.tab.w + i)), B = __ldg((const float4 *)(V.tab.w + V.tab.plane + i));
+        const float4 C = __ldg((const float4 *)(V.tab.w + 2 * V.tab.plane + i)), D = __ldg((const float4 *)(V.tab.w + 3 * V.tab.plane + i));
+        off[0] = o.x; off[1] = o.y; off[2] = o.z; off[3] = o.w;
+        wa[0] = A.x; wa[1] = A.y; wa[2] = A.z; wa[3] = A.w; wb[0] = B.x; wb[1] = B.y; wb[2] = B.z; wb[3] = B.w;
+        wc[0] = C.x; wc[1] = C.y; wc[2] = C.z; wc[3] = C.w; wd[0] = D.x; wd[1] = D.y; wd[2] = D.z; wd[3] = D.w;
+    }
+    const bool slow = (off[0] | off[1] | off[2] | off[3]) < 0;
+    // LANES: this thread stores words lane, lane + 32, lane + 64 of the 96-word (128-pixel) row; word j starts in pixel 4j / 3
+    int wp[3], wr[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { const int j = threadIdx.x + 32 * m; wp[m] = (4 * j) / 3; wr[m] = 8 * (4 * j - 3 * wp[m]); }
+    const int row_bytes = 3 * min(RM_BX * RM_PX, V.w - tx0);  // valid bytes of this tile row
     const int n = min(RM_PX, V.w - x0);
-    uint8_t *dst = V.P + (size_t)y * V.p_pitch + (size_t)x0 * 3;
+    uint8_t *dst = V.P + (size_t)y * V.p_pitch + (size_t)(LANES ? tx0 : x0) * 3;
 #pragma unroll 1
     for (int f = 0; f < p.n_frames; ++f, dst += V.p_frame_stride) {
         const uint8_t *src = p.src[f * p.n_views + vi - p.v0];
@@ -251,12 +283,26 @@ __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage1_tab(const __grid_
 #pragma unroll 1
             for (int k = 0; k < RM_PX; ++k) {
                 if (off[k] >= 0) continue;
-                const float fx = __ldg((const float *)((const char *)V.xmap + (size_t)y * V.map_pitch) + x0 + k);
-                const float fy = __ldg((const float *)((const char *)V.ymap + (size_t)y * V.map_pitch) + x0 + k);
+                const float fx = __ldg((const float *)((const char *)V.xmap + (size_t)y * V.map_pitch) + x0 + k * XSTEP);
+                const float fy = __ldg((const float *)((const char *)V.ymap + (size_t)y * V.map_pitch) + x0 + k * XSTEP);
                 px[k] = remap_gain_px_edge<true>(src, p.src_pitch, V.src_w, V.src_h, fx, fy, V.gain);
             }
         }
-        if (n == RM_PX) {  // 12 bytes = three aligned 32-bit stores
+        if (LANES) {
+            unsigned *row = sP[threadIdx.y];
+            __syncwarp();  // the previous frame's reads of this row are done
+#pragma unroll
+            for (int k = 0; k < RM_PX; ++k) row[threadIdx.x + k * XSTEP] = px[k];
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const int b0 = 4 * (threadIdx.x + 32 * m);
+                if (b0 >= row_bytes) continue;
+                const unsigned word = (row[wp[m]] >> wr[m]) | (row[wp[m] + 1] << (24 - wr[m]));
+                if (b0 + 4 <= row_bytes) *(unsigned *)(dst + b0) = word;
+                else for (int e = 0; b0 + e < row_bytes; ++e) dst[b0 + e] = (word >> (8 * e)) & 0xff;
+            }
+        } else if (n == RM_PX) {  // 12 bytes = three aligned 32-bit stores
             unsigned *d32 = (unsigned *)dst;
             d32[0] = px[0] | (px[1] << 24);
             d32[1] = (px[1] >> 8) | (px[2] << 16);
@@ -1239,12 +1285,13 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
     return check_launch("k_coarse / k_blend");
 }
 
-// which form of the remap kernels runs (both bit-identical): VSB_REMAP_VARIANT = -1 forces the coordinate-driven kernels
-// that also serve unaligned caller frames, anything else the table-driven ones
+// which form of the remap kernels runs (all bit-identical): VSB_REMAP_VARIANT = -1 forces the coordinate-driven kernels that
+// also serve unaligned caller frames; 0 / 1 = table-driven with 4 consecutive pixels per thread / lane-interleaved pixels
+// (default, ~3 % faster: fewer cache lines per window load)
 static int remap_variant()
 {
     static int v = -2;
-    if (v < -1) { const char *e = std::getenv("VSB_REMAP_VARIANT"); v = e ? std::max(-1, std::min(3, std::atoi(e))) : 0; }
+    if (v < -1) { const char *e = std::getenv("VSB_REMAP_VARIANT"); v = e ? std::max(-1, std::min(3, std::atoi(e))) : 1; }
     return v;
 }
 
@@ -1344,7 +1391,8 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
             p.v0 = v0; p.n_views = n; p.src_pitch = (unsigned)src_pitch; p.n_frames = n_frames;
             for (int f = 0; f < n_frames; ++f) for (int j = 0; j < n; ++j) p.src[f * n + j] = d_srcs[f * n + j];
             if (count > 0) {
-                k_remap_stage1_tab<<<(unsigned)count, dim3(RM_BX, RM_BY), 0, st>>>(p);
+                if (remap_variant() & 1) k_remap_stage1_tab<true><<<(unsigned)count, dim3(RM_BX, RM_BY), 0, st>>>(p);
+                else k_remap_stage1_tab<false><<<(unsigned)count, dim3(RM_BX, RM_BY), 0, st>>>(p);
             }
         } else {
             Stage1Params p;
