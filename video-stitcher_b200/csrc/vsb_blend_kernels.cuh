@@ -578,6 +578,14 @@ __global__ void __launch_bounds__(C_THREADS) k_coarse(const __grid_constant__ Co
             const uint8_t *g = V.g[j] + (size_t)f * V.g_fs[j] + (size_t)c * w * h;
             const int vx0 = (X0 >> j) + Gm.a_lo[j] - (V.x_tl >> k), vy0 = (Y0 >> j) + Gm.a_lo[j] - (V.y_tl >> k);
             uint8_t *dst = G + Gm.g_off[j];
+            if (n == CT && vx0 >= 0 && vx0 + CT <= w && ((((size_t)(g + vx0)) | (size_t)w) & 3) == 0) {
+                // level 2, region inside the plane: 16 aligned words per row instead of 64 byte loads
+                for (int i = t; i < CT * (CT / 4); i += C_THREADS) {
+                    const int r = i / (CT / 4), q4 = i - r * (CT / 4);
+                    ((unsigned *)dst)[i] = __ldg((const unsigned *)(g + (size_t)min(max(vy0 + r, 0), h - 1) * w + vx0) + q4);
+                }
+                continue;
+            }
             for (int r = warp; r < n; r += C_THREADS / 32) {
                 const uint8_t *row = g + (size_t)min(max(vy0 + r, 0), h - 1) * w;
                 for (int q = lane; q < n; q += 32) dst[r * n + q] = (uint8_t)ldg_u8(row + min(max(vx0 + q, 0), w - 1));
