@@ -143,6 +143,10 @@ public:
         check(vsb_set_maps(h_, i, (const float *)xmap.data, (const float *)ymap.data, xmap.cols, xmap.rows, xmap.step, 1, src.width, src.height));
     }
     void setGain(int i, double gain) { check(vsb_set_gain(h_, i, (float)gain)); }
+    /* wire format in / consumer format out: VSB_IN_NV12 = the capture boards' NV12 frames (cv::cvtColor(CV_YUV2BGR_NV12),
+       A/networking.cpp:46, runs on the device); VSB_OUT_U8C3 = the consumer's mat.convertTo(mat_8u, CV_8U) (A/timed.cpp:250)
+       fused into blend(): gpuOut is then CV_8UC3 */
+    void setFormats(int input_format, int output_format) { check(vsb_set_formats(h_, input_format, output_format)); }
 
     /* void feed_online(cuda::GpuMat &gpu_img, int img_num, cuda::Stream &stream): gpu_img = warped CV_8UC3 view */
     void feed_online(const DeviceMat &gpu_img, int img_num, Stream stream)

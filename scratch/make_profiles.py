@@ -6,7 +6,7 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r01b"
 frames_per_launch = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 G, P = "gpurun_out", "profiles"
 os.makedirs(P, exist_ok=True)
-for f in ("bench.json", "bench_reference.json", "launches.csv"):
+for f in ("bench.json", "bench_reference.json", "launches.csv", "bench_cfg3.json", "bench_cfg4.json", "bench_n2_replicas.json"):
     src = os.path.join(G, f"{tag}_{f}")
     if os.path.exists(src):
         open(os.path.join(P, f"{tag}_{f}"), "w").write(open(src).read())
@@ -18,7 +18,7 @@ for r in rows[1:]:
     if r[ki] == "Kernel Name": continue
     try: tot[r[ki]] = tot.get(r[ki], [0, 0.0]); tot[r[ki]][0] += 1; tot[r[ki]][1] += float(r[vi].replace(",", ""))
     except ValueError: pass
-mine = {k: v for k, v in tot.items() if k.startswith("k_") or "vsb" in k}
+mine = {k: v for k, v in tot.items() if k.startswith("k_") or k.startswith("void k_") or "vsb" in k}
 s = sum(v[1] for v in mine.values())
 with open(os.path.join(P, f"{tag}_launch_shares.txt"), "w") as fh:
     fh.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3` (cold-cache, serialised: compare SHARES)\n")
@@ -31,7 +31,7 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem']
 traffic = {"note": f"dram__bytes_read.sum + dram__bytes_write.sum of one launch from ncu --set full --clock-control none ({tag}); bench.py scales by frames per launch", "kernels": {}}
-names = {"k_blend": "blend", "k_remap_stage1": "remap_stage1", "k_remap_stage2": "remap_stage2", "k_down2": "down2", "k_coarse": "coarse", "k_down1": "down1_L3"}
+names = {"k_blend": "blend", "k_remap_stage1_tab": "remap_stage1", "k_remap_stage2_tab": "remap_stage2", "k_down2": "down2", "k_coarse": "coarse", "k_down_tail": "down_tail"}
 with open(os.path.join(P, f"{tag}_ncu_full_summary.txt"), "w") as fh:
     for k, short in names.items():
         rep = os.path.join(G, f"{tag}_prof_{k}.ncu-rep")
