@@ -33,6 +33,10 @@ WORKLOADS = {
                  name="6x1080p->3840 spherical, CPW on, 5 bands"),
     "cfg3": dict(n_views=6, src_w=1920, src_h=1080, pano_width=7680, num_bands=5, enable_local=True, projection=0,
                  name="6x1080p->7680 spherical, CPW on, 5 bands"),
+    # BASELINE.json configs[4]: config 2 with the recalibration thread publishing a new CPW mesh while frames are composed
+    # (A/timed.cpp:414-463 re-solves every RECALIB_DEL = 1000 ms; here every `recalib_ms` to stress the overlap)
+    "cfg5": dict(n_views=6, src_w=1920, src_h=1080, pano_width=3840, num_bands=5, enable_local=True, projection=0, recalib_ms=20,
+                 name="6x1080p->3840 spherical, CPW on, 5 bands, mesh re-installed every 20 ms by a second host thread"),
     "cfg4": dict(n_views=12, src_w=3840, src_h=2160, pano_width=15360, num_bands=5, enable_local=True, projection=0,
                  name="12x2160p->15360 spherical, CPW on, 5 bands"),
     "cfg1": dict(n_views=2, src_w=1280, src_h=720, pano_width=4021, num_bands=5, enable_local=False, projection=0,
@@ -316,6 +320,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # config 5: a second host thread keeps publishing alternating meshes (vsb_set_mesh is thread-safe and double buffered:
+    # the kernels that build the maps and the tap table run on the handle's mesh stream while the compose stream keeps going)
+    recal = {"stop": False, "installs": 0}
+    recal_thread = None
+    if cfg.get("recalib_ms"):
+        meshes = [[S.mesh(info.view_roi[i][2], info.view_roi[i][3], phase=ph) for i in range(n)] for ph in (0.0, 0.7)]
+        def recalibrate():
+            k = 0
+            while not recal["stop"]:
+                for i in range(n):
+                    mx, my = meshes[k & 1][i]
+                    st.set_mesh(i, mx.ctypes.data, my.ctypes.data, mx.shape[0], mx.shape[1])
+                recal["installs"] += 1
+                k += 1
+                time.sleep(cfg["recalib_ms"] / 1000.0)
+        recal_thread = threading.Thread(target=recalibrate, daemon=True)
+        recal_thread.start()
+
     for w in range(W):
         calls[w % n_sets]()
     launches_per_step = st.last_launch_count()
@@ -341,6 +363,10 @@ def main():
         torch.cuda.synchronize()
         t_wall1 = time.time()
     sampler.stop()
+    if recal_thread is not None:
+        recal["stop"] = True
+        recal_thread.join()
+        torch.cuda.synchronize()
     clocks = sampler.summary(t_wall0, t_wall1)
     fps = world * F * K / (ms / 1000.0)
 
@@ -441,7 +467,7 @@ def main():
             "dtype": "u8/s16 (fp32 taps)", "data": "synthetic",
             "config": {"workload": cfg["name"], "frames_per_step": F, "ring_frame_sets": n_sets,
                        "l2_policy": f"inputs larger than L2: ring of {n_sets} frame sets = {n_sets * n * cfg['src_w'] * cfg['src_h'] * 3 / 1e6:.0f} MB",
-                       "pano": f"{OW}x{OH} CV_16SC3", "bands": nb, "multi_gpu": "frame-level replicas, no collective" if world > 1 else "single GPU"},
+                       "pano": f"{OW}x{OH} CV_16SC3", "bands": nb, **({"mesh_installs_during_run": recal["installs"]} if cfg.get("recalib_ms") else {}), "multi_gpu": "frame-level replicas, no collective" if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "e2e_wire": e2e_wire, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
             "roofline": roofline, "roofline_path": roofline_path, "kernels": kernels, "cpu_baseline": cpu,
         }

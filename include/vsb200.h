@@ -133,6 +133,15 @@ enum { VSB_OUT_S16C3 = 0, VSB_OUT_U8C3 = 1 };
 int vsb_set_formats(vsb_stitcher *s, int input_format, int output_format);
 /* cv::cvtColor(CV_YUV2BGR_NV12) on device buffers: IMG/src/color.cpp:8759-8819 (YUV420sp2RGB888Invoker<0,0>) */
 int vsb_nv12_to_bgr(const uint8_t *d_nv12, int w, int h, size_t pitch, uint8_t *d_bgr, size_t bgr_pitch, void *stream);
+/* ---- consumer epilogue: what the reference's consumer thread does on the CPU after its download
+ *      (A/timed.cpp:254-315), on the device: cv::resize(INTER_LINEAR) of the CV_8UC3 panorama to out_w x image_height
+ *      (vsb_consumer_image_height = A/timed.cpp:254-270), then VSB_CONSUME_RGB: COLOR_BGR2RGB (:291), d_out = image_height rows
+ *      of out_w RGB pixels; or VSB_CONSUME_I420: the image centred in a black out_w x out_h frame (:283-289) through
+ *      COLOR_BGR2YUV_I420 (:310-315), d_out = out_w * out_h * 3 / 2 contiguous bytes (what kvazaar is fed).  Bit-exact. ---- */
+enum { VSB_CONSUME_RGB = 0, VSB_CONSUME_I420 = 1 };
+int vsb_consumer_image_height(int src_w, int src_h, int out_w, int out_h, int keep_aspect);
+int vsb_consume(vsb_stitcher *s, const uint8_t *d_pano_u8, size_t pitch_bytes, int out_w, int out_h, int keep_aspect, int format,
+                uint8_t *d_out, size_t out_pitch_bytes, void *stream);
 /* ---- view-sharded multi-GPU mode (the reference is single-GPU, A/timed.cpp:495-496).  One process and
  *      one calibrated handle per GPU.  Rank r owns a canvas strip (its part of `blend`) and the views whose seam masks lie
  *      mostly inside it (their `stitch_online`).  Per frame: vsb_feed the owned views -> exchange the Gaussian sub-planes

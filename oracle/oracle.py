@@ -135,6 +135,40 @@ def s16_to_u8(a):
     return dst
 
 
+def resize_linear_u8c3(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    sh, sw, _ = src.shape
+    dst = np.empty((dh, dw, 3), np.uint8)
+    lib().og_resize_linear_u8c3(_p(src, C.c_uint8), sw, sh, C.c_size_t(sw * 3), _p(dst, C.c_uint8), dw, dh, C.c_size_t(dw * 3))
+    return dst
+
+
+def bgr_to_i420(bgr):
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    h, w, _ = bgr.shape
+    dst = np.empty(w * h * 3 // 2, np.uint8)
+    lib().og_bgr_to_i420(_p(bgr, C.c_uint8), w, h, C.c_size_t(w * 3), _p(dst, C.c_uint8))
+    return dst
+
+
+def consumer_image_height(src_w, src_h, out_w, out_h, keep_aspect=True):
+    return int(lib().og_consumer_image_height(src_w, src_h, out_w, out_h, int(keep_aspect)))
+
+
+def consume(pano_u8, out_w, out_h, fmt, keep_aspect=True):
+    """The consumer thread of 360_stitcher/timed.cpp:254-315 after the download: resize, then RGB (fmt 0) or the letter-boxed
+    out_w x out_h frame as I420 (fmt 1)."""
+    h, w, _ = pano_u8.shape
+    ih = consumer_image_height(w, h, out_w, out_h, keep_aspect)
+    img = resize_linear_u8c3(pano_u8, out_w, ih)
+    if fmt == 0:
+        return np.ascontiguousarray(img[..., ::-1])
+    canvas = np.zeros((out_h, out_w, 3), np.uint8)
+    row0 = out_h // 2 - ih // 2
+    canvas[row0:row0 + ih] = img
+    return bgr_to_i420(canvas)
+
+
 def resize_linear_u8c1(src, dw, dh):
     src = np.ascontiguousarray(src, np.uint8)
     sh, sw = src.shape

@@ -310,6 +310,78 @@ void og_s16_to_u8(const int16_t *src, size_t n, uint8_t *dst)
     for (size_t i = 0; i < n; ++i) dst[i] = sat_u8_int(src[i]);
 }
 
+/* ---- consumer epilogue (CPU code in the reference, downstream of the download: 360_stitcher/timed.cpp:254-315) ---- */
+/* coefficient tables of cv::hal::resize for INTER_LINEAR on 8U: IMG/src/resize.cpp:3933-3958 (x), 3991-4016 (y) */
+static void resize_tables(int ssize, int dsize, int clamp_x, int *ofs, short *coef)
+{
+    const double inv_scale = (double)dsize / ssize;   /* cv::resize: inv_scale_x = (double)dsize.width / ssize.width */
+    const double scale = 1. / inv_scale;              /* hal::resize: scale_x = 1. / inv_scale_x */
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= s;
+        if (clamp_x) {
+            if (s < 0) { f = 0; s = 0; }
+            if (s >= ssize - 1) { f = 0; s = ssize - 1; }
+        }
+        ofs[d] = s;
+        float c0 = 1.f - f, c1 = f;
+        long r0 = lrintf(c0 * 2048), r1 = lrintf(c1 * 2048);   /* saturate_cast<short>(float) = cvRound, round-half-even */
+        coef[2 * d] = (short)(r0 > 32767 ? 32767 : (r0 < -32768 ? -32768 : r0));
+        coef[2 * d + 1] = (short)(r1 > 32767 ? 32767 : (r1 < -32768 ? -32768 : r1));
+    }
+}
+void og_resize_linear_u8c3(const uint8_t *src, int sw, int sh, size_t sstep, uint8_t *dst, int dw, int dh, size_t dstep)
+{
+    int *xofs = (int *)malloc(sizeof(int) * (dw + dh)), *yofs = xofs + dw;
+    short *ia = (short *)malloc(sizeof(short) * 2 * (dw + dh)), *ib = ia + 2 * dw;
+    resize_tables(sw, dw, 1, xofs, ia);
+    resize_tables(sh, dh, 0, yofs, ib);
+#pragma omp parallel for
+    for (int dy = 0; dy < dh; ++dy) {
+        /* resizeGeneric_Invoker: rows sy0 - ksize2 + 1 + k clipped into the image (IMG/src/resize.cpp:2200-2240) */
+        int s0 = yofs[dy], s1 = yofs[dy] + 1;
+        s0 = s0 < 0 ? 0 : (s0 >= sh ? sh - 1 : s0);
+        s1 = s1 < 0 ? 0 : (s1 >= sh ? sh - 1 : s1);
+        const uint8_t *r0 = src + sstep * (size_t)s0, *r1 = src + sstep * (size_t)s1;
+        const int b0 = ib[2 * dy], b1 = ib[2 * dy + 1];
+        for (int dx = 0; dx < dw; ++dx) {
+            const int sx = xofs[dx], sx1 = sx + 1 < sw ? sx + 1 : sw - 1;
+            const int a0 = ia[2 * dx], a1 = ia[2 * dx + 1];
+            for (int c = 0; c < 3; ++c) {
+                const int S0 = r0[sx * 3 + c] * a0 + r0[sx1 * 3 + c] * a1;   /* HResizeLinear (:1923-1941) */
+                const int S1 = r1[sx * 3 + c] * a0 + r1[sx1 * 3 + c] * a1;
+                dst[dstep * (size_t)dy + dx * 3 + c] = (uint8_t)((((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2);  /* VResizeLinear (:2013) */
+            }
+        }
+    }
+    free(xofs); free(ia);
+}
+
+void og_bgr_to_i420(const uint8_t *bgr, int w, int h, size_t step, uint8_t *yuv)
+{
+    const int CRY = 269484, CGY = 528482, CBY = 102760, CRU = -155188, CGU = -305135, CBU = 460324, CGV = -385875, CBV = -74448;
+    const int SHIFT = 20, half = 1 << (SHIFT - 1), s16 = 16 << SHIFT, s128 = 128 << SHIFT;
+    uint8_t *yp = yuv, *up = yuv + (size_t)w * h, *vp = up + (size_t)(w / 2) * (h / 2);
+    for (int j = 0; j < h; ++j)
+        for (int i = 0; i < w; ++i) {
+            const uint8_t *p = bgr + step * (size_t)j + 3 * i;
+            const int b = p[0], g = p[1], r = p[2];
+            yp[(size_t)j * w + i] = sat_u8_int((CRY * r + CGY * g + CBY * b + half + s16) >> SHIFT);
+            if (!(j & 1) && !(i & 1)) {
+                up[(size_t)(j / 2) * (w / 2) + i / 2] = sat_u8_int((CRU * r + CGU * g + CBU * b + half + s128) >> SHIFT);
+                vp[(size_t)(j / 2) * (w / 2) + i / 2] = sat_u8_int((CBU * r + CGV * g + CBV * b + half + s128) >> SHIFT);
+            }
+        }
+}
+
+int og_consumer_image_height(int src_w, int src_h, int out_w, int out_h, int keep_aspect)
+{
+    if (!keep_aspect) return out_h;
+    int ih = (int)((double)out_w / (double)src_w * src_h + 0.5);   /* timed.cpp:260 */
+    return ih > out_h ? out_h : ih;
+}
+
 /* cuda::resize INTER_LINEAR on CV_8UC1: CW/src/cuda/resize.cu:71-106, host CW/src/resize.cpp:76-105 */
 void og_resize_linear_u8c1(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh)
 {

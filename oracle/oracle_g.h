@@ -47,6 +47,14 @@ void og_nv12_to_bgr(const uint8_t *nv12, int w, int h, size_t step, uint8_t *bgr
 /* GpuMat::convertTo(CV_8U) of the CV_16SC3 panorama: saturate_cast<uchar>(short) */
 void og_s16_to_u8(const int16_t *src, size_t n, uint8_t *dst);
 
+/* consumer epilogue on the CPU in the reference (360_stitcher/timed.cpp:254-315) */
+/* cv::resize(src, dst, Size(dw, dh), 0, 0, INTER_LINEAR) on CV_8UC3 (fixed point, IMG/src/resize.cpp:3930-4021, 1907-1957, 1993-2016) */
+void og_resize_linear_u8c3(const uint8_t *src, int sw, int sh, size_t sstep, uint8_t *dst, int dw, int dh, size_t dstep);
+/* cv::cvtColor(COLOR_BGR2YUV_I420): w, h even; dst = w*h Y bytes, then (w/2)*(h/2) U, then V (IMG/src/color.cpp:9082-9160) */
+void og_bgr_to_i420(const uint8_t *bgr, int w, int h, size_t step, uint8_t *yuv);
+/* image height the consumer resizes to (timed.cpp:254-270) */
+int og_consumer_image_height(int src_w, int src_h, int out_w, int out_h, int keep_aspect);
+
 /* ---------------------------------------------------------------- CPW mesh -> backward map */
 void og_custom_resize(const float *in, int cols, int rows, float *out, int tx, int ty);
 /* half-res table (W/2 x H/2) of step m1-m3; then og_custom_resize gives the full map (m4) */

@@ -123,6 +123,16 @@ def convert_s16_u8(a):
     return dst
 
 
+def consume(pano_u8, out_w, out_h, fmt, keep_aspect=True):
+    pano_u8 = np.ascontiguousarray(pano_u8, np.uint8)
+    h, w, _ = pano_u8.shape
+    out = np.zeros(out_w * out_h * 3, np.uint8)
+    ih = lib().vr_consume(_p(pano_u8), w, h, out_w, out_h, int(keep_aspect), fmt, _p(out))
+    if fmt == 0:
+        return out[:ih * out_w * 3].reshape(ih, out_w, 3).copy()
+    return out[:out_w * out_h * 3 // 2].copy()
+
+
 def resize_linear_u8c1(src, dw, dh):
     src = np.ascontiguousarray(src, np.uint8)
     sh, sw = src.shape

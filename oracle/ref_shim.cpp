@@ -173,6 +173,33 @@ void vr_convert_s16_u8(const int16_t *src, int w, int h, int cn, uint8_t *dst)
     s.convertTo(o, CV_8U);  // 360_stitcher/timed.cpp:250 (CPU twin of GpuMat::convertTo)
     o.copyTo(d);
 }
+/* the consumer thread after the download, with the reference's own OpenCV calls (360_stitcher/timed.cpp:254-315):
+   fmt 0: resize + COLOR_BGR2RGB (:281, :291); fmt 1: resize, BGR2RGB, copy into the black out_w x out_h frame, BGR2RGB back,
+   COLOR_BGR2YUV_I420 (:281-289, :310-311).  Returns the image height. */
+int vr_consume(const uint8_t *pano, int w, int h, int out_w, int out_h, int keep_aspect, int fmt, uint8_t *out)
+{
+    Mat original_8u(h, w, CV_8UC3, const_cast<uint8_t *>(pano)), resized_bgr, resized_rgb;
+    int image_height = out_h;
+    if (keep_aspect) {
+        image_height = (double)out_w / (double)original_8u.cols * original_8u.rows + 0.5;
+        if (image_height > out_h) image_height = out_h;
+    }
+    resize(original_8u, resized_bgr, Size(out_w, image_height), 0, 0, INTER_LINEAR);
+    if (fmt == 0) {
+        Mat final_result(image_height, out_w, CV_8UC3, out), o;
+        cvtColor(resized_bgr, o, COLOR_BGR2RGB);
+        o.copyTo(final_result);
+        return image_height;
+    }
+    Mat final_result = Mat(Size(out_w, out_h), CV_8UC3, cv::Scalar(0)), final_result_yuv;
+    cvtColor(resized_bgr, resized_rgb, COLOR_BGR2RGB);
+    uchar *row_ptr = final_result.ptr(final_result.rows / 2 - resized_rgb.rows / 2);
+    memcpy(row_ptr, resized_rgb.data, (size_t)resized_rgb.rows * resized_rgb.cols * 3);
+    cvtColor(final_result, final_result, COLOR_BGR2RGB);
+    cvtColor(final_result, final_result_yuv, COLOR_BGR2YUV_I420);
+    memcpy(out, final_result_yuv.data, (size_t)out_w * out_h * 3 / 2);
+    return image_height;
+}
 void vr_resize_linear_u8c1(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh)
 {
     Mat s(sh, sw, CV_8U, const_cast<uint8_t *>(src)), d(dh, dw, CV_8U, dst), o;

@@ -67,6 +67,12 @@ def s16_input(seed=19):
     return a
 
 
+def consume_input(seed=23):
+    """A panorama-shaped CV_8UC3 image (odd sizes like dst_roi_final) for the consumer epilogue, and its output frame sizes."""
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, (63, 383, 3), dtype=np.uint8), 512, 256
+
+
 def blend_recipe(size=128, seed=5):
     """Upstream MultiBandBlender.CanBlendTwoImages recipe (sources/modules/stitching/test/test_blenders.cpp:57-72):
     two images, left/right half masks, 5 bands -- on seeded synthetic images because baboon/lena are not vendored."""
@@ -183,6 +189,10 @@ def main():
     nv, w, h = nv12_input()
     out["nv12_bgr"] = vr.cvt_nv12_bgr(nv, w, h)
     out["s16_to_u8"] = vr.convert_s16_u8(s16_input())
+    # 11. consumer epilogue: resize INTER_LINEAR + BGR2RGB / letter-boxed BGR2YUV_I420 (A/timed.cpp:254-315)
+    pano, ow, oh = consume_input()
+    out["consume_rgb"] = vr.consume(pano, ow, oh, 0)
+    out["consume_i420"] = vr.consume(pano, ow, oh, 1)
     path = os.path.join(HERE, "reference_cpu.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")

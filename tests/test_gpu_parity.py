@@ -315,6 +315,35 @@ def test_nv12_input_and_u8_output(cuda, og, case):
     _eq(host(out1), want8[1], "feed + blend, CV_8UC3 out")
 
 
+@pytest.mark.parametrize("case,out_w,out_h", [("small4", 1280, 640), ("cfg2", 4096, 2048), ("wide2", 512, 300)])
+def test_consumer_epilogue(cuda, og, case, out_w, out_h):
+    """SURVEY 8f row 2 complete: CV_8UC3 panorama (convertTo fused) -> cv::resize + COLOR_BGR2RGB, and the letter-boxed I420 frame
+    the encoder is fed (A/timed.cpp:250-315) -- on the device, bit-exact against the restated CPU consumer."""
+    import torch
+    import vsb200
+    from tests.gpu_util import dev, host, stream
+    B = vsb200.binding
+    orig, grig, kw = _rigs(case, inject=False)
+    frames = [vsb200.synth.frame(i, 2, kw["src_w"], kw["src_h"]) for i in range(kw["n_views"])]
+    pano8 = og.s16_to_u8(orig.compose(frames)[0])
+    W, H = grig.roi_final[2], grig.roi_final[3]
+    grig.st.set_formats(B.IN_BGR8, B.OUT_U8C3)
+    pitch = (W * 3 + 15) // 16 * 16
+    d_pano = torch.zeros((H, pitch), dtype=torch.uint8, device="cuda")
+    srcs = [dev(f) for f in frames]
+    grig.st.compose([t.data_ptr() for t in srcs], kw["src_w"] * 3, [d_pano.data_ptr()], pitch, stream())
+    _eq(host(d_pano)[:, :W * 3].reshape(H, W, 3), pano8, "CV_8UC3 panorama")
+    ih = og.consumer_image_height(W, H, out_w, out_h)
+    rgb = torch.full((ih, out_w * 3 + 7), 5, dtype=torch.uint8, device="cuda")
+    grig.st.consume(d_pano.data_ptr(), pitch, out_w, out_h, B.CONSUME_RGB, rgb.data_ptr(), out_w * 3 + 7, stream=stream())
+    got = host(rgb)
+    _eq(got[:, :out_w * 3].reshape(ih, out_w, 3), og.consume(pano8, out_w, out_h, 0), "resize + BGR2RGB")
+    assert (got[:, out_w * 3:] == 5).all()
+    yuv = torch.zeros(out_w * out_h * 3 // 2, dtype=torch.uint8, device="cuda")
+    grig.st.consume(d_pano.data_ptr(), pitch, out_w, out_h, B.CONSUME_I420, yuv.data_ptr(), out_w, stream=stream())
+    _eq(host(yuv), og.consume(pano8, out_w, out_h, 1), "letter-boxed I420 frame")
+
+
 def test_compose_host_roundtrip(cuda, og):
     import vsb200
     orig, grig, kw = _rigs("small4", inject=False, max_batch=2)

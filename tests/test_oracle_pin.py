@@ -56,6 +56,13 @@ def test_wire_and_consumer_formats_exact(og, gold):
     assert np.array_equal(og.s16_to_u8(G.s16_input()), gold["s16_to_u8"])
 
 
+def test_consumer_epilogue_exact(og, gold):
+    """cv::resize(INTER_LINEAR) fixed point + COLOR_BGR2RGB / letter-boxed COLOR_BGR2YUV_I420 (A/timed.cpp:254-315): bit-exact."""
+    pano, ow, oh = G.consume_input()
+    assert np.array_equal(og.consume(pano, ow, oh, 0), gold["consume_rgb"])
+    assert np.array_equal(og.consume(pano, ow, oh, 1), gold["consume_i420"])
+
+
 def test_border_gain_dilate_distance_exact(og, gold):
     img = G.pyr_input((20, 37)).astype(np.uint8)
     assert np.array_equal(og.border_reflect_u8c3_to_s16(img, 17, 19, 30, 3), gold["border_reflect"].astype(np.int16))
@@ -168,6 +175,16 @@ def test_live_nv12_full_frame(og):
     import vsb200
     nv = vsb200.synth.frame_nv12(2, 1, 320, 240)
     assert np.array_equal(og.nv12_to_bgr(nv, 320, 240), vr.cvt_nv12_bgr(nv, 320, 240))
+
+
+def test_live_consumer_epilogue_full_size(og):
+    vr = _vr()
+    rng = np.random.default_rng(31)
+    pano = rng.integers(0, 256, (627, 3839, 3), dtype=np.uint8)   # config 2 panorama -> OUTPUT_WIDTH x OUTPUT_HEIGHT (A/defs.h:41-42)
+    for fmt in (0, 1):
+        assert np.array_equal(og.consume(pano, 4096, 2048, fmt), vr.consume(pano, 4096, 2048, fmt))
+    small = rng.integers(0, 256, (77, 101, 3), dtype=np.uint8)     # downscaling and no aspect keeping
+    assert np.array_equal(og.consume(small, 64, 64, 1, keep_aspect=False), vr.consume(small, 64, 64, 1, keep_aspect=False))
 
 
 def test_live_pyramids_bordered_size(og):

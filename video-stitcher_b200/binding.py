@@ -26,8 +26,9 @@ SYMBOLS = [
     "vsb_add_src_weight_32f", "vsb_normalize_32f", "vsb_debug_read",
     "vsb_shard_set", "vsb_shard_info", "vsb_shard_rect", "vsb_get_plane",
     "vsb_rig_camera", "vsb_voronoi_seams", "vsb_calibrate_rig", "vsb_rig_info_get", "vsb_get_config", "vsb_set_profiling", "vsb_get_profile",
-    "vsb_set_formats", "vsb_nv12_to_bgr",
+    "vsb_set_formats", "vsb_nv12_to_bgr", "vsb_consumer_image_height", "vsb_consume",
 ]
+CONSUME_RGB, CONSUME_I420 = 0, 1
 IN_BGR8, IN_NV12 = 0, 1
 OUT_S16C3, OUT_U8C3 = 0, 1
 
@@ -208,6 +209,11 @@ class Stitcher:
 
     def last_launch_count(self):
         return lib().vsb_last_launch_count(self._h)
+
+    def consume(self, pano_u8_ptr, pitch, out_w, out_h, fmt, out_ptr, out_pitch, keep_aspect=True, stream=0):
+        """Consumer epilogue on the device: resize + RGB, or letter-boxed I420 (A/timed.cpp:254-315)."""
+        check(lib().vsb_consume(self._h, _vp(pano_u8_ptr), C.c_size_t(pitch), out_w, out_h, int(keep_aspect), int(fmt),
+                                _vp(out_ptr), C.c_size_t(out_pitch), _vp(stream)))
 
     def set_formats(self, input_format=IN_BGR8, output_format=OUT_S16C3):
         """NV12 frames in (cvtColor on the device) and / or CV_8UC3 panoramas out (convertTo(CV_8U) fused into the blend)."""

@@ -17,6 +17,7 @@
 // HBM layout: all per-view intermediates are PLANAR u8 (one plane per colour channel) with the bordered
 // width (a multiple of 2^nb) as row length, so rows of every level start word aligned.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -422,6 +423,73 @@ __global__ void __launch_bounds__(256) k_nv12_to_bgr(const __grid_constant__ Nv1
     }
 }
 
+// ---- consumer epilogue: what the reference's consumer thread does on the CPU after the download --------
+// cv::resize(original_8u, resized_bgr, Size(OUTPUT_WIDTH, image_height), 0, 0, INTER_LINEAR) in 11-bit fixed point
+// (sources/modules/imgproc/src/resize.cpp:3930-4021 tables, :1923-1941 horizontal pass, :2013 vertical pass), then either
+// COLOR_BGR2RGB (360_stitcher/timed.cpp:291) or the letter-boxed frame through COLOR_BGR2YUV_I420 (:283-289, :310-315,
+// sources/modules/imgproc/src/color.cpp:9137-9157).  Integer work: bit-exact.
+struct ConsumeParams {
+    const uint8_t *src;   // CV_8UC3 panorama
+    size_t src_pitch;
+    int sw, sh;
+    const int *xofs, *yofs;          // source column / row of every destination column / row (resize tables)
+    const int *ia, *ib;              // the two 11-bit coefficients of every column / row, packed lo | hi << 16
+    int out_w, out_h, ih, row0;      // output frame, resized image height, first frame row of the image
+    uint8_t *dst;
+    size_t dst_pitch;
+};
+
+__device__ __forceinline__ unsigned consume_px(const ConsumeParams &p, int dx, int dy)  // resized pixel as b | g << 8 | r << 16
+{
+    const int sy = __ldg(p.yofs + dy), cb = __ldg(p.ib + dy), sx = __ldg(p.xofs + dx), ca = __ldg(p.ia + dx);
+    const int b0 = (short)(cb & 0xffff), b1 = cb >> 16, a0 = (short)(ca & 0xffff), a1 = ca >> 16;
+    const uint8_t *r0 = p.src + (size_t)min(max(sy, 0), p.sh - 1) * p.src_pitch, *r1 = p.src + (size_t)min(max(sy + 1, 0), p.sh - 1) * p.src_pitch;
+    const int x0 = sx * 3, x1 = min(sx + 1, p.sw - 1) * 3;
+    unsigned out = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int S0 = (int)__ldg(r0 + x0 + c) * a0 + (int)__ldg(r0 + x1 + c) * a1;
+        const int S1 = (int)__ldg(r1 + x0 + c) * a0 + (int)__ldg(r1 + x1 + c) * a1;
+        out |= (unsigned)((((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2 & 0xff) << (8 * c);
+    }
+    return out;
+}
+
+__global__ void __launch_bounds__(256) k_consume_rgb(const __grid_constant__ ConsumeParams p)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= p.out_w || y >= p.ih) return;
+    const unsigned v = consume_px(p, x, y);
+    uint8_t *d = p.dst + (size_t)y * p.dst_pitch + (size_t)x * 3;
+    d[0] = (v >> 16) & 0xff; d[1] = (v >> 8) & 0xff; d[2] = v & 0xff;  // COLOR_BGR2RGB
+}
+
+__device__ __forceinline__ int sat_u8i(int v) { return min(255, max(0, v)); }
+
+// one thread = one 2 x 2 block of the out_w x out_h frame: four Y samples, one U and one V (from the block's top-left pixel)
+__global__ void __launch_bounds__(256) k_consume_i420(const __grid_constant__ ConsumeParams p)
+{
+    const int x = (blockIdx.x * 32 + threadIdx.x) * 2, y = (blockIdx.y * 8 + threadIdx.y) * 2;
+    if (x >= p.out_w || y >= p.out_h) return;
+    uint8_t *yp = p.dst, *up = p.dst + (size_t)p.out_w * p.out_h, *vp = up + (size_t)(p.out_w / 2) * (p.out_h / 2);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int iy = y + j - p.row0;  // row of the resized image (the rest of the frame is black)
+        unsigned yy = 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const unsigned v = (unsigned)iy < (unsigned)p.ih ? consume_px(p, x + i, iy) : 0u;
+            const int b = v & 0xff, g = (v >> 8) & 0xff, r = (v >> 16) & 0xff;
+            yy |= (unsigned)sat_u8i((269484 * r + 528482 * g + 102760 * b + (1 << 19) + (16 << 20)) >> 20) << (8 * i);
+            if (i == 0 && j == 0) {
+                up[(size_t)(y / 2) * (p.out_w / 2) + x / 2] = (uint8_t)sat_u8i((-155188 * r - 305135 * g + 460324 * b + (1 << 19) + (128 << 20)) >> 20);
+                vp[(size_t)(y / 2) * (p.out_w / 2) + x / 2] = (uint8_t)sat_u8i((460324 * r - 385875 * g - 74448 * b + (1 << 19) + (128 << 20)) >> 20);
+            }
+        }
+        *(uint16_t *)(yp + (size_t)(y + j) * p.out_w + x) = (uint16_t)yy;
+    }
+}
+
 // ---- K3: pyrDown on planes ----------------------------------------------------------------------------
 // out(y,x) = rhe( sum_{j,i} k5[j] k5[i] in(r101(2y+j-2), r101(2x+i-2)) / 256 ): the exact integer form of the
 // reference's fp32 vertical-then-horizontal 5-tap passes (every partial sum is exactly representable).
@@ -756,6 +824,8 @@ struct vsb_stitcher {
     uint8_t *nv_bgr = nullptr;          // [max_batch][num_views] BGR images, rows nv_pitch bytes apart
     size_t nv_pitch = 0, nv_stride = 0;
     int nv_w = 0, nv_h = 0;
+    int *cons_tab = nullptr;            // consumer resize tables for (cons_w x cons_ih): xofs | yofs | ia | ib
+    int cons_w = 0, cons_ih = 0;
     uint8_t *stage_nv12 = nullptr;      // host path: device copy of the caller's NV12 frames
     size_t stage_nv12_frame = 0;
     // optional per-kernel timing (vsb_set_profiling): events bracket every launch of the last submission
@@ -1559,7 +1629,7 @@ int vsb_destroy(vsb_stitcher *s)
     for (int k = 0; k < MAXL; ++k) cudaFree(s->dw[k]);
     cudaFree(s->d_plan);
     cudaFree(s->d_blend_views); cudaFree(s->d_coarse_views); cudaFree(s->d_down2_tiles); cudaFree(s->C2);
-    cudaFree(s->stage_src); cudaFree(s->stage_out); cudaFree(s->nv_bgr); cudaFree(s->stage_nv12);
+    cudaFree(s->stage_src); cudaFree(s->stage_out); cudaFree(s->nv_bgr); cudaFree(s->stage_nv12); cudaFree(s->cons_tab);
     cudaFreeHost(s->pin_src); cudaFreeHost(s->pin_out);
     if (s->setup_stream) cudaStreamDestroy(s->setup_stream);
     if (s->mesh_stream) cudaStreamDestroy(s->mesh_stream);
@@ -1839,6 +1909,66 @@ int vsb_nv12_to_bgr(const uint8_t *d_nv12, int w, int h, size_t pitch, uint8_t *
     p.src[0] = d_nv12; p.dst[0] = d_bgr; p.pitch = pitch; p.dst_pitch = bgr_pitch; p.w = w; p.h = h;
     k_nv12_to_bgr<<<dim3(((w + 3) / 4 + 31) / 32, (h / 2 + 7) / 8, 1), dim3(32, 8), 0, (cudaStream_t)stream>>>(p);
     return check_launch("k_nv12_to_bgr");
+}
+
+// coefficient tables of cv::hal::resize, INTER_LINEAR on 8U (sources/modules/imgproc/src/resize.cpp:3933-3958, 3991-4016)
+static void consumer_tables(int ssize, int dsize, bool clamp_x, int *ofs, int *coef)
+{
+    const double inv_scale = (double)dsize / ssize, scale = 1. / inv_scale;
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int sidx = (int)floorf(f);
+        f -= sidx;
+        if (clamp_x) {
+            if (sidx < 0) { f = 0; sidx = 0; }
+            if (sidx >= ssize - 1) { f = 0; sidx = ssize - 1; }
+        }
+        ofs[d] = sidx;
+        const float c0 = 1.f - f, c1 = f;
+        const long r0 = std::min(32767L, std::max(-32768L, lrintf(c0 * 2048))), r1 = std::min(32767L, std::max(-32768L, lrintf(c1 * 2048)));
+        coef[d] = (int)((unsigned)(r0 & 0xffff) | ((unsigned)(r1 & 0xffff) << 16));
+    }
+}
+
+int vsb_consumer_image_height(int src_w, int src_h, int out_w, int out_h, int keep_aspect)
+{
+    if (!keep_aspect || src_w <= 0) return out_h;
+    const int ih = (int)((double)out_w / (double)src_w * src_h + 0.5);  // 360_stitcher/timed.cpp:260
+    return std::min(ih, out_h);
+}
+
+int vsb_consume(vsb_stitcher *s, const uint8_t *d_pano_u8, size_t pitch, int out_w, int out_h, int keep_aspect, int format,
+                uint8_t *d_out, size_t out_pitch, void *stream)
+{
+    REQ(s && d_pano_u8 && d_out, VSB_ERR_INVALID, "consume: null argument");
+    REQ(s->prepared, VSB_ERR_STATE, "consume: call vsb_prepare first");
+    REQ(format == VSB_CONSUME_RGB || format == VSB_CONSUME_I420, VSB_ERR_INVALID, "consume: unknown format %d", format);
+    const int sw = s->roi_final[2], sh = s->roi_final[3];
+    REQ(out_w > 0 && out_h > 0 && pitch >= (size_t)sw * 3, VSB_ERR_INVALID, "consume: bad sizes");
+    REQ(format != VSB_CONSUME_I420 || ((out_w | out_h) & 1) == 0, VSB_ERR_INVALID, "consume: I420 needs even output sizes");
+    REQ(format != VSB_CONSUME_RGB || out_pitch >= (size_t)out_w * 3, VSB_ERR_INVALID, "consume: output pitch too small");
+    DeviceGuard g(s->device);
+    const int ih = vsb_consumer_image_height(sw, sh, out_w, out_h, keep_aspect);
+    REQ(ih > 0, VSB_ERR_INVALID, "consume: empty image");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!s->cons_tab || s->cons_w != out_w || s->cons_ih != ih) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(s->cons_tab); s->cons_tab = nullptr;
+        std::vector<int> tab((size_t)2 * (out_w + ih));
+        consumer_tables(sw, out_w, true, tab.data(), tab.data() + out_w + ih);
+        consumer_tables(sh, ih, false, tab.data() + out_w, tab.data() + 2 * out_w + ih);
+        CK(cudaMalloc(&s->cons_tab, tab.size() * sizeof(int)));
+        CK(cudaMemcpy(s->cons_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+        s->cons_w = out_w; s->cons_ih = ih;
+    }
+    ConsumeParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.src = d_pano_u8; p.src_pitch = pitch; p.sw = sw; p.sh = sh;
+    p.xofs = s->cons_tab; p.yofs = s->cons_tab + out_w; p.ia = s->cons_tab + out_w + ih; p.ib = s->cons_tab + 2 * out_w + ih;
+    p.out_w = out_w; p.out_h = out_h; p.ih = ih; p.row0 = out_h / 2 - ih / 2; p.dst = d_out; p.dst_pitch = out_pitch;
+    if (format == VSB_CONSUME_RGB) k_consume_rgb<<<dim3((out_w + 31) / 32, (ih + 7) / 8), dim3(32, 8), 0, st>>>(p);
+    else k_consume_i420<<<dim3((out_w / 2 + 31) / 32, (out_h / 2 + 7) / 8), dim3(32, 8), 0, st>>>(p);
+    return check_launch("k_consume");
 }
 
 int vsb_feed(vsb_stitcher *s, int i, const uint8_t *d_bgr, size_t pitch, void *stream)
