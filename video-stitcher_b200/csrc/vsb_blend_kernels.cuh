@@ -184,6 +184,7 @@ struct Down2View {
 };
 struct Down2Params {
     const uint32_t *tiles;  // view | tile_x << 8 | tile_y << 20
+    int f0;                 // first frame slot of this launch (blockIdx.z counts from it)
     Down2View v[MAXV];
 };
 // TMA descriptors of the G0 buffers, one per view: 3-D u8 tensor {bw, bh, 3 * max_batch}, box {160, 73, 1} (= one k_down2 region)
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Do
     const unsigned tile = __ldg(P.tiles + blockIdx.x);
     const Down2View &V = P.v[tile & 0xff];
     const int X0 = ((tile >> 8) & 0xfff) * D2_TW, Y0 = (tile >> 20) * D2_TH;
-    const int c = blockIdx.y, f = blockIdx.z, t = threadIdx.x;
+    const int c = blockIdx.y, f = blockIdx.z + P.f0, t = threadIdx.x;
     const int w0 = V.bw, h0 = V.bh, w1 = w0 >> 1, h1 = h0 >> 1, w2 = w0 >> 2, h2 = h0 >> 2;
     const uint8_t *g0 = V.g0 + (size_t)f * V.g0_fs + (size_t)c * w0 * h0;
     const int gx0 = 4 * X0 - 16, gy0 = 4 * Y0 - 6;
@@ -374,7 +375,7 @@ struct Down1View {
     int w, h;  // source plane size
 };
 struct Down1Params {
-    int n;
+    int n, f0;
     int start[MAXV + 1];  // prefix sums of tiles per view
     int tiles_x[MAXV];
     Down1View v[MAXV];
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(D1_TX *D1_TY) k_down1(const __grid_constant__ 
     const int x = (tl % P.tiles_x[vi]) * D1_TX + threadIdx.x, y = (tl / P.tiles_x[vi]) * D1_TY + threadIdx.y;
     const int ws = V.w, hs = V.h, wd = ws >> 1, hd = hs >> 1;
     if (x >= wd || y >= hd) return;
-    const int c = blockIdx.z, f = blockIdx.y;
+    const int c = blockIdx.z, f = blockIdx.y + P.f0;
     const uint8_t *src = V.src + (size_t)f * V.src_fs + (size_t)c * ws * hs;
     int acc = 0;
     if (2 * y - 2 >= 0 && 2 * y + 2 < hs && 2 * x - 2 >= 0 && 2 * x + 2 < ws) {
@@ -421,7 +422,7 @@ struct DownTailView {
     int w2, h2;                  // size of level k0
 };
 struct DownTailParams {
-    int nb, k0;
+    int nb, k0, f0;
     DownTailView v[MAXV];
 };
 constexpr int DT_TX = 32, DT_TY = 32;
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(DT_TX *DT_TY) k_down_tail(const __grid_constan
 {
     extern __shared__ __align__(16) uint8_t dt_smem[];
     const DownTailView &V = P.v[blockIdx.x];
-    const int c = blockIdx.y, f = blockIdx.z;
+    const int c = blockIdx.y, f = blockIdx.z + P.f0;
     int w = V.w2, h = V.h2;
     uint8_t *level = dt_smem;
     const uint8_t *src = V.g2 + (size_t)f * V.g2_fs + (size_t)c * w * h;
@@ -530,7 +531,7 @@ struct CoarseParams {
     int16_t *c2;                 // frame 0, plane 0: [3][ch2][cw2]
     size_t c2_fs;                // elements
     const uint32_t *tile_views;  // bit v: view v has weight in this tile (any level >= 2)
-    int tiles_x;
+    int tiles_x, f0;
     const CoarseView *views;     // device array [n_views]
 };
 
@@ -563,7 +564,7 @@ __global__ void __launch_bounds__(C_THREADS) k_coarse(const __grid_constant__ Co
     const CoarseGeo &Gm = P.geo;
     int16_t *A = (int16_t *)c_smem;
     uint8_t *G = c_smem + (size_t)Gm.a_total * 2;
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, c = blockIdx.y, f = blockIdx.z, nlev = Gm.nlev;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, c = blockIdx.y, f = blockIdx.z + P.f0, nlev = Gm.nlev;
     const int X0 = (blockIdx.x % P.tiles_x) * CT, Y0 = (blockIdx.x / P.tiles_x) * CT;
     unsigned views = __ldg(P.tile_views + blockIdx.x);
     if (views & 0x80000000u) return;  // view-sharded mode: another rank owns this canvas strip
@@ -683,7 +684,7 @@ struct BlendView {
     int x_tl, y_tl, bw, bh;
 };
 struct BlendParams {
-    int nb, tiles_x;
+    int nb, tiles_x, f0;
     int cw0, ch0, cw1, ch1, cw2, ch2;
     int out_w, out_h;
     const int16_t *c2;
@@ -700,7 +701,7 @@ __global__ void __launch_bounds__(BL_THREADS, 3) k_blend_v1(const __grid_constan
     __shared__ int16_t sC2[3][BL_R2H][BL_R2W];
     __shared__ int16_t sD1[3][BL_R1H][BL_R1W];
     __shared__ __align__(16) int16_t sOut[BL_TH][BL_TW * 3];
-    const int t = threadIdx.x, f = blockIdx.z, nb = P.nb;
+    const int t = threadIdx.x, f = blockIdx.z + P.f0, nb = P.nb;
     const int tx0 = blockIdx.x * BL_TW, ty0 = blockIdx.y * BL_TH;
     const int lx = (t & 7) * 8, ly = t >> 3;  // this thread's 8 consecutive level-0 samples
     const int px0 = tx0 + lx, py = ty0 + ly;
@@ -967,7 +968,7 @@ __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__
     __shared__ __align__(16) float sD1f[B2_G1F];
     float *sG1f = sStage, *sG2f = sStage + B2_G1F;
     static_assert(sizeof(float) * (B2_G1F + B2_G2F) >= sizeof(int16_t) * BL_TH * BL_TW * 3, "output tile must fit the staging area");
-    const int t = threadIdx.x, f = blockIdx.z;
+    const int t = threadIdx.x, f = blockIdx.z + P.f0;
     const int tx0 = blockIdx.x * BL_TW, ty0 = blockIdx.y * BL_TH;
     const unsigned views_all = __ldg(P.tile_views + blockIdx.y * P.tiles_x + blockIdx.x);
     if (views_all & 0x80000000u) return;  // view-sharded mode: another rank owns this canvas strip

@@ -60,9 +60,9 @@ struct Stage1View {
 struct Stage1Params {
     const uint32_t *tiles;      // view | tile_x << 8 | tile_y << 20
     Stage1View v[MAXV];
-    const uint8_t *src[MAX_BATCH * MAXV];  // [frame][view - v0]
+    const uint8_t *src[MAX_BATCH * MAXV];  // [frame slot][view - v0]
     size_t src_pitch;
-    int v0, n_views;
+    int v0, n_views, f0;                   // f0: first frame slot of this launch
 };
 
 constexpr int RM_BX = 32, RM_BY = 8, RM_PX = 4;  // 4 consecutive pixels per thread
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage1(const __grid_cons
     const Stage1View &V = p.v[vi];
     const int x0 = ((int)((tile >> 8) & 0xfff) * RM_BX + threadIdx.x) * RM_PX, y = (int)(tile >> 20) * RM_BY + threadIdx.y;
     if (x0 >= V.w || y >= V.h) return;
-    const int f = blockIdx.y;
+    const int f = blockIdx.y + p.f0;
     const uint8_t *src = p.src[f * p.n_views + vi - p.v0];
     const float *mx = (const float *)((const char *)V.xmap + (size_t)y * V.map_pitch) + x0;
     const float *my = (const float *)((const char *)V.ymap + (size_t)y * V.map_pitch) + x0;
@@ -114,6 +114,7 @@ struct Stage2View {
 struct Stage2Params {
     const uint32_t *tiles;
     Stage2View v[MAXV];
+    int f0;
 };
 
 __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage2(const __grid_constant__ Stage2Params p)
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage2(const __grid_cons
     const Stage2View &V = p.v[tile & 0xff];
     const int bx0 = ((int)((tile >> 8) & 0xfff) * RM_BX + threadIdx.x) * RM_PX, by = (int)(tile >> 20) * RM_BY + threadIdx.y;
     if (bx0 >= V.bw || by >= V.bh) return;
-    const int f = blockIdx.y;
+    const int f = blockIdx.y + p.f0;
     const uint8_t *P = V.P + (size_t)f * V.p_frame_stride;
     const int y = reflect_idx(by - V.top, V.h);
     const int n = min(RM_PX, V.bw - bx0);
@@ -219,9 +220,9 @@ struct Stage1TabView {
 struct Stage1TabParams {
     const uint32_t *tiles;
     Stage1TabView v[MAXV];
-    const uint8_t *src[MAX_BATCH * MAXV];  // [frame][view - v0]
+    const uint8_t *src[MAX_BATCH * MAXV];  // [frame slot][view - v0]
     unsigned src_pitch;
-    int v0, n_views, n_frames;
+    int v0, n_views, n_frames, f0;         // frame slots f0 .. f0 + n_frames - 1
 };
 
 // One CTA = one 128 x 8 tile for ALL frames of the submission: the table entries of the thread's 4 pixels are loaded once
@@ -273,9 +274,9 @@ __global__ void __launch_bounds__(RM_BX *RM_BY, VSB_RM1_MINB) k_remap_stage1_tab
     for (int m = 0; m < 3; ++m) { const int j = threadIdx.x + 32 * m; wp[m] = (4 * j) / 3; wr[m] = 8 * (4 * j - 3 * wp[m]); }
     const int row_bytes = 3 * min(RM_BX * RM_PX, V.w - tx0);  // valid bytes of this tile row
     const int n = min(RM_PX, V.w - x0);
-    uint8_t *dst = V.P + (size_t)y * V.p_pitch + (size_t)(LANES ? tx0 : x0) * 3;
+    uint8_t *dst = V.P + (size_t)p.f0 * V.p_frame_stride + (size_t)y * V.p_pitch + (size_t)(LANES ? tx0 : x0) * 3;
 #pragma unroll 1
-    for (int f = 0; f < p.n_frames; ++f, dst += V.p_frame_stride) {
+    for (int f = p.f0; f < p.f0 + p.n_frames; ++f, dst += V.p_frame_stride) {
         const uint8_t *src = p.src[f * p.n_views + vi - p.v0];
         unsigned px[RM_PX];
 #pragma unroll
@@ -325,7 +326,7 @@ struct Stage2TabView {
 struct Stage2TabParams {
     const uint32_t *tiles;
     Stage2TabView v[MAXV];
-    int n_frames;
+    int n_frames, f0;
 };
 
 __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage2_tab(const __grid_constant__ Stage2TabParams p)
@@ -341,8 +342,8 @@ __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage2_tab(const __grid_
     const size_t plane = (size_t)V.bw * V.bh;
     const int n = min(RM_PX, V.bw - bx0);
     const bool vec = n == RM_PX && (V.bw & 3) == 0;
-    const uint8_t *P = V.Pbase;
-    uint8_t *g = V.G0 + (size_t)by * V.bw + bx0;
+    const uint8_t *P = V.Pbase + (size_t)p.f0 * V.p_frame_stride;
+    uint8_t *g = V.G0 + (size_t)p.f0 * V.g0_frame_stride + (size_t)by * V.bw + bx0;
 #pragma unroll 1
     for (int f = 0; f < p.n_frames; ++f, P += V.p_frame_stride, g += V.g0_frame_stride) {
         unsigned px[RM_PX];
@@ -808,6 +809,9 @@ struct vsb_stitcher {
     cudaEvent_t last_compose = nullptr;
     bool last_compose_valid = false;
     std::mutex mu;  // guards mesh publication
+    int f0 = 0;                         // first frame slot the launch helpers address (vsb_compose splits a batch over two streams)
+    cudaStream_t sub[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     int launches = 0, launches_last = 0;  // running count of the submission in flight / count of the last finished one
     // vsb_feed / vsb_blend bookkeeping (frame slot 0)
     // host-buffer path staging
@@ -1217,6 +1221,7 @@ static int launch_down2(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
         else if (i < v1) { count += nt; bytes += (double)nt * 3 * (16.0 * D2_TW * D2_TH + 4.0 * D2_TW * D2_TH + D2_TW * D2_TH); }
     }
     p.tiles = s->d_down2_tiles + first;
+    p.f0 = s->f0;
     bool tma = true;
     Down2Maps maps;
     std::memset(&maps, 0, sizeof(maps));
@@ -1248,7 +1253,7 @@ static int launch_down1_level(vsb_stitcher *s, int k, int v0, int v1, int n_fram
             bytes += 3.0 * (V.bw >> k) * (V.bh >> k) + 3.0 * wd * hd;
             ++m;
         }
-        p.n = m;
+        p.n = m; p.f0 = s->f0;
         if (m > 0) k_down1<<<dim3(p.start[m], n_frames, 3), dim3(D1_TX, D1_TY), 0, st>>>(p);
         ++s->launches;
         static const char *names[MAXL] = {"", "", "down1_L3", "down1_L4", "down1_L5", "down1_L6", "down1_L7", ""};
@@ -1284,7 +1289,7 @@ static int launch_down1(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
         }
         DownTailParams p;
         std::memset(&p, 0, sizeof(p));
-        p.nb = nb; p.k0 = k0;
+        p.nb = nb; p.k0 = k0; p.f0 = s->f0;
         for (int i = v0; i < v1; ++i) {
             const View &V = s->v[i];
             DownTailView &D = p.v[i - v0];
@@ -1318,7 +1323,7 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
         p.geo = s->cgeo;
         for (int j = 0; j < s->cgeo.nlev; ++j) { p.cw[j] = s->cw[2 + j]; p.ch[j] = s->ch[2 + j]; p.dw[j] = s->dw[2 + j]; }
         p.c2 = s->C2; p.c2_fs = s->c2_frame_stride; p.tile_views = s->d_coarse_views; p.tiles_x = s->coarse_tiles_x;
-        p.views = s->d_coarse_desc;
+        p.views = s->d_coarse_desc; p.f0 = s->f0;
         double bytes = 6.0 * s->cw[2] * s->ch[2];  // Gaussian levels >= 2 of every view in once + C2 (s16 x 3) out once
         for (int i = 0; i < n; ++i)
             for (int k = 2; k <= nb; ++k) bytes += 3.0 * (s->v[i].bw >> k) * (s->v[i].bh >> k);
@@ -1329,7 +1334,7 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
     {
         BlendParams p;
         std::memset(&p, 0, sizeof(p));
-        p.nb = nb; p.tiles_x = s->blend_tiles_x;
+        p.nb = nb; p.tiles_x = s->blend_tiles_x; p.f0 = s->f0;
         p.cw0 = s->cw[0]; p.ch0 = s->ch[0]; p.cw1 = s->cw[1]; p.ch1 = s->ch[1]; p.cw2 = s->cw[2]; p.ch2 = s->ch[2];
         p.out_w = s->roi_final[2]; p.out_h = s->roi_final[3];
         p.c2 = s->C2; p.c2_fs = s->c2_frame_stride; p.tile_views = s->d_blend_views;
@@ -1345,7 +1350,7 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
         }
         OutPtrs o;
         std::memset(&o, 0, sizeof(o));
-        for (int f = 0; f < n_frames; ++f) o.out[f] = d_outs[f];
+        for (int f = 0; f < n_frames; ++f) o.out[s->f0 + f] = d_outs[f];
         const dim3 g(s->blend_tiles_x, s->blend_tiles_y, n_frames);
         if (s->out_format == VSB_OUT_U8C3) k_blend<true><<<g, BL_THREADS, 0, st>>>(p, o, out_pitch);
         else k_blend<false><<<g, BL_THREADS, 0, st>>>(p, o, out_pitch);
@@ -1387,7 +1392,7 @@ static int launch_nv12(vsb_stitcher *s, int v0, int v1, int n_frames, const uint
     for (int f = 0; f < n_frames; ++f)
         for (int j = 0; j < n; ++j) {
             p.src[f * n + j] = d_srcs[f * n + j];
-            p.dst[f * n + j] = s->nv_bgr + s->nv_stride * ((size_t)f * nv + v0 + j);
+            p.dst[f * n + j] = s->nv_bgr + s->nv_stride * ((size_t)(s->f0 + f) * nv + v0 + j);
             bgr_ptrs[f * n + j] = p.dst[f * n + j];
         }
     p.pitch = src_pitch; p.dst_pitch = s->nv_pitch; p.w = w; p.h = h;
@@ -1458,8 +1463,8 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
                 S.w = V.roi_w; S.h = V.roi_h; S.src_w = V.src_w; S.src_h = V.src_h;
             }
             p.tiles = s->d_s1_tiles + first;
-            p.v0 = v0; p.n_views = n; p.src_pitch = (unsigned)src_pitch; p.n_frames = n_frames;
-            for (int f = 0; f < n_frames; ++f) for (int j = 0; j < n; ++j) p.src[f * n + j] = d_srcs[f * n + j];
+            p.v0 = v0; p.n_views = n; p.src_pitch = (unsigned)src_pitch; p.n_frames = n_frames; p.f0 = s->f0;
+            for (int f = 0; f < n_frames; ++f) for (int j = 0; j < n; ++j) p.src[(s->f0 + f) * n + j] = d_srcs[f * n + j];
             if (count > 0) {
                 if (remap_variant() & 1) k_remap_stage1_tab<true><<<(unsigned)count, dim3(RM_BX, RM_BY), 0, st>>>(p);
                 else k_remap_stage1_tab<false><<<(unsigned)count, dim3(RM_BX, RM_BY), 0, st>>>(p);
@@ -1475,8 +1480,8 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
                 S.w = V.roi_w; S.h = V.roi_h; S.src_w = V.src_w; S.src_h = V.src_h;
             }
             p.tiles = s->d_s1_tiles + first;
-            p.v0 = v0; p.n_views = n; p.src_pitch = src_pitch;
-            for (int f = 0; f < n_frames; ++f) for (int j = 0; j < n; ++j) p.src[f * n + j] = d_srcs[f * n + j];
+            p.v0 = v0; p.n_views = n; p.src_pitch = src_pitch; p.f0 = s->f0;
+            for (int f = 0; f < n_frames; ++f) for (int j = 0; j < n; ++j) p.src[(s->f0 + f) * n + j] = d_srcs[f * n + j];
             if (count > 0) k_remap_stage1<<<dim3(count, n_frames), dim3(RM_BX, RM_BY), 0, st>>>(p);
         }
         ++s->launches;
@@ -1504,7 +1509,7 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
                 S.Pbase = V.P_alloc; S.G0 = V.G0; S.p_frame_stride = V.p_frame_stride; S.g0_frame_stride = V.g0_frame_stride;
                 S.p_pitch = (unsigned)V.p_pitch; S.bw = V.bw; S.bh = V.bh;
             }
-            p.tiles = s->d_s2_tiles + first; p.n_frames = n_frames;
+            p.tiles = s->d_s2_tiles + first; p.n_frames = n_frames; p.f0 = s->f0;
             if (count > 0) {
                 k_remap_stage2_tab<<<(unsigned)count, dim3(RM_BX, RM_BY), 0, st>>>(p);
             }
@@ -1521,7 +1526,7 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
                 if (warped && i == v0) { S.P = warped; S.p_pitch = src_pitch; S.p_frame_stride = 0; }  // feed_online: the caller's warped view
                 S.w = V.roi_w; S.h = V.roi_h; S.bw = V.bw; S.bh = V.bh; S.top = V.top; S.left = V.left;
             }
-            p.tiles = s->d_s2_tiles + first;
+            p.tiles = s->d_s2_tiles + first; p.f0 = s->f0;
             if (count > 0) k_remap_stage2<<<dim3(count, n_frames), dim3(RM_BX, RM_BY), 0, st>>>(p);
         }
         ++s->launches;
@@ -1636,6 +1641,8 @@ int vsb_destroy(vsb_stitcher *s)
     if (s->io_stream) cudaStreamDestroy(s->io_stream);
     if (s->in_stream) cudaStreamDestroy(s->in_stream);
     if (s->out_stream) cudaStreamDestroy(s->out_stream);
+    for (int h = 0; h < 2; ++h) { if (s->sub[h]) cudaStreamDestroy(s->sub[h]); if (s->ev_join[h]) cudaEventDestroy(s->ev_join[h]); }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     for (int f = 0; f < MAX_BATCH; ++f) { if (s->ev_in[f]) cudaEventDestroy(s->ev_in[f]); if (s->ev_done[f]) cudaEventDestroy(s->ev_done[f]); }
     if (s->last_compose) cudaEventDestroy(s->last_compose);
     for (int i = 0; i <= VSB_MAX_STAGES; ++i) if (s->prof_ev[i]) cudaEventDestroy(s->prof_ev[i]);
@@ -2028,6 +2035,40 @@ int vsb_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, siz
     s->launches = 0;
     r = adopt_meshes(s, st);
     if (r != VSB_OK) return r;
+    static const bool no_split = std::getenv("VSB_NO_SPLIT") != nullptr;
+    if (n_frames >= 2 && s->fast && !s->profiling && !no_split) {
+        // Two half-batches on two internal streams: the short kernels (k_down_tail: 144 CTAs, k_coarse: ~1.2 waves) and the
+        // last partial wave of every kernel of one half overlap with the other half's work.  Frame slots are disjoint; the
+        // static tables are built on the caller's stream before the fork.
+        const int n = s->cfg.num_views;
+        if (!s->sub[0]) {
+            for (int h = 0; h < 2; ++h) {
+                CK(cudaStreamCreateWithFlags(&s->sub[h], cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&s->ev_join[h], cudaEventDisableTiming));
+            }
+            CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+        }
+        r = sync_tile_lists(s);
+        if (r != VSB_OK) return r;
+        if (s->in_format == VSB_IN_BGR8 && remap_variant() >= 0 && src_pitch % 4 == 0)
+            for (int i = 0; i < n; ++i)
+                if (s->v[i].src_h >= 2 && (unsigned long long)src_pitch * s->v[i].src_h < 0x7fffffffull) { r = build_taps1(s, i, src_pitch, st); if (r != VSB_OK) return r; }
+        CK(cudaEventRecord(s->ev_fork, st));
+        const int half[3] = {0, (n_frames + 1) / 2, n_frames};
+        for (int h = 0; h < 2 && r == VSB_OK; ++h) {
+            CK(cudaStreamWaitEvent(s->sub[h], s->ev_fork, 0));
+            s->f0 = half[h];
+            const int nf = half[h + 1] - half[h];
+            if (h == 1 && s->in_format == VSB_IN_NV12) CK(cudaStreamWaitEvent(s->sub[1], s->ev_join[0], 0));  // first NV12 use sizes the staging and the tap tables in half 0
+            r = launch_front(s, 0, n, nf, d_srcs + (size_t)half[h] * n, src_pitch, s->sub[h]);
+            if (r == VSB_OK && h == 0 && s->in_format == VSB_IN_NV12) CK(cudaEventRecord(s->ev_join[0], s->sub[0]));
+            if (r == VSB_OK) r = launch_back(s, nf, d_outs + half[h], out_pitch, s->sub[h]);
+            if (r == VSB_OK) { CK(cudaEventRecord(s->ev_join[h], s->sub[h])); CK(cudaStreamWaitEvent(st, s->ev_join[h], 0)); }
+        }
+        s->f0 = 0;
+        if (r != VSB_OK) return r;
+        return note_compose_done(s, st);
+    }
     prof_begin(s, st);
     r = launch_front(s, 0, s->cfg.num_views, n_frames, d_srcs, src_pitch, st);
     if (r != VSB_OK) return r;
