@@ -28,6 +28,8 @@ namespace vsb {
 constexpr int MAXV = VSB_MAX_VIEWS;
 constexpr int MAXL = VSB_MAX_BANDS + 1;
 constexpr int MAX_BATCH = 8;
+constexpr float B2_MAGIC = 12582912.f;      // 1.5 * 2^23: adding it rounds an fp32 value to an integer (half to even) in the low mantissa bits
+constexpr int B2_MAGIC_BITS = 0x4B400000;
 
 struct OutPtrs { int16_t *out[MAX_BATCH]; };
 
@@ -72,78 +74,6 @@ __device__ __forceinline__ int pyr_up_sample(const Acc &a, int x, int y, int n_x
         acc = 16 * (a(xc, yc) + a(xp, yc) + a(xc, yp) + a(xp, yp));
     }
     return sat_s16(rhe_shift<6>(acc));
-}
-
-// pyrUp of the 8 consecutive samples x0 .. x0+7 (x0 even) of row y; same integers as pyr_up_sample, columns shared.
-template <typename Acc>
-__device__ __forceinline__ void pyr_up_row8(const Acc &a, int x0, int y, int n_x, int n_y, int out[8])
-{
-    const int ix0 = x0 >> 1, iy = y >> 1;
-    int col[6];
-    if (y & 1) {
-        const int yc = iy, yp = up_idx(iy + 1, n_y);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { const int cx = up_idx(ix0 - 1 + i, n_x); col[i] = 4 * (a(cx, yc) + a(cx, yp)); }
-    } else {
-        const int ym = up_idx(iy - 1, n_y), yc = iy, yp = up_idx(iy + 1, n_y);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { const int cx = up_idx(ix0 - 1 + i, n_x); col[i] = a(cx, ym) + 6 * a(cx, yc) + a(cx, yp); }
-    }
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        out[2 * p] = sat_s16(rhe_shift<6>(col[p] + 6 * col[p + 1] + col[p + 2]));
-        out[2 * p + 1] = sat_s16(rhe_shift<6>(4 * (col[p + 1] + col[p + 2])));
-    }
-}
-
-
-// pyr_up_row8 on a shared-memory region `reg` (row pitch PITCH elements) whose element (0, 0) is plane sample (ox, oy).
-// Interior threads (no index clamps) read their 6 x 3 neighbourhood through one base pointer and immediate offsets.
-template <typename T, int PITCH>
-__device__ __forceinline__ void pyr_up_row8_region(const T *reg, int ox, int oy, int x0, int y, int n_x, int n_y, int out[8])
-{
-    const int ix0 = x0 >> 1, iy = y >> 1;
-    if (ix0 >= 1 && ix0 + 4 < n_x && iy >= 1 && iy + 1 < n_y) {
-        const T *p = reg + (iy - 1 - oy) * PITCH + (ix0 - 1 - ox);
-        int col[6];
-        if (y & 1) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) col[i] = 4 * ((int)p[PITCH + i] + (int)p[2 * PITCH + i]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) col[i] = (int)p[i] + 6 * (int)p[PITCH + i] + (int)p[2 * PITCH + i];
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            out[2 * q] = sat_s16(rhe_shift<6>(col[q] + 6 * col[q + 1] + col[q + 2]));
-            out[2 * q + 1] = sat_s16(rhe_shift<6>(4 * (col[q + 1] + col[q + 2])));
-        }
-    } else {
-        auto a = [&](int xi, int yi) { return (int)reg[(yi - oy) * PITCH + (xi - ox)]; };
-        pyr_up_row8(a, x0, y, n_x, n_y, out);
-    }
-}
-
-// pyrUp of the 2x2 quad {x0, x0+1} x {y0, y0+1} with x0 and y0 ODD (x0 = -1 allowed: only the valid samples are used).
-// out[0] = (x0, y0), out[1] = (x0+1, y0), out[2] = (x0, y0+1), out[3] = (x0+1, y0+1); same integers as pyr_up_sample,
-// the 3x3 source neighbourhood is read once and no lane diverges on parity.
-template <typename Acc>
-__device__ __forceinline__ void pyr_up_quad_odd(const Acc &a, int x0, int y0, int n_x, int n_y, int out[4])
-{
-    const int m = x0 >> 1, n = y0 >> 1;
-    const int c0 = up_idx(m, n_x), c1 = up_idx(m + 1, n_x), c2 = up_idx(m + 2, n_x);
-    int h[3], p[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const int r = up_idx(n + i, n_y);
-        const int s0 = a(c0, r), s1 = a(c1, r), s2 = a(c2, r);
-        h[i] = s0 + 6 * s1 + s2;
-        p[i] = s0 + s1;
-    }
-    out[0] = sat_s16(rhe_shift<6>(16 * (p[0] + p[1])));
-    out[1] = sat_s16(rhe_shift<6>(4 * (h[0] + h[1])));
-    out[2] = sat_s16(rhe_shift<6>(4 * (p[0] + 6 * p[1] + p[2])));
-    out[3] = sat_s16(rhe_shift<6>(h[0] + 6 * h[1] + h[2]));
 }
 
 // (short)(acc / (weight_sum + WEIGHT_EPS)) of normalizeUsingWeightKernel32F; `acc` is the wrapped 16-bit accumulator.
@@ -517,6 +447,8 @@ struct CoarseGeo {  // tile-independent offsets, relative to (X0 >> j, Y0 >> j);
     int g_lo[C_MAXJ], g_n[C_MAXJ];    // host only: support of the tile in Gaussian level 2 + j (marks the G2 tiles k_down2 must compute)
     int a_off[C_MAXJ], g_off[C_MAXJ]; // shared-memory offsets: A in int16 units, G (u8 copy of the a-region) in bytes after A
     int a_total;                      // int16 elements
+    int f_off[C_MAXJ], d_off[C_MAXJ]; // k_coarse (v2): float offsets of the staged fp32 region / of the collapsed fp32 region of level 2 + j
+    int f_total;                      // floats
 };
 struct CoarseView {
     const uint8_t *g[C_MAXJ];  // Gaussian level 2 + j, frame 0
@@ -535,136 +467,207 @@ struct CoarseParams {
     const CoarseView *views;     // device array [n_views]
 };
 
-// pyrUp of the 2x2 quad {x0, x0+1} x {y0, y0+1} (any parity; uniform per call site in practice) from a plane accessor.
-// out[0] = (x0, y0), out[1] = (x0+1, y0), out[2] = (x0, y0+1), out[3] = (x0+1, y0+1); same integers as pyr_up_sample.
-template <typename Acc>
-__device__ __forceinline__ void pyr_up_quad(const Acc &a, int x0, int y0, int n_x, int n_y, int out[4])
+// ======================================================================================================= k_coarse (v2)
+// Restructured like k_blend (the first version kept u8 regions and int16 accumulators in shared memory, 100 -> 86 us): the per-view Gaussian regions are staged once as fp32
+// with pyrUp's index rules applied (so readers need no clamps), every pyrUp is fp32 with the rounding fused into one
+// multiply-add, and the accumulators live in registers: each thread owns four level-2 quads and up to two quads of the
+// coarser levels for the whole view loop (no shared-memory read-modify-write per view).
+__device__ __forceinline__ void up_quad_f(const float *p, int pitch, int px, int py, float r[4])
 {
-    const int px = x0 & 1, py = y0 & 1;
-    const int cb = (x0 >> 1) - 1 + px, rb = (y0 >> 1) - 1 + py;
-    const int c0 = up_idx(cb, n_x), c1 = up_idx(cb + 1, n_x), c2 = up_idx(cb + 2, n_x);
-    int h0[3], h1[3];
+    // p -> (row (y0 >> 1) - 1 + py, column (x0 >> 1) - 1 + px) of the coarser region; same integers as pyr_up_sample at the four positions
+    float ha[3], hb[3];  // horizontal sums for x0 and x0 + 1 (without their factor 4 where the position is odd)
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const int r = up_idx(rb + i, n_y);
-        const int s0 = a(c0, r), s1 = a(c1, r), s2 = a(c2, r);
-        const int tri = s0 + 6 * s1 + s2;
-        h0[i] = px ? 4 * (s0 + s1) : tri;
-        h1[i] = px ? tri : 4 * (s1 + s2);
+        const float s0 = p[i * pitch], s1 = p[i * pitch + 1], s2 = p[i * pitch + 2];
+        const float tri = __fadd_rn(__fmaf_rn(s1, 6.f, s0), s2);
+        ha[i] = px ? __fadd_rn(s0, s1) : tri;
+        hb[i] = px ? tri : __fadd_rn(s1, s2);
     }
-    out[0] = sat_s16(rhe_shift<6>(py ? 4 * (h0[0] + h0[1]) : h0[0] + 6 * h0[1] + h0[2]));
-    out[1] = sat_s16(rhe_shift<6>(py ? 4 * (h1[0] + h1[1]) : h1[0] + 6 * h1[1] + h1[2]));
-    out[2] = sat_s16(rhe_shift<6>(py ? h0[0] + 6 * h0[1] + h0[2] : 4 * (h0[1] + h0[2])));
-    out[3] = sat_s16(rhe_shift<6>(py ? h1[0] + 6 * h1[1] + h1[2] : 4 * (h1[1] + h1[2])));
+    const float sa = px ? 4.f : 1.f, sb = px ? 1.f : 4.f;          // horizontal factor of x0 / x0 + 1
+    const float s0y = py ? 4.f : 1.f, s1y = py ? 1.f : 4.f;        // vertical factor of y0 / y0 + 1
+    const float va0 = py ? __fadd_rn(ha[0], ha[1]) : __fadd_rn(__fmaf_rn(ha[1], 6.f, ha[0]), ha[2]);
+    const float vb0 = py ? __fadd_rn(hb[0], hb[1]) : __fadd_rn(__fmaf_rn(hb[1], 6.f, hb[0]), hb[2]);
+    const float va1 = py ? __fadd_rn(__fmaf_rn(ha[1], 6.f, ha[0]), ha[2]) : __fadd_rn(ha[1], ha[2]);
+    const float vb1 = py ? __fadd_rn(__fmaf_rn(hb[1], 6.f, hb[0]), hb[2]) : __fadd_rn(hb[1], hb[2]);
+    r[0] = __fmaf_rn(va0, sa * s0y * 0.015625f, B2_MAGIC);
+    r[1] = __fmaf_rn(vb0, sb * s0y * 0.015625f, B2_MAGIC);
+    r[2] = __fmaf_rn(va1, sa * s1y * 0.015625f, B2_MAGIC);
+    r[3] = __fmaf_rn(vb1, sb * s1y * 0.015625f, B2_MAGIC);
 }
 
-__global__ void __launch_bounds__(C_THREADS) k_coarse(const __grid_constant__ CoarseParams P)
+constexpr int C2_UQ = 2;  // quads of levels >= 3 per thread (425 quads at num_bands 5, 456 at 7: at most 2 x 256)
+
+__global__ void __launch_bounds__(C_THREADS, 3) k_coarse(const __grid_constant__ CoarseParams P)
 {
     extern __shared__ __align__(16) uint8_t c_smem[];
     const CoarseGeo &Gm = P.geo;
-    int16_t *A = (int16_t *)c_smem;
-    uint8_t *G = c_smem + (size_t)Gm.a_total * 2;
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, c = blockIdx.y, f = blockIdx.z + P.f0, nlev = Gm.nlev;
+    float *F = (float *)c_smem;  // staged regions at Gm.f_off[j], collapsed regions at Gm.d_off[j] (j >= 1)
+    const int t = threadIdx.x, c = blockIdx.y, f = blockIdx.z + P.f0, nlev = Gm.nlev;
     const int X0 = (blockIdx.x % P.tiles_x) * CT, Y0 = (blockIdx.x / P.tiles_x) * CT;
     unsigned views = __ldg(P.tile_views + blockIdx.x);
     if (views & 0x80000000u) return;  // view-sharded mode: another rank owns this canvas strip
-    for (int i = t; i < Gm.a_total; i += C_THREADS) A[i] = 0;
+    // this thread's quads: four of level 2 (quad row (t >> 5) + 8k, quad column t & 31) and up to two of the coarser levels
+    int uj[C2_UQ], ur[C2_UQ], uc[C2_UQ];
+    {
+        int first[C_MAXJ + 1];
+        first[1] = 0;
+        for (int j = 1; j < nlev; ++j) first[j + 1] = first[j] + (Gm.a_n[j] >> 1) * (Gm.a_n[j] >> 1);
+#pragma unroll
+        for (int k = 0; k < C2_UQ; ++k) {
+            const int idx = t + k * C_THREADS;
+            uj[k] = -1; ur[k] = uc[k] = 0;
+            for (int j = 1; j < nlev; ++j)
+                if (idx >= first[j] && idx < first[j + 1]) { const int nq = Gm.a_n[j] >> 1, q = idx - first[j]; uj[k] = j; ur[k] = 2 * (q / nq); uc[k] = 2 * (q % nq); }
+        }
+    }
+    int acc0[4][4], accu[C2_UQ][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc0[k][0] = acc0[k][1] = acc0[k][2] = acc0[k][3] = 0;
+#pragma unroll
+    for (int k = 0; k < C2_UQ; ++k) accu[k][0] = accu[k][1] = accu[k][2] = accu[k][3] = 0;
+
     while (views) {
         const int vi = __ffs(views) - 1;
         views &= views - 1;
         const CoarseView &V = P.views[vi];
         __syncthreads();
-        for (int j = 0; j < nlev; ++j) {  // copy of the a-region of Gaussian level 2 + j (coordinates clamped into the plane)
+        for (int j = 0; j < nlev; ++j) {  // a-region of Gaussian level 2 + j as fp32; out-of-plane positions follow pyrUp's index rules
             const int k = 2 + j, w = V.bw >> k, h = V.bh >> k, n = Gm.a_n[j];
             const uint8_t *g = V.g[j] + (size_t)f * V.g_fs[j] + (size_t)c * w * h;
             const int vx0 = (X0 >> j) + Gm.a_lo[j] - (V.x_tl >> k), vy0 = (Y0 >> j) + Gm.a_lo[j] - (V.y_tl >> k);
-            uint8_t *dst = G + Gm.g_off[j];
+            float *dst = F + Gm.f_off[j];
             if (n == CT && vx0 >= 0 && vx0 + CT <= w && ((((size_t)(g + vx0)) | (size_t)w) & 3) == 0) {
-                // level 2, region inside the plane: 16 aligned words per row instead of 64 byte loads
-                for (int i = t; i < CT * (CT / 4); i += C_THREADS) {
+                for (int i = t; i < CT * (CT / 4); i += C_THREADS) {  // level 2 inside the plane: aligned words
                     const int r = i / (CT / 4), q4 = i - r * (CT / 4);
-                    ((unsigned *)dst)[i] = __ldg((const unsigned *)(g + (size_t)min(max(vy0 + r, 0), h - 1) * w + vx0) + q4);
+                    const unsigned word = __ldg((const unsigned *)(g + (size_t)up_idx(vy0 + r, h) * w + vx0) + q4);
+                    *(float4 *)(dst + r * CT + 4 * q4) = make_float4((float)(word & 0xffu), (float)((word >> 8) & 0xffu), (float)((word >> 16) & 0xffu), (float)(word >> 24));
                 }
                 continue;
             }
-            for (int r = warp; r < n; r += C_THREADS / 32) {
-                const uint8_t *row = g + (size_t)min(max(vy0 + r, 0), h - 1) * w;
-                for (int q = lane; q < n; q += 32) dst[r * n + q] = (uint8_t)ldg_u8(row + min(max(vx0 + q, 0), w - 1));
+            for (int i = t; i < n * n; i += C_THREADS) {
+                const int r = i / n, q = i - r * n;
+                dst[i] = (float)ldg_u8(g + (size_t)up_idx(vy0 + r, h) * w + up_idx(vx0 + q, w));
             }
         }
         __syncthreads();
-        for (int j = 0; j < nlev; ++j) {  // A(j) += trunc(L(j) * W(j)), one 2x2 quad per thread
-            const int k = 2 + j, wv = V.bw >> k, hv = V.bh >> k, n = Gm.a_n[j], nq = n >> 1;
-            const int ax0 = (X0 >> j) + Gm.a_lo[j] - (V.x_tl >> k), ay0 = (Y0 >> j) + Gm.a_lo[j] - (V.y_tl >> k);
-            const uint8_t *gs = G + Gm.g_off[j];
-            int16_t *Aj = A + Gm.a_off[j];
-            const float *wgt = V.w[j];
-            const bool top = j + 1 == nlev;
-            const uint8_t *gu = top ? gs : G + Gm.g_off[j + 1];
-            const int un = top ? 0 : Gm.a_n[j + 1];
-            const int ux0 = top ? 0 : (X0 >> (j + 1)) + Gm.a_lo[j + 1] - (V.x_tl >> (k + 1));
-            const int uy0 = top ? 0 : (Y0 >> (j + 1)) + Gm.a_lo[j + 1] - (V.y_tl >> (k + 1));
-            for (int qr = warp; qr < nq; qr += C_THREADS / 32)
-                for (int qc = lane; qc < nq; qc += 32) {
-                    const int x0 = ax0 + 2 * qc, y0 = ay0 + 2 * qr;
-                    float wq[4];
-                    bool any = false;
+        // ---- level 2: four quads per thread
+        {
+            const int wv = V.bw >> 2, hv = V.bh >> 2;
+            const int ax0 = X0 - (V.x_tl >> 2), ay0 = Y0 - (V.y_tl >> 2);  // a_lo[0] == 0
+            const float *wgt = V.w[0];
+            const bool top = nlev == 1;
+            const int px = ax0 & 1, py = ay0 & 1;
+            const float *G0r = F + Gm.f_off[0];
+            const float *G1r = top ? G0r : F + Gm.f_off[1];
+            const int un = top ? 0 : Gm.a_n[1];
+            const int ux0 = top ? 0 : (X0 >> 1) + Gm.a_lo[1] - (V.x_tl >> 3), uy0 = top ? 0 : (Y0 >> 1) + Gm.a_lo[1] - (V.y_tl >> 3);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int x = x0 + (q & 1), y = y0 + (q >> 1);
-                        wq[q] = ((unsigned)x < (unsigned)wv && (unsigned)y < (unsigned)hv) ? __ldg(wgt + (size_t)y * wv + x) : 0.f;
-                        any |= wq[q] != 0.f;
-                    }
-                    if (!any) continue;  // (short)(L * 0) == 0
-                    int up4[4] = {0, 0, 0, 0};
-                    if (!top) {
-                        auto acc = [&](int xi, int yi) { return (int)gu[(yi - uy0) * un + (xi - ux0)]; };
-                        pyr_up_quad(acc, x0, y0, wv >> 1, hv >> 1, up4);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (wq[q] == 0.f) continue;
-                        const int o = (2 * qr + (q >> 1)) * n + 2 * qc + (q & 1);
-                        Aj[o] = (int16_t)(Aj[o] + rz_s16(__fmul_rn((float)((int)gs[o] - up4[q]), wq[q])));
-                    }
-                }
-        }
-    }
-    __syncthreads();
-    for (int j = nlev - 1; j >= 0; --j) {  // normalise, then C(j) = D(j) + up(C(j+1)), saturating
-        const int cwj = P.cw[j], chj = P.ch[j], n = Gm.a_n[j], nq = n >> 1;
-        const int x00 = (X0 >> j) + Gm.a_lo[j], y00 = (Y0 >> j) + Gm.a_lo[j];
-        int16_t *Aj = A + Gm.a_off[j];
-        const bool top = j + 1 == nlev;
-        const int16_t *Au = top ? Aj : A + Gm.a_off[j + 1];
-        const int un = top ? 0 : Gm.a_n[j + 1];
-        const int ux0 = top ? 0 : (X0 >> (j + 1)) + Gm.a_lo[j + 1], uy0 = top ? 0 : (Y0 >> (j + 1)) + Gm.a_lo[j + 1];
-        const int cwu = top ? 1 : P.cw[j + 1], chu = top ? 1 : P.ch[j + 1];
-        const float *dw = P.dw[j];
-        for (int qr = warp; qr < nq; qr += C_THREADS / 32)
-            for (int qc = lane; qc < nq; qc += 32) {
-                const int x0 = x00 + 2 * qc, y0 = y00 + 2 * qr;
-                int up4[4] = {0, 0, 0, 0};
-                if (!top) {
-                    auto acc = [&](int xi, int yi) { return (int)Au[(yi - uy0) * un + (xi - ux0)]; };
-                    pyr_up_quad(acc, x0, y0, cwu, chu, up4);
-                }
+            for (int k = 0; k < 4; ++k) {
+                const int qr = 2 * ((t >> 5) + 8 * k), qc = 2 * (t & 31);
+                const int x0 = ax0 + qc, y0 = ay0 + qr;
+                float wq[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int x = x0 + (q & 1), y = y0 + (q >> 1);
-                    if ((unsigned)x >= (unsigned)cwj || (unsigned)y >= (unsigned)chj) continue;
-                    const int o = (2 * qr + (q >> 1)) * n + 2 * qc + (q & 1);
-                    Aj[o] = (int16_t)sat_s16(normalize_s16(Aj[o], __ldg(dw + (size_t)y * cwj + x)) + up4[q]);
+                    wq[q] = ((unsigned)x < (unsigned)wv && (unsigned)y < (unsigned)hv) ? __ldg(wgt + (size_t)y * wv + x) : 0.f;
+                }
+                if (wq[0] == 0.f && wq[1] == 0.f && wq[2] == 0.f && wq[3] == 0.f) continue;  // (short)(L * 0) == 0
+                float up[4] = {B2_MAGIC, B2_MAGIC, B2_MAGIC, B2_MAGIC};
+                if (!top) up_quad_f(G1r + ((y0 >> 1) - 1 + py - uy0) * un + ((x0 >> 1) - 1 + px - ux0), un, px, py, up);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float gv = G0r[(qr + (q >> 1)) * CT + qc + (q & 1)];
+                    acc0[k][q] += rz_s16(__fmul_rn(__fsub_rn(__fadd_rn(gv, B2_MAGIC), up[q]), wq[q]));
                 }
             }
+        }
+        // ---- levels >= 3: up to two quads per thread
+#pragma unroll
+        for (int k = 0; k < C2_UQ; ++k) {
+            const int j = uj[k];
+            if (j < 0) continue;
+            const int lv = 2 + j, wv = V.bw >> lv, hv = V.bh >> lv, n = Gm.a_n[j];
+            const int x0 = (X0 >> j) + Gm.a_lo[j] - (V.x_tl >> lv) + uc[k], y0 = (Y0 >> j) + Gm.a_lo[j] - (V.y_tl >> lv) + ur[k];
+            const float *wgt = V.w[j];
+            float wq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int x = x0 + (q & 1), y = y0 + (q >> 1);
+                wq[q] = ((unsigned)x < (unsigned)wv && (unsigned)y < (unsigned)hv) ? __ldg(wgt + (size_t)y * wv + x) : 0.f;
+            }
+            if (wq[0] == 0.f && wq[1] == 0.f && wq[2] == 0.f && wq[3] == 0.f) continue;
+            const bool top = j + 1 == nlev;
+            float up[4] = {B2_MAGIC, B2_MAGIC, B2_MAGIC, B2_MAGIC};
+            if (!top) {
+                const int un = Gm.a_n[j + 1];
+                const int ux0 = (X0 >> (j + 1)) + Gm.a_lo[j + 1] - (V.x_tl >> (lv + 1)), uy0 = (Y0 >> (j + 1)) + Gm.a_lo[j + 1] - (V.y_tl >> (lv + 1));
+                const int px = x0 & 1, py = y0 & 1;
+                up_quad_f(F + Gm.f_off[j + 1] + ((y0 >> 1) - 1 + py - uy0) * un + ((x0 >> 1) - 1 + px - ux0), un, px, py, up);
+            }
+            const float *Gr = F + Gm.f_off[j];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float gv = Gr[(ur[k] + (q >> 1)) * n + uc[k] + (q & 1)];
+                accu[k][q] += rz_s16(__fmul_rn(__fsub_rn(__fadd_rn(gv, B2_MAGIC), up[q]), wq[q]));
+            }
+        }
+    }
+    // ---- normalise and collapse nb -> 2: D(j) = sat(norm(acc(j)) + up(D(j + 1))), coarsest level first; canvas samples only
+    auto collapse_quad = [&](int j, int qr, int qc, const int acc[4], int out[4]) {
+        const int cwj = P.cw[j], chj = P.ch[j];
+        const int x0 = (X0 >> j) + Gm.a_lo[j] + qc, y0 = (Y0 >> j) + Gm.a_lo[j] + qr;  // canvas coordinates of level 2 + j
+        const bool top = j + 1 == nlev;
+        float up[4] = {B2_MAGIC, B2_MAGIC, B2_MAGIC, B2_MAGIC};
+        if (!top) {
+            // the collapsed region of level j + 1 holds canvas samples only: apply pyrUp's index rules on the canvas here
+            const int un = Gm.a_n[j + 1], cwu = P.cw[j + 1], chu = P.ch[j + 1];
+            const int ux0 = (X0 >> (j + 1)) + Gm.a_lo[j + 1], uy0 = (Y0 >> (j + 1)) + Gm.a_lo[j + 1];
+            const int px = x0 & 1, py = y0 & 1, cb = (x0 >> 1) - 1 + px, rb = (y0 >> 1) - 1 + py;
+            const float *D = F + Gm.d_off[j + 1];
+            float nb9[9];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int e = 0; e < 3; ++e) nb9[3 * i + e] = D[(up_idx(rb + i, chu) - uy0) * un + (up_idx(cb + e, cwu) - ux0)];
+            up_quad_f(nb9, 3, px, py, up);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int x = x0 + (q & 1), y = y0 + (q >> 1);
+            out[q] = 0;
+            if ((unsigned)x >= (unsigned)cwj || (unsigned)y >= (unsigned)chj) continue;
+            const int d = max(B2_MAGIC_BITS - 32768, min(B2_MAGIC_BITS + 32767, normalize_s16(acc[q], __ldg(P.dw[j] + (size_t)y * cwj + x)) + __float_as_int(up[q])));
+            out[q] = d - B2_MAGIC_BITS;
+        }
+    };
+    __syncthreads();  // every reader of the staged regions is done before the collapsed regions are written (separate storage, but
+                      // the first write below must also follow the last view's reads of F)
+    for (int j = nlev - 1; j >= 1; --j) {
+#pragma unroll
+        for (int k = 0; k < C2_UQ; ++k) {
+            if (uj[k] != j) continue;
+            int out[4];
+            collapse_quad(j, ur[k], uc[k], accu[k], out);
+            const int n = Gm.a_n[j];
+            float *D = F + Gm.d_off[j];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) D[(ur[k] + (q >> 1)) * n + uc[k] + (q & 1)] = (float)out[q];
+        }
         __syncthreads();
     }
     {
         const int cw2 = P.cw[0], ch2 = P.ch[0];
         int16_t *o = P.c2 + (size_t)f * P.c2_fs + (size_t)c * cw2 * ch2;
-        for (int i = t; i < CT * CT; i += C_THREADS) {
-            const int y = Y0 + i / CT, x = X0 + (i & (CT - 1));
-            if (y < ch2 && x < cw2) o[(size_t)y * cw2 + x] = A[Gm.a_off[0] + i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int qr = 2 * ((t >> 5) + 8 * k), qc = 2 * (t & 31);
+            int out[4];
+            collapse_quad(0, qr, qc, acc0[k], out);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int x = X0 + qc + (q & 1), y = Y0 + qr + (q >> 1);
+                if (y < ch2 && x < cw2) o[(size_t)y * cw2 + x] = (int16_t)out[q];
+            }
         }
     }
 }
@@ -694,189 +697,8 @@ struct BlendParams {
     BlendView v[MAXV];
 };
 
-__global__ void __launch_bounds__(BL_THREADS, 3) k_blend_v1(const __grid_constant__ BlendParams P, const __grid_constant__ OutPtrs outs, size_t out_pitch)
-{
-    __shared__ uint8_t sG1[3][BL_R1H][BL_R1W + 2];
-    __shared__ uint8_t sG2[3][BL_R2H][BL_R2W];
-    __shared__ int16_t sC2[3][BL_R2H][BL_R2W];
-    __shared__ int16_t sD1[3][BL_R1H][BL_R1W];
-    __shared__ __align__(16) int16_t sOut[BL_TH][BL_TW * 3];
-    const int t = threadIdx.x, f = blockIdx.z + P.f0, nb = P.nb;
-    const int tx0 = blockIdx.x * BL_TW, ty0 = blockIdx.y * BL_TH;
-    const int lx = (t & 7) * 8, ly = t >> 3;  // this thread's 8 consecutive level-0 samples
-    const int px0 = tx0 + lx, py = ty0 + ly;
-    int acc0[3][8], acc1[3][4];
-    float dw0[8], dw1[4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { dw0[i] = 0.f; acc0[0][i] = acc0[1][i] = acc0[2][i] = 0; }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { dw1[q] = 0.f; acc1[0][q] = acc1[1][q] = acc1[2][q] = 0; }
-    const int qr1 = 2 * (t / BL_QW), qc1 = 2 * (t % BL_QW);  // this thread's level-1 quad (threads < BL_NQ)
-
-    unsigned views = __ldg(P.tile_views + blockIdx.y * P.tiles_x + blockIdx.x);
-    if (views & 0x80000000u) return;  // view-sharded mode: another rank owns this canvas strip
-    while (views) {
-        const int vi = __ffs(views) - 1;  // ascending view order: the weight sums below add in the reference's order
-        views &= views - 1;
-        const BlendView &V = P.v[vi];
-        const int w0 = V.bw, h0 = V.bh, w1 = w0 >> 1, h1 = h0 >> 1, w2 = w0 >> 2, h2 = h0 >> 2;
-        const int v1x0 = (tx0 >> 1) - 1 - (V.x_tl >> 1), v1y0 = (ty0 >> 1) - 1 - (V.y_tl >> 1);  // plane coords of region (0,0)
-        __syncthreads();
-        if (nb >= 1) {  // G1 region 34 x 18 (written by k_down2) and G2 region 20 x 12, coordinates clamped like pyrUp does
-            const uint8_t *g1 = V.g1 + (size_t)f * V.g1_fs;
-            for (int i = t; i < 3 * BL_R1H * BL_R1W; i += BL_THREADS) {
-                const int c = i / (BL_R1H * BL_R1W), rem = i - c * (BL_R1H * BL_R1W);
-                const int r = rem / BL_R1W, q = rem - r * BL_R1W;
-                sG1[c][r][q] = (uint8_t)ldg_u8(g1 + ((size_t)c * h1 + up_idx(v1y0 + r, h1)) * w1 + up_idx(v1x0 + q, w1));
-            }
-            if (nb >= 2) {
-                const uint8_t *g2 = V.g2 + (size_t)f * V.g2_fs;
-                const int ux0 = (tx0 >> 2) - 2 - (V.x_tl >> 2), uy0 = (ty0 >> 2) - 2 - (V.y_tl >> 2);
-                for (int i = t; i < 3 * BL_R2H * BL_R2W; i += BL_THREADS) {
-                    const int c = i / (BL_R2H * BL_R2W), rem = i - c * (BL_R2H * BL_R2W);
-                    const int r = rem / BL_R2W, q = rem - r * BL_R2W;
-                    sG2[c][r][q] = (uint8_t)ldg_u8(g2 + ((size_t)c * h2 + up_idx(uy0 + r, h2)) * w2 + up_idx(ux0 + q, w2));
-                }
-            }
-        }
-        __syncthreads();
-        // ---- level 0: this thread's 8 samples
-        const int qx0 = px0 - V.x_tl, qy = py - V.y_tl;
-        if ((unsigned)qx0 < (unsigned)w0 && (unsigned)qy < (unsigned)h0) {
-            const uint2 mm = __ldg((const uint2 *)(V.m0 + (size_t)qy * w0 + qx0));
-            float wv[8];
-            bool any = false;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const unsigned m = ((i < 4 ? mm.x : mm.y) >> (8 * (i & 3))) & 0xff;
-                wv[i] = __fmul_rn((float)(1. / 255.), (float)m);
-                dw0[i] = __fadd_rn(dw0[i], wv[i]);
-                any |= m != 0;
-            }
-            if (any) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const uint2 gg = __ldg((const uint2 *)(V.g0 + (size_t)f * V.g0_fs + ((size_t)c * h0 + qy) * w0 + qx0));
-                    const unsigned ga = gg.x, gb = gg.y;
-                    int up[8];
-                    if (nb >= 1) {
-                        pyr_up_row8_region<uint8_t, BL_R1W + 2>(&sG1[c][0][0], v1x0, v1y0, qx0, qy, w1, h1, up);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) up[i] = 0;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int g = ((i < 4 ? ga : gb) >> (8 * (i & 3))) & 0xff;
-                        acc0[c][i] += rz_s16(__fmul_rn((float)(g - up[i]), wv[i]));
-                    }
-                }
-            }
-        }
-        // ---- level 1: one 2x2 quad of the 34 x 18 region per thread
-        if (nb >= 1 && t < BL_NQ) {
-            const int u2x0 = (tx0 >> 2) - 2 - (V.x_tl >> 2), u2y0 = (ty0 >> 2) - 2 - (V.y_tl >> 2);
-            const int x0 = v1x0 + qc1, y0 = v1y0 + qr1;  // plane coordinates, both odd
-            float wq[4];
-            bool any = false;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int x = x0 + (q & 1), y = y0 + (q >> 1);
-                wq[q] = 0.f;
-                if ((unsigned)x < (unsigned)w1 && (unsigned)y < (unsigned)h1) {
-                    wq[q] = __ldg(V.w1 + (size_t)y * w1 + x);
-                    dw1[q] = __fadd_rn(dw1[q], wq[q]);
-                    any |= wq[q] != 0.f;
-                }
-            }
-            if (any) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    int up4[4] = {0, 0, 0, 0};
-                    if (nb >= 2) {
-                        auto a = [&](int xi, int yi) { return (int)sG2[c][yi - u2y0][xi - u2x0]; };
-                        pyr_up_quad_odd(a, x0, y0, w2, h2, up4);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (wq[q] != 0.f) acc1[c][q] += rz_s16(__fmul_rn((float)((int)sG1[c][qr1 + (q >> 1)][qc1 + (q & 1)] - up4[q]), wq[q]));
-                }
-            }
-        }
-    }
-    // ---- collapse: C2 (global) -> D1 (shared) -> D0 -> output
-    if (nb >= 2) {
-        const int16_t *c2 = P.c2 + (size_t)f * P.c2_fs;
-        const int ux0 = (tx0 >> 2) - 2, uy0 = (ty0 >> 2) - 2;
-        for (int i = t; i < 3 * BL_R2H * BL_R2W; i += BL_THREADS) {
-            const int c = i / (BL_R2H * BL_R2W), rem = i - c * (BL_R2H * BL_R2W);
-            const int r = rem / BL_R2W, q = rem - r * BL_R2W;
-            sC2[c][r][q] = __ldg(c2 + ((size_t)c * P.ch2 + up_idx(uy0 + r, P.ch2)) * P.cw2 + up_idx(ux0 + q, P.cw2));
-        }
-        __syncthreads();
-    }
-    if (nb >= 1) {
-        if (t < BL_NQ) {
-            const int ux0 = (tx0 >> 2) - 2, uy0 = (ty0 >> 2) - 2;
-            const int x0 = (tx0 >> 1) - 1 + qc1, y0 = (ty0 >> 1) - 1 + qr1;  // canvas coordinates, both odd
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                int up4[4] = {0, 0, 0, 0};
-                if (nb >= 2) {
-                    auto a = [&](int xi, int yi) { return (int)sC2[c][yi - uy0][xi - ux0]; };
-                    pyr_up_quad_odd(a, x0, y0, P.cw2, P.ch2, up4);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int x = x0 + (q & 1), y = y0 + (q >> 1);
-                    if ((unsigned)x < (unsigned)P.cw1 && (unsigned)y < (unsigned)P.ch1)
-                        sD1[c][qr1 + (q >> 1)][qc1 + (q & 1)] = (int16_t)sat_s16(normalize_s16(acc1[c][q], dw1[q]) + up4[q]);
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (px0 < P.cw0 && py < P.ch0) {
-        const int X1 = (tx0 >> 1) - 1, Y1 = (ty0 >> 1) - 1;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            int up[8];
-            if (nb >= 1) {
-                pyr_up_row8_region<int16_t, BL_R1W>(&sD1[c][0][0], X1, Y1, px0, py, P.cw1, P.ch1, up);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) up[i] = 0;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int d = sat_s16(normalize_s16(acc0[c][i], dw0[i]) + up[i]);
-                sOut[ly][(lx + i) * 3 + c] = dw0[i] > 1e-5f ? (int16_t)d : (int16_t)0;  // dst_mask = dst_band_weights_[0] > WEIGHT_EPS
-            }
-        }
-    }
-    __syncthreads();
-    // ---- cropped, interleaved CV_16SC3 store: 16-byte vectors where the caller's buffer allows
-    const int n_px = min(BL_TW, P.out_w - tx0), n_rows = min(BL_TH, P.out_h - ty0);
-    if (n_px <= 0 || n_rows <= 0) return;
-    char *obase = (char *)outs.out[f] + (size_t)tx0 * 6;
-    const bool vec_ok = ((((size_t)obase) | out_pitch) & 15) == 0;
-    const int row_bytes = n_px * 6;
-    for (int r = t >> 5; r < n_rows; r += BL_THREADS / 32) {  // one warp per row: 24 chunks of 16 bytes
-        const int ck = t & 31, b0 = ck * 16;
-        if (ck >= BL_TW * 6 / 16 || b0 >= row_bytes) continue;
-        char *o = obase + (size_t)(ty0 + r) * out_pitch + b0;
-        const int16_t *sp = &sOut[r][ck * 8];
-        if (vec_ok && b0 + 16 <= row_bytes) {
-            *(uint4 *)o = *(const uint4 *)sp;
-        } else {
-            const int n = min(8, (row_bytes - b0) >> 1);
-            for (int e = 0; e < n; ++e) ((int16_t *)o)[e] = sp[e];
-        }
-    }
-}
-
 // ======================================================================================================== k_blend (v2)
-// Same result as k_blend_v1, restructured around what the profile showed (56 % issue utilisation, 80 registers, the two
+// Restructured (from a first version with integer pyrUp and one pass over the views) around what the profile showed (56 % issue utilisation, 80 registers, the two
 // pyrUp evaluations per output sample dominating):
 //   * the level-1 / level-2 regions are staged ONCE per view as fp32 (clamped like pyrUp's index rules, so the readers
 //     need no edge cases) and every pyrUp is evaluated in fp32: all partial sums are integers below 2^24, the final
@@ -890,11 +712,9 @@ constexpr int B2_G1P = 44, B2_G1OFF = 4;    // fp32 level-1 region: row pitch (f
 constexpr int B2_G2P = 24, B2_G2OFF = 2;    // fp32 level-2 region
 constexpr int B2_G1F = 3 * BL_R1H * B2_G1P, B2_G2F = 3 * BL_R2H * B2_G2P;  // floats per staged region
 constexpr int B2_ITEMS = 3 * BL_NQ;         // (channel, level-1 quad) work items
-constexpr float B2_MAGIC = 12582912.f;      // 1.5 * 2^23
-constexpr int B2_MAGIC_BITS = 0x4B400000;
 
 // pyrUp of the quad {x0, x0+1} x {y0, y0+1}, x0 and y0 odd, from an fp32 region; p points at (row y0 >> 1, column x0 >> 1).
-// r[q] = value + 1.5 * 2^23 (the integer sits in the low mantissa bits); same integers as pyr_up_quad_odd.
+// r[q] = value + 1.5 * 2^23 (the integer sits in the low mantissa bits); same integers as pyr_up_sample at the four positions.
 __device__ __forceinline__ void up_quad_odd_f(const float *p, int pitch, float r[4])
 {
     float h[3], s[3];

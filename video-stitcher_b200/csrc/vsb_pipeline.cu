@@ -940,11 +940,16 @@ static void coarse_geometry(int nb, CoarseGeo &g)
         g.g_off[j] = g_total; g_total += (int)align_up((size_t)g.a_n[j] * g.a_n[j], 16);
     }
     g.a_total = a_total;
+    int f_total = 0;
+    for (int j = 0; j < nlev; ++j) { g.f_off[j] = f_total; f_total += (int)align_up((size_t)g.a_n[j] * g.a_n[j], 4); }
+    for (int j = 1; j < nlev; ++j) { g.d_off[j] = f_total; f_total += (int)align_up((size_t)g.a_n[j] * g.a_n[j], 4); }
+    g.f_total = f_total;
 }
 static size_t coarse_smem_bytes(const CoarseGeo &g)
 {
     const int j = g.nlev - 1;
-    return (size_t)g.a_total * 2 + g.g_off[j] + align_up((size_t)g.a_n[j] * g.a_n[j], 16);
+    (void)j;
+    return (size_t)g.f_total * 4;
 }
 
 struct HostWeights {  // nonzero structure of one view's static weight pyramid
