@@ -254,6 +254,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--batch", type=int, default=8, help="frames per vsb_compose submission (F)")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--ring", type=int, default=RING, help="distinct frame sets resident in HBM (inputs must exceed L2: 8 at cfg2, 2 suffice at cfg4)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -301,7 +302,7 @@ def main():
     out_pitch = (OW * 6 + 255) // 256 * 256  # pitched rows like cv::cuda::GpuMat (cudaMallocPitch): 16-byte vector stores
 
     # ring of RING frame sets (each rank gets different frames: frame-level data parallelism)
-    n_sets = max(RING, F)
+    n_sets = max(args.ring, F)
     host_sets = []
     for f in range(n_sets):
         host_sets.append([torch.from_numpy(S.frame(i, f + vsb200.dist.ring_seed_offset(rank, n_sets), cfg["src_w"], cfg["src_h"])).pin_memory() for i in range(n)])

@@ -92,6 +92,14 @@ def test_host_voronoi_matches_reference(vsb, og):
         assert np.array_equal(np.packbits(m > 0, axis=1), gold[f"voronoi_{n}_{pano}_{proj}_{i}"])
 
 
+def test_consumer_geometry_matches_oracle(vsb, og):
+    """Host-only part of the consumer epilogue: the image height of 360_stitcher/timed.cpp:254-270 (no device needed)."""
+    lib = vsb.lib()
+    for (w, h, ow, oh) in ((3839, 627, 4096, 2048), (7678, 1253, 4096, 2048), (383, 63, 512, 256), (100, 400, 64, 64), (1, 1, 2, 2)):
+        for keep in (0, 1):
+            assert lib.vsb_consumer_image_height(w, h, ow, oh, keep) == og.consumer_image_height(w, h, ow, oh, bool(keep))
+
+
 def test_unit_weight_normalisation_shortcut_is_exact():
     """k_blend / k_coarse replace trunc(acc / (1 + 1e-5f)) by acc - sign(acc) when the weight sum is exactly 1
     (vsb_blend_kernels.cuh normalize_s16): exhaustive over the 16-bit accumulator range, in fp32."""

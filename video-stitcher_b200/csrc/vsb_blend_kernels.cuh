@@ -780,7 +780,10 @@ __device__ __noinline__ void up_row8_f_edge(const float *reg, int ox, int oy, in
 // U8: the consumer's `mat.convertTo(mat_8u, CV_8U)` (360_stitcher/timed.cpp:250) is applied in the final store: the
 // panorama leaves as CV_8UC3 (saturate_cast<uchar> of the CV_16SC3 sample) -- half the bytes to write and to download.
 template <bool U8>
-__global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__ BlendParams P, const __grid_constant__ OutPtrs outs, size_t out_pitch)
+#ifndef VSB_BL_MINB
+#define VSB_BL_MINB 4
+#endif
+__global__ void __launch_bounds__(BL_THREADS, VSB_BL_MINB) k_blend(const __grid_constant__ BlendParams P, const __grid_constant__ OutPtrs outs, size_t out_pitch)
 {
     // staging area: fp32 G1 and G2 regions of the current view; re-used for the interleaved output tile at the end
     __shared__ __align__(16) float sStage[B2_G1F + B2_G2F];
@@ -790,8 +793,12 @@ __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__
     static_assert(sizeof(float) * (B2_G1F + B2_G2F) >= sizeof(int16_t) * BL_TH * BL_TW * 3, "output tile must fit the staging area");
     const int t = threadIdx.x, f = blockIdx.z + P.f0;
     const int tx0 = blockIdx.x * BL_TW, ty0 = blockIdx.y * BL_TH;
-    const unsigned views_all = __ldg(P.tile_views + blockIdx.y * P.tiles_x + blockIdx.x);
-    if (views_all & 0x80000000u) return;  // view-sharded mode: another rank owns this canvas strip
+    const unsigned views_word = __ldg(P.tile_views + blockIdx.y * P.tiles_x + blockIdx.x);
+    if (views_word & 0x80000000u) return;  // view-sharded mode: another rank owns this canvas strip
+    // interior tile (static flag): one view whose level-0 / level-1 weights are exactly 1 over everything this tile reads, so the
+    // mask, the weights and the weight sums need not be loaded (they are 1) -- the arithmetic below is unchanged
+    const bool interior = (views_word & 0x40000000u) != 0;
+    const unsigned views_all = views_word & 0x3fffffffu;
     // level-0 mapping: a warp holds four rows of one parity, a thread 8 consecutive samples
     const int warp = t >> 5, lane = t & 31;
     const int ly = (warp >> 1) * 8 + (lane >> 3) * 2 + (warp & 1), lx = (lane & 7) * 8;
@@ -799,8 +806,8 @@ __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__
     const bool row_odd = warp & 1;
     const int reg_off = (ly >> 1) * B2_G1P + (lx >> 1) + B2_G1OFF;  // region sample (row (y>>1) - 1, column (x0>>1) - 1) of this thread
     // static weight sum of this thread's 8 samples: exactly 1 on most of the panorama (one view, full weight)
-    bool dw_all_one = false;
-    if (px0 < P.cw0 && py < P.ch0) {
+    bool dw_all_one = interior;
+    if (!interior && px0 < P.cw0 && py < P.ch0) {
         const float4 da = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0)), db = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0 + 4));
         dw_all_one = da.x == 1.f && da.y == 1.f && da.z == 1.f && da.w == 1.f && db.x == 1.f && db.y == 1.f && db.z == 1.f && db.w == 1.f;
     }
@@ -911,7 +918,7 @@ __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int x = x0 + (q & 1), y = y0 + (q >> 1);
-                wq[q] = ((unsigned)x < (unsigned)w1 && (unsigned)y < (unsigned)h1) ? __ldg(V.w1 + (size_t)y * w1 + x) : 0.f;
+                wq[q] = interior ? 1.f : (((unsigned)x < (unsigned)w1 && (unsigned)y < (unsigned)h1) ? __ldg(V.w1 + (size_t)y * w1 + x) : 0.f);
                 any |= wq[q] != 0.f;
             }
             if (!any) continue;
@@ -938,7 +945,7 @@ __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__
         for (int q = 0; q < 4; ++q) {
             const int x = x0 + (q & 1), y = y0 + (q >> 1);
             if ((unsigned)x >= (unsigned)P.cw1 || (unsigned)y >= (unsigned)P.ch1) continue;
-            const float dw = __ldg(P.dw1 + (size_t)y * P.cw1 + x);
+            const float dw = interior ? 1.f : __ldg(P.dw1 + (size_t)y * P.cw1 + x);
             const int d = max(B2_MAGIC_BITS - 32768, min(B2_MAGIC_BITS + 32767, normalize_s16(acc1[k][q], dw) + __float_as_int(up[q])));  // biased, see pass 2
             sD1f[(c * BL_R1H + qr1 + (q >> 1)) * B2_G1P + B2_G1OFF + qc1 + (q & 1)] = __fsub_rn(__int_as_float(d), B2_MAGIC);
         }
@@ -960,8 +967,11 @@ __global__ void __launch_bounds__(BL_THREADS, 4) k_blend(const __grid_constant__
         const int w0 = V.bw, h0 = V.bh;
         const int qx0 = px0 - V.x_tl, qy = py - V.y_tl;
         if ((unsigned)qx0 >= (unsigned)w0 || (unsigned)qy >= (unsigned)h0) continue;
-        const uint2 mm = __ldg((const uint2 *)(V.m0 + (size_t)qy * w0 + qx0));
-        if ((mm.x | mm.y) == 0u) continue;  // (short)(L * 0) == 0
+        uint2 mm = make_uint2(0xffffffffu, 0xffffffffu);
+        if (!interior) {
+            mm = __ldg((const uint2 *)(V.m0 + (size_t)qy * w0 + qx0));
+            if ((mm.x | mm.y) == 0u) continue;  // (short)(L * 0) == 0
+        }
         uint2 gg[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) gg[c] = __ldg((const uint2 *)(V.g0 + (size_t)f * V.g0_fs + ((size_t)c * h0 + qy) * w0 + qx0));

@@ -954,6 +954,16 @@ static size_t coarse_smem_bytes(const CoarseGeo &g)
 
 struct HostWeights {  // nonzero structure of one view's static weight pyramid
     std::vector<std::vector<uint8_t>> nz;  // [level][h * w]: weight != 0
+    std::vector<uint8_t> one[2];           // levels 0 and 1: weight == 1.0f exactly
+    bool all_one(int k, int x0, int y0, int x1, int y1) const  // half-open plane rect; false when it leaves the plane
+    {
+        if (x0 < 0 || y0 < 0 || x1 > w[k] || y1 > h[k]) return false;
+        for (int y = y0; y < y1; ++y) {
+            const uint8_t *r = one[k].data() + (size_t)y * w[k];
+            for (int x = x0; x < x1; ++x) if (!r[x]) return false;
+        }
+        return true;
+    }
     int w[MAXL], h[MAXL];
     bool any(int k, int x0, int y0, int x1, int y1) const  // half-open plane rect, clipped here
     {
@@ -981,6 +991,10 @@ static int build_fast_plan(vsb_stitcher *s)
             CK(cudaMemcpy(tmp.data(), V.weight[k], tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
             hw[i].nz[k].resize(tmp.size());
             for (size_t j = 0; j < tmp.size(); ++j) hw[i].nz[k][j] = tmp[j] != 0.f;
+            if (k <= 1) {
+                hw[i].one[k].resize(tmp.size());
+                for (size_t j = 0; j < tmp.size(); ++j) hw[i].one[k][j] = tmp[j] == 1.0f;
+            }
         }
     }
     for (int i = 0; i < n; ++i) {
@@ -1001,6 +1015,21 @@ static int build_fast_plan(vsb_stitcher *s)
                 if (hw[i].any(0, x0, y0, x0 + BL_TW, y0 + BL_TH) || hw[i].any(1, x1, y1, x1 + BL_R1W, y1 + BL_R1H))
                     bviews[(size_t)ty * s->blend_tiles_x + tx] |= 1u << i;
             }
+    // interior tiles (bit 30): exactly one view, whose level-0 and level-1 weights are exactly 1 over everything the tile reads --
+    // k_blend then skips the mask / weight / weight-sum loads (most of the panorama away from the seams)
+    for (int ty = 0; ty < s->blend_tiles_y; ++ty)
+        for (int tx = 0; tx < s->blend_tiles_x; ++tx) {
+            uint32_t &b = bviews[(size_t)ty * s->blend_tiles_x + tx];
+            if (b == 0 || (b & (b - 1)) != 0) continue;
+            int i = 0;
+            while (!(b >> i & 1)) ++i;
+            const View &V = s->v[i];
+            const int x0 = tx * BL_TW - V.x_tl, y0 = ty * BL_TH - V.y_tl;
+            const int x1 = fdiv2(tx * BL_TW) - 1 - (V.x_tl >> 1), y1 = fdiv2(ty * BL_TH) - 1 - (V.y_tl >> 1);
+            if ((tx + 1) * BL_TW <= s->cw[0] && (ty + 1) * BL_TH <= s->ch[0] && x1 >= 0 && y1 >= 0 &&
+                hw[i].all_one(0, x0, y0, x0 + BL_TW, y0 + BL_TH) && hw[i].all_one(1, x1, y1, x1 + BL_R1W, y1 + BL_R1H))
+                b |= 0x40000000u;
+        }
     // ---- k_coarse: views with weight at any level >= 2 per 64 x 64 level-2 canvas tile
     coarse_geometry(nb, s->cgeo);
     s->coarse_smem = coarse_smem_bytes(s->cgeo);
