@@ -2070,7 +2070,7 @@ int vsb_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, siz
     r = adopt_meshes(s, st);
     if (r != VSB_OK) return r;
     static const bool no_split = std::getenv("VSB_NO_SPLIT") != nullptr;
-    if (n_frames >= 2 && s->fast && !s->profiling && !no_split) {
+    if (n_frames >= 4 && s->fast && !s->profiling && !no_split) {  // (with 2-3 frames the halves lose the per-tile table reuse: measured slower)
         // Two half-batches on two internal streams: the short kernels (k_down_tail: 144 CTAs, k_coarse: ~1.2 waves) and the
         // last partial wave of every kernel of one half overlap with the other half's work.  Frame slots are disjoint; the
         // static tables are built on the caller's stream before the fork.
