@@ -211,12 +211,17 @@ def test_full_size_config4_compose(cuda, og):
 
 def test_batched_compose_and_mesh_swap(cuda, og):
     import vsb200
-    orig, grig, kw = _rigs("small4", inject=False, max_batch=3)
-    fr = [[vsb200.synth.frame(i, f, kw["src_w"], kw["src_h"]) for i in range(kw["n_views"])] for f in range(3)]
+    orig, grig, kw = _rigs("small4", inject=False, max_batch=5)
+    fr = [[vsb200.synth.frame(i, f, kw["src_w"], kw["src_h"]) for i in range(kw["n_views"])] for f in range(5)]
     want = [orig.compose(f)[0] for f in fr]
-    got = grig.compose(fr)
-    for f in range(3):
+    got = grig.compose(fr)  # 5 frames: two half-batches (3 + 2) on the handle's two internal streams
+    for f in range(5):
         _eq(got[f], want[f], f"batched frame {f}")
+    assert grig.st.last_launch_count() == 12
+    got3 = grig.compose(fr[1:4])  # 3 frames: one submission on the caller's stream
+    for f in range(3):
+        _eq(got3[f], want[1 + f], f"3-frame batch, frame {f}")
+    assert grig.st.last_launch_count() == 6
     # install a different mesh (recalibration, config 5) and compose again
     for i in range(kw["n_views"]):
         mx, my = vsb200.synth.mesh(*orig.sizes[i], phase=0.7)
@@ -277,32 +282,33 @@ def test_nv12_input_and_u8_output(cuda, og, case):
     import vsb200
     from tests.gpu_util import dev, host, stream
     B = vsb200.binding
-    orig, grig, kw = _rigs(case, inject=False, max_batch=2)
+    NF = 4 if case == "small4" else 2   # 4 frames: the split (two-stream) submission with NV12 staging
+    orig, grig, kw = _rigs(case, inject=False, max_batch=NF)
     n, sw, sh = kw["n_views"], kw["src_w"], kw["src_h"]
-    nv = [[vsb200.synth.frame_nv12(i, f, sw, sh) for i in range(n)] for f in range(2)]
+    nv = [[vsb200.synth.frame_nv12(i, f, sw, sh) for i in range(n)] for f in range(NF)]
     want16 = [orig.compose([og.nv12_to_bgr(a, sw, sh) for a in fr])[0] for fr in nv]
     want8 = [og.s16_to_u8(w) for w in want16]
     W, H = grig.roi_final[2], grig.roi_final[3]
     srcs = [dev(a) for fr in nv for a in fr]
     # NV12 in, CV_16SC3 out
     grig.st.set_formats(B.IN_NV12, B.OUT_S16C3)
-    outs = [torch.full((H, W, 3), -12345, dtype=torch.int16, device="cuda") for _ in range(2)]
+    outs = [torch.full((H, W, 3), -12345, dtype=torch.int16, device="cuda") for _ in range(NF)]
     grig.st.compose([t.data_ptr() for t in srcs], sw, [o.data_ptr() for o in outs], W * 6, stream())
-    for f in range(2):
+    for f in range(NF):
         _eq(host(outs[f]), want16[f], f"NV12 in, frame {f}")
     # NV12 in, CV_8UC3 out, pitched output
     grig.st.set_formats(B.IN_NV12, B.OUT_U8C3)
     pitch = (W * 3 + 63) // 64 * 64
-    outs8 = [torch.full((H, pitch), 99, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    outs8 = [torch.full((H, pitch), 99, dtype=torch.uint8, device="cuda") for _ in range(NF)]
     grig.st.compose([t.data_ptr() for t in srcs], sw, [o.data_ptr() for o in outs8], pitch, stream())
-    for f in range(2):
+    for f in range(NF):
         got = host(outs8[f])
         _eq(got[:, :W * 3].reshape(H, W, 3), want8[f], f"NV12 in, CV_8UC3 out, frame {f}")
         assert (got[:, W * 3:] == 99).all(), "row padding must stay untouched"
     # host entry point with both formats
-    houts = [np.zeros((H, W, 3), np.uint8) for _ in range(2)]
+    houts = [np.zeros((H, W, 3), np.uint8) for _ in range(NF)]
     grig.st.compose_host([a.ctypes.data for fr in nv for a in fr], sw, [o.ctypes.data for o in houts], W * 3)
-    for f in range(2):
+    for f in range(NF):
         _eq(houts[f], want8[f], f"host path NV12 -> CV_8UC3 frame {f}")
     # BGR in, CV_8UC3 out through feed + blend
     grig.st.set_formats(B.IN_BGR8, B.OUT_U8C3)
@@ -342,6 +348,54 @@ def test_consumer_epilogue(cuda, og, case, out_w, out_h):
     yuv = torch.zeros(out_w * out_h * 3 // 2, dtype=torch.uint8, device="cuda")
     grig.st.consume(d_pano.data_ptr(), pitch, out_w, out_h, B.CONSUME_I420, yuv.data_ptr(), out_w, stream=stream())
     _eq(host(yuv), og.consume(pano8, out_w, out_h, 1), "letter-boxed I420 frame")
+
+
+def test_recalibration_thread_concurrent_with_compose(cuda, og):
+    """BASELINE config 5: a second host thread keeps publishing new CPW meshes (vsb_set_mesh) while the main thread submits
+    batches.  Every composed frame must be exactly the panorama of ONE of the published meshes (never a mixture within a view,
+    never a half-written map), and the last publication must be the one in effect afterwards."""
+    import threading
+    import vsb200
+    orig, grig, kw = _rigs("small4", inject=False, max_batch=4)
+    n = kw["n_views"]
+    fr = [[vsb200.synth.frame(i, f, kw["src_w"], kw["src_h"]) for i in range(n)] for f in range(4)]
+    V = 1  # the view whose mesh alternates (the others keep theirs, so a frame has exactly two possible panoramas)
+    meshes = [vsb200.synth.mesh(*orig.sizes[V], phase=ph) for ph in (0.0, 0.9)]
+    want = []
+    for m in meshes:
+        orig.set_mesh(V, *m)
+        want.append([orig.compose(f)[0] for f in fr])
+    stop, installs, errors = threading.Event(), [0], []
+
+    def recalibrate():
+        k = 1
+        try:
+            while not stop.is_set():
+                grig.set_mesh(V, *meshes[k & 1])
+                installs[0] += 1
+                k += 1
+        except Exception as e:  # surfaces in the main thread's assert
+            errors.append(e)
+
+    th = threading.Thread(target=recalibrate, daemon=True)
+    th.start()
+    seen = [0, 0]
+    try:
+        for it in range(25):
+            got = grig.compose(fr)
+            for f in range(4):
+                which = [np.array_equal(got[f], want[k][f]) for k in range(2)]
+                assert any(which), f"iteration {it} frame {f}: panorama matches neither published mesh"
+                seen[which.index(True)] += 1
+    finally:
+        stop.set()
+        th.join()
+    assert not errors, errors
+    assert installs[0] >= 2
+    grig.set_mesh(V, *meshes[0])
+    got = grig.compose(fr)
+    for f in range(4):
+        _eq(got[f], want[0][f], f"after the last publication, frame {f}")
 
 
 def test_compose_host_roundtrip(cuda, og):
