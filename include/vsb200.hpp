@@ -176,6 +176,19 @@ public:
         check(vsb_compose(h_, (int)outs.size(), sp.data(), srcs[0].step, op.data(), outs[0].step, stream));
     }
     /* dst_roi_final_ (the Rect `blend` crops to) and the padded dst_roi_ */
+    /* the consumer thread after blend (360_stitcher/timed.cpp:254-315), on the device: resize(INTER_LINEAR) of the CV_8UC3
+       panorama (setFormats(..., VSB_OUT_U8C3)) to out.width x consumerImageHeight, then VSB_CONSUME_RGB (cvtColor BGR2RGB) or
+       VSB_CONSUME_I420 (black bars to out.height + cvtColor BGR2YUV_I420: the frame the encoder is fed) */
+    int consumerImageHeight(Size out, bool keep_aspect_ratio = true) const
+    {
+        const Rect r = resultRoi();
+        return vsb_consumer_image_height(r.width, r.height, out.width, out.height, keep_aspect_ratio ? 1 : 0);
+    }
+    void consume(const DeviceMat &pano_8u, Size out, bool keep_aspect_ratio, int format, void *d_out, size_t out_pitch, Stream stream)
+    {
+        check(vsb_consume(h_, (const uint8_t *)pano_8u.data, pano_8u.step, out.width, out.height, keep_aspect_ratio ? 1 : 0, format,
+                          (uint8_t *)d_out, out_pitch, stream));
+    }
     Rect resultRoi() const { int a[4], b[4], nb; check(vsb_get_roi(h_, a, b, &nb)); return Rect(a[0], a[1], a[2], a[3]); }
     Rect paddedRoi() const { int a[4], b[4], nb; check(vsb_get_roi(h_, a, b, &nb)); return Rect(b[0], b[1], b[2], b[3]); }
 

@@ -470,6 +470,19 @@ def test_cpp_host_demo_matches_oracle(cuda, og, tmp_path):
     got = np.fromfile(fout, np.int16).reshape(nf, H, W, 3)
     for f in range(nf):
         _eq(got[f], orig.compose(frames[f])[0], f"C++ demo frame {f}")
+    # wire-to-wire variant: NV12 frames in, letter-boxed I420 frames out (setFormats + consume through the C++ adapter)
+    ow, oh = 1280, 640
+    nv = [[vsb200.synth.frame_nv12(i, f, sw, sh) for i in range(n)] for f in range(nf)]
+    with open(fin, "wb") as fh:
+        for fr in nv:
+            for a in fr:
+                fh.write(a.tobytes())
+    r = subprocess.run([exe, str(n), str(sw), str(sh), str(pano), str(nb), str(nf), str(fin), str(fout), str(ow), str(oh)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(fout, np.uint8).reshape(nf, ow * oh * 3 // 2)
+    for f in range(nf):
+        pano8 = og.s16_to_u8(orig.compose([og.nv12_to_bgr(a, sw, sh) for a in nv[f]])[0])
+        _eq(got[f], og.consume(pano8, ow, oh, 1), f"C++ demo, NV12 -> I420, frame {f}")
 
 
 def test_error_behaviour(cuda, vsb):
