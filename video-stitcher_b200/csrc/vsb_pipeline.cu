@@ -235,6 +235,10 @@ struct Stage1TabParams {
 #ifndef VSB_RM1_MINB
 #define VSB_RM1_MINB 4
 #endif
+#ifndef VSB_RM_UNROLL
+#define VSB_RM_UNROLL 1
+#endif
+constexpr int RM_UNROLL = VSB_RM_UNROLL;  // frames of the per-tile loop in flight per thread
 template <bool LANES>
 __global__ void __launch_bounds__(RM_BX *RM_BY, VSB_RM1_MINB) k_remap_stage1_tab(const __grid_constant__ Stage1TabParams p)
 {
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(RM_BX *RM_BY, VSB_RM1_MINB) k_remap_stage1_tab
     const int row_bytes = 3 * min(RM_BX * RM_PX, V.w - tx0);  // valid bytes of this tile row
     const int n = min(RM_PX, V.w - x0);
     uint8_t *dst = V.P + (size_t)p.f0 * V.p_frame_stride + (size_t)y * V.p_pitch + (size_t)(LANES ? tx0 : x0) * 3;
-#pragma unroll 1
+#pragma unroll RM_UNROLL
     for (int f = p.f0; f < p.f0 + p.n_frames; ++f, dst += V.p_frame_stride) {
         const uint8_t *src = p.src[f * p.n_views + vi - p.v0];
         unsigned px[RM_PX];
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage2_tab(const __grid_
     const bool vec = n == RM_PX && (V.bw & 3) == 0;
     const uint8_t *P = V.Pbase + (size_t)p.f0 * V.p_frame_stride;
     uint8_t *g = V.G0 + (size_t)p.f0 * V.g0_frame_stride + (size_t)by * V.bw + bx0;
-#pragma unroll 1
+#pragma unroll RM_UNROLL
     for (int f = 0; f < p.n_frames; ++f, P += V.p_frame_stride, g += V.g0_frame_stride) {
         unsigned px[RM_PX];
         px[0] = remap_tab_px<false>(P, V.p_pitch, (unsigned)o.x, A.x, B.x, C.x, D.x, 1.f);
