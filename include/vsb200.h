@@ -150,6 +150,18 @@ int vsb_shard_set(vsb_stitcher *s, int rank, int world);
 int vsb_shard_info(const vsb_stitcher *s, int *strip_x0, int *strip_x1, unsigned *owned_view_mask);
 /* rect = {x0, y0, w, h} of Gaussian level `level` of `view` (plane coordinates) that rank dst_rank reads; w = 0: nothing */
 int vsb_shard_rect(const vsb_stitcher *s, int dst_rank, int view, int level, int rect[4]);
+/* batched form: n_frames frames per exchange and ONE message per peer.  vsb_shard_plan(owners[num_views]) fixes the per-peer
+ * rectangle lists (same order on both sides); vsb_shard_pack gathers what `peer` reads of this rank's planes into a contiguous
+ * buffer (n_frames * send_bytes_per_frame), vsb_shard_unpack scatters what this rank reads of `peer`'s.  Per submission:
+ * vsb_feed_batch over the owned view range(s) -> pack -> send / recv (caller's transport) -> unpack -> vsb_blend_batch. */
+int vsb_shard_plan(vsb_stitcher *s, const int *owners);
+int vsb_shard_peer_bytes(const vsb_stitcher *s, int peer, size_t *send_bytes_per_frame, size_t *recv_bytes_per_frame);
+int vsb_shard_pack(vsb_stitcher *s, int peer, int n_frames, void *d_buf, void *stream);
+int vsb_shard_unpack(vsb_stitcher *s, int peer, int n_frames, void *d_buf, void *stream);
+/* stitch_online (A/timed.cpp:56-121) for views [v0, v1) of n_frames frames; d_srcs[f * (v1 - v0) + (i - v0)];
+ * MultiBandBlender::blend (S/src/blenders.cpp:758-832) for n_frames frames */
+int vsb_feed_batch(vsb_stitcher *s, int v0, int v1, int n_frames, const uint8_t *const *d_srcs, size_t pitch_bytes, void *stream);
+int vsb_blend_batch(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, size_t out_pitch_bytes, void *stream);
 /* device address of Gaussian level `level` (0, 1, 2..num_bands) of `view`, frame slot `frame`: [3][h][w] u8 */
 int vsb_get_plane(vsb_stitcher *s, int view, int level, int frame, void **ptr, int *w, int *h);
 /* number of kernels the last vsb_compose / vsb_feed+vsb_blend submission launched */

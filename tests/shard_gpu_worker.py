@@ -25,7 +25,7 @@ def main():
     B, S, D = vsb200.binding, vsb200.synth, vsb200.dist
     n, sw, sh = case["n_views"], case["src_w"], case["src_h"]
     gains = S.gains(n)
-    st = B.Stitcher(n, case["num_bands"], True, 1)
+    st = B.Stitcher(n, case["num_bands"], True, max(1, int(case.get("batch", 0))))
     st.calibrate_rig(0, case["pano_width"], sw, sh, 90.0, gains)
     info = st.rig_info()
     for i in range(n):
@@ -39,6 +39,50 @@ def main():
     pitch = (W * 6 + 255) // 256 * 256
     out = torch.zeros((H, pitch // 2), dtype=torch.int16, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
+    batch = int(case.get("batch", 0))
+    if batch:
+        # batched exchange: F different frames per submission, one packed message per peer; every frame is checked
+        fr = [[S.frame(i, f, sw, sh) for i in range(n)] for f in range(batch)]
+        d_fr = [[torch.from_numpy(a).cuda() for a in one] for one in fr]
+        outs = [torch.zeros((H, pitch // 2), dtype=torch.int16, device="cuda") for _ in range(batch)]
+        def run_batch():
+            sh_st.compose_batch([[t.data_ptr() for t in one] for one in d_fr], sw * 3, [o.data_ptr() for o in outs], pitch, stream)
+        run_batch()
+        torch.cuda.synchronize()
+        fulls = []
+        for o in outs:
+            full_f = o.to(torch.int32)
+            dist.all_reduce(full_f)
+            fulls.append(full_f)
+        res = {"rank": rank, "owned": sh_st.owned, "send_bytes": D.exchange_bytes(sh_st.sends), "recv_bytes": D.exchange_bytes(sh_st.recvs), "debug": {}}
+        if steps > 0:
+            for _ in range(3):
+                run_batch()
+            dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                run_batch()
+            e1.record()
+            dist.barrier(); torch.cuda.synchronize()
+            res["fps"] = steps * batch / (D.reduce_step_time(e0.elapsed_time(e1), dist, "cuda") / 1000.0)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, res)
+        if rank == 0:
+            from oracle import oracle as og
+            from oracle import pipeline as op
+            og.set_num_threads(min(8, os.cpu_count() or 1))
+            orig = op.OracleRig(n, sw, sh, case["pano_width"], num_bands=case["num_bands"], enable_local=True, gains=gains)
+            for i in range(n):
+                orig.set_mesh(i, *S.mesh(*orig.sizes[i]))
+            bad = 0
+            for f in range(batch):
+                want, _ = orig.compose(fr[f])
+                got = fulls[f].cpu().numpy()[:, :W * 3].reshape(H, W, 3).astype(np.int16)
+                bad += int(np.count_nonzero(got != want))
+            print(json.dumps({"world": world, "bad": bad, "batch": batch, "ranks": gathered}), flush=True)
+        dist.destroy_process_group()
+        return
     sh_st.compose([t.data_ptr() for t in d_src], sw * 3, out.data_ptr(), pitch, stream)
     torch.cuda.synchronize()
     full = out.to(torch.int32)

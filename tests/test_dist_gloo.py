@@ -115,3 +115,11 @@ def test_view_shard_exchange_plan_and_transport(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert out["ok0"] and out["symmetric"] and min(out["bytes"]) > 0
+
+
+def test_contiguous_runs_of_owned_views():
+    import vsb200
+    D = vsb200.dist
+    assert D.contiguous_runs([0, 1, 5]) == [(0, 2), (5, 6)]
+    assert D.contiguous_runs([4, 3, 5]) == [(3, 6)]
+    assert D.contiguous_runs([]) == []

@@ -27,6 +27,7 @@ SYMBOLS = [
     "vsb_shard_set", "vsb_shard_info", "vsb_shard_rect", "vsb_get_plane",
     "vsb_rig_camera", "vsb_voronoi_seams", "vsb_calibrate_rig", "vsb_rig_info_get", "vsb_get_config", "vsb_set_profiling", "vsb_get_profile",
     "vsb_set_formats", "vsb_nv12_to_bgr", "vsb_consumer_image_height", "vsb_consume",
+    "vsb_shard_plan", "vsb_shard_peer_bytes", "vsb_shard_pack", "vsb_shard_unpack", "vsb_feed_batch", "vsb_blend_batch",
 ]
 CONSUME_RGB, CONSUME_I420 = 0, 1
 IN_BGR8, IN_NV12 = 0, 1
@@ -201,6 +202,29 @@ class Stitcher:
         r = (C.c_int * 4)()
         check(lib().vsb_shard_rect(self._h, dst_rank, view, level, r))
         return tuple(r)
+
+    def shard_plan(self, owners):
+        arr = (C.c_int * len(owners))(*[int(o) for o in owners])
+        check(lib().vsb_shard_plan(self._h, arr))
+
+    def shard_peer_bytes(self, peer):
+        a, b = C.c_size_t(), C.c_size_t()
+        check(lib().vsb_shard_peer_bytes(self._h, peer, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def shard_pack(self, peer, n_frames, buf_ptr, stream=0):
+        check(lib().vsb_shard_pack(self._h, peer, n_frames, _vp(buf_ptr), _vp(stream)))
+
+    def shard_unpack(self, peer, n_frames, buf_ptr, stream=0):
+        check(lib().vsb_shard_unpack(self._h, peer, n_frames, _vp(buf_ptr), _vp(stream)))
+
+    def feed_batch(self, v0, v1, n_frames, src_ptrs, pitch, stream=0):
+        sp = (C.c_void_p * len(src_ptrs))(*[int(p) for p in src_ptrs])
+        check(lib().vsb_feed_batch(self._h, v0, v1, n_frames, sp, C.c_size_t(pitch), _vp(stream)))
+
+    def blend_batch(self, out_ptrs, out_pitch, stream=0):
+        op = (C.c_void_p * len(out_ptrs))(*[int(p) for p in out_ptrs])
+        check(lib().vsb_blend_batch(self._h, len(out_ptrs), op, C.c_size_t(out_pitch), _vp(stream)))
 
     def get_plane(self, view, level, frame=0):
         p, w, h = C.c_void_p(), C.c_int(), C.c_int()

@@ -495,6 +495,27 @@ __global__ void __launch_bounds__(256) k_consume_i420(const __grid_constant__ Co
     }
 }
 
+// ---- view-sharded mode: pack / unpack of the Gaussian sub-planes one peer reads (one message per peer and submission) ---------
+struct ShardRect {
+    uint8_t *plane;        // plane 0 of frame slot 0 of that Gaussian level: [3][ph][pw] u8
+    size_t frame_stride;   // bytes between frame slots
+    size_t off;            // byte offset of this rectangle inside one frame's packed block
+    int pw, ph, x0, y0, w, h;
+};
+template <bool PACK>
+__global__ void __launch_bounds__(256) k_shard_copy(const ShardRect *__restrict__ tab, uint8_t *__restrict__ buf, size_t frame_bytes)
+{
+    const ShardRect R = tab[blockIdx.x];
+    const int c = blockIdx.y, f = blockIdx.z;
+    uint8_t *pl = R.plane + (size_t)f * R.frame_stride + ((size_t)c * R.ph + R.y0) * R.pw + R.x0;
+    uint8_t *pk = buf + (size_t)f * frame_bytes + R.off + (size_t)c * R.w * R.h;
+    for (int i = threadIdx.x; i < R.w * R.h; i += 256) {
+        const int r = i / R.w, q = i - r * R.w;
+        if (PACK) pk[i] = pl[(size_t)r * R.pw + q];
+        else pl[(size_t)r * R.pw + q] = pk[i];
+    }
+}
+
 // ---- K3: pyrDown on planes ----------------------------------------------------------------------------
 // out(y,x) = rhe( sum_{j,i} k5[j] k5[i] in(r101(2y+j-2), r101(2x+i-2)) / 256 ): the exact integer form of the
 // reference's fp32 vertical-then-horizontal 5-tap passes (every partial sum is exactly representable).
@@ -806,6 +827,10 @@ struct vsb_stitcher {
     std::vector<uint32_t> h_bviews, h_cviews;
     int shard_rank = -1, shard_world = 1, strip_w = 0;
     bool owned[vsb::MAXV] = {};
+    // batched exchange plan (vsb_shard_plan): per peer, the rectangles this rank sends / receives, on the device
+    vsb::ShardRect *d_send[vsb::MAXV] = {}, *d_recv[vsb::MAXV] = {};
+    int n_send[vsb::MAXV] = {}, n_recv[vsb::MAXV] = {};
+    size_t send_bytes[vsb::MAXV] = {}, recv_bytes[vsb::MAXV] = {};  // per frame
     uint32_t *d_blend_views_all = nullptr, *d_coarse_views_all = nullptr;  // unsharded tables (d_*_views point at the active ones)
     bool tiles_dirty = true;
     cudaStream_t setup_stream = nullptr, mesh_stream = nullptr, io_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
@@ -1672,6 +1697,7 @@ int vsb_destroy(vsb_stitcher *s)
     for (int k = 0; k < MAXL; ++k) cudaFree(s->dw[k]);
     cudaFree(s->d_plan);
     cudaFree(s->d_blend_views); cudaFree(s->d_coarse_views); cudaFree(s->d_down2_tiles); cudaFree(s->C2);
+    for (int i = 0; i < MAXV; ++i) { cudaFree(s->d_send[i]); cudaFree(s->d_recv[i]); }
     cudaFree(s->stage_src); cudaFree(s->stage_out); cudaFree(s->nv_bgr); cudaFree(s->stage_nv12); cudaFree(s->cons_tab);
     cudaFreeHost(s->pin_src); cudaFreeHost(s->pin_out);
     if (s->setup_stream) cudaStreamDestroy(s->setup_stream);
@@ -2292,6 +2318,105 @@ int vsb_get_plane(vsb_stitcher *s, int view, int level, int frame, void **ptr, i
     if (w) *w = V.bw >> level;
     if (h) *h = V.bh >> level;
     return VSB_OK;
+}
+
+// ---- view-sharded mode, batched: F frames per exchange and ONE message per peer -------------------------------------------------
+// vsb_shard_plan fixes, from the owner of every view, what this rank sends to / receives from each peer (the rectangles of
+// vsb_shard_rect, ordered by (view, level) on both sides); vsb_shard_pack / vsb_shard_unpack move them between the planes and a
+// contiguous buffer with one kernel each.  Per submission: vsb_feed_batch (owned views) -> pack -> send/recv -> unpack -> vsb_blend_batch.
+int vsb_shard_plan(vsb_stitcher *s, const int *owners)
+{
+    REQ(s && owners, VSB_ERR_INVALID, "shard_plan: null argument");
+    REQ(s->shard_rank >= 0, VSB_ERR_STATE, "shard_plan: vsb_shard_set first");
+    DeviceGuard g(s->device);
+    CK(cudaDeviceSynchronize());
+    const int n = s->cfg.num_views, me = s->shard_rank;
+    for (int p = 0; p < s->shard_world && p < MAXV; ++p) {
+        cudaFree(s->d_send[p]); cudaFree(s->d_recv[p]);
+        s->d_send[p] = s->d_recv[p] = nullptr; s->n_send[p] = s->n_recv[p] = 0; s->send_bytes[p] = s->recv_bytes[p] = 0;
+        if (p == me) continue;
+        for (int dir = 0; dir < 2; ++dir) {  // 0: what p reads of MY views; 1: what I read of p's views
+            std::vector<ShardRect> tab;
+            size_t off = 0;
+            for (int v = 0; v < n; ++v) {
+                REQ(owners[v] >= 0 && owners[v] < s->shard_world, VSB_ERR_INVALID, "shard_plan: bad owner of view %d", v);
+                if (owners[v] != (dir == 0 ? me : p)) continue;
+                for (int k = 0; k <= s->nb; ++k) {
+                    int rc[4];
+                    int r = vsb_shard_rect(s, dir == 0 ? p : me, v, k, rc);
+                    if (r != VSB_OK) return r;
+                    if (rc[2] <= 0 || rc[3] <= 0) continue;
+                    const View &V = s->v[v];
+                    ShardRect R;
+                    R.plane = k == 0 ? V.G0 : (k == 1 ? V.G1 : V.Gu[k]);
+                    R.frame_stride = k == 0 ? V.g0_frame_stride : (k == 1 ? V.g1_frame_stride : V.gu_frame_stride[k]);
+                    R.pw = V.bw >> k; R.ph = V.bh >> k; R.x0 = rc[0]; R.y0 = rc[1]; R.w = rc[2]; R.h = rc[3]; R.off = off;
+                    off += (size_t)3 * rc[2] * rc[3];
+                    tab.push_back(R);
+                }
+            }
+            ShardRect **d = dir == 0 ? &s->d_send[p] : &s->d_recv[p];
+            (dir == 0 ? s->n_send[p] : s->n_recv[p]) = (int)tab.size();
+            (dir == 0 ? s->send_bytes[p] : s->recv_bytes[p]) = off;
+            if (!tab.empty()) {
+                CK(cudaMalloc(d, tab.size() * sizeof(ShardRect)));
+                CK(cudaMemcpy(*d, tab.data(), tab.size() * sizeof(ShardRect), cudaMemcpyHostToDevice));
+            }
+        }
+    }
+    return VSB_OK;
+}
+
+int vsb_shard_peer_bytes(const vsb_stitcher *s, int peer, size_t *send_bytes_per_frame, size_t *recv_bytes_per_frame)
+{
+    REQ(s && s->shard_rank >= 0 && peer >= 0 && peer < s->shard_world && peer < MAXV, VSB_ERR_INVALID, "shard_peer_bytes: bad argument");
+    if (send_bytes_per_frame) *send_bytes_per_frame = s->send_bytes[peer];
+    if (recv_bytes_per_frame) *recv_bytes_per_frame = s->recv_bytes[peer];
+    return VSB_OK;
+}
+
+static int shard_copy(vsb_stitcher *s, int peer, int n_frames, void *d_buf, void *stream, bool pack)
+{
+    REQ(s && d_buf, VSB_ERR_INVALID, "shard_pack/unpack: null argument");
+    REQ(s->shard_rank >= 0 && peer >= 0 && peer < s->shard_world && peer < MAXV && peer != s->shard_rank, VSB_ERR_INVALID, "shard_pack/unpack: bad peer");
+    REQ(n_frames >= 1 && n_frames <= s->cfg.max_batch, VSB_ERR_INVALID, "shard_pack/unpack: n_frames must be 1..max_batch");
+    DeviceGuard g(s->device);
+    const int n = pack ? s->n_send[peer] : s->n_recv[peer];
+    if (n == 0) return VSB_OK;
+    if (pack) k_shard_copy<true><<<dim3(n, 3, n_frames), 256, 0, (cudaStream_t)stream>>>(s->d_send[peer], (uint8_t *)d_buf, s->send_bytes[peer]);
+    else k_shard_copy<false><<<dim3(n, 3, n_frames), 256, 0, (cudaStream_t)stream>>>(s->d_recv[peer], (uint8_t *)d_buf, s->recv_bytes[peer]);
+    return check_launch("k_shard_copy");
+}
+int vsb_shard_pack(vsb_stitcher *s, int peer, int n_frames, void *d_buf, void *stream) { return shard_copy(s, peer, n_frames, d_buf, stream, true); }
+int vsb_shard_unpack(vsb_stitcher *s, int peer, int n_frames, void *d_buf, void *stream) { return shard_copy(s, peer, n_frames, d_buf, stream, false); }
+
+// stitch_online for views [v0, v1) of n_frames frames in one submission; d_srcs[f * (v1 - v0) + (i - v0)]
+int vsb_feed_batch(vsb_stitcher *s, int v0, int v1, int n_frames, const uint8_t *const *d_srcs, size_t pitch, void *stream)
+{
+    REQ(s && d_srcs, VSB_ERR_INVALID, "feed_batch: null argument");
+    REQ(v0 >= 0 && v1 <= s->cfg.num_views && v0 < v1, VSB_ERR_INVALID, "feed_batch: bad view range");
+    REQ(n_frames >= 1 && n_frames <= s->cfg.max_batch, VSB_ERR_INVALID, "feed_batch: n_frames must be 1..max_batch (%d)", s->cfg.max_batch);
+    int r = ready_for_frames(s);
+    if (r != VSB_OK) return r;
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->launches == 0) prof_begin(s, st);
+    r = adopt_meshes(s, st);
+    if (r != VSB_OK) return r;
+    return launch_front(s, v0, v1, n_frames, d_srcs, pitch, st);
+}
+
+int vsb_blend_batch(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, size_t out_pitch, void *stream)
+{
+    REQ(s && d_outs, VSB_ERR_INVALID, "blend_batch: null argument");
+    REQ(s->finalized, VSB_ERR_STATE, "blend_batch: prepare + init_view for every view must come first");
+    REQ(n_frames >= 1 && n_frames <= s->cfg.max_batch, VSB_ERR_INVALID, "blend_batch: n_frames must be 1..max_batch (%d)", s->cfg.max_batch);
+    REQ(s->out_format == VSB_OUT_S16C3 || s->fast, VSB_ERR_STATE, "blend_batch: CV_8UC3 output needs num_bands >= 3");
+    REQ(out_pitch >= (size_t)s->roi_final[2] * (s->out_format == VSB_OUT_U8C3 ? 3 : 6), VSB_ERR_INVALID, "blend_batch: output pitch too small");
+    DeviceGuard g(s->device);
+    int r = launch_back(s, n_frames, d_outs, out_pitch, (cudaStream_t)stream);
+    if (r != VSB_OK) return r;
+    return note_compose_done(s, (cudaStream_t)stream);
 }
 
 int vsb_last_launch_count(const vsb_stitcher *s) { return s ? s->launches_last : 0; }

@@ -87,6 +87,17 @@ def run_exchange(dist, torch, plane_fn, sends, recvs):
         p[:, y0:y0 + h, x0:x0 + w].copy_(buf)
 
 
+def contiguous_runs(views):
+    """[0, 1, 5] -> [(0, 2), (5, 6)]: half-open runs of consecutive view indices (one vsb_feed_batch call each)."""
+    runs = []
+    for v in sorted(views):
+        if runs and runs[-1][1] == v:
+            runs[-1] = (runs[-1][0], v + 1)
+        else:
+            runs.append((v, v + 1))
+    return runs
+
+
 class _DeviceArray:
     """Zero-copy view of handle-owned device memory for torch.as_tensor (CUDA array interface, version 2)."""
 
@@ -120,6 +131,43 @@ class ShardedStitcher:
             ptr, w, h = self.st.get_plane(view, level, 0)
             self._planes[key] = self.torch.as_tensor(_DeviceArray(ptr, (3, h, w)), device="cuda")
         return self._planes[key]
+
+    # ---- batched form: F frames per exchange, one packed message per peer (vsb_shard_plan / pack / unpack)
+    def _batch_setup(self, n_frames):
+        if getattr(self, "_batch_frames", 0) >= n_frames:
+            return
+        self.st.shard_plan(self.owners)
+        self.runs = contiguous_runs(self.owned)
+        self._send, self._recv = {}, {}
+        for peer in range(self.world):
+            if peer == self.rank:
+                continue
+            sb, rb = self.st.shard_peer_bytes(peer)
+            if sb:
+                self._send[peer] = (sb, self.torch.empty(sb * n_frames, dtype=self.torch.uint8, device="cuda"))
+            if rb:
+                self._recv[peer] = (rb, self.torch.empty(rb * n_frames, dtype=self.torch.uint8, device="cuda"))
+        self._batch_frames = n_frames
+
+    def compose_batch(self, src_ptrs_per_frame, src_pitch, out_ptrs, out_pitch, stream):
+        """src_ptrs_per_frame[f][v]: device BGR frame of view v, frame f (only the owned views are read); out_ptrs[f]: full-size
+        CV_16SC3 buffers, this rank writes its strip of each."""
+        F = len(out_ptrs)
+        self._batch_setup(F)
+        for v0, v1 in self.runs:
+            self.st.feed_batch(v0, v1, F, [src_ptrs_per_frame[f][v] for f in range(F) for v in range(v0, v1)], src_pitch, stream)
+        ops = []
+        for peer, (sb, buf) in self._send.items():
+            self.st.shard_pack(peer, F, buf.data_ptr(), stream)
+            ops.append(self.dist.P2POp(self.dist.isend, buf[:sb * F], peer))
+        for peer, (rb, buf) in self._recv.items():
+            ops.append(self.dist.P2POp(self.dist.irecv, buf[:rb * F], peer))
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+        for peer, (rb, buf) in self._recv.items():
+            self.st.shard_unpack(peer, F, buf.data_ptr(), stream)
+        self.st.blend_batch(out_ptrs, out_pitch, stream)
 
     def compose(self, src_ptrs, src_pitch, out_ptr, out_pitch, stream):
         """src_ptrs: device BGR frames of ALL views (only the owned ones are read).  Writes this rank's strip of the
