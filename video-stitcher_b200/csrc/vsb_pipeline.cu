@@ -502,6 +502,8 @@ struct ShardRect {
     size_t off;            // byte offset of this rectangle inside one frame's packed block
     int pw, ph, x0, y0, w, h;
 };
+// block = 32 x 8 threads: rows over threadIdx.y, 32-bit words (rectangles are widened to word boundaries at plan time whenever
+// the plane rows are word aligned) or bytes over threadIdx.x
 template <bool PACK>
 __global__ void __launch_bounds__(256) k_shard_copy(const ShardRect *__restrict__ tab, uint8_t *__restrict__ buf, size_t frame_bytes)
 {
@@ -509,10 +511,20 @@ __global__ void __launch_bounds__(256) k_shard_copy(const ShardRect *__restrict_
     const int c = blockIdx.y, f = blockIdx.z;
     uint8_t *pl = R.plane + (size_t)f * R.frame_stride + ((size_t)c * R.ph + R.y0) * R.pw + R.x0;
     uint8_t *pk = buf + (size_t)f * frame_bytes + R.off + (size_t)c * R.w * R.h;
-    for (int i = threadIdx.x; i < R.w * R.h; i += 256) {
-        const int r = i / R.w, q = i - r * R.w;
-        if (PACK) pk[i] = pl[(size_t)r * R.pw + q];
-        else pl[(size_t)r * R.pw + q] = pk[i];
+    const bool words = ((R.pw | R.x0 | R.w) & 3) == 0;
+    for (int r = threadIdx.y; r < R.h; r += 8) {
+        uint8_t *a = pl + (size_t)r * R.pw, *b = pk + (size_t)r * R.w;
+        if (words) {
+            for (int q = threadIdx.x; q < (R.w >> 2); q += 32) {
+                if (PACK) ((unsigned *)b)[q] = ((const unsigned *)a)[q];
+                else ((unsigned *)a)[q] = ((const unsigned *)b)[q];
+            }
+        } else {
+            for (int q = threadIdx.x; q < R.w; q += 32) {
+                if (PACK) b[q] = a[q];
+                else a[q] = b[q];
+            }
+        }
     }
 }
 
@@ -2351,7 +2363,11 @@ int vsb_shard_plan(vsb_stitcher *s, const int *owners)
                     R.plane = k == 0 ? V.G0 : (k == 1 ? V.G1 : V.Gu[k]);
                     R.frame_stride = k == 0 ? V.g0_frame_stride : (k == 1 ? V.g1_frame_stride : V.gu_frame_stride[k]);
                     R.pw = V.bw >> k; R.ph = V.bh >> k; R.x0 = rc[0]; R.y0 = rc[1]; R.w = rc[2]; R.h = rc[3]; R.off = off;
-                    off += (size_t)3 * rc[2] * rc[3];
+                    if ((R.pw & 3) == 0) {  // widen to word boundaries (still inside the plane): both sides do the same, the extra columns are valid data
+                        const int x1 = std::min(R.pw, (R.x0 + R.w + 3) & ~3);
+                        R.x0 &= ~3; R.w = x1 - R.x0;
+                    }
+                    off += (size_t)3 * R.w * R.h;
                     tab.push_back(R);
                 }
             }
@@ -2383,8 +2399,8 @@ static int shard_copy(vsb_stitcher *s, int peer, int n_frames, void *d_buf, void
     DeviceGuard g(s->device);
     const int n = pack ? s->n_send[peer] : s->n_recv[peer];
     if (n == 0) return VSB_OK;
-    if (pack) k_shard_copy<true><<<dim3(n, 3, n_frames), 256, 0, (cudaStream_t)stream>>>(s->d_send[peer], (uint8_t *)d_buf, s->send_bytes[peer]);
-    else k_shard_copy<false><<<dim3(n, 3, n_frames), 256, 0, (cudaStream_t)stream>>>(s->d_recv[peer], (uint8_t *)d_buf, s->recv_bytes[peer]);
+    if (pack) k_shard_copy<true><<<dim3(n, 3, n_frames), dim3(32, 8), 0, (cudaStream_t)stream>>>(s->d_send[peer], (uint8_t *)d_buf, s->send_bytes[peer]);
+    else k_shard_copy<false><<<dim3(n, 3, n_frames), dim3(32, 8), 0, (cudaStream_t)stream>>>(s->d_recv[peer], (uint8_t *)d_buf, s->recv_bytes[peer]);
     return check_launch("k_shard_copy");
 }
 int vsb_shard_pack(vsb_stitcher *s, int peer, int n_frames, void *d_buf, void *stream) { return shard_copy(s, peer, n_frames, d_buf, stream, true); }
