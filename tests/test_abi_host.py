@@ -41,6 +41,23 @@ def test_cpp_adapter_header_compiles():
         subprocess.check_call([gxx, "-std=c++11", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src])
 
 
+def test_c_header_is_plain_c_and_links(vsb):
+    """include/vsb200.h is a C ABI: a C99 translation unit includes it, links against libvsb200.so and calls a host-only entry."""
+    import shutil
+    import subprocess
+    import tempfile
+    gcc = shutil.which("gcc", path="/usr/bin") or shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    libdir = os.path.dirname(vsb.LIB_PATH)
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "t.c"), os.path.join(d, "t")
+        open(src, "w").write('#include "vsb200.h"\nint main(void) { return vsb_consumer_image_height(3839, 627, 4096, 2048, 1) == 669 ? 0 : 1; }\n')
+        subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-L", libdir, "-lvsb200",
+                               "-Wl,-rpath," + libdir, "-o", exe])
+        assert subprocess.call([exe]) == 0
+
+
 def test_no_device_fails_loudly(vsb):
     import torch
     if torch.cuda.is_available():
