@@ -1756,6 +1756,7 @@ int vsb_prepare(vsb_stitcher *s, const int *corners_xy, const int *sizes_wh)
         CK(cudaMalloc(&s->dw[k], sizeof(float) * s->cw[k] * s->ch[k]));
     }
     cudaFree(s->stage_src); cudaFree(s->stage_out); s->stage_src = nullptr; s->stage_out = nullptr;  // sized per calibration
+    s->cons_w = s->cons_ih = 0;  // the consumer's resize tables depend on the panorama size
     s->views_inited = 0; s->prepared = true; s->finalized = false;
     return VSB_OK;
 }
