@@ -1,0 +1,21 @@
+"""Writes tests/golden/oracle_compose_hashes.json: SHA-256 of oracle-G's composed panoramas for two small rigs (whole-path known-answer
+vectors: they freeze the oracle this round's GPU parity runs were green against; tests/test_oracle_pin.py replays them)."""
+import sys, json, hashlib
+sys.path.insert(0, '/root/repo')
+import numpy as np
+import vsb200
+from oracle import oracle as og, pipeline as op
+S = vsb200.synth
+og.set_num_threads(8)
+out = {}
+for name, kw in (("small4", dict(n_views=4, src_w=320, src_h=240, pano_width=1024, num_bands=3, enable_local=True)),
+                 ("cyl5", dict(n_views=5, src_w=256, src_h=192, pano_width=800, num_bands=4, enable_local=True, projection=1))):
+    rig = op.OracleRig(gains=S.gains(kw["n_views"]), **kw)
+    for i in range(kw["n_views"]):
+        rig.set_mesh(i, *S.mesh(*rig.sizes[i]))
+    frames = [S.frame(i, 0, kw["src_w"], kw["src_h"]) for i in range(kw["n_views"])]
+    pano, mask = rig.compose(frames)
+    out[name] = {"shape": list(pano.shape), "sha256": hashlib.sha256(np.ascontiguousarray(pano).tobytes()).hexdigest(),
+                 "mask_sha256": hashlib.sha256(np.ascontiguousarray(mask).tobytes()).hexdigest(), "sum": int(pano.astype(np.int64).sum())}
+json.dump(out, open('/root/repo/tests/golden/oracle_compose_hashes.json', 'w'), indent=1)
+print(out)

@@ -63,6 +63,27 @@ def test_consumer_epilogue_exact(og, gold):
     assert np.array_equal(og.consume(pano, ow, oh, 1), gold["consume_i420"])
 
 
+def test_whole_path_known_answers(og):
+    """Whole-path KAT: oracle-G's panoramas of two small rigs hash to the committed values (tests/golden/make_compose_hashes.py).
+    The GPU parity suite was green against exactly this oracle, so a drift of the restatement cannot go unnoticed."""
+    import hashlib
+    import json
+    import vsb200
+    from oracle import pipeline as op
+    S = vsb200.synth
+    want = json.load(open(os.path.join(os.path.dirname(GOLD), "oracle_compose_hashes.json")))
+    cases = {"small4": dict(n_views=4, src_w=320, src_h=240, pano_width=1024, num_bands=3, enable_local=True),
+             "cyl5": dict(n_views=5, src_w=256, src_h=192, pano_width=800, num_bands=4, enable_local=True, projection=1)}
+    for name, kw in cases.items():
+        rig = op.OracleRig(gains=S.gains(kw["n_views"]), **kw)
+        for i in range(kw["n_views"]):
+            rig.set_mesh(i, *S.mesh(*rig.sizes[i]))
+        pano, mask = rig.compose([S.frame(i, 0, kw["src_w"], kw["src_h"]) for i in range(kw["n_views"])])
+        assert list(pano.shape) == want[name]["shape"]
+        assert hashlib.sha256(np.ascontiguousarray(pano).tobytes()).hexdigest() == want[name]["sha256"], name
+        assert hashlib.sha256(np.ascontiguousarray(mask).tobytes()).hexdigest() == want[name]["mask_sha256"], name
+
+
 def test_border_gain_dilate_distance_exact(og, gold):
     img = G.pyr_input((20, 37)).astype(np.uint8)
     assert np.array_equal(og.border_reflect_u8c3_to_s16(img, 17, 19, 30, 3), gold["border_reflect"].astype(np.int16))
