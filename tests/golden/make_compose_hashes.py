@@ -1,7 +1,12 @@
 """Writes tests/golden/oracle_compose_hashes.json: SHA-256 of oracle-G's composed panoramas for two small rigs (whole-path known-answer
 vectors: they freeze the oracle this round's GPU parity runs were green against; tests/test_oracle_pin.py replays them)."""
-import sys, json, hashlib
-sys.path.insert(0, '/root/repo')
+import hashlib
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 import numpy as np
 import vsb200
 from oracle import oracle as og, pipeline as op
@@ -17,5 +22,5 @@ for name, kw in (("small4", dict(n_views=4, src_w=320, src_h=240, pano_width=102
     pano, mask = rig.compose(frames)
     out[name] = {"shape": list(pano.shape), "sha256": hashlib.sha256(np.ascontiguousarray(pano).tobytes()).hexdigest(),
                  "mask_sha256": hashlib.sha256(np.ascontiguousarray(mask).tobytes()).hexdigest(), "sum": int(pano.astype(np.int64).sum())}
-json.dump(out, open('/root/repo/tests/golden/oracle_compose_hashes.json', 'w'), indent=1)
+json.dump(out, open(os.path.join(ROOT, 'tests', 'golden', 'oracle_compose_hashes.json'), 'w'), indent=1)
 print(out)
