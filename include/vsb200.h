@@ -62,6 +62,14 @@ int vsb_warp_roi(int projection, float scale, const float K[9], const float R[9]
 int vsb_build_maps(int projection, float scale, const float K[9], const float R[9], int src_w, int src_h,
                    float *d_xmap, float *d_ymap, size_t pitch_bytes, int roi[4], void *stream);
 
+/* RotationWarperGpu::warp(src, K, R, interp_mode, border_mode, dst) (S/src/warpers_cuda.cpp:279-298; used by the
+ * application at A/calibration.cpp:118,122,227): buildMaps into scratch + cuda::remap.  d_src: CV_8UC1 / CV_8UC3 (channels = 1 / 3);
+ * d_dst: roi[2] x roi[3] pixels of the same type (size it with vsb_warp_roi first); returns the roi whose tl is warp()'s Point. */
+enum { VSB_INTER_NEAREST = 0, VSB_INTER_LINEAR = 1 };      /* cv::INTER_NEAREST, cv::INTER_LINEAR */
+enum { VSB_BORDER_CONSTANT = 0, VSB_BORDER_REFLECT = 2 };   /* cv::BORDER_CONSTANT (value 0), cv::BORDER_REFLECT */
+int vsb_warp(int projection, float scale, const float K[9], const float R[9], const uint8_t *d_src, int src_w, int src_h,
+             size_t src_pitch, int channels, int interp, int border, uint8_t *d_dst, size_t dst_pitch, int roi[4], void *stream);
+
 /* ---- B6: static setup.  MultiBandBlender::prepare / init_gpu (S/src/blenders.cpp:237-295,344-461),
  *      x_maps/y_maps (A/calibration.cpp:221), GainCompensator::gains (A/timed.cpp:94) ----------------- */
 int vsb_prepare(vsb_stitcher *s, const int *corners_xy, const int *sizes_wh);

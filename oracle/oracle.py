@@ -113,6 +113,23 @@ def remap_nearest_u8c1(src, xmap, ymap):
     return dst
 
 
+INTER_NEAREST, INTER_LINEAR = 0, 1
+BORDER_CONSTANT, BORDER_REFLECT = 0, 2
+
+
+def remap_u8(src, xmap, ymap, interp=INTER_LINEAR, border=BORDER_CONSTANT):
+    """cuda::remap as RotationWarperGpu::warp calls it: NEAREST / LINEAR x BORDER_CONSTANT(0) / BORDER_REFLECT, 1 or 3 channels."""
+    src = np.ascontiguousarray(src, np.uint8)
+    cn = 1 if src.ndim == 2 else src.shape[2]
+    sh, sw = src.shape[:2]
+    xmap, ymap = _f32(xmap), _f32(ymap)
+    dh, dw = xmap.shape
+    dst = np.empty((dh, dw) if src.ndim == 2 else (dh, dw, cn), np.uint8)
+    lib().og_remap_u8_border(_p(src, C.c_uint8), sw, sh, cn, C.c_size_t(sw * cn), _p(xmap, C.c_float), _p(ymap, C.c_float),
+                             C.c_size_t(dw), _p(dst, C.c_uint8), dw, dh, C.c_size_t(dw * cn), int(interp), int(border))
+    return dst
+
+
 def gain_u8(img, gain):
     out = np.ascontiguousarray(img, np.uint8).copy()
     lib().og_gain_u8(_p(out, C.c_uint8), C.c_size_t(out.size), C.c_float(gain))

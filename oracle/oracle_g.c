@@ -12,13 +12,13 @@
  * every other operation is a separately rounded fp32 op.  The s16 pyramids are exact in fp32
  * (see og_pyr_down_s16_int) so contraction is immaterial there.
  *
- * Parity pin status: the reference ships no golden vectors for this path that are vendored
- * (SURVEY.md 8c).  This restatement is pinned by (1) tests/test_oracle_vs_cv2.py against the
- * upstream CPU implementation of the same algorithms (pip cv2, fixtures in tests/golden/ with the
- * generating script), (2) oracle/_ref = the reference's own vendored OpenCV 3.4.0 CPU sources
- * compiled in place when /root/reference is present (see oracle/Makefile), (3) replayed recipes of
- * the reference's own tests (CW/test/test_remap.cpp, CW/test/test_pyramids.cpp,
- * S/test/test_blenders.cpp).
+ * Parity pin status: PINNED.  The reference ships no vendored golden vectors for this path, so the pin
+ * is the reference's own code run here: (1) oracle/_ref = the reference's vendored OpenCV 3.4.0 CPU sources compiled in
+ * place by oracle/ref.mk when /root/reference is present; its outputs are committed as tests/golden/reference_cpu.npz
+ * (generator: tests/golden/make_golden.py) and checked live and from the fixture by tests/test_oracle_pin.py;
+ * (2) the reference's float gold for cuda::remap (CW/test/interpolation.hpp:66-84, compiled into oracle/ref_shim.cpp)
+ * on the CW/test/test_remap.cpp:158-177 recipe; (3) replayed recipes of the reference's own tests
+ * (CW/test/test_pyramids.cpp, S/test/test_blenders.cpp).
  */
 #include "oracle_g.h"
 
@@ -268,6 +268,45 @@ void og_remap_nearest_u8c1(const uint8_t *src, int sw, int sh, size_t sstep,
         for (int xx = 0; xx < dw; ++xx) {
             int x = f2i_rz(xmap[(size_t)yy * mstep + xx]), y = f2i_rz(ymap[(size_t)yy * mstep + xx]);
             dst[(size_t)yy * dstep + xx] = (x >= 0 && x < sw && y >= 0 && y < sh) ? src[(size_t)y * sstep + x] : 0;
+        }
+}
+
+/* cuda::remap as the warpers call it (RotationWarperGpu::warp, S/src/warpers_cuda.cpp:279-298 -> CW/src/cuda/remap.cu:56-68):
+ * interp 0 = PointFilter (filters.hpp:64-78, __float2int_rz), 1 = LinearFilter (:90-114); border 0 = BrdConstant(0)
+ * (border_interpolate.hpp:698-717), 2 = BrdReflect (:484-534: idx_low(idx_high(i)), low = (|i| - (i < 0)) % len,
+ * high = last - |last - i| + (i > last)).  The application uses LINEAR/REFLECT for the seam-scale images and
+ * NEAREST/CONSTANT for the masks (360_stitcher/calibration.cpp:118,122,227). */
+static int brd_reflect(int i, int len)
+{
+    const int last = len - 1;
+    int j = last - abs(last - i) + (i > last);
+    return (abs(j) - (j < 0)) % len;
+}
+static float read_brd(const uint8_t *src, int sw, int sh, int cn, size_t sstep, int y, int x, int c, int border)
+{
+    if (border == 0) return (x >= 0 && x < sw && y >= 0 && y < sh) ? (float)src[(size_t)y * sstep + (size_t)x * cn + c] : 0.f;
+    return (float)src[(size_t)brd_reflect(y, sh) * sstep + (size_t)brd_reflect(x, sw) * cn + c];
+}
+void og_remap_u8_border(const uint8_t *src, int sw, int sh, int cn, size_t sstep, const float *xmap, const float *ymap, size_t mstep,
+                        uint8_t *dst, int dw, int dh, size_t dstep, int interp, int border)
+{
+#pragma omp parallel for num_threads(g_threads)
+    for (int yy = 0; yy < dh; ++yy)
+        for (int xx = 0; xx < dw; ++xx) {
+            const float x = xmap[(size_t)yy * mstep + xx], y = ymap[(size_t)yy * mstep + xx];
+            for (int c = 0; c < cn; ++c) {
+                uint8_t *d = dst + (size_t)yy * dstep + (size_t)xx * cn + c;
+                if (interp == 0) {
+                    *d = (uint8_t)read_brd(src, sw, sh, cn, sstep, f2i_rz(y), f2i_rz(x), c, border);
+                    continue;
+                }
+                const int x1 = f2i_rd(x), y1 = f2i_rd(y), x2 = x1 + 1, y2 = y1 + 1;
+                float out = fmaf(read_brd(src, sw, sh, cn, sstep, y1, x1, c, border), ((float)x2 - x) * ((float)y2 - y), 0.f);
+                out = fmaf(read_brd(src, sw, sh, cn, sstep, y1, x2, c, border), (x - (float)x1) * ((float)y2 - y), out);
+                out = fmaf(read_brd(src, sw, sh, cn, sstep, y2, x1, c, border), ((float)x2 - x) * (y - (float)y1), out);
+                out = fmaf(read_brd(src, sw, sh, cn, sstep, y2, x2, c, border), (x - (float)x1) * (y - (float)y1), out);
+                *d = rni_sat_u8(out);
+            }
         }
 }
 

@@ -37,6 +37,8 @@ void og_remap_linear_u8(const uint8_t *src, int sw, int sh, int cn, size_t sstep
 void og_remap_nearest_u8c1(const uint8_t *src, int sw, int sh, size_t sstep,
                            const float *xmap, const float *ymap, size_t mstep,
                            uint8_t *dst, int dw, int dh, size_t dstep);
+void og_remap_u8_border(const uint8_t *src, int sw, int sh, int cn, size_t sstep, const float *xmap, const float *ymap, size_t mstep,
+                        uint8_t *dst, int dw, int dh, size_t dstep, int interp, int border);
 void og_gain_u8(uint8_t *buf, size_t n, float gain);
 void og_resize_linear_u8c1(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh);
 void og_dilate3x3_u8c1(const uint8_t *src, int w, int h, uint8_t *dst);

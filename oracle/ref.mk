@@ -68,7 +68,7 @@ $(OBJ)/imgproc/%.o: $(MOD)/imgproc/src/%.cpp $(GEN)/.stamp
 $(OBJ)/stitching/%.o: $(MOD)/stitching/src/%.cpp $(GEN)/.stamp
 	$(CXX) $(CXXFLAGS) -I$(MOD)/stitching/src -c $< -o $@
 $(OBJ)/ref_shim.o: ref_shim.cpp $(GEN)/.stamp
-	$(CXX) $(CXXFLAGS) -fopenmp -c $< -o $@
+	$(CXX) $(CXXFLAGS) -I$(MOD)/cudawarping/test -ffp-contract=off -fopenmp -c $< -o $@
 
 $(OUT)/libvsref.so: $(CORE_OBJS) $(IMG_OBJS) $(ST_OBJS) $(OBJ)/ref_shim.o
 	$(CXX) -shared -o $@ $^ -pthread -fopenmp -lz -ldl -lm

@@ -94,6 +94,19 @@ def remap_u8(src, xmap, ymap, nearest=False):
     return dst
 
 
+def remap_gold_u8(src, xmap, ymap):
+    """The reference's float gold of cuda::remap LINEAR / BORDER_CONSTANT(0) (CW/test/interpolation.hpp:66-84)."""
+    src = np.ascontiguousarray(src, np.uint8)
+    cn = 1 if src.ndim == 2 else src.shape[2]
+    sh, sw = src.shape[:2]
+    xmap = np.ascontiguousarray(xmap, np.float32)
+    ymap = np.ascontiguousarray(ymap, np.float32)
+    dh, dw = xmap.shape
+    dst = np.empty((dh, dw) if src.ndim == 2 else (dh, dw, cn), np.uint8)
+    lib().vr_remap_gold_u8(_p(src), sw, sh, cn, _p(xmap), _p(ymap), _p(dst), dw, dh)
+    return dst
+
+
 def copy_make_border(src, t, top, bottom, left, right, reflect=True):
     src = _typed(src, t)
     h, w = src.shape[:2]

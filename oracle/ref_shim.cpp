@@ -22,6 +22,10 @@
 #include <opencv2/stitching/detail/util.hpp>
 #include <opencv2/stitching/detail/warpers.hpp>
 
+/* the reference's own float gold for cuda::remap (LinearInterpolator / readVal), included from where it lies:
+ * sources/modules/cudawarping/test/interpolation.hpp:50-84 (ref.mk adds that directory to the include path) */
+#include "interpolation.hpp"
+
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -148,6 +152,17 @@ void vr_remap_u8(const uint8_t *src, int sw, int sh, int cn, const float *xmap, 
         ym(dh, dw, CV_32F, const_cast<float *>(ymap)), d(dh, dw, CV_8UC(cn), dst), o;
     remap(s, o, xm, ym, nearest ? INTER_NEAREST : INTER_LINEAR, BORDER_CONSTANT);
     o.copyTo(d);
+}
+/* remapGold(INTER_LINEAR, BORDER_CONSTANT, 0) of the CUDA remap test: the per-pixel loop of remapImpl<uchar, LinearInterpolator>
+ * (sources/modules/cudawarping/test/test_remap.cpp:54-71) over the header's LinearInterpolator<uchar>::getValue */
+void vr_remap_gold_u8(const uint8_t *src, int sw, int sh, int cn, const float *xmap, const float *ymap, uint8_t *dst, int dw, int dh)
+{
+    Mat s(sh, sw, CV_8UC(cn), const_cast<uint8_t *>(src)), xm(dh, dw, CV_32F, const_cast<float *>(xmap)),
+        ym(dh, dw, CV_32F, const_cast<float *>(ymap)), d(dh, dw, CV_8UC(cn), dst);
+    for (int y = 0; y < dh; ++y)
+        for (int x = 0; x < dw; ++x)
+            for (int c = 0; c < cn; ++c)
+                d.at<uchar>(y, x * cn + c) = LinearInterpolator<uchar>::getValue(s, ym.at<float>(y, x), xm.at<float>(y, x), c, BORDER_CONSTANT, Scalar());
 }
 void vr_copy_make_border(const void *src, int w, int h, int type, int top, int bottom, int left, int right, int reflect, void *dst)
 {

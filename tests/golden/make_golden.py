@@ -54,6 +54,19 @@ def remap_input(seed=3):
     return src, xm, ym
 
 
+def remap_test_recipe(size=(128, 128), seed=5):
+    """CW/test/test_remap.cpp:127-148 (SetUp): maps of a 45-degree rotation, M = [[cos, -sin, w/2], [sin, cos, 0]], on a
+    randomMat CV_8UC3 source of the same size."""
+    h, w = size
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    a = np.pi / 4
+    xm = (np.cos(a) * xx - np.sin(a) * yy + w / 2.0).astype(np.float32)
+    ym = (np.sin(a) * xx + np.cos(a) * yy).astype(np.float32)
+    return src, xm, ym
+
+
 def nv12_input(w=64, h=48, seed=17):
     """Random NV12 frame (Y plane then interleaved UV) covering the full byte range, incl. the saturating branches."""
     rng = np.random.default_rng(seed)
@@ -166,6 +179,12 @@ def main():
     src, xm, ym = remap_input()
     out["remap_linear"] = vr.remap_u8(src, xm, ym)
     out["remap_nearest"] = vr.remap_u8(src[..., 0].copy(), xm, ym, nearest=True)
+    # 7b. the reference's FLOAT gold of cuda::remap (CW/test/interpolation.hpp:66-84) on the same recipe and on the recipe at
+    #     the size / map of CW/test/test_remap.cpp:127-148 (128x128 source, 45-degree rotation about (w/2, 0)): this is the
+    #     arithmetic oracle-G restates (floor, 4 fp32 taps, saturate_cast), unlike the fixed-point CPU cv::remap above
+    out["remap_gold_linear"] = vr.remap_gold_u8(src, xm, ym)
+    src2, xm2, ym2 = remap_test_recipe()
+    out["remap_gold_recipe"] = vr.remap_gold_u8(src2, xm2, ym2)
     # 8. gain convertTo
     out["gain_1.03"] = vr.gain_u8(np.arange(256, dtype=np.uint8), 1.03)
     out["gain_0.97"] = vr.gain_u8(np.arange(256, dtype=np.uint8), 0.97)

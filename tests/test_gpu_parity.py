@@ -103,6 +103,54 @@ def test_border_gain_resize_weighted_add_match_oracle(cuda, og, vsb):
     _eq(host(d_dst), want2, "normalize32F")
 
 
+@pytest.mark.parametrize("proj,n,sw,sh,pano", [(0, 6, 640, 360, 1280), (1, 5, 320, 240, 900), (0, 6, 1920, 1080, 3840)])
+def test_build_maps_and_warp_match_oracle(cuda, og, vsb, proj, n, sw, sh, pano):
+    """B3: {Spherical,Cylindrical}WarperGpu::buildMaps (S/src/warpers_cuda.cpp:210-277, S/src/cuda/build_warp_maps.cu:88-152) and
+    ::warp (:279-298) on the device.  ROI exact; maps within 2e-3 px of oracle-G's (device sinf / cosf vs libm, the same bound the
+    oracle's own maps keep against the reference's CPU projector, tests/test_oracle_pin.py); the warp itself is checked on the
+    DEVICE maps, bit-exact (NEAREST / LINEAR x CONSTANT / REFLECT, CV_8UC1 / CV_8UC3: the modes of A/calibration.cpp:118,122,227)."""
+    from tests.gpu_util import dev, host, stream
+    C = vsb.C
+    L = vsb.lib()
+    scale = np.float32(pano / (2.0 * 3.1415926535897932384626))
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+    mask = np.full((sh, sw), 255, np.uint8)
+    d_img, d_mask = dev(img), dev(mask)
+    for i in (0, n // 2, n - 1):
+        K, R = og.rig_camera(n, i, sw, sh)
+        want_roi = og.warp_roi(proj, scale, K, R, sw, sh)
+        assert vsb.warp_roi(proj, float(scale), K.reshape(9), R.reshape(9), sw, sh) == want_roi
+        w, h = want_roi[2], want_roi[3]
+        pitch = (w * 4 + 255) // 256 * 256
+        d_x = cuda.full((h, pitch // 4), -7.0, dtype=cuda.float32, device="cuda")
+        d_y = cuda.full((h, pitch // 4), -7.0, dtype=cuda.float32, device="cuda")
+        roi = (C.c_int * 4)()
+        vsb.check(L.vsb_build_maps(proj, C.c_float(scale), vsb._fp9(K.reshape(9)), vsb._fp9(R.reshape(9)), sw, sh, vsb._vp(d_x.data_ptr()),
+                                   vsb._vp(d_y.data_ptr()), C.c_size_t(pitch), roi, vsb._vp(stream())))
+        assert tuple(roi) == want_roi
+        gx, gy = host(d_x), host(d_y)
+        assert (gx[:, w:] == -7.0).all() and (gy[:, w:] == -7.0).all(), "row padding must stay untouched"
+        gx, gy = np.ascontiguousarray(gx[:, :w]), np.ascontiguousarray(gy[:, :w])
+        wx, wy = og.build_maps(proj, scale, K, R, *want_roi)
+        behind = (wx == -1) & (wy == -1)
+        assert np.array_equal(behind, (gx == -1) & (gy == -1)), "rays behind the camera map to (-1, -1)"
+        inside = ~behind & (wx > -2) & (wx < sw + 1) & (wy > -2) & (wy < sh + 1)   # the part of the map that addresses the image
+        assert inside.any()
+        assert np.abs(gx - wx)[inside].max() <= 2e-3 and np.abs(gy - wy)[inside].max() <= 2e-3
+        for (src, d_src, cn, interp, border) in ((img, d_img, 3, 1, 2), (mask, d_mask, 1, 0, 0), (img, d_img, 3, 1, 0), (img[..., 1].copy(), None, 1, 1, 2)):
+            if d_src is None:
+                d_src = dev(src)
+            dp = w * cn + 3
+            d_dst = cuda.full((h, dp), 9, dtype=cuda.uint8, device="cuda")
+            vsb.check(L.vsb_warp(proj, C.c_float(scale), vsb._fp9(K.reshape(9)), vsb._fp9(R.reshape(9)), vsb._vp(d_src.data_ptr()), sw, sh,
+                                 C.c_size_t(sw * cn), cn, interp, border, vsb._vp(d_dst.data_ptr()), C.c_size_t(dp), roi, vsb._vp(stream())))
+            got = host(d_dst)
+            assert tuple(roi) == want_roi and (got[:, w * cn:] == 9).all()
+            got = got[:, :w * cn].reshape((h, w, 3) if cn == 3 else (h, w))
+            _eq(got, og.remap_u8(src, gx, gy, interp, border), f"warp view {i} cn {cn} interp {interp} border {border}")
+
+
 # ------------------------------------------------------------------------------------------ whole path
 CASES = {
     "small4": dict(n_views=4, src_w=320, src_h=240, pano_width=1024, num_bands=3, enable_local=True),
@@ -207,6 +255,26 @@ def test_full_size_config4_compose(cuda, og):
     got = grig.compose([frames])[0]
     _eq(got, want, "config 4 panorama (CV_16SC3)")
     assert grig.st.last_launch_count() == 7  # K1 K2 down2 down1(L3: too large for shared memory) down_tail coarse blend
+
+
+@pytest.mark.parametrize("name,kw", [
+    # BASELINE.json configs[2] at full size (6 x 1080p -> 7680-wide spherical panorama, CPW on, 5 bands)
+    ("cfg3", dict(n_views=6, src_w=1920, src_h=1080, pano_width=7680, num_bands=5, enable_local=True)),
+    # BASELINE.json configs[0] at its true shape (2 x 1280x720 -> 4021-wide spherical panorama, enable_local = false, 5 bands)
+    ("cfg1", dict(n_views=2, src_w=1280, src_h=720, pano_width=4021, num_bands=5, enable_local=False)),
+])
+def test_full_size_config3_and_config1_compose(cuda, og, name, kw):
+    import vsb200
+    CASES[name] = kw
+    orig, grig, _ = _rigs(name, inject=False)
+    assert grig.roi_final == orig.roi_final and grig.roi_padded == orig.roi_padded and grig.num_bands == orig.num_bands
+    for i in range(kw["n_views"]):
+        assert grig.geom[i] == orig.blender.view_geom(i), f"view {i} border geometry"
+    frames = [vsb200.synth.frame(i, 1, kw["src_w"], kw["src_h"]) for i in range(kw["n_views"])]
+    want, want_mask = orig.compose(frames)
+    got = grig.compose([frames])[0]
+    _eq(got, want, f"{name} panorama (CV_16SC3)")
+    _eq((np.abs(got).sum(axis=2) > 0) | (want_mask > 0), want_mask > 0, "output mask support")
 
 
 def test_batched_compose_and_mesh_swap(cuda, og):

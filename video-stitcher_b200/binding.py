@@ -19,7 +19,7 @@ MAX_BANDS = 7
 # every symbol include/vsb200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "vsb_last_error", "vsb_version", "vsb_device_count", "vsb_create", "vsb_destroy", "vsb_warp_roi",
-    "vsb_build_maps", "vsb_prepare", "vsb_get_roi", "vsb_init_view", "vsb_get_view_geometry", "vsb_set_maps",
+    "vsb_build_maps", "vsb_warp", "vsb_prepare", "vsb_get_roi", "vsb_init_view", "vsb_get_view_geometry", "vsb_set_maps",
     "vsb_set_gain", "vsb_set_mesh", "vsb_custom_resize", "vsb_feed", "vsb_feed_warped", "vsb_blend", "vsb_compose",
     "vsb_compose_host", "vsb_last_launch_count", "vsb_remap_linear_u8c3", "vsb_gain_u8",
     "vsb_border_reflect_u8c3_to_s16c3", "vsb_pyr_down_s16c3", "vsb_pyr_up_s16c3", "vsb_pyr_down_f32",

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(256) k_nv12_to_bgr(const __grid_constant__ Nv1
             pb[2 * k + q] = nv12_px((int)((yb >> (8 * (2 * k + q))) & 0xff), ruv, guv, buv);
         }
     }
-    if (n == 4 && (p.dst_pitch & 3) == 0) {  // 12 bytes per row = three aligned words (staging rows are 16-byte aligned)
+    if (n == 4 && ((((size_t)p.dst[blockIdx.z]) | p.dst_pitch) & 3) == 0) {  // 12 bytes per row = three aligned words
         unsigned *d0 = (unsigned *)d, *d1 = (unsigned *)(d + p.dst_pitch);
         d0[0] = pa[0] | (pa[1] << 24); d0[1] = (pa[1] >> 8) | (pa[2] << 16); d0[2] = (pa[2] >> 16) | (pa[3] << 8);
         d1[0] = pb[0] | (pb[1] << 24); d1[1] = (pb[1] >> 8) | (pb[2] << 16); d1[2] = (pb[2] >> 16) | (pb[3] << 8);
@@ -828,7 +828,7 @@ struct vsb_stitcher {
     // fast path (num_bands >= 3): static tile tables + per-frame canvas buffer
     bool fast = false;
     vsb::CoarseGeo cgeo;
-    size_t coarse_smem = 0, down_tail_smem = 48 * 1024;
+    size_t coarse_smem = 0;
     uint32_t *d_blend_views = nullptr, *d_coarse_views = nullptr, *d_down2_tiles = nullptr;
     int blend_tiles_x = 0, blend_tiles_y = 0, coarse_tiles_x = 0, coarse_tiles_y = 0, n_down2_tiles = 0;
     int16_t *C2 = nullptr;
@@ -843,7 +843,6 @@ struct vsb_stitcher {
     vsb::ShardRect *d_send[vsb::MAXV] = {}, *d_recv[vsb::MAXV] = {};
     int n_send[vsb::MAXV] = {}, n_recv[vsb::MAXV] = {};
     size_t send_bytes[vsb::MAXV] = {}, recv_bytes[vsb::MAXV] = {};  // per frame
-    uint32_t *d_blend_views_all = nullptr, *d_coarse_views_all = nullptr;  // unsharded tables (d_*_views point at the active ones)
     bool tiles_dirty = true;
     cudaStream_t setup_stream = nullptr, mesh_stream = nullptr, io_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
     cudaEvent_t ev_in[vsb::MAX_BATCH] = {}, ev_done[vsb::MAX_BATCH] = {};
@@ -858,10 +857,8 @@ struct vsb_stitcher {
     // host-buffer path staging
     uint8_t *stage_src = nullptr;
     int16_t *stage_out = nullptr;
-    uint8_t *pin_src = nullptr;
-    int16_t *pin_out = nullptr;
     size_t stage_src_pitch = 0, stage_src_frame = 0, stage_out_pitch = 0, stage_out_frame = 0;
-    int stage_src_w = 0, stage_src_h = 0;
+    int stage_src_w = 0, stage_src_h = 0, stage_views = 0, stage_batch = 0;  // what stage_src / stage_nv12 were sized for
     int rig_projection = -1, rig_src_w = 0, rig_src_h = 0;
     float rig_scale = 0.f;
     // wire / consumer formats (vsb_set_formats): NV12 input goes through k_nv12_to_bgr into nv_bgr; CV_8UC3 output is k_blend<true>
@@ -1017,6 +1014,22 @@ struct HostWeights {  // nonzero structure of one view's static weight pyramid
     }
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (device, function), not per handle: raise it once per device to the
+// architectural maximum so that handles with different needs can coexist (a smaller later request must never lower it).
+template <typename Kernel>
+static int raise_dynamic_smem(Kernel kernel, int device)
+{
+    static std::mutex mu;
+    static bool done[64] = {};
+    std::lock_guard<std::mutex> lk(mu);
+    if (device >= 0 && device < 64 && done[device]) return VSB_OK;
+    int optin = 0;
+    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    if (device >= 0 && device < 64) done[device] = true;
+    return VSB_OK;
+}
+
 static int build_fast_plan(vsb_stitcher *s)
 {
     const int n = s->cfg.num_views, nb = s->nb, F = s->cfg.max_batch;
@@ -1156,8 +1169,7 @@ static int build_fast_plan(vsb_stitcher *s)
     if (!d2tiles.empty()) CK(cudaMemcpy(s->d_down2_tiles, d2tiles.data(), d2tiles.size() * 4, cudaMemcpyHostToDevice));
     s->c2_frame_stride = (size_t)3 * s->cw[2] * s->ch[2];
     CK(cudaMalloc(&s->C2, s->c2_frame_stride * sizeof(int16_t) * F));
-    if (s->coarse_smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(k_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->coarse_smem));
+    if (s->coarse_smem > 48 * 1024) { int r = raise_dynamic_smem(k_coarse, s->device); if (r != VSB_OK) return r; }
     std::vector<CoarseView> desc(n);
     std::memset(desc.data(), 0, sizeof(CoarseView) * n);
     for (int i = 0; i < n; ++i) {
@@ -1201,6 +1213,19 @@ static int ready_for_frames(vsb_stitcher *s)
         REQ(!s->cfg.enable_local || s->v[i].mesh_cur >= 0 || s->v[i].mesh_pending >= 0, VSB_ERR_STATE,
             "compose: enable_local is set but view %d has no mesh (vsb_set_mesh)", i);
     }
+    return VSB_OK;
+}
+
+// Host-side wait for the frame work this handle has submitted (the event every per-frame entry point records), instead of
+// cudaDeviceSynchronize(): other handles, other streams and the mesh builder keep running.
+static int wait_own_frames(vsb_stitcher *s)
+{
+    cudaEvent_t ev = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (s->last_compose_valid) ev = s->last_compose;
+    }
+    if (ev) CK(cudaEventSynchronize(ev));
     return VSB_OK;
 }
 
@@ -1256,7 +1281,7 @@ static int sync_tile_lists(vsb_stitcher *s)
         a.insert(a.end(), s->v[i].s1_tiles.begin(), s->v[i].s1_tiles.end());
         b.insert(b.end(), s->v[i].s2_tiles.begin(), s->v[i].s2_tiles.end());
     }
-    CK(cudaDeviceSynchronize());
+    { int r = wait_own_frames(s); if (r != VSB_OK) return r; }  // submissions in flight still read the old lists
     cudaFree(s->d_s1_tiles); cudaFree(s->d_s2_tiles);
     s->d_s1_tiles = s->d_s2_tiles = nullptr;
     CK(cudaMalloc(&s->d_s1_tiles, std::max<size_t>(a.size(), 1) * 4));
@@ -1358,10 +1383,7 @@ static int launch_down1(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
         double bytes = 0;
         for (int i = v0; i < v1; ++i)
             for (int k = k0; k <= nb; ++k) bytes += 3.0 * (s->v[i].bw >> k) * (s->v[i].bh >> k);
-        if (smem > s->down_tail_smem) {
-            CK(cudaFuncSetAttribute(k_down_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            s->down_tail_smem = smem;
-        }
+        if (smem > 48 * 1024) { int r = raise_dynamic_smem(k_down_tail, s->device); if (r != VSB_OK) return r; }
         DownTailParams p;
         std::memset(&p, 0, sizeof(p));
         p.nb = nb; p.k0 = k0; p.f0 = s->f0;
@@ -1482,7 +1504,10 @@ static int build_taps1(vsb_stitcher *s, int i, size_t src_pitch, cudaStream_t st
 {
     View &V = s->v[i];
     if (V.t1_src_pitch == src_pitch) return VSB_OK;
-    if (V.t1_src_pitch != 0) CK(cudaDeviceSynchronize());  // an earlier submission on another stream may still read the old table
+    if (V.t1_src_pitch != 0) {  // an earlier submission on another stream may still read the old table: order the rebuild after it
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (s->last_compose_valid) CK(cudaStreamWaitEvent(st, s->last_compose, 0));
+    }
     if (!V.t1_off) {
         V.t1_pitch = (int)align_up((size_t)V.roi_w, 4);
         V.t1_plane = (size_t)V.t1_pitch * V.roi_h;
@@ -1658,6 +1683,16 @@ static int launch_back(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, si
     return check_launch("k_legacy_blend_collapse");
 }
 
+// a front half (vsb_feed*) without its blend yet: later table / map updates must still be ordered after it
+static int note_front_done(vsb_stitcher *s, cudaStream_t st, int r)
+{
+    if (r != VSB_OK) return r;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CK(cudaEventRecord(s->last_compose, st));
+    s->last_compose_valid = true;
+    return VSB_OK;
+}
+
 static int note_compose_done(vsb_stitcher *s, cudaStream_t st)
 {
     s->launches_last = s->launches;
@@ -1709,9 +1744,9 @@ int vsb_destroy(vsb_stitcher *s)
     for (int k = 0; k < MAXL; ++k) cudaFree(s->dw[k]);
     cudaFree(s->d_plan);
     cudaFree(s->d_blend_views); cudaFree(s->d_coarse_views); cudaFree(s->d_down2_tiles); cudaFree(s->C2);
+    cudaFree(s->d_coarse_desc); cudaFree(s->d_s1_tiles); cudaFree(s->d_s2_tiles);
     for (int i = 0; i < MAXV; ++i) { cudaFree(s->d_send[i]); cudaFree(s->d_recv[i]); }
     cudaFree(s->stage_src); cudaFree(s->stage_out); cudaFree(s->nv_bgr); cudaFree(s->stage_nv12); cudaFree(s->cons_tab);
-    cudaFreeHost(s->pin_src); cudaFreeHost(s->pin_out);
     if (s->setup_stream) cudaStreamDestroy(s->setup_stream);
     if (s->mesh_stream) cudaStreamDestroy(s->mesh_stream);
     if (s->io_stream) cudaStreamDestroy(s->io_stream);
@@ -1755,7 +1790,8 @@ int vsb_prepare(vsb_stitcher *s, const int *corners_xy, const int *sizes_wh)
         s->ch[k] = k == 0 ? H : (s->ch[k - 1] + 1) / 2;
         CK(cudaMalloc(&s->dw[k], sizeof(float) * s->cw[k] * s->ch[k]));
     }
-    cudaFree(s->stage_src); cudaFree(s->stage_out); s->stage_src = nullptr; s->stage_out = nullptr;  // sized per calibration
+    cudaFree(s->stage_src); cudaFree(s->stage_nv12); cudaFree(s->stage_out);  // sized per calibration
+    s->stage_src = s->stage_nv12 = nullptr; s->stage_out = nullptr; s->stage_src_w = s->stage_src_h = 0;
     s->cons_w = s->cons_ih = 0;  // the consumer's resize tables depend on the panorama size
     s->views_inited = 0; s->prepared = true; s->finalized = false;
     return VSB_OK;
@@ -1880,7 +1916,10 @@ int vsb_set_maps(vsb_stitcher *s, int i, const float *xmap, const float *ymap, i
     REQ(w == V.roi_w && h == V.roi_h, VSB_ERR_INVALID, "set_maps: maps are %dx%d but the view's mask is %dx%d", w, h, V.roi_w, V.roi_h);
     REQ(src_w >= 2 && src_h >= 1 && pitch >= (size_t)w * 4, VSB_ERR_INVALID, "set_maps: bad sizes");
     DeviceGuard g(s->device);
-    CK(cudaDeviceSynchronize());
+    {   // frames in flight may still read the old maps / P: the copies below are stream-ordered after them (no device-wide sync)
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (s->last_compose_valid) CK(cudaStreamWaitEvent(s->setup_stream, s->last_compose, 0));
+    }
     if (!V.xmap) { CK(cudaMalloc(&V.xmap, V.map_pitch * h)); CK(cudaMalloc(&V.ymap, V.map_pitch * h)); }
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     CK(cudaMemcpy2DAsync(V.xmap, V.map_pitch, xmap, pitch, (size_t)w * 4, h, kind, s->setup_stream));
@@ -1913,9 +1952,7 @@ int vsb_set_gain(vsb_stitcher *s, int i, float gain)
 {
     REQ(s && i >= 0 && i < s->cfg.num_views && s->v[i].inited, VSB_ERR_STATE, "set_gain: view %d is not initialised", i);
     REQ(gain >= 0.f && gain < 1e6f, VSB_ERR_INVALID, "set_gain: gain must be a finite non-negative number");
-    DeviceGuard g(s->device);
-    CK(cudaDeviceSynchronize());
-    s->v[i].gain = gain;
+    s->v[i].gain = gain;  // travels by value in the kernel parameters of every later launch: nothing in flight reads it
     return VSB_OK;
 }
 
@@ -2067,7 +2104,7 @@ int vsb_feed(vsb_stitcher *s, int i, const uint8_t *d_bgr, size_t pitch, void *s
     r = adopt_meshes(s, st);
     if (r != VSB_OK) return r;
     const uint8_t *srcs[1] = {d_bgr};
-    return launch_front(s, i, i + 1, 1, srcs, pitch, st);
+    return note_front_done(s, st, launch_front(s, i, i + 1, 1, srcs, pitch, st));
 }
 
 // MultiBandBlender::feed_online(gpu_img, img_num, stream) itself (sources/modules/stitching/src/blenders.cpp:700-749):
@@ -2081,7 +2118,7 @@ int vsb_feed_warped(vsb_stitcher *s, int i, const uint8_t *d_warped, size_t pitc
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (s->launches == 0) prof_begin(s, st);
-    return launch_front(s, i, i + 1, 1, nullptr, pitch, st, d_warped);
+    return note_front_done(s, st, launch_front(s, i, i + 1, 1, nullptr, pitch, st, d_warped));
 }
 
 int vsb_blend(vsb_stitcher *s, int16_t *d_out, size_t out_pitch, void *stream)
@@ -2170,6 +2207,14 @@ int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs
     const int src_rows = nv12 ? sh * 3 / 2 : sh;
     REQ(src_pitch >= src_row && out_pitch >= (size_t)s->roi_final[2] * opx, VSB_ERR_INVALID, "compose_host: pitch too small");
     REQ(!nv12 || ((sw | sh) & 1) == 0, VSB_ERR_INVALID, "compose_host: NV12 needs even source sizes");
+    // device staging of the caller's frames, sized for (source size, views, max_batch) and re-made when any of them changes
+    // (vsb_set_maps may install a different camera resolution without vsb_prepare)
+    if (s->stage_src_w != sw || s->stage_src_h != sh || s->stage_views != n || s->stage_batch != F) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(s->stage_src); cudaFree(s->stage_nv12);
+        s->stage_src = s->stage_nv12 = nullptr;
+        s->stage_src_w = sw; s->stage_src_h = sh; s->stage_views = n; s->stage_batch = F;
+    }
     if (!nv12 && !s->stage_src) {
         s->stage_src_pitch = align_up((size_t)sw * 3, 4);  // tight rows: a packed host frame moves as ONE contiguous DMA
         s->stage_src_frame = align_up(s->stage_src_pitch * sh + 16, 256);
@@ -2420,7 +2465,7 @@ int vsb_feed_batch(vsb_stitcher *s, int v0, int v1, int n_frames, const uint8_t 
     if (s->launches == 0) prof_begin(s, st);
     r = adopt_meshes(s, st);
     if (r != VSB_OK) return r;
-    return launch_front(s, v0, v1, n_frames, d_srcs, pitch, st);
+    return note_front_done(s, st, launch_front(s, v0, v1, n_frames, d_srcs, pitch, st));
 }
 
 int vsb_blend_batch(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, size_t out_pitch, void *stream)

@@ -179,6 +179,35 @@ __global__ void k_build_maps(int proj, float scale, Mat3 k, int tl_u, int tl_v, 
     *(float *)((char *)my + (size_t)dv * pitch + (size_t)du * 4) = y;
 }
 
+// cuda::remap as RotationWarperGpu::warp calls it (sources/modules/stitching/src/warpers_cuda.cpp:279-298 ->
+// sources/modules/cudawarping/src/cuda/remap.cu:56-68): PointFilter / LinearFilter over BrdConstant(0) / BrdReflect readers
+// (sources/modules/core/include/opencv2/core/cuda/filters.hpp:59-117, border_interpolate.hpp:484-534,698-717), CV_8UC1 / CV_8UC3.
+// Calibration-time code (seam-scale images and masks, 360_stitcher/calibration.cpp:118,122,227): one thread per pixel.
+template <int CN>
+__global__ void k_warp_remap(const uint8_t *__restrict__ src, int sw, int sh, size_t sp, const float *__restrict__ xmap,
+                             const float *__restrict__ ymap, size_t mp, uint8_t *__restrict__ dst, int dw, int dh, size_t dp, int interp, int border)
+{
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x, yy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (xx >= dw || yy >= dh) return;
+    const float x = *(const float *)((const char *)xmap + (size_t)yy * mp + (size_t)xx * 4);
+    const float y = *(const float *)((const char *)ymap + (size_t)yy * mp + (size_t)xx * 4);
+    auto rd = [&](int r, int c, int ch) -> float {
+        if (border == 0) return ((unsigned)c < (unsigned)sw && (unsigned)r < (unsigned)sh) ? (float)src[(size_t)r * sp + (size_t)c * CN + ch] : 0.f;
+        return (float)src[(size_t)reflect_idx(r, sh) * sp + (size_t)reflect_idx(c, sw) * CN + ch];
+    };
+    uint8_t *d = dst + (size_t)yy * dp + (size_t)xx * CN;
+    if (interp == 0) {
+        const int c = __float2int_rz(x), r = __float2int_rz(y);
+#pragma unroll
+        for (int ch = 0; ch < CN; ++ch) d[ch] = (uint8_t)rd(r, c, ch);
+        return;
+    }
+    const BilinearTaps t = make_taps(x, y);
+#pragma unroll
+    for (int ch = 0; ch < CN; ++ch)
+        d[ch] = (uint8_t)rni_sat_u8(bilerp(rd(t.y1, t.x1, ch), rd(t.y1, t.x1 + 1, ch), rd(t.y1 + 1, t.x1, ch), rd(t.y1 + 1, t.x1 + 1, ch), t));
+}
+
 }  // namespace vsb
 
 using namespace vsb;
@@ -279,6 +308,34 @@ int vsb_build_maps(int projection, float scale, const float K[9], const float R[
     const dim3 b(32, 8);
     k_build_maps<<<grid2d(roi[2], roi[3], b), b, 0, (cudaStream_t)stream>>>(projection, scale, k, roi[0], roi[1], roi[2], roi[3], d_xmap, d_ymap, pitch_bytes);
     return vsb::check_launch("k_build_maps");
+}
+
+int vsb_warp(int projection, float scale, const float K[9], const float R[9], const uint8_t *d_src, int src_w, int src_h, size_t src_pitch,
+             int channels, int interp, int border, uint8_t *d_dst, size_t dst_pitch, int roi[4], void *stream)
+{
+    VSB_REQUIRE(K && R && d_src && d_dst && roi, "warp: bad arguments");
+    VSB_REQUIRE(channels == 1 || channels == 3, "warp: CV_8UC1 or CV_8UC3 only");
+    VSB_REQUIRE((interp == VSB_INTER_NEAREST || interp == VSB_INTER_LINEAR) && (border == VSB_BORDER_CONSTANT || border == VSB_BORDER_REFLECT),
+                "warp: interp must be NEAREST / LINEAR, border CONSTANT / REFLECT");
+    int r = vsb_warp_roi(projection, scale, K, R, src_w, src_h, roi);
+    if (r != VSB_OK) return r;
+    VSB_REQUIRE(src_pitch >= (size_t)src_w * channels && dst_pitch >= (size_t)roi[2] * channels, "warp: pitch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t mp = ((size_t)roi[2] * 4 + 15) / 16 * 16;
+    float *maps = nullptr;  // d_xmap_ / d_ymap_ of the warper object (warpers.hpp:547-549): scratch here, stream-ordered
+    cudaError_t e = cudaMallocAsync(&maps, 2 * mp * roi[3], st);
+    if (e != cudaSuccess) return vsb::check_cuda(e, "warp: map scratch");
+    float *xm = maps, *ym = (float *)((char *)maps + mp * roi[3]);
+    Mat3 k;
+    float r_kinv[9], rinv[9];
+    vsb::projector_setup(K, R, k.m, r_kinv, rinv);
+    const dim3 b(32, 8);
+    k_build_maps<<<grid2d(roi[2], roi[3], b), b, 0, st>>>(projection, scale, k, roi[0], roi[1], roi[2], roi[3], xm, ym, mp);
+    if (channels == 1) k_warp_remap<1><<<grid2d(roi[2], roi[3], b), b, 0, st>>>(d_src, src_w, src_h, src_pitch, xm, ym, mp, d_dst, roi[2], roi[3], dst_pitch, interp, border);
+    else k_warp_remap<3><<<grid2d(roi[2], roi[3], b), b, 0, st>>>(d_src, src_w, src_h, src_pitch, xm, ym, mp, d_dst, roi[2], roi[3], dst_pitch, interp, border);
+    r = vsb::check_launch("k_warp_remap");
+    cudaFreeAsync(maps, st);
+    return r;
 }
 
 }  // extern "C"
