@@ -166,6 +166,21 @@ int vsb_shard_plan(vsb_stitcher *s, const int *owners);
 int vsb_shard_peer_bytes(const vsb_stitcher *s, int peer, size_t *send_bytes_per_frame, size_t *recv_bytes_per_frame);
 int vsb_shard_pack(vsb_stitcher *s, int peer, int n_frames, void *d_buf, void *stream);
 int vsb_shard_unpack(vsb_stitcher *s, int peer, int n_frames, void *d_buf, void *stream);
+/* Native transport (no caller-side exchange): vsb_shard_unique_id on rank 0 returns VSB_SHARD_ID_BYTES bytes (an ncclUniqueId) that
+ * the host hands to every rank (MPI / TCP / torch.distributed -- control plane only); vsb_shard_init(rank, world, id) = vsb_shard_set +
+ * vsb_shard_plan with the ownership rule every rank evaluates identically + ncclCommInitRank.  libnccl.so.2 is loaded with dlopen
+ * at that point (no link-time dependency).  vsb_shard_compose is stitch_one (A/timed.cpp:123-152) for n_frames frames of ONE frame
+ * stream on `world` GPUs: front half of the owned views -> one grouped ncclSend / ncclRecv per peer (u8 Gaussian sub-planes over
+ * NVLink, stream-ordered) -> back half of the owned strip, written into the FULL-SIZE buffers d_outs[f] (every rank writes its
+ * strip; gather only if the consumer needs one contiguous frame).  d_srcs[f * num_views + v]: entries of views this rank does not own
+ * may be NULL.  Submissions alternate between two halves of the frame slots when 2 * n_frames <= max_batch, so the exchange and back
+ * half of submission k overlap the front half of submission k + 1 (use two caller streams alternately to let them). */
+#define VSB_SHARD_ID_BYTES 128
+int vsb_shard_unique_id(void *id128);
+int vsb_shard_init(vsb_stitcher *s, int rank, int world, const void *id128);
+int vsb_shard_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch_bytes,
+                      int16_t *const *d_outs, size_t out_pitch_bytes, void *stream);
+int vsb_shard_exchange_bytes(const vsb_stitcher *s, size_t *send_bytes_per_frame, size_t *recv_bytes_per_frame);
 /* stitch_online (A/timed.cpp:56-121) for views [v0, v1) of n_frames frames; d_srcs[f * (v1 - v0) + (i - v0)];
  * MultiBandBlender::blend (S/src/blenders.cpp:758-832) for n_frames frames */
 int vsb_feed_batch(vsb_stitcher *s, int v0, int v1, int n_frames, const uint8_t *const *d_srcs, size_t pitch_bytes, void *stream);

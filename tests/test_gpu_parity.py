@@ -237,7 +237,7 @@ def test_compose_matches_oracle(cuda, og, case, inject):
             gk = og.pyr_down_s16(gk)
     _eq(got, want, "composed panorama (CV_16SC3)")
     _eq((np.abs(got).sum(axis=2) > 0) | (want_mask > 0), want_mask > 0, "output mask support")
-    assert grig.st.last_launch_count() == (6 if orig.num_bands >= 3 else 3 + orig.num_bands)  # K1 K2 down2 down_tail coarse blend
+    assert grig.st.last_launch_count() == (7 if orig.num_bands >= 3 else 3 + orig.num_bands)  # K1 K2 down2 down_tail coarse blend_seam blend_int
     # B4/B5 per-view entry points give the same frame
     _eq(grig.feed_blend(frames), want, "feed + blend")
 
@@ -254,7 +254,7 @@ def test_full_size_config4_compose(cuda, og):
     want, want_mask = orig.compose(frames)
     got = grig.compose([frames])[0]
     _eq(got, want, "config 4 panorama (CV_16SC3)")
-    assert grig.st.last_launch_count() == 7  # K1 K2 down2 down1(L3: too large for shared memory) down_tail coarse blend
+    assert grig.st.last_launch_count() == 8  # K1 K2 down2 down1(L3: too large for shared memory) down_tail coarse blend_seam blend_int
 
 
 @pytest.mark.parametrize("name,kw", [
@@ -282,14 +282,14 @@ def test_batched_compose_and_mesh_swap(cuda, og):
     orig, grig, kw = _rigs("small4", inject=False, max_batch=5)
     fr = [[vsb200.synth.frame(i, f, kw["src_w"], kw["src_h"]) for i in range(kw["n_views"])] for f in range(5)]
     want = [orig.compose(f)[0] for f in fr]
-    got = grig.compose(fr)  # 5 frames: two half-batches (3 + 2) on the handle's two internal streams
+    got = grig.compose(fr)  # 5 frames: one remap launch pair, then two sub-batches (2 + 3) on the handle's internal streams
     for f in range(5):
         _eq(got[f], want[f], f"batched frame {f}")
-    assert grig.st.last_launch_count() == 12
+    assert grig.st.last_launch_count() == 12  # K1 K2 + 2 x (down2 down_tail coarse blend_seam blend_int)
     got3 = grig.compose(fr[1:4])  # 3 frames: one submission on the caller's stream
     for f in range(3):
         _eq(got3[f], want[1 + f], f"3-frame batch, frame {f}")
-    assert grig.st.last_launch_count() == 6
+    assert grig.st.last_launch_count() == 7
     # install a different mesh (recalibration, config 5) and compose again
     for i in range(kw["n_views"]):
         mx, my = vsb200.synth.mesh(*orig.sizes[i], phase=0.7)
@@ -464,6 +464,40 @@ def test_recalibration_thread_concurrent_with_compose(cuda, og):
     got = grig.compose(fr)
     for f in range(4):
         _eq(got[f], want[0][f], f"after the last publication, frame {f}")
+
+
+def test_shard_compose_single_rank(cuda, og):
+    """The native view-sharded entry point with world = 1 (no peer): front / exchange / back on the handle's three internal streams,
+    submissions alternating between the two halves of the frame slots and between two caller streams -- every frame bit-exact.
+    (The N > 1 exchange itself is covered by tests/test_gpu_shard.py on >= 2 GPUs and by bench.py's in-run parity check.)"""
+    import torch
+    import vsb200
+    from tests.gpu_util import dev, host
+    B = vsb200.binding
+    orig, grig, kw = _rigs("small4", inject=False, max_batch=4)
+    n = kw["n_views"]
+    fr = [[vsb200.synth.frame(i, f, kw["src_w"], kw["src_h"]) for i in range(n)] for f in range(6)]
+    want = [orig.compose(f)[0] for f in fr]
+    grig.st.shard_init(0, 1, B.shard_unique_id())
+    assert grig.st.shard_info()[2] == list(range(n))
+    W, H = grig.roi_final[2], grig.roi_final[3]
+    srcs = [[dev(a) for a in one] for one in fr]
+    outs = [torch.full((H, W, 3), -12345, dtype=torch.int16, device="cuda") for _ in range(6)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for k in range(3):  # three submissions of two frames: slot halves 0, 1, 0
+        st_ = streams[k & 1]
+        grig.st.shard_compose([t.data_ptr() for f in (2 * k, 2 * k + 1) for t in srcs[f]], kw["src_w"] * 3,
+                              [outs[2 * k].data_ptr(), outs[2 * k + 1].data_ptr()], W * 6, st_.cuda_stream)
+    torch.cuda.synchronize()
+    for f in range(6):
+        _eq(host(outs[f]), want[f], f"shard_compose (world 1) frame {f}")
+    # a 4-frame submission (no second slot half: fully serialised) on the default stream
+    outs4 = [torch.full((H, W, 3), -12345, dtype=torch.int16, device="cuda") for _ in range(4)]
+    grig.st.shard_compose([t.data_ptr() for f in range(4) for t in srcs[f]], kw["src_w"] * 3, [o.data_ptr() for o in outs4], W * 6,
+                          torch.cuda.current_stream().cuda_stream)
+    for f in range(4):
+        _eq(host(outs4[f]), want[f], f"shard_compose (world 1, 4 frames) frame {f}")
 
 
 def test_compose_host_roundtrip(cuda, og):

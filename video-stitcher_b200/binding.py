@@ -27,6 +27,7 @@ SYMBOLS = [
     "vsb_shard_set", "vsb_shard_info", "vsb_shard_rect", "vsb_get_plane",
     "vsb_rig_camera", "vsb_voronoi_seams", "vsb_calibrate_rig", "vsb_rig_info_get", "vsb_get_config", "vsb_set_profiling", "vsb_get_profile",
     "vsb_set_formats", "vsb_nv12_to_bgr", "vsb_consumer_image_height", "vsb_consume",
+    "vsb_shard_unique_id", "vsb_shard_init", "vsb_shard_compose", "vsb_shard_exchange_bytes",
     "vsb_shard_plan", "vsb_shard_peer_bytes", "vsb_shard_pack", "vsb_shard_unpack", "vsb_feed_batch", "vsb_blend_batch",
 ]
 CONSUME_RGB, CONSUME_I420 = 0, 1
@@ -83,6 +84,13 @@ def warp_roi(projection, scale, K, R, src_w, src_h):
     roi = (C.c_int * 4)()
     check(lib().vsb_warp_roi(projection, C.c_float(scale), _fp9(K), _fp9(R), src_w, src_h, roi))
     return tuple(roi)
+
+
+def shard_unique_id():
+    """ncclUniqueId (128 bytes) for vsb_shard_init; call on rank 0 and hand the bytes to every rank."""
+    buf = (C.c_char * 128)()
+    check(lib().vsb_shard_unique_id(buf))
+    return bytes(buf.raw)
 
 
 def rig_camera(n_views, i, src_w, src_h, hfov_deg=90.0):
@@ -217,6 +225,33 @@ class Stitcher:
 
     def shard_unpack(self, peer, n_frames, buf_ptr, stream=0):
         check(lib().vsb_shard_unpack(self._h, peer, n_frames, _vp(buf_ptr), _vp(stream)))
+
+    def shard_init(self, rank, world, unique_id):
+        """Native view-sharded mode: unique_id = the 128 bytes of shard_unique_id() from rank 0 (same on every rank)."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        check(lib().vsb_shard_init(self._h, rank, world, buf))
+
+    def make_shard_compose_call(self, src_ptrs, src_pitch, out_ptrs, out_pitch, stream=0):
+        """src_ptrs[f * num_views + v] (0 for views this rank does not own); out_ptrs[f]: full-size panoramas."""
+        n_frames = len(out_ptrs)
+        sp = (C.c_void_p * len(src_ptrs))(*[int(p) for p in src_ptrs])
+        op = (C.c_void_p * n_frames)(*[int(p) for p in out_ptrs])
+        fn, h, a, b, st = lib().vsb_shard_compose, self._h, C.c_size_t(src_pitch), C.c_size_t(out_pitch), _vp(stream)
+
+        def call():
+            rc = fn(h, n_frames, sp, a, op, b, st)
+            if rc != OK:
+                check(rc)
+        call._keep = (sp, op)
+        return call
+
+    def shard_compose(self, src_ptrs, src_pitch, out_ptrs, out_pitch, stream=0):
+        self.make_shard_compose_call(src_ptrs, src_pitch, out_ptrs, out_pitch, stream)()
+
+    def shard_exchange_bytes(self):
+        a, b = C.c_size_t(), C.c_size_t()
+        check(lib().vsb_shard_exchange_bytes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def feed_batch(self, v0, v1, n_frames, src_ptrs, pitch, stream=0):
         sp = (C.c_void_p * len(src_ptrs))(*[int(p) for p in src_ptrs])

@@ -105,6 +105,8 @@ constexpr int D2_R1W = 2 * D2_TW + 3, D2_R1H = 2 * D2_TH + 3;  // G1 region 67 x
 constexpr int D2_R0VEC = 10, D2_R0H = 4 * D2_TH + 9;            // G0 region 160 B x 73: origin (4*X0 - 16, 4*Y0 - 6)
 constexpr int D2_R1PAIRS = (D2_R1W + 1) / 2;                      // G1 region columns are computed in pairs (2m, 2m + 1)
 constexpr int D2_S1OFF = 2, D2_S1PITCH = 72;                    // G1 column c1 lives at byte c1 + 2: the owned block is word aligned
+constexpr int D2_G1RUN = 5, D2_G1SEG = D2_R1H / D2_G1RUN;        // a thread owns 5 consecutive G1 region rows of one column pair: 34 x 7 threads
+static_assert(D2_G1RUN * D2_G1SEG == D2_R1H && D2_R1PAIRS * D2_G1SEG <= D2_THREADS, "G1 work split");
 
 struct Down2View {
     const uint8_t *g0;  // frame 0, plane 0
@@ -214,25 +216,43 @@ __global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Do
     __syncthreads();
     }
     // G1 over the region, at true in-plane positions only (nested reflection does not commute at the high edge).
-    // One thread computes the column pair (2m, 2m + 1): the two 5-tap windows start at byte 2 of word m + 2 and byte 0 of
-    // word m + 3 of the region row, so no lane diverges on the alignment and the three words per row are loaded once.
-    for (int i = t; i < D2_R1H * D2_R1PAIRS; i += D2_THREADS) {
-        const int r1 = i / D2_R1PAIRS, m = i - r1 * D2_R1PAIRS;
-        const int y1 = 2 * Y0 - 2 + r1, x1 = 2 * X0 - 2 + 2 * m;
-        if ((unsigned)y1 >= (unsigned)h1) continue;
-        const unsigned *row = &s0[2 * r1][m + 2];
-        unsigned acc_e = 0, acc_o = 0;
+    // One thread computes the column pair (2m, 2m + 1) of D2_G1RUN consecutive region rows: the two 5-tap windows start at byte 2
+    // of word m + 2 and byte 0 of word m + 3 of the region row, so no lane diverges on the alignment, and the five G0 rows of
+    // a window slide down in registers (two new rows = six shared-memory words per output row instead of fifteen).
+    if (t < D2_R1PAIRS * D2_G1SEG) {
+        const int sg = t / D2_R1PAIRS, m = t - sg * D2_R1PAIRS;
+        const int x1 = 2 * X0 - 2 + 2 * m;
+        const unsigned *col = &s0[2 * D2_G1RUN * sg][m + 2];
+        unsigned ra[5], rb[5], rc[5];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const unsigned kj = j == 2 ? 6u : ((j & 1) ? 4u : 1u);
-            const unsigned a = row[j * (D2_R0VEC * 4)], b = row[j * (D2_R0VEC * 4) + 1], c2 = row[j * (D2_R0VEC * 4) + 2];
-            acc_e = taps5<false>(a, b, kj, acc_e);
-            acc_o = taps5<true>(b, c2, kj, acc_o);
+        for (int j = 0; j < 3; ++j) { ra[j] = col[j * (D2_R0VEC * 4)]; rb[j] = col[j * (D2_R0VEC * 4) + 1]; rc[j] = col[j * (D2_R0VEC * 4) + 2]; }
+#pragma unroll
+        for (int q = 0; q < D2_G1RUN; ++q) {
+            const int r1 = D2_G1RUN * sg + q, y1 = 2 * Y0 - 2 + r1;
+#pragma unroll
+            for (int j = 3; j < 5; ++j) {
+                const unsigned *w = col + (2 * q + j) * (D2_R0VEC * 4);
+                ra[j] = w[0]; rb[j] = w[1]; rc[j] = w[2];
+            }
+            unsigned acc_e = 127u, acc_o = 127u;  // the constant of the half-even rounding rides in the accumulator
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const unsigned kj = j == 2 ? 6u : ((j & 1) ? 4u : 1u);
+                acc_e = taps5<false>(ra[j], rb[j], kj, acc_e);
+                acc_o = taps5<true>(rb[j], rc[j], kj, acc_o);
+            }
+            // rhe_shift<8>: (v + 127 + ((v >> 8) & 1)) >> 8 < 256, i.e. byte 1 of the sum: both results leave through one PRMT
+            acc_e += ((acc_e - 127u) >> 8) & 1u;
+            acc_o += ((acc_o - 127u) >> 8) & 1u;
+            const unsigned pair = __byte_perm(acc_e, acc_o, 0x0051u);
+            if ((unsigned)y1 < (unsigned)h1) {
+                // column c1 lives at byte c1 + D2_S1OFF: the pair is one aligned 16-bit store; out-of-plane columns are never read
+                if ((unsigned)x1 < (unsigned)w1) *(uint16_t *)&s1[r1][2 * m + D2_S1OFF] = (uint16_t)pair;
+                else if ((unsigned)(x1 + 1) < (unsigned)w1) s1[r1][2 * m + 1 + D2_S1OFF] = (uint8_t)(pair >> 8);
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { ra[j] = ra[j + 2]; rb[j] = rb[j + 2]; rc[j] = rc[j + 2]; }
         }
-        const unsigned ge = (unsigned)rhe_shift<8>((int)acc_e), go = (unsigned)rhe_shift<8>((int)acc_o);
-        // column c1 lives at byte c1 + D2_S1OFF: the pair is one aligned 16-bit store; out-of-plane columns are never read
-        if ((unsigned)x1 < (unsigned)w1) *(uint16_t *)&s1[r1][2 * m + D2_S1OFF] = (uint16_t)(ge | (go << 8));
-        else if ((unsigned)(x1 + 1) < (unsigned)w1) s1[r1][2 * m + 1 + D2_S1OFF] = (uint8_t)go;
     }
     __syncthreads();
     {   // the tile's own 64 x 32 block of G1 (region rows 2..33, columns 2..65), one word per thread and pass
@@ -248,12 +268,18 @@ __global__ void __launch_bounds__(D2_THREADS) k_down2(const __grid_constant__ Do
     // in-plane sample, which lies inside the region), so that the G2 taps below need no index arithmetic.
     const bool reflect_ok = 2 * X0 - 2 >= 0 && 2 * X0 - 2 + D2_R1W - 1 < w1 && 2 * Y0 - 2 >= 0 && 2 * Y0 - 2 + D2_R1H - 1 < h1;
     if (!reflect_ok && w1 >= 6 && h1 >= 6) {
-        for (int i = t; i < D2_R1H * D2_R1W; i += D2_THREADS) {
-            const int r1 = i / D2_R1W, c1 = i - r1 * D2_R1W;
-            const int y1 = 2 * Y0 - 2 + r1, x1 = 2 * X0 - 2 + c1;
-            if ((unsigned)y1 < (unsigned)h1 && (unsigned)x1 < (unsigned)w1) continue;
-            if (y1 < -2 || y1 > h1 || x1 < -2 || x1 > w1) continue;  // never tapped
-            const int my = r101_idx(y1, h1) - (2 * Y0 - 2), mx = r101_idx(x1, w1) - (2 * X0 - 2);
+        // only plane rows / columns -2, -1 and h1 / w1 are ever tapped: three region rows and three region columns at most
+        const int oy = 2 * Y0 - 2, ox = 2 * X0 - 2;
+        for (int i = t; i < 3 * (D2_R1W + D2_R1H); i += D2_THREADS) {
+            int y1, x1;
+            if (i < 3 * D2_R1W) { const int k = i / D2_R1W; y1 = k == 0 ? -2 : (k == 1 ? -1 : h1); x1 = ox + (i - k * D2_R1W); }
+            else { const int e = i - 3 * D2_R1W, k = e / D2_R1H; x1 = k == 0 ? -2 : (k == 1 ? -1 : w1); y1 = oy + (e - k * D2_R1H); }
+            const int r1 = y1 - oy, c1 = x1 - ox;
+            if ((unsigned)r1 >= (unsigned)D2_R1H || (unsigned)c1 >= (unsigned)D2_R1W) continue;      // not in this tile's region
+            if ((unsigned)y1 < (unsigned)h1 && (unsigned)x1 < (unsigned)w1) continue;                // a true sample
+            if (y1 < -2 || y1 > h1 || x1 < -2 || x1 > w1) continue;                                  // never tapped
+            if (i >= 3 * D2_R1W && ((unsigned)y1 >= (unsigned)h1)) continue;                          // corners belong to the row pass
+            const int my = r101_idx(y1, h1) - oy, mx = r101_idx(x1, w1) - ox;
             if ((unsigned)my < (unsigned)D2_R1H && (unsigned)mx < (unsigned)D2_R1W) s1[r1][c1 + D2_S1OFF] = s1[my][mx + D2_S1OFF];
         }
         __syncthreads();
@@ -674,6 +700,21 @@ __global__ void __launch_bounds__(C_THREADS, 3) k_coarse(const __grid_constant__
 
 // =========================================================================================================== k_blend
 // Levels 0 and 1, the final collapse, the output mask and the crop for one 64x32 canvas tile (all three channels).
+// Two kernels over two static tile lists (vsb_pipeline.cu: upload_blend_lists):
+//   k_blend_int   INTERIOR tiles (about 3/4 of a panorama): exactly one view, whose level-0 / level-1 weights -- and therefore
+//                 the weight sums -- are exactly 1 over everything the tile reads.  Then trunc(L * 1) = L, the normalisation
+//                 trunc(acc / 1.00001f) is acc - sign(acc) (exhaustive check in tests/test_abi_host.py) and the output mask is
+//                 all ones: no weights, masks, weight sums, conversions or divisions at all, everything stays fp32.
+//   k_blend_seam  every other tile: view loop, truncating weighted adds, IEEE division by the static weight sums, mask.
+// Shared machinery:
+//   * the level-1 / level-2 regions of a view are staged ONCE per view as fp32 with pyrUp's index rules applied (readers need
+//     no edge cases).  A u8 sample b is staged as the float 32768 + b, which is ONE byte-permute (0x4700bb00) -- no int->float
+//     conversion, no bias removal: every pyrUp partial sum stays an integer below 2^24, and the bias (the taps of every pyrUp
+//     phase sum to 1) is folded into the constant of the single fused multiply-add that scales and rounds half-to-even:
+//     r = fma(sum, 2^-k, 1.5 * 2^23 - 32768) = 1.5 * 2^23 + rne(value), the integer in the low mantissa bits;
+//   * a warp covers rows of ONE parity, so the vertical pyrUp phase never diverges; rows are read as 16-byte vectors;
+//   * CV_16SC3 never saturates on this path (|L| <= 255, |acc| <= 255 * sum(w), |D_k| <= 255 * (nb + 1)), so the reference's
+//     saturate_cast<short> calls are identities and cost nothing here; CV_8UC3 output clamps once, in the final store.
 constexpr int BL_TW = 64, BL_TH = 32, BL_THREADS = 256;
 constexpr int BL_R1W = BL_TW / 2 + 2, BL_R1H = BL_TH / 2 + 2;   // level-1 region 34 x 18, origin (tx0/2 - 1, ty0/2 - 1)
 constexpr int BL_R2W = BL_TW / 4 + 4, BL_R2H = BL_TH / 4 + 4;   // level-2 region 20 x 12, origin (tx0/4 - 2, ty0/4 - 2)
@@ -692,30 +733,27 @@ struct BlendParams {
     int out_w, out_h;
     const int16_t *c2;
     size_t c2_fs;
-    const uint32_t *tile_views;  // bit v: view v has level-0 or level-1 weight in this tile
+    const uint32_t *tile_views;  // seam kernel: bit v: view v has level-0 or level-1 weight in this tile
+    const uint32_t *tiles;       // this launch's tile list: tile_x | tile_y << 12 | (interior kernel: view << 24)
     const float *dw0, *dw1;      // static weight sums of canvas levels 0 and 1 (accumulated in view order at calibration)
     BlendView v[MAXV];
 };
 
-// ======================================================================================================== k_blend (v2)
-// Restructured (from a first version with integer pyrUp and one pass over the views) around what the profile showed (56 % issue utilisation, 80 registers, the two
-// pyrUp evaluations per output sample dominating):
-//   * the level-1 / level-2 regions are staged ONCE per view as fp32 (clamped like pyrUp's index rules, so the readers
-//     need no edge cases) and every pyrUp is evaluated in fp32: all partial sums are integers below 2^24, the final
-//     scale is a power of two and one fused multiply-add onto 1.5 * 2^23 rounds half-to-even at integer granularity --
-//     the same integer as rhe_shift<6>, without the four-instruction integer rounding per sample;
-//   * two passes over the tile's views -- level 1 first (accumulators: 8 registers), then level 0 (24 registers) -- instead
-//     of carrying both sets plus the weight sums through one loop; the weight sums come from the static tables;
-//   * a warp covers rows of ONE parity, so the vertical pyrUp phase never diverges; rows are read as 16-byte vectors;
-//   * the level-1 work is 3 x 153 (channel, quad) items spread over all 256 threads.
 constexpr int B2_G1P = 44, B2_G1OFF = 4;    // fp32 level-1 region: row pitch (floats) and index of region column 0
 constexpr int B2_G2P = 24, B2_G2OFF = 2;    // fp32 level-2 region
 constexpr int B2_G1F = 3 * BL_R1H * B2_G1P, B2_G2F = 3 * BL_R2H * B2_G2P;  // floats per staged region
 constexpr int B2_ITEMS = 3 * BL_NQ;         // (channel, level-1 quad) work items
+constexpr float B2_U8BIAS = 32768.f;        // staged u8 samples are 32768 + b
+constexpr float B2_CB_U8 = B2_MAGIC - B2_U8BIAS, B2_CB_0 = B2_MAGIC;  // rounding constants for biased / unbiased regions
+
+// byte `k` of `w` as the float 32768 + b: exponent 2^15, the byte in mantissa bits 8..15
+__device__ __forceinline__ float u8_b15(unsigned w, int k) { return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404u | ((unsigned)k << 4))); }
+__device__ __forceinline__ float4 u8x4_b15(unsigned w) { return make_float4(u8_b15(w, 0), u8_b15(w, 1), u8_b15(w, 2), u8_b15(w, 3)); }
 
 // pyrUp of the quad {x0, x0+1} x {y0, y0+1}, x0 and y0 odd, from an fp32 region; p points at (row y0 >> 1, column x0 >> 1).
 // r[q] = value + 1.5 * 2^23 (the integer sits in the low mantissa bits); same integers as pyr_up_sample at the four positions.
-__device__ __forceinline__ void up_quad_odd_f(const float *p, int pitch, float r[4])
+// cb = B2_CB_U8 for a region staged with the 32768 bias, B2_CB_0 for a plain one.
+__device__ __forceinline__ void up_quad_odd_f(const float *p, int pitch, float cb, float r[4])
 {
     float h[3], s[3];
 #pragma unroll
@@ -724,16 +762,16 @@ __device__ __forceinline__ void up_quad_odd_f(const float *p, int pitch, float r
         h[i] = __fadd_rn(__fmaf_rn(s1, 6.f, s0), s2);
         s[i] = __fadd_rn(s0, s1);
     }
-    r[0] = __fmaf_rn(__fadd_rn(s[0], s[1]), 0.25f, B2_MAGIC);
-    r[1] = __fmaf_rn(__fadd_rn(h[0], h[1]), 0.0625f, B2_MAGIC);
-    r[2] = __fmaf_rn(__fadd_rn(__fmaf_rn(s[1], 6.f, s[0]), s[2]), 0.0625f, B2_MAGIC);
-    r[3] = __fmaf_rn(__fadd_rn(__fmaf_rn(h[1], 6.f, h[0]), h[2]), 0.015625f, B2_MAGIC);
+    r[0] = __fmaf_rn(__fadd_rn(s[0], s[1]), 0.25f, cb);
+    r[1] = __fmaf_rn(__fadd_rn(h[0], h[1]), 0.0625f, cb);
+    r[2] = __fmaf_rn(__fadd_rn(__fmaf_rn(s[1], 6.f, s[0]), s[2]), 0.0625f, cb);
+    r[3] = __fmaf_rn(__fadd_rn(__fmaf_rn(h[1], 6.f, h[0]), h[2]), 0.015625f, cb);
 }
 
 // pyrUp of 8 consecutive samples (first one at an even column) of one row from an fp32 region; p points at the region
 // sample (row (y >> 1) - 1, column (x0 >> 1) - 1), 16-byte aligned.  ODD = parity of the destination row.
 template <bool ODD>
-__device__ __forceinline__ void up_row8_f(const float *p, float r[8])
+__device__ __forceinline__ void up_row8_f(const float *p, float cb, float r[8])
 {
     float col[6];
     const float4 m4 = *(const float4 *)(p + B2_G1P), b4 = *(const float4 *)(p + 2 * B2_G1P);
@@ -752,65 +790,264 @@ __device__ __forceinline__ void up_row8_f(const float *p, float r[8])
     const float ke = ODD ? 0.0625f : 0.015625f, ko = ODD ? 0.25f : 0.0625f;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        r[2 * q] = __fmaf_rn(__fadd_rn(__fmaf_rn(col[q + 1], 6.f, col[q]), col[q + 2]), ke, B2_MAGIC);
-        r[2 * q + 1] = __fmaf_rn(__fadd_rn(col[q + 1], col[q + 2]), ko, B2_MAGIC);
+        r[2 * q] = __fmaf_rn(__fadd_rn(__fmaf_rn(col[q + 1], 6.f, col[q]), col[q + 2]), ke, cb);
+        r[2 * q + 1] = __fmaf_rn(__fadd_rn(col[q + 1], col[q + 2]), ko, cb);
     }
 }
 
-// the same 8 samples through pyrUp's index rules (abs at the low edge, clamp at the high edge) for threads at the canvas border;
-// reg(0, 0) is plane sample (ox, oy) and sits at reg[B2_G1OFF]
-__device__ __noinline__ void up_row8_f_edge(const float *reg, int ox, int oy, int x0, int y, int n_x, int n_y, float r[8])
+// ---- staging (both kernels) ---------------------------------------------------------------------------------------------
+// level-1 region of one view: 10 aligned words per region row (plane columns v1x0 - 3 .. v1x0 + 36), pyrUp's index rules
+// (abs at the low edge, clamp at the high edge) applied on the view's plane; all loads are issued before the first store
+__device__ __forceinline__ void stage_g1(float *sG1f, const BlendView &V, int f, int tx0, int ty0, int t)
 {
-    const int ix0 = x0 >> 1, iy = y >> 1;
-    float col[6];
+    const int w1 = V.bw >> 1, h1 = V.bh >> 1;
+    const int v1x0 = (tx0 >> 1) - 1 - (V.x_tl >> 1), v1y0 = (ty0 >> 1) - 1 - (V.y_tl >> 1);
+    const uint8_t *g1 = V.g1 + (size_t)f * V.g1_fs;
+    constexpr int N = 3 * BL_R1H * 10, ROUNDS = (N + BL_THREADS - 1) / BL_THREADS;
+    unsigned word[ROUNDS];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const int cx = up_idx(ix0 - 1 + i, n_x) - ox + B2_G1OFF;
-        const float mid = reg[(iy - oy) * B2_G1P + cx], bot = reg[(up_idx(iy + 1, n_y) - oy) * B2_G1P + cx];
-        col[i] = (y & 1) ? __fadd_rn(mid, bot) : __fadd_rn(__fmaf_rn(mid, 6.f, reg[(up_idx(iy - 1, n_y) - oy) * B2_G1P + cx]), bot);
+    for (int it = 0; it < ROUNDS; ++it) {
+        const int i = t + it * BL_THREADS;
+        word[it] = 0;
+        if (i >= N) continue;
+        const int rk = i / 10, k = i - rk * 10, c = rk / BL_R1H, r = rk - c * BL_R1H;
+        const uint8_t *row = g1 + ((size_t)c * h1 + up_idx(v1y0 + r, h1)) * w1;
+        const int col0 = v1x0 - 3 + 4 * k;
+        if (col0 >= 0 && col0 + 3 < w1 && (((size_t)(row + col0)) & 3) == 0) {
+            word[it] = __ldg((const unsigned *)(row + col0));
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) word[it] |= ldg_u8(row + up_idx(col0 + b, w1)) << (8 * b);
+        }
     }
-    const float ke = (y & 1) ? 0.0625f : 0.015625f, ko = (y & 1) ? 0.25f : 0.0625f;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        r[2 * q] = __fmaf_rn(__fadd_rn(__fmaf_rn(col[q + 1], 6.f, col[q]), col[q + 2]), ke, B2_MAGIC);
-        r[2 * q + 1] = __fmaf_rn(__fadd_rn(col[q + 1], col[q + 2]), ko, B2_MAGIC);
+    for (int it = 0; it < ROUNDS; ++it) {
+        const int i = t + it * BL_THREADS;
+        if (i >= N) continue;
+        const int rk = i / 10, k = i - rk * 10;  // rk = c * BL_R1H + r
+        float *d = sG1f + rk * B2_G1P + 1 + 4 * k;
+        const float4 v = u8x4_b15(word[it]);
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+}
+// level-2 region of one view: 6 aligned words per row (plane columns ux0 - 2 .. ux0 + 21)
+__device__ __forceinline__ void stage_g2(float *sG2f, const BlendView &V, int f, int tx0, int ty0, int t)
+{
+    const int w2 = V.bw >> 2, h2 = V.bh >> 2;
+    const uint8_t *g2 = V.g2 + (size_t)f * V.g2_fs;
+    const int ux0 = (tx0 >> 2) - 2 - (V.x_tl >> 2), uy0 = (ty0 >> 2) - 2 - (V.y_tl >> 2);
+    if (t < 3 * BL_R2H * 6) {
+        const int rk = t / 6, k = t - rk * 6, c = rk / BL_R2H, r = rk - c * BL_R2H;
+        const uint8_t *row = g2 + ((size_t)c * h2 + up_idx(uy0 + r, h2)) * w2;
+        const int col0 = ux0 - 2 + 4 * k;
+        unsigned word;
+        if (col0 >= 0 && col0 + 3 < w2 && (((size_t)(row + col0)) & 3) == 0) {  // rows are word aligned from num_bands >= 4 on
+            word = __ldg((const unsigned *)(row + col0));
+        } else {
+            word = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) word |= ldg_u8(row + up_idx(col0 + b, w2)) << (8 * b);
+        }
+        *(float4 *)(sG2f + rk * B2_G2P + 4 * k) = u8x4_b15(word);
+    }
+}
+// C2 region (canvas level 2, s16, collapsed levels 2..nb) as plain fp32, pyrUp's index rules applied on the canvas
+__device__ __forceinline__ void stage_c2(float *sC2f, const BlendParams &P, int f, int tx0, int ty0, int t)
+{
+    const int16_t *c2 = P.c2 + (size_t)f * P.c2_fs;
+    const int ux0 = (tx0 >> 2) - 2, uy0 = (ty0 >> 2) - 2;
+    if (t < 3 * BL_R2H * 6) {
+        const int rk = t / 6, k = t - rk * 6, c = rk / BL_R2H, r = rk - c * BL_R2H;
+        const int16_t *row = c2 + ((size_t)c * P.ch2 + up_idx(uy0 + r, P.ch2)) * P.cw2;
+        const int col0 = ux0 - 2 + 4 * k;
+        float4 v;
+        if (col0 >= 0 && col0 + 3 < P.cw2 && (((size_t)(row + col0)) & 7) == 0) {
+            const uint2 w = __ldg((const uint2 *)(row + col0));
+            v = make_float4((float)(short)(w.x & 0xffffu), (float)(short)(w.x >> 16), (float)(short)(w.y & 0xffffu), (float)(short)(w.y >> 16));
+        } else {
+            v = make_float4((float)__ldg(row + up_idx(col0, P.cw2)), (float)__ldg(row + up_idx(col0 + 1, P.cw2)),
+                            (float)__ldg(row + up_idx(col0 + 2, P.cw2)), (float)__ldg(row + up_idx(col0 + 3, P.cw2)));
+        }
+        *(float4 *)(sC2f + rk * B2_G2P + 4 * k) = v;
+    }
+}
+// The collapsed level-1 region holds canvas samples only; its one-sample ring may lie outside the canvas (tiles on the canvas
+// border).  pyrUp reads those positions through abs() at the low edge (-1 -> 1) and a clamp at the high edge (n -> n - 1):
+// write the mapped samples into the ring once, and every reader takes the plain fast path.
+__device__ __forceinline__ void fix_d1_ring(float *sD1f, const BlendParams &P, int tx0, int ty0, int t)
+{
+    const int ox = (tx0 >> 1) - 1, oy = (ty0 >> 1) - 1;
+    if (ox >= 0 && oy >= 0 && ox + BL_R1W <= P.cw1 && oy + BL_R1H <= P.ch1) return;  // region inside the canvas (uniform)
+    __syncthreads();
+    for (int i = t; i < 3 * BL_R1H * BL_R1W; i += BL_THREADS) {
+        const int c = i / (BL_R1H * BL_R1W), rem = i - c * (BL_R1H * BL_R1W), r = rem / BL_R1W, q = rem - r * BL_R1W;
+        const int x = ox + q, y = oy + r;
+        if ((unsigned)x < (unsigned)P.cw1 && (unsigned)y < (unsigned)P.ch1) continue;
+        const int mx = up_idx(x, P.cw1) - ox, my = up_idx(y, P.ch1) - oy;
+        float v = 0.f;
+        if ((unsigned)mx < (unsigned)BL_R1W && (unsigned)my < (unsigned)BL_R1H) v = sD1f[(c * BL_R1H + my) * B2_G1P + B2_G1OFF + mx];
+        sD1f[(c * BL_R1H + r) * B2_G1P + B2_G1OFF + q] = v;
     }
 }
 
-// U8: the consumer's `mat.convertTo(mat_8u, CV_8U)` (360_stitcher/timed.cpp:250) is applied in the final store: the
-// panorama leaves as CV_8UC3 (saturate_cast<uchar> of the CV_16SC3 sample) -- half the bytes to write and to download.
+// 8 pixels x 3 channels of one thread (o[c][i] = biased float bits, low half-word / byte = the sample) into the interleaved
+// output tile in shared memory: element e = 3 * i + c, 48 contiguous bytes of CV_16SC3 or 24 of CV_8UC3
 template <bool U8>
+__device__ __forceinline__ void put_out8(void *sTile, int ly, int lx, const unsigned (&o)[3][8])
+{
+    if (U8) {
+        uint2 *o2 = (uint2 *)((uint8_t *)sTile + ly * (BL_TW * 3) + lx * 3);
+#pragma unroll
+        for (int v2 = 0; v2 < 3; ++v2) {
+            unsigned w[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int e = 8 * v2 + 4 * k;
+                const unsigned lo = __byte_perm(o[e % 3][e / 3], o[(e + 1) % 3][(e + 1) / 3], 0x0040u);
+                const unsigned hi = __byte_perm(o[(e + 2) % 3][(e + 2) / 3], o[(e + 3) % 3][(e + 3) / 3], 0x0040u);
+                w[k] = __byte_perm(lo, hi, 0x5410u);
+            }
+            o2[v2] = make_uint2(w[0], w[1]);
+        }
+    } else {
+        uint4 *o4 = (uint4 *)((int16_t *)sTile + ly * (BL_TW * 3) + lx * 3);
+#pragma unroll
+        for (int v4 = 0; v4 < 3; ++v4) {
+            unsigned w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int e0 = 8 * v4 + 2 * k, e1 = e0 + 1;
+                w[k] = __byte_perm(o[e0 % 3][e0 / 3], o[e1 % 3][e1 / 3], 0x5410u);
+            }
+            o4[v4] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+// cropped, interleaved store of the tile: 16-byte vectors where the caller's buffer allows; one warp per row
+template <bool U8>
+__device__ __forceinline__ void store_tile(const void *sTile, const BlendParams &P, void *out, size_t out_pitch, int tx0, int ty0, int t)
+{
+    constexpr int PXB = U8 ? 3 : 6;  // bytes per output pixel
+    const int n_px = min(BL_TW, P.out_w - tx0), n_rows = min(BL_TH, P.out_h - ty0);
+    if (n_px <= 0 || n_rows <= 0) return;
+    char *obase = (char *)out + (size_t)tx0 * PXB;
+    const bool vec_ok = ((((size_t)obase) | out_pitch) & 15) == 0;
+    const int row_bytes = n_px * PXB;
+    const int ck = t & 31, b0 = ck * 16;
+    if (ck >= BL_TW * PXB / 16 || b0 >= row_bytes) return;
+    for (int r = t >> 5; r < n_rows; r += BL_THREADS / 32) {
+        char *o = obase + (size_t)(ty0 + r) * out_pitch + b0;
+        const char *sp = (const char *)sTile + r * (BL_TW * PXB) + b0;
+        if (vec_ok && b0 + 16 <= row_bytes) {
+            *(uint4 *)o = *(const uint4 *)sp;
+        } else {
+            const int n = min(16, row_bytes - b0);
+            for (int e = 0; e < n; ++e) o[e] = sp[e];
+        }
+    }
+}
+
 #ifndef VSB_BL_MINB
 #define VSB_BL_MINB 4
 #endif
-__global__ void __launch_bounds__(BL_THREADS, VSB_BL_MINB) k_blend(const __grid_constant__ BlendParams P, const __grid_constant__ OutPtrs outs, size_t out_pitch)
+#ifndef VSB_BLI_MINB
+#define VSB_BLI_MINB 5
+#endif
+
+// ============================================================================================================ k_blend_int
+// U8: the consumer's `mat.convertTo(mat_8u, CV_8U)` (360_stitcher/timed.cpp:250) is applied in the final store: the
+// panorama leaves as CV_8UC3 (saturate_cast<uchar> of the CV_16SC3 sample) -- half the bytes to write and to download.
+template <bool U8>
+__global__ void __launch_bounds__(BL_THREADS, VSB_BLI_MINB) k_blend_int(const __grid_constant__ BlendParams P, const __grid_constant__ OutPtrs outs, size_t out_pitch)
 {
-    // staging area: fp32 G1 and G2 regions of the current view; re-used for the interleaved output tile at the end
-    __shared__ __align__(16) float sStage[B2_G1F + B2_G2F];
+    __shared__ __align__(16) float sStage[B2_G1F + B2_G2F];  // fp32 G1 and G2 regions of the view; re-used for the output tile
     __shared__ __align__(16) float sC2f[B2_G2F];
     __shared__ __align__(16) float sD1f[B2_G1F];
     float *sG1f = sStage, *sG2f = sStage + B2_G1F;
     static_assert(sizeof(float) * (B2_G1F + B2_G2F) >= sizeof(int16_t) * BL_TH * BL_TW * 3, "output tile must fit the staging area");
-    const int t = threadIdx.x, f = blockIdx.z + P.f0;
-    const int tx0 = blockIdx.x * BL_TW, ty0 = blockIdx.y * BL_TH;
-    const unsigned views_word = __ldg(P.tile_views + blockIdx.y * P.tiles_x + blockIdx.x);
-    if (views_word & 0x80000000u) return;  // view-sharded mode: another rank owns this canvas strip
-    // interior tile (static flag): one view whose level-0 / level-1 weights are exactly 1 over everything this tile reads, so the
-    // mask, the weights and the weight sums need not be loaded (they are 1) -- the arithmetic below is unchanged
-    const bool interior = (views_word & 0x40000000u) != 0;
-    const unsigned views_all = views_word & 0x3fffffffu;
+    const int t = threadIdx.x, f = blockIdx.y + P.f0;
+    const unsigned tile = __ldg(P.tiles + blockIdx.x);
+    const int tx0 = (int)(tile & 0xfffu) * BL_TW, ty0 = (int)((tile >> 12) & 0xfffu) * BL_TH;
+    const BlendView &V = P.v[tile >> 24];
+    stage_g1(sG1f, V, f, tx0, ty0, t);
+    stage_g2(sG2f, V, f, tx0, ty0, t);
+    stage_c2(sC2f, P, f, tx0, ty0, t);
+    // level-0 inputs of this thread are independent of the staging: issue the loads before the barrier
+    const int warp = t >> 5, lane = t & 31;
+    const int ly = (warp >> 1) * 8 + (lane >> 3) * 2 + (warp & 1), lx = (lane & 7) * 8;  // a warp holds four rows of one parity
+    const int px0 = tx0 + lx, py = ty0 + ly;
+    const bool row_odd = warp & 1;
+    const int reg_off = (ly >> 1) * B2_G1P + (lx >> 1) + B2_G1OFF;  // region sample (row (y>>1) - 1, column (x0>>1) - 1) of this thread
+    uint2 gg[3];
+    {
+        const int w0 = V.bw, h0 = V.bh, qx0 = px0 - V.x_tl, qy = py - V.y_tl;  // inside the plane (interior tile)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gg[c] = __ldg((const uint2 *)(V.g0 + (size_t)f * V.g0_fs + ((size_t)c * h0 + qy) * w0 + qx0));
+    }
+    __syncthreads();
+    // ---- level 1: D1 = (L1 - sign(L1)) + pyrUp(C2), L1 = G1 - pyrUp(G2); quads of the 34 x 18 region, all three channels
+#pragma unroll 1
+    for (int it = t; it < B2_ITEMS; it += BL_THREADS) {
+        const int c = it / BL_NQ, quad = it - c * BL_NQ;
+        const int qr1 = 2 * (quad / BL_QW), qc1 = 2 * (quad - (quad / BL_QW) * BL_QW);
+        float up[4], uc[4];
+        up_quad_odd_f(sG2f + (c * BL_R2H + 1 + (qr1 >> 1)) * B2_G2P + B2_G2OFF + 1 + (qc1 >> 1), B2_G2P, B2_CB_U8, up);
+        up_quad_odd_f(sC2f + (c * BL_R2H + 1 + (qr1 >> 1)) * B2_G2P + B2_G2OFF + 1 + (qc1 >> 1), B2_G2P, B2_CB_0, uc);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int idx = (c * BL_R1H + qr1 + (q >> 1)) * B2_G1P + B2_G1OFF + qc1 + (q & 1);
+            const float lap = __fsub_rn(__fadd_rn(sG1f[idx], B2_CB_U8), up[q]);        // G1 - pyrUp(G2), exact
+            const float n = __fsub_rn(lap, fminf(fmaxf(lap, -1.f), 1.f));               // trunc(L / 1.00001f)
+            sD1f[idx] = __fsub_rn(__fadd_rn(n, uc[q]), B2_MAGIC);                       // + pyrUp(C2), plain fp32
+        }
+    }
+    fix_d1_ring(sD1f, P, tx0, ty0, t);
+    __syncthreads();
+    // ---- level 0: out = (L0 - sign(L0)) + pyrUp(D1), L0 = G0 - pyrUp(G1)
+    unsigned o[3][8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float up[8], ud[8];
+        const float *rp = sG1f + c * (BL_R1H * B2_G1P) + reg_off, *dp = sD1f + c * (BL_R1H * B2_G1P) + reg_off;
+        if (row_odd) { up_row8_f<true>(rp, B2_CB_U8, up); up_row8_f<true>(dp, B2_CB_0, ud); }
+        else { up_row8_f<false>(rp, B2_CB_U8, up); up_row8_f<false>(dp, B2_CB_0, ud); }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float gb = __uint_as_float(__byte_perm(i < 4 ? gg[c].x : gg[c].y, (unsigned)B2_MAGIC_BITS, 0x7650u | (unsigned)(i & 3)));  // G0 + 1.5 * 2^23
+            const float lap = __fsub_rn(gb, up[i]);
+            float v = __fadd_rn(__fsub_rn(lap, fminf(fmaxf(lap, -1.f), 1.f)), ud[i]);  // bits 0x4B400000 + sample: the low half-word is the CV_16SC3 value
+            if (U8) v = fminf(fmaxf(v, B2_MAGIC), B2_MAGIC + 255.f);
+            o[c][i] = __float_as_uint(v);
+        }
+    }
+    __syncthreads();  // every reader of the staging area is done (the output tile re-uses it)
+    put_out8<U8>(sStage, ly, lx, o);
+    __syncthreads();
+    store_tile<U8>(sStage, P, outs.out[f], out_pitch, tx0, ty0, t);
+}
+
+// =========================================================================================================== k_blend_seam
+// Every tile that is not interior: two passes over the tile's views -- level 1 first (accumulators: 8 registers), then level 0
+// (24 registers); the weight sums come from the static tables; the level-1 work is 3 x 153 (channel, quad) items spread over
+// all 256 threads.
+template <bool U8>
+__global__ void __launch_bounds__(BL_THREADS, VSB_BL_MINB) k_blend_seam(const __grid_constant__ BlendParams P, const __grid_constant__ OutPtrs outs, size_t out_pitch)
+{
+    __shared__ __align__(16) float sStage[B2_G1F + B2_G2F];
+    __shared__ __align__(16) float sC2f[B2_G2F];
+    __shared__ __align__(16) float sD1f[B2_G1F];
+    float *sG1f = sStage, *sG2f = sStage + B2_G1F;
+    const int t = threadIdx.x, f = blockIdx.y + P.f0;
+    const unsigned tile = __ldg(P.tiles + blockIdx.x);
+    const int bx = (int)(tile & 0xfffu), by = (int)((tile >> 12) & 0xfffu);
+    const int tx0 = bx * BL_TW, ty0 = by * BL_TH;
+    const unsigned views_all = __ldg(P.tile_views + by * P.tiles_x + bx) & 0x3fffffffu;
     // level-0 mapping: a warp holds four rows of one parity, a thread 8 consecutive samples
     const int warp = t >> 5, lane = t & 31;
     const int ly = (warp >> 1) * 8 + (lane >> 3) * 2 + (warp & 1), lx = (lane & 7) * 8;
     const int px0 = tx0 + lx, py = ty0 + ly;
     const bool row_odd = warp & 1;
-    const int reg_off = (ly >> 1) * B2_G1P + (lx >> 1) + B2_G1OFF;  // region sample (row (y>>1) - 1, column (x0>>1) - 1) of this thread
-    // static weight sum of this thread's 8 samples: exactly 1 on most of the panorama (one view, full weight)
-    bool dw_all_one = interior;
-    if (!interior && px0 < P.cw0 && py < P.ch0) {
-        const float4 da = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0)), db = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0 + 4));
-        dw_all_one = da.x == 1.f && da.y == 1.f && da.z == 1.f && da.w == 1.f && db.x == 1.f && db.y == 1.f && db.z == 1.f && db.w == 1.f;
-    }
+    const int reg_off = (ly >> 1) * B2_G1P + (lx >> 1) + B2_G1OFF;
     // level-1 mapping: up to two (channel, quad) items per thread
     int it_c[2], it_qr[2], it_qc[2];
 #pragma unroll
@@ -824,87 +1061,16 @@ __global__ void __launch_bounds__(BL_THREADS, VSB_BL_MINB) k_blend(const __grid_
 #pragma unroll
     for (int k = 0; k < 2; ++k) acc1[k][0] = acc1[k][1] = acc1[k][2] = acc1[k][3] = 0;
 
-    auto stage_view = [&](const BlendView &V, bool with_g2) {
-        const int w1 = V.bw >> 1, h1 = V.bh >> 1, w2 = V.bw >> 2, h2 = V.bh >> 2;
-        const int v1x0 = (tx0 >> 1) - 1 - (V.x_tl >> 1), v1y0 = (ty0 >> 1) - 1 - (V.y_tl >> 1);
-        const uint8_t *g1 = V.g1 + (size_t)f * V.g1_fs;
-        {   // 10 aligned words per region row (plane columns v1x0 - 3 .. v1x0 + 36); all loads are issued before the first conversion
-            constexpr int N = 3 * BL_R1H * 10, ROUNDS = (N + BL_THREADS - 1) / BL_THREADS;
-            unsigned word[ROUNDS];
-#pragma unroll
-            for (int it = 0; it < ROUNDS; ++it) {
-                const int i = t + it * BL_THREADS;
-                word[it] = 0;
-                if (i >= N) continue;
-                const int c = i / (BL_R1H * 10), rem = i - c * (BL_R1H * 10);
-                const int r = rem / 10, k = rem - r * 10;
-                const uint8_t *row = g1 + ((size_t)c * h1 + up_idx(v1y0 + r, h1)) * w1;
-                const int col0 = v1x0 - 3 + 4 * k;
-                if (col0 >= 0 && col0 + 3 < w1 && (((size_t)(row + col0)) & 3) == 0) {
-                    word[it] = __ldg((const unsigned *)(row + col0));
-                } else {
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) word[it] |= ldg_u8(row + up_idx(col0 + b, w1)) << (8 * b);
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < ROUNDS; ++it) {
-                const int i = t + it * BL_THREADS;
-                if (i >= N) continue;
-                const int rk = i / 10, k = i - rk * 10;  // rk = c * BL_R1H + r
-                float *d = sG1f + rk * B2_G1P + 1 + 4 * k;
-                d[0] = (float)(word[it] & 0xffu); d[1] = (float)((word[it] >> 8) & 0xffu); d[2] = (float)((word[it] >> 16) & 0xffu); d[3] = (float)(word[it] >> 24);
-            }
-        }
-        if (with_g2) {
-            const uint8_t *g2 = V.g2 + (size_t)f * V.g2_fs;
-            const int ux0 = (tx0 >> 2) - 2 - (V.x_tl >> 2), uy0 = (ty0 >> 2) - 2 - (V.y_tl >> 2);
-            for (int i = t; i < 3 * BL_R2H * 6; i += BL_THREADS) {  // 6 aligned words per row: plane columns ux0 - 2 .. ux0 + 21
-                const int c = i / (BL_R2H * 6), rem = i - c * (BL_R2H * 6);
-                const int r = rem / 6, k = rem - r * 6;
-                const uint8_t *row = g2 + ((size_t)c * h2 + up_idx(uy0 + r, h2)) * w2;
-                const int col0 = ux0 - 2 + 4 * k;
-                unsigned word;
-                if (col0 >= 0 && col0 + 3 < w2 && (((size_t)(row + col0)) & 3) == 0) {  // rows are word aligned from num_bands >= 4 on
-                    word = __ldg((const unsigned *)(row + col0));
-                } else {
-                    word = 0;
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) word |= ldg_u8(row + up_idx(col0 + b, w2)) << (8 * b);
-                }
-                *(float4 *)(sG2f + (c * BL_R2H + r) * B2_G2P + 4 * k) =
-                    make_float4((float)(word & 0xffu), (float)((word >> 8) & 0xffu), (float)((word >> 16) & 0xffu), (float)(word >> 24));
-            }
-        }
-    };
-
-    // ---- pass 1: level 1.  C2 region (canvas level 2, s16) -> fp32 once per tile
-    {
-        const int16_t *c2 = P.c2 + (size_t)f * P.c2_fs;
-        const int ux0 = (tx0 >> 2) - 2, uy0 = (ty0 >> 2) - 2;
-        for (int i = t; i < 3 * BL_R2H * 6; i += BL_THREADS) {
-            const int c = i / (BL_R2H * 6), rem = i - c * (BL_R2H * 6);
-            const int r = rem / 6, k = rem - r * 6;
-            const int16_t *row = c2 + ((size_t)c * P.ch2 + up_idx(uy0 + r, P.ch2)) * P.cw2;
-            const int col0 = ux0 - 2 + 4 * k;
-            float4 v;
-            if (col0 >= 0 && col0 + 3 < P.cw2 && (((size_t)(row + col0)) & 7) == 0) {
-                const uint2 w = __ldg((const uint2 *)(row + col0));
-                v = make_float4((float)(short)(w.x & 0xffffu), (float)(short)(w.x >> 16), (float)(short)(w.y & 0xffffu), (float)(short)(w.y >> 16));
-            } else {
-                v = make_float4((float)__ldg(row + up_idx(col0, P.cw2)), (float)__ldg(row + up_idx(col0 + 1, P.cw2)),
-                                (float)__ldg(row + up_idx(col0 + 2, P.cw2)), (float)__ldg(row + up_idx(col0 + 3, P.cw2)));
-            }
-            *(float4 *)(sC2f + (c * BL_R2H + r) * B2_G2P + 4 * k) = v;
-        }
-    }
+    // ---- pass 1: level 1
+    stage_c2(sC2f, P, f, tx0, ty0, t);
     const bool single = (views_all & (views_all - 1)) == 0;  // at most one view: its staged G1 region survives into pass 2
     for (unsigned views = views_all; views;) {
         const int vi = __ffs(views) - 1;
         views &= views - 1;
         const BlendView &V = P.v[vi];
         __syncthreads();
-        stage_view(V, true);
+        stage_g1(sG1f, V, f, tx0, ty0, t);
+        stage_g2(sG2f, V, f, tx0, ty0, t);
         __syncthreads();
         const int w1 = V.bw >> 1, h1 = V.bh >> 1;
         const int v1x0 = (tx0 >> 1) - 1 - (V.x_tl >> 1), v1y0 = (ty0 >> 1) - 1 - (V.y_tl >> 1);
@@ -918,38 +1084,39 @@ __global__ void __launch_bounds__(BL_THREADS, VSB_BL_MINB) k_blend(const __grid_
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int x = x0 + (q & 1), y = y0 + (q >> 1);
-                wq[q] = interior ? 1.f : (((unsigned)x < (unsigned)w1 && (unsigned)y < (unsigned)h1) ? __ldg(V.w1 + (size_t)y * w1 + x) : 0.f);
+                wq[q] = ((unsigned)x < (unsigned)w1 && (unsigned)y < (unsigned)h1) ? __ldg(V.w1 + (size_t)y * w1 + x) : 0.f;
                 any |= wq[q] != 0.f;
             }
             if (!any) continue;
             float up[4];
-            up_quad_odd_f(sG2f + (c * BL_R2H + 1 + (qr1 >> 1)) * B2_G2P + B2_G2OFF + 1 + (qc1 >> 1), B2_G2P, up);
+            up_quad_odd_f(sG2f + (c * BL_R2H + 1 + (qr1 >> 1)) * B2_G2P + B2_G2OFF + 1 + (qc1 >> 1), B2_G2P, B2_CB_U8, up);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float g = sG1f[(c * BL_R1H + qr1 + (q >> 1)) * B2_G1P + B2_G1OFF + qc1 + (q & 1)];
-                const float lap = __fsub_rn(__fadd_rn(g, B2_MAGIC), up[q]);  // G1 - pyrUp(G2), exact
+                const float lap = __fsub_rn(__fadd_rn(g, B2_CB_U8), up[q]);  // G1 - pyrUp(G2), exact
                 acc1[k][q] += rz_s16(__fmul_rn(lap, wq[q]));
             }
         }
     }
     if (views_all == 0) __syncthreads();  // sC2f complete (the loop above did not run)
-    // D1 = normalised level 1 + pyrUp(C2), saturating, as fp32 into sD1f (in-canvas samples only)
+    // D1 = normalised level 1 + pyrUp(C2) as plain fp32 into sD1f (in-canvas samples; the ring is fixed up below)
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         if (it_c[k] < 0) continue;
         const int qr1 = it_qr[k], qc1 = it_qc[k], c = it_c[k];
         const int x0 = (tx0 >> 1) - 1 + qc1, y0 = (ty0 >> 1) - 1 + qr1;  // canvas level-1 coordinates, both odd
         float up[4];
-        up_quad_odd_f(sC2f + (c * BL_R2H + 1 + (qr1 >> 1)) * B2_G2P + B2_G2OFF + 1 + (qc1 >> 1), B2_G2P, up);
+        up_quad_odd_f(sC2f + (c * BL_R2H + 1 + (qr1 >> 1)) * B2_G2P + B2_G2OFF + 1 + (qc1 >> 1), B2_G2P, B2_CB_0, up);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int x = x0 + (q & 1), y = y0 + (q >> 1);
             if ((unsigned)x >= (unsigned)P.cw1 || (unsigned)y >= (unsigned)P.ch1) continue;
-            const float dw = interior ? 1.f : __ldg(P.dw1 + (size_t)y * P.cw1 + x);
-            const int d = max(B2_MAGIC_BITS - 32768, min(B2_MAGIC_BITS + 32767, normalize_s16(acc1[k][q], dw) + __float_as_int(up[q])));  // biased, see pass 2
+            const float dw = __ldg(P.dw1 + (size_t)y * P.cw1 + x);
+            const int d = normalize_s16(acc1[k][q], dw) + __float_as_int(up[q]);  // biased by 0x4B400000
             sD1f[(c * BL_R1H + qr1 + (q >> 1)) * B2_G1P + B2_G1OFF + qc1 + (q & 1)] = __fsub_rn(__int_as_float(d), B2_MAGIC);
         }
     }
+    fix_d1_ring(sD1f, P, tx0, ty0, t);
 
     // ---- pass 2: level 0
     int acc0[3][8];
@@ -961,28 +1128,26 @@ __global__ void __launch_bounds__(BL_THREADS, VSB_BL_MINB) k_blend(const __grid_
         const BlendView &V = P.v[vi];
         if (!single) {
             __syncthreads();
-            stage_view(V, false);
+            stage_g1(sG1f, V, f, tx0, ty0, t);
             __syncthreads();
         }
         const int w0 = V.bw, h0 = V.bh;
         const int qx0 = px0 - V.x_tl, qy = py - V.y_tl;
         if ((unsigned)qx0 >= (unsigned)w0 || (unsigned)qy >= (unsigned)h0) continue;
-        uint2 mm = make_uint2(0xffffffffu, 0xffffffffu);
-        if (!interior) {
-            mm = __ldg((const uint2 *)(V.m0 + (size_t)qy * w0 + qx0));
-            if ((mm.x | mm.y) == 0u) continue;  // (short)(L * 0) == 0
-        }
+        const uint2 mm = __ldg((const uint2 *)(V.m0 + (size_t)qy * w0 + qx0));
+        if ((mm.x | mm.y) == 0u) continue;  // (short)(L * 0) == 0
         uint2 gg[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) gg[c] = __ldg((const uint2 *)(V.g0 + (size_t)f * V.g0_fs + ((size_t)c * h0 + qy) * w0 + qx0));
         float wv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) wv[i] = __fmul_rn((float)(1. / 255.), (float)(((i < 4 ? mm.x : mm.y) >> (8 * (i & 3))) & 0xffu));
+        for (int i = 0; i < 8; ++i)  // W0 = (1/255) * mask byte (the product of init_gpu); byte -> fp32 through the 2^23 bias, no conversion unit
+            wv[i] = __fmul_rn((float)(1. / 255.), __fsub_rn(__uint_as_float(__byte_perm(i < 4 ? mm.x : mm.y, 0x4B000000u, 0x7540u | (unsigned)(i & 3))), 8388608.f));
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float up[8];
             const float *rp = sG1f + c * (BL_R1H * B2_G1P) + reg_off;
-            if (row_odd) up_row8_f<true>(rp, up); else up_row8_f<false>(rp, up);
+            if (row_odd) up_row8_f<true>(rp, B2_CB_U8, up); else up_row8_f<false>(rp, B2_CB_U8, up);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float gb = __uint_as_float(__byte_perm(i < 4 ? gg[c].x : gg[c].y, (unsigned)B2_MAGIC_BITS, 0x7650u | (unsigned)(i & 3)));  // G0 + 1.5 * 2^23
@@ -990,88 +1155,33 @@ __global__ void __launch_bounds__(BL_THREADS, VSB_BL_MINB) k_blend(const __grid_
             }
         }
     }
-    __syncthreads();  // sD1f complete; every reader of the staging area is done (the output tile re-uses it)
-    int16_t *sOut = (int16_t *)sStage;
+    __syncthreads();  // sD1f complete (ring included); every reader of the staging area is done (the output tile re-uses it)
+    unsigned o[3][8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[c][i] = 0u;
     if (px0 < P.cw0 && py < P.ch0) {
-        const int ix0 = px0 >> 1, iy = py >> 1;
-        const bool interior = ix0 >= 1 && ix0 + 4 < P.cw1 && iy >= 1 && iy + 1 < P.ch1;
+        const float4 da = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0)), db = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0 + 4));
+        const float dw[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
         // Outputs keep the 1.5 * 2^23 bias of the pyrUp result (bits 0x4B400000 + value): its low 16 bits are zero, so the
-        // CV_16SC3 sample is simply the low half-word.  Saturation bounds are shifted by the same constant.
-        constexpr int LO = U8 ? B2_MAGIC_BITS : B2_MAGIC_BITS - 32768, HI = U8 ? B2_MAGIC_BITS + 255 : B2_MAGIC_BITS + 32767;
+        // CV_16SC3 sample is simply the low half-word.  CV_8UC3: saturation bounds shifted by the same constant.
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float up[8];
-            if (interior) {
-                const float *rp = sD1f + c * (BL_R1H * B2_G1P) + reg_off;
-                if (row_odd) up_row8_f<true>(rp, up); else up_row8_f<false>(rp, up);
-            } else {
-                up_row8_f_edge(sD1f + c * (BL_R1H * B2_G1P), (tx0 >> 1) - 1, (ty0 >> 1) - 1, px0, py, P.cw1, P.ch1, up);
-            }
-            if (dw_all_one) {  // one view with full weight (most of the panorama): acc / 1.00001f truncates to acc - sign(acc)
+            const float *rp = sD1f + c * (BL_R1H * B2_G1P) + reg_off;
+            if (row_odd) up_row8_f<true>(rp, B2_CB_0, up); else up_row8_f<false>(rp, B2_CB_0, up);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int a = acc0[c][i];
-                    acc0[c][i] = max(LO, min(HI, a - max(-1, min(1, a)) + __float_as_int(up[i])));
-                }
-            } else {
-                const float4 da = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0)), db = __ldg((const float4 *)(P.dw0 + (size_t)py * P.cw0 + px0 + 4));
-                const float dw[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int d = max(LO, min(HI, normalize_s16(acc0[c][i], dw[i]) + __float_as_int(up[i])));
-                    acc0[c][i] = dw[i] > 1e-5f ? d : 0;  // dst_mask = dst_band_weights_[0] > WEIGHT_EPS
-                }
-            }
-        }
-        // 8 pixels x 3 channels, element e = 3 * i + c: 48 contiguous bytes of CV_16SC3 or 24 of CV_8UC3
-        if (U8) {
-            uint2 *o2 = (uint2 *)((uint8_t *)sStage + ly * (BL_TW * 3) + lx * 3);
-#pragma unroll
-            for (int v2 = 0; v2 < 3; ++v2) {
-                unsigned w[2];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int e = 8 * v2 + 4 * k;
-                    const unsigned lo = __byte_perm((unsigned)acc0[e % 3][e / 3], (unsigned)acc0[(e + 1) % 3][(e + 1) / 3], 0x0040u);
-                    const unsigned hi = __byte_perm((unsigned)acc0[(e + 2) % 3][(e + 2) / 3], (unsigned)acc0[(e + 3) % 3][(e + 3) / 3], 0x0040u);
-                    w[k] = __byte_perm(lo, hi, 0x5410u);
-                }
-                o2[v2] = make_uint2(w[0], w[1]);
-            }
-        } else {
-            uint4 *o4 = (uint4 *)(sOut + ly * (BL_TW * 3) + lx * 3);
-#pragma unroll
-            for (int v4 = 0; v4 < 3; ++v4) {
-                unsigned w[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int e0 = 8 * v4 + 2 * k, e1 = e0 + 1;
-                    w[k] = __byte_perm((unsigned)acc0[e0 % 3][e0 / 3], (unsigned)acc0[e1 % 3][e1 / 3], 0x5410u);
-                }
-                o4[v4] = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int i = 0; i < 8; ++i) {
+                int d = normalize_s16(acc0[c][i], dw[i]) + __float_as_int(up[i]);
+                if (U8) d = max(B2_MAGIC_BITS, min(B2_MAGIC_BITS + 255, d));
+                o[c][i] = dw[i] > 1e-5f ? (unsigned)d : 0u;  // dst_mask = dst_band_weights_[0] > WEIGHT_EPS
             }
         }
     }
+    put_out8<U8>(sStage, ly, lx, o);
     __syncthreads();
-    // ---- cropped, interleaved store: 16-byte vectors where the caller's buffer allows
-    constexpr int PXB = U8 ? 3 : 6;  // bytes per output pixel
-    const int n_px = min(BL_TW, P.out_w - tx0), n_rows = min(BL_TH, P.out_h - ty0);
-    if (n_px <= 0 || n_rows <= 0) return;
-    char *obase = (char *)outs.out[f] + (size_t)tx0 * PXB;
-    const bool vec_ok = ((((size_t)obase) | out_pitch) & 15) == 0;
-    const int row_bytes = n_px * PXB;
-    for (int r = t >> 5; r < n_rows; r += BL_THREADS / 32) {  // one warp per row: 16-byte chunks
-        const int ck = t & 31, b0 = ck * 16;
-        if (ck >= BL_TW * PXB / 16 || b0 >= row_bytes) continue;
-        char *o = obase + (size_t)(ty0 + r) * out_pitch + b0;
-        const char *sp = (const char *)sStage + r * (BL_TW * PXB) + b0;
-        if (vec_ok && b0 + 16 <= row_bytes) {
-            *(uint4 *)o = *(const uint4 *)sp;
-        } else {
-            const int n = min(16, row_bytes - b0);
-            for (int e = 0; e < n; ++e) o[e] = sp[e];
-        }
-    }
+    store_tile<U8>(sStage, P, outs.out[f], out_pitch, tx0, ty0, t);
 }
 
 }  // namespace vsb

@@ -280,6 +280,18 @@ __device__ __forceinline__ TapEntry make_tap_entry(float x, float y, int sw, int
     return e;
 }
 
+// Table weights are stored pre-multiplied by 2^126 (TAP_WSCALE) and the taps enter the chain as DENORMALS: PRMT puts the byte
+// into the low mantissa bits of a zero word, i.e. the float b * 2^-149 -- no bias to remove.  Every product and partial sum of
+// the chain is then the reference's value times 2^-23 exactly (scaling by a power of two commutes with rounding as long as
+// nothing leaves the normal range: the builders route entries with a non-zero weight below TAP_WMIN to the coordinate path),
+// and ONE fused multiply-add (v * 2^23 + 1.5 * 2^23) undoes the scale and rounds half-to-even.  12 FADDs fewer per pixel.
+constexpr float TAP_WSCALE = 8.507059173023462e37f;   // 2^126
+constexpr float TAP_WMIN = 8.077935669463161e-28f;    // 2^-90: products stay normal (255 * w * 2^-23 >= 2^-113)
+__device__ __forceinline__ float u8_den(unsigned packed, int byte)
+{
+    return __uint_as_float(__byte_perm(packed, 0u, 0x4440u | (unsigned)byte));
+}
+
 // One pixel from a table entry: `base` is 4-byte aligned, `pitch` a multiple of 4 (both rows share the byte shift).
 template <bool GAIN>
 __device__ __forceinline__ unsigned remap_tab_px(const uint8_t *__restrict__ base, unsigned pitch, unsigned off, float wa, float wb, float wc, float wd, float gain)
@@ -295,11 +307,11 @@ __device__ __forceinline__ unsigned remap_tab_px(const uint8_t *__restrict__ bas
     float o[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {  // left pixel = bytes 0..2 of lo, right pixel = byte 3 of lo, bytes 0..1 of hi
-        float v = __fmul_rn(u8_to_f32(lo1, c), wa);
-        v = __fmaf_rn(c == 0 ? u8_to_f32(lo1, 3) : u8_to_f32(hi1, c - 1), wb, v);
-        v = __fmaf_rn(u8_to_f32(lo2, c), wc, v);
-        v = __fmaf_rn(c == 0 ? u8_to_f32(lo2, 3) : u8_to_f32(hi2, c - 1), wd, v);
-        v = rni_biased(v);
+        float v = __fmul_rn(u8_den(lo1, c), wa);
+        v = __fmaf_rn(c == 0 ? u8_den(lo1, 3) : u8_den(hi1, c - 1), wb, v);
+        v = __fmaf_rn(u8_den(lo2, c), wc, v);
+        v = __fmaf_rn(c == 0 ? u8_den(lo2, 3) : u8_den(hi2, c - 1), wd, v);
+        v = __fmaf_rn(v, 8388608.f, 12582912.f);   // undo the 2^-23 scale and round: sat_u8(rni(.)) as an integer in the low mantissa bits
         o[c] = GAIN ? rni_biased(fminf(__fmul_rn(gain, __fsub_rn(v, 12582912.f)), 255.f)) : v;
     }
     return __byte_perm(__byte_perm(__float_as_uint(o[0]), __float_as_uint(o[1]), 0x0040u), __float_as_uint(o[2]), 0x0410u) & 0xffffffu;

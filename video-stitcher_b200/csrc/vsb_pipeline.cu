@@ -16,6 +16,9 @@
 //
 // HBM layout: all per-view intermediates are PLANAR u8 (one plane per colour channel) with the bordered
 // width (a multiple of 2^nb) as row length, so rows of every level start word aligned.
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is loaded with dlopen when the view-sharded mode is initialised (single-GPU use needs no NCCL)
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -31,6 +34,8 @@
 namespace vsb {
 
 // ============================================================================================ device side
+
+constexpr int MAX_SPLIT = 4;  // sub-batches of one submission's back half (internal streams)
 
 struct TileMap {
     int n;
@@ -169,6 +174,12 @@ struct TapTable {
     int tab_pitch;
 };
 
+// a non-zero weight so small that the 2^126-scaled, denormal-tap chain of remap_tab_px could round differently from the reference
+__device__ __forceinline__ bool tap_weight_tiny(const TapEntry &e)
+{
+    return (e.wa != 0.f && e.wa < TAP_WMIN) || (e.wb != 0.f && e.wb < TAP_WMIN) || (e.wc != 0.f && e.wc < TAP_WMIN) || (e.wd != 0.f && e.wd < TAP_WMIN);
+}
+
 // One thread per table entry of remap #1.  Entries whose 32-bit window loads would leave the caller's image buffer
 // (last bytes of the last row) are marked TAP_SLOW and take the coordinate-driven edge routine in the frame kernel.
 __global__ void k_build_taps1(const float *__restrict__ xmap, const float *__restrict__ ymap, size_t map_pitch, int w, int h,
@@ -185,15 +196,18 @@ __global__ void k_build_taps1(const float *__restrict__ xmap, const float *__res
         const unsigned p2 = (unsigned)e.off + pitch;                       // second row of the window
         const unsigned end = (p2 & ~3u) + ((p2 & 3u) == 3u ? 12u : 8u);    // one past the last byte the word loads touch
         if (end > (unsigned)(sh - 1) * pitch + (unsigned)sw * 3u) e.off = TAP_SLOW;
+        if (tap_weight_tiny(e)) e.off = TAP_SLOW;                          // the scaled chain could leave the normal range
     }
     const size_t i = (size_t)y * tab_pitch + x;
-    off[i] = e.off; wgt[i] = e.wa; wgt[plane + i] = e.wb; wgt[2 * plane + i] = e.wc; wgt[3 * plane + i] = e.wd;
+    off[i] = e.off;
+    wgt[i] = __fmul_rn(e.wa, TAP_WSCALE); wgt[plane + i] = __fmul_rn(e.wb, TAP_WSCALE);
+    wgt[2 * plane + i] = __fmul_rn(e.wc, TAP_WSCALE); wgt[3 * plane + i] = __fmul_rn(e.wd, TAP_WSCALE);
 }
 
 // One thread per BORDERED pixel of remap #2: the REFLECT border is resolved here, the taps address the zero-framed P.
 __global__ void k_build_taps2(const float *__restrict__ xmesh, const float *__restrict__ ymesh, size_t map_pitch, int w, int h,
                               int bw, int bh, int top, int left, unsigned p_pitch, unsigned origin,
-                              int *__restrict__ off, float *__restrict__ wgt, size_t plane, int tab_pitch)
+                              int *__restrict__ off, float *__restrict__ wgt, size_t plane, int tab_pitch, int *unsafe)
 {
     const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
     if (bx >= tab_pitch || by >= bh) return;
@@ -204,9 +218,12 @@ __global__ void k_build_taps2(const float *__restrict__ xmesh, const float *__re
         const float fx = *((const float *)((const char *)xmesh + (size_t)y * map_pitch) + x);
         const float fy = *((const float *)((const char *)ymesh + (size_t)y * map_pitch) + x);
         e = make_tap_entry(fx, fy, w, h, p_pitch, origin, true);
+        if (tap_weight_tiny(e)) atomicOr(unsafe, 1);  // (never seen: needs a map coordinate within 2^-90 of an integer) -> coordinate kernel
     }
     const size_t i = (size_t)by * tab_pitch + bx;
-    off[i] = e.off; wgt[i] = e.wa; wgt[plane + i] = e.wb; wgt[2 * plane + i] = e.wc; wgt[3 * plane + i] = e.wd;
+    off[i] = e.off;
+    wgt[i] = __fmul_rn(e.wa, TAP_WSCALE); wgt[plane + i] = __fmul_rn(e.wb, TAP_WSCALE);
+    wgt[2 * plane + i] = __fmul_rn(e.wc, TAP_WSCALE); wgt[3 * plane + i] = __fmul_rn(e.wd, TAP_WSCALE);
 }
 
 struct Stage1TabView {
@@ -237,6 +254,9 @@ struct Stage1TabParams {
 #endif
 #ifndef VSB_RM_UNROLL
 #define VSB_RM_UNROLL 1
+#endif
+#ifndef VSB_K1_PREFETCH
+#define VSB_K1_PREFETCH 0  // 1: prefetch.global.L2 of the next frame's tap windows, 2: prefetch.global.L1
 #endif
 constexpr int RM_UNROLL = VSB_RM_UNROLL;  // frames of the per-tile loop in flight per thread
 template <bool LANES>
@@ -282,6 +302,24 @@ __global__ void __launch_bounds__(RM_BX *RM_BY, VSB_RM1_MINB) k_remap_stage1_tab
 #pragma unroll RM_UNROLL
     for (int f = p.f0; f < p.f0 + p.n_frames; ++f, dst += V.p_frame_stride) {
         const uint8_t *src = p.src[f * p.n_views + vi - p.v0];
+#if VSB_K1_PREFETCH
+        // the next frame's windows are known now (same table entries, next source buffer): pull their lines towards the SM while
+        // this frame is computed -- no registers held, the demand loads of the next iteration hit L2 / L1 instead of HBM
+        if (f + 1 < p.f0 + p.n_frames) {
+            const uint8_t *nsrc = p.src[(f + 1) * p.n_views + vi - p.v0];
+#pragma unroll
+            for (int k = 0; k < RM_PX; ++k) {
+                const uint8_t *a = nsrc + ((unsigned)off[k] & 0x7ffffffcu);
+#if VSB_K1_PREFETCH == 1
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a + p.src_pitch));
+#else
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a + p.src_pitch));
+#endif
+            }
+        }
+#endif
         unsigned px[RM_PX];
 #pragma unroll
         for (int k = 0; k < RM_PX; ++k) px[k] = remap_tab_px<true>(src, p.src_pitch, (unsigned)off[k] & 0x7fffffffu, wa[k], wb[k], wc[k], wd[k], V.gain);
@@ -505,11 +543,11 @@ struct ShardRect {
 // block = 32 x 8 threads: rows over threadIdx.y, 32-bit words (rectangles are widened to word boundaries at plan time whenever
 // the plane rows are word aligned) or bytes over threadIdx.x
 template <bool PACK>
-__global__ void __launch_bounds__(256) k_shard_copy(const ShardRect *__restrict__ tab, uint8_t *__restrict__ buf, size_t frame_bytes)
+__global__ void __launch_bounds__(256) k_shard_copy(const ShardRect *__restrict__ tab, uint8_t *__restrict__ buf, size_t frame_bytes, int f0)
 {
     const ShardRect R = tab[blockIdx.x];
-    const int c = blockIdx.y, f = blockIdx.z;
-    uint8_t *pl = R.plane + (size_t)f * R.frame_stride + ((size_t)c * R.ph + R.y0) * R.pw + R.x0;
+    const int c = blockIdx.y, f = blockIdx.z;  // f counts frames of the submission (packed buffer); the planes start at frame slot f0
+    uint8_t *pl = R.plane + (size_t)(f0 + f) * R.frame_stride + ((size_t)c * R.ph + R.y0) * R.pw + R.x0;
     uint8_t *pk = buf + (size_t)f * frame_bytes + R.off + (size_t)c * R.w * R.h;
     const bool words = ((R.pw | R.x0 | R.w) & 3) == 0;
     for (int r = threadIdx.y; r < R.h; r += 8) {
@@ -793,6 +831,7 @@ struct View {
     // tap tables (see TapTable): remap #1, valid for caller row pitch t1_src_pitch; remap #2, one per mesh buffer
     int *t1_off = nullptr; float *t1_w = nullptr; size_t t1_plane = 0; int t1_pitch = 0; size_t t1_src_pitch = 0;
     int *t2_off[2] = {nullptr, nullptr}; float *t2_w[2] = {nullptr, nullptr}; size_t t2_plane = 0; int t2_pitch = 0;
+    bool t2_unsafe[2] = {false, false};  // the table of that mesh buffer holds a weight the scaled tap chain cannot take: coordinate kernel
     uint8_t *G0 = nullptr;
     size_t g0_frame_stride = 0;
     CUtensorMap g0_map;                 // TMA descriptor of G0 for k_down2 (valid when g0_map_ok)
@@ -830,6 +869,8 @@ struct vsb_stitcher {
     vsb::CoarseGeo cgeo;
     size_t coarse_smem = 0;
     uint32_t *d_blend_views = nullptr, *d_coarse_views = nullptr, *d_down2_tiles = nullptr;
+    uint32_t *d_blend_lists = nullptr;   // interior tiles (tile_x | tile_y << 12 | view << 24), then the other tiles (k_blend_int / k_blend_seam)
+    int n_blend_int = 0, n_blend_seam = 0;
     int blend_tiles_x = 0, blend_tiles_y = 0, coarse_tiles_x = 0, coarse_tiles_y = 0, n_down2_tiles = 0;
     int16_t *C2 = nullptr;
     size_t c2_frame_stride = 0;
@@ -843,6 +884,16 @@ struct vsb_stitcher {
     vsb::ShardRect *d_send[vsb::MAXV] = {}, *d_recv[vsb::MAXV] = {};
     int n_send[vsb::MAXV] = {}, n_recv[vsb::MAXV] = {};
     size_t send_bytes[vsb::MAXV] = {}, recv_bytes[vsb::MAXV] = {};  // per frame
+    // native transport of the view-sharded mode (vsb_shard_init): NCCL communicator, per-peer exchange buffers (two sets:
+    // submissions alternate between two halves of the frame slots so that exchange k overlaps front half k + 1)
+    ncclComm_t comm = nullptr;
+    int owners[vsb::MAXV] = {};
+    uint8_t *x_send[2][vsb::MAXV] = {}, *x_recv[2][vsb::MAXV] = {};
+    int x_frames = 0;                     // frames per submission the buffers are sized for
+    cudaStream_t sh_front = nullptr, sh_comm = nullptr, sh_back = nullptr;
+    cudaEvent_t ev_call = nullptr, ev_packed[2] = {}, ev_recv[2] = {}, ev_back[2] = {};
+    bool ev_back_valid[2] = {false, false};
+    unsigned shard_seq = 0;
     bool tiles_dirty = true;
     cudaStream_t setup_stream = nullptr, mesh_stream = nullptr, io_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
     cudaEvent_t ev_in[vsb::MAX_BATCH] = {}, ev_done[vsb::MAX_BATCH] = {};
@@ -850,8 +901,8 @@ struct vsb_stitcher {
     bool last_compose_valid = false;
     std::mutex mu;  // guards mesh publication
     int f0 = 0;                         // first frame slot the launch helpers address (vsb_compose splits a batch over two streams)
-    cudaStream_t sub[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaStream_t sub[vsb::MAX_SPLIT] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[vsb::MAX_SPLIT] = {};
     int launches = 0, launches_last = 0;  // running count of the submission in flight / count of the last finished one
     // vsb_feed / vsb_blend bookkeeping (frame slot 0)
     // host-buffer path staging
@@ -1030,6 +1081,32 @@ static int raise_dynamic_smem(Kernel kernel, int device)
     return VSB_OK;
 }
 
+// The two k_blend launches run over static tile lists derived from the per-tile words (view bits, bit 30 = interior,
+// bit 31 = tile of another rank's strip in view-sharded mode): interior tiles carry their single view in the list entry.
+static int upload_blend_lists(vsb_stitcher *s, const std::vector<uint32_t> &words)
+{
+    std::vector<uint32_t> li, ls;
+    for (int ty = 0; ty < s->blend_tiles_y; ++ty)
+        for (int tx = 0; tx < s->blend_tiles_x; ++tx) {
+            const uint32_t w = words[(size_t)ty * s->blend_tiles_x + tx];
+            if (w & 0x80000000u) continue;
+            const uint32_t id = (uint32_t)tx | ((uint32_t)ty << 12);
+            if (w & 0x40000000u) {
+                int v = 0;
+                while (!(w >> v & 1)) ++v;
+                li.push_back(id | ((uint32_t)v << 24));
+            } else {
+                ls.push_back(id);
+            }
+        }
+    cudaFree(s->d_blend_lists); s->d_blend_lists = nullptr;
+    s->n_blend_int = (int)li.size(); s->n_blend_seam = (int)ls.size();
+    li.insert(li.end(), ls.begin(), ls.end());
+    CK(cudaMalloc(&s->d_blend_lists, std::max<size_t>(li.size(), 1) * 4));
+    if (!li.empty()) CK(cudaMemcpy(s->d_blend_lists, li.data(), li.size() * 4, cudaMemcpyHostToDevice));
+    return VSB_OK;
+}
+
 static int build_fast_plan(vsb_stitcher *s)
 {
     const int n = s->cfg.num_views, nb = s->nb, F = s->cfg.max_batch;
@@ -1166,6 +1243,7 @@ static int build_fast_plan(vsb_stitcher *s)
     for (int i = 0; i < MAXV; ++i) s->owned[i] = i < n;
     CK(cudaMemcpy(s->d_blend_views, bviews.data(), bviews.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->d_coarse_views, cviews.data(), cviews.size() * 4, cudaMemcpyHostToDevice));
+    { int r = upload_blend_lists(s, bviews); if (r != VSB_OK) return r; }
     if (!d2tiles.empty()) CK(cudaMemcpy(s->d_down2_tiles, d2tiles.data(), d2tiles.size() * 4, cudaMemcpyHostToDevice));
     s->c2_frame_stride = (size_t)3 * s->cw[2] * s->ch[2];
     CK(cudaMalloc(&s->C2, s->c2_frame_stride * sizeof(int16_t) * F));
@@ -1448,11 +1526,25 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
         OutPtrs o;
         std::memset(&o, 0, sizeof(o));
         for (int f = 0; f < n_frames; ++f) o.out[s->f0 + f] = d_outs[f];
-        const dim3 g(s->blend_tiles_x, s->blend_tiles_y, n_frames);
-        if (s->out_format == VSB_OUT_U8C3) k_blend<true><<<g, BL_THREADS, 0, st>>>(p, o, out_pitch);
-        else k_blend<false><<<g, BL_THREADS, 0, st>>>(p, o, out_pitch);
+        const bool u8 = s->out_format == VSB_OUT_U8C3;
+        // the seam tiles first (two to three views each: the long CTAs), the interior tiles fill in behind them
+        if (s->n_blend_seam > 0) {
+            p.tiles = s->d_blend_lists + s->n_blend_int;
+            const dim3 g(s->n_blend_seam, n_frames);
+            if (u8) k_blend_seam<true><<<g, BL_THREADS, 0, st>>>(p, o, out_pitch);
+            else k_blend_seam<false><<<g, BL_THREADS, 0, st>>>(p, o, out_pitch);
+        }
+        const double share = (double)s->n_blend_seam / std::max(1, s->n_blend_seam + s->n_blend_int);
         ++s->launches;
-        prof_stage(s, st, "blend", bytes * n_frames);  // G0 + G1 + G2 of every view once, C2 once, CV_16SC3 pano out once
+        prof_stage(s, st, "blend_seam", bytes * n_frames * share);
+        if (s->n_blend_int > 0) {
+            p.tiles = s->d_blend_lists;
+            const dim3 g(s->n_blend_int, n_frames);
+            if (u8) k_blend_int<true><<<g, BL_THREADS, 0, st>>>(p, o, out_pitch);
+            else k_blend_int<false><<<g, BL_THREADS, 0, st>>>(p, o, out_pitch);
+        }
+        ++s->launches;
+        prof_stage(s, st, "blend_int", bytes * n_frames * (1.0 - share));  // G0 + G1 + G2 of every view once, C2 once, CV_16SC3 pano out once (split by tile count)
     }
     return check_launch("k_coarse / k_blend");
 }
@@ -1522,14 +1614,16 @@ static int build_taps1(vsb_stitcher *s, int i, size_t src_pitch, cudaStream_t st
 }
 
 // remap stages + pyramid for views [v0, v1) of n_frames frames
+enum { FRONT_REMAP = 1, FRONT_PYRAMID = 2, FRONT_ALL = 3 };
 static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch, cudaStream_t st,
-                        const uint8_t *warped = nullptr)
+                        const uint8_t *warped = nullptr, int stages = FRONT_ALL)
 {
     const int n = v1 - v0;
     int ws[MAXV], hs[MAXV];
     int r = sync_tile_lists(s);
     if (r != VSB_OK) return r;
     const uint8_t *bgr_ptrs[MAX_BATCH * MAXV];
+    if (!(stages & FRONT_REMAP)) goto pyramid;
     if (!warped && s->in_format == VSB_IN_NV12) {
         r = launch_nv12(s, v0, v1, n_frames, d_srcs, src_pitch, st, bgr_ptrs);
         if (r != VSB_OK) return r;
@@ -1596,7 +1690,7 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
             if (i < v0) first += (int)V.s2_tiles.size();
             else if (i < v1) {
                 count += (int)V.s2_tiles.size(); bytes += 3.0 * V.roi_w * V.roi_h + 3.0 * V.bw * V.bh;
-                tab = tab && V.mesh_cur >= 0 && V.t2_off[V.mesh_cur] != nullptr;
+                tab = tab && V.mesh_cur >= 0 && V.t2_off[V.mesh_cur] != nullptr && !V.t2_unsafe[V.mesh_cur];
             }
         }
         if (tab) {
@@ -1632,6 +1726,8 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
         ++s->launches;
         prof_stage(s, st, "remap_stage2", bytes * n_frames);
     }
+pyramid:
+    if (!(stages & FRONT_PYRAMID)) return check_launch("front half (remap)");
     if (s->fast) {
         r = launch_down2(s, v0, v1, n_frames, st);
         return r != VSB_OK ? r : launch_down1(s, v0, v1, n_frames, st);
@@ -1703,6 +1799,53 @@ static int note_compose_done(vsb_stitcher *s, cudaStream_t st)
     return VSB_OK;
 }
 
+// ---- NCCL through dlopen (view-sharded mode) + view ownership -------------------------------------------------------
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(ncclResult_t);
+};
+const NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static int state = 0;  // 0 = not tried, 1 = ok, -1 = missing
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (state == 0) {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        state = -1;
+        if (h) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+            api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
+            api.Send = (decltype(api.Send))dlsym(h, "ncclSend");
+            api.Recv = (decltype(api.Recv))dlsym(h, "ncclRecv");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+            if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send && api.Recv && api.GetErrorString) state = 1;
+        }
+    }
+    return state == 1 ? &api : nullptr;
+}
+#define NC(expr) do { ncclResult_t _n = (expr); if (_n != ncclSuccess) return fail(VSB_ERR_CUDA, "%s: %s", #expr, nccl->GetErrorString(_n)); } while (0)
+
+// the rank whose canvas strip holds most of the view's level-0 seam weight (same rule on every rank: no exchange needed)
+int view_owner(const vsb_stitcher *s, int i, int world)
+{
+    const View &V = s->v[i];
+    std::vector<long long> per(world, 0);
+    for (int x = 0; x < V.bw; ++x) per[std::min((V.x_tl + x) / s->strip_w, world - 1)] += V.w0_cols[x];
+    int best = 0;
+    for (int r = 1; r < world; ++r) if (per[r] > per[best]) best = r;
+    return best;
+}
 }  // namespace vsb
 
 using namespace vsb;
@@ -1744,15 +1887,20 @@ int vsb_destroy(vsb_stitcher *s)
     for (int k = 0; k < MAXL; ++k) cudaFree(s->dw[k]);
     cudaFree(s->d_plan);
     cudaFree(s->d_blend_views); cudaFree(s->d_coarse_views); cudaFree(s->d_down2_tiles); cudaFree(s->C2);
-    cudaFree(s->d_coarse_desc); cudaFree(s->d_s1_tiles); cudaFree(s->d_s2_tiles);
+    cudaFree(s->d_coarse_desc); cudaFree(s->d_s1_tiles); cudaFree(s->d_s2_tiles); cudaFree(s->d_blend_lists);
     for (int i = 0; i < MAXV; ++i) { cudaFree(s->d_send[i]); cudaFree(s->d_recv[i]); }
     cudaFree(s->stage_src); cudaFree(s->stage_out); cudaFree(s->nv_bgr); cudaFree(s->stage_nv12); cudaFree(s->cons_tab);
+    for (int b = 0; b < 2; ++b)
+        for (int p = 0; p < MAXV; ++p) { cudaFree(s->x_send[b][p]); cudaFree(s->x_recv[b][p]); }
+    if (s->comm) { const NcclApi *api = nccl_api(); if (api) api->CommDestroy(s->comm); }
+    if (s->sh_front) { cudaStreamDestroy(s->sh_front); cudaStreamDestroy(s->sh_comm); cudaStreamDestroy(s->sh_back); cudaEventDestroy(s->ev_call); }
+    for (int b = 0; b < 2; ++b) { if (s->ev_packed[b]) cudaEventDestroy(s->ev_packed[b]); if (s->ev_recv[b]) cudaEventDestroy(s->ev_recv[b]); if (s->ev_back[b]) cudaEventDestroy(s->ev_back[b]); }
     if (s->setup_stream) cudaStreamDestroy(s->setup_stream);
     if (s->mesh_stream) cudaStreamDestroy(s->mesh_stream);
     if (s->io_stream) cudaStreamDestroy(s->io_stream);
     if (s->in_stream) cudaStreamDestroy(s->in_stream);
     if (s->out_stream) cudaStreamDestroy(s->out_stream);
-    for (int h = 0; h < 2; ++h) { if (s->sub[h]) cudaStreamDestroy(s->sub[h]); if (s->ev_join[h]) cudaEventDestroy(s->ev_join[h]); }
+    for (int h = 0; h < MAX_SPLIT; ++h) { if (s->sub[h]) cudaStreamDestroy(s->sub[h]); if (s->ev_join[h]) cudaEventDestroy(s->ev_join[h]); }
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     for (int f = 0; f < MAX_BATCH; ++f) { if (s->ev_in[f]) cudaEventDestroy(s->ev_in[f]); if (s->ev_done[f]) cudaEventDestroy(s->ev_done[f]); }
     if (s->last_compose) cudaEventDestroy(s->last_compose);
@@ -1977,13 +2125,15 @@ int vsb_set_mesh(vsb_stitcher *s, int i, const float *mesh_x, const float *mesh_
         if (s->last_compose_valid) CK(cudaStreamWaitEvent(st, s->last_compose, 0));
     }
     const size_t half = (size_t)hw * hh;
-    if (!V.mesh_scratch) CK(cudaMalloc(&V.mesh_scratch, sizeof(float) * (3 * half + 2 * 4096)));
+    if (!V.mesh_scratch) CK(cudaMalloc(&V.mesh_scratch, sizeof(float) * (3 * half + 2 * 4096 + 1)));
     for (int c = 0; c < 2; ++c)
         if (!V.mesh[target][c]) CK(cudaMalloc(&V.mesh[target][c], V.map_pitch * H));
     float *sum_x = V.mesh_scratch, *sum_y = sum_x + half, *cnt = sum_y + half, *d_mx = cnt + half, *d_my = d_mx + 4096;
+    int *d_unsafe = (int *)(d_my + 4096);
     CK(cudaMemcpyAsync(d_mx, mesh_x, sizeof(float) * rows * cols, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_my, mesh_y, sizeof(float) * rows * cols, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(sum_x, 0, sizeof(float) * 3 * half, st));
+    CK(cudaMemsetAsync(d_unsafe, 0, sizeof(int), st));
     const dim3 b(32, 8);
     k_mesh_splat<<<grid2d(W, H, b), b, 0, st>>>(d_mx, d_my, rows, cols, W, H, sum_x, sum_y, cnt);
     k_mesh_divide<<<(unsigned)((half + 255) / 256), 256, 0, st>>>(sum_x, sum_y, cnt, (int)half);
@@ -1996,14 +2146,17 @@ int vsb_set_mesh(vsb_stitcher *s, int i, const float *mesh_x, const float *mesh_
             CK(cudaMalloc(&V.t2_w[target], V.t2_plane * 4 * sizeof(float)));
         }
         k_build_taps2<<<grid2d(V.t2_pitch, V.bh, b), b, 0, st>>>(V.mesh[target][0], V.mesh[target][1], V.map_pitch, W, H, V.bw, V.bh, V.top, V.left,
-                                                                 (unsigned)V.p_pitch, V.p_origin, V.t2_off[target], V.t2_w[target], V.t2_plane, V.t2_pitch);
+                                                                 (unsigned)V.p_pitch, V.p_origin, V.t2_off[target], V.t2_w[target], V.t2_plane, V.t2_pitch, d_unsafe);
     }
     int r = check_launch("set_mesh kernels");
     if (r != VSB_OK) return r;
+    int h_unsafe = 0;
+    CK(cudaMemcpyAsync(&h_unsafe, d_unsafe, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(V.mesh_ready, st));
     CK(cudaStreamSynchronize(st));  // host mesh arrays may be reused by the caller after return (pageable H2D)
     {
         std::lock_guard<std::mutex> lk(s->mu);
+        V.t2_unsafe[target] = h_unsafe != 0;
         V.mesh_pending = target;
     }
     return VSB_OK;
@@ -2149,34 +2302,31 @@ int vsb_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, siz
     s->launches = 0;
     r = adopt_meshes(s, st);
     if (r != VSB_OK) return r;
-    static const bool no_split = std::getenv("VSB_NO_SPLIT") != nullptr;
-    if (n_frames >= 4 && s->fast && !s->profiling && !no_split) {  // (with 2-3 frames the halves lose the per-tile table reuse: measured slower)
-        // Two half-batches on two internal streams: the short kernels (k_down_tail: 144 CTAs, k_coarse: ~1.2 waves) and the
-        // last partial wave of every kernel of one half overlap with the other half's work.  Frame slots are disjoint; the
-        // static tables are built on the caller's stream before the fork.
-        const int n = s->cfg.num_views;
+    // VSB_SPLIT = number of sub-batches of the back half (default 2; 1 = everything on the caller's stream)
+    static const int n_split = [] { const char *e = std::getenv("VSB_SPLIT"); return e ? std::max(1, std::min(MAX_SPLIT, std::atoi(e))) : (std::getenv("VSB_NO_SPLIT") ? 1 : 2); }();
+    if (n_frames >= 4 && s->fast && !s->profiling && n_split > 1) {
+        // The remap kernels run ONCE for the whole submission on the caller's stream (their tap tables -- 20 B per pixel -- are
+        // read once and stay in registers while all frames stream through).  From the pyramid on, the submission continues as
+        // sub-batches on internal streams: the short kernels (k_down_tail: 144 CTAs, k_coarse: ~1.2 waves) and the last partial
+        // wave of every kernel of one sub-batch overlap with the other's work.  Frame slots are disjoint.
+        const int n = s->cfg.num_views, ns = std::min(n_split, n_frames / 2);
         if (!s->sub[0]) {
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < MAX_SPLIT; ++h) {
                 CK(cudaStreamCreateWithFlags(&s->sub[h], cudaStreamNonBlocking));
                 CK(cudaEventCreateWithFlags(&s->ev_join[h], cudaEventDisableTiming));
             }
             CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
         }
-        r = sync_tile_lists(s);
+        s->f0 = 0;
+        r = launch_front(s, 0, n, n_frames, d_srcs, src_pitch, st, nullptr, FRONT_REMAP);
         if (r != VSB_OK) return r;
-        if (s->in_format == VSB_IN_BGR8 && remap_variant() >= 0 && src_pitch % 4 == 0)
-            for (int i = 0; i < n; ++i)
-                if (s->v[i].src_h >= 2 && (unsigned long long)src_pitch * s->v[i].src_h < 0x7fffffffull) { r = build_taps1(s, i, src_pitch, st); if (r != VSB_OK) return r; }
         CK(cudaEventRecord(s->ev_fork, st));
-        const int half[3] = {0, (n_frames + 1) / 2, n_frames};
-        for (int h = 0; h < 2 && r == VSB_OK; ++h) {
+        for (int h = 0; h < ns && r == VSB_OK; ++h) {
+            const int b0 = n_frames * h / ns, b1 = n_frames * (h + 1) / ns;
             CK(cudaStreamWaitEvent(s->sub[h], s->ev_fork, 0));
-            s->f0 = half[h];
-            const int nf = half[h + 1] - half[h];
-            if (h == 1 && s->in_format == VSB_IN_NV12) CK(cudaStreamWaitEvent(s->sub[1], s->ev_join[0], 0));  // first NV12 use sizes the staging and the tap tables in half 0
-            r = launch_front(s, 0, n, nf, d_srcs + (size_t)half[h] * n, src_pitch, s->sub[h]);
-            if (r == VSB_OK && h == 0 && s->in_format == VSB_IN_NV12) CK(cudaEventRecord(s->ev_join[0], s->sub[0]));
-            if (r == VSB_OK) r = launch_back(s, nf, d_outs + half[h], out_pitch, s->sub[h]);
+            s->f0 = b0;
+            r = launch_front(s, 0, n, b1 - b0, nullptr, src_pitch, s->sub[h], nullptr, FRONT_PYRAMID);
+            if (r == VSB_OK) r = launch_back(s, b1 - b0, d_outs + b0, out_pitch, s->sub[h]);
             if (r == VSB_OK) { CK(cudaEventRecord(s->ev_join[h], s->sub[h])); CK(cudaStreamWaitEvent(st, s->ev_join[h], 0)); }
         }
         s->f0 = 0;
@@ -2315,7 +2465,7 @@ int vsb_shard_set(vsb_stitcher *s, int rank, int world)
             if (!coarse_tile_of_rank(s, tx, rank)) c[(size_t)ty * s->coarse_tiles_x + tx] = 0x80000000u;
     CK(cudaMemcpy(s->d_blend_views, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->d_coarse_views, c.data(), c.size() * 4, cudaMemcpyHostToDevice));
-    return VSB_OK;
+    return upload_blend_lists(s, b);
 }
 
 int vsb_shard_info(const vsb_stitcher *s, int *strip_x0, int *strip_x1, unsigned *owned_mask)
@@ -2445,8 +2595,8 @@ static int shard_copy(vsb_stitcher *s, int peer, int n_frames, void *d_buf, void
     DeviceGuard g(s->device);
     const int n = pack ? s->n_send[peer] : s->n_recv[peer];
     if (n == 0) return VSB_OK;
-    if (pack) k_shard_copy<true><<<dim3(n, 3, n_frames), dim3(32, 8), 0, (cudaStream_t)stream>>>(s->d_send[peer], (uint8_t *)d_buf, s->send_bytes[peer]);
-    else k_shard_copy<false><<<dim3(n, 3, n_frames), dim3(32, 8), 0, (cudaStream_t)stream>>>(s->d_recv[peer], (uint8_t *)d_buf, s->recv_bytes[peer]);
+    if (pack) k_shard_copy<true><<<dim3(n, 3, n_frames), dim3(32, 8), 0, (cudaStream_t)stream>>>(s->d_send[peer], (uint8_t *)d_buf, s->send_bytes[peer], 0);
+    else k_shard_copy<false><<<dim3(n, 3, n_frames), dim3(32, 8), 0, (cudaStream_t)stream>>>(s->d_recv[peer], (uint8_t *)d_buf, s->recv_bytes[peer], 0);
     return check_launch("k_shard_copy");
 }
 int vsb_shard_pack(vsb_stitcher *s, int peer, int n_frames, void *d_buf, void *stream) { return shard_copy(s, peer, n_frames, d_buf, stream, true); }
@@ -2479,6 +2629,168 @@ int vsb_blend_batch(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, size_
     int r = launch_back(s, n_frames, d_outs, out_pitch, (cudaStream_t)stream);
     if (r != VSB_OK) return r;
     return note_compose_done(s, (cudaStream_t)stream);
+}
+
+// ---- view-sharded mode, native transport: the exchange lives in the library, so a C++ host needs nothing else ------
+// NCCL is reached through dlopen (nccl_api above): libvsb200 has no link-time dependency on it, and inside a process that
+// already loaded an NCCL (torch) the same library instance is used.
+
+int vsb_shard_unique_id(void *id128)
+{
+    REQ(id128, VSB_ERR_INVALID, "shard_unique_id: null argument");
+    const NcclApi *nccl = nccl_api();
+    REQ(nccl, VSB_ERR_STATE, "shard_unique_id: libnccl.so.2 not found (%s)", dlerror());
+    ncclUniqueId id;
+    NC(nccl->GetUniqueId(&id));
+    static_assert(sizeof(id) == VSB_SHARD_ID_BYTES, "ncclUniqueId size");
+    std::memcpy(id128, &id, sizeof(id));
+    return VSB_OK;
+}
+
+static void shard_free_transport(vsb_stitcher *s)
+{
+    for (int b = 0; b < 2; ++b)
+        for (int p = 0; p < MAXV; ++p) { cudaFree(s->x_send[b][p]); cudaFree(s->x_recv[b][p]); s->x_send[b][p] = s->x_recv[b][p] = nullptr; }
+    s->x_frames = 0;
+}
+
+int vsb_shard_init(vsb_stitcher *s, int rank, int world, const void *id128)
+{
+    REQ(s && id128, VSB_ERR_INVALID, "shard_init: null argument");
+    REQ(world >= 1 && world <= MAXV && rank >= 0 && rank < world, VSB_ERR_INVALID, "shard_init: bad rank / world (at most %d ranks)", MAXV);
+    const NcclApi *nccl = nccl_api();
+    REQ(nccl, VSB_ERR_STATE, "shard_init: libnccl.so.2 not found");
+    int r = vsb_shard_set(s, rank, world);
+    if (r != VSB_OK) return r;
+    DeviceGuard g(s->device);
+    for (int i = 0; i < s->cfg.num_views; ++i) s->owners[i] = view_owner(s, i, world);
+    r = vsb_shard_plan(s, s->owners);
+    if (r != VSB_OK) return r;
+    shard_free_transport(s);
+    if (!s->sh_front) {
+        CK(cudaStreamCreateWithFlags(&s->sh_front, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s->sh_comm, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s->sh_back, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s->ev_call, cudaEventDisableTiming));
+        for (int b = 0; b < 2; ++b) {
+            CK(cudaEventCreateWithFlags(&s->ev_packed[b], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s->ev_recv[b], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s->ev_back[b], cudaEventDisableTiming));
+        }
+    }
+    s->ev_back_valid[0] = s->ev_back_valid[1] = false;
+    s->shard_seq = 0;
+    if (s->comm) { nccl->CommDestroy(s->comm); s->comm = nullptr; }
+    if (world > 1) {
+        ncclUniqueId id;
+        std::memcpy(&id, id128, sizeof(id));
+        NC(nccl->CommInitRank(&s->comm, world, id, rank));
+    }
+    return VSB_OK;
+}
+
+// stitch_one (A/timed.cpp:123-152) for n_frames frames of ONE frame stream composed by `world` GPUs: this rank remaps / builds
+// the pyramids of its views, the ranks exchange the Gaussian sub-planes foreign strips read (one grouped ncclSend / ncclRecv
+// per peer, stream-ordered, no host wait), and this rank blends its canvas strip into d_outs (full-size buffers).
+// d_srcs[f * num_views + v]: only the entries of owned views are read.  Three internal streams (front / exchange / back) and
+// two alternating halves of the frame slots (when 2 * n_frames <= max_batch): submission k + 1's front half overlaps
+// submission k's exchange and back half.  Outputs are ordered on `stream`.
+int vsb_shard_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch, int16_t *const *d_outs, size_t out_pitch, void *stream)
+{
+    REQ(s && d_srcs && d_outs, VSB_ERR_INVALID, "shard_compose: null argument");
+    REQ(s->shard_rank >= 0 && s->sh_front, VSB_ERR_STATE, "shard_compose: vsb_shard_init first");
+    REQ(n_frames >= 1 && n_frames <= s->cfg.max_batch, VSB_ERR_INVALID, "shard_compose: n_frames must be 1..max_batch (%d)", s->cfg.max_batch);
+    REQ(out_pitch >= (size_t)s->roi_final[2] * (s->out_format == VSB_OUT_U8C3 ? 3 : 6), VSB_ERR_INVALID, "shard_compose: output pitch too small");
+    const NcclApi *nccl = nccl_api();
+    REQ(nccl || s->shard_world == 1, VSB_ERR_STATE, "shard_compose: libnccl.so.2 not found");
+    int r = ready_for_frames(s);
+    if (r != VSB_OK) return r;
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = s->cfg.num_views, me = s->shard_rank, world = s->shard_world, F = n_frames;
+    if (s->x_frames < F) {  // exchange buffers: per peer and direction, two sets
+        CK(cudaDeviceSynchronize());
+        shard_free_transport(s);
+        for (int b = 0; b < 2; ++b)
+            for (int p = 0; p < world; ++p) {
+                if (p == me) continue;
+                if (s->send_bytes[p]) CK(cudaMalloc(&s->x_send[b][p], s->send_bytes[p] * F));
+                if (s->recv_bytes[p]) CK(cudaMalloc(&s->x_recv[b][p], s->recv_bytes[p] * F));
+            }
+        s->x_frames = F;
+    }
+    const bool two = 2 * F <= s->cfg.max_batch;
+    const int b = two ? (int)(s->shard_seq & 1u) : 0;
+    const int f0 = b * F;
+    ++s->shard_seq;
+    s->launches = 0;
+    // ---- front half on sh_front: inputs ready when `stream` reaches this call; the slots are free once their previous back half is done
+    CK(cudaEventRecord(s->ev_call, st));
+    CK(cudaStreamWaitEvent(s->sh_front, s->ev_call, 0));
+    if (s->ev_back_valid[b]) CK(cudaStreamWaitEvent(s->sh_front, s->ev_back[b], 0));
+    r = adopt_meshes(s, s->sh_front);
+    if (r != VSB_OK) return r;
+    s->f0 = f0;
+    for (int v0 = 0; v0 < n && r == VSB_OK;) {
+        if (!s->owned[v0]) { ++v0; continue; }
+        int v1 = v0;
+        while (v1 < n && s->owned[v1]) ++v1;
+        const uint8_t *srcs[MAX_BATCH * MAXV];
+        for (int f = 0; f < F; ++f)
+            for (int v = v0; v < v1; ++v) {
+                srcs[f * (v1 - v0) + (v - v0)] = d_srcs[f * n + v];
+                if (!d_srcs[f * n + v]) { s->f0 = 0; return fail(VSB_ERR_INVALID, "shard_compose: frame %d of owned view %d is null", f, v); }
+            }
+        r = launch_front(s, v0, v1, F, srcs, src_pitch, s->sh_front);
+        v0 = v1;
+    }
+    for (int p = 0; p < world && r == VSB_OK; ++p)
+        if (p != me && s->n_send[p] > 0) {
+            k_shard_copy<true><<<dim3(s->n_send[p], 3, F), dim3(32, 8), 0, s->sh_front>>>(s->d_send[p], s->x_send[b][p], s->send_bytes[p], f0);
+            ++s->launches;
+        }
+    if (r == VSB_OK) r = check_launch("shard front half");
+    if (r != VSB_OK) { s->f0 = 0; return r; }
+    CK(cudaEventRecord(s->ev_packed[b], s->sh_front));
+    // ---- exchange on sh_comm: one grouped send / recv per peer, then scatter into the local copies of the foreign planes
+    CK(cudaStreamWaitEvent(s->sh_comm, s->ev_packed[b], 0));
+    if (s->ev_back_valid[b]) CK(cudaStreamWaitEvent(s->sh_comm, s->ev_back[b], 0));  // the planes the scatter overwrites were read by that back half
+    if (world > 1) {
+        NC(nccl->GroupStart());
+        for (int p = 0; p < world; ++p) {
+            if (p == me) continue;
+            if (s->send_bytes[p]) NC(nccl->Send(s->x_send[b][p], s->send_bytes[p] * F, ncclUint8, p, s->comm, s->sh_comm));
+            if (s->recv_bytes[p]) NC(nccl->Recv(s->x_recv[b][p], s->recv_bytes[p] * F, ncclUint8, p, s->comm, s->sh_comm));
+        }
+        NC(nccl->GroupEnd());
+        for (int p = 0; p < world; ++p)
+            if (p != me && s->n_recv[p] > 0) {
+                k_shard_copy<false><<<dim3(s->n_recv[p], 3, F), dim3(32, 8), 0, s->sh_comm>>>(s->d_recv[p], s->x_recv[b][p], s->recv_bytes[p], f0);
+                ++s->launches;
+            }
+        r = check_launch("shard exchange");
+        if (r != VSB_OK) { s->f0 = 0; return r; }
+    }
+    CK(cudaEventRecord(s->ev_recv[b], s->sh_comm));
+    // ---- back half on sh_back: this rank's canvas strip
+    CK(cudaStreamWaitEvent(s->sh_back, s->ev_recv[b], 0));
+    r = launch_back(s, F, d_outs, out_pitch, s->sh_back);
+    s->f0 = 0;
+    if (r != VSB_OK) return r;
+    CK(cudaEventRecord(s->ev_back[b], s->sh_back));
+    s->ev_back_valid[b] = true;
+    CK(cudaStreamWaitEvent(st, s->ev_back[b], 0));
+    return note_compose_done(s, st);
+}
+
+int vsb_shard_exchange_bytes(const vsb_stitcher *s, size_t *send_bytes_per_frame, size_t *recv_bytes_per_frame)
+{
+    REQ(s && s->shard_rank >= 0, VSB_ERR_STATE, "shard_exchange_bytes: vsb_shard_init first");
+    size_t a = 0, b = 0;
+    for (int p = 0; p < s->shard_world && p < MAXV; ++p) { a += s->send_bytes[p]; b += s->recv_bytes[p]; }
+    if (send_bytes_per_frame) *send_bytes_per_frame = a;
+    if (recv_bytes_per_frame) *recv_bytes_per_frame = b;
+    return VSB_OK;
 }
 
 int vsb_last_launch_count(const vsb_stitcher *s) { return s ? s->launches_last : 0; }
