@@ -130,6 +130,12 @@ int vsb_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, siz
  * returns after the outputs are in host memory. */
 int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs, size_t src_pitch_bytes,
                      int16_t *const *h_outs, size_t out_pitch_bytes);
+/* Asynchronous form: vsb_submit_host enqueues one submission (pinned host buffers must stay valid) and returns; up to two
+ * submissions are in flight, so the download of one overlaps the upload of the next; vsb_wait_host blocks until the OLDEST
+ * outstanding submission's panoramas are in host memory (the reference's result queue, A/timed.cpp:150,243, plays this role). */
+int vsb_submit_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs, size_t src_pitch_bytes,
+                    int16_t *const *h_outs, size_t out_pitch_bytes);
+int vsb_wait_host(vsb_stitcher *s);
 /* ---- wire format in, consumer format out (both default to the reference's stage boundary).
  *      VSB_IN_NV12: the source pointers of vsb_feed / vsb_compose / vsb_compose_host are NV12 frames as the capture
  *      boards send them (A/defs.h:10-17: h rows of Y then h/2 rows of interleaved U,V; `pitch` = row pitch of both) and

@@ -14,7 +14,9 @@ S = vsb200.synth
 og.set_num_threads(8)
 out = {}
 for name, kw in (("small4", dict(n_views=4, src_w=320, src_h=240, pano_width=1024, num_bands=3, enable_local=True)),
-                 ("cyl5", dict(n_views=5, src_w=256, src_h=192, pano_width=800, num_bands=4, enable_local=True, projection=1))):
+                 ("cyl5", dict(n_views=5, src_w=256, src_h=192, pano_width=800, num_bands=4, enable_local=True, projection=1)),
+                 # the rig bench.py composes view-sharded on N GPUs to verify parity inside the scaling run ("parity_checked")
+                 ("shard6", dict(n_views=6, src_w=480, src_h=270, pano_width=1536, num_bands=4, enable_local=True))):
     rig = op.OracleRig(gains=S.gains(kw["n_views"]), **kw)
     for i in range(kw["n_views"]):
         rig.set_mesh(i, *S.mesh(*rig.sizes[i]))

@@ -305,10 +305,12 @@ def test_batched_compose_and_mesh_swap(cuda, og):
     _eq(grig.compose([fr[2]])[0], orig.compose(fr[2])[0], "after double mesh swap")
 
 
-@pytest.mark.parametrize("variant,pad", [(-1, 0), (0, 0), (1, 0), (0, 1), (1, 4)])
+@pytest.mark.parametrize("variant,pad", [(-1, 0), (0, 0), (1, 0), (2, 0), (3, 0), (0, 1), (1, 4), (2, 4), (3, 4), (3, 16)])
 def test_remap_kernel_variants(cuda, og, tmp_path, variant, pad):
-    """Every form of the remap kernels (coordinate-driven, table-driven scalar / packed-pair / conversion-unit mixes) gives the
-    oracle's frames; pad = 1 makes the caller's rows unaligned (falls back to the coordinate-driven kernels)."""
+    """Every form of the remap kernels (coordinate-driven; table-driven with consecutive / lane-interleaved pixels, 4 or 2 per thread;
+    3 = shared-memory staged source footprints, the default) gives the oracle's frames; pad = 1 makes the caller's rows unaligned
+    (falls back to the coordinate-driven kernels), pad = 4 keeps them word but not 16-byte aligned (the staged form falls back to
+    the lane-interleaved one), pad = 16 gives 16-byte aligned rows longer than the image (staged, boxes may not run past the last row)."""
     import os
     import subprocess
     import sys

@@ -21,7 +21,7 @@ SYMBOLS = [
     "vsb_last_error", "vsb_version", "vsb_device_count", "vsb_create", "vsb_destroy", "vsb_warp_roi",
     "vsb_build_maps", "vsb_warp", "vsb_prepare", "vsb_get_roi", "vsb_init_view", "vsb_get_view_geometry", "vsb_set_maps",
     "vsb_set_gain", "vsb_set_mesh", "vsb_custom_resize", "vsb_feed", "vsb_feed_warped", "vsb_blend", "vsb_compose",
-    "vsb_compose_host", "vsb_last_launch_count", "vsb_remap_linear_u8c3", "vsb_gain_u8",
+    "vsb_compose_host", "vsb_submit_host", "vsb_wait_host", "vsb_last_launch_count", "vsb_remap_linear_u8c3", "vsb_gain_u8",
     "vsb_border_reflect_u8c3_to_s16c3", "vsb_pyr_down_s16c3", "vsb_pyr_up_s16c3", "vsb_pyr_down_f32",
     "vsb_add_src_weight_32f", "vsb_normalize_32f", "vsb_debug_read",
     "vsb_shard_set", "vsb_shard_info", "vsb_shard_rect", "vsb_get_plane",
@@ -196,6 +196,23 @@ class Stitcher:
         sp = (C.c_void_p * len(src_ptrs))(*[int(p) for p in src_ptrs])
         op = (C.c_void_p * n_frames)(*[int(p) for p in out_ptrs])
         check(lib().vsb_compose_host(self._h, n_frames, sp, C.c_size_t(src_pitch), op, C.c_size_t(out_pitch)))
+
+    def make_submit_host_call(self, src_ptrs, src_pitch, out_ptrs, out_pitch):
+        """Pre-marshalled vsb_submit_host (asynchronous; pair every call with wait_host())."""
+        n_frames = len(out_ptrs)
+        sp = (C.c_void_p * len(src_ptrs))(*[int(p) for p in src_ptrs])
+        op = (C.c_void_p * n_frames)(*[int(p) for p in out_ptrs])
+        fn, h, a, b = lib().vsb_submit_host, self._h, C.c_size_t(src_pitch), C.c_size_t(out_pitch)
+
+        def call():
+            rc = fn(h, n_frames, sp, a, op, b)
+            if rc != OK:
+                check(rc)
+        call._keep = (sp, op)
+        return call
+
+    def wait_host(self):
+        check(lib().vsb_wait_host(self._h))
 
     # ---- view-sharded mode
     def shard_set(self, rank, world):

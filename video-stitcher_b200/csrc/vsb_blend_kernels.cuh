@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(DT_TX *DT_TY) k_down_tail(const __grid_constan
 // normalisation by the static weight sums and the collapse nb -> 2.  Output: C2 = D2 + up(D3 + up(... Dnb)).
 // Every level is processed as 2x2 quads (one thread each): the 3x3 neighbourhood of the coarser level is read once and
 // no lane diverges on the pyrUp phase.
-constexpr int CT = 64, C_MAXJ = 6, C_THREADS = 256;
+constexpr int C_MAXJ = 6, C_THREADS = 256;  // (the tile edge is a template parameter of k_coarse: 64 or 32 level-2 samples)
 
 struct CoarseGeo {  // tile-independent offsets, relative to (X0 >> j, Y0 >> j); same for x and y (square tiles)
     int nlev;                         // levels 2 .. nb  ->  nb - 1
@@ -521,15 +521,23 @@ __device__ __forceinline__ void up_quad_f(const float *p, int pitch, int px, int
     r[3] = __fmaf_rn(vb1, sb * s1y * 0.015625f, B2_MAGIC);
 }
 
-constexpr int C2_UQ = 2;  // quads of levels >= 3 per thread (425 quads at num_bands 5, 456 at 7: at most 2 x 256)
-
-__global__ void __launch_bounds__(C_THREADS, 3) k_coarse(const __grid_constant__ CoarseParams P)
+// TCT = tile edge in level-2 samples.  64: four level-2 quads and up to two coarser quads per thread (425 coarser quads at
+// num_bands 5, 456 at 7), 80 registers, 3 CTAs / SM.  32 (num_bands <= 6, where every region size stays even): one quad of each
+// kind per thread (at most 142 coarser quads), four times as many CTAs of a quarter of the work: the grid no longer ends in a
+// nearly empty second wave and more CTAs per SM hide the load latency this kernel is bound by.
+#ifndef VSB_CO32_MINB
+#define VSB_CO32_MINB 4
+#endif
+template <int TCT>
+__global__ void __launch_bounds__(C_THREADS, TCT == 64 ? 3 : VSB_CO32_MINB) k_coarse(const __grid_constant__ CoarseParams P)
 {
+    constexpr int C2_UQ = TCT == 64 ? 2 : 1;                            // quads of levels >= 3 per thread
+    constexpr int QN = TCT / 2, C2_Q0 = QN * QN / C_THREADS;            // level-2 quads per row / per thread
     extern __shared__ __align__(16) uint8_t c_smem[];
     const CoarseGeo &Gm = P.geo;
     float *F = (float *)c_smem;  // staged regions at Gm.f_off[j], collapsed regions at Gm.d_off[j] (j >= 1)
     const int t = threadIdx.x, c = blockIdx.y, f = blockIdx.z + P.f0, nlev = Gm.nlev;
-    const int X0 = (blockIdx.x % P.tiles_x) * CT, Y0 = (blockIdx.x / P.tiles_x) * CT;
+    const int X0 = (blockIdx.x % P.tiles_x) * TCT, Y0 = (blockIdx.x / P.tiles_x) * TCT;
     unsigned views = __ldg(P.tile_views + blockIdx.x);
     if (views & 0x80000000u) return;  // view-sharded mode: another rank owns this canvas strip
     // this thread's quads: four of level 2 (quad row (t >> 5) + 8k, quad column t & 31) and up to two of the coarser levels
@@ -546,9 +554,9 @@ __global__ void __launch_bounds__(C_THREADS, 3) k_coarse(const __grid_constant__
                 if (idx >= first[j] && idx < first[j + 1]) { const int nq = Gm.a_n[j] >> 1, q = idx - first[j]; uj[k] = j; ur[k] = 2 * (q / nq); uc[k] = 2 * (q % nq); }
         }
     }
-    int acc0[4][4], accu[C2_UQ][4];
+    int acc0[C2_Q0][4], accu[C2_UQ][4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) acc0[k][0] = acc0[k][1] = acc0[k][2] = acc0[k][3] = 0;
+    for (int k = 0; k < C2_Q0; ++k) acc0[k][0] = acc0[k][1] = acc0[k][2] = acc0[k][3] = 0;
 #pragma unroll
     for (int k = 0; k < C2_UQ; ++k) accu[k][0] = accu[k][1] = accu[k][2] = accu[k][3] = 0;
 
@@ -562,11 +570,11 @@ __global__ void __launch_bounds__(C_THREADS, 3) k_coarse(const __grid_constant__
             const uint8_t *g = V.g[j] + (size_t)f * V.g_fs[j] + (size_t)c * w * h;
             const int vx0 = (X0 >> j) + Gm.a_lo[j] - (V.x_tl >> k), vy0 = (Y0 >> j) + Gm.a_lo[j] - (V.y_tl >> k);
             float *dst = F + Gm.f_off[j];
-            if (n == CT && vx0 >= 0 && vx0 + CT <= w && ((((size_t)(g + vx0)) | (size_t)w) & 3) == 0) {
-                for (int i = t; i < CT * (CT / 4); i += C_THREADS) {  // level 2 inside the plane: aligned words
-                    const int r = i / (CT / 4), q4 = i - r * (CT / 4);
+            if (n == TCT && vx0 >= 0 && vx0 + TCT <= w && ((((size_t)(g + vx0)) | (size_t)w) & 3) == 0) {
+                for (int i = t; i < TCT * (TCT / 4); i += C_THREADS) {  // level 2 inside the plane: aligned words
+                    const int r = i / (TCT / 4), q4 = i - r * (TCT / 4);
                     const unsigned word = __ldg((const unsigned *)(g + (size_t)up_idx(vy0 + r, h) * w + vx0) + q4);
-                    *(float4 *)(dst + r * CT + 4 * q4) = make_float4((float)(word & 0xffu), (float)((word >> 8) & 0xffu), (float)((word >> 16) & 0xffu), (float)(word >> 24));
+                    *(float4 *)(dst + r * TCT + 4 * q4) = make_float4((float)(word & 0xffu), (float)((word >> 8) & 0xffu), (float)((word >> 16) & 0xffu), (float)(word >> 24));
                 }
                 continue;
             }
@@ -588,8 +596,8 @@ __global__ void __launch_bounds__(C_THREADS, 3) k_coarse(const __grid_constant__
             const int un = top ? 0 : Gm.a_n[1];
             const int ux0 = top ? 0 : (X0 >> 1) + Gm.a_lo[1] - (V.x_tl >> 3), uy0 = top ? 0 : (Y0 >> 1) + Gm.a_lo[1] - (V.y_tl >> 3);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int qr = 2 * ((t >> 5) + 8 * k), qc = 2 * (t & 31);
+            for (int k = 0; k < C2_Q0; ++k) {
+                const int qi = t + k * C_THREADS, qr = 2 * (qi / QN), qc = 2 * (qi % QN);
                 const int x0 = ax0 + qc, y0 = ay0 + qr;
                 float wq[4];
 #pragma unroll
@@ -602,7 +610,7 @@ __global__ void __launch_bounds__(C_THREADS, 3) k_coarse(const __grid_constant__
                 if (!top) up_quad_f(G1r + ((y0 >> 1) - 1 + py - uy0) * un + ((x0 >> 1) - 1 + px - ux0), un, px, py, up);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float gv = G0r[(qr + (q >> 1)) * CT + qc + (q & 1)];
+                    const float gv = G0r[(qr + (q >> 1)) * TCT + qc + (q & 1)];
                     acc0[k][q] += rz_s16(__fmul_rn(__fsub_rn(__fadd_rn(gv, B2_MAGIC), up[q]), wq[q]));
                 }
             }
@@ -685,8 +693,8 @@ __global__ void __launch_bounds__(C_THREADS, 3) k_coarse(const __grid_constant__
         const int cw2 = P.cw[0], ch2 = P.ch[0];
         int16_t *o = P.c2 + (size_t)f * P.c2_fs + (size_t)c * cw2 * ch2;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int qr = 2 * ((t >> 5) + 8 * k), qc = 2 * (t & 31);
+        for (int k = 0; k < C2_Q0; ++k) {
+            const int qi = t + k * C_THREADS, qr = 2 * (qi / QN), qc = 2 * (qi % QN);
             int out[4];
             collapse_quad(0, qr, qc, acc0[k], out);
 #pragma unroll
@@ -950,6 +958,9 @@ __device__ __forceinline__ void store_tile(const void *sTile, const BlendParams 
 #ifndef VSB_BL_MINB
 #define VSB_BL_MINB 4
 #endif
+#ifndef VSB_SEAM_STRIPS
+#define VSB_SEAM_STRIPS 0  // measured 4 % slower (126 vs 121 us per 8 frames): the narrow strips cost more in G0 sectors than the skipped work saves
+#endif
 #ifndef VSB_BLI_MINB
 #define VSB_BLI_MINB 5
 #endif
@@ -1042,9 +1053,15 @@ __global__ void __launch_bounds__(BL_THREADS, VSB_BL_MINB) k_blend_seam(const __
     const int bx = (int)(tile & 0xfffu), by = (int)((tile >> 12) & 0xfffu);
     const int tx0 = bx * BL_TW, ty0 = by * BL_TH;
     const unsigned views_all = __ldg(P.tile_views + by * P.tiles_x + bx) & 0x3fffffffu;
-    // level-0 mapping: a warp holds four rows of one parity, a thread 8 consecutive samples
+    // level-0 mapping: a warp holds a 16-column strip of the tile -- all 16 rows of one parity, two 8-sample groups per row.  Seams
+    // run mostly vertically, so the second view, the non-unit weight sums and with them the IEEE divisions concern one or two of the
+    // four strips; the other warps skip them without divergence.  (One parity per warp: the vertical pyrUp phase never diverges.)
     const int warp = t >> 5, lane = t & 31;
+#if VSB_SEAM_STRIPS
+    const int ly = (lane >> 1) * 2 + (warp & 1), lx = (warp >> 1) * 16 + (lane & 1) * 8;
+#else
     const int ly = (warp >> 1) * 8 + (lane >> 3) * 2 + (warp & 1), lx = (lane & 7) * 8;
+#endif
     const int px0 = tx0 + lx, py = ty0 + ly;
     const bool row_odd = warp & 1;
     const int reg_off = (ly >> 1) * B2_G1P + (lx >> 1) + B2_G1OFF;

@@ -36,6 +36,8 @@ namespace vsb {
 // ============================================================================================ device side
 
 constexpr int MAX_SPLIT = 4;  // sub-batches of one submission's back half (internal streams)
+constexpr int HOST_DEPTH = 2;  // vsb_submit_host: submissions in flight (each with its own device staging)
+constexpr int HOST_SUB = 2;    // ... frames per upload -> compose -> download pipeline stage
 
 struct TileMap {
     int n;
@@ -353,6 +355,265 @@ __global__ void __launch_bounds__(RM_BX *RM_BY, VSB_RM1_MINB) k_remap_stage1_tab
             d32[2] = (px[2] >> 16) | (px[3] << 8);
         } else {
             for (int k = 0; k < n; ++k) { dst[3 * k] = px[k] & 0xff; dst[3 * k + 1] = (px[k] >> 8) & 0xff; dst[3 * k + 2] = (px[k] >> 16) & 0xff; }
+        }
+    }
+}
+
+// K1, higher-occupancy form: the same 128 x 8 tile by 512 threads, TWO lane-interleaved pixels per thread.  A warp owns half a
+// tile row (64 pixels = 48 output words): half the table entries and tap values live per thread, 40 registers instead of 64,
+// so six instead of four warps per scheduler hide the latency of the window gathers (the kernel's dominant stall).
+constexpr int S1H_PX = 2, S1H_SEG = 32 * S1H_PX;  // pixels per thread / per warp
+__global__ void __launch_bounds__(RM_BX * RM_BY * 2, 3) k_remap_stage1_tab_h(const __grid_constant__ Stage1TabParams p)
+{
+    __shared__ unsigned sP[RM_BY * 2][S1H_SEG + 1];
+    const unsigned tile = __ldg(p.tiles + blockIdx.x);
+    const int vi = tile & 0xff;
+    const Stage1TabView &V = p.v[vi];
+    const int half = threadIdx.y & 1, y = (int)(tile >> 20) * RM_BY + (threadIdx.y >> 1);
+    const int sx0 = (int)((tile >> 8) & 0xfff) * (RM_BX * RM_PX) + half * S1H_SEG;  // first pixel of this warp's half row
+    const int x0 = sx0 + threadIdx.x;
+    if (y >= V.h || sx0 >= V.w) return;  // (warp-uniform)
+    const size_t i = (size_t)y * V.tab.tab_pitch + x0;
+    int off[S1H_PX];
+    float wa[S1H_PX], wb[S1H_PX], wc[S1H_PX], wd[S1H_PX];
+#pragma unroll
+    for (int k = 0; k < S1H_PX; ++k) {
+        const bool in = x0 + k * 32 < V.tab.tab_pitch;
+        off[k] = in ? __ldg(V.tab.off + i + k * 32) : 0;
+        wa[k] = in ? __ldg(V.tab.w + i + k * 32) : 0.f;
+        wb[k] = in ? __ldg(V.tab.w + V.tab.plane + i + k * 32) : 0.f;
+        wc[k] = in ? __ldg(V.tab.w + 2 * V.tab.plane + i + k * 32) : 0.f;
+        wd[k] = in ? __ldg(V.tab.w + 3 * V.tab.plane + i + k * 32) : 0.f;
+    }
+    const bool slow = (off[0] | off[1]) < 0;
+    // this thread stores words lane and lane + 32 (< 48) of the half row; word j starts in pixel 4j / 3
+    int wp[2], wr[2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) { const int j = threadIdx.x + 32 * m; wp[m] = (4 * j) / 3; wr[m] = 8 * (4 * j - 3 * wp[m]); }
+    const int row_bytes = 3 * min(S1H_SEG, V.w - sx0);
+    uint8_t *dst = V.P + (size_t)p.f0 * V.p_frame_stride + (size_t)y * V.p_pitch + (size_t)sx0 * 3;
+    unsigned *row = sP[threadIdx.y];
+#pragma unroll 1
+    for (int f = p.f0; f < p.f0 + p.n_frames; ++f, dst += V.p_frame_stride) {
+        const uint8_t *src = p.src[f * p.n_views + vi - p.v0];
+        unsigned px[S1H_PX];
+#pragma unroll
+        for (int k = 0; k < S1H_PX; ++k) px[k] = remap_tab_px<true>(src, p.src_pitch, (unsigned)off[k] & 0x7fffffffu, wa[k], wb[k], wc[k], wd[k], V.gain);
+        if (slow) {
+#pragma unroll 1
+            for (int k = 0; k < S1H_PX; ++k) {
+                if (off[k] >= 0) continue;
+                const float fx = __ldg((const float *)((const char *)V.xmap + (size_t)y * V.map_pitch) + x0 + k * 32);
+                const float fy = __ldg((const float *)((const char *)V.ymap + (size_t)y * V.map_pitch) + x0 + k * 32);
+                px[k] = remap_gain_px_edge<true>(src, p.src_pitch, V.src_w, V.src_h, fx, fy, V.gain);
+            }
+        }
+        __syncwarp();  // the previous frame's reads of this row are done
+#pragma unroll
+        for (int k = 0; k < S1H_PX; ++k) row[threadIdx.x + k * 32] = px[k];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const int b0 = 4 * (threadIdx.x + 32 * m);
+            if (b0 >= row_bytes) continue;
+            const unsigned word = (row[wp[m]] >> wr[m]) | (row[wp[m] + 1] << (24 - wr[m]));
+            if (b0 + 4 <= row_bytes) *(unsigned *)(dst + b0) = word;
+            else for (int e = 0; b0 + e < row_bytes; ++e) dst[b0 + e] = (word >> (8 * e)) & 0xff;
+        }
+    }
+}
+
+// ---- K1, shared-memory staged form (default whenever the caller's frames are 16-byte aligned) ------------------------------------
+// The scalar window gathers of the kernels above are bound by the L1 data pipe: a warp's 32 four-byte loads touch ~4 cache lines,
+// i.e. ~4 wavefronts per instruction, ~20 per pixel.  Here one CTA owns a 32 x 32 tile of the warped ROI whose SOURCE FOOTPRINT --
+// the bounding box of every 2x2 window its table entries address, a static property of the tile computed once per map
+// (k_s1_boxes) -- is brought into shared memory with asynchronous 16-byte copies (cp.async: global -> shared without passing
+// through registers, perfectly coalesced rows), once per frame of the submission, and the gathers run against shared memory.
+// Boxes that fit twice into the buffer (most) are double buffered: the copies of frame f + 1 fly while frame f is computed.
+// A thread owns 4 consecutive pixels (one 12-byte store) and keeps its table entries in registers while the frames stream
+// through.  Tiles whose footprint exceeds the box (never at the BASELINE configurations) take the global-memory gathers inside
+// the same kernel.  (A bulk-tensor copy would need one descriptor per caller frame buffer and a fixed box; cp.async.bulk per
+// row is a uniform-datapath instruction and serialises over the lanes that issue it.)
+constexpr int S1S_T = 32;                       // tile edge (pixels)
+constexpr int S1S_BW = 320, S1S_BH = 104;       // footprint box: bytes per row x rows (33 280 B of shared memory)
+struct S1STile { uint32_t id, xw, yh, magic; };  // id = view | tx << 8 | ty << 20; xw = x0 (bytes) | row bytes << 16; yh = y0 | rows << 16 (rows == 0: not staged);
+                                                // magic = ceil(2^32 / (row bytes / 16)): chunk index -> box row by one multiply-high
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// footprint boxes of the 32 x 32 tiles of one view for the current table (one CTA per tile, one thread per 4 entries)
+__global__ void __launch_bounds__(256) k_s1_boxes(const uint32_t *__restrict__ ids, S1STile *__restrict__ out, TapTable tab, int w, int h,
+                                                  unsigned pitch, int sw, int sh)
+{
+    __shared__ int mn_x, mx_x, mn_y, mx_y;
+    if (threadIdx.x == 0) { mn_x = mn_y = 0x7fffffff; mx_x = mx_y = -1; }
+    __syncthreads();
+    const uint32_t id = ids[blockIdx.x];
+    const int x0 = (int)((id >> 8) & 0xfff) * S1S_T + (threadIdx.x & 7) * 4, y = (int)(id >> 20) * S1S_T + (threadIdx.x >> 3);
+    if (y < h) {
+        for (int k = 0; k < 4 && x0 + k < w; ++k) {
+            const size_t i = (size_t)y * tab.tab_pitch + x0 + k;
+            const int off = tab.off[i];
+            if (off < 0) continue;  // TAP_SLOW: coordinate path
+            if (tab.w[i] == 0.f && tab.w[tab.plane + i] == 0.f && tab.w[2 * tab.plane + i] == 0.f && tab.w[3 * tab.plane + i] == 0.f) continue;
+            const int r = (int)((unsigned)off / pitch), xb = (int)((unsigned)off - (unsigned)r * pitch);
+            atomicMin(&mn_x, xb); atomicMax(&mx_x, xb); atomicMin(&mn_y, r); atomicMax(&mx_y, r);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        S1STile T;
+        T.id = id; T.magic = 0;
+        if (mx_x < 0) { T.xw = 16u << 16; T.yh = 1u << 16; }  // nothing addresses the image: a dummy 16-byte box (row 0)
+        else {
+            int bx0 = mn_x & ~15, bx1 = (mx_x + 10 + 15) & ~15;  // word loads of a window reach 9 bytes past its first byte
+            if (bx1 - bx0 < 32) { if ((unsigned)bx0 + 32u <= pitch) bx1 = bx0 + 32; else if (bx0 >= 16) bx0 -= 16; }  // >= 2 chunks per row (multiply-high row index)
+            const int bw = bx1 - bx0, bh = mx_y + 2 - mn_y;
+            // the last image row must not be read past the end of the caller's buffer
+            const bool overrun = mx_y + 1 == sh - 1 && (unsigned)bx1 > (unsigned)sw * 3u;
+            const bool fits = bw >= 32 && bw <= S1S_BW && bh <= S1S_BH && (unsigned)bx1 <= pitch && !overrun;
+            T.xw = (unsigned)bx0 | ((unsigned)bw << 16);
+            T.yh = (unsigned)mn_y | ((fits ? (unsigned)bh : 0u) << 16);
+        }
+        const unsigned cpr = (T.xw >> 16) / 16u;
+        T.magic = cpr <= 1u ? 0u : (unsigned)((0x100000000ull + cpr - 1u) / cpr);  // exact for chunk indices < 2^16 (<= 2080 here); the dummy box has one chunk
+        out[blockIdx.x] = T;
+    }
+}
+
+// remap_tab_px against a shared-memory image (plain loads: the table offset is relative to the staged box)
+template <bool GAIN>
+__device__ __forceinline__ unsigned remap_tab_px_smem(const uint8_t *base, unsigned pitch, unsigned off, float wa, float wb, float wc, float wd, float gain)
+{
+    const uint8_t *a = base + (off & ~3u);
+    const unsigned s8 = (off & 3u) * 8u;
+    const unsigned t0 = *(const unsigned *)a, t1 = *(const unsigned *)(a + 4);
+    const unsigned u0 = *(const unsigned *)(a + pitch), u1 = *(const unsigned *)(a + pitch + 4);
+    const unsigned t2 = *(const unsigned *)(a + 8), u2 = *(const unsigned *)(a + pitch + 8);  // inside the box by construction
+    const unsigned lo1 = __funnelshift_r(t0, t1, s8), hi1 = __funnelshift_r(t1, t2, s8);
+    const unsigned lo2 = __funnelshift_r(u0, u1, s8), hi2 = __funnelshift_r(u1, u2, s8);
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float v = __fmul_rn(u8_den(lo1, c), wa);
+        v = __fmaf_rn(c == 0 ? u8_den(lo1, 3) : u8_den(hi1, c - 1), wb, v);
+        v = __fmaf_rn(u8_den(lo2, c), wc, v);
+        v = __fmaf_rn(c == 0 ? u8_den(lo2, 3) : u8_den(hi2, c - 1), wd, v);
+        v = __fmaf_rn(v, 8388608.f, 12582912.f);
+        o[c] = GAIN ? rni_biased(fminf(__fmul_rn(gain, __fsub_rn(v, 12582912.f)), 255.f)) : v;
+    }
+    return __byte_perm(__byte_perm(__float_as_uint(o[0]), __float_as_uint(o[1]), 0x0040u), __float_as_uint(o[2]), 0x0410u) & 0xffffffu;
+}
+
+struct Stage1StParams {
+    Stage1TabParams t;
+    const S1STile *tiles_s;
+};
+
+#ifndef VSB_S1S_MINB
+#define VSB_S1S_MINB 4
+#endif
+__global__ void __launch_bounds__(256, VSB_S1S_MINB) k_remap_stage1_st(const __grid_constant__ Stage1StParams pp)
+{
+    __shared__ __align__(128) uint8_t box[S1S_BW * S1S_BH + 16];
+    const Stage1TabParams &p = pp.t;
+    const S1STile T = pp.tiles_s[blockIdx.x];
+    const int vi = T.id & 0xff;
+    const Stage1TabView &V = p.v[vi];
+    const int t = threadIdx.x;
+    const int x0 = (int)((T.id >> 8) & 0xfff) * S1S_T + (t & 7) * RM_PX, y = (int)(T.id >> 20) * S1S_T + (t >> 3);
+    const bool live = y < V.h && x0 < V.w;
+    const unsigned bx0 = T.xw & 0xffffu, bw = T.xw >> 16, by0 = T.yh & 0xffffu, bh = T.yh >> 16;
+    const bool staged = bh != 0u;  // (uniform)
+    const unsigned box_bytes = bw * bh, cpr = bw >> 4, n_chunks = cpr * bh;
+    const bool dbl = staged && 2u * box_bytes <= (unsigned)(S1S_BW * S1S_BH);  // (uniform) two half buffers, 128-byte aligned
+    const unsigned half = dbl ? ((box_bytes + 127u) & ~127u) : 0u;
+    int off[RM_PX];
+    float wa[RM_PX], wb[RM_PX], wc[RM_PX], wd[RM_PX];
+#pragma unroll
+    for (int k = 0; k < RM_PX; ++k) { off[k] = 0; wa[k] = wb[k] = wc[k] = wd[k] = 0.f; }
+    if (live) {  // table rows are 16-byte aligned and x0 % 4 == 0; the padding entries of the last vector are zero
+        const size_t i = (size_t)y * V.tab.tab_pitch + x0;
+        const int4 o = __ldg((const int4 *)(V.tab.off + i));
+        const float4 A = __ldg((const float4 *)(V.tab.w + i)), B = __ldg((const float4 *)(V.tab.w + V.tab.plane + i));
+        const float4 C = __ldg((const float4 *)(V.tab.w + 2 * V.tab.plane + i)), D = __ldg((const float4 *)(V.tab.w + 3 * V.tab.plane + i));
+        off[0] = o.x; off[1] = o.y; off[2] = o.z; off[3] = o.w;
+        wa[0] = A.x; wa[1] = A.y; wa[2] = A.z; wa[3] = A.w; wb[0] = B.x; wb[1] = B.y; wb[2] = B.z; wb[3] = B.w;
+        wc[0] = C.x; wc[1] = C.y; wc[2] = C.z; wc[3] = C.w; wd[0] = D.x; wd[1] = D.y; wd[2] = D.z; wd[3] = D.w;
+    }
+    const bool slow = (off[0] | off[1] | off[2] | off[3]) < 0;
+    unsigned so[RM_PX];  // staged: offset of the window inside the box; entries without any tap in the image read the box origin (weights 0)
+#pragma unroll
+    for (int k = 0; k < RM_PX; ++k) {
+        so[k] = (unsigned)off[k] & 0x7fffffffu;
+        if (staged) {
+            const bool null = off[k] < 0 || (wa[k] == 0.f && wb[k] == 0.f && wc[k] == 0.f && wd[k] == 0.f);
+            const unsigned r = so[k] / p.src_pitch, xb = so[k] - r * p.src_pitch;
+            so[k] = null ? 0u : (r - by0) * bw + (xb - bx0);
+        }
+    }
+    // the box of one frame: 16-byte chunks, chunk c = row c / cpr, column c % cpr (rows of the box are contiguous in the source row)
+    auto fetch = [&](const uint8_t *src, uint8_t *dstbox) {
+        const uint8_t *g = src + (size_t)by0 * p.src_pitch + bx0;
+        for (unsigned c = t; c < n_chunks; c += 256) {
+            const unsigned r = __umulhi(c, T.magic), q = c - r * cpr;
+            cp_async16(dstbox + c * 16u, g + (size_t)r * p.src_pitch + q * 16u);
+        }
+        cp_async_commit();
+    };
+    const int n = min(RM_PX, V.w - x0);
+    uint8_t *dst = V.P + (size_t)p.f0 * V.p_frame_stride + (size_t)y * V.p_pitch + (size_t)x0 * 3;
+    const int f_end = p.f0 + p.n_frames;
+    if (staged) fetch(p.src[p.f0 * p.n_views + vi - p.v0], box);
+#pragma unroll 1
+    for (int f = p.f0; f < f_end; ++f, dst += V.p_frame_stride) {
+        const uint8_t *src = p.src[f * p.n_views + vi - p.v0];
+        const uint8_t *cur = box + ((f - p.f0) & 1) * half;
+        if (staged) {
+            if (dbl && f + 1 < f_end) {  // the next frame's box flies while this one is computed
+                fetch(p.src[(f + 1) * p.n_views + vi - p.v0], box + ((f + 1 - p.f0) & 1) * half);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();  // every thread's copies of this frame have landed
+        }
+        if (live) {
+            unsigned px[RM_PX];
+            if (staged) {
+#pragma unroll
+                for (int k = 0; k < RM_PX; ++k) px[k] = remap_tab_px_smem<true>(cur, bw, so[k], wa[k], wb[k], wc[k], wd[k], V.gain);
+            } else {
+#pragma unroll
+                for (int k = 0; k < RM_PX; ++k) px[k] = remap_tab_px<true>(src, p.src_pitch, so[k], wa[k], wb[k], wc[k], wd[k], V.gain);
+            }
+            if (slow) {  // TAP_SLOW entries: the result comes from the coordinates
+#pragma unroll 1
+                for (int k = 0; k < RM_PX; ++k) {
+                    if (off[k] >= 0) continue;
+                    const float fx = __ldg((const float *)((const char *)V.xmap + (size_t)y * V.map_pitch) + x0 + k);
+                    const float fy = __ldg((const float *)((const char *)V.ymap + (size_t)y * V.map_pitch) + x0 + k);
+                    px[k] = remap_gain_px_edge<true>(src, p.src_pitch, V.src_w, V.src_h, fx, fy, V.gain);
+                }
+            }
+            if (n == RM_PX) {  // 12 bytes = three aligned 32-bit stores
+                unsigned *d32 = (unsigned *)dst;
+                d32[0] = px[0] | (px[1] << 24);
+                d32[1] = (px[1] >> 8) | (px[2] << 16);
+                d32[2] = (px[2] >> 16) | (px[3] << 8);
+            } else {
+                for (int k = 0; k < n; ++k) { dst[3 * k] = px[k] & 0xff; dst[3 * k + 1] = (px[k] >> 8) & 0xff; dst[3 * k + 2] = (px[k] >> 16) & 0xff; }
+            }
+        }
+        if (staged) {
+            __syncthreads();  // every reader is done before this buffer is filled again
+            if (!dbl && f + 1 < f_end) fetch(p.src[(f + 1) * p.n_views + vi - p.v0], box);
         }
     }
 }
@@ -848,6 +1109,7 @@ struct View {
     std::vector<uint8_t> g2_needed;     // per k_down2 tile: computed (1) or skipped (0); host copy for vsb_debug_read
     int d2_tiles_x = 0, d2_tiles_y = 0;
     std::vector<uint32_t> s1_tiles, s2_tiles;  // 128 x 8 tiles k_remap_stage1 / k_remap_stage2 compute (packed view|tx|ty)
+    std::vector<uint32_t> s1s_tiles;           // 32 x 32 tiles of the staged remap #1 (k_remap_stage1_st), same packing
     std::vector<int> w0_cols;                  // per plane column: number of non-zero level-0 weights (view -> strip ownership)
 };
 
@@ -867,6 +1129,7 @@ struct vsb_stitcher {
     // fast path (num_bands >= 3): static tile tables + per-frame canvas buffer
     bool fast = false;
     vsb::CoarseGeo cgeo;
+    int ct = 64;                          // k_coarse tile edge (level-2 samples)
     size_t coarse_smem = 0;
     uint32_t *d_blend_views = nullptr, *d_coarse_views = nullptr, *d_down2_tiles = nullptr;
     uint32_t *d_blend_lists = nullptr;   // interior tiles (tile_x | tile_y << 12 | view << 24), then the other tiles (k_blend_int / k_blend_seam)
@@ -875,6 +1138,8 @@ struct vsb_stitcher {
     int16_t *C2 = nullptr;
     size_t c2_frame_stride = 0;
     uint32_t *d_s1_tiles = nullptr, *d_s2_tiles = nullptr;  // concatenated per-view lists, view order
+    uint32_t *d_s1s_ids = nullptr;                           // ... of the staged remap #1
+    vsb::S1STile *d_s1s_tiles = nullptr;                     // its tile records (footprint boxes: k_s1_boxes, rebuilt with the tap tables)
     vsb::CoarseView *d_coarse_desc = nullptr;
     // view-sharded mode (vsb_shard_set): this rank's views and canvas strip; host copies of the tile tables
     std::vector<uint32_t> h_bviews, h_cviews;
@@ -902,12 +1167,15 @@ struct vsb_stitcher {
     std::mutex mu;  // guards mesh publication
     int f0 = 0;                         // first frame slot the launch helpers address (vsb_compose splits a batch over two streams)
     cudaStream_t sub[vsb::MAX_SPLIT] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[vsb::MAX_SPLIT] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[vsb::MAX_SPLIT] = {}, ev_forks[vsb::MAX_SPLIT] = {};
     int launches = 0, launches_last = 0;  // running count of the submission in flight / count of the last finished one
     // vsb_feed / vsb_blend bookkeeping (frame slot 0)
     // host-buffer path staging
-    uint8_t *stage_src = nullptr;
-    int16_t *stage_out = nullptr;
+    uint8_t *stage_src[vsb::HOST_DEPTH] = {};
+    int16_t *stage_out[vsb::HOST_DEPTH] = {};
+    cudaEvent_t ev_host[vsb::HOST_DEPTH] = {};
+    unsigned host_seq = 0;      // submissions enqueued by vsb_submit_host
+    int host_pending = 0;       // ... of which not yet waited for
     size_t stage_src_pitch = 0, stage_src_frame = 0, stage_out_pitch = 0, stage_out_frame = 0;
     int stage_src_w = 0, stage_src_h = 0, stage_views = 0, stage_batch = 0;  // what stage_src / stage_nv12 were sized for
     int rig_projection = -1, rig_src_w = 0, rig_src_h = 0;
@@ -919,7 +1187,7 @@ struct vsb_stitcher {
     int nv_w = 0, nv_h = 0;
     int *cons_tab = nullptr;            // consumer resize tables for (cons_w x cons_ih): xofs | yofs | ia | ib
     int cons_w = 0, cons_ih = 0;
-    uint8_t *stage_nv12 = nullptr;      // host path: device copy of the caller's NV12 frames
+    uint8_t *stage_nv12[vsb::HOST_DEPTH] = {};  // host path: device copy of the caller's NV12 frames
     size_t stage_nv12_frame = 0;
     // optional per-kernel timing (vsb_set_profiling): events bracket every launch of the last submission
     bool profiling = false;
@@ -1011,7 +1279,7 @@ static int build_plan(vsb_stitcher *s)
 static inline int fdiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }  // floor(v / 2)
 
 // region offsets of k_coarse, relative to the tile origin at each level (see vsb_blend_kernels.cuh)
-static void coarse_geometry(int nb, CoarseGeo &g)
+static void coarse_geometry(int nb, int CT, CoarseGeo &g)
 {
     std::memset(&g, 0, sizeof(g));
     const int nlev = nb - 1;
@@ -1162,7 +1430,11 @@ static int build_fast_plan(vsb_stitcher *s)
                 b |= 0x40000000u;
         }
     // ---- k_coarse: views with weight at any level >= 2 per 64 x 64 level-2 canvas tile
-    coarse_geometry(nb, s->cgeo);
+    // k_coarse tile edge: 32 level-2 samples while every region size stays even (num_bands <= 6), else 64
+    static const int ct_env = [] { const char *e = std::getenv("VSB_COARSE_TILE"); return e ? std::atoi(e) : 0; }();
+    s->ct = ct_env == 32 && nb <= 6 ? 32 : (ct_env == 64 || nb > 6 || s->cfg.max_batch > 2 ? 64 : 32);  // 32 pays off at 1-2 frames per launch (measured: +8 % single-frame rate, -10 % at 8 frames)
+    const int CT = s->ct;
+    coarse_geometry(nb, CT, s->cgeo);
     s->coarse_smem = coarse_smem_bytes(s->cgeo);
     s->coarse_tiles_x = (s->cw[2] + CT - 1) / CT; s->coarse_tiles_y = (s->ch[2] + CT - 1) / CT;
     std::vector<uint32_t> cviews((size_t)s->coarse_tiles_x * s->coarse_tiles_y, 0);
@@ -1247,7 +1519,7 @@ static int build_fast_plan(vsb_stitcher *s)
     if (!d2tiles.empty()) CK(cudaMemcpy(s->d_down2_tiles, d2tiles.data(), d2tiles.size() * 4, cudaMemcpyHostToDevice));
     s->c2_frame_stride = (size_t)3 * s->cw[2] * s->ch[2];
     CK(cudaMalloc(&s->C2, s->c2_frame_stride * sizeof(int16_t) * F));
-    if (s->coarse_smem > 48 * 1024) { int r = raise_dynamic_smem(k_coarse, s->device); if (r != VSB_OK) return r; }
+    if (s->coarse_smem > 48 * 1024) { int r = raise_dynamic_smem(k_coarse<64>, s->device); if (r != VSB_OK) return r; }
     std::vector<CoarseView> desc(n);
     std::memset(desc.data(), 0, sizeof(CoarseView) * n);
     for (int i = 0; i < n; ++i) {
@@ -1354,18 +1626,23 @@ static void fill_tilemap(TileMap &tm, int n, const int *w, const int *h, int til
 static int sync_tile_lists(vsb_stitcher *s)
 {
     if (!s->tiles_dirty) return VSB_OK;
-    std::vector<uint32_t> a, b;
+    std::vector<uint32_t> a, b, c;
     for (int i = 0; i < s->cfg.num_views; ++i) {
         a.insert(a.end(), s->v[i].s1_tiles.begin(), s->v[i].s1_tiles.end());
         b.insert(b.end(), s->v[i].s2_tiles.begin(), s->v[i].s2_tiles.end());
+        c.insert(c.end(), s->v[i].s1s_tiles.begin(), s->v[i].s1s_tiles.end());
+        s->v[i].t1_src_pitch = 0;  // the footprint boxes live next to the lists: rebuilt (with the tap table) by the next compose
     }
     { int r = wait_own_frames(s); if (r != VSB_OK) return r; }  // submissions in flight still read the old lists
-    cudaFree(s->d_s1_tiles); cudaFree(s->d_s2_tiles);
-    s->d_s1_tiles = s->d_s2_tiles = nullptr;
+    cudaFree(s->d_s1_tiles); cudaFree(s->d_s2_tiles); cudaFree(s->d_s1s_ids); cudaFree(s->d_s1s_tiles);
+    s->d_s1_tiles = s->d_s2_tiles = s->d_s1s_ids = nullptr; s->d_s1s_tiles = nullptr;
     CK(cudaMalloc(&s->d_s1_tiles, std::max<size_t>(a.size(), 1) * 4));
     CK(cudaMalloc(&s->d_s2_tiles, std::max<size_t>(b.size(), 1) * 4));
+    CK(cudaMalloc(&s->d_s1s_ids, std::max<size_t>(c.size(), 1) * 4));
+    CK(cudaMalloc(&s->d_s1s_tiles, std::max<size_t>(c.size(), 1) * sizeof(S1STile)));
     if (!a.empty()) CK(cudaMemcpy(s->d_s1_tiles, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
     if (!b.empty()) CK(cudaMemcpy(s->d_s2_tiles, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    if (!c.empty()) CK(cudaMemcpy(s->d_s1s_ids, c.data(), c.size() * 4, cudaMemcpyHostToDevice));
     s->tiles_dirty = false;
     return VSB_OK;
 }
@@ -1502,7 +1779,8 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
         double bytes = 6.0 * s->cw[2] * s->ch[2];  // Gaussian levels >= 2 of every view in once + C2 (s16 x 3) out once
         for (int i = 0; i < n; ++i)
             for (int k = 2; k <= nb; ++k) bytes += 3.0 * (s->v[i].bw >> k) * (s->v[i].bh >> k);
-        k_coarse<<<dim3(s->coarse_tiles_x * s->coarse_tiles_y, 3, n_frames), C_THREADS, s->coarse_smem, st>>>(p);
+        if (s->ct == 64) k_coarse<64><<<dim3(s->coarse_tiles_x * s->coarse_tiles_y, 3, n_frames), C_THREADS, s->coarse_smem, st>>>(p);
+        else k_coarse<32><<<dim3(s->coarse_tiles_x * s->coarse_tiles_y, 3, n_frames), C_THREADS, s->coarse_smem, st>>>(p);
         ++s->launches;
         prof_stage(s, st, "coarse", bytes * n_frames);
     }
@@ -1551,7 +1829,10 @@ static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_out
 
 // which form of the remap kernels runs (all bit-identical): VSB_REMAP_VARIANT = -1 forces the coordinate-driven kernels that
 // also serve unaligned caller frames; 0 / 1 = table-driven with 4 consecutive pixels per thread / lane-interleaved pixels
-// (default, ~3 % faster: fewer cache lines per window load)
+// (default, ~3 % faster: fewer cache lines per window load); 2 = lane-interleaved, 2 pixels per thread, 512-thread CTAs (measured
+// 4 % slower: the kernel is bound by L1 data-pipe wavefronts, not by latency); 3 = remap #1 gathers from a shared-memory copy of the
+// tile's source footprint filled by cp.async (k_remap_stage1_st; measured 3 % slower: the shared-memory gathers of a 4-pixel-per-thread
+// mapping take ~3 wavefronts each through bank conflicts, and the fill adds instructions to an issue-bound loop)
 static int remap_variant()
 {
     static int v = -2;
@@ -1609,8 +1890,16 @@ static int build_taps1(vsb_stitcher *s, int i, size_t src_pitch, cudaStream_t st
     const dim3 b(32, 8);
     k_build_taps1<<<grid2d(V.t1_pitch, V.roi_h, b), b, 0, st>>>(V.xmap, V.ymap, V.map_pitch, V.roi_w, V.roi_h, V.src_w, V.src_h,
                                                                 (unsigned)src_pitch, V.t1_off, V.t1_w, V.t1_plane, V.t1_pitch);
+    {   // footprint boxes of the staged remap #1 tiles of this view (they follow the table: same maps, same pitch)
+        int first = 0;
+        for (int j = 0; j < i; ++j) first += (int)s->v[j].s1s_tiles.size();
+        const int nt = (int)V.s1s_tiles.size();
+        TapTable tab;
+        tab.off = V.t1_off; tab.w = V.t1_w; tab.plane = V.t1_plane; tab.tab_pitch = V.t1_pitch;
+        if (nt > 0) k_s1_boxes<<<nt, 256, 0, st>>>(s->d_s1s_ids + first, s->d_s1s_tiles + first, tab, V.roi_w, V.roi_h, (unsigned)src_pitch, V.src_w, V.src_h);
+    }
     V.t1_src_pitch = src_pitch;
-    return check_launch("k_build_taps1");
+    return check_launch("k_build_taps1 / k_s1_boxes");
 }
 
 // remap stages + pyramid for views [v0, v1) of n_frames frames
@@ -1659,8 +1948,23 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
             p.tiles = s->d_s1_tiles + first;
             p.v0 = v0; p.n_views = n; p.src_pitch = (unsigned)src_pitch; p.n_frames = n_frames; p.f0 = s->f0;
             for (int f = 0; f < n_frames; ++f) for (int j = 0; j < n; ++j) p.src[(s->f0 + f) * n + j] = d_srcs[f * n + j];
-            if (count > 0) {
-                if (remap_variant() & 1) k_remap_stage1_tab<true><<<(unsigned)count, dim3(RM_BX, RM_BY), 0, st>>>(p);
+            // staged form: 16-byte aligned frames and rows, box coordinates in 16 bits
+            bool staged = remap_variant() == 3 && src_pitch % 16 == 0;
+            for (int i = v0; i < v1 && staged; ++i) staged = (size_t)s->v[i].src_w * 3 < 65536 && s->v[i].src_h < 65536;
+            for (int j = 0; j < n * n_frames && staged; ++j) staged = ((size_t)d_srcs[j] & 15) == 0;
+            if (staged) {
+                int sfirst = 0, scount = 0;
+                for (int i = 0; i < s->cfg.num_views; ++i) {
+                    if (i < v0) sfirst += (int)s->v[i].s1s_tiles.size();
+                    else if (i < v1) scount += (int)s->v[i].s1s_tiles.size();
+                }
+                Stage1StParams ps;
+                ps.t = p;
+                ps.tiles_s = s->d_s1s_tiles + sfirst;
+                if (scount > 0) k_remap_stage1_st<<<(unsigned)scount, 256, 0, st>>>(ps);
+            } else if (count > 0) {
+                if (remap_variant() == 2) k_remap_stage1_tab_h<<<(unsigned)count, dim3(RM_BX, RM_BY * 2), 0, st>>>(p);
+                else if (remap_variant() & 1) k_remap_stage1_tab<true><<<(unsigned)count, dim3(RM_BX, RM_BY), 0, st>>>(p);
                 else k_remap_stage1_tab<false><<<(unsigned)count, dim3(RM_BX, RM_BY), 0, st>>>(p);
             }
         } else {
@@ -1888,8 +2192,10 @@ int vsb_destroy(vsb_stitcher *s)
     cudaFree(s->d_plan);
     cudaFree(s->d_blend_views); cudaFree(s->d_coarse_views); cudaFree(s->d_down2_tiles); cudaFree(s->C2);
     cudaFree(s->d_coarse_desc); cudaFree(s->d_s1_tiles); cudaFree(s->d_s2_tiles); cudaFree(s->d_blend_lists);
+    cudaFree(s->d_s1s_ids); cudaFree(s->d_s1s_tiles);
     for (int i = 0; i < MAXV; ++i) { cudaFree(s->d_send[i]); cudaFree(s->d_recv[i]); }
-    cudaFree(s->stage_src); cudaFree(s->stage_out); cudaFree(s->nv_bgr); cudaFree(s->stage_nv12); cudaFree(s->cons_tab);
+    cudaFree(s->nv_bgr); cudaFree(s->cons_tab);
+    for (int d = 0; d < HOST_DEPTH; ++d) { cudaFree(s->stage_src[d]); cudaFree(s->stage_out[d]); cudaFree(s->stage_nv12[d]); if (s->ev_host[d]) cudaEventDestroy(s->ev_host[d]); }
     for (int b = 0; b < 2; ++b)
         for (int p = 0; p < MAXV; ++p) { cudaFree(s->x_send[b][p]); cudaFree(s->x_recv[b][p]); }
     if (s->comm) { const NcclApi *api = nccl_api(); if (api) api->CommDestroy(s->comm); }
@@ -1900,7 +2206,7 @@ int vsb_destroy(vsb_stitcher *s)
     if (s->io_stream) cudaStreamDestroy(s->io_stream);
     if (s->in_stream) cudaStreamDestroy(s->in_stream);
     if (s->out_stream) cudaStreamDestroy(s->out_stream);
-    for (int h = 0; h < MAX_SPLIT; ++h) { if (s->sub[h]) cudaStreamDestroy(s->sub[h]); if (s->ev_join[h]) cudaEventDestroy(s->ev_join[h]); }
+    for (int h = 0; h < MAX_SPLIT; ++h) { if (s->sub[h]) cudaStreamDestroy(s->sub[h]); if (s->ev_join[h]) cudaEventDestroy(s->ev_join[h]); if (s->ev_forks[h]) cudaEventDestroy(s->ev_forks[h]); }
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     for (int f = 0; f < MAX_BATCH; ++f) { if (s->ev_in[f]) cudaEventDestroy(s->ev_in[f]); if (s->ev_done[f]) cudaEventDestroy(s->ev_done[f]); }
     if (s->last_compose) cudaEventDestroy(s->last_compose);
@@ -1938,8 +2244,11 @@ int vsb_prepare(vsb_stitcher *s, const int *corners_xy, const int *sizes_wh)
         s->ch[k] = k == 0 ? H : (s->ch[k - 1] + 1) / 2;
         CK(cudaMalloc(&s->dw[k], sizeof(float) * s->cw[k] * s->ch[k]));
     }
-    cudaFree(s->stage_src); cudaFree(s->stage_nv12); cudaFree(s->stage_out);  // sized per calibration
-    s->stage_src = s->stage_nv12 = nullptr; s->stage_out = nullptr; s->stage_src_w = s->stage_src_h = 0;
+    for (int d = 0; d < HOST_DEPTH; ++d) {  // sized per calibration
+        cudaFree(s->stage_src[d]); cudaFree(s->stage_nv12[d]); cudaFree(s->stage_out[d]);
+        s->stage_src[d] = s->stage_nv12[d] = nullptr; s->stage_out[d] = nullptr;
+    }
+    s->stage_src_w = s->stage_src_h = 0; s->host_pending = 0;
     s->cons_w = s->cons_ih = 0;  // the consumer's resize tables depend on the panorama size
     s->views_inited = 0; s->prepared = true; s->finalized = false;
     return VSB_OK;
@@ -2090,6 +2399,17 @@ int vsb_set_maps(vsb_stitcher *s, int i, const float *xmap, const float *ymap, i
                     if (fx >= -1.f && fx < (float)src_w && fy >= -1.f && fy < (float)src_h) { any = true; break; }
                 }
             if (any) V.s1_tiles.push_back((uint32_t)i | ((uint32_t)tx << 8) | ((uint32_t)ty << 20));
+        }
+    V.s1s_tiles.clear();
+    for (int ty = 0; ty < (h + S1S_T - 1) / S1S_T; ++ty)
+        for (int tx = 0; tx < (w + S1S_T - 1) / S1S_T; ++tx) {
+            bool any = false;
+            for (int y = ty * S1S_T; y < std::min(h, (ty + 1) * S1S_T) && !any; ++y)
+                for (int x = tx * S1S_T; x < std::min(w, (tx + 1) * S1S_T); ++x) {
+                    const float fx = hx[(size_t)y * w + x], fy = hy[(size_t)y * w + x];
+                    if (fx >= -1.f && fx < (float)src_w && fy >= -1.f && fy < (float)src_h) { any = true; break; }
+                }
+            if (any) V.s1s_tiles.push_back((uint32_t)i | ((uint32_t)tx << 8) | ((uint32_t)ty << 20));
         }
     s->tiles_dirty = true;
     V.src_w = src_w; V.src_h = src_h; V.has_maps = true;
@@ -2314,21 +2634,36 @@ int vsb_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, siz
             for (int h = 0; h < MAX_SPLIT; ++h) {
                 CK(cudaStreamCreateWithFlags(&s->sub[h], cudaStreamNonBlocking));
                 CK(cudaEventCreateWithFlags(&s->ev_join[h], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&s->ev_forks[h], cudaEventDisableTiming));
             }
             CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
         }
-        s->f0 = 0;
-        r = launch_front(s, 0, n, n_frames, d_srcs, src_pitch, st, nullptr, FRONT_REMAP);
-        if (r != VSB_OK) return r;
-        CK(cudaEventRecord(s->ev_fork, st));
+        // VSB_STAGGER=1: the remap launches are split per sub-batch too and issued back to back on the caller's stream, so the
+        // remaps of sub-batch h + 1 overlap the pyramid / blend of sub-batch h (at the price of reading the tap tables once per
+        // sub-batch).  Default: one remap launch pair for the whole submission.
+        static const bool stagger = [] { const char *e = std::getenv("VSB_STAGGER"); return e && std::atoi(e) != 0; }();
+        if (!stagger) {
+            s->f0 = 0;
+            r = launch_front(s, 0, n, n_frames, d_srcs, src_pitch, st, nullptr, FRONT_REMAP);
+            if (r != VSB_OK) return r;
+            CK(cudaEventRecord(s->ev_fork, st));
+        }
         for (int h = 0; h < ns && r == VSB_OK; ++h) {
             const int b0 = n_frames * h / ns, b1 = n_frames * (h + 1) / ns;
-            CK(cudaStreamWaitEvent(s->sub[h], s->ev_fork, 0));
             s->f0 = b0;
+            if (stagger) {
+                r = launch_front(s, 0, n, b1 - b0, d_srcs + (size_t)b0 * n, src_pitch, st, nullptr, FRONT_REMAP);
+                if (r != VSB_OK) break;
+                CK(cudaEventRecord(s->ev_forks[h], st));
+                CK(cudaStreamWaitEvent(s->sub[h], s->ev_forks[h], 0));
+            } else {
+                CK(cudaStreamWaitEvent(s->sub[h], s->ev_fork, 0));
+            }
             r = launch_front(s, 0, n, b1 - b0, nullptr, src_pitch, s->sub[h], nullptr, FRONT_PYRAMID);
             if (r == VSB_OK) r = launch_back(s, b1 - b0, d_outs + b0, out_pitch, s->sub[h]);
-            if (r == VSB_OK) { CK(cudaEventRecord(s->ev_join[h], s->sub[h])); CK(cudaStreamWaitEvent(st, s->ev_join[h], 0)); }
+            if (r == VSB_OK) CK(cudaEventRecord(s->ev_join[h], s->sub[h]));
         }
+        for (int h = 0; h < ns && r == VSB_OK; ++h) CK(cudaStreamWaitEvent(st, s->ev_join[h], 0));
         s->f0 = 0;
         if (r != VSB_OK) return r;
         return note_compose_done(s, st);
@@ -2341,49 +2676,40 @@ int vsb_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, siz
     return note_compose_done(s, st);
 }
 
-int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs, size_t src_pitch, int16_t *const *h_outs, size_t out_pitch)
+// Host-buffer entry points (what A/timed.cpp:68 `upload` and the consumer thread's `download`, :252, do around the path).
+// vsb_submit_host enqueues ONE submission and returns: upload (copy engine, in_stream) -> compose (io_stream) -> download (second
+// copy engine, out_stream), pipelined over sub-batches of HOST_SUB frames -- sub-batch g + 1 uploads while g composes and g - 1
+// downloads -- and over submissions: up to HOST_DEPTH submissions are in flight, each with its own device staging, so the tail of
+// one (last compose + download) overlaps the head of the next (first uploads).  vsb_wait_host blocks until the OLDEST outstanding
+// submission's panoramas are in host memory (the reference hands results to its consumer through a queue the same way,
+// A/timed.cpp:150,243).  Composing sub-batches instead of single frames reads the remap tap tables once per sub-batch.
+static int host_stage_setup(vsb_stitcher *s, bool nv12, int sw, int sh, int src_rows, size_t out_pitch)
 {
-    REQ(s && h_srcs && h_outs, VSB_ERR_INVALID, "compose_host: null argument");
-    REQ(n_frames >= 1 && n_frames <= s->cfg.max_batch, VSB_ERR_INVALID, "compose_host: n_frames must be 1..max_batch (%d)", s->cfg.max_batch);
-    int r = ready_for_frames(s);
-    if (r != VSB_OK) return r;
-    DeviceGuard g(s->device);
     const int n = s->cfg.num_views, F = s->cfg.max_batch;
-    const int sw = s->v[0].src_w, sh = s->v[0].src_h;
-    for (int i = 1; i < n; ++i) REQ(s->v[i].src_w == sw && s->v[i].src_h == sh, VSB_ERR_INVALID, "compose_host: all views must share one source size");
-    const bool nv12 = s->in_format == VSB_IN_NV12;
-    const size_t opx = s->out_format == VSB_OUT_U8C3 ? 3 : 6;     // bytes per output pixel
-    const size_t src_row = nv12 ? (size_t)sw : (size_t)sw * 3;    // bytes per source row, rows per source frame
-    const int src_rows = nv12 ? sh * 3 / 2 : sh;
-    REQ(src_pitch >= src_row && out_pitch >= (size_t)s->roi_final[2] * opx, VSB_ERR_INVALID, "compose_host: pitch too small");
-    REQ(!nv12 || ((sw | sh) & 1) == 0, VSB_ERR_INVALID, "compose_host: NV12 needs even source sizes");
-    // device staging of the caller's frames, sized for (source size, views, max_batch) and re-made when any of them changes
-    // (vsb_set_maps may install a different camera resolution without vsb_prepare)
     if (s->stage_src_w != sw || s->stage_src_h != sh || s->stage_views != n || s->stage_batch != F) {
         CK(cudaDeviceSynchronize());
-        cudaFree(s->stage_src); cudaFree(s->stage_nv12);
-        s->stage_src = s->stage_nv12 = nullptr;
+        for (int d = 0; d < HOST_DEPTH; ++d) { cudaFree(s->stage_src[d]); cudaFree(s->stage_nv12[d]); s->stage_src[d] = s->stage_nv12[d] = nullptr; }
         s->stage_src_w = sw; s->stage_src_h = sh; s->stage_views = n; s->stage_batch = F;
     }
-    if (!nv12 && !s->stage_src) {
-        s->stage_src_pitch = align_up((size_t)sw * 3, 4);  // tight rows: a packed host frame moves as ONE contiguous DMA
-        s->stage_src_frame = align_up(s->stage_src_pitch * sh + 16, 256);
-        CK(cudaMalloc(&s->stage_src, s->stage_src_frame * n * F));
+    for (int d = 0; d < HOST_DEPTH; ++d) {
+        if (!nv12 && !s->stage_src[d]) {
+            s->stage_src_pitch = align_up((size_t)sw * 3, 4);  // tight rows: a packed host frame moves as ONE contiguous DMA
+            s->stage_src_frame = align_up(s->stage_src_pitch * sh + 16, 256);
+            CK(cudaMalloc(&s->stage_src[d], s->stage_src_frame * n * F));
+        }
+        if (nv12 && !s->stage_nv12[d]) {
+            s->stage_nv12_frame = align_up(align_up((size_t)sw, 4) * src_rows + 16, 256);
+            CK(cudaMalloc(&s->stage_nv12[d], s->stage_nv12_frame * n * F));
+        }
     }
-    if (nv12 && !s->stage_nv12) {
-        s->stage_nv12_frame = align_up(align_up((size_t)sw, 4) * src_rows + 16, 256);
-        CK(cudaMalloc(&s->stage_nv12, s->stage_nv12_frame * n * F));
-    }
-    const size_t st_pitch = nv12 ? align_up((size_t)sw, 4) : s->stage_src_pitch, st_frame = nv12 ? s->stage_nv12_frame : s->stage_src_frame;
-    uint8_t *st_base = nv12 ? s->stage_nv12 : s->stage_src;
     // the device-side panorama staging uses the HOST pitch, so each download is one contiguous DMA (a 2-D copy of 600+
     // rows whose pitches differ by a few bytes runs at a fraction of the link rate)
-    if (!s->stage_out || s->stage_out_pitch != out_pitch) {
+    if (!s->stage_out[0] || s->stage_out_pitch != out_pitch) {
         CK(cudaDeviceSynchronize());
-        cudaFree(s->stage_out); s->stage_out = nullptr;
+        for (int d = 0; d < HOST_DEPTH; ++d) { cudaFree(s->stage_out[d]); s->stage_out[d] = nullptr; }
         s->stage_out_pitch = out_pitch;
         s->stage_out_frame = align_up(out_pitch * s->roi_final[3], 256);
-        CK(cudaMalloc(&s->stage_out, s->stage_out_frame * F));
+        for (int d = 0; d < HOST_DEPTH; ++d) CK(cudaMalloc(&s->stage_out[d], s->stage_out_frame * F));
     }
     if (!s->in_stream) {
         CK(cudaStreamCreateWithFlags(&s->in_stream, cudaStreamNonBlocking));
@@ -2392,35 +2718,87 @@ int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs
             CK(cudaEventCreateWithFlags(&s->ev_in[f], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&s->ev_done[f], cudaEventDisableTiming));
         }
+        for (int d = 0; d < HOST_DEPTH; ++d) CK(cudaEventCreateWithFlags(&s->ev_host[d], cudaEventDisableTiming));
     }
-    // Three-stage pipeline over the frames of the submission: upload (copy engine, in_stream) -> compose (io_stream) ->
-    // download (second copy engine, out_stream).  Frame f+1 uploads while frame f composes and frame f-1 downloads.
-    // (The reference uploads pageable memory on the compute stream and downloads in the consumer thread, A/timed.cpp:68,252.)
-    for (int f = 0; f < n_frames; ++f) {
-        const uint8_t *d_srcs[MAXV];
-        for (int i = 0; i < n; ++i) {
-            uint8_t *d = st_base + st_frame * (size_t)(f * n + i);
-            if (src_pitch == st_pitch)
-                CK(cudaMemcpyAsync(d, h_srcs[f * n + i], src_pitch * src_rows, cudaMemcpyHostToDevice, s->in_stream));
-            else
-                CK(cudaMemcpy2DAsync(d, st_pitch, h_srcs[f * n + i], src_pitch, src_row, src_rows, cudaMemcpyHostToDevice, s->in_stream));
-            d_srcs[i] = d;
-        }
-        CK(cudaEventRecord(s->ev_in[f], s->in_stream));
-        CK(cudaStreamWaitEvent(s->io_stream, s->ev_in[f], 0));
-        int16_t *d_out = (int16_t *)((char *)s->stage_out + s->stage_out_frame * f);
-        r = vsb_compose(s, 1, d_srcs, st_pitch, &d_out, s->stage_out_pitch, s->io_stream);
-        if (r != VSB_OK) { cudaDeviceSynchronize(); return r; }
-        CK(cudaEventRecord(s->ev_done[f], s->io_stream));
-        CK(cudaStreamWaitEvent(s->out_stream, s->ev_done[f], 0));
-        if (out_pitch == (size_t)s->roi_final[2] * opx)  // packed host rows: one contiguous DMA
-            CK(cudaMemcpyAsync(h_outs[f], d_out, out_pitch * (size_t)s->roi_final[3], cudaMemcpyDeviceToHost, s->out_stream));
-        else                                              // padded host rows: leave the caller's padding untouched
-            CK(cudaMemcpy2DAsync(h_outs[f], out_pitch, d_out, s->stage_out_pitch, (size_t)s->roi_final[2] * opx, s->roi_final[3], cudaMemcpyDeviceToHost, s->out_stream));
-    }
-    CK(cudaStreamSynchronize(s->out_stream));
-    CK(cudaStreamSynchronize(s->io_stream));
     return VSB_OK;
+}
+
+int vsb_wait_host(vsb_stitcher *s)
+{
+    REQ(s, VSB_ERR_INVALID, "wait_host: null handle");
+    REQ(s->host_pending > 0, VSB_ERR_STATE, "wait_host: no submission outstanding");
+    DeviceGuard g(s->device);
+    const int d = (int)((s->host_seq - (unsigned)s->host_pending) % HOST_DEPTH);
+    CK(cudaEventSynchronize(s->ev_host[d]));
+    --s->host_pending;
+    return VSB_OK;
+}
+
+int vsb_submit_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs, size_t src_pitch, int16_t *const *h_outs, size_t out_pitch)
+{
+    REQ(s && h_srcs && h_outs, VSB_ERR_INVALID, "submit_host: null argument");
+    REQ(n_frames >= 1 && n_frames <= s->cfg.max_batch, VSB_ERR_INVALID, "submit_host: n_frames must be 1..max_batch (%d)", s->cfg.max_batch);
+    int r = ready_for_frames(s);
+    if (r != VSB_OK) return r;
+    DeviceGuard g(s->device);
+    const int n = s->cfg.num_views;
+    const int sw = s->v[0].src_w, sh = s->v[0].src_h;
+    for (int i = 1; i < n; ++i) REQ(s->v[i].src_w == sw && s->v[i].src_h == sh, VSB_ERR_INVALID, "submit_host: all views must share one source size");
+    const bool nv12 = s->in_format == VSB_IN_NV12;
+    const size_t opx = s->out_format == VSB_OUT_U8C3 ? 3 : 6;     // bytes per output pixel
+    const size_t src_row = nv12 ? (size_t)sw : (size_t)sw * 3;    // bytes per source row, rows per source frame
+    const int src_rows = nv12 ? sh * 3 / 2 : sh;
+    REQ(src_pitch >= src_row && out_pitch >= (size_t)s->roi_final[2] * opx, VSB_ERR_INVALID, "submit_host: pitch too small");
+    REQ(!nv12 || ((sw | sh) & 1) == 0, VSB_ERR_INVALID, "submit_host: NV12 needs even source sizes");
+    while (s->host_pending >= HOST_DEPTH) { r = vsb_wait_host(s); if (r != VSB_OK) return r; }  // this slot's staging is still in use
+    r = host_stage_setup(s, nv12, sw, sh, src_rows, out_pitch);
+    if (r != VSB_OK) return r;
+    const int d = (int)(s->host_seq % HOST_DEPTH);
+    const size_t st_pitch = nv12 ? align_up((size_t)sw, 4) : s->stage_src_pitch, st_frame = nv12 ? s->stage_nv12_frame : s->stage_src_frame;
+    uint8_t *st_base = nv12 ? s->stage_nv12[d] : s->stage_src[d];
+    static const int host_sub = [] { const char *e = std::getenv("VSB_HOST_SUB"); return e ? std::max(1, std::min(MAX_BATCH, std::atoi(e))) : HOST_SUB; }();
+    for (int f0 = 0, gidx = 0; f0 < n_frames; f0 += host_sub, ++gidx) {
+        const int nf = std::min(host_sub, n_frames - f0);
+        const uint8_t *d_srcs[MAX_BATCH * MAXV];
+        int16_t *d_outs[MAX_BATCH];
+        for (int f = f0; f < f0 + nf; ++f) {
+            for (int i = 0; i < n; ++i) {
+                uint8_t *dd = st_base + st_frame * (size_t)(f * n + i);
+                if (src_pitch == st_pitch)
+                    CK(cudaMemcpyAsync(dd, h_srcs[f * n + i], src_pitch * src_rows, cudaMemcpyHostToDevice, s->in_stream));
+                else
+                    CK(cudaMemcpy2DAsync(dd, st_pitch, h_srcs[f * n + i], src_pitch, src_row, src_rows, cudaMemcpyHostToDevice, s->in_stream));
+                d_srcs[(f - f0) * n + i] = dd;
+            }
+            d_outs[f - f0] = (int16_t *)((char *)s->stage_out[d] + s->stage_out_frame * f);
+        }
+        CK(cudaEventRecord(s->ev_in[gidx], s->in_stream));
+        CK(cudaStreamWaitEvent(s->io_stream, s->ev_in[gidx], 0));
+        r = vsb_compose(s, nf, d_srcs, st_pitch, d_outs, s->stage_out_pitch, s->io_stream);
+        if (r != VSB_OK) { cudaDeviceSynchronize(); return r; }
+        CK(cudaEventRecord(s->ev_done[gidx], s->io_stream));
+        CK(cudaStreamWaitEvent(s->out_stream, s->ev_done[gidx], 0));
+        for (int f = f0; f < f0 + nf; ++f) {
+            if (out_pitch == (size_t)s->roi_final[2] * opx)  // packed host rows: one contiguous DMA
+                CK(cudaMemcpyAsync(h_outs[f], d_outs[f - f0], out_pitch * (size_t)s->roi_final[3], cudaMemcpyDeviceToHost, s->out_stream));
+            else                                              // padded host rows: leave the caller's padding untouched
+                CK(cudaMemcpy2DAsync(h_outs[f], out_pitch, d_outs[f - f0], s->stage_out_pitch, (size_t)s->roi_final[2] * opx, s->roi_final[3], cudaMemcpyDeviceToHost, s->out_stream));
+        }
+    }
+    CK(cudaEventRecord(s->ev_host[d], s->out_stream));
+    // the next submission's uploads reuse the OTHER staging set; this one is reused two submissions from now, after its wait
+    ++s->host_seq;
+    ++s->host_pending;
+    return VSB_OK;
+}
+
+int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs, size_t src_pitch, int16_t *const *h_outs, size_t out_pitch)
+{
+    REQ(s, VSB_ERR_INVALID, "compose_host: null handle");
+    while (s->host_pending > 0) { int r = vsb_wait_host(s); if (r != VSB_OK) return r; }
+    int r = vsb_submit_host(s, n_frames, h_srcs, src_pitch, h_outs, out_pitch);
+    if (r != VSB_OK) return r;
+    return vsb_wait_host(s);
 }
 
 
@@ -2433,7 +2811,7 @@ int vsb_compose_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs
 // tiles that touch its strip widened by that margin (the neighbour computes the same tile for itself).
 static bool coarse_tile_of_rank(const vsb_stitcher *s, int tx, int rank)
 {
-    const int unit = vsb::CT * 4, x0 = rank * s->strip_w - 8, x1 = std::min((rank + 1) * s->strip_w, s->cw[0]) + 8;
+    const int unit = s->ct * 4, x0 = rank * s->strip_w - 8, x1 = std::min((rank + 1) * s->strip_w, s->cw[0]) + 8;
     return tx * unit < x1 && (tx + 1) * unit > x0;
 }
 
@@ -2445,7 +2823,7 @@ int vsb_shard_set(vsb_stitcher *s, int rank, int world)
     DeviceGuard g(s->device);
     CK(cudaDeviceSynchronize());
     const int n = s->cfg.num_views, cw0 = s->cw[0];
-    const int unit = CT * 4;  // k_coarse tiles are 256 level-0 columns wide
+    const int unit = 256;  // strips are multiples of 256 level-0 columns (whole k_coarse tiles at either tile size)
     s->strip_w = (int)(align_up((size_t)(cw0 + world - 1) / world, unit));
     s->shard_rank = rank; s->shard_world = world;
     for (int i = 0; i < n; ++i) {
@@ -2505,7 +2883,7 @@ int vsb_shard_rect(const vsb_stitcher *s, int dst_rank, int view, int level, int
         for (int ty = 0; ty < s->coarse_tiles_y; ++ty)
             for (int tx = 0; tx < s->coarse_tiles_x; ++tx) {
                 if (!coarse_tile_of_rank(s, tx, dst_rank) || !(s->h_cviews[(size_t)ty * s->coarse_tiles_x + tx] >> view & 1)) continue;
-                add(((tx * CT) >> j) + s->cgeo.a_lo[j] - (V.x_tl >> level), ((ty * CT) >> j) + s->cgeo.a_lo[j] - (V.y_tl >> level), s->cgeo.a_n[j], s->cgeo.a_n[j]);
+                add(((tx * s->ct) >> j) + s->cgeo.a_lo[j] - (V.x_tl >> level), ((ty * s->ct) >> j) + s->cgeo.a_lo[j] - (V.y_tl >> level), s->cgeo.a_n[j], s->cgeo.a_n[j]);
             }
     }
     if (x0 > x1) { rect[0] = rect[1] = rect[2] = rect[3] = 0; return VSB_OK; }
