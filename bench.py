@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch F] [--workload cfg2] [--impl ours|reference]
 
-A step = one vsb_compose submission of F frames (default 8) of the workload (BASELINE.json configs[1]: 6 x 1080p ->
+A step = one vsb_compose submission of F frames (default 16) of the workload (BASELINE.json configs[1]: 6 x 1080p ->
 3840-wide spherical panorama, CPW mesh remap on, 5-band blend).  Source frames live in a ring of frame sets larger than
 L2, so every step reads its inputs from HBM.
   value        frames/s with inputs resident in HBM; CUDA events on the launching stream; max over ranks
@@ -274,7 +274,7 @@ def run_sharded(args, cfg, rank, world, local_rank):
         dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29655", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
     n, K, W_, F = cfg["n_views"], args.steps, max(args.warmup, 3), max(1, args.batch)
     parity = sharded_parity_check(dist, torch, rank, world)
-    st, info = make_rig(cfg, 2 * F if 2 * F <= 8 else F)  # two submissions in flight when both fit the handle's frame slots (max 8)
+    st, info = make_rig(cfg, 2 * F if 2 * F <= 16 else F)  # two submissions in flight when both fit the handle's frame slots (max 16)
     st.shard_init(rank, world, shard_unique_id(dist, rank))
     roi, _, nb = st.get_roi()
     OW, OH = roi[2], roi[3]
@@ -341,8 +341,9 @@ def run_sharded(args, cfg, rank, world, local_rank):
     # ---- e2e: pinned host frames of the owned views in, this rank's strip of the host panorama out, every step
     e2e = None
     if not args.no_e2e:
-        h_out = [torch.zeros((OH, OW * 3), dtype=torch.int16).pin_memory() for _ in range(F)]
-        xe = min(x1, OW)  # the strip is cut from the padded canvas; the panorama ends at OW
+        xe = max(x0, min(x1, OW))  # the strip is cut from the padded canvas; the panorama ends at OW
+        h_out = [torch.zeros((OH, 3 * (xe - x0)), dtype=torch.int16).pin_memory() for _ in range(F)]
+        strip_dev = [torch.zeros((OH, 3 * (xe - x0)), dtype=torch.int16, device="cuda") for _ in range(F)]
         stage = [[torch.empty_like(host_sets[0][i], device="cuda") if i in owned else None for i in range(n)] for _ in range(F)]
         e2e_call = st.make_shard_compose_call([(stage[j][i].data_ptr() if i in owned else 0) for j in range(F) for i in range(n)], cfg["src_w"] * 3,
                                               [o.data_ptr() for o in outs[0]], out_pitch, main.cuda_stream)
@@ -351,8 +352,9 @@ def run_sharded(args, cfg, rank, world, local_rank):
                 for i in owned:
                     stage[j][i].copy_(host_sets[(k * F + j) % n_sets][i], non_blocking=True)
             e2e_call()
-            for j in range(F):
-                h_out[j][:, 3 * x0:3 * xe].copy_(outs[0][j][:, 3 * x0:3 * xe], non_blocking=True)
+            for j in range(F):  # the strip leaves as ONE contiguous DMA (a strided 2-D copy runs at a fraction of the link rate)
+                strip_dev[j].copy_(outs[0][j][:, 3 * x0:3 * xe])
+                h_out[j].copy_(strip_dev[j], non_blocking=True)
         for w in range(2):
             host_step(w)
         Ke = max(3, min(K, 20))
@@ -453,7 +455,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--batch", type=int, default=8, help="frames per vsb_compose submission (F)")
+    ap.add_argument("--batch", type=int, default=16, help="frames per vsb_compose submission (F; default 16 = the handle's frame slots)")
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
                     help="default: cfg2 on one GPU; view-sharded runs take the configurations BASELINE.json names for N GPUs "
                          "(cfg3 = 7680-wide on 2 and 4, cfg4 = 12 x 4K -> 15360 on 8)")
@@ -476,7 +478,7 @@ def main():
     if args.workload is None:
         args.workload = "cfg2" if (world == 1 or args.mode == "replicas") else ("cfg4" if world >= 8 else "cfg3")
     if args.mode == "shard" and not batch_given:
-        args.batch = 2 if args.workload == "cfg4" else 4  # two submissions in flight: 2 x batch frame slots
+        args.batch = 2 if args.workload == "cfg4" else 8  # two submissions in flight: 2 x batch frame slots (16 at most)
     cfg = WORKLOADS[args.workload]
 
     if args.impl == "reference":

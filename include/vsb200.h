@@ -101,6 +101,27 @@ int vsb_rig_camera(int n_views, int i, int src_w, int src_h, double hfov_deg, fl
 int vsb_voronoi_seams(int n, const int *sizes_wh, const int *corners_xy, uint8_t *const *masks);
 int vsb_calibrate_rig(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg,
                       const float *gains);
+/* ---- the same calibration with every per-pixel loop on the DEVICE (the reference runs these stages on the GPU
+ *      too, A/calibration.cpp:92-246): projection maps (buildWarp*Maps), mask warps, VoronoiSeamFinder, dilate / cuda::resize /
+ *      bitwise_and, weight pyramids.  ROIs stay on the host (as RotationWarperBase::detectResultRoi does in the reference).  Maps
+ *      agree with vsb_calibrate_rig to ~1e-3 px (device sinf / cosf), everything downstream of the maps is exact.  Keeps the
+ *      seam-scale state vsb_estimate_gains needs. -------------------------------------------------------------------------- */
+int vsb_calibrate_rig_device(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg,
+                             const float *gains);
+/* GainCompensator::feed (S/src/exposure_compensate.cpp:71-142) at run time: the n camera frames (device, CV_8UC3) are resized to
+ * seam scale and warped like A/calibration.cpp:95,118, the pairwise overlap statistics are reduced on the device in the
+ * reference's summation order, the n x n system is solved on the host (hal::LU64f restated).  n >= 4.  apply != 0 installs the
+ * gains for the following frames (the reference's docx lists "dynamically update the gain compensation" as an open TODO). */
+int vsb_estimate_gains(vsb_stitcher *s, const uint8_t *const *d_frames, size_t pitch_bytes, float *gains_out, int apply, void *stream);
+/* the building blocks, on device buffers: VoronoiSeamFinder::find (S/src/seam_finders.cpp:72-162; masks modified in place),
+ * MORPH_DILATE 3x3 (A/calibration.cpp:209,232), cuda::resize INTER_LINEAR on CV_8UC1 / CV_8UC3 (fx = fy = 0: factors from the
+ * sizes; CW/src/resize.cpp:76-105), GainCompensator::feed on warped images (tight rows; gains as float64) */
+int vsb_voronoi_seams_device(int n, const int *sizes_wh, const int *corners_xy, uint8_t *const *d_masks, void *stream);
+int vsb_dilate3x3_u8(const uint8_t *d_src, int w, int h, uint8_t *d_dst, void *stream);
+int vsb_resize_linear_u8(const uint8_t *d_src, int sw, int sh, size_t src_pitch, int channels, uint8_t *d_dst, int dw, int dh,
+                         size_t dst_pitch, double fx, double fy, void *stream);
+int vsb_gain_compensator_feed(int n, const uint8_t *const *d_imgs, const uint8_t *const *d_masks, const int *sizes_wh,
+                              const int *corners_xy, double *gains_out, void *stream);
 int vsb_rig_info_get(const vsb_stitcher *s, vsb_rig_info *out);
 int vsb_get_config(const vsb_stitcher *s, vsb_config *out);
 
@@ -228,7 +249,8 @@ int vsb_normalize_32f(const float *d_w, size_t w_pitch, int16_t *d_src, size_t s
 /* ---- introspection for parity tests: copy an internal buffer of frame slot `frame` to host.
  *      what: 0 = warped view Q (u8x3 interleaved, roi size), 1 = Gaussian level k (s16x3 interleaved, k>=0,
  *      bordered size >> k), 2 = weight level k (f32), 3 = canvas weight sum level k (f32, view ignored),
- *      4 = x mesh map (f32, roi size), 5 = y mesh map. `bytes` must match exactly. ---------------------- */
+ *      4 = x mesh map (f32, roi size), 5 = y mesh map, 8 = x projection map, 9 = y projection map (f32, roi size).
+ *      `bytes` must match exactly. ------------------------------------------------------------------------- */
 int vsb_debug_read(vsb_stitcher *s, int what, int view, int level, int frame, void *h_dst, size_t bytes);
 
 #ifdef __cplusplus

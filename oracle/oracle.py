@@ -130,6 +130,32 @@ def remap_u8(src, xmap, ymap, interp=INTER_LINEAR, border=BORDER_CONSTANT):
     return dst
 
 
+def cuda_resize_linear_u8(src, dw, dh, fx=0.0, fy=0.0):
+    """cuda::resize INTER_LINEAR (CV_8UC1 / CV_8UC3); fx = fy = 0: factors from the sizes, else the explicit-scale form."""
+    src = np.ascontiguousarray(src, np.uint8)
+    cn = 1 if src.ndim == 2 else src.shape[2]
+    sh, sw = src.shape[:2]
+    dst = np.empty((dh, dw) if src.ndim == 2 else (dh, dw, cn), np.uint8)
+    lib().og_cuda_resize_linear_u8(_p(src, C.c_uint8), sw, sh, cn, _p(dst, C.c_uint8), dw, dh, C.c_double(fx), C.c_double(fy))
+    return dst
+
+
+def gain_compensator_feed(imgs, masks, corners_xy, sizes_wh):
+    """GainCompensator::feed on warped CV_8UC3 images + CV_8U masks: returns the gains (float64, n >= 4)."""
+    n = len(imgs)
+    imgs = [np.ascontiguousarray(a, np.uint8) for a in imgs]
+    masks = [np.ascontiguousarray(a, np.uint8) for a in masks]
+    ip = (C.POINTER(C.c_uint8) * n)(*[_p(a, C.c_uint8) for a in imgs])
+    mp = (C.POINTER(C.c_uint8) * n)(*[_p(a, C.c_uint8) for a in masks])
+    sz = (C.c_int * (2 * n))(*[int(v) for p in sizes_wh for v in p])
+    co = (C.c_int * (2 * n))(*[int(v) for p in corners_xy for v in p])
+    g = np.zeros(n, np.float64)
+    rc = lib().og_gain_compensator_feed(n, ip, mp, sz, co, _p(g, C.c_double))
+    if rc != 0:
+        raise ValueError("gain_compensator_feed: singular system or fewer than 4 views")
+    return g
+
+
 def gain_u8(img, gain):
     out = np.ascontiguousarray(img, np.uint8).copy()
     lib().og_gain_u8(_p(out, C.c_uint8), C.c_size_t(out.size), C.c_float(gain))

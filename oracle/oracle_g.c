@@ -441,6 +441,98 @@ void og_resize_linear_u8c1(const uint8_t *src, int sw, int sh, uint8_t *dst, int
         }
 }
 
+/* cuda::resize INTER_LINEAR on CV_8UC1 / CV_8UC3 with explicit scale factors (CW/src/resize.cpp:76-105, CW/src/cuda/resize.cu:71-106):
+ * fx = fy = 0 derives them from the sizes (dsize given); the application resizes the camera frames to seam scale with
+ * cuda::resize(img, seam_img, Size(), seam_scale, seam_scale, INTER_LINEAR) (360_stitcher/calibration.cpp:95). */
+void og_cuda_resize_linear_u8(const uint8_t *src, int sw, int sh, int cn, uint8_t *dst, int dw, int dh, double fx, double fy)
+{
+    if (!(fx > 0) || !(fy > 0)) { fx = (double)dw / sw; fy = (double)dh / sh; }
+    if (dw == sw && dh == sh) { memcpy(dst, src, (size_t)sw * sh * cn); return; }
+    const float kx = (float)(1.0 / fx), ky = (float)(1.0 / fy);
+    for (int dy = 0; dy < dh; ++dy)
+        for (int dx = 0; dx < dw; ++dx) {
+            float src_x = (float)dx * kx, src_y = (float)dy * ky;
+            int x1 = f2i_rd(src_x), y1 = f2i_rd(src_y);
+            int x2 = x1 + 1, y2 = y1 + 1;
+            int x2r = x2 < sw - 1 ? x2 : sw - 1, y2r = y2 < sh - 1 ? y2 : sh - 1;
+            for (int c = 0; c < cn; ++c) {
+                float out = fmaf((float)src[((size_t)y1 * sw + x1) * cn + c], ((float)x2 - src_x) * ((float)y2 - src_y), 0.f);
+                out = fmaf((float)src[((size_t)y1 * sw + x2r) * cn + c], (src_x - (float)x1) * ((float)y2 - src_y), out);
+                out = fmaf((float)src[((size_t)y2r * sw + x1) * cn + c], ((float)x2 - src_x) * (src_y - (float)y1), out);
+                out = fmaf((float)src[((size_t)y2r * sw + x2r) * cn + c], (src_x - (float)x1) * (src_y - (float)y1), out);
+                dst[((size_t)dy * dw + dx) * cn + c] = rni_sat_u8(out);
+            }
+        }
+}
+
+/* GainCompensator::feed (S/src/exposure_compensate.cpp:71-142): pairwise overlap counts N and mean intensities I (double sums of
+ * sqrt(b^2 + g^2 + r^2) in row-major order over the overlap, masks == 255), then A g = b with alpha = 0.01, beta = 100, solved by
+ * cv::solve(DECOMP_LU) = hal::LU64f (CORE/src/matrix_decomp.cpp:52-107) for n >= 4.  Returns 0, or -1 for a singular system / n < 4. */
+int og_gain_compensator_feed(int n, const uint8_t *const *imgs, const uint8_t *const *masks, const int *sizes, const int *corners, double *gains)
+{
+    if (n < 4 || n > 64) return -1;
+    int *N = (int *)calloc((size_t)n * n, sizeof(int));
+    double *I = (double *)calloc((size_t)n * n, sizeof(double)), *A = (double *)calloc((size_t)n * n, sizeof(double));
+    for (int i = 0; i < n; ++i)
+        for (int j = i; j < n; ++j) {
+            const int wi = sizes[2 * i], hi = sizes[2 * i + 1], wj = sizes[2 * j], hj = sizes[2 * j + 1];
+            const int xi = corners[2 * i], yi = corners[2 * i + 1], xj = corners[2 * j], yj = corners[2 * j + 1];
+            const int x_tl = xi > xj ? xi : xj, y_tl = yi > yj ? yi : yj;
+            const int x_br = xi + wi < xj + wj ? xi + wi : xj + wj, y_br = yi + hi < yj + hj ? yi + hi : yj + hj;
+            if (!(x_tl < x_br && y_tl < y_br)) continue;
+            int cnt = 0;
+            double s1 = 0, s2 = 0;
+            for (int y = y_tl; y < y_br; ++y)
+                for (int x = x_tl; x < x_br; ++x) {
+                    const size_t o1 = (size_t)(y - yi) * wi + (x - xi), o2 = (size_t)(y - yj) * wj + (x - xj);
+                    if (masks[i][o1] != 255 || masks[j][o2] != 255) continue;
+                    ++cnt;
+                    const uint8_t *p = imgs[i] + o1 * 3, *q = imgs[j] + o2 * 3;
+                    s1 += sqrt((double)(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));
+                    s2 += sqrt((double)(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]));
+                }
+            const int nn = cnt > 1 ? cnt : 1;
+            N[i * n + j] = N[j * n + i] = nn;
+            I[i * n + j] = s1 / nn;
+            I[j * n + i] = s2 / nn;
+        }
+    const double alpha = 0.01, beta = 100;
+    for (int i = 0; i < n; ++i) gains[i] = 0;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            gains[i] += beta * N[i * n + j];
+            A[i * n + i] += beta * N[i * n + j];
+            if (j == i) continue;
+            A[i * n + i] += 2 * alpha * I[i * n + j] * I[i * n + j] * N[i * n + j];
+            A[i * n + j] -= 2 * alpha * I[i * n + j] * I[j * n + i] * N[i * n + j];
+        }
+    int ok = 0;
+    const double eps = 2.220446049250313e-16 * 100;
+    for (int i = 0; i < n && ok == 0; ++i) {  /* LUImpl: partial pivoting, d = -1 / pivot */
+        int k = i;
+        for (int j = i + 1; j < n; ++j) if (fabs(A[j * n + i]) > fabs(A[k * n + i])) k = j;
+        if (fabs(A[k * n + i]) < eps) { ok = -1; break; }
+        if (k != i) {
+            for (int j = i; j < n; ++j) { double t = A[i * n + j]; A[i * n + j] = A[k * n + j]; A[k * n + j] = t; }
+            double t = gains[i]; gains[i] = gains[k]; gains[k] = t;
+        }
+        const double d = -1 / A[i * n + i];
+        for (int j = i + 1; j < n; ++j) {
+            const double al = A[j * n + i] * d;
+            for (int q = i + 1; q < n; ++q) A[j * n + q] += al * A[i * n + q];
+            gains[j] += al * gains[i];
+        }
+    }
+    if (ok == 0)
+        for (int i = n - 1; i >= 0; --i) {
+            double s = gains[i];
+            for (int q = i + 1; q < n; ++q) s -= A[i * n + q] * gains[q];
+            gains[i] = s / A[i * n + i];
+        }
+    free(N); free(I); free(A);
+    return ok;
+}
+
 /* cuda::createMorphologyFilter(MORPH_DILATE, CV_8U, Mat(), {-1,-1}, 1): 3x3 rect max, border REFLECT_101
  * (sources/modules/cudafilters/src/filtering.cpp:543-606; A/calibration.cpp:209,232) */
 void og_dilate3x3_u8c1(const uint8_t *src, int w, int h, uint8_t *dst)

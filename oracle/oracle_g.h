@@ -40,6 +40,8 @@ void og_remap_nearest_u8c1(const uint8_t *src, int sw, int sh, size_t sstep,
 void og_remap_u8_border(const uint8_t *src, int sw, int sh, int cn, size_t sstep, const float *xmap, const float *ymap, size_t mstep,
                         uint8_t *dst, int dw, int dh, size_t dstep, int interp, int border);
 void og_gain_u8(uint8_t *buf, size_t n, float gain);
+void og_cuda_resize_linear_u8(const uint8_t *src, int sw, int sh, int cn, uint8_t *dst, int dw, int dh, double fx, double fy);
+int og_gain_compensator_feed(int n, const uint8_t *const *imgs, const uint8_t *const *masks, const int *sizes, const int *corners, double *gains);
 void og_resize_linear_u8c1(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh);
 void og_dilate3x3_u8c1(const uint8_t *src, int w, int h, uint8_t *dst);
 

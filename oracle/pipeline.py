@@ -49,6 +49,7 @@ class OracleRig:
         seam_warp_scale = np.float32(float(self.scale) * seam_scale)
         swa = np.float32(seam_scale)
         seam_masks, seam_corners, seam_sizes = [], [], []
+        self.seam_scale, self.seam_size, self.seam_maps = seam_scale, (seam_w, seam_h), []
         ones = np.full((seam_h, seam_w), 255, np.uint8)
         for i in range(n_views):
             Ks = self.K[i].copy()
@@ -57,6 +58,8 @@ class OracleRig:
             xm, ym = og.build_maps(projection, seam_warp_scale, Ks, self.R[i], *roi)
             seam_masks.append(og.remap_nearest_u8c1(ones, xm, ym))
             seam_corners.append(roi[:2]); seam_sizes.append(roi[2:])
+            self.seam_maps.append((xm, ym))
+        self.seam_warped_masks = [m.copy() for m in seam_masks]  # what the exposure compensator gets (before the seam finder)
         og.voronoi_find(seam_sizes, seam_corners, seam_masks)
         self.seam_masks, self.seam_corners, self.seam_sizes = seam_masks, seam_corners, seam_sizes
 
@@ -79,6 +82,37 @@ class OracleRig:
         self.mesh_maps = [None] * n_views
         self.roi_final, self.roi_padded = self.blender.dst_roi()
         self.num_bands = self.blender.num_bands
+
+    @classmethod
+    def from_products(cls, src_w, src_h, corners, sizes, xmaps, ymaps, masks, num_bands=5, enable_local=True, gains=None):
+        """A rig whose static inputs come from elsewhere (e.g. read back from vsb_calibrate_rig_device): only the blender geometry
+        and weight pyramids are derived here (prepare + init_gpu)."""
+        self = cls.__new__(cls)
+        n = len(corners)
+        self.n, self.src_w, self.src_h = n, src_w, src_h
+        self.enable_local = enable_local
+        self.gains = [1.0] * n if gains is None else [float(g) for g in gains]
+        self.corners, self.sizes = [tuple(c) for c in corners], [tuple(z) for z in sizes]
+        self.blender = og.Blender(num_bands)
+        self.blender.prepare(self.corners, self.sizes)
+        self.xmaps, self.ymaps, self.masks = list(xmaps), list(ymaps), list(masks)
+        for i in range(n):
+            self.blender.init_view(self.masks[i], self.corners[i])
+        self.mesh_maps = [None] * n
+        self.roi_final, self.roi_padded = self.blender.dst_roi()
+        self.num_bands = self.blender.num_bands
+        return self
+
+    def estimate_gains(self, frames, seam_maps=None):
+        """GainCompensator::feed as the application drives it (calibration.cpp:95,118,131): frames -> cuda::resize to seam scale ->
+        warp LINEAR / BORDER_REFLECT with the seam-scale maps -> feed with the warped all-255 masks.  Returns float64 gains."""
+        seam_w, seam_h = self.seam_size
+        maps = self.seam_maps if seam_maps is None else seam_maps
+        imgs = []
+        for i in range(self.n):
+            small = og.cuda_resize_linear_u8(frames[i], seam_w, seam_h, self.seam_scale, self.seam_scale)
+            imgs.append(og.remap_u8(small, maps[i][0], maps[i][1], og.INTER_LINEAR, og.BORDER_REFLECT))
+        return og.gain_compensator_feed(imgs, self.seam_warped_masks, self.seam_corners, self.seam_sizes)
 
     def set_mesh(self, i, mesh_x, mesh_y):
         w, h = self.sizes[i]

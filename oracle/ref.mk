@@ -28,7 +28,7 @@ CORE_SRCS := $(filter-out $(addprefix $(MOD)/core/src/,$(CORE_SKIP)),$(wildcard 
              $(wildcard $(MOD)/core/src/utils/*.cpp)
 IMG_SKIP  := imgwarp.avx2.cpp imgwarp.sse4_1.cpp resize.avx2.cpp resize.sse4_1.cpp undistort.avx2.cpp filter.avx2.cpp corner.avx.cpp accum.cpp accum.dispatch.cpp
 IMG_SRCS  := $(filter-out $(addprefix $(MOD)/imgproc/src/,$(IMG_SKIP)),$(wildcard $(MOD)/imgproc/src/*.cpp))
-ST_SRCS   := $(addprefix $(MOD)/stitching/src/,warpers.cpp seam_finders.cpp util.cpp camera.cpp)
+ST_SRCS   := $(addprefix $(MOD)/stitching/src/,warpers.cpp seam_finders.cpp util.cpp camera.cpp exposure_compensate.cpp)
 
 CORE_OBJS := $(patsubst $(MOD)/core/src/%.cpp,$(OBJ)/core/%.o,$(CORE_SRCS))
 IMG_OBJS  := $(patsubst $(MOD)/imgproc/src/%.cpp,$(OBJ)/imgproc/%.o,$(IMG_SRCS))

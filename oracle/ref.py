@@ -107,6 +107,20 @@ def remap_gold_u8(src, xmap, ymap):
     return dst
 
 
+def gain_compensator_feed(imgs, masks, corners_xy, sizes_wh):
+    """The reference's own GainCompensator::feed + gains() (exposure_compensate.cpp:71-142) on warped CV_8UC3 images / CV_8U masks."""
+    n = len(imgs)
+    imgs = [np.ascontiguousarray(a, np.uint8) for a in imgs]
+    masks = [np.ascontiguousarray(a, np.uint8) for a in masks]
+    ip = (C.c_void_p * n)(*[a.ctypes.data for a in imgs])
+    mp = (C.c_void_p * n)(*[a.ctypes.data for a in masks])
+    sz = (C.c_int * (2 * n))(*[int(v) for p in sizes_wh for v in p])
+    co = (C.c_int * (2 * n))(*[int(v) for p in corners_xy for v in p])
+    g = np.zeros(n, np.float64)
+    lib().vr_gain_compensator_feed(n, ip, mp, sz, co, g.ctypes.data_as(C.c_void_p))
+    return g
+
+
 def copy_make_border(src, t, top, bottom, left, right, reflect=True):
     src = _typed(src, t)
     h, w = src.shape[:2]

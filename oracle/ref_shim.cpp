@@ -18,6 +18,7 @@
  */
 #include <opencv2/core.hpp>
 #include <opencv2/imgproc.hpp>
+#include <opencv2/stitching/detail/exposure_compensate.hpp>
 #include <opencv2/stitching/detail/seam_finders.hpp>
 #include <opencv2/stitching/detail/util.hpp>
 #include <opencv2/stitching/detail/warpers.hpp>
@@ -163,6 +164,24 @@ void vr_remap_gold_u8(const uint8_t *src, int sw, int sh, int cn, const float *x
         for (int x = 0; x < dw; ++x)
             for (int c = 0; c < cn; ++c)
                 d.at<uchar>(y, x * cn + c) = LinearInterpolator<uchar>::getValue(s, ym.at<float>(y, x), xm.at<float>(y, x), c, BORDER_CONSTANT, Scalar());
+}
+/* the reference's own GainCompensator::feed + gains() (S/src/exposure_compensate.cpp:71-142,162-168), compiled from its source:
+ * imgs[i] CV_8UC3 / masks[i] CV_8U (255 = valid) of sizes_wh[i] at corners_xy[i] */
+void vr_gain_compensator_feed(int n, const uint8_t *const *imgs, const uint8_t *const *masks, const int *sizes_wh, const int *corners_xy, double *gains)
+{
+    std::vector<Point> corners(n);
+    std::vector<UMat> images(n);
+    std::vector<std::pair<UMat, uchar> > ms(n);
+    for (int i = 0; i < n; ++i) {
+        corners[i] = Point(corners_xy[2 * i], corners_xy[2 * i + 1]);
+        Mat(sizes_wh[2 * i + 1], sizes_wh[2 * i], CV_8UC3, const_cast<uint8_t *>(imgs[i])).copyTo(images[i]);
+        Mat(sizes_wh[2 * i + 1], sizes_wh[2 * i], CV_8U, const_cast<uint8_t *>(masks[i])).copyTo(ms[i].first);
+        ms[i].second = 255;
+    }
+    detail::GainCompensator comp;
+    comp.feed(corners, images, ms);
+    const std::vector<double> g = comp.gains();
+    for (int i = 0; i < n; ++i) gains[i] = g[i];
 }
 void vr_copy_make_border(const void *src, int w, int h, int type, int top, int bottom, int left, int right, int reflect, void *dst)
 {

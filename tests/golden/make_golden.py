@@ -67,6 +67,16 @@ def remap_test_recipe(size=(128, 128), seed=5):
     return src, xm, ym
 
 
+def gain_input(seed=23, n=6):
+    """Warped-image-like inputs of GainCompensator::feed: n overlapping CV_8UC3 images + CV_8U masks (255 = valid) on a ring."""
+    rng = np.random.default_rng(seed)
+    sizes = [(40 + 3 * i, 30 + i) for i in range(n)]
+    corners = [(25 * i, 2 * (i % 3)) for i in range(n)]
+    imgs = [np.clip(rng.integers(0, 256, (h, w, 3)) * (0.8 + 0.08 * i), 0, 255).astype(np.uint8) for i, (w, h) in enumerate(sizes)]
+    masks = [np.where(rng.random((h, w)) < 0.9, 255, 0).astype(np.uint8) for (w, h) in sizes]
+    return imgs, masks, corners, sizes
+
+
 def nv12_input(w=64, h=48, seed=17):
     """Random NV12 frame (Y plane then interleaved UV) covering the full byte range, incl. the saturating branches."""
     rng = np.random.default_rng(seed)
@@ -204,6 +214,10 @@ def main():
         for i in range(2):
             for k in range(b.num_bands + 1):
                 out[f"blend_{name}_w_{i}_{k}"] = b.view_weight(i, k)
+    # 9b. the reference's own GainCompensator::feed (S/src/exposure_compensate.cpp:71-142, compiled from its source) and
+    #     cuda::resize's arithmetic twin is pinned through the mask pipeline above; the gains are float64, compared bit for bit
+    imgs, masks, corners, sizes = gain_input()
+    out["gain_compensator"] = vr.gain_compensator_feed(imgs, masks, corners, sizes)
     # 10. wire / consumer formats: cvtColor(CV_YUV2BGR_NV12) (A/networking.cpp:46), convertTo(CV_8U) (A/timed.cpp:250)
     nv, w, h = nv12_input()
     out["nv12_bgr"] = vr.cvt_nv12_bgr(nv, w, h)

@@ -30,10 +30,12 @@ class GpuRig:
     """Drives a vsb_stitcher for a rig; static inputs either from the oracle (inject) or from vsb_calibrate_rig."""
 
     def __init__(self, n_views, src_w, src_h, pano_width, projection=0, num_bands=5, enable_local=True, gains=None,
-                 max_batch=1, oracle_rig=None):
+                 max_batch=1, oracle_rig=None, device_calibration=False):
         self.n, self.src_w, self.src_h = n_views, src_w, src_h
         self.st = B.Stitcher(n_views, num_bands, enable_local, max_batch)
-        if oracle_rig is None:
+        if device_calibration:
+            self.st.calibrate_rig_device(projection, pano_width, src_w, src_h, 90.0, gains)
+        elif oracle_rig is None:
             self.st.calibrate_rig(projection, pano_width, src_w, src_h, 90.0, gains)
         else:
             r = oracle_rig
@@ -103,6 +105,10 @@ class GpuRig:
         g = self.geom[i]
         bw, bh = (g["x_br"] - g["x_tl"]) >> k, (g["y_br"] - g["y_tl"]) >> k
         return self.read(2, i, k, (bh, bw), np.float32)
+
+    def proj_map(self, i, which):
+        w, h = self.sizes[i]
+        return self.read(8 + which, i, 0, (h, w), np.float32)
 
     def mesh_map(self, i, which):
         w, h = self.sizes[i]

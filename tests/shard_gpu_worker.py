@@ -25,7 +25,7 @@ def main():
     B, S, D = vsb200.binding, vsb200.synth, vsb200.dist
     n, sw, sh = case["n_views"], case["src_w"], case["src_h"]
     gains = S.gains(n)
-    st = B.Stitcher(n, case["num_bands"], True, max(1, int(case.get("batch", 0))))
+    st = B.Stitcher(n, case["num_bands"], True, max(1, int(case.get("batch", 0))) * (2 if case.get("native") else 1))
     st.calibrate_rig(0, case["pano_width"], sw, sh, 90.0, gains)
     info = st.rig_info()
     for i in range(n):
@@ -33,6 +33,48 @@ def main():
         st.set_mesh(i, mx.ctypes.data, my.ctypes.data, mx.shape[0], mx.shape[1])
     roi, _, nb = st.get_roi()
     W, H = roi[2], roi[3]
+    if case.get("native"):
+        # the library's own transport (vsb_shard_init / vsb_shard_compose: grouped ncclSend / ncclRecv inside libvsb200);
+        # three submissions of `batch` frames on two alternating caller streams = both halves of the frame slots, overlapped
+        F = max(1, int(case.get("batch", 1)))
+        box = [B.shard_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        st.shard_init(rank, world, box[0])
+        x0, x1, owned = st.shard_info()
+        pitch = (W * 6 + 255) // 256 * 256
+        nsub = 3
+        fr = [[S.frame(i, f, sw, sh) for i in range(n)] for f in range(nsub * F)]
+        d_fr = [[torch.from_numpy(a).cuda() if i in owned else None for i, a in enumerate(one)] for one in fr]
+        outs = [torch.zeros((H, pitch // 2), dtype=torch.int16, device="cuda") for _ in range(nsub * F)]
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        torch.cuda.synchronize()
+        for k in range(nsub):
+            srcs = [(d_fr[k * F + j][i].data_ptr() if i in owned else 0) for j in range(F) for i in range(n)]
+            st.shard_compose(srcs, sw * 3, [outs[k * F + j].data_ptr() for j in range(F)], pitch, streams[k & 1].cuda_stream)
+        torch.cuda.synchronize()
+        fulls = []
+        for o in outs:
+            full_f = o.to(torch.int32)
+            dist.all_reduce(full_f)
+            fulls.append(full_f)
+        sb, rb = st.shard_exchange_bytes()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {"rank": rank, "owned": owned, "send_bytes": sb, "recv_bytes": rb})
+        if rank == 0:
+            from oracle import oracle as og
+            from oracle import pipeline as op
+            og.set_num_threads(min(8, os.cpu_count() or 1))
+            orig = op.OracleRig(n, sw, sh, case["pano_width"], num_bands=case["num_bands"], enable_local=True, gains=gains)
+            for i in range(n):
+                orig.set_mesh(i, *S.mesh(*orig.sizes[i]))
+            bad = 0
+            for f in range(nsub * F):
+                want, _ = orig.compose(fr[f])
+                got = fulls[f].cpu().numpy()[:, :W * 3].reshape(H, W, 3).astype(np.int16)
+                bad += int(np.count_nonzero(got != want))
+            print(json.dumps({"world": world, "bad": bad, "batch": F, "native": True, "ranks": gathered}), flush=True)
+        dist.destroy_process_group()
+        return
     sh_st = D.ShardedStitcher(st, dist, torch)
     frames = [S.frame(i, 0, sw, sh) for i in range(n)]
     d_src = [torch.from_numpy(f).cuda() for f in frames]

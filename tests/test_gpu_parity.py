@@ -151,6 +151,97 @@ def test_build_maps_and_warp_match_oracle(cuda, og, vsb, proj, n, sw, sh, pano):
             _eq(got, og.remap_u8(src, gx, gy, interp, border), f"warp view {i} cn {cn} interp {interp} border {border}")
 
 
+# ------------------------------------------------------------------------------------------ calibration on the device (8f row 4)
+def test_device_voronoi_dilate_resize_gain_primitives(cuda, og, vsb):
+    """VoronoiSeamFinder on device masks against the reference's golden seams (bit-exact), MORPH_DILATE / cuda::resize against
+    oracle-G, GainCompensator::feed on device images against the reference's own gains (float64, bit for bit)."""
+    import torch
+    from tests.gpu_util import dev, host, stream
+    from tests.golden import make_golden as G
+    import os
+    gold = np.load(os.path.join(os.path.dirname(G.__file__), "reference_cpu.npz"))
+    C, L = vsb.C, vsb.lib()
+    for (n, sw, sh, pano, proj) in G.SEAM_RIGS:
+        masks, corners, sizes = G.seam_inputs(og, n, sw, sh, pano, proj)
+        d_masks = [dev(m) for m in masks]
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in d_masks])
+        sz = (C.c_int * (2 * n))(*[int(v) for p in sizes for v in p])
+        co = (C.c_int * (2 * n))(*[int(v) for p in corners for v in p])
+        vsb.check(L.vsb_voronoi_seams_device(n, sz, co, ptrs, vsb._vp(stream())))
+        for i, t in enumerate(d_masks):
+            got = host(t)
+            assert np.array_equal(np.packbits(got > 0, axis=1), gold[f"voronoi_{n}_{pano}_{proj}_{i}"]), f"rig {n}/{pano}/{proj} view {i}"
+            assert set(np.unique(got)) <= {0, 255}
+    rng = np.random.default_rng(9)
+    sm = (rng.random((57, 101)) > 0.5).astype(np.uint8) * 255
+    d_sm, d_dil = dev(sm), cuda.zeros((57, 101), dtype=cuda.uint8, device="cuda")
+    vsb.check(L.vsb_dilate3x3_u8(vsb._vp(d_sm.data_ptr()), 101, 57, vsb._vp(d_dil.data_ptr()), vsb._vp(stream())))
+    _eq(host(d_dil), og.dilate3x3_u8c1(sm), "dilate 3x3")
+    d_big = cuda.zeros((627, 961), dtype=cuda.uint8, device="cuda")
+    vsb.check(L.vsb_resize_linear_u8(vsb._vp(d_dil.data_ptr()), 101, 57, C.c_size_t(101), 1, vsb._vp(d_big.data_ptr()), 961, 627, C.c_size_t(961),
+                                     C.c_double(0.0), C.c_double(0.0), vsb._vp(stream())))
+    _eq(host(d_big), og.resize_linear_u8c1(host(d_dil), 961, 627), "cuda::resize CV_8UC1 (sizes)")
+    img = rng.integers(0, 256, (270, 480, 3), dtype=np.uint8)
+    ss = min(1.0, (0.01e6 / (480 * 270)) ** 0.5)
+    dw, dh = int(np.rint(480 * ss)), int(np.rint(270 * ss))
+    d_img, d_small = dev(img), cuda.zeros((dh, dw, 3), dtype=cuda.uint8, device="cuda")
+    vsb.check(L.vsb_resize_linear_u8(vsb._vp(d_img.data_ptr()), 480, 270, C.c_size_t(480 * 3), 3, vsb._vp(d_small.data_ptr()), dw, dh, C.c_size_t(dw * 3),
+                                     C.c_double(ss), C.c_double(ss), vsb._vp(stream())))
+    _eq(host(d_small), og.cuda_resize_linear_u8(img, dw, dh, ss, ss), "cuda::resize CV_8UC3 (explicit scale)")
+    imgs, masks, corners, sizes = G.gain_input()
+    n = len(imgs)
+    d_i, d_m = [dev(a) for a in imgs], [dev(a) for a in masks]
+    ip = (C.c_void_p * n)(*[t.data_ptr() for t in d_i]); mp = (C.c_void_p * n)(*[t.data_ptr() for t in d_m])
+    sz = (C.c_int * (2 * n))(*[int(v) for p in sizes for v in p]); co = (C.c_int * (2 * n))(*[int(v) for p in corners for v in p])
+    g = (C.c_double * n)()
+    vsb.check(L.vsb_gain_compensator_feed(n, ip, mp, sz, co, g, vsb._vp(stream())))
+    assert np.array_equal(np.array(list(g)), gold["gain_compensator"]), "device gain estimation vs the reference's GainCompensator"
+
+
+@pytest.mark.parametrize("case", ["small6_nolocal", "cfg2"])
+def test_device_calibration_products_and_compose(cuda, og, case):
+    """vsb_calibrate_rig_device: ROIs and blender geometry equal the oracle's; projection maps within 2e-3 px (device sinf / cosf);
+    seam masks equal except where a map difference moves a boundary sample (< 0.2 % of the samples); and, with the DEVICE's own
+    products injected into oracle-G, the composed panorama is bit-exact -- everything downstream of the maps is exact.  Gains
+    estimated at run time (vsb_estimate_gains) agree with the oracle's pipeline on its libm maps to 1e-4."""
+    import vsb200
+    from oracle import pipeline as op
+    from tests.gpu_util import GpuRig, dev, stream
+    kw = dict(CASES[case])
+    gains = vsb200.synth.gains(kw["n_views"])
+    ref = op.OracleRig(gains=gains, **kw)
+    grig = GpuRig(gains=gains, device_calibration=True, **kw)
+    n = kw["n_views"]
+    assert grig.roi_final == ref.roi_final and grig.roi_padded == ref.roi_padded and grig.num_bands == ref.num_bands
+    xmaps, ymaps, masks = [], [], []
+    for i in range(n):
+        assert grig.geom[i] == ref.blender.view_geom(i) and grig.sizes[i] == tuple(ref.sizes[i]) and grig.corners[i] == tuple(ref.corners[i])
+        gx, gy = grig.proj_map(i, 0), grig.proj_map(i, 1)
+        inside = (ref.xmaps[i] > -2) & (ref.xmaps[i] < kw["src_w"] + 1) & (ref.ymaps[i] > -2) & (ref.ymaps[i] < kw["src_h"] + 1) & ~((ref.xmaps[i] == -1) & (ref.ymaps[i] == -1))
+        assert np.abs(gx - ref.xmaps[i])[inside].max() <= 2e-3 and np.abs(gy - ref.ymaps[i])[inside].max() <= 2e-3
+        g = grig.geom[i]
+        w0 = grig.weight(i, 0)[g["top"]:g["top"] + grig.sizes[i][1], g["left"]:g["left"] + grig.sizes[i][0]]
+        m = np.rint(w0 * 255).astype(np.uint8)
+        assert np.count_nonzero(m != ref.masks[i]) <= 0.002 * m.size, f"seam mask view {i}"
+        xmaps.append(gx); ymaps.append(gy); masks.append(m)
+    mine = op.OracleRig.from_products(kw["src_w"], kw["src_h"], grig.corners, grig.sizes, xmaps, ymaps, masks, kw["num_bands"], kw["enable_local"], gains)
+    if kw["enable_local"]:
+        for i in range(n):
+            mx, my = vsb200.synth.mesh(*grig.sizes[i])
+            mine.set_mesh(i, mx, my); grig.set_mesh(i, mx, my)
+    frames = [vsb200.synth.frame(i, 0, kw["src_w"], kw["src_h"]) for i in range(n)]
+    _eq(grig.compose([frames])[0], mine.compose(frames)[0], "panorama from the device's calibration products")
+    # run-time gain refresh: darken two cameras, estimate, install, and the estimate follows
+    dim = [np.clip(f.astype(np.float32) * (0.8 if i in (1, 4 % n) else 1.0), 0, 255).astype(np.uint8) for i, f in enumerate(frames)]
+    srcs = [dev(f) for f in dim]
+    got = np.array(grig.st.estimate_gains([t.data_ptr() for t in srcs], kw["src_w"] * 3, apply=True, stream=stream()))
+    want = ref.estimate_gains(dim)
+    assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max(), (got, want)
+    assert got[1] > got[0], "the darkened camera gets the larger gain"
+    mine.gains = [float(np.float32(v)) for v in got]
+    _eq(grig.compose([dim])[0], mine.compose(dim)[0], "panorama after the run-time gain refresh")
+
+
 # ------------------------------------------------------------------------------------------ whole path
 CASES = {
     "small4": dict(n_views=4, src_w=320, src_h=240, pano_width=1024, num_bands=3, enable_local=True),

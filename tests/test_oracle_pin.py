@@ -137,6 +137,14 @@ def test_remap_vs_reference_cpu_sanity(og, gold):
     assert d.max() <= 8 and d.mean() < 1.0 and np.count_nonzero(d <= 1) > 0.8 * d.size
 
 
+def test_gain_compensator_vs_reference(og, gold):
+    """oracle-G's GainCompensator::feed restatement (pairwise overlap statistics in the reference's summation order + hal::LU64f)
+    gives the reference's gains BIT FOR BIT (float64): the fixture comes from the reference's own exposure_compensate.cpp compiled
+    in place (oracle/ref.mk)."""
+    imgs, masks, corners, sizes = G.gain_input()
+    assert np.array_equal(og.gain_compensator_feed(imgs, masks, corners, sizes), gold["gain_compensator"])
+
+
 @pytest.mark.parametrize("which", ["linear", "recipe"])
 def test_remap_vs_reference_float_gold(og, gold, which):
     """oracle-G's remap against the reference's own float gold for cuda::remap (LinearInterpolator,
@@ -206,6 +214,7 @@ def test_live_golden_file_is_current(gold):
     src, xm, ym = G.remap_input()
     assert np.array_equal(vr.remap_u8(src, xm, ym), gold["remap_linear"])
     assert np.array_equal(vr.remap_gold_u8(src, xm, ym), gold["remap_gold_linear"])
+    assert np.array_equal(vr.gain_compensator_feed(*G.gain_input()), gold["gain_compensator"])
 
 
 def test_live_nv12_full_frame(og):

@@ -27,7 +27,8 @@ SYMBOLS = [
     "vsb_shard_set", "vsb_shard_info", "vsb_shard_rect", "vsb_get_plane",
     "vsb_rig_camera", "vsb_voronoi_seams", "vsb_calibrate_rig", "vsb_rig_info_get", "vsb_get_config", "vsb_set_profiling", "vsb_get_profile",
     "vsb_set_formats", "vsb_nv12_to_bgr", "vsb_consumer_image_height", "vsb_consume",
-    "vsb_shard_unique_id", "vsb_shard_init", "vsb_shard_compose", "vsb_shard_exchange_bytes",
+    "vsb_calibrate_rig_device", "vsb_estimate_gains", "vsb_voronoi_seams_device", "vsb_dilate3x3_u8", "vsb_resize_linear_u8",
+    "vsb_gain_compensator_feed", "vsb_shard_unique_id", "vsb_shard_init", "vsb_shard_compose", "vsb_shard_exchange_bytes",
     "vsb_shard_plan", "vsb_shard_peer_bytes", "vsb_shard_pack", "vsb_shard_unpack", "vsb_feed_batch", "vsb_blend_batch",
 ]
 CONSUME_RGB, CONSUME_I420 = 0, 1
@@ -154,6 +155,18 @@ class Stitcher:
         if gains is not None:
             g = (C.c_float * self.num_views)(*[float(v) for v in gains])
         check(lib().vsb_calibrate_rig(self._h, projection, pano_width, src_w, src_h, C.c_double(hfov_deg), g))
+
+    def calibrate_rig_device(self, projection, pano_width, src_w, src_h, hfov_deg=90.0, gains=None):
+        g = None
+        if gains is not None:
+            g = (C.c_float * self.num_views)(*[float(v) for v in gains])
+        check(lib().vsb_calibrate_rig_device(self._h, projection, pano_width, src_w, src_h, C.c_double(hfov_deg), g))
+
+    def estimate_gains(self, frame_ptrs, pitch, apply=False, stream=0):
+        fp = (C.c_void_p * len(frame_ptrs))(*[int(p) for p in frame_ptrs])
+        out = (C.c_float * self.num_views)()
+        check(lib().vsb_estimate_gains(self._h, fp, C.c_size_t(pitch), out, int(bool(apply)), _vp(stream)))
+        return [float(v) for v in out]
 
     def rig_info(self):
         info = RigInfo()

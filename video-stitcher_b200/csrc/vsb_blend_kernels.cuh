@@ -27,7 +27,7 @@ namespace vsb {
 
 constexpr int MAXV = VSB_MAX_VIEWS;
 constexpr int MAXL = VSB_MAX_BANDS + 1;
-constexpr int MAX_BATCH = 8;
+constexpr int MAX_BATCH = 16;  // frame slots per handle (kernel parameter blocks grow with it: up to ~6 KB, within the 32 KB of CUDA >= 12.1)
 constexpr float B2_MAGIC = 12582912.f;      // 1.5 * 2^23: adding it rounds an fp32 value to an integer (half to even) in the low mantissa bits
 constexpr int B2_MAGIC_BITS = 0x4B400000;
 

@@ -182,6 +182,229 @@ static void resize_linear_u8(const uint8_t *src, int sw, int sh, uint8_t *dst, i
         }
 }
 
+
+// ============================================================================================ calibration on the device
+// the per-pixel work of the static half of the path as CUDA kernels, so that seams and gains can be
+// refreshed at run time without a host loop over pixels.  Integer / index work (Voronoi labels, masks) is bit-exact against the
+// host functions above and the reference's golden vectors; the fp32 pieces use the same operation order as the host twins.
+
+// warp of an all-255 mask, INTER_NEAREST / BORDER_CONSTANT (A/calibration.cpp:122,227): 255 where the map addresses the image
+__global__ void k_full_mask(const float *__restrict__ xm, const float *__restrict__ ym, size_t mp, int w, int h, int sw, int sh, uint8_t *__restrict__ dst)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int sx = __float2int_rz(*(const float *)((const char *)xm + (size_t)y * mp + (size_t)x * 4));
+    const int sy = __float2int_rz(*(const float *)((const char *)ym + (size_t)y * mp + (size_t)x * 4));
+    dst[(size_t)y * w + x] = ((unsigned)sx < (unsigned)sw && (unsigned)sy < (unsigned)sh) ? 255 : 0;
+}
+
+// VoronoiSeamFinder::findInPair (sources/modules/stitching/src/seam_finders.cpp:111-162) for one pair of views.
+// distanceTransform(DIST_L1, 3) (sources/modules/imgproc/src/distransform.cpp:68-140) is the exact city-block distance to the
+// nearest zero pixel (chamfer weights 1 / 2), which separates: a column pass (distance along the column), then for every pixel
+// the minimum over the row of |dx| + column distance.  "No zero pixel anywhere" keeps one shared INF, which orders exactly like
+// the reference's INIT-based values (larger than every finite distance, equal on both sides).
+struct VorPair {
+    uint8_t *m1, *m2;
+    int w1, h1, t1x, t1y, w2, h2, t2x, t2y;
+    int x_tl, y_tl, rw, rh;  // overlap rect (canvas coordinates) and size
+};
+constexpr int VOR_GAP = 10, VOR_INF = 1 << 28;
+
+__device__ __forceinline__ void vor_unique(const VorPair &P, int x, int y, bool &u1, bool &u2)  // (x, y) relative to the overlap origin
+{
+    const int y1 = P.y_tl - P.t1y + y, x1 = P.x_tl - P.t1x + x, y2 = P.y_tl - P.t2y + y, x2 = P.x_tl - P.t2x + x;
+    const bool s1 = (unsigned)y1 < (unsigned)P.h1 && (unsigned)x1 < (unsigned)P.w1 && P.m1[(size_t)y1 * P.w1 + x1] != 0;
+    const bool s2 = (unsigned)y2 < (unsigned)P.h2 && (unsigned)x2 < (unsigned)P.w2 && P.m2[(size_t)y2 * P.w2 + x2] != 0;
+    u1 = s1 && !s2; u2 = s2 && !s1;  // pixels that belong to one image only: the zeros the distances are measured to
+}
+
+// one thread per column of the padded region: distance along the column to the nearest unique pixel of image 1 / image 2
+__global__ void k_vor_columns(const VorPair P, int *__restrict__ g1, int *__restrict__ g2)
+{
+    const int sw = P.rw + 2 * VOR_GAP, sh = P.rh + 2 * VOR_GAP;
+    const int xc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xc >= sw) return;
+    int d1 = VOR_INF, d2 = VOR_INF;
+    for (int yc = 0; yc < sh; ++yc) {
+        bool u1, u2;
+        vor_unique(P, xc - VOR_GAP, yc - VOR_GAP, u1, u2);
+        d1 = u1 ? 0 : min(d1 + 1, VOR_INF); d2 = u2 ? 0 : min(d2 + 1, VOR_INF);
+        g1[(size_t)yc * sw + xc] = d1; g2[(size_t)yc * sw + xc] = d2;
+    }
+    d1 = d2 = VOR_INF;
+    for (int yc = sh - 1; yc >= 0; --yc) {
+        const size_t o = (size_t)yc * sw + xc;
+        d1 = g1[o] == 0 ? 0 : min(d1 + 1, VOR_INF); d2 = g2[o] == 0 ? 0 : min(d2 + 1, VOR_INF);
+        g1[o] = min(g1[o], d1); g2[o] = min(g2[o], d2);
+    }
+}
+// one thread per pixel of the overlap: row minimum, then the pixel leaves the mask of the farther image (seam_finders.cpp:153-161)
+__global__ void k_vor_decide(const VorPair P, const int *__restrict__ g1, const int *__restrict__ g2)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= P.rw || y >= P.rh) return;
+    const int sw = P.rw + 2 * VOR_GAP, xc = x + VOR_GAP;
+    const int *r1 = g1 + (size_t)(y + VOR_GAP) * sw, *r2 = g2 + (size_t)(y + VOR_GAP) * sw;
+    int d1 = VOR_INF, d2 = VOR_INF;
+    for (int q = 0; q < sw; ++q) {
+        const int dx = abs(q - xc);
+        d1 = min(d1, min(r1[q] + dx, VOR_INF)); d2 = min(d2, min(r2[q] + dx, VOR_INF));
+    }
+    if (d1 < d2) P.m2[(size_t)(P.y_tl - P.t2y + y) * P.w2 + (P.x_tl - P.t2x + x)] = 0;
+    else P.m1[(size_t)(P.y_tl - P.t1y + y) * P.w1 + (P.x_tl - P.t1x + x)] = 0;
+}
+
+// MORPH_DILATE 3x3 rect, BORDER_REFLECT_101 (sources/modules/cudafilters/src/filtering.cpp:543-606; A/calibration.cpp:209,232)
+__global__ void k_dilate3x3(const uint8_t *__restrict__ src, int w, int h, uint8_t *__restrict__ dst)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    unsigned m = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            int yy = y + dy, xx = x + dx;
+            if (yy < 0) yy = -yy;
+            if (yy >= h) yy = 2 * (h - 1) - yy;
+            if (xx < 0) xx = -xx;
+            if (xx >= w) xx = 2 * (w - 1) - xx;
+            yy = max(yy, 0); xx = max(xx, 0);
+            m = max(m, (unsigned)src[(size_t)yy * w + xx]);
+        }
+    dst[(size_t)y * w + x] = (uint8_t)m;
+}
+
+// cuda::resize INTER_LINEAR on CV_8UC1 / CV_8UC3 (sources/modules/cudawarping/src/cuda/resize.cu:71-106): no half-pixel centre,
+// fp32 weights in the kernel's order, cvt.rni.sat.u8.  fx / fy are the factors the host wrapper passes (src/resize.cpp:76-105).
+template <int CN>
+__global__ void k_resize_linear_u8(const uint8_t *__restrict__ src, int sw, int sh, size_t sp, uint8_t *__restrict__ dst, int dw, int dh, size_t dp, float fx, float fy)
+{
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (dx >= dw || dy >= dh) return;
+    const float sx = __fmul_rn((float)dx, fx), sy = __fmul_rn((float)dy, fy);
+    const int x1 = __float2int_rd(sx), y1 = __float2int_rd(sy), x2 = x1 + 1, y2 = y1 + 1;
+    const int x2r = min(x2, sw - 1), y2r = min(y2, sh - 1);
+    const float w11 = __fmul_rn(__fsub_rn((float)x2, sx), __fsub_rn((float)y2, sy)), w12 = __fmul_rn(__fsub_rn(sx, (float)x1), __fsub_rn((float)y2, sy));
+    const float w21 = __fmul_rn(__fsub_rn((float)x2, sx), __fsub_rn(sy, (float)y1)), w22 = __fmul_rn(__fsub_rn(sx, (float)x1), __fsub_rn(sy, (float)y1));
+#pragma unroll
+    for (int c = 0; c < CN; ++c) {
+        float o = __fmaf_rn((float)src[(size_t)y1 * sp + (size_t)x1 * CN + c], w11, 0.f);
+        o = __fmaf_rn((float)src[(size_t)y1 * sp + (size_t)x2r * CN + c], w12, o);
+        o = __fmaf_rn((float)src[(size_t)y2r * sp + (size_t)x1 * CN + c], w21, o);
+        o = __fmaf_rn((float)src[(size_t)y2r * sp + (size_t)x2r * CN + c], w22, o);
+        dst[(size_t)dy * dp + (size_t)dx * CN + c] = (uint8_t)rni_sat_u8(o);
+    }
+}
+
+__global__ void k_and_u8(uint8_t *__restrict__ a, const uint8_t *__restrict__ b, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] &= b[i];
+}
+
+// GainCompensator::feed, the reductions (sources/modules/stitching/src/exposure_compensate.cpp:89-121): one thread per pair
+// (i <= j) walks the overlap in the reference's order (rows, then columns), so the double sums are the reference's bit for bit.
+struct GainView { const uint8_t *img, *mask; int w, h, tx, ty; };  // warped seam-scale image (CV_8UC3, tight rows), its warped mask, corner
+struct GainParams { int n; GainView v[VSB_MAX_VIEWS]; };
+__global__ void k_gain_pairs(const GainParams P, int *__restrict__ N, double *__restrict__ I)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n * P.n) return;
+    const int i = t / P.n, j = t - i * P.n;
+    if (j < i) return;
+    const GainView &A = P.v[i], &B = P.v[j];
+    const int x_tl = max(A.tx, B.tx), y_tl = max(A.ty, B.ty), x_br = min(A.tx + A.w, B.tx + B.w), y_br = min(A.ty + A.h, B.ty + B.h);
+    if (!(x_tl < x_br && y_tl < y_br)) return;  // overlapRoi (util.cpp:101-113): N and I stay 0
+    int cnt = 0;
+    double s1 = 0, s2 = 0;
+    for (int y = y_tl; y < y_br; ++y)
+        for (int x = x_tl; x < x_br; ++x) {
+            const size_t o1 = (size_t)(y - A.ty) * A.w + (x - A.tx), o2 = (size_t)(y - B.ty) * B.w + (x - B.tx);
+            if (A.mask[o1] != 255 || B.mask[o2] != 255) continue;
+            ++cnt;
+            const uint8_t *p = A.img + o1 * 3, *q = B.img + o2 * 3;
+            s1 += sqrt((double)((int)p[0] * p[0] + (int)p[1] * p[1] + (int)p[2] * p[2]));
+            s2 += sqrt((double)((int)q[0] * q[0] + (int)q[1] * q[1] + (int)q[2] * q[2]));
+        }
+    const int nn = max(1, cnt);
+    N[i * P.n + j] = N[j * P.n + i] = nn;
+    I[i * P.n + j] = s1 / nn;
+    I[j * P.n + i] = s2 / nn;
+}
+
+// seam-scale state kept with the handle (vsb_calibrate_rig_device): what a gain refresh needs
+struct CalibState {
+    int n = 0, projection = 0, src_w = 0, src_h = 0, seam_w = 0, seam_h = 0;
+    double seam_scale = 1.0;
+    float seam_warp_scale = 0.f;
+    float Ks[VSB_MAX_VIEWS][9], R[VSB_MAX_VIEWS][9];
+    int roi[VSB_MAX_VIEWS][4];
+    uint8_t *warped_mask[VSB_MAX_VIEWS] = {};  // warped all-255 masks at seam scale, BEFORE the seam finder (what the compensator gets)
+};
+static void calib_state_free(void *p)
+{
+    CalibState *c = static_cast<CalibState *>(p);
+    for (int i = 0; i < VSB_MAX_VIEWS; ++i) cudaFree(c->warped_mask[i]);
+    delete c;
+}
+
+// cv::solve(A, b, x, DECOMP_LU) for n >= 4 (sources/modules/core/src/lapack.cpp -> hal::LU64f, matrix_decomp.cpp:52-107)
+static bool lu_solve(std::vector<double> &A, std::vector<double> &b, int m)
+{
+    const double eps = 2.220446049250313e-16 * 100;
+    for (int i = 0; i < m; ++i) {
+        int k = i;
+        for (int j = i + 1; j < m; ++j) if (std::abs(A[j * m + i]) > std::abs(A[k * m + i])) k = j;
+        if (std::abs(A[k * m + i]) < eps) return false;
+        if (k != i) { for (int j = i; j < m; ++j) std::swap(A[i * m + j], A[k * m + j]); std::swap(b[i], b[k]); }
+        const double d = -1 / A[i * m + i];
+        for (int j = i + 1; j < m; ++j) {
+            const double alpha = A[j * m + i] * d;
+            for (int q = i + 1; q < m; ++q) A[j * m + q] += alpha * A[i * m + q];
+            b[j] += alpha * b[i];
+        }
+    }
+    for (int i = m - 1; i >= 0; --i) {
+        double sum = b[i];
+        for (int q = i + 1; q < m; ++q) sum -= A[i * m + q] * b[q];
+        b[i] = sum / A[i * m + i];
+    }
+    return true;
+}
+
+static inline dim3 grid2(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }
+
+// VoronoiSeamFinder::find on device masks (pairs in the reference's order: every pair sees the masks the earlier ones left)
+static int voronoi_device(int n, const int *sizes, const int *corners, uint8_t *const *d_masks, cudaStream_t st)
+{
+    int *g = nullptr;
+    size_t cap = 0;
+    int rc = VSB_OK;
+    for (int a = 0; a < n - 1 && rc == VSB_OK; ++a)
+        for (int b = a + 1; b < n && rc == VSB_OK; ++b) {
+            VorPair P;
+            P.m1 = d_masks[a]; P.m2 = d_masks[b];
+            P.w1 = sizes[2 * a]; P.h1 = sizes[2 * a + 1]; P.w2 = sizes[2 * b]; P.h2 = sizes[2 * b + 1];
+            P.t1x = corners[2 * a]; P.t1y = corners[2 * a + 1]; P.t2x = corners[2 * b]; P.t2y = corners[2 * b + 1];
+            P.x_tl = std::max(P.t1x, P.t2x); P.y_tl = std::max(P.t1y, P.t2y);
+            const int x_br = std::min(P.t1x + P.w1, P.t2x + P.w2), y_br = std::min(P.t1y + P.h1, P.t2y + P.h2);
+            if (!(P.x_tl < x_br && P.y_tl < y_br)) continue;
+            P.rw = x_br - P.x_tl; P.rh = y_br - P.y_tl;
+            const size_t need = (size_t)(P.rw + 2 * VOR_GAP) * (P.rh + 2 * VOR_GAP) * 2 * sizeof(int);
+            if (need > cap) {
+                if (g) cudaFreeAsync(g, st);
+                rc = check_cuda(cudaMallocAsync(&g, need, st), "voronoi scratch");
+                if (rc != VSB_OK) break;
+                cap = need;
+            }
+            int *g1 = g, *g2 = g + (size_t)(P.rw + 2 * VOR_GAP) * (P.rh + 2 * VOR_GAP);
+            k_vor_columns<<<(P.rw + 2 * VOR_GAP + 127) / 128, 128, 0, st>>>(P, g1, g2);
+            k_vor_decide<<<grid2(P.rw, P.rh, dim3(32, 8)), dim3(32, 8), 0, st>>>(P, g1, g2);
+            rc = check_launch("voronoi kernels");
+        }
+    if (g) cudaFreeAsync(g, st);
+    return rc;
+}
+
 }  // namespace vsb
 
 
@@ -281,6 +504,253 @@ int vsb_calibrate_rig(vsb_stitcher *s, int projection, int pano_width, int src_w
         if (gains) { r = vsb_set_gain(s, i, gains[i]); if (r != VSB_OK) return r; }
     }
     return vsb_note_rig(s, projection, scale, src_w, src_h);
+}
+
+// ---- device-side calibration entry points -------------------------------------------------------------------------------------
+int vsb_voronoi_seams_device(int n, const int *sizes_wh, const int *corners_xy, uint8_t *const *d_masks, void *stream)
+{
+    if (n < 1 || n > VSB_MAX_VIEWS || !sizes_wh || !corners_xy || !d_masks) return vsb::fail(VSB_ERR_INVALID, "voronoi_seams_device: bad arguments");
+    return vsb::voronoi_device(n, sizes_wh, corners_xy, d_masks, (cudaStream_t)stream);
+}
+
+int vsb_dilate3x3_u8(const uint8_t *d_src, int w, int h, uint8_t *d_dst, void *stream)
+{
+    if (!d_src || !d_dst || w <= 0 || h <= 0) return vsb::fail(VSB_ERR_INVALID, "dilate3x3: bad arguments");
+    const dim3 b(32, 8);
+    vsb::k_dilate3x3<<<vsb::grid2(w, h, b), b, 0, (cudaStream_t)stream>>>(d_src, w, h, d_dst);
+    return vsb::check_launch("k_dilate3x3");
+}
+
+int vsb_resize_linear_u8(const uint8_t *d_src, int sw, int sh, size_t src_pitch, int channels, uint8_t *d_dst, int dw, int dh, size_t dst_pitch,
+                         double fx, double fy, void *stream)
+{
+    if (!d_src || !d_dst || sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0 || (channels != 1 && channels != 3))
+        return vsb::fail(VSB_ERR_INVALID, "resize_linear: bad arguments");
+    // cuda::resize (sources/modules/cudawarping/src/resize.cpp:76-105): with fx = fy = 0 the factors follow from the sizes
+    if (!(fx > 0) || !(fy > 0)) { fx = (double)dw / sw; fy = (double)dh / sh; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dw == sw && dh == sh) return vsb::check_cuda(cudaMemcpy2DAsync(d_dst, dst_pitch, d_src, src_pitch, (size_t)sw * channels, sh, cudaMemcpyDeviceToDevice, st), "resize (copy)");
+    const dim3 b(32, 8);
+    const float kx = (float)(1.0 / fx), ky = (float)(1.0 / fy);
+    if (channels == 1) vsb::k_resize_linear_u8<1><<<vsb::grid2(dw, dh, b), b, 0, st>>>(d_src, sw, sh, src_pitch, d_dst, dw, dh, dst_pitch, kx, ky);
+    else vsb::k_resize_linear_u8<3><<<vsb::grid2(dw, dh, b), b, 0, st>>>(d_src, sw, sh, src_pitch, d_dst, dw, dh, dst_pitch, kx, ky);
+    return vsb::check_launch("k_resize_linear_u8");
+}
+
+// vsb_calibrate_rig with every per-pixel loop on the device: seam-scale and compose-scale maps (k_build_maps), mask warps,
+// Voronoi seams, dilate / resize / AND, weight pyramids (vsb_init_view with a device mask).  The ROIs stay on the host like in the
+// reference (RotationWarperBase::detectResultRoi runs on the CPU there too: a walk along the image border).  The device evaluates
+// sinf / cosf itself, so the projection maps agree with the host path to ~1e-3 px, not bit for bit (the reference's own maps come
+// from the same kind of device code); everything downstream of the maps is exact.
+int vsb_calibrate_rig_device(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains)
+{
+    using namespace vsb;
+    if (!s || pano_width <= 0 || src_w <= 0 || src_h <= 0) return fail(VSB_ERR_INVALID, "calibrate_rig_device: bad arguments");
+    vsb_config cfg;
+    int r = vsb_get_config(s, &cfg);
+    if (r != VSB_OK) return r;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(vsb_handle_device(s));
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev};
+    const int n = cfg.num_views;
+    const float scale = (float)(pano_width / (2.0 * 3.1415926535897932384626));
+    CalibState *cs = new CalibState();
+    cs->n = n; cs->projection = projection; cs->src_w = src_w; cs->src_h = src_h;
+    std::vector<float> K(9 * n), R(9 * n);
+    for (int i = 0; i < n; ++i) {
+        r = vsb_rig_camera(n, i, src_w, src_h, hfov_deg, &K[9 * i], &R[9 * i]);
+        if (r != VSB_OK) { calib_state_free(cs); return r; }
+    }
+    cudaStream_t st = nullptr;  // calibration time: the default stream, synchronised at the end of every phase
+    const dim3 b(32, 8);
+    auto bail = [&](int code) { cudaDeviceSynchronize(); calib_state_free(cs); return code; };
+    // ---- seam scale (360_stitcher/calibration.cpp:92-135)
+    const double seam_scale = std::min(1.0, std::sqrt(0.01 * 1e6 / ((double)src_w * src_h)));
+    const int seam_w = (int)std::nearbyint(src_w * seam_scale), seam_h = (int)std::nearbyint(src_h * seam_scale);
+    const float seam_warp_scale = static_cast<float>(scale * seam_scale), swa = (float)seam_scale;
+    cs->seam_scale = seam_scale; cs->seam_w = seam_w; cs->seam_h = seam_h; cs->seam_warp_scale = seam_warp_scale;
+    std::vector<int> seam_sizes(2 * n), seam_corners(2 * n);
+    std::vector<uint8_t *> seam_masks(n, nullptr);
+    auto free_seams = [&]() { for (uint8_t *p : seam_masks) cudaFree(p); };
+    for (int i = 0; i < n; ++i) {
+        float *Ks = cs->Ks[i];
+        std::memcpy(Ks, &K[9 * i], sizeof(float) * 9);
+        std::memcpy(cs->R[i], &R[9 * i], sizeof(float) * 9);
+        Ks[0] *= swa; Ks[2] *= swa; Ks[4] *= swa; Ks[5] *= swa;
+        int *roi = cs->roi[i];
+        r = vsb_warp_roi(projection, seam_warp_scale, Ks, &R[9 * i], seam_w, seam_h, roi);
+        if (r != VSB_OK) { free_seams(); return bail(r); }
+        const size_t mp = ((size_t)roi[2] * 4 + 15) / 16 * 16;
+        float *xm = nullptr, *ym = nullptr;
+        if (cudaMalloc(&xm, mp * roi[3]) != cudaSuccess || cudaMalloc(&ym, mp * roi[3]) != cudaSuccess ||
+            cudaMalloc(&seam_masks[i], (size_t)roi[2] * roi[3]) != cudaSuccess || cudaMalloc(&cs->warped_mask[i], (size_t)roi[2] * roi[3]) != cudaSuccess) {
+            cudaFree(xm); cudaFree(ym); free_seams();
+            return bail(fail(VSB_ERR_NOMEM, "calibrate_rig_device: out of device memory"));
+        }
+        int roi2[4];
+        r = vsb_build_maps(projection, seam_warp_scale, Ks, &R[9 * i], seam_w, seam_h, xm, ym, mp, roi2, st);
+        if (r == VSB_OK) {
+            k_full_mask<<<grid2(roi[2], roi[3], b), b, 0, st>>>(xm, ym, mp, roi[2], roi[3], seam_w, seam_h, seam_masks[i]);
+            r = check_launch("k_full_mask");
+        }
+        if (r == VSB_OK) r = check_cuda(cudaMemcpyAsync(cs->warped_mask[i], seam_masks[i], (size_t)roi[2] * roi[3], cudaMemcpyDeviceToDevice, st), "seam mask copy");
+        cudaStreamSynchronize(st);
+        cudaFree(xm); cudaFree(ym);
+        if (r != VSB_OK) { free_seams(); return bail(r); }
+        seam_corners[2 * i] = roi[0]; seam_corners[2 * i + 1] = roi[1]; seam_sizes[2 * i] = roi[2]; seam_sizes[2 * i + 1] = roi[3];
+    }
+    r = voronoi_device(n, seam_sizes.data(), seam_corners.data(), seam_masks.data(), st);
+    if (r != VSB_OK) { free_seams(); return bail(r); }
+    // ---- compose scale (360_stitcher/calibration.cpp:137-246), compose_scale = 1
+    std::vector<int> corners(2 * n), sizes(2 * n);
+    for (int i = 0; i < n; ++i) {
+        int roi[4];
+        r = vsb_warp_roi(projection, scale, &K[9 * i], &R[9 * i], src_w, src_h, roi);
+        if (r != VSB_OK) { free_seams(); return bail(r); }
+        corners[2 * i] = roi[0]; corners[2 * i + 1] = roi[1]; sizes[2 * i] = roi[2]; sizes[2 * i + 1] = roi[3];
+    }
+    r = vsb_prepare(s, corners.data(), sizes.data());
+    if (r != VSB_OK) { free_seams(); return bail(r); }
+    for (int i = 0; i < n && r == VSB_OK; ++i) {
+        const int w = sizes[2 * i], h = sizes[2 * i + 1], sw = seam_sizes[2 * i], sh = seam_sizes[2 * i + 1];
+        const size_t mp = ((size_t)w * 4 + 15) / 16 * 16;
+        float *xm = nullptr, *ym = nullptr;
+        uint8_t *warped = nullptr, *seam = nullptr, *dil = nullptr;
+        if (cudaMalloc(&xm, mp * h) != cudaSuccess || cudaMalloc(&ym, mp * h) != cudaSuccess || cudaMalloc(&warped, (size_t)w * h) != cudaSuccess ||
+            cudaMalloc(&seam, (size_t)w * h) != cudaSuccess || cudaMalloc(&dil, (size_t)sw * sh) != cudaSuccess)
+            r = fail(VSB_ERR_NOMEM, "calibrate_rig_device: out of device memory");
+        int roi2[4];
+        if (r == VSB_OK) r = vsb_build_maps(projection, scale, &K[9 * i], &R[9 * i], src_w, src_h, xm, ym, mp, roi2, st);
+        if (r == VSB_OK) {
+            k_full_mask<<<grid2(w, h, b), b, 0, st>>>(xm, ym, mp, w, h, src_w, src_h, warped);
+            const uint8_t *small = seam_masks[i];
+            if (cfg.enable_local) { k_dilate3x3<<<grid2(sw, sh, b), b, 0, st>>>(seam_masks[i], sw, sh, dil); small = dil; }
+            r = check_launch("mask kernels");
+            if (r == VSB_OK) r = vsb_resize_linear_u8(small, sw, sh, (size_t)sw, 1, seam, w, h, (size_t)w, 0.0, 0.0, st);
+            if (r == VSB_OK) {
+                k_and_u8<<<(unsigned)(((size_t)w * h + 255) / 256), 256, 0, st>>>(seam, warped, (size_t)w * h);
+                r = check_launch("k_and_u8");
+            }
+        }
+        if (r == VSB_OK) r = check_cuda(cudaStreamSynchronize(st), "calibrate_rig_device");
+        if (r == VSB_OK) r = vsb_init_view(s, i, seam, w, h, (size_t)w, corners[2 * i], corners[2 * i + 1], 1);
+        if (r == VSB_OK) r = vsb_set_maps(s, i, xm, ym, w, h, mp, 1, src_w, src_h);
+        if (r == VSB_OK && gains) r = vsb_set_gain(s, i, gains[i]);
+        cudaDeviceSynchronize();
+        cudaFree(xm); cudaFree(ym); cudaFree(warped); cudaFree(seam); cudaFree(dil);
+    }
+    free_seams();
+    if (r != VSB_OK) return bail(r);
+    vsb_attach_calib(s, cs, calib_state_free);
+    return vsb_note_rig(s, projection, scale, src_w, src_h);
+}
+
+// GainCompensator::feed (sources/modules/stitching/src/exposure_compensate.cpp:71-142) on warped images already on the device:
+// d_imgs[i] CV_8UC3 (tight rows), d_masks[i] CV_8U (255 = valid), sizes / corners as the reference passes them.  The pairwise
+// reductions run on the device (one thread per pair, the reference's summation order), the n x n solve on the host.
+int vsb_gain_compensator_feed(int n, const uint8_t *const *d_imgs, const uint8_t *const *d_masks, const int *sizes_wh, const int *corners_xy,
+                              double *gains_out, void *stream)
+{
+    using namespace vsb;
+    if (n < 4 || n > VSB_MAX_VIEWS || !d_imgs || !d_masks || !sizes_wh || !corners_xy || !gains_out)
+        return fail(VSB_ERR_INVALID, "gain_compensator_feed: bad arguments (4..%d views: cv::solve takes closed forms below 4, not restated)", VSB_MAX_VIEWS);
+    cudaStream_t st = (cudaStream_t)stream;
+    GainParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.n = n;
+    for (int i = 0; i < n; ++i) {
+        P.v[i].img = d_imgs[i]; P.v[i].mask = d_masks[i];
+        P.v[i].w = sizes_wh[2 * i]; P.v[i].h = sizes_wh[2 * i + 1]; P.v[i].tx = corners_xy[2 * i]; P.v[i].ty = corners_xy[2 * i + 1];
+    }
+    int *dN = nullptr;
+    double *dI = nullptr;
+    std::vector<int> N((size_t)n * n, 0);
+    std::vector<double> I((size_t)n * n, 0.0);
+    int r = VSB_OK;
+    if (cudaMalloc(&dN, sizeof(int) * n * n) != cudaSuccess || cudaMalloc(&dI, sizeof(double) * n * n) != cudaSuccess)
+        r = fail(VSB_ERR_NOMEM, "gain_compensator_feed: out of device memory");
+    if (r == VSB_OK) {
+        cudaMemsetAsync(dN, 0, sizeof(int) * n * n, st);
+        cudaMemsetAsync(dI, 0, sizeof(double) * n * n, st);
+        k_gain_pairs<<<(n * n + 63) / 64, 64, 0, st>>>(P, dN, dI);
+        r = check_launch("k_gain_pairs");
+        if (r == VSB_OK) r = check_cuda(cudaMemcpyAsync(N.data(), dN, sizeof(int) * n * n, cudaMemcpyDeviceToHost, st), "gain_compensator_feed");
+        if (r == VSB_OK) r = check_cuda(cudaMemcpyAsync(I.data(), dI, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st), "gain_compensator_feed");
+        if (r == VSB_OK) r = check_cuda(cudaStreamSynchronize(st), "gain_compensator_feed");
+    }
+    cudaFree(dN); cudaFree(dI);
+    if (r != VSB_OK) return r;
+    const double alpha = 0.01, beta = 100;
+    std::vector<double> A((size_t)n * n, 0.0), bb(n, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            bb[i] += beta * N[i * n + j];
+            A[i * n + i] += beta * N[i * n + j];
+            if (j == i) continue;
+            A[i * n + i] += 2 * alpha * I[i * n + j] * I[i * n + j] * N[i * n + j];
+            A[i * n + j] -= 2 * alpha * I[i * n + j] * I[j * n + i] * N[i * n + j];
+        }
+    if (!lu_solve(A, bb, n)) return fail(VSB_ERR_INVALID, "gain_compensator_feed: singular system");
+    for (int i = 0; i < n; ++i) gains_out[i] = bb[i];
+    return VSB_OK;
+}
+
+// GainCompensator::feed (sources/modules/stitching/src/exposure_compensate.cpp:71-142) on the device, callable at run time
+// ("Dynamically update the gain compensation" is an open TODO of the reference): the frames are resized to seam scale
+// (cuda::resize, A/calibration.cpp:95) and warped LINEAR / BORDER_REFLECT (:118) with the seam-scale maps, the pairwise
+// overlap counts and mean intensities are reduced on the device in the reference's summation order, the n x n system is solved
+// on the host (hal::LU64f restated: bit-identical gains for n >= 4).  apply != 0 installs the gains (vsb_set_gain).
+int vsb_estimate_gains(vsb_stitcher *s, const uint8_t *const *d_frames, size_t pitch, float *gains_out, int apply, void *stream)
+{
+    using namespace vsb;
+    if (!s || !d_frames) return fail(VSB_ERR_INVALID, "estimate_gains: null argument");
+    CalibState *cs = static_cast<CalibState *>(vsb_get_calib(s));
+    if (!cs) return fail(VSB_ERR_STATE, "estimate_gains: the handle was not calibrated with vsb_calibrate_rig_device");
+    const int n = cs->n;
+    if (n < 4) return fail(VSB_ERR_INVALID, "estimate_gains: needs >= 4 views (cv::solve takes closed forms below that; not restated)");
+    if (pitch < (size_t)cs->src_w * 3) return fail(VSB_ERR_INVALID, "estimate_gains: pitch too small");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(vsb_handle_device(s));
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev};
+    cudaStream_t st = (cudaStream_t)stream;
+    GainParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.n = n;
+    std::vector<uint8_t *> tmp;
+    int r = VSB_OK;
+    uint8_t *small = nullptr;
+    auto cleanup = [&]() { cudaStreamSynchronize(st); for (uint8_t *p : tmp) cudaFree(p); cudaFree(small); };
+    if (cudaMalloc(&small, (size_t)cs->seam_w * cs->seam_h * 3) != cudaSuccess) return fail(VSB_ERR_NOMEM, "estimate_gains: out of device memory");
+    for (int i = 0; i < n && r == VSB_OK; ++i) {
+        if (!d_frames[i]) { r = fail(VSB_ERR_INVALID, "estimate_gains: frame %d is null", i); break; }
+        const int *roi = cs->roi[i];
+        uint8_t *img = nullptr;
+        if (cudaMalloc(&img, (size_t)roi[2] * roi[3] * 3) != cudaSuccess) { r = fail(VSB_ERR_NOMEM, "estimate_gains: out of device memory"); break; }
+        tmp.push_back(img);
+        // cuda::resize(img, seam_img, Size(), seam_scale, seam_scale, INTER_LINEAR): the factors are the scale itself
+        r = vsb_resize_linear_u8(d_frames[i], cs->src_w, cs->src_h, pitch, 3, small, cs->seam_w, cs->seam_h, (size_t)cs->seam_w * 3, cs->seam_scale, cs->seam_scale, st);
+        int roi2[4];
+        if (r == VSB_OK) r = vsb_warp(cs->projection, cs->seam_warp_scale, cs->Ks[i], cs->R[i], small, cs->seam_w, cs->seam_h, (size_t)cs->seam_w * 3, 3,
+                                      VSB_INTER_LINEAR, VSB_BORDER_REFLECT, img, (size_t)roi[2] * 3, roi2, st);
+        P.v[i].img = img; P.v[i].mask = cs->warped_mask[i]; P.v[i].w = roi[2]; P.v[i].h = roi[3]; P.v[i].tx = roi[0]; P.v[i].ty = roi[1];
+    }
+    std::vector<double> g(n, 1.0);
+    if (r == VSB_OK) {
+        std::vector<const uint8_t *> imgs(n), masks(n);
+        std::vector<int> sz(2 * n), co(2 * n);
+        for (int i = 0; i < n; ++i) { imgs[i] = P.v[i].img; masks[i] = P.v[i].mask; sz[2 * i] = P.v[i].w; sz[2 * i + 1] = P.v[i].h; co[2 * i] = P.v[i].tx; co[2 * i + 1] = P.v[i].ty; }
+        r = vsb_gain_compensator_feed(n, imgs.data(), masks.data(), sz.data(), co.data(), g.data(), st);
+    }
+    cleanup();
+    if (r != VSB_OK) return r;
+    std::vector<double> &bb = g;
+    for (int i = 0; i < n; ++i) {
+        if (gains_out) gains_out[i] = (float)bb[i];
+        if (apply) { r = vsb_set_gain(s, i, (float)bb[i]); if (r != VSB_OK) return r; }
+    }
+    return VSB_OK;
 }
 
 }  // extern "C"

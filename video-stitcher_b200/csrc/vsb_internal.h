@@ -41,3 +41,7 @@ __device__ __forceinline__ float custom_resize_at(const float *__restrict__ in, 
 
 // internal: records the rig parameters after vsb_calibrate_rig
 extern "C" int vsb_note_rig(vsb_stitcher *s, int projection, float scale, int src_w, int src_h);
+// internal: seam-scale state of vsb_calibrate_rig_device (owned by vsb_calib.cu, released with the handle)
+extern "C" void vsb_attach_calib(vsb_stitcher *s, void *state, void (*dtor)(void *));
+extern "C" void *vsb_get_calib(const vsb_stitcher *s);
+extern "C" int vsb_handle_device(const vsb_stitcher *s);

@@ -1142,7 +1142,7 @@ struct vsb_stitcher {
     vsb::S1STile *d_s1s_tiles = nullptr;                     // its tile records (footprint boxes: k_s1_boxes, rebuilt with the tap tables)
     vsb::CoarseView *d_coarse_desc = nullptr;
     // view-sharded mode (vsb_shard_set): this rank's views and canvas strip; host copies of the tile tables
-    std::vector<uint32_t> h_bviews, h_cviews;
+    std::vector<uint32_t> h_bviews, h_cviews, h_d2tiles;
     int shard_rank = -1, shard_world = 1, strip_w = 0;
     bool owned[vsb::MAXV] = {};
     // batched exchange plan (vsb_shard_plan): per peer, the rectangles this rank sends / receives, on the device
@@ -1178,6 +1178,8 @@ struct vsb_stitcher {
     int host_pending = 0;       // ... of which not yet waited for
     size_t stage_src_pitch = 0, stage_src_frame = 0, stage_out_pitch = 0, stage_out_frame = 0;
     int stage_src_w = 0, stage_src_h = 0, stage_views = 0, stage_batch = 0;  // what stage_src / stage_nv12 were sized for
+    void *calib_state = nullptr;            // seam-scale state of vsb_calibrate_rig_device (vsb_calib.cu)
+    void (*calib_dtor)(void *) = nullptr;
     int rig_projection = -1, rig_src_w = 0, rig_src_h = 0;
     float rig_scale = 0.f;
     // wire / consumer formats (vsb_set_formats): NV12 input goes through k_nv12_to_bgr into nv_bgr; CV_8UC3 output is k_blend<true>
@@ -1506,6 +1508,7 @@ static int build_fast_plan(vsb_stitcher *s)
     }
     s->tiles_dirty = true;
     s->n_down2_tiles = (int)d2tiles.size();
+    s->h_d2tiles = d2tiles;
     cudaFree(s->d_blend_views); cudaFree(s->d_coarse_views); cudaFree(s->d_down2_tiles); cudaFree(s->C2);
     s->d_blend_views = s->d_coarse_views = s->d_down2_tiles = nullptr; s->C2 = nullptr;
     CK(cudaMalloc(&s->d_blend_views, bviews.size() * 4));
@@ -1554,6 +1557,10 @@ static int finalize(vsb_stitcher *s)
     s->finalized = true;
     return VSB_OK;
 }
+
+// view-sharded handles keep only the tiles of their own views in the device tile lists, so that ONE launch of each front-half
+// kernel covers an arbitrary (not necessarily contiguous) set of owned views
+static inline bool front_view(const vsb_stitcher *s, int i) { return s->shard_rank < 0 || s->owned[i]; }
 
 static int ready_for_frames(vsb_stitcher *s)
 {
@@ -1628,10 +1635,11 @@ static int sync_tile_lists(vsb_stitcher *s)
     if (!s->tiles_dirty) return VSB_OK;
     std::vector<uint32_t> a, b, c;
     for (int i = 0; i < s->cfg.num_views; ++i) {
+        s->v[i].t1_src_pitch = 0;  // the footprint boxes live next to the lists: rebuilt (with the tap table) by the next compose
+        if (!front_view(s, i)) continue;
         a.insert(a.end(), s->v[i].s1_tiles.begin(), s->v[i].s1_tiles.end());
         b.insert(b.end(), s->v[i].s2_tiles.begin(), s->v[i].s2_tiles.end());
         c.insert(c.end(), s->v[i].s1s_tiles.begin(), s->v[i].s1s_tiles.end());
-        s->v[i].t1_src_pitch = 0;  // the footprint boxes live next to the lists: rebuilt (with the tap table) by the next compose
     }
     { int r = wait_own_frames(s); if (r != VSB_OK) return r; }  // submissions in flight still read the old lists
     cudaFree(s->d_s1_tiles); cudaFree(s->d_s2_tiles); cudaFree(s->d_s1s_ids); cudaFree(s->d_s1s_tiles);
@@ -1671,6 +1679,7 @@ static int launch_down2(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
     double bytes = 0;
     for (int i = 0; i < s->cfg.num_views; ++i) {
         int nt = 0;
+        if (!front_view(s, i)) continue;  // (view-sharded: the device list holds the owned views' tiles only)
         for (uint8_t b : s->v[i].g2_needed) nt += b;
         if (i < v0) first += nt;
         else if (i < v1) { count += nt; bytes += (double)nt * 3 * (16.0 * D2_TW * D2_TH + 4.0 * D2_TW * D2_TH + D2_TW * D2_TH); }
@@ -1680,7 +1689,7 @@ static int launch_down2(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
     bool tma = true;
     Down2Maps maps;
     std::memset(&maps, 0, sizeof(maps));
-    for (int i = v0; i < v1; ++i) { tma = tma && s->v[i].g0_map_ok; maps.g0[i] = s->v[i].g0_map; }
+    for (int i = v0; i < v1; ++i) { if (!front_view(s, i)) continue; tma = tma && s->v[i].g0_map_ok; maps.g0[i] = s->v[i].g0_map; }
     if (count > 0) {
         if (tma) k_down2<true><<<dim3(count, 3, n_frames), D2_THREADS, 0, st>>>(p, maps);
         else k_down2<false><<<dim3(count, 3, n_frames), D2_THREADS, 0, st>>>(p, maps);
@@ -1699,6 +1708,7 @@ static int launch_down1_level(vsb_stitcher *s, int k, int v0, int v1, int n_fram
         double bytes = 0;
         int m = 0;
         for (int i = v0; i < v1; ++i) {
+            if (!front_view(s, i)) continue;
             const View &V = s->v[i];
             p.v[m].src = V.Gu[k]; p.v[m].dst = V.Gu[k + 1]; p.v[m].src_fs = V.gu_frame_stride[k]; p.v[m].dst_fs = V.gu_frame_stride[k + 1];
             p.v[m].w = V.bw >> k; p.v[m].h = V.bh >> k;
@@ -1742,9 +1752,11 @@ static int launch_down1(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
         DownTailParams p;
         std::memset(&p, 0, sizeof(p));
         p.nb = nb; p.k0 = k0; p.f0 = s->f0;
+        int m = 0;
         for (int i = v0; i < v1; ++i) {
+            if (!front_view(s, i)) continue;
             const View &V = s->v[i];
-            DownTailView &D = p.v[i - v0];
+            DownTailView &D = p.v[m++];
             D.g2 = V.Gu[k0]; D.g2_fs = V.gu_frame_stride[k0]; D.w2 = V.bw >> k0; D.h2 = V.bh >> k0;
             for (int k = k0 + 1; k <= nb; ++k) { D.g[k] = V.Gu[k]; D.fs[k] = V.gu_frame_stride[k]; }
         }
@@ -1753,7 +1765,7 @@ static int launch_down1(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
             int r = launch_down1_level(s, k, v0, v1, n_frames, st);
             if (r != VSB_OK) return r;
         }
-        k_down_tail<<<dim3(v1 - v0, 3, n_frames), dim3(DT_TX, DT_TY), smem, st>>>(p);
+        if (m > 0) k_down_tail<<<dim3(m, 3, n_frames), dim3(DT_TX, DT_TY), smem, st>>>(p);
         ++s->launches;
         prof_stage(s, st, "down_tail", bytes * n_frames);  // level k0 in once, levels k0 + 1 .. nb out once
         return check_launch("k_down_tail");
@@ -1892,7 +1904,7 @@ static int build_taps1(vsb_stitcher *s, int i, size_t src_pitch, cudaStream_t st
                                                                 (unsigned)src_pitch, V.t1_off, V.t1_w, V.t1_plane, V.t1_pitch);
     {   // footprint boxes of the staged remap #1 tiles of this view (they follow the table: same maps, same pitch)
         int first = 0;
-        for (int j = 0; j < i; ++j) first += (int)s->v[j].s1s_tiles.size();
+        for (int j = 0; j < i; ++j) if (front_view(s, j)) first += (int)s->v[j].s1s_tiles.size();
         const int nt = (int)V.s1s_tiles.size();
         TapTable tab;
         tab.off = V.t1_off; tab.w = V.t1_w; tab.plane = V.t1_plane; tab.tab_pitch = V.t1_pitch;
@@ -1922,16 +1934,18 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
         // table-driven remap #1 whenever the caller's frames allow aligned 32-bit window loads
         bool tab = remap_variant() >= 0 && src_pitch % 4 == 0;
         for (int i = v0; i < v1 && tab; ++i) tab = s->v[i].src_h >= 2 && (unsigned long long)src_pitch * s->v[i].src_h < 0x7fffffffull;
-        for (int j = 0; j < n * n_frames && tab; ++j) tab = ((size_t)d_srcs[j] & 3) == 0;
+        for (int j = 0; j < n * n_frames && tab; ++j) tab = ((size_t)d_srcs[j] & 3) == 0;  // (null entries of views another rank owns pass)
         int first = 0, count = 0;
         double bytes = 0;  // algorithmic: every source pixel once + P once
         for (int i = 0; i < s->cfg.num_views; ++i) {
             const View &V = s->v[i];
+            if (!front_view(s, i)) continue;
             if (i < v0) first += (int)V.s1_tiles.size();
             else if (i < v1) { count += (int)V.s1_tiles.size(); bytes += 3.0 * V.src_w * V.src_h + 3.0 * V.roi_w * V.roi_h; }
         }
         if (tab) {
             for (int i = v0; i < v1; ++i) {
+                if (!front_view(s, i)) continue;
                 r = build_taps1(s, i, src_pitch, st);
                 if (r != VSB_OK) return r;
             }
@@ -1955,6 +1969,7 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
             if (staged) {
                 int sfirst = 0, scount = 0;
                 for (int i = 0; i < s->cfg.num_views; ++i) {
+                    if (!front_view(s, i)) continue;
                     if (i < v0) sfirst += (int)s->v[i].s1s_tiles.size();
                     else if (i < v1) scount += (int)s->v[i].s1s_tiles.size();
                 }
@@ -1991,6 +2006,7 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
         bool tab = remap_variant() >= 0 && s->cfg.enable_local && !warped;
         for (int i = 0; i < s->cfg.num_views; ++i) {
             const View &V = s->v[i];
+            if (!front_view(s, i)) continue;
             if (i < v0) first += (int)V.s2_tiles.size();
             else if (i < v1) {
                 count += (int)V.s2_tiles.size(); bytes += 3.0 * V.roi_w * V.roi_h + 3.0 * V.bw * V.bh;
@@ -2187,6 +2203,7 @@ int vsb_destroy(vsb_stitcher *s)
     if (!s) return VSB_OK;
     DeviceGuard g(s->device);
     cudaDeviceSynchronize();
+    if (s->calib_state && s->calib_dtor) s->calib_dtor(s->calib_state);
     for (int i = 0; i < MAXV; ++i) free_view(s->v[i]);
     for (int k = 0; k < MAXL; ++k) cudaFree(s->dw[k]);
     cudaFree(s->d_plan);
@@ -2843,6 +2860,12 @@ int vsb_shard_set(vsb_stitcher *s, int rank, int world)
             if (!coarse_tile_of_rank(s, tx, rank)) c[(size_t)ty * s->coarse_tiles_x + tx] = 0x80000000u;
     CK(cudaMemcpy(s->d_blend_views, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->d_coarse_views, c.data(), c.size() * 4, cudaMemcpyHostToDevice));
+    {   // front-half tile lists of the owned views only (one launch per kernel for any set of views)
+        std::vector<uint32_t> d2;
+        for (uint32_t tl : s->h_d2tiles) if (s->owned[tl & 0xff]) d2.push_back(tl);
+        if (!d2.empty()) CK(cudaMemcpy(s->d_down2_tiles, d2.data(), d2.size() * 4, cudaMemcpyHostToDevice));
+        s->tiles_dirty = true;
+    }
     return upload_blend_lists(s, b);
 }
 
@@ -3109,19 +3132,11 @@ int vsb_shard_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_src
     r = adopt_meshes(s, s->sh_front);
     if (r != VSB_OK) return r;
     s->f0 = f0;
-    for (int v0 = 0; v0 < n && r == VSB_OK;) {
-        if (!s->owned[v0]) { ++v0; continue; }
-        int v1 = v0;
-        while (v1 < n && s->owned[v1]) ++v1;
-        const uint8_t *srcs[MAX_BATCH * MAXV];
-        for (int f = 0; f < F; ++f)
-            for (int v = v0; v < v1; ++v) {
-                srcs[f * (v1 - v0) + (v - v0)] = d_srcs[f * n + v];
-                if (!d_srcs[f * n + v]) { s->f0 = 0; return fail(VSB_ERR_INVALID, "shard_compose: frame %d of owned view %d is null", f, v); }
-            }
-        r = launch_front(s, v0, v1, F, srcs, src_pitch, s->sh_front);
-        v0 = v1;
-    }
+    for (int f = 0; f < F; ++f)
+        for (int v = 0; v < n; ++v)
+            if (s->owned[v] && !d_srcs[f * n + v]) { s->f0 = 0; return fail(VSB_ERR_INVALID, "shard_compose: frame %d of owned view %d is null", f, v); }
+    // one launch per front-half kernel: the device tile lists hold this rank's views only (vsb_shard_set)
+    r = launch_front(s, 0, n, F, d_srcs, src_pitch, s->sh_front);
     for (int p = 0; p < world && r == VSB_OK; ++p)
         if (p != me && s->n_send[p] > 0) {
             k_shard_copy<true><<<dim3(s->n_send[p], 3, F), dim3(32, 8), 0, s->sh_front>>>(s->d_send[p], s->x_send[b][p], s->send_bytes[p], f0);
@@ -3207,6 +3222,14 @@ int vsb_get_config(const vsb_stitcher *s, vsb_config *out)
     return VSB_OK;
 }
 
+void vsb_attach_calib(vsb_stitcher *s, void *state, void (*dtor)(void *))
+{
+    if (s->calib_state && s->calib_dtor) s->calib_dtor(s->calib_state);
+    s->calib_state = state; s->calib_dtor = dtor;
+}
+void *vsb_get_calib(const vsb_stitcher *s) { return s ? s->calib_state : nullptr; }
+int vsb_handle_device(const vsb_stitcher *s) { return s ? s->device : -1; }
+
 int vsb_note_rig(vsb_stitcher *s, int projection, float scale, int src_w, int src_h)
 {
     s->rig_projection = projection; s->rig_scale = scale; s->rig_src_w = src_w; s->rig_src_h = src_h;
@@ -3280,6 +3303,11 @@ int vsb_debug_read(vsb_stitcher *s, int what, int view, int level, int frame, vo
         REQ(bytes == (size_t)V.roi_w * V.roi_h * 4, VSB_ERR_INVALID, "debug_read: size mismatch");
         return check_cuda(cudaMemcpy2D(h_dst, (size_t)V.roi_w * 4, V.mesh[buf][what - 4], V.map_pitch, (size_t)V.roi_w * 4, V.roi_h, cudaMemcpyDeviceToHost), "debug_read mesh");
     }
+    case 8:
+    case 9:
+        REQ(V.has_maps, VSB_ERR_STATE, "debug_read: no projection maps set");
+        REQ(bytes == (size_t)V.roi_w * V.roi_h * 4, VSB_ERR_INVALID, "debug_read: size mismatch");
+        return check_cuda(cudaMemcpy2D(h_dst, (size_t)V.roi_w * 4, what == 8 ? V.xmap : V.ymap, V.map_pitch, (size_t)V.roi_w * 4, V.roi_h, cudaMemcpyDeviceToHost), "debug_read map");
     case 6: {  // which level-2 samples k_down2 computes (1) / skips because no tile reads them (0)
         REQ(s->fast, VSB_ERR_STATE, "debug_read: the generic path computes every level");
         const int w = V.bw >> 2, h = V.bh >> 2;
