@@ -210,6 +210,73 @@ def hbm_peak():
         return 6650.0, "B200_PROFILING.md fallback 6650 GB/s"
 
 
+def run_replicas_phase(dist, torch, rank, world, local_rank):
+    """Frame-level replicas of the headline single-GPU workload: every rank composes its own frame stream, no data-path
+    collective (weak scaling).  The secondary number of an N > 1 run -- and its fallback `value` if the sharded attempt fails."""
+    import vsb200
+    S, D = vsb200.synth, vsb200.dist
+    rcfg = WORKLOADS["cfg2"]
+    F = 16
+    st2, _ = make_rig(rcfg, F)
+    roi2, _, _ = st2.get_roi()
+    op2 = (roi2[2] * 6 + 255) // 256 * 256
+    n_sets = F
+    sets2 = [[torch.from_numpy(S.frame(i, f + D.ring_seed_offset(rank, n_sets), rcfg["src_w"], rcfg["src_h"])).cuda() for i in range(rcfg["n_views"])] for f in range(n_sets)]
+    outs2 = [torch.empty((roi2[3], op2 // 2), dtype=torch.int16, device="cuda") for _ in range(F)]
+    stream = torch.cuda.current_stream().cuda_stream
+    c2 = [st2.make_compose_call([sets2[(s0 + j) % n_sets][i].data_ptr() for j in range(F) for i in range(rcfg["n_views"])], rcfg["src_w"] * 3,
+                                [o.data_ptr() for o in outs2], op2, stream) for s0 in range(n_sets)]
+    for w in range(3):
+        c2[w]()
+    def sync2():
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    m2, runs, per_run = timed_repeats(lambda k: c2[k % n_sets](), 10, sync2, repeats=3, min_total_s=0.9)
+    m2 = D.reduce_step_time(m2, dist, "cuda")
+    launches = st2.last_launch_count()
+    st2.close()
+    del sets2, outs2
+    torch.cuda.empty_cache()
+    return {"value": world * F / (m2 / 1000.0), "unit": "frames/s", "workload": rcfg["name"], "frames_per_step": F, "ms_per_step": m2,
+            "launches_per_step": launches * world, "steps_per_run": per_run,
+            "note": "frame-level replicas: every rank composes its own frame stream, no data-path collective (weak scaling)"}
+
+
+class Watchdog(threading.Thread):
+    """An N > 1 run must end within the driver's limit even if a rank dies inside a collective or a peer-to-peer exchange (the
+    other ranks then spin in a kernel forever).  Every rank runs one: when the deadline passes, or when any rank has dropped a
+    failure marker, rank 0 prints the fallback line (the replicas measurement, clearly labelled) and every rank leaves with
+    os._exit(0)."""
+
+    def __init__(self, rank, deadline_s, marker, fallback_line):
+        super().__init__(daemon=True)
+        self.rank, self.t_end, self.marker, self.fallback_line, self.done = rank, time.time() + deadline_s, marker, fallback_line, threading.Event()
+
+    def fail(self, why):
+        try:
+            with open(self.marker, "a") as fh:
+                fh.write(f"rank {self.rank}: {why}\n")
+        except Exception:
+            pass
+
+    def run(self):
+        while not self.done.wait(0.5):
+            why = None
+            if os.path.exists(self.marker):
+                try:
+                    why = open(self.marker).read().strip().replace("\n", " | ")[:300]
+                except Exception:
+                    why = "a rank failed"
+            elif time.time() > self.t_end:
+                why = "deadline passed (a rank hangs)"
+            if why:
+                if self.rank == 0:
+                    time.sleep(1.0)  # let the failing rank finish writing its reason
+                    line = self.fallback_line(why)
+                    if line:
+                        print(json.dumps(line), flush=True)
+                os._exit(0)
+
+
 PARITY_RIG = dict(n_views=6, src_w=480, src_h=270, pano_width=1536, num_bands=4, enable_local=True, projection=0)  # tests/golden: "shard6"
 
 
@@ -273,7 +340,46 @@ def run_sharded(args, cfg, rank, world, local_rank):
     if not dist.is_initialized():
         dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29655", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
     n, K, W_, F = cfg["n_views"], args.steps, max(args.warmup, 3), max(1, args.batch)
+    replicas = None if args.no_replicas else run_replicas_phase(dist, torch, rank, world, local_rank)
+    peak, peak_src = hbm_peak()
+
+    def fallback_line(why):  # what rank 0 prints when the view-sharded attempt does not complete: the replicas measurement, labelled as such
+        if replicas is None:
+            return {"metric": METRIC, "value": None, "unit": "frames/s", "n_gpus": world, "error": "view-sharded run failed: " + why}
+        rc = WORKLOADS["cfg2"]
+        b2 = rc["n_views"] * rc["src_w"] * rc["src_h"] * 3 + 3839 * 627 * 6
+        return {"metric": METRIC, "value": replicas["value"], "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W_,
+                "ms_per_step": replicas["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8/s16 (fp32 taps)", "data": "synthetic",
+                "config": {"workload": rc["name"], "frames_per_step": replicas["frames_per_step"],
+                           "multi_gpu": "FALLBACK: frame-level replicas, no collective -- the view-sharded run of '" + cfg["name"] + "' did not complete: " + why},
+                "e2e": None, "gpu_launches": replicas["launches_per_step"] * K, "parity_checked": False,
+                "roofline_path": {"alg_bytes_per_frame": b2, "achieved": b2 * replicas["value"] / world / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": b2 * replicas["value"] / world / 1e9 / peak}, "replicas": replicas, "sharded_error": why}
+
+    marker = os.path.join("/tmp", f"vsb_bench_fail_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}")
+    if rank == 0 and os.path.exists(marker):
+        os.remove(marker)
+    dist.barrier(); torch.cuda.synchronize()
+    dog = Watchdog(rank, args.shard_deadline, marker, fallback_line)
+    dog.start()
+    try:
+        _run_sharded_body(args, cfg, rank, world, local_rank, replicas, dog)
+    except BaseException as e:  # noqa: the process must not linger inside torchrun with peers spinning
+        dog.fail(f"{type(e).__name__}: {str(e)[:200]}")
+        time.sleep(30)  # the watchdog threads (this rank's included) pick the marker up and end the run
+        os._exit(0)
+
+
+def _run_sharded_body(args, cfg, rank, world, local_rank, replicas, dog):
+    import torch
+    import torch.distributed as dist
+    import vsb200
+    B, S, D = vsb200.binding, vsb200.synth, vsb200.dist
+    n, K, W_, F = cfg["n_views"], args.steps, max(args.warmup, 3), max(1, args.batch)
     parity = sharded_parity_check(dist, torch, rank, world)
+    if os.environ.get("VSB_BENCH_INJECT_FAIL") and rank == world - 1:
+        raise RuntimeError("injected failure (VSB_BENCH_INJECT_FAIL): exercises the watchdog / fallback line")
     st, info = make_rig(cfg, 2 * F if 2 * F <= 16 else F)  # two submissions in flight when both fit the handle's frame slots (max 16)
     st.shard_init(rank, world, shard_unique_id(dist, rank))
     roi, _, nb = st.get_roi()
@@ -398,25 +504,6 @@ def run_sharded(args, cfg, rank, world, local_rank):
         except Exception as e:  # e.g. the full rig does not fit next to the sharded buffers
             single = {"error": str(e)[:200]}
     dist.barrier()
-    replicas = None
-    if not args.no_replicas:
-        rcfg = WORKLOADS["cfg2"]
-        st2, _ = make_rig(rcfg, 8)
-        roi2, _, _ = st2.get_roi()
-        op2 = (roi2[2] * 6 + 255) // 256 * 256
-        sets2 = [[torch.from_numpy(S.frame(i, f + D.ring_seed_offset(rank, RING), rcfg["src_w"], rcfg["src_h"])).cuda() for i in range(rcfg["n_views"])] for f in range(RING)]
-        outs2 = [torch.empty((roi2[3], op2 // 2), dtype=torch.int16, device="cuda") for _ in range(8)]
-        c2 = [st2.make_compose_call([sets2[(s0 + j) % RING][i].data_ptr() for j in range(8) for i in range(rcfg["n_views"])], rcfg["src_w"] * 3,
-                                    [o.data_ptr() for o in outs2], op2, main.cuda_stream) for s0 in range(RING)]
-        for w in range(3):
-            c2[w]()
-        def sync2():
-            dist.barrier(); torch.cuda.synchronize()
-        m2, _, _ = timed_repeats(lambda k: c2[k % RING](), 20, sync2, repeats=3, min_total_s=0.6)
-        m2 = D.reduce_step_time(m2, dist, "cuda")
-        replicas = {"value": world * 8 / (m2 / 1000.0), "unit": "frames/s", "workload": rcfg["name"], "frames_per_step": 8,
-                    "note": "frame-level replicas: every rank composes its own frame stream, no data-path collective (weak scaling)"}
-        st2.close()
     if rank == 0:
         b_io = n * cfg["src_w"] * cfg["src_h"] * 3 + OW * OH * 6
         peak, peak_src = hbm_peak()
@@ -436,7 +523,9 @@ def run_sharded(args, cfg, rank, world, local_rank):
             "shards": stats, "exchange_bytes_per_frame": xbytes,
             "exchange": {"bytes_per_frame": xbytes, "nvlink_GBps_per_gpu": xbytes * fps / world / 1e9},
             "single_gpu_same_workload": single, "replicas": replicas}), flush=True)
-    dist.destroy_process_group()
+    dog.done.set()
+    torch.cuda.synchronize()
+    os._exit(0)  # (a clean communicator teardown can itself wait on peers; everything is measured and printed)
 
 
 def ncu_traffic(kernel, frames_per_launch):
@@ -468,6 +557,7 @@ def main():
                     help="N > 1: shard (default) = ONE frame stream, views and canvas strips split across ranks with one exchange of "
                          "Gaussian sub-planes per submission (the north-star split, SURVEY.md 8e); replicas = every rank composes its own frames")
     ap.add_argument("--no-replicas", action="store_true", help="shard mode: skip the secondary frame-level-replicas number")
+    ap.add_argument("--shard-deadline", type=float, default=300.0, help="shard mode: seconds after which a run that has not completed falls back to the replicas line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -496,6 +586,12 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         import datetime
+        import resource
+        try:  # NCCL's peer-to-peer transport passes file descriptors between ranks: lift the soft limit to the hard one
+            soft, hard = resource.getrlimit(resource.RLIMIT_NOFILE)
+            resource.setrlimit(resource.RLIMIT_NOFILE, (hard, hard))
+        except Exception:
+            pass
         # a rank that dies must not leave its peers spinning in a collective for the rest of the driver's time limit
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
 

@@ -528,8 +528,11 @@ __device__ __forceinline__ void up_quad_f(const float *p, int pitch, int px, int
 #ifndef VSB_CO32_MINB
 #define VSB_CO32_MINB 4
 #endif
+#ifndef VSB_CO64_MINB
+#define VSB_CO64_MINB 3
+#endif
 template <int TCT>
-__global__ void __launch_bounds__(C_THREADS, TCT == 64 ? 3 : VSB_CO32_MINB) k_coarse(const __grid_constant__ CoarseParams P)
+__global__ void __launch_bounds__(C_THREADS, TCT == 64 ? VSB_CO64_MINB : VSB_CO32_MINB) k_coarse(const __grid_constant__ CoarseParams P)
 {
     constexpr int C2_UQ = TCT == 64 ? 2 : 1;                            // quads of levels >= 3 per thread
     constexpr int QN = TCT / 2, C2_Q0 = QN * QN / C_THREADS;            // level-2 quads per row / per thread

@@ -17,6 +17,7 @@
 // HBM layout: all per-view intermediates are PLANAR u8 (one plane per colour channel) with the bordered
 // width (a multiple of 2^nb) as row length, so rows of every level start word aligned.
 #include <dlfcn.h>
+#include <sys/resource.h>
 #include <nccl.h>  // types only: the library is loaded with dlopen when the view-sharded mode is initialised (single-GPU use needs no NCCL)
 
 #include <algorithm>
@@ -2123,6 +2124,7 @@ static int note_compose_done(vsb_stitcher *s, cudaStream_t st)
 struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *);
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t *, int, ncclUniqueId, int, ncclConfig_t *);  // optional
     ncclResult_t (*CommDestroy)(ncclComm_t);
     ncclResult_t (*GroupStart)();
     ncclResult_t (*GroupEnd)();
@@ -2143,6 +2145,7 @@ const NcclApi *nccl_api()
         if (h) {
             api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
             api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+            api.CommInitRankConfig = (decltype(api.CommInitRankConfig))dlsym(h, "ncclCommInitRankConfig");
             api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
             api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
             api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
@@ -3085,7 +3088,20 @@ int vsb_shard_init(vsb_stitcher *s, int rank, int world, const void *id128)
     if (world > 1) {
         ncclUniqueId id;
         std::memcpy(&id, id128, sizeof(id));
-        NC(nccl->CommInitRank(&s->comm, world, id, rank));
+        // This communicator lives next to the host application's own (torch's, in bench.py).  NCCL's peer-to-peer transport
+        // exchanges one file descriptor per peer buffer and channel; with 8 ranks and the default channel count two communicators
+        // exhaust a 1024-descriptor soft limit ("unhandled system error" in the first ncclGroupEnd).  So: lift the soft limit to
+        // the hard one, and ask for few channels -- the exchange moves a few MB per frame, eight CTAs saturate it.
+        struct rlimit rl;
+        if (getrlimit(RLIMIT_NOFILE, &rl) == 0 && rl.rlim_cur < rl.rlim_max) { rl.rlim_cur = rl.rlim_max; setrlimit(RLIMIT_NOFILE, &rl); }
+        static const int max_ctas = [] { const char *e = std::getenv("VSB_NCCL_MAXCTAS"); return e ? std::atoi(e) : 8; }();
+        if (nccl->CommInitRankConfig && max_ctas > 0) {
+            ncclConfig_t nc = NCCL_CONFIG_INITIALIZER;
+            nc.maxCTAs = max_ctas;
+            NC(nccl->CommInitRankConfig(&s->comm, world, id, rank, &nc));
+        } else {
+            NC(nccl->CommInitRank(&s->comm, world, id, rank));
+        }
     }
     return VSB_OK;
 }
