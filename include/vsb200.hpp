@@ -78,6 +78,15 @@ public:
         check(vsb_build_maps(projection_, scale_, K, R, src.width, src.height, (float *)xmap.data, (float *)ymap.data, xmap.step, roi, stream));
         return Rect(roi[0], roi[1], roi[2], roi[3]);
     }
+    /* Point warp(const GpuMat &src, K, R, int interp_mode, int border_mode, GpuMat &dst) (S/src/warpers_cuda.cpp:279-298):
+     * dst must be a warpRoi-sized matrix of src's type (CV_8UC1 / CV_8UC3); returns the roi's top-left corner */
+    Point warp(const DeviceMat &src, int channels, const float K[9], const float R[9], int interp_mode, int border_mode, DeviceMat &dst, Stream stream = 0) const
+    {
+        int roi[4];
+        check(vsb_warp(projection_, scale_, K, R, (const uint8_t *)src.data, src.cols, src.rows, src.step, channels, interp_mode, border_mode,
+                       (uint8_t *)dst.data, dst.step, roi, stream));
+        return Point(roi[0], roi[1]);
+    }
 private:
     int projection_;
     float scale_;
@@ -197,6 +206,45 @@ public:
     {
         check(vsb_calibrate_rig(h_, projection, pano_width, src.width, src.height, hfov_deg, gains));
         next_view_ = n_;
+    }
+    /* the same with every per-pixel loop on the device (maps, mask warps, VoronoiSeamFinder, dilate / resize / and, weight pyramids);
+       keeps the seam-scale state estimateGains() needs */
+    void calibrateRigDevice(int projection, int pano_width, Size src, double hfov_deg = 90.0, const float *gains = 0)
+    {
+        check(vsb_calibrate_rig_device(h_, projection, pano_width, src.width, src.height, hfov_deg, gains));
+        next_view_ = n_;
+    }
+    /* GainCompensator::feed + gains() (S/src/exposure_compensate.cpp:71-142,162-168) from the current camera frames, at run time;
+       apply = true installs them (what A/timed.cpp:94 multiplies by) */
+    std::vector<float> estimateGains(const std::vector<DeviceMat> &frames, bool apply, Stream stream = 0)
+    {
+        if ((int)frames.size() != n_) throw Error(VSB_ERR_INVALID, "vsb200: estimateGains: one frame per view");
+        std::vector<const uint8_t *> fp(n_);
+        for (int i = 0; i < n_; ++i) { fp[i] = (const uint8_t *)frames[i].data; if (frames[i].step != frames[0].step) throw Error(VSB_ERR_INVALID, "vsb200: estimateGains: frames must share one pitch"); }
+        std::vector<float> g(n_);
+        check(vsb_estimate_gains(h_, fp.data(), frames[0].step, g.data(), apply ? 1 : 0, stream));
+        return g;
+    }
+    /* host buffers in / out, asynchronous: submit returns once the copies and kernels are enqueued (pinned buffers), wait blocks until
+       the OLDEST outstanding submission's panoramas are in host memory -- the role of BlockingQueue<GpuMat> results (A/timed.cpp:150,243) */
+    void submitHost(const std::vector<const uint8_t *> &h_srcs, size_t src_pitch, const std::vector<int16_t *> &h_outs, size_t out_pitch)
+    {
+        if (h_outs.empty() || h_srcs.size() != h_outs.size() * (size_t)n_) throw Error(VSB_ERR_INVALID, "vsb200: submitHost: need num_views sources per output");
+        check(vsb_submit_host(h_, (int)h_outs.size(), h_srcs.data(), src_pitch, h_outs.data(), out_pitch));
+    }
+    void waitHost() { check(vsb_wait_host(h_)); }
+    /* one frame stream on several GPUs (one process and one calibrated blender per GPU): id = the bytes vsb_shard_unique_id() returned
+       on rank 0, handed to every rank by the host's control plane; stitchSharded composes this rank's strip of every output */
+    void shardInit(int rank, int world, const void *id128) { check(vsb_shard_init(h_, rank, world, id128)); }
+    void stitchSharded(const std::vector<DeviceMat> &srcs /* [f * num_views + i]; data = 0 for views of other ranks */, std::vector<DeviceMat> &outs, Stream stream)
+    {
+        if (outs.empty() || srcs.size() != outs.size() * (size_t)n_) throw Error(VSB_ERR_INVALID, "vsb200: stitchSharded: need num_views sources per output");
+        std::vector<const uint8_t *> sp(srcs.size());
+        std::vector<int16_t *> op(outs.size());
+        size_t pitch = 0;
+        for (size_t k = 0; k < srcs.size(); ++k) { sp[k] = (const uint8_t *)srcs[k].data; if (srcs[k].data) pitch = srcs[k].step; }
+        for (size_t k = 0; k < outs.size(); ++k) op[k] = (int16_t *)outs[k].data;
+        check(vsb_shard_compose(h_, (int)outs.size(), sp.data(), pitch, op.data(), outs[0].step, stream));
     }
     Size viewSize(int i) const { vsb_rig_info info; check(vsb_rig_info_get(h_, &info)); return Size(info.view_roi[i][2], info.view_roi[i][3]); }
 

@@ -457,6 +457,20 @@ def test_nv12_input_and_u8_output(cuda, og, case):
     grig.st.compose([t.data_ptr() for t in srcs], sw, [o.data_ptr() for o in outs], W * 6, stream())
     for f in range(NF):
         _eq(host(outs[f]), want16[f], f"NV12 in, frame {f}")
+    # the conversion runs inside remap #1's tap fetch (k_remap_stage1_nv12): no separate nv12_to_bgr launch
+    assert grig.st.last_launch_count() == (12 if NF >= 4 else 7)
+    # an ODD row pitch cannot take the fused form (16-bit chroma loads): the BGR staging path (k_nv12_to_bgr) gives the same frames
+    odd = sw + 1
+    padded = []
+    for t in srcs:
+        buf = torch.zeros((sh * 3 // 2, odd), dtype=torch.uint8, device="cuda")
+        buf[:, :sw] = t
+        padded.append(buf)
+    outs_p = [torch.full((H, W, 3), -12345, dtype=torch.int16, device="cuda") for _ in range(NF)]
+    grig.st.compose([t.data_ptr() for t in padded], odd, [o.data_ptr() for o in outs_p], W * 6, stream())
+    for f in range(NF):
+        _eq(host(outs_p[f]), want16[f], f"NV12 in (odd pitch, staged conversion), frame {f}")
+    assert grig.st.last_launch_count() == (13 if NF >= 4 else 8)
     # NV12 in, CV_8UC3 out, pitched output
     grig.st.set_formats(B.IN_NV12, B.OUT_U8C3)
     pitch = (W * 3 + 63) // 64 * 64

@@ -529,7 +529,7 @@ __device__ __forceinline__ void up_quad_f(const float *p, int pitch, int px, int
 #define VSB_CO32_MINB 4
 #endif
 #ifndef VSB_CO64_MINB
-#define VSB_CO64_MINB 3
+#define VSB_CO64_MINB 4  // 64 registers, 4 CTAs per SM: measured 145 -> 129 us per 16 frames (no spills)
 #endif
 template <int TCT>
 __global__ void __launch_bounds__(C_THREADS, TCT == 64 ? VSB_CO64_MINB : VSB_CO32_MINB) k_coarse(const __grid_constant__ CoarseParams P)

@@ -258,7 +258,7 @@ constexpr int TAP_SLOW = (int)0x80000000;
 // Image of sw x sh pixels (sw, sh >= 2) whose pixel (0, 0) sits at byte `origin` and whose rows are `pitch` bytes apart.
 // `guard` = true: taps one pixel outside the image exist in memory and read 0 (zero frame around the buffer), so no
 // clamping is needed; false: clamp into the image and move the weights (order of the non-zero terms is preserved).
-__device__ __forceinline__ TapEntry make_tap_entry(float x, float y, int sw, int sh, unsigned pitch, unsigned origin, bool guard)
+__device__ __forceinline__ TapEntry make_tap_entry(float x, float y, int sw, int sh, unsigned pitch, unsigned origin, bool guard, unsigned bpp = 3u)
 {
     TapEntry e;
     e.off = (int)origin; e.wa = e.wb = e.wc = e.wd = 0.f;
@@ -275,7 +275,7 @@ __device__ __forceinline__ TapEntry make_tap_entry(float x, float y, int sw, int
         if (y1 < 0) { ys = 0; wa = wc; wb = wd; wc = wd = 0.f; }
         else if (y1 > sh - 2) { ys = sh - 2; wc = wa; wd = wb; wa = wb = 0.f; }
     }
-    e.off = (int)(origin + (unsigned)(ys * (int)pitch + xs * 3));
+    e.off = (int)(origin + (unsigned)(ys * (int)pitch) + (unsigned)xs * bpp);  // bpp: 3 = interleaved BGR, 1 = the luma plane of an NV12 frame
     e.wa = wa; e.wb = wb; e.wc = wc; e.wd = wd;
     return e;
 }

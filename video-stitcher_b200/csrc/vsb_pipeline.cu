@@ -18,6 +18,7 @@
 // width (a multiple of 2^nb) as row length, so rows of every level start word aligned.
 #include <dlfcn.h>
 #include <sys/resource.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: named ranges per stage for nsys / ncu timelines (no cost without a tool attached)
 #include <nccl.h>  // types only: the library is loaded with dlopen when the view-sharded mode is initialised (single-GPU use needs no NCCL)
 
 #include <algorithm>
@@ -185,8 +186,11 @@ __device__ __forceinline__ bool tap_weight_tiny(const TapEntry &e)
 
 // One thread per table entry of remap #1.  Entries whose 32-bit window loads would leave the caller's image buffer
 // (last bytes of the last row) are marked TAP_SLOW and take the coordinate-driven edge routine in the frame kernel.
+// nv12 != 0: the table addresses the luma plane of an NV12 frame (one byte per pixel, byte loads: no end-of-buffer entries);
+// a tiny weight then raises *unsafe and the host keeps the BGR staging path for this view.
 __global__ void k_build_taps1(const float *__restrict__ xmap, const float *__restrict__ ymap, size_t map_pitch, int w, int h,
-                              int sw, int sh, unsigned pitch, int *__restrict__ off, float *__restrict__ wgt, size_t plane, int tab_pitch)
+                              int sw, int sh, unsigned pitch, int *__restrict__ off, float *__restrict__ wgt, size_t plane, int tab_pitch,
+                              int nv12, int *unsafe)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= tab_pitch || y >= h) return;
@@ -195,11 +199,15 @@ __global__ void k_build_taps1(const float *__restrict__ xmap, const float *__res
     if (x < w) {
         const float fx = *((const float *)((const char *)xmap + (size_t)y * map_pitch) + x);
         const float fy = *((const float *)((const char *)ymap + (size_t)y * map_pitch) + x);
-        e = make_tap_entry(fx, fy, sw, sh, pitch, 0u, false);
-        const unsigned p2 = (unsigned)e.off + pitch;                       // second row of the window
-        const unsigned end = (p2 & ~3u) + ((p2 & 3u) == 3u ? 12u : 8u);    // one past the last byte the word loads touch
-        if (end > (unsigned)(sh - 1) * pitch + (unsigned)sw * 3u) e.off = TAP_SLOW;
-        if (tap_weight_tiny(e)) e.off = TAP_SLOW;                          // the scaled chain could leave the normal range
+        e = make_tap_entry(fx, fy, sw, sh, pitch, 0u, false, nv12 ? 1u : 3u);
+        if (nv12) {
+            if (tap_weight_tiny(e)) atomicOr(unsafe, 1);
+        } else {
+            const unsigned p2 = (unsigned)e.off + pitch;                       // second row of the window
+            const unsigned end = (p2 & ~3u) + ((p2 & 3u) == 3u ? 12u : 8u);    // one past the last byte the word loads touch
+            if (end > (unsigned)(sh - 1) * pitch + (unsigned)sw * 3u) e.off = TAP_SLOW;
+            if (tap_weight_tiny(e)) e.off = TAP_SLOW;                          // the scaled chain could leave the normal range
+        }
     }
     const size_t i = (size_t)y * tab_pitch + x;
     off[i] = e.off;
@@ -615,6 +623,94 @@ __global__ void __launch_bounds__(256, VSB_S1S_MINB) k_remap_stage1_st(const __g
         if (staged) {
             __syncthreads();  // every reader is done before this buffer is filled again
             if (!dbl && f + 1 < f_end) fetch(p.src[(f + 1) * p.n_views + vi - p.v0], box);
+        }
+    }
+}
+
+// ---- K1 on NV12 frames: cv::cvtColor(CV_YUV2BGR_NV12) (A/networking.cpp:46) inside remap #1's tap fetch ----------
+// The table addresses the luma plane; every tap is converted in registers with the integer BT.601 arithmetic of
+// YUV420sp2RGB888Invoker<0, 0> (sources/modules/imgproc/src/color.cpp:8741-8818, the same constants as k_nv12_to_bgr) and enters
+// the bilinear chain as an exact denormal (the integer's bit pattern IS the float b * 2^-149): no BGR staging image is written or
+// read -- 1.5 instead of 3 + 3 bytes of HBM traffic per source pixel.  Lane-interleaved pixels and transposed stores like
+// k_remap_stage1_tab<true>.  Bit-exact against nv12_to_bgr followed by the BGR kernels.
+struct Nv12Tap { int b, g, r; };
+__device__ __forceinline__ Nv12Tap nv12_tap(unsigned y, unsigned uv)
+{
+    const int u = (int)(uv & 0xffu) - 128, v = (int)(uv >> 8) - 128;
+    const int ruv = (1 << 19) + 1673527 * v, guv = (1 << 19) - 852492 * v - 409993 * u, buv = (1 << 19) + 2116026 * u;
+    const int yy = max(0, (int)y - 16) * 1220542;
+    Nv12Tap t;
+    t.b = min(255, max(0, (yy + buv) >> 20)); t.g = min(255, max(0, (yy + guv) >> 20)); t.r = min(255, max(0, (yy + ruv) >> 20));
+    return t;
+}
+__global__ void __launch_bounds__(RM_BX *RM_BY, 4) k_remap_stage1_nv12(const __grid_constant__ Stage1TabParams p, int src_h)
+{
+    __shared__ unsigned sP[RM_BY][RM_BX * RM_PX + 1];
+    const unsigned tile = __ldg(p.tiles + blockIdx.x);
+    const int vi = tile & 0xff;
+    const Stage1TabView &V = p.v[vi];
+    const int tx0 = (int)((tile >> 8) & 0xfff) * (RM_BX * RM_PX), y = (int)(tile >> 20) * RM_BY + threadIdx.y;
+    const int x0 = tx0 + threadIdx.x;
+    if (y >= V.h) return;
+    const size_t i = (size_t)y * V.tab.tab_pitch + x0;
+    unsigned offy[RM_PX], offuv[RM_PX];  // luma window; chroma pair of its first tap, bit 0 = window starts on an odd column, bit 31 of offy = odd row
+    float wa[RM_PX], wb[RM_PX], wc[RM_PX], wd[RM_PX];
+#pragma unroll
+    for (int k = 0; k < RM_PX; ++k) {
+        const bool in = x0 + k * RM_BX < V.tab.tab_pitch;
+        const unsigned o = in ? (unsigned)__ldg(V.tab.off + i + k * RM_BX) : 0u;
+        wa[k] = in ? __ldg(V.tab.w + i + k * RM_BX) : 0.f;
+        wb[k] = in ? __ldg(V.tab.w + V.tab.plane + i + k * RM_BX) : 0.f;
+        wc[k] = in ? __ldg(V.tab.w + 2 * V.tab.plane + i + k * RM_BX) : 0.f;
+        wd[k] = in ? __ldg(V.tab.w + 3 * V.tab.plane + i + k * RM_BX) : 0.f;
+        const unsigned ys = o / p.src_pitch, xs = o - ys * p.src_pitch;
+        offy[k] = o | ((ys & 1u) << 31);
+        offuv[k] = ((unsigned)src_h + (ys >> 1)) * p.src_pitch + (xs & ~1u) + (xs & 1u);
+    }
+    int wp[3], wr[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { const int j = threadIdx.x + 32 * m; wp[m] = (4 * j) / 3; wr[m] = 8 * (4 * j - 3 * wp[m]); }
+    const int row_bytes = 3 * min(RM_BX * RM_PX, V.w - tx0);
+    uint8_t *dst = V.P + (size_t)p.f0 * V.p_frame_stride + (size_t)y * V.p_pitch + (size_t)tx0 * 3;
+#pragma unroll 1
+    for (int f = p.f0; f < p.f0 + p.n_frames; ++f, dst += V.p_frame_stride) {
+        const uint8_t *src = p.src[f * p.n_views + vi - p.v0];
+        unsigned px[RM_PX];
+#pragma unroll
+        for (int k = 0; k < RM_PX; ++k) {
+            const uint8_t *py = src + (offy[k] & 0x7fffffffu);
+            const unsigned dx2 = (offuv[k] & 1u) * 2u, dyp = (offy[k] >> 31) * p.src_pitch;
+            const uint8_t *puv = src + (offuv[k] & ~1u);
+            const unsigned y00 = __ldg(py), y01 = __ldg(py + 1), y10 = __ldg(py + p.src_pitch), y11 = __ldg(py + p.src_pitch + 1);
+            const unsigned uv00 = __ldg((const unsigned short *)puv), uv01 = __ldg((const unsigned short *)(puv + dx2));
+            const unsigned uv10 = __ldg((const unsigned short *)(puv + dyp)), uv11 = __ldg((const unsigned short *)(puv + dyp + dx2));
+            const Nv12Tap a = nv12_tap(y00, uv00), b = nv12_tap(y01, uv01), c = nv12_tap(y10, uv10), d = nv12_tap(y11, uv11);
+            float o[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const int ta = ch == 0 ? a.b : (ch == 1 ? a.g : a.r), tb = ch == 0 ? b.b : (ch == 1 ? b.g : b.r);
+                const int tc = ch == 0 ? c.b : (ch == 1 ? c.g : c.r), td = ch == 0 ? d.b : (ch == 1 ? d.g : d.r);
+                float v = __fmul_rn(__int_as_float(ta), wa[k]);
+                v = __fmaf_rn(__int_as_float(tb), wb[k], v);
+                v = __fmaf_rn(__int_as_float(tc), wc[k], v);
+                v = __fmaf_rn(__int_as_float(td), wd[k], v);
+                v = __fmaf_rn(v, 8388608.f, 12582912.f);
+                o[ch] = rni_biased(fminf(__fmul_rn(V.gain, __fsub_rn(v, 12582912.f)), 255.f));
+            }
+            px[k] = __byte_perm(__byte_perm(__float_as_uint(o[0]), __float_as_uint(o[1]), 0x0040u), __float_as_uint(o[2]), 0x0410u) & 0xffffffu;
+        }
+        unsigned *row = sP[threadIdx.y];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < RM_PX; ++k) row[threadIdx.x + k * RM_BX] = px[k];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const int b0 = 4 * (threadIdx.x + 32 * m);
+            if (b0 >= row_bytes) continue;
+            const unsigned word = (row[wp[m]] >> wr[m]) | (row[wp[m] + 1] << (24 - wr[m]));
+            if (b0 + 4 <= row_bytes) *(unsigned *)(dst + b0) = word;
+            else for (int e = 0; b0 + e < row_bytes; ++e) dst[b0 + e] = (word >> (8 * e)) & 0xff;
         }
     }
 }
@@ -1092,6 +1188,8 @@ struct View {
     unsigned p_origin = 0;              // P - P_alloc
     // tap tables (see TapTable): remap #1, valid for caller row pitch t1_src_pitch; remap #2, one per mesh buffer
     int *t1_off = nullptr; float *t1_w = nullptr; size_t t1_plane = 0; int t1_pitch = 0; size_t t1_src_pitch = 0;
+    bool t1_nv12 = false, t1_nv12_unsafe = false;  // the table addresses an NV12 luma plane (fused conversion) / it holds a weight that path cannot take
+    int *t1_flag = nullptr;                         // device int raised by the builder
     int *t2_off[2] = {nullptr, nullptr}; float *t2_w[2] = {nullptr, nullptr}; size_t t2_plane = 0; int t2_pitch = 0;
     bool t2_unsafe[2] = {false, false};  // the table of that mesh buffer holds a weight the scaled tap chain cannot take: coordinate kernel
     uint8_t *G0 = nullptr;
@@ -1202,6 +1300,12 @@ struct vsb_stitcher {
 
 namespace vsb {
 
+// NVTX range per stage (the reference keeps std::chrono stamps per stage in times[5], A/timed.cpp:43-44, never printed)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 #define CK(expr) do { int _r = check_cuda((expr), #expr); if (_r != VSB_OK) return _r; } while (0)
 #define REQ(cond, code, ...) do { if (!(cond)) return fail((code), __VA_ARGS__); } while (0)
 
@@ -1218,7 +1322,7 @@ static void free_view(View &V)
     cudaFree(V.mesh_scratch);
     for (int k = 0; k < MAXL; ++k) { cudaFree(V.weight[k]); cudaFree(V.G[k]); }
     cudaFree(V.P_alloc); cudaFree(V.G0); cudaFree(V.G1); cudaFree(V.G2); cudaFree(V.M0);
-    cudaFree(V.t1_off); cudaFree(V.t1_w);
+    cudaFree(V.t1_off); cudaFree(V.t1_w); cudaFree(V.t1_flag);
     for (int b = 0; b < 2; ++b) { cudaFree(V.t2_off[b]); cudaFree(V.t2_w[b]); }
     for (int k = 3; k < MAXL; ++k) cudaFree(V.Gu[k]);
     if (V.mesh_ready) cudaEventDestroy(V.mesh_ready);
@@ -1667,6 +1771,7 @@ static void all_tiles(int view, int w, int h, std::vector<uint32_t> &out)
 // K3: G0 -> G2 for the needed tiles of views [v0, v1)
 static int launch_down2(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStream_t st)
 {
+    NvtxRange nvtx("vsb: pyrDown levels 0-2 (k_down2)");
     Down2Params p;
     std::memset(&p, 0, sizeof(p));
     for (int i = 0; i < s->cfg.num_views; ++i) {
@@ -1731,6 +1836,7 @@ static int launch_down1_level(vsb_stitcher *s, int k, int v0, int v1, int n_fram
 // K3b: Gaussian levels 3..nb of views [v0, v1) (tiny planes), one launch per level
 static int launch_down1(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStream_t st)
 {
+    NvtxRange nvtx("vsb: pyrDown levels 3..nb (k_down_tail)");
     const int nb = s->nb;
     // Levels whose outputs fit in shared memory together (all of them up to ~8k-wide panoramas, all but level 3 at 16k) are
     // produced by ONE k_down_tail launch starting at level k0; the levels before it take one k_down1 launch each.
@@ -1781,6 +1887,7 @@ static int launch_down1(vsb_stitcher *s, int v0, int v1, int n_frames, cudaStrea
 // K4 + K5
 static int launch_back_fast(vsb_stitcher *s, int n_frames, int16_t *const *d_outs, size_t out_pitch, cudaStream_t st)
 {
+    NvtxRange nvtx("vsb: blend (k_coarse, k_blend_seam, k_blend_int)");
     const int n = s->cfg.num_views, nb = s->nb;
     {
         CoarseParams p;
@@ -1886,10 +1993,10 @@ static int launch_nv12(vsb_stitcher *s, int v0, int v1, int n_frames, const uint
 }
 
 // (re)builds the remap #1 tap table of view i for the caller's row pitch; stream-ordered before the kernels that read it
-static int build_taps1(vsb_stitcher *s, int i, size_t src_pitch, cudaStream_t st)
+static int build_taps1(vsb_stitcher *s, int i, size_t src_pitch, cudaStream_t st, bool nv12 = false)
 {
     View &V = s->v[i];
-    if (V.t1_src_pitch == src_pitch) return VSB_OK;
+    if (V.t1_src_pitch == src_pitch && V.t1_nv12 == nv12) return VSB_OK;
     if (V.t1_src_pitch != 0) {  // an earlier submission on another stream may still read the old table: order the rebuild after it
         std::lock_guard<std::mutex> lk(s->mu);
         if (s->last_compose_valid) CK(cudaStreamWaitEvent(st, s->last_compose, 0));
@@ -1899,11 +2006,19 @@ static int build_taps1(vsb_stitcher *s, int i, size_t src_pitch, cudaStream_t st
         V.t1_plane = (size_t)V.t1_pitch * V.roi_h;
         CK(cudaMalloc(&V.t1_off, V.t1_plane * sizeof(int)));
         CK(cudaMalloc(&V.t1_w, V.t1_plane * 4 * sizeof(float)));
+        CK(cudaMalloc(&V.t1_flag, sizeof(int)));
     }
     const dim3 b(32, 8);
+    CK(cudaMemsetAsync(V.t1_flag, 0, sizeof(int), st));
     k_build_taps1<<<grid2d(V.t1_pitch, V.roi_h, b), b, 0, st>>>(V.xmap, V.ymap, V.map_pitch, V.roi_w, V.roi_h, V.src_w, V.src_h,
-                                                                (unsigned)src_pitch, V.t1_off, V.t1_w, V.t1_plane, V.t1_pitch);
-    {   // footprint boxes of the staged remap #1 tiles of this view (they follow the table: same maps, same pitch)
+                                                                (unsigned)src_pitch, V.t1_off, V.t1_w, V.t1_plane, V.t1_pitch, nv12 ? 1 : 0, V.t1_flag);
+    V.t1_nv12_unsafe = false;
+    if (nv12) {  // (calibration-time: the table is rebuilt only when the pitch or the input format changes)
+        int flag = 0;
+        CK(cudaMemcpyAsync(&flag, V.t1_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        V.t1_nv12_unsafe = flag != 0;
+    } else {   // footprint boxes of the staged remap #1 tiles of this view (they follow the table: same maps, same pitch)
         int first = 0;
         for (int j = 0; j < i; ++j) if (front_view(s, j)) first += (int)s->v[j].s1s_tiles.size();
         const int nt = (int)V.s1s_tiles.size();
@@ -1911,7 +2026,7 @@ static int build_taps1(vsb_stitcher *s, int i, size_t src_pitch, cudaStream_t st
         tab.off = V.t1_off; tab.w = V.t1_w; tab.plane = V.t1_plane; tab.tab_pitch = V.t1_pitch;
         if (nt > 0) k_s1_boxes<<<nt, 256, 0, st>>>(s->d_s1s_ids + first, s->d_s1s_tiles + first, tab, V.roi_w, V.roi_h, (unsigned)src_pitch, V.src_w, V.src_h);
     }
-    V.t1_src_pitch = src_pitch;
+    V.t1_src_pitch = src_pitch; V.t1_nv12 = nv12;
     return check_launch("k_build_taps1 / k_s1_boxes");
 }
 
@@ -1920,18 +2035,60 @@ enum { FRONT_REMAP = 1, FRONT_PYRAMID = 2, FRONT_ALL = 3 };
 static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch, cudaStream_t st,
                         const uint8_t *warped = nullptr, int stages = FRONT_ALL)
 {
+    NvtxRange nvtx(stages == FRONT_PYRAMID ? "vsb: feed (pyramid)" : "vsb: feed (remap #1 + gain, remap #2 + border, pyramid)");
     const int n = v1 - v0;
     int ws[MAXV], hs[MAXV];
     int r = sync_tile_lists(s);
     if (r != VSB_OK) return r;
     const uint8_t *bgr_ptrs[MAX_BATCH * MAXV];
+    bool nv12_fused = false;
     if (!(stages & FRONT_REMAP)) goto pyramid;
     if (!warped && s->in_format == VSB_IN_NV12) {
-        r = launch_nv12(s, v0, v1, n_frames, d_srcs, src_pitch, st, bgr_ptrs);
-        if (r != VSB_OK) return r;
-        d_srcs = bgr_ptrs; src_pitch = s->nv_pitch;
+        // fused form: remap #1 converts its taps itself (k_remap_stage1_nv12), no BGR staging image.  Needs 2-byte aligned frames
+        // and an even pitch (16-bit chroma loads), 31-bit offsets, and tables free of weights its scaled chain cannot take.
+        static const bool want = [] { const char *e = std::getenv("VSB_NV12_FUSED"); return !e || std::atoi(e) != 0; }();
+        nv12_fused = want && remap_variant() >= 0 && src_pitch % 2 == 0;
+        for (int i = v0; i < v1 && nv12_fused; ++i)
+            nv12_fused = s->v[i].src_w >= 2 && s->v[i].src_h >= 2 && s->v[i].src_h % 2 == 0 && (unsigned long long)src_pitch * (s->v[i].src_h * 3 / 2) < 0x7fffffffull;
+        for (int j = 0; j < n * n_frames && nv12_fused; ++j) nv12_fused = ((size_t)d_srcs[j] & 1) == 0;
+        for (int i = v0; i < v1 && nv12_fused; ++i) {
+            if (!front_view(s, i)) continue;
+            r = build_taps1(s, i, src_pitch, st, true);
+            if (r != VSB_OK) return r;
+            nv12_fused = !s->v[i].t1_nv12_unsafe;
+        }
+        if (!nv12_fused) {
+            r = launch_nv12(s, v0, v1, n_frames, d_srcs, src_pitch, st, bgr_ptrs);
+            if (r != VSB_OK) return r;
+            d_srcs = bgr_ptrs; src_pitch = s->nv_pitch;
+        }
     }
-    if (!warped) {
+    if (!warped && nv12_fused) {
+        int first = 0, count = 0;
+        double bytes = 0;  // algorithmic: every NV12 source byte once + P once
+        for (int i = 0; i < s->cfg.num_views; ++i) {
+            const View &V = s->v[i];
+            if (!front_view(s, i)) continue;
+            if (i < v0) first += (int)V.s1_tiles.size();
+            else if (i < v1) { count += (int)V.s1_tiles.size(); bytes += 1.5 * V.src_w * V.src_h + 3.0 * V.roi_w * V.roi_h; }
+        }
+        Stage1TabParams p;
+        std::memset(&p, 0, sizeof(p));
+        for (int i = 0; i < s->cfg.num_views; ++i) {
+            const View &V = s->v[i];
+            Stage1TabView &S = p.v[i];
+            S.tab.off = V.t1_off; S.tab.w = V.t1_w; S.tab.plane = V.t1_plane; S.tab.tab_pitch = V.t1_pitch;
+            S.xmap = V.xmap; S.ymap = V.ymap; S.P = V.P; S.gain = V.gain;
+            S.map_pitch = V.map_pitch; S.p_pitch = V.p_pitch; S.p_frame_stride = V.p_frame_stride;
+            S.w = V.roi_w; S.h = V.roi_h; S.src_w = V.src_w; S.src_h = V.src_h;
+        }
+        p.tiles = s->d_s1_tiles + first;
+        p.v0 = v0; p.n_views = n; p.src_pitch = (unsigned)src_pitch; p.n_frames = n_frames; p.f0 = s->f0;
+        for (int f = 0; f < n_frames; ++f) for (int j = 0; j < n; ++j) p.src[(s->f0 + f) * n + j] = d_srcs[f * n + j];
+        if (count > 0) k_remap_stage1_nv12<<<(unsigned)count, dim3(RM_BX, RM_BY), 0, st>>>(p, s->v[v0].src_h);
+        ++s->launches;
+        prof_stage(s, st, "remap_stage1_nv12", bytes * n_frames);
+    } else if (!warped) {
         // table-driven remap #1 whenever the caller's frames allow aligned 32-bit window loads
         bool tab = remap_variant() >= 0 && src_pitch % 4 == 0;
         for (int i = v0; i < v1 && tab; ++i) tab = s->v[i].src_h >= 2 && (unsigned long long)src_pitch * s->v[i].src_h < 0x7fffffffull;
@@ -2447,6 +2604,7 @@ int vsb_set_gain(vsb_stitcher *s, int i, float gain)
 // MeshWarper::convertMeshesToMap for one view (360_stitcher/meshwarper.cpp:823-886), entirely on the device
 int vsb_set_mesh(vsb_stitcher *s, int i, const float *mesh_x, const float *mesh_y, int rows, int cols)
 {
+    NvtxRange nvtx("vsb: convertMeshesToMap (vsb_set_mesh)");
     REQ(s && mesh_x && mesh_y, VSB_ERR_INVALID, "set_mesh: null argument");
     REQ(i >= 0 && i < s->cfg.num_views && s->v[i].inited, VSB_ERR_STATE, "set_mesh: view %d is not initialised", i);
     REQ(rows >= 2 && cols >= 2 && rows * cols <= 4096, VSB_ERR_INVALID, "set_mesh: mesh must be between 2x2 and 4096 vertices");
@@ -2630,6 +2788,7 @@ int vsb_blend(vsb_stitcher *s, int16_t *d_out, size_t out_pitch, void *stream)
 
 int vsb_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch, int16_t *const *d_outs, size_t out_pitch, void *stream)
 {
+    NvtxRange nvtx("vsb_compose");
     REQ(s && d_srcs && d_outs, VSB_ERR_INVALID, "compose: null argument");
     REQ(n_frames >= 1 && n_frames <= s->cfg.max_batch, VSB_ERR_INVALID, "compose: n_frames must be 1..max_batch (%d)", s->cfg.max_batch);
     REQ(s->shard_rank < 0, VSB_ERR_STATE, "compose: handle is view-sharded; feed the owned views, exchange, then blend");
@@ -2756,6 +2915,7 @@ int vsb_wait_host(vsb_stitcher *s)
 
 int vsb_submit_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs, size_t src_pitch, int16_t *const *h_outs, size_t out_pitch)
 {
+    NvtxRange nvtx("vsb_submit_host (H2D, compose, D2H)");
     REQ(s && h_srcs && h_outs, VSB_ERR_INVALID, "submit_host: null argument");
     REQ(n_frames >= 1 && n_frames <= s->cfg.max_batch, VSB_ERR_INVALID, "submit_host: n_frames must be 1..max_batch (%d)", s->cfg.max_batch);
     int r = ready_for_frames(s);
@@ -3114,6 +3274,7 @@ int vsb_shard_init(vsb_stitcher *s, int rank, int world, const void *id128)
 // submission k's exchange and back half.  Outputs are ordered on `stream`.
 int vsb_shard_compose(vsb_stitcher *s, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch, int16_t *const *d_outs, size_t out_pitch, void *stream)
 {
+    NvtxRange nvtx("vsb_shard_compose (front, exchange, back)");
     REQ(s && d_srcs && d_outs, VSB_ERR_INVALID, "shard_compose: null argument");
     REQ(s->shard_rank >= 0 && s->sh_front, VSB_ERR_STATE, "shard_compose: vsb_shard_init first");
     REQ(n_frames >= 1 && n_frames <= s->cfg.max_batch, VSB_ERR_INVALID, "shard_compose: n_frames must be 1..max_batch (%d)", s->cfg.max_batch);
