@@ -46,6 +46,7 @@ WORKLOADS = {
 }
 RING = 8  # distinct frame sets resident in HBM (8 x 37 MB = 299 MB > 126 MB L2 at cfg2)
 METRIC = "stitched equirect frames/sec"
+CTL_DEV = "cpu"  # device of the control-plane tensors (gloo: cpu; --ctl-backend nccl: cuda)
 
 
 class ClockSampler(threading.Thread):
@@ -231,7 +232,7 @@ def run_replicas_phase(dist, torch, rank, world, local_rank):
     def sync2():
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     m2, runs, per_run = timed_repeats(lambda k: c2[k % n_sets](), 10, sync2, repeats=3, min_total_s=0.9)
-    m2 = D.reduce_step_time(m2, dist, "cuda")
+    m2 = D.reduce_step_time(m2, dist, CTL_DEV)
     launches = st2.last_launch_count()
     st2.close()
     del sets2, outs2
@@ -318,7 +319,7 @@ def sharded_parity_check(dist, torch, rank, world):
     out = torch.zeros((H, W, 3), dtype=torch.int16, device="cuda")
     st.shard_compose([t.data_ptr() if t is not None else 0 for t in srcs], cfg["src_w"] * 3, [out.data_ptr()], W * 6, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    full = out.to(torch.int32)
+    full = out.to(torch.int32).to(CTL_DEV)
     dist.all_reduce(full)  # strips are disjoint and the rest of every rank's buffer is zero
     got = full.to(torch.int16).cpu().numpy()
     want = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_compose_hashes.json")))["shard6"]
@@ -338,7 +339,7 @@ def run_sharded(args, cfg, rank, world, local_rank):
     import vsb200
     B, S, D = vsb200.binding, vsb200.synth, vsb200.dist
     if not dist.is_initialized():
-        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29655", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29655", rank=0, world_size=1)
     n, K, W_, F = cfg["n_views"], args.steps, max(args.warmup, 3), max(1, args.batch)
     replicas = None if args.no_replicas else run_replicas_phase(dist, torch, rank, world, local_rank)
     peak, peak_src = hbm_peak()
@@ -429,7 +430,7 @@ def _run_sharded_body(args, cfg, rank, world, local_rank, replicas, dog):
         for k in range(K):
             step(k)
     sync()
-    probe = D.reduce_step_time(tm.e0.elapsed_time(tm.e1), dist, "cuda") / K
+    probe = D.reduce_step_time(tm.e0.elapsed_time(tm.e1), dist, CTL_DEV) / K
     per_run = max(K, int(2000.0 / 5 / max(probe, 1e-3)) + 1)
     runs = []
     for r in range(5):
@@ -438,7 +439,7 @@ def _run_sharded_body(args, cfg, rank, world, local_rank, replicas, dog):
             for k in range(per_run):
                 step(k)
         sync()
-        runs.append(D.reduce_step_time(tm.e0.elapsed_time(tm.e1), dist, "cuda") / per_run)  # MAX over ranks
+        runs.append(D.reduce_step_time(tm.e0.elapsed_time(tm.e1), dist, CTL_DEV) / per_run)  # MAX over ranks
     t1 = time.time()
     sampler.stop()
     ms = sorted(runs)[2]
@@ -469,9 +470,9 @@ def _run_sharded_body(args, cfg, rank, world, local_rank, replicas, dog):
         for k in range(Ke):
             host_step(k)
         torch.cuda.synchronize()
-        dt = D.reduce_step_time(time.perf_counter() - tw, dist, "cuda")
+        dt = D.reduce_step_time(time.perf_counter() - tw, dist, CTL_DEV)
         bytes_in = sum(host_sets[0][i].numel() for i in owned) * F
-        tot = torch.tensor([float(bytes_in), float(OH * max(0, xe - x0) * 6 * F)], dtype=torch.float64, device="cuda")
+        tot = torch.tensor([float(bytes_in), float(OH * max(0, xe - x0) * 6 * F)], dtype=torch.float64, device=CTL_DEV)
         dist.all_reduce(tot)
         e2e = {"value": F * Ke / dt, "unit": "frames/s", "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[1].item()), "steps": Ke,
                "api": "per rank: pinned host frames of the owned views -> device, vsb_shard_compose, the rank's strip of the panorama -> host"}
@@ -514,6 +515,7 @@ def _run_sharded_body(args, cfg, rank, world, local_rank, replicas, dog):
             "config": {"workload": cfg["name"], "frames_per_step": F, "pano": f"{OW}x{OH} CV_16SC3", "bands": nb,
                        "multi_gpu": "view-sharded (north-star split): views + canvas strips per rank, ONE exchange of Gaussian u8 sub-planes per submission "
                                     "(grouped ncclSend/ncclRecv inside libvsb200, one packed message per peer), exchange k overlapped with front half k+1",
+                       "control_plane": f"torch.distributed {args.ctl_backend} (barriers / timing reductions only); data path: the library's own NCCL communicator",
                        "l2_policy": f"ring of {n_sets} frame sets per owned view", "timing": f"median of 5 runs of {per_run} steps (>= 2 s in total), CUDA events, max over ranks"},
             "clocks": sampler.summary(t0, t1), "e2e": e2e, "gpu_launches": sum(s_["launches_per_step"] for s_ in stats) * K, "launches_per_step": sum(s_["launches_per_step"] for s_ in stats),
             "ms_per_frame": ms / F, "runs_ms_per_step": runs,
@@ -557,6 +559,7 @@ def main():
                     help="N > 1: shard (default) = ONE frame stream, views and canvas strips split across ranks with one exchange of "
                          "Gaussian sub-planes per submission (the north-star split, SURVEY.md 8e); replicas = every rank composes its own frames")
     ap.add_argument("--no-replicas", action="store_true", help="shard mode: skip the secondary frame-level-replicas number")
+    ap.add_argument("--ctl-backend", choices=["gloo", "nccl"], default="gloo", help="N > 1: torch.distributed backend of the control plane (barriers, timing reductions); the frame data never goes through it")
     ap.add_argument("--shard-deadline", type=float, default=300.0, help="shard mode: seconds after which a run that has not completed falls back to the replicas line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -592,8 +595,18 @@ def main():
             resource.setrlimit(resource.RLIMIT_NOFILE, (hard, hard))
         except Exception:
             pass
-        # a rank that dies must not leave its peers spinning in a collective for the rest of the driver's time limit
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
+        # Control plane (barriers, max-over-ranks of the timings, the unique id) over gloo on the loopback interface; the data
+        # path's NCCL communicator is the one libvsb200 owns (vsb_shard_init), so each process holds ONE set of NCCL peer
+        # connections.  --ctl-backend nccl gives torch its own communicator instead.  The timeout: a rank that dies must not
+        # leave its peers waiting in a collective for the rest of the driver's time limit.
+        global CTL_DEV
+        if args.ctl_backend == "gloo":
+            os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+            dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=180))
+            CTL_DEV = "cpu"
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
+            CTL_DEV = "cuda"
 
     if args.mode == "shard":
         run_sharded(args, cfg, rank, world, local_rank)
@@ -667,9 +680,9 @@ def main():
         calls[k % n_sets]()
     e1.record()
     barrier()
-    ms_k = vsb200.dist.reduce_step_time(e0.elapsed_time(e1), dist if world > 1 else None, "cuda") / K  # MAX over ranks
+    ms_k = vsb200.dist.reduce_step_time(e0.elapsed_time(e1), dist if world > 1 else None, CTL_DEV) / K  # MAX over ranks
     ms_med, runs, per_run = timed_repeats(lambda k: calls[k % n_sets](), K, barrier, repeats=5, min_total_s=2.0, probe=ms_k)
-    runs = [vsb200.dist.reduce_step_time(r_, dist if world > 1 else None, "cuda") for r_ in runs]
+    runs = [vsb200.dist.reduce_step_time(r_, dist if world > 1 else None, CTL_DEV) for r_ in runs]
     ms_step = sorted(runs)[len(runs) // 2]
     t_wall1 = time.time()
     sampler.stop()
@@ -696,7 +709,7 @@ def main():
             a0.record(); calls1[k % n_sets](); a1.record()
             torch.cuda.synchronize()
             lat.append(a0.elapsed_time(a1))
-        f1 = {"value_f1": world * 1000.0 / vsb200.dist.reduce_step_time(m1, dist if world > 1 else None, "cuda"), "unit": "frames/s",
+        f1 = {"value_f1": world * 1000.0 / vsb200.dist.reduce_step_time(m1, dist if world > 1 else None, CTL_DEV), "unit": "frames/s",
               "latency_ms_f1": sorted(lat)[len(lat) // 2], "launches_per_frame": st.last_launch_count(),
               "note": "vsb_compose with n_frames = 1: the remap tap tables are read once per frame instead of once per submission"}
 
@@ -745,7 +758,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         host_run(Ke)
-        dt = vsb200.dist.reduce_step_time(time.perf_counter() - t0, dist if world > 1 else None, "cuda")
+        dt = vsb200.dist.reduce_step_time(time.perf_counter() - t0, dist if world > 1 else None, CTL_DEV)
         e2e = {"value": world * F * Ke / dt, "unit": "frames/s", "h2d_bytes_per_step": F * n * cfg["src_w"] * cfg["src_h"] * 3,
                "d2h_bytes_per_step": F * OW * OH * 6, "steps": Ke,
                "api": "vsb_submit_host / vsb_wait_host: pinned host frames in, host panoramas out; upload / compose / download pipelined over "
@@ -782,7 +795,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         wire_run(Ke)
-        dt = vsb200.dist.reduce_step_time(time.perf_counter() - t0, dist if world > 1 else None, "cuda")
+        dt = vsb200.dist.reduce_step_time(time.perf_counter() - t0, dist if world > 1 else None, CTL_DEV)
         st.set_formats(B.IN_BGR8, B.OUT_S16C3)
         e2e_wire = {"value": world * F * Ke / dt, "unit": "frames/s", "h2d_bytes_per_step": F * n * sw_ * sh_ * 3 // 2,
                     "d2h_bytes_per_step": F * OW * OH * 3, "steps": Ke,

@@ -3262,6 +3262,32 @@ int vsb_shard_init(vsb_stitcher *s, int rank, int world, const void *id128)
         } else {
             NC(nccl->CommInitRank(&s->comm, world, id, rank));
         }
+        // Connect the peers of the plan now, one peer pair per group (step d: send to rank + d, receive from rank - d), instead
+        // of all at once inside the first exchange: a transport that cannot be set up fails here, with the peer named, and the
+        // first vsb_shard_compose does not pay the set-up.
+        static const int eager = [] { const char *e = std::getenv("VSB_NCCL_EAGER"); return e ? std::atoi(e) : 1; }();
+        if (eager) {
+            uint8_t *d_tok = nullptr;
+            CK(cudaMalloc(&d_tok, 2 * 16));
+            CK(cudaMemsetAsync(d_tok, 0, 2 * 16, s->sh_comm));
+            for (int d = 1; d < world; ++d) {
+                const int to = (rank + d) % world, from = (rank - d + world) % world;
+                const bool tx = s->send_bytes[to] != 0, rx = s->recv_bytes[from] != 0;
+                if (!tx && !rx) continue;
+                ncclResult_t e = nccl->GroupStart();
+                if (e == ncclSuccess && tx) e = nccl->Send(d_tok, 16, ncclUint8, to, s->comm, s->sh_comm);
+                if (e == ncclSuccess && rx) e = nccl->Recv(d_tok + 16, 16, ncclUint8, from, s->comm, s->sh_comm);
+                const ncclResult_t e2 = nccl->GroupEnd();
+                if (e == ncclSuccess) e = e2;
+                if (e != ncclSuccess) {
+                    cudaFree(d_tok);
+                    return fail(VSB_ERR_CUDA, "shard_init: connecting rank %d -> %d / %d -> %d: %s", rank, to, from, rank, nccl->GetErrorString(e));
+                }
+            }
+            cudaError_t ce = cudaStreamSynchronize(s->sh_comm);
+            cudaFree(d_tok);
+            CK(ce);
+        }
     }
     return VSB_OK;
 }
