@@ -487,7 +487,7 @@ def _run_sharded_body(args, cfg, rank, world, local_rank, replicas, dog):
     # ---- secondary numbers: (a) ONE GPU on the same workload through the same handle type (what the sharded rate is a speed-up of),
     #      (b) frame-level replicas of the headline single-GPU workload (every rank its own stream, no collective)
     single = None
-    if rank == 0:
+    if rank == 0 and not args.no_single:
         try:
             Fs = min(F, 4) if cfg["n_views"] > 8 else F
             st1, _ = make_rig(cfg, Fs)
@@ -559,6 +559,7 @@ def main():
                     help="N > 1: shard (default) = ONE frame stream, views and canvas strips split across ranks with one exchange of "
                          "Gaussian sub-planes per submission (the north-star split, SURVEY.md 8e); replicas = every rank composes its own frames")
     ap.add_argument("--no-replicas", action="store_true", help="shard mode: skip the secondary frame-level-replicas number")
+    ap.add_argument("--no-single", action="store_true", help="shard mode: skip the one-GPU run of the same workload on rank 0")
     ap.add_argument("--ctl-backend", choices=["gloo", "nccl"], default="gloo", help="N > 1: torch.distributed backend of the control plane (barriers, timing reductions); the frame data never goes through it")
     ap.add_argument("--shard-deadline", type=float, default=300.0, help="shard mode: seconds after which a run that has not completed falls back to the replicas line")
     args = ap.parse_args()

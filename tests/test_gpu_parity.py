@@ -346,6 +346,51 @@ def test_full_size_config4_compose(cuda, og):
     got = grig.compose([frames])[0]
     _eq(got, want, "config 4 panorama (CV_16SC3)")
     assert grig.st.last_launch_count() == 8  # K1 K2 down2 down1(L3: too large for shared memory) down_tail coarse blend_seam blend_int
+    # The 8-rank view-sharded split of this rig (bench.py --gpus 8) walked through on this one handle, rank after rank: the shard
+    # plan, every packed per-peer message (pack as the owner, unpack as the reader), each rank's front half over its own tile
+    # lists and each rank's strip blend.  The strips add up to the same panorama.
+    import torch
+    from tests.gpu_util import dev, host, stream
+    world, n = 8, kw["n_views"]
+    st = grig.st
+    owners, strips = [None] * n, []
+    for r in range(world):
+        st.shard_set(r, world)
+        x0, x1, owned = st.shard_info()
+        strips.append((x0, x1, owned))
+        for v in owned:
+            assert owners[v] is None
+            owners[v] = r
+    assert None not in owners, owners
+    d_src = [dev(f) for f in frames]
+    bufs = {}
+    for r in range(world):
+        st.shard_set(r, world)
+        st.shard_plan(owners)
+        for p in range(world):
+            sb = st.shard_peer_bytes(p)[0] if p != r else 0
+            if sb:
+                assert sb % 16 == 0
+                bufs[(r, p)] = torch.zeros(sb, dtype=torch.uint8, device="cuda")
+                st.shard_pack(p, 1, bufs[(r, p)].data_ptr(), stream())
+    W, H = grig.roi_final[2], grig.roi_final[3]
+    total = torch.zeros((H, W, 3), dtype=torch.int32, device="cuda")
+    for r in range(world):
+        st.shard_set(r, world)
+        st.shard_plan(owners)
+        for v0, v1 in vsb200.dist.contiguous_runs(strips[r][2]):
+            st.feed_batch(v0, v1, 1, [d_src[v].data_ptr() for v in range(v0, v1)], kw["src_w"] * 3, stream())
+        for p in range(world):
+            rb = st.shard_peer_bytes(p)[1] if p != r else 0
+            assert rb == (bufs[(p, r)].numel() if (p, r) in bufs else 0), (p, r, rb)
+            if rb:
+                st.shard_unpack(p, 1, bufs[(p, r)].data_ptr(), stream())
+        out = torch.zeros((H, W, 3), dtype=torch.int16, device="cuda")
+        st.blend_batch([out.data_ptr()], W * 6, stream())
+        total += out.to(torch.int32)
+        del out
+    _eq(host(total).astype(np.int16), want, "config 4, sum of the 8 ranks' strips")
+    assert len(bufs) >= world  # every rank exchanges with at least its neighbours
 
 
 @pytest.mark.parametrize("name,kw", [

@@ -61,3 +61,93 @@ def test_view_sharded_native_transport_matches_oracle(cuda, world, batch):
     owned = sorted(v for rk in out["ranks"] for v in rk["owned"])
     assert owned == list(range(case["n_views"]))
     assert sum(rk["send_bytes"] for rk in out["ranks"]) == sum(rk["recv_bytes"] for rk in out["ranks"]) > 0
+
+
+def _emulated_ranks(torch, case, world, n_frames):
+    """`world` handles on ONE GPU, one per rank: each calibrates the same rig, takes its shard (vsb_shard_set / vsb_shard_plan),
+    runs its front half, packs one buffer per peer; the buffers are handed over in-process instead of through NCCL, unpacked,
+    and every rank blends its strip.  Returns (frames, per-frame panoramas summed over the ranks' strips, per-rank facts)."""
+    import numpy as np
+    import vsb200
+    B, S, D = vsb200.binding, vsb200.synth, vsb200.dist
+    n, sw, sh = case["n_views"], case["src_w"], case["src_h"]
+    gains = S.gains(n)
+    hs = []
+    for r in range(world):
+        st = B.Stitcher(n, case["num_bands"], True, n_frames)
+        st.calibrate_rig(0, case["pano_width"], sw, sh, 90.0, gains)
+        info = st.rig_info()
+        for i in range(n):
+            mx, my = S.mesh(info.view_roi[i][2], info.view_roi[i][3])
+            st.set_mesh(i, mx.ctypes.data, my.ctypes.data, mx.shape[0], mx.shape[1])
+        st.shard_set(r, world)
+        hs.append(st)
+    roi, _, _ = hs[0].get_roi()
+    W, H = roi[2], roi[3]
+    infos = [st.shard_info() for st in hs]
+    owners = [None] * n
+    for r, (_, _, owned) in enumerate(infos):
+        for v in owned:
+            assert owners[v] is None, f"view {v} has two owners"
+            owners[v] = r
+    assert None not in owners, f"unowned view: {owners}"
+    for st in hs:
+        st.shard_plan(owners)
+    frames = [[S.frame(i, f, sw, sh) for i in range(n)] for f in range(n_frames)]
+    d_fr = [[torch.from_numpy(a).cuda() for a in one] for one in frames]
+    stream = torch.cuda.current_stream().cuda_stream
+    pitch = (W * 6 + 255) // 256 * 256
+    bufs, facts = {}, []
+    for r, st in enumerate(hs):  # front halves + pack
+        owned = infos[r][2]
+        for v0, v1 in D.contiguous_runs(owned):
+            st.feed_batch(v0, v1, n_frames, [d_fr[f][v].data_ptr() for f in range(n_frames) for v in range(v0, v1)], sw * 3, stream)
+        sent = 0
+        for p in range(world):
+            if p == r:
+                continue
+            sb, _ = st.shard_peer_bytes(p)
+            _, rb = hs[p].shard_peer_bytes(r)
+            assert sb == rb, f"rank {r} sends {sb} bytes per frame to {p}, which expects {rb}"
+            assert sb % 16 == 0
+            if sb:
+                bufs[(r, p)] = torch.full((sb * n_frames,), 0xAB, dtype=torch.uint8, device="cuda")
+                st.shard_pack(p, n_frames, bufs[(r, p)].data_ptr(), stream)
+                sent += sb
+        facts.append({"rank": r, "owned": owned, "strip": infos[r][:2], "send_bytes": sent})
+    torch.cuda.synchronize()
+    total = [torch.zeros((H, pitch // 2), dtype=torch.int32, device="cuda") for _ in range(n_frames)]
+    for r, st in enumerate(hs):  # unpack + back halves
+        for p in range(world):
+            if (p, r) in bufs:
+                st.shard_unpack(p, n_frames, bufs[(p, r)].data_ptr(), stream)
+        outs = [torch.zeros((H, pitch // 2), dtype=torch.int16, device="cuda") for _ in range(n_frames)]
+        st.blend_batch([o.data_ptr() for o in outs], pitch, stream)
+        torch.cuda.synchronize()
+        for f in range(n_frames):
+            total[f] += outs[f].to(torch.int32)
+    panos = [t.cpu().numpy()[:, :W * 3].reshape(H, W, 3).astype(np.int16) for t in total]
+    for st in hs:
+        st.close()
+    return frames, panos, facts
+
+
+@pytest.mark.parametrize("n_views,pano_width,world", [(6, 1536, 8), (6, 1536, 3), (12, 2048, 8), (12, 2048, 5)])
+def test_view_shard_plan_for_any_world_on_one_gpu(cuda, og, n_views, pano_width, world):
+    """The shard plan, the packed per-peer messages and the strip blend for world sizes the box may not have GPUs for (8 ranks;
+    odd worlds; ranks that own two views, one view or none; strips past the end of the canvas): `world` handles on one GPU, the
+    packed buffers handed over in-process.  Two frames per submission; every frame bit-exact against oracle-G."""
+    import numpy as np
+    import vsb200
+    from oracle import pipeline as op
+    S = vsb200.synth
+    case = dict(n_views=n_views, src_w=480 if n_views == 6 else 320, src_h=270 if n_views == 6 else 180, pano_width=pano_width, num_bands=4 if n_views == 6 else 5)
+    frames, panos, facts = _emulated_ranks(cuda, case, world, 2)
+    orig = op.OracleRig(n_views, case["src_w"], case["src_h"], pano_width, num_bands=case["num_bands"], enable_local=True, gains=S.gains(n_views))
+    for i in range(n_views):
+        orig.set_mesh(i, *S.mesh(*orig.sizes[i]))
+    for f, fr in enumerate(frames):
+        want, _ = orig.compose(fr)
+        bad = int(np.count_nonzero(panos[f] != want))
+        assert bad == 0, (f, bad, facts)
+    assert sum(x["send_bytes"] for x in facts) > 0

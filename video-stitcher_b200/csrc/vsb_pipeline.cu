@@ -3127,7 +3127,9 @@ int vsb_shard_plan(vsb_stitcher *s, const int *owners)
                         const int x1 = std::min(R.pw, (R.x0 + R.w + 3) & ~3);
                         R.x0 &= ~3; R.w = x1 - R.x0;
                     }
-                    off += (size_t)3 * R.w * R.h;
+                    // every block starts on a 16-byte boundary of the packed buffer (k_shard_copy moves words when the plane side
+                    // allows it; blocks of odd-sized coarse levels sit between them), and so does every frame of a submission
+                    off = align_up(off + (size_t)3 * R.w * R.h, 16);
                     tab.push_back(R);
                 }
             }
