@@ -3250,10 +3250,9 @@ int vsb_shard_init(vsb_stitcher *s, int rank, int world, const void *id128)
     if (world > 1) {
         ncclUniqueId id;
         std::memcpy(&id, id128, sizeof(id));
-        // This communicator lives next to the host application's own (torch's, in bench.py).  NCCL's peer-to-peer transport
-        // exchanges one file descriptor per peer buffer and channel; with 8 ranks and the default channel count two communicators
-        // exhaust a 1024-descriptor soft limit ("unhandled system error" in the first ncclGroupEnd).  So: lift the soft limit to
-        // the hard one, and ask for few channels -- the exchange moves a few MB per frame, eight CTAs saturate it.
+        // This communicator may live next to the host application's own.  NCCL's peer-to-peer transport passes file descriptors
+        // between ranks while it connects, so the soft descriptor limit is lifted to the hard one; and the exchange moves a few
+        // MB per frame, which eight CTAs saturate, so the communicator is asked for few channels (less memory per peer).
         struct rlimit rl;
         if (getrlimit(RLIMIT_NOFILE, &rl) == 0 && rl.rlim_cur < rl.rlim_max) { rl.rlim_cur = rl.rlim_max; setrlimit(RLIMIT_NOFILE, &rl); }
         static const int max_ctas = [] { const char *e = std::getenv("VSB_NCCL_MAXCTAS"); return e ? std::atoi(e) : 8; }();
