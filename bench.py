@@ -47,6 +47,15 @@ WORKLOADS = {
 RING = 8  # distinct frame sets resident in HBM (8 x 37 MB = 299 MB > 126 MB L2 at cfg2)
 METRIC = "stitched equirect frames/sec"
 CTL_DEV = "cpu"  # device of the control-plane tensors (gloo: cpu; --ctl-backend nccl: cuda)
+_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the run, written to the process's original stdout.  main() points file descriptor 1 at stderr for
+    everything else, so that what a library prints there (NCCL's version banner at communicator init) cannot land next to it."""
+    out = _OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 class ClockSampler(threading.Thread):
@@ -172,7 +181,7 @@ def run_reference(args, cfg, rank, world):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def timed_repeats(step, K, sync, repeats=5, min_total_s=2.0, probe=None):
@@ -274,7 +283,7 @@ class Watchdog(threading.Thread):
                     time.sleep(1.0)  # let the failing rank finish writing its reason
                     line = self.fallback_line(why)
                     if line:
-                        print(json.dumps(line), flush=True)
+                        emit(line)
                 os._exit(0)
 
 
@@ -509,7 +518,7 @@ def _run_sharded_body(args, cfg, rank, world, local_rank, replicas, dog):
         b_io = n * cfg["src_w"] * cfg["src_h"] * 3 + OW * OH * 6
         peak, peak_src = hbm_peak()
         xbytes = sum(s_["send_bytes_per_frame"] for s_ in stats)
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/s16 (fp32 taps)", "data": "synthetic",
             "config": {"workload": cfg["name"], "frames_per_step": F, "pano": f"{OW}x{OH} CV_16SC3", "bands": nb,
@@ -524,7 +533,7 @@ def _run_sharded_body(args, cfg, rank, world, local_rank, replicas, dog):
             "parity_checked": bool(parity["bit_exact"]), "parity": parity,
             "shards": stats, "exchange_bytes_per_frame": xbytes,
             "exchange": {"bytes_per_frame": xbytes, "nvlink_GBps_per_gpu": xbytes * fps / world / 1e9},
-            "single_gpu_same_workload": single, "replicas": replicas}), flush=True)
+            "single_gpu_same_workload": single, "replicas": replicas})
     dog.done.set()
     torch.cuda.synchronize()
     os._exit(0)  # (a clean communicator teardown can itself wait on peers; everything is measured and printed)
@@ -563,6 +572,10 @@ def main():
     ap.add_argument("--ctl-backend", choices=["gloo", "nccl"], default="gloo", help="N > 1: torch.distributed backend of the control plane (barriers, timing reductions); the frame data never goes through it")
     ap.add_argument("--shard-deadline", type=float, default=300.0, help="shard mode: seconds after which a run that has not completed falls back to the replicas line")
     args = ap.parse_args()
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -824,7 +837,7 @@ def main():
             "f1": f1,
             "roofline": roofline, "roofline_path": roofline_path, "kernels": kernels, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
