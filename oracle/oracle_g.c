@@ -17,7 +17,8 @@
  * place by oracle/ref.mk when /root/reference is present; its outputs are committed as tests/golden/reference_cpu.npz
  * (generator: tests/golden/make_golden.py) and checked live and from the fixture by tests/test_oracle_pin.py;
  * (2) the reference's float gold for cuda::remap (CW/test/interpolation.hpp:66-84, compiled into oracle/ref_shim.cpp)
- * on the CW/test/test_remap.cpp:158-177 recipe; (3) replayed recipes of the reference's own tests
+ * on the CW/test/test_remap.cpp:158-177 recipe, and for cuda::resize (CW/test/test_resize.cpp:54-74) on that test's recipe;
+ * (3) replayed recipes of the reference's own tests
  * (CW/test/test_pyramids.cpp, S/test/test_blenders.cpp).
  */
 #include "oracle_g.h"

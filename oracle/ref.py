@@ -94,6 +94,17 @@ def remap_u8(src, xmap, ymap, nearest=False):
     return dst
 
 
+def resize_gold_u8(src, fx, fy):
+    """The reference's float gold of cuda::resize INTER_LINEAR (CW/test/test_resize.cpp:54-74): dsize = saturate_cast<int>(size * f)."""
+    src = np.ascontiguousarray(src, np.uint8)
+    cn = 1 if src.ndim == 2 else src.shape[2]
+    sh, sw = src.shape[:2]
+    dw, dh = int(np.rint(sw * fx)), int(np.rint(sh * fy))
+    dst = np.empty((dh, dw) if src.ndim == 2 else (dh, dw, cn), np.uint8)
+    lib().vr_resize_gold_u8(_p(src), sw, sh, cn, C.c_double(fx), C.c_double(fy), _p(dst), dw, dh)
+    return dst
+
+
 def remap_gold_u8(src, xmap, ymap):
     """The reference's float gold of cuda::remap LINEAR / BORDER_CONSTANT(0) (CW/test/interpolation.hpp:66-84)."""
     src = np.ascontiguousarray(src, np.uint8)

@@ -165,6 +165,17 @@ void vr_remap_gold_u8(const uint8_t *src, int sw, int sh, int cn, const float *x
             for (int c = 0; c < cn; ++c)
                 d.at<uchar>(y, x * cn + c) = LinearInterpolator<uchar>::getValue(s, ym.at<float>(y, x), xm.at<float>(y, x), c, BORDER_CONSTANT, Scalar());
 }
+/* resizeGold(INTER_LINEAR) of the CUDA resize test: resizeImpl<uchar, LinearInterpolator>
+ * (sources/modules/cudawarping/test/test_resize.cpp:54-74) -- the gold cuda::resize is tested against with a bound of 1.0 (:152) */
+void vr_resize_gold_u8(const uint8_t *src, int sw, int sh, int cn, double fx, double fy, uint8_t *dst, int dw, int dh)
+{
+    Mat s(sh, sw, CV_8UC(cn), const_cast<uint8_t *>(src)), d(dh, dw, CV_8UC(cn), dst);
+    const float ifx = static_cast<float>(1.0 / fx), ify = static_cast<float>(1.0 / fy);
+    for (int y = 0; y < dh; ++y)
+        for (int x = 0; x < dw; ++x)
+            for (int c = 0; c < cn; ++c)
+                d.at<uchar>(y, x * cn + c) = LinearInterpolator<uchar>::getValue(s, y * ify, x * ifx, c, BORDER_REPLICATE);
+}
 /* the reference's own GainCompensator::feed + gains() (S/src/exposure_compensate.cpp:71-142,162-168), compiled from its source:
  * imgs[i] CV_8UC3 / masks[i] CV_8U (255 = valid) of sizes_wh[i] at corners_xy[i] */
 void vr_gain_compensator_feed(int n, const uint8_t *const *imgs, const uint8_t *const *masks, const int *sizes_wh, const int *corners_xy, double *gains)

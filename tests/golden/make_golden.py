@@ -54,6 +54,15 @@ def remap_input(seed=3):
     return src, xm, ym
 
 
+RESIZE_COEFFS = (0.3, 0.5, 1.5, 2.0)  # CW/test/test_resize.cpp:160
+
+
+def resize_test_recipe(channels, seed=7):
+    """CW/test/test_resize.cpp:142-153: a randomMat CV_8UC1 / CV_8UC3 of one of DIFFERENT_SIZES (113 x 113), resized by each coefficient."""
+    rng = np.random.default_rng(seed + channels)
+    return rng.integers(0, 256, (113, 113) if channels == 1 else (113, 113, channels), dtype=np.uint8)
+
+
 def remap_test_recipe(size=(128, 128), seed=5):
     """CW/test/test_remap.cpp:127-148 (SetUp): maps of a 45-degree rotation, M = [[cos, -sin, w/2], [sin, cos, 0]], on a
     randomMat CV_8UC3 source of the same size."""
@@ -195,6 +204,10 @@ def main():
     out["remap_gold_linear"] = vr.remap_gold_u8(src, xm, ym)
     src2, xm2, ym2 = remap_test_recipe()
     out["remap_gold_recipe"] = vr.remap_gold_u8(src2, xm2, ym2)
+    # 7c. the reference's float gold of cuda::resize INTER_LINEAR (CW/test/test_resize.cpp:54-74) on its own recipe
+    for cn in (1, 3):
+        for c in RESIZE_COEFFS:
+            out[f"resize_gold_c{cn}_{c}"] = vr.resize_gold_u8(resize_test_recipe(cn), c, c)
     # 8. gain convertTo
     out["gain_1.03"] = vr.gain_u8(np.arange(256, dtype=np.uint8), 1.03)
     out["gain_0.97"] = vr.gain_u8(np.arange(256, dtype=np.uint8), 0.97)

@@ -160,6 +160,19 @@ def test_remap_vs_reference_float_gold(og, gold, which):
     assert want.any() and (want == 0).any()  # the maps reach outside the image: BORDER_CONSTANT(0) is exercised
 
 
+@pytest.mark.parametrize("cn", [1, 3])
+def test_cuda_resize_vs_reference_float_gold(og, gold, cn):
+    """oracle-G's cuda::resize(INTER_LINEAR) (the seam-scale resize in front of the gain compensator, A/calibration.cpp:95) against
+    the float gold of the reference's own CUDA-module test (resizeImpl<uchar, LinearInterpolator>, CW/test/test_resize.cpp:54-74),
+    on that test's recipe (113 x 113 randomMat, coefficients 0.3 / 0.5 / 1.5 / 2.0).  The reference's bound is 1.0 (:152); the
+    restatement equals the gold exactly."""
+    src = G.resize_test_recipe(cn)
+    for c in G.RESIZE_COEFFS:
+        want = gold[f"resize_gold_c{cn}_{c}"]
+        got = og.cuda_resize_linear_u8(src, want.shape[1], want.shape[0], c, c)
+        assert np.array_equal(got, want), (cn, c, int(np.abs(got.astype(int) - want.astype(int)).max()))
+
+
 @pytest.mark.parametrize("name", ["recipe", "offset"])
 def test_blender_vs_reference_cpu(og, gold, name):
     imgs, masks, tls = G.blend_recipe() if name == "recipe" else G.offset_recipe()
@@ -215,6 +228,7 @@ def test_live_golden_file_is_current(gold):
     assert np.array_equal(vr.remap_u8(src, xm, ym), gold["remap_linear"])
     assert np.array_equal(vr.remap_gold_u8(src, xm, ym), gold["remap_gold_linear"])
     assert np.array_equal(vr.gain_compensator_feed(*G.gain_input()), gold["gain_compensator"])
+    assert np.array_equal(vr.resize_gold_u8(G.resize_test_recipe(3), 0.3, 0.3), gold["resize_gold_c3_0.3"])
 
 
 def test_live_nv12_full_frame(og):
