@@ -229,6 +229,26 @@ def dilate3x3_u8c1(src):
 
 
 # ---------------------------------------------------------------- mesh
+def add_src_weight_32f(src, weight, dst, dst_weight):
+    """addSrcWeightKernel32F on CV_16SC3 src / dst and CV_32F weights: returns (dst, dst_weight) after the accumulation."""
+    src = np.ascontiguousarray(src, np.int16)
+    weight = np.ascontiguousarray(weight, np.float32)
+    dst = np.array(dst, np.int16, order="C")
+    dw = np.array(dst_weight, np.float32, order="C")
+    rows, cols = weight.shape
+    lib().og_add_src_weight_32f(_p(src, C.c_int16), _p(weight, C.c_float), _p(dst, C.c_int16), _p(dw, C.c_float), rows, cols)
+    return dst, dw
+
+
+def normalize_32f(weight, src):
+    """normalizeUsingWeightKernel32F: returns the normalised CV_16SC3 array."""
+    weight = np.ascontiguousarray(weight, np.float32)
+    out = np.array(src, np.int16, order="C")
+    rows, cols = weight.shape
+    lib().og_normalize_32f(_p(weight, C.c_float), _p(out, C.c_int16), rows, cols)
+    return out
+
+
 def custom_resize(inp, tx, ty):
     inp = _f32(inp)
     rows, cols = inp.shape

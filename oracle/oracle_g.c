@@ -18,7 +18,10 @@
  * (generator: tests/golden/make_golden.py) and checked live and from the fixture by tests/test_oracle_pin.py;
  * (2) the reference's float gold for cuda::remap (CW/test/interpolation.hpp:66-84, compiled into oracle/ref_shim.cpp)
  * on the CW/test/test_remap.cpp:158-177 recipe, and for cuda::resize (CW/test/test_resize.cpp:54-74) on that test's recipe;
- * (3) replayed recipes of the reference's own tests
+ * (3) the reference's own CUDA KERNELS of the path -- cuda::remap, pyrDown, pyrUp, addSrcWeightKernel32F, normalizeUsingWeightKernel32F,
+ * the application's resize -- compiled to PTX from the reference's unmodified .cu files (oracle/ref_ptx.mk) and executed on the CPU with
+ * exact binary32 arithmetic (oracle/ptx_interp.py): oracle-G equals them bit for bit (tests/test_oracle_ptx.py, fixture
+ * tests/golden/reference_ptx.npz); (4) replayed recipes of the reference's own tests
  * (CW/test/test_pyramids.cpp, S/test/test_blenders.cpp).
  */
 #include "oracle_g.h"
@@ -556,9 +559,11 @@ void og_dilate3x3_u8c1(const uint8_t *src, int w, int h, uint8_t *dst)
 
 /* ---------------------------------------------------------------- CPW mesh -> backward map */
 
-/* kernel `resize`, A/resize.cu:9-27.  nvcc contraction of
+/* kernel `resize`, A/resize.cu:9-27.  What nvcc makes of
  *   (1-uu)*(1-vv)*in00 + uu*(1-vv)*in01 + (1-uu)*vv*in10 + uu*vv*in11
- * is mul,mul then three fmas whose multiplicand is the separately rounded weight product. */
+ * (checked on the PTX of the reference's own file, oracle/ref_ptx.mk, same on sm_61 ... sm_100a): the four weight products are
+ * rounded on their own; the SECOND term w01*in01 is a rounded multiply, the first term is fused onto it, then the third and
+ * the fourth:  fma(w11,in11, fma(w10,in10, fma(w00,in00, rn(w01*in01)))).  tests/test_oracle_ptx.py executes that PTX. */
 void og_custom_resize(const float *in, int cols, int rows, float *out, int tx, int ty)
 {
 #pragma omp parallel for num_threads(g_threads)
@@ -568,8 +573,8 @@ void og_custom_resize(const float *in, int cols, int rows, float *out, int tx, i
             int top = v * (rows - 1) / ty;
             float uu = ((float)u * (float)(cols - 1)) / (float)tx - (float)left;
             float vv = ((float)v * (float)(rows - 1)) / (float)ty - (float)top;
-            float a = ((1.f - uu) * (1.f - vv)) * in[(size_t)top * cols + left];
-            a = fmaf(uu * (1.f - vv), in[(size_t)top * cols + left + 1], a);
+            float a = (uu * (1.f - vv)) * in[(size_t)top * cols + left + 1];
+            a = fmaf((1.f - uu) * (1.f - vv), in[(size_t)top * cols + left], a);
             a = fmaf((1.f - uu) * vv, in[(size_t)(top + 1) * cols + left], a);
             a = fmaf(uu * vv, in[(size_t)(top + 1) * cols + left + 1], a);
             out[(size_t)v * tx + u] = a;
@@ -1118,6 +1123,29 @@ const int16_t *og_blender_src_level(const og_blender *b, int i, int level, int *
     return b->views[i].lap[level];
 }
 
+/* one pixel of addSrcWeightKernel32F (S/src/cuda/multiband_blend.cu:36-50): dst.c += static_cast<short>(v.c * w) -- one rounded
+ * multiply, cvt.rzi, 16-bit wrap-around add (the PTX of the reference's file says add.s16) -- and dst_weight += w */
+static inline void add_src_weight_px(const int16_t *s, float wgt, int16_t *d, float *dw)
+{
+    for (int c = 0; c < 3; ++c) d[c] = (int16_t)(d[c] + rz_s16((float)s[c] * wgt));
+    *dw += wgt;
+}
+/* one pixel of normalizeUsingWeightKernel32F (S/src/cuda/multiband_blend.cu:85-99): v.c / (w + WEIGHT_EPS), IEEE division, cvt.rzi */
+static inline void normalize_px(int16_t *d, float w)
+{
+    const float wv = w + 1e-5f;
+    for (int c = 0; c < 3; ++c) d[c] = rz_s16((float)d[c] / wv);
+}
+/* the two kernels over a rows x cols rectangle of densely packed arrays (what addSrcWeightGpu32F / normalizeUsingWeightMapGpu32F launch) */
+void og_add_src_weight_32f(const int16_t *src, const float *weight, int16_t *dst, float *dst_weight, int rows, int cols)
+{
+    for (size_t j = 0; j < (size_t)rows * cols; ++j) add_src_weight_px(src + 3 * j, weight[j], dst + 3 * j, dst_weight + j);
+}
+void og_normalize_32f(const float *weight, int16_t *src, int rows, int cols)
+{
+    for (size_t j = 0; j < (size_t)rows * cols; ++j) normalize_px(src + 3 * j, weight[j]);
+}
+
 /* MultiBandBlender::feed_online, S/src/blenders.cpp:700-749; addSrcWeightKernel32F S/src/cuda/multiband_blend.cu:36-50;
  * subtract = saturating s16 (CA/src/cuda/sub_mat.cu:59-65) */
 void og_blender_feed_online(og_blender *b, int i, const uint8_t *img, int w, int h, size_t step)
@@ -1147,8 +1175,7 @@ void og_blender_feed_online(og_blender *b, int i, const uint8_t *img, int w, int
                 float wgt = v->weight[k][(size_t)y * lw[k] + x];
                 const int16_t *s = v->lap[k] + ((size_t)y * lw[k] + x) * 3;
                 int16_t *d = b->dst[k] + ((size_t)(y_tl + y) * b->lw[k] + (x_tl + x)) * 3;
-                for (int c = 0; c < 3; ++c) d[c] = (int16_t)(d[c] + rz_s16((float)s[c] * wgt));
-                b->dstw[k][(size_t)(y_tl + y) * b->lw[k] + (x_tl + x)] += wgt;
+                add_src_weight_px(s, wgt, d, &b->dstw[k][(size_t)(y_tl + y) * b->lw[k] + (x_tl + x)]);
             }
         x_tl /= 2; y_tl /= 2; x_br /= 2; y_br /= 2;
     }
@@ -1163,10 +1190,7 @@ void og_blender_blend(og_blender *b, int16_t *out, uint8_t *mask_out)
     for (int k = 0; k <= nb; ++k) {
         size_t n = (size_t)b->lw[k] * b->lh[k];
 #pragma omp parallel for num_threads(g_threads)
-        for (size_t j = 0; j < n; ++j) {
-            float wv = b->dstw[k][j] + WEIGHT_EPS;
-            for (int c = 0; c < 3; ++c) b->dst[k][j * 3 + c] = rz_s16((float)b->dst[k][j * 3 + c] / wv);
-        }
+        for (size_t j = 0; j < n; ++j) normalize_px(b->dst[k] + j * 3, b->dstw[k][j]);
     }
     for (int k = nb; k > 0; --k) {
         size_t n = (size_t)3 * b->lw[k - 1] * b->lh[k - 1];

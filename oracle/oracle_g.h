@@ -102,6 +102,9 @@ const float *og_blender_view_weight(const og_blender *b, int i, int level, int *
 const float *og_blender_dst_weight(const og_blender *b, int level, int *w, int *h); /* valid after feeds */
 const int16_t *og_blender_dst_level(const og_blender *b, int level, int *w, int *h);
 const int16_t *og_blender_src_level(const og_blender *b, int i, int level, int *w, int *h); /* laplacian of last feed */
+/* addSrcWeightKernel32F / normalizeUsingWeightKernel32F (S/src/cuda/multiband_blend.cu:36-50, 85-99) on densely packed CV_16SC3 / CV_32F arrays */
+void og_add_src_weight_32f(const int16_t *src, const float *weight, int16_t *dst, float *dst_weight, int rows, int cols);
+void og_normalize_32f(const float *weight, int16_t *src, int rows, int cols);
 void og_blender_feed_online(og_blender *b, int i, const uint8_t *img, int w, int h, size_t step);
 /* out: CV_16SC3 of dst_roi_final size, tightly packed; mask_out (optional) u8 */
 void og_blender_blend(og_blender *b, int16_t *out, uint8_t *mask_out);

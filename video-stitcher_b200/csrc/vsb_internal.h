@@ -30,8 +30,10 @@ __device__ __forceinline__ float custom_resize_at(const float *__restrict__ in, 
     const float *r0 = (const float *)((const char *)in + (size_t)top * in_pitch) + left;
     const float *r1 = (const float *)((const char *)in + (size_t)(top + 1) * in_pitch) + left;
     const float iu = __fsub_rn(1.f, uu), iv = __fsub_rn(1.f, vv);
-    float a = __fmul_rn(__fmul_rn(iu, iv), __ldg(r0));
-    a = __fmaf_rn(__fmul_rn(uu, iv), __ldg(r0 + 1), a);
+    // nvcc's contraction of the reference's four-term sum (read off the PTX of 360_stitcher/resize.cu): the second
+    // term is a rounded multiply, the first one is fused onto it, then the third and the fourth
+    float a = __fmul_rn(__fmul_rn(uu, iv), __ldg(r0 + 1));
+    a = __fmaf_rn(__fmul_rn(iu, iv), __ldg(r0), a);
     a = __fmaf_rn(__fmul_rn(iu, vv), __ldg(r1), a);
     a = __fmaf_rn(__fmul_rn(uu, vv), __ldg(r1 + 1), a);
     return a;
