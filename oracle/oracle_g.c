@@ -18,8 +18,8 @@
  * (generator: tests/golden/make_golden.py) and checked live and from the fixture by tests/test_oracle_pin.py;
  * (2) the reference's float gold for cuda::remap (CW/test/interpolation.hpp:66-84, compiled into oracle/ref_shim.cpp)
  * on the CW/test/test_remap.cpp:158-177 recipe, and for cuda::resize (CW/test/test_resize.cpp:54-74) on that test's recipe;
- * (3) the reference's own CUDA KERNELS of the path -- cuda::remap, pyrDown, pyrUp, addSrcWeightKernel32F, normalizeUsingWeightKernel32F,
- * the application's resize -- compiled to PTX from the reference's unmodified .cu files (oracle/ref_ptx.mk) and executed on the CPU with
+ * (3) the reference's own CUDA KERNELS of the path -- cuda::remap, pyrDown, pyrUp, cuda::resize, copyMakeBorder, convertTo (gain),
+ * addSrcWeightKernel32F, normalizeUsingWeightKernel32F, the application's resize -- compiled to PTX from the reference's unmodified .cu files (oracle/ref_ptx.mk) and executed on the CPU with
  * exact binary32 arithmetic (oracle/ptx_interp.py): oracle-G equals them bit for bit (tests/test_oracle_ptx.py, fixture
  * tests/golden/reference_ptx.npz); (4) replayed recipes of the reference's own tests
  * (CW/test/test_pyramids.cpp, S/test/test_blenders.cpp).

@@ -17,7 +17,7 @@ PTX_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ptx"
 
 
 def available():
-    return all(os.path.exists(os.path.join(PTX_DIR, f)) for f in ("app_resize.ptx", "multiband_blend.ptx", "pyr_down.ptx", "pyr_up.ptx", "remap.ptx"))
+    return all(os.path.exists(os.path.join(PTX_DIR, f + ".ptx")) for f in ("app_resize", "multiband_blend", "pyr_down", "pyr_up", "remap", "resize", "gpu_mat", "copy_make_border"))
 
 
 _parsed = {}
@@ -191,12 +191,104 @@ def remap_oracle(og, inp):
             "linear_reflect_c3": og.remap_u8(inp["c3"], inp["xmap"], inp["ymap"], og.INTER_LINEAR, og.BORDER_REFLECT)}
 
 
+# ---- sources/modules/core/src/cuda/gpu_mat.cu:488-512 (GpuMat::convertTo(type, alpha): the gain of 360_stitcher/timed.cpp:94) --------------
+# cudev gridTransformUnary_ -> grid_transform_detail::transformSimple<GlobPtr<uchar>, uchar, Convertor<uchar, uchar, float>, WithOutMask>
+# over the image reshaped to one channel, 32 x 8 threads (the 4-samples-per-thread "smart" form computes the same values)
+def gain_inputs(rng):
+    return {"img": rng.integers(0, 256, (13, 41, 3), dtype=np.uint8), "gains": np.array([0.97, 1.0, 1.03, 1.7], np.float32)}
+
+
+def gain_ptx(inp):
+    K = kernels("gpu_mat")
+    k = [v for n, v in K.items() if "transformSimple" in n and "ConvertorIhhfE" in n]
+    assert len(k) == 1
+    img = inp["img"]
+    rows, cols = img.shape[0], img.shape[1] * 3
+    out = {}
+    for g in inp["gains"]:
+        dst = np.zeros_like(img)
+        mem = P.Memory()
+        a_s, a_d = mem.add(img), mem.add(dst)
+        P.launch(k[0], (_grid(cols, 32), _grid(rows, 8)), (32, 8),
+                 [P.ptr_step(a_s, cols), P.ptr_step(a_d, cols), struct.pack("<ff", np.float32(g), 0.0), b"\0", P.i32(rows), P.i32(cols)], mem)
+        out[f"{float(g):.2f}"] = dst
+    return out
+
+
+def gain_oracle(og, inp):
+    return {f"{float(g):.2f}": og.gain_u8(inp["img"], np.float32(g)) for g in inp["gains"]}
+
+
+# ---- sources/modules/cudaarithm/src/cuda/copy_make_border.cu:56-115 (BORDER_REFLECT, CV_8UC3: S/src/blenders.cpp:711) -----------------------
+# cudev gridCopy -> grid_copy_detail::copy<RemapPtr1<BrdBase<BrdReflect, GlobPtr<uchar3>>, ShiftMap>, uchar3, WithOutMask>, 32 x 8 threads
+BORDER_SHAPES = ((20, 31, 5, 7, 9, 4), (6, 8, 3, 2, 7, 5), (5, 4, 7, 9, 9, 6))   # (h, w, top, bottom, left, right); the last: borders wider than the image
+
+
+def border_inputs(rng):
+    return {f"img{j}": rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for j, (h, w, *_) in enumerate(BORDER_SHAPES)}
+
+
+def border_ptx(inp):
+    k = P.find(kernels("copy_make_border"), "BrdBaseINS0_10BrdReflectENS0_7GlobPtrI6uchar3")
+    out = {}
+    for j, (h, w, t, b, l, r) in enumerate(BORDER_SHAPES):
+        src = inp[f"img{j}"]
+        H, W = h + t + b, w + l + r
+        dst = np.zeros((H, W, 3), np.uint8)
+        mem = P.Memory()
+        a_s, a_d = mem.add(src), mem.add(dst)
+        # RemapPtr1{BrdBase{GlobPtr{data, step}; int rows, cols}; ShiftMap{int top, left}}
+        P.launch(k, (_grid(W, 32), _grid(H, 8)), (32, 8), [struct.pack("<QQiiii", a_s, w * 3, h, w, t, l), P.ptr_step(a_d, W * 3), b"\0", P.i32(H), P.i32(W)], mem)
+        out[f"img{j}"] = dst
+    return out
+
+
+def border_oracle(og, inp):
+    # the oracle's border function also does the convertTo(CV_16S) that follows (S/src/blenders.cpp:713): exact, undone here
+    return {f"img{j}": og.border_reflect_u8c3_to_s16(inp[f"img{j}"], t, b, l, r).astype(np.uint8) for j, (h, w, t, b, l, r) in enumerate(BORDER_SHAPES)}
+
+
+# ---- sources/modules/cudawarping/src/cuda/resize.cu:71-106, 211-219 (resize_linear, 32 x 8 threads; host side src/resize.cpp:76-105) ------
+def cuda_resize_inputs(rng):
+    return {"mask": (rng.random((17, 23)) > 0.5).astype(np.uint8) * 255, "frame": rng.integers(0, 256, (54, 96, 3), dtype=np.uint8)}
+
+
+def _cuda_resize(frag, src, dw, dh, fx, fy):
+    k = P.find(kernels("resize"), frag)
+    sh, sw = src.shape[:2]
+    cn = 1 if src.ndim == 2 else 3
+    out = np.zeros((dh, dw) + src.shape[2:], np.uint8)
+    mem = P.Memory()
+    a_s, a_d = mem.add(src), mem.add(out)
+    # cuda::resize passes static_cast<float>(1.0 / fy), static_cast<float>(1.0 / fx) (src/resize.cpp:103)
+    P.launch(k, (_grid(dw, 32), _grid(dh, 8)), (32, 8), [_ptr_step_sz(a_s, sw * cn, sw, sh), _ptr_step_sz(a_d, dw * cn, dw, dh),
+                                                        struct.pack("<f", np.float32(1.0 / fy)), struct.pack("<f", np.float32(1.0 / fx))], mem)
+    return out
+
+
+def cuda_resize_ptx(inp):
+    m, f = inp["mask"], inp["frame"]
+    s = 0.3
+    return {"mask_up": _cuda_resize("resize_linearIhEE", m, 61, 40, 61 / m.shape[1], 40 / m.shape[0]),                    # A/calibration.cpp:236 (dsize given)
+            "frame_down": _cuda_resize("resize_linearI6uchar3EE", f, int(np.rint(f.shape[1] * s)), int(np.rint(f.shape[0] * s)), s, s)}  # A/calibration.cpp:95
+
+
+def cuda_resize_oracle(og, inp):
+    m, f = inp["mask"], inp["frame"]
+    s = 0.3
+    return {"mask_up": og.resize_linear_u8c1(m, 61, 40),
+            "frame_down": og.cuda_resize_linear_u8(f, int(np.rint(f.shape[1] * s)), int(np.rint(f.shape[0] * s)), s, s)}
+
+
 CASES = {
     "app_resize": (resize_inputs, resize_ptx, resize_oracle, 3),
     "multiband_blend": (blend_inputs, blend_ptx, blend_oracle, 11),
     "pyr_down": (pyr_down_inputs, pyr_down_ptx, pyr_down_oracle, 2),
     "pyr_up": (pyr_up_inputs, pyr_up_ptx, pyr_up_oracle, 4),
     "remap": (remap_inputs, remap_ptx, remap_oracle, 9),
+    "gain": (gain_inputs, gain_ptx, gain_oracle, 1),
+    "copy_make_border": (border_inputs, border_ptx, border_oracle, 6),
+    "cuda_resize": (cuda_resize_inputs, cuda_resize_ptx, cuda_resize_oracle, 8),
 }
 
 
