@@ -99,6 +99,10 @@ typedef struct vsb_rig_info {
 } vsb_rig_info;
 int vsb_rig_camera(int n_views, int i, int src_w, int src_h, double hfov_deg, float K[9], float R[9]);
 int vsb_voronoi_seams(int n, const int *sizes_wh, const int *corners_xy, uint8_t *const *masks);
+/* HOST buffers, no device needed: the projection maps exactly as vsb_calibrate_rig builds them -- buildWarpMapsKernel's arithmetic
+ * (S/src/cuda/build_warp_maps.cu:88-152) with the host's sinf / cosf -- for the w x h rectangle at (tl_x, tl_y); dense rows. */
+int vsb_host_build_maps(int projection, float scale, const float K[9], const float R[9], int tl_x, int tl_y, int w, int h,
+                        float *xmap, float *ymap);
 int vsb_calibrate_rig(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg,
                       const float *gains);
 /* ---- the same calibration with every per-pixel loop on the DEVICE (the reference runs these stages on the GPU

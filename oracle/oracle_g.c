@@ -195,7 +195,10 @@ void og_warp_roi(int proj, float scale, const float K[9], const float R[9], int 
 }
 
 /* SphericalMapper / CylindricalMapper::mapBackward + buildWarpMapsKernel, S/src/cuda/build_warp_maps.cu:88-152.
- * nvcc contraction: x = fma(k2,z_, fma(k1,y_, k0*x_)). sinf/cosf are the host libm's (the device's differ by ulps). */
+ * What nvcc makes of  x = k[0]*x_ + k[1]*y_ + k[2]*z_  (PTX of the reference's own file, oracle/ref_ptx.mk; executed by
+ * tests/test_oracle_ptx.py): spherical, where y_ = -cos(v): the negation is folded into a SUBTRACTION of two separately rounded
+ * products and only the third term is fused; cylindrical: the second product is rounded on its own, the first and the third
+ * are fused onto it.  sinf / cosf are the host libm's here (the device's differ by ulps: map parity is a 2e-3 px bound). */
 void og_build_maps(int proj, float scale, const float K[9], const float R[9], int tl_x, int tl_y,
                    int w, int h, float *xmap, float *ymap)
 {
@@ -205,22 +208,26 @@ void og_build_maps(int proj, float scale, const float K[9], const float R[9], in
     for (int dv = 0; dv < h; ++dv) {
         for (int du = 0; du < w; ++du) {
             float u = (float)(tl_x + du), v = (float)(tl_y + dv);
-            float x_, y_, z_;
+            float x, y, z;
             if (proj == OG_PROJ_SPHERICAL) {
                 v = v / scale; u = u / scale;
-                float sinv = sinf(v);
-                x_ = sinv * sinf(u);
-                y_ = -cosf(v);
-                z_ = sinv * cosf(u);
+                const float sinv = sinf(v);
+                const float x_ = sinv * sinf(u);
+                const float cosv = cosf(v);
+                const float z_ = sinv * cosf(u);
+                const float x0 = x_ * k[0], x1 = cosv * k[1], y0 = x_ * k[3], y1 = cosv * k[4], z0 = x_ * k[6], z1 = cosv * k[7];
+                x = fmaf(k[2], z_, x0 - x1);
+                y = fmaf(k[5], z_, y0 - y1);
+                z = fmaf(k[8], z_, z0 - z1);
             } else {
                 u = u / scale;
-                x_ = sinf(u);
-                y_ = v / scale;
-                z_ = cosf(u);
+                const float x_ = sinf(u);
+                const float y_ = v / scale;
+                const float z_ = cosf(u);
+                x = fmaf(k[2], z_, fmaf(x_, k[0], y_ * k[1]));
+                y = fmaf(k[5], z_, fmaf(x_, k[3], y_ * k[4]));
+                z = fmaf(k[8], z_, fmaf(x_, k[6], y_ * k[7]));
             }
-            float x = fmaf(k[2], z_, fmaf(k[1], y_, k[0] * x_));
-            float y = fmaf(k[5], z_, fmaf(k[4], y_, k[3] * x_));
-            float z = fmaf(k[8], z_, fmaf(k[7], y_, k[6] * x_));
             if (z > 0) { x = x / z; y = y / z; } else { x = y = -1.f; }
             xmap[(size_t)dv * w + du] = x;
             ymap[(size_t)dv * w + du] = y;

@@ -17,7 +17,7 @@ PTX_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ptx"
 
 
 def available():
-    return all(os.path.exists(os.path.join(PTX_DIR, f + ".ptx")) for f in ("app_resize", "multiband_blend", "pyr_down", "pyr_up", "remap", "resize", "gpu_mat", "copy_make_border"))
+    return all(os.path.exists(os.path.join(PTX_DIR, f + ".ptx")) for f in ("app_resize", "multiband_blend", "pyr_down", "pyr_up", "remap", "resize", "gpu_mat", "copy_make_border", "build_warp_maps"))
 
 
 _parsed = {}
@@ -278,6 +278,39 @@ def cuda_resize_oracle(og, inp):
     s = 0.3
     return {"mask_up": og.resize_linear_u8c1(m, 61, 40),
             "frame_down": og.cuda_resize_linear_u8(f, int(np.rint(f.shape[1] * s)), int(np.rint(f.shape[0] * s)), s, s)}
+
+
+# ---- sources/modules/stitching/src/cuda/build_warp_maps.cu:88-152, 176-215 (32 x 8 threads; k_rinv / scale in __constant__ memory) ---------
+# Not in CASES: the kernel evaluates CUDA's sinf / cosf (inlined in its PTX, executed here as compiled), oracle-G the host libm's, so
+# oracle and kernel agree to a few 1e-5 px, not bit for bit.  What IS bit-exact against this kernel is the product's k_build_maps
+# executed the same way (tests/test_oracle_ptx.py).
+MAP_PATCHES = (("spherical", 0, 1, 100, 60), ("spherical_wrapped", 0, 3, 0, 60), ("cylindrical", 1, 1, 100, 60))   # name, projection, view of a 6-view rig, offset into its ROI
+MAP_RIG = dict(n_views=6, src_w=640, src_h=360, pano_width=1280, patch_w=40, patch_h=24)
+
+
+def map_patch_args(og, proj, view, dx, dy):
+    K, R = og.rig_camera(MAP_RIG["n_views"], view, MAP_RIG["src_w"], MAP_RIG["src_h"], 90.0)
+    scale = np.float32(MAP_RIG["pano_width"] / (2 * 3.1415926535897932384626))
+    roi = og.warp_roi(proj, scale, K, R, MAP_RIG["src_w"], MAP_RIG["src_h"])
+    return K, R, scale, roi[0] + dx, roi[1] + dy, MAP_RIG["patch_w"], MAP_RIG["patch_h"]
+
+
+def build_warp_maps_ptx(og):
+    out = {}
+    K_ = kernels("build_warp_maps")
+    for name, proj, view, dx, dy in MAP_PATCHES:
+        K, R, scale, tl_x, tl_y, w, h = map_patch_args(og, proj, view, dx, dy)
+        k = [v for n, v in K_.items() if ("SphericalMapper" if proj == 0 else "CylindricalMapper") in n][0]
+        k_rinv, r_kinv, _ = og.projector(K, R)      # ProjectorBase::setCameraParams: host-side 3 x 3 products (S/src/warpers.cpp:49-79)
+        k.module.set_const("ck_rinv", np.asarray(k_rinv, np.float32).tobytes())
+        k.module.set_const("cr_kinv", np.asarray(r_kinv, np.float32).tobytes())
+        k.module.set_const("cscale", struct.pack("<f", scale))
+        xm, ym = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
+        mem = P.Memory()
+        ax, ay = mem.add(xm), mem.add(ym)
+        P.launch(k, (_grid(w, 32), _grid(h, 8)), (32, 8), [P.i32(tl_x), P.i32(tl_y), P.i32(w), P.i32(h), P.ptr_step(ax, w * 4), P.ptr_step(ay, w * 4)], mem)
+        out[f"{name}_x"], out[f"{name}_y"] = xm, ym
+    return out
 
 
 CASES = {

@@ -83,9 +83,25 @@ def _signed(v, bits):
     return v - (1 << bits) if v >> (bits - 1) else v
 
 
+class Module:
+    """Module-scope state: the .const bank (what cudaMemcpyToSymbol writes) and the names of .global / .local arrays."""
+
+    def __init__(self):
+        self.const_off, self.const_mem, self.other_syms, self.funcs = {}, bytearray(), set(), {}
+
+    def set_const(self, fragment, data):
+        hits = [n for n in self.const_off if fragment in n]
+        assert len(hits) == 1, (fragment, list(self.const_off))
+        off, size = self.const_off[hits[0]]
+        assert len(data) == size, (hits[0], len(data), size)
+        self.const_mem[off:off + size] = data
+
+
 class Kernel:
-    def __init__(self, name, params, body, shared):
+    def __init__(self, name, params, body, shared, module=None, ret=None):
         self.name, self.params, self.shared = name, params, shared  # params: list of (name, size, align)
+        self.module = module or Module()
+        self.ret = ret                                              # .func only: (name, size) of the return parameter
         self.instrs, self.labels = [], {}
         for line in body:
             m = re.match(r"^(\$?[A-Za-z_][\w$]*):$", line)
@@ -114,9 +130,9 @@ class Kernel:
 def _split_operands(s):
     out, depth, cur = [], 0, ""
     for ch in s:
-        if ch in "[{":
+        if ch in "[{(":
             depth += 1
-        elif ch in "]}":
+        elif ch in "]})":
             depth -= 1
         if ch == "," and depth == 0:
             out.append(cur.strip())
@@ -132,8 +148,16 @@ def parse(ptx_text):
     """-> {mangled entry name: Kernel}"""
     kernels = {}
     text = re.sub(r"//[^\n]*", "", ptx_text)
-    for m in re.finditer(r"\.entry\s+([\w$]+)\s*\((.*?)\)\s*(?:\.maxntid[^\n{]*)?\{(.*?)\n\}", text, re.S):
-        name, ptxt, btxt = m.group(1), m.group(2), m.group(3)
+    module = Module()
+    for m in re.finditer(r"^\.const\s+\.align\s+(\d+)\s+\.(\w+)\s+([\w$]+)(?:\[(\d+)\])?\s*;", text, re.M):
+        align, ty, cname, arr = int(m.group(1)), m.group(2), m.group(3), m.group(4)
+        size = _WIDTH[ty] // 8 * (int(arr) if arr else 1)
+        off = (len(module.const_mem) + align - 1) // align * align
+        module.const_mem.extend(b"\0" * (off + size - len(module.const_mem)))
+        module.const_off[cname] = (off, size)
+    for m in re.finditer(r"^\.global\s+\.align\s+\d+\s+\.\w+\s+([\w$]+)", text, re.M):
+        module.other_syms.add(m.group(1))
+    def parse_params(ptxt):
         params = []
         for p in ptxt.split(","):
             p = p.strip()
@@ -144,17 +168,43 @@ def parse(ptx_text):
             align, ty, pname, arr = mm.group(1), mm.group(2), mm.group(3), mm.group(4)
             size = _WIDTH[ty] // 8 * (int(arr) if arr else 1)
             params.append((pname, size, int(align) if align else _WIDTH[ty] // 8))
-        body, shared = [], {}
+        return params
+
+    def parse_body(btxt):
+        body, shared, cur = [], {}, ""
         for line in btxt.split("\n"):
             line = line.strip()
-            if not line or line.startswith(".reg") or line.startswith(".loc") or line.startswith(".file"):
+            if not line or line in ("{", "}"):
                 continue
-            ms = re.match(r"\.shared\s+\.align\s+(\d+)\s+\.b8\s+([\w$]+)\[(\d+)\];", line)
+            if not cur and (line.startswith(".reg") or line.startswith(".loc ") or line.startswith(".file") or line.startswith(".pragma")):
+                continue
+            if not cur and line.endswith(":"):
+                body.append(line)
+                continue
+            cur = (cur + " " + line).strip()
+            if not cur.endswith(";"):
+                continue                      # a statement that continues on the next line (call argument lists)
+            stmt, cur = cur, ""
+            ms = re.match(r"\.shared\s+\.align\s+(\d+)\s+\.b8\s+([\w$]+)\[(\d+)\];", stmt)
             if ms:
                 shared[ms.group(2)] = int(ms.group(3))
                 continue
-            body.append(line)
-        kernels[name] = Kernel(name, params, body, shared)
+            ml = re.match(r"\.local\s+\.align\s+\d+\s+\.b8\s+([\w$]+)\[(\d+)\];", stmt)
+            if ml:
+                module.other_syms.add(ml.group(1))   # per-thread scratch of library slow paths (e.g. sinf's Payne-Hanek): addressable, never dereferenced here
+                continue
+            if stmt.startswith(".param"):
+                continue                      # a call sequence's parameter variable: created when it is written
+            body.append(stmt)
+        return body, shared
+
+    for m in re.finditer(r"\.func\s+(?:\(([^)]*)\)\s*)?([\w$]+)\s*\(([^)]*)\)\s*\{(.*?)\n\}", text, re.S):
+        ret = parse_params(m.group(1))[0][:2] if m.group(1) else None
+        body, shared = parse_body(m.group(4))
+        module.funcs[m.group(2)] = Kernel(m.group(2), parse_params(m.group(3)), body, shared, module, ret)
+    for m in re.finditer(r"\.entry\s+([\w$]+)\s*\((.*?)\)\s*(?:\.maxntid[^\n{]*)?\{(.*?)\n\}", text, re.S):
+        body, shared = parse_body(m.group(3))
+        kernels[m.group(1)] = Kernel(m.group(1), parse_params(m.group(2)), body, shared, module)
     return kernels
 
 
@@ -198,9 +248,16 @@ class Memory:
 
 def _thread(kernel, params, mem, shared_mem, shared_off, ctaid, ntid, nctaid, tid):
     """Coroutine for one thread: yields at every bar.sync, returns at ret / the end of the body."""
-    R = {}
     special = {"%tid.x": tid[0], "%tid.y": tid[1], "%tid.z": tid[2], "%ntid.x": ntid[0], "%ntid.y": ntid[1], "%ntid.z": ntid[2],
                "%ctaid.x": ctaid[0], "%ctaid.y": ctaid[1], "%ctaid.z": ctaid[2], "%nctaid.x": nctaid[0], "%nctaid.y": nctaid[1], "%nctaid.z": nctaid[2]}
+    yield from _frame(kernel, params, mem, shared_mem, shared_off, special)
+
+
+def _frame(kernel, params, mem, shared_mem, shared_off, special):
+    """One activation of a kernel or device function (own registers and call-sequence parameter variables); returns the bytes
+    of the return parameter for a .func."""
+    R, lp = {}, {}
+    retbuf = bytearray(kernel.ret[1]) if kernel.ret else bytearray()
 
     def val(o, ty):
         """operand -> Python int (bit pattern / value) or np.float32 for f32"""
@@ -214,6 +271,10 @@ def _thread(kernel, params, mem, shared_mem, shared_off, ctaid, ntid, nctaid, ti
             return F32(float(o))
         if o in shared_off:
             return shared_off[o]                 # shared-window offsets: ld.shared / st.shared name their space explicitly
+        if o in kernel.module.const_off:
+            return kernel.module.const_off[o][0]
+        if o in kernel.module.other_syms:
+            return 0                             # .global / .local arrays of code paths the cases never take: any load there is out of bounds
         return int(o, 0)
 
     def addr_of(o):
@@ -225,9 +286,15 @@ def _thread(kernel, params, mem, shared_mem, shared_off, ctaid, ntid, nctaid, ti
     def ld(space, n, o):
         base, off = addr_of(o)
         if space == "param":
-            p = kernel.param_off[base] + off
-            return int.from_bytes(params[p:p + n], "little")
+            if base in kernel.param_off:
+                p = kernel.param_off[base] + off
+                return int.from_bytes(params[p:p + n], "little")
+            return int.from_bytes(bytes(lp[base][off:off + n]), "little")
         a = (val(base, "u64") + off) & 0xFFFFFFFFFFFFFFFF
+        if space == "const":
+            cm = kernel.module.const_mem
+            assert a + n <= len(cm), f"constant access out of bounds at {a}"
+            return int.from_bytes(bytes(cm[a:a + n]), "little")
         if space == "shared":
             a &= 0xFFFFFFFF                      # the shared window is addressed with 32-bit arithmetic
             assert 0 <= a and a + n <= len(shared_mem), f"shared access out of bounds at {a}"
@@ -236,6 +303,10 @@ def _thread(kernel, params, mem, shared_mem, shared_off, ctaid, ntid, nctaid, ti
 
     def st(space, n, o, v):
         base, off = addr_of(o)
+        if space == "param":
+            buf = retbuf if (kernel.ret and base == kernel.ret[0]) else lp.setdefault(base, bytearray(16))
+            buf[off:off + n] = int(v & ((1 << (8 * n)) - 1)).to_bytes(n, "little")
+            return
         a = (val(base, "u64") + off) & 0xFFFFFFFFFFFFFFFF
         if space == "shared":
             a &= 0xFFFFFFFF
@@ -264,7 +335,20 @@ def _thread(kernel, params, mem, shared_mem, shared_off, ctaid, ntid, nctaid, ti
                 continue
             name, ty = op[0], op[-1]
             if name == "ret" or name == "exit":
-                return
+                return bytes(retbuf)
+            if name == "call":
+                # call.uni (retval0), fname, (param0, param1, ...);   or   call.uni fname, (param0, ...);
+                has_ret = ops[0].startswith("(") and len(ops) == 3
+                fname = ops[1] if has_ret else ops[0]
+                args = [a.strip() for a in ops[-1].strip("()").split(",") if a.strip()]
+                func = kernel.module.funcs[fname]
+                blob = bytearray(func.param_bytes)
+                for (pname, size, _), a in zip(func.params, args):
+                    blob[func.param_off[pname]:func.param_off[pname] + size] = lp[a][:size]
+                ret = yield from _frame(func, bytes(blob), mem, shared_mem, shared_off, special)
+                if has_ret:
+                    lp[ops[0].strip("()").strip()] = bytearray(ret) + bytearray(16)
+                continue
             if name == "bra":
                 pc = kernel.labels[ops[-1]]
                 continue
@@ -292,8 +376,34 @@ def _thread(kernel, params, mem, shared_mem, shared_off, ctaid, ntid, nctaid, ti
                 else:
                     st(op[1], nbytes, ops[0], from_reg(ty, val(ops[1], ty)))
                 continue
+            if name == "mov" and (ops[0].startswith("{") or ops[1].startswith("{")):
+                # pack / unpack: mov.b32 %r, {%rs_lo, %rs_hi};   mov.b32 {%rs_lo, %rs_hi}, %r;   (also b64 <-> two b32)
+                total = _WIDTH[ty]
+                if ops[1].startswith("{"):
+                    parts = [q_.strip() for q_ in ops[1][1:-1].split(",")]
+                    w_ = total // len(parts)
+                    v = 0
+                    for k_, q_ in enumerate(parts):
+                        pv = val(q_, "b32")
+                        pv = f32_bits(pv) if isinstance(pv, np.floating) else int(pv)
+                        v |= _mask(pv, w_) << (w_ * k_)
+                    R[ops[0]] = f32_from_bits(v) if ops[0].startswith("%f") and total == 32 else v
+                else:
+                    parts = [q_.strip() for q_ in ops[0][1:-1].split(",")]
+                    w_ = total // len(parts)
+                    v = val(ops[1], ty)
+                    v = f32_bits(v) if isinstance(v, np.floating) else int(v)
+                    for k_, q_ in enumerate(parts):
+                        R[q_] = _mask(v >> (w_ * k_), w_)
+                continue
             if name in ("mov", "cvta"):
-                R[ops[0]] = val(ops[1], ty)
+                v = val(ops[1], ty)
+                if ty == "b32":                  # a bit cast when the register classes differ (%f <-> %r)
+                    if ops[0].startswith("%f") and not isinstance(v, np.floating):
+                        v = f32_from_bits(int(v))
+                    elif not ops[0].startswith("%f") and isinstance(v, np.floating):
+                        v = f32_bits(v)
+                R[ops[0]] = v
                 continue
             if name == "setp":
                 cmp_, a, b = op[1], val(ops[1], ty), val(ops[2], ty)
@@ -302,7 +412,9 @@ def _thread(kernel, params, mem, shared_mem, shared_off, ctaid, ntid, nctaid, ti
                 if ty == "f32":
                     unordered = bool(np.isnan(a) or np.isnan(b))
                     table = {"eq": a == b, "ne": a != b, "lt": a < b, "le": a <= b, "gt": a > b, "ge": a >= b}
-                    if cmp_ in table:
+                    if cmp_ in ("nan", "num"):
+                        res = unordered if cmp_ == "nan" else not unordered
+                    elif cmp_ in table:
                         res = bool(table[cmp_]) and not unordered
                     else:  # ltu, leu, gtu, geu, equ, neu: true if unordered
                         res = bool(table[cmp_[:-1]]) or unordered
@@ -382,6 +494,38 @@ def _thread(kernel, params, mem, shared_mem, shared_off, ctaid, ntid, nctaid, ti
                     raise NotImplementedError(op)
                 R[ops[0]] = r
                 continue
+            if name == "prmt":                   # byte permute, default mode: nibble k of c picks byte (0-7) of {b, a}; bit 3 replicates its sign
+                a, b, c = _mask(val(ops[1], "b32"), 32), _mask(val(ops[2], "b32"), 32), _mask(val(ops[3], "b32"), 32)
+                assert len(op) == 2, "only the default prmt mode is modelled"
+                pool = (b << 32) | a
+                r = 0
+                for k_ in range(4):
+                    sel = (c >> (4 * k_)) & 0xF
+                    byte = (pool >> (8 * (sel & 7))) & 0xFF
+                    if sel & 8:
+                        byte = 0xFF if byte & 0x80 else 0
+                    r |= byte << (8 * k_)
+                R[ops[0]] = r
+                continue
+            if name == "dp2a":                   # d = c + a.half0 * b.byte(0|2) + a.half1 * b.byte(1|3)   (.lo: bytes 0, 1; .hi: bytes 2, 3)
+                at, bt = op[2], op[3]
+                a, b = _mask(val(ops[1], "b32"), 32), _mask(val(ops[2], "b32"), 32)
+                c = val(ops[3], "b32")
+                sh = 0 if op[1] == "lo" else 16
+                acc = _signed(c, 32) if at[0] == "s" or bt[0] == "s" else _mask(c, 32)
+                for h in range(2):
+                    av = (a >> (16 * h)) & 0xFFFF
+                    bv = (b >> (sh + 8 * h)) & 0xFF
+                    av = _signed(av, 16) if at[0] == "s" else av
+                    bv = _signed(bv, 8) if bt[0] == "s" else bv
+                    acc += av * bv
+                R[ops[0]] = _mask(acc, 32)
+                continue
+            if name == "shf":                    # funnel shift of {b, a} (b high), wrap mode
+                a, b, c = _mask(val(ops[1], "b32"), 32), _mask(val(ops[2], "b32"), 32), _mask(val(ops[3], "b32"), 32) & 31
+                pool = (b << 32) | a
+                R[ops[0]] = _mask(pool >> (32 - c), 32) if op[1] == "l" else _mask(pool >> c, 32)
+                continue
             # ---- integer arithmetic
             bits = _WIDTH[ty]
             sgn = ty[0] == "s"
@@ -422,7 +566,7 @@ def _thread(kernel, params, mem, shared_mem, shared_off, ctaid, ntid, nctaid, ti
                 R[ops[0]] = _mask(get(ops[1]) >> sh, bits)
             else:
                 raise NotImplementedError(op)
-    return
+    return bytes(retbuf)
 
 
 def launch(kernel, grid, block, params, mem):

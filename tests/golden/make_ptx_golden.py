@@ -18,6 +18,10 @@ def main():
     for name, (_, run, _, _) in PC.CASES.items():
         for key, arr in run(PC.inputs_of(name)).items():
             out[f"{name}__{key}"] = arr
+    from oracle import oracle as og
+    og.build()
+    for key, arr in PC.build_warp_maps_ptx(og).items():   # the map builder: device sinf / cosf as compiled into the kernel
+        out[f"build_warp_maps__{key}"] = arr
     path = os.path.join(ROOT, "tests", "golden", "reference_ptx.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")

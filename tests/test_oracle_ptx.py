@@ -9,7 +9,8 @@ oracle/ptx_cases.py are committed as tests/golden/reference_ptx.npz (generator: 
 
 * test_oracle_equals_reference_kernels: oracle-G == those outputs, everywhere (no reference, no nvcc needed).
 * test_live_*: where oracle/_ref/ptx exists the kernels are executed again (the fixture is current); where nvcc exists, the
-  product's own device function behind custom_resize is compiled with the product's flags and executed the same way."""
+  PRODUCT's primitive kernels (vsb_primitives.cu) are compiled with the product's flags and executed the same way: product
+  device code == reference device code, bit for bit, with no GPU involved."""
 import os
 import shutil
 import struct
@@ -52,26 +53,61 @@ def test_live_reference_ptx_matches_fixture(gold, case):
         assert _same(arr, gold[f"{case}__{key}"]), f"{case}/{key}"
 
 
-def test_live_product_custom_resize_matches_reference_kernel(gold, tmp_path):
-    """vsb::custom_resize_at (video-stitcher_b200/csrc/vsb_internal.h: what vsb_custom_resize and the mesh -> map kernels evaluate),
-    compiled to PTX with the product's flags (--fmad=false) and executed on the CPU, equals the reference's `resize` kernel
-    (360_stitcher/resize.cu:9-27) bit for bit -- a device-vs-reference comparison that needs no GPU."""
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
+@pytest.mark.parametrize("case", sorted(PC.CASES))
+def test_live_product_primitives_match_reference_kernels(gold, case):
+    """The PRODUCT's device code against the REFERENCE's device code, without a GPU and without the oracle in between: the kernels
+    behind the device-launcher layer of the C ABI (video-stitcher_b200/csrc/vsb_primitives.cu: vsb_remap_linear_u8c3 -- the fused
+    path's own tap routine --, vsb_warp, vsb_gain_u8, vsb_border_reflect_u8c3_to_s16c3, vsb_pyr_down_s16c3, vsb_pyr_up_s16c3,
+    vsb_pyr_down_f32, vsb_add_src_weight_32f, vsb_normalize_32f, vsb_custom_resize; vsb_calib.cu: vsb_resize_linear_u8), compiled to PTX with the product's flags
+    (--fmad=false) and executed on the CPU, write exactly what the reference's kernels write."""
+    from oracle import ptx_product as PP
+    if not PP.available():
         pytest.skip("nvcc not found")
-    ptx = tmp_path / "wrap_device.ptx"
-    subprocess.check_call([nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=compute_100a", "--fmad=false", "-ptx",
-                           os.path.join(ROOT, "oracle", "ptx_wrap_device.cu"), "-o", str(ptx)])
-    k = P.find(P.parse(ptx.read_text()), "w_custom_resize")
-    inp = PC.inputs_of("app_resize")
-    src, (tx, ty) = inp["in"], [int(v) for v in inp["size"]]
-    rows, cols = src.shape
-    out = np.zeros((ty, tx), np.float32)
-    mem = P.Memory()
-    a_in, a_out = mem.add(src), mem.add(out)
-    q = lambda v: struct.pack("<Q", v)
-    P.launch(k, ((tx + 15) // 16, (ty + 15) // 16), (16, 16), [P.i32(tx), P.i32(ty), P.i32(cols), P.i32(rows), q(a_in), q(cols * 4), q(a_out), q(tx * 4)], mem)
-    assert _same(out, gold["app_resize__out"])
+    inp = PC.inputs_of(case)
+    for key, arr in PP.RUNNERS[case](inp).items():
+        assert _same(arr, gold[f"{case}__{key}"]), f"{case}/{key}"
+    if case == "remap":   # vsb_warp's LINEAR / CONSTANT form (k_warp_remap<3>) is a second implementation of the same kernel
+        assert _same(PP.remap_warp_linear_constant(inp), gold["remap__linear_constant_c3"])
+
+
+def test_map_builder_product_equals_reference_kernel_and_oracle_is_close(og, gold):
+    """buildWarpMapsKernel<SphericalMapper / CylindricalMapper> (S/src/cuda/build_warp_maps.cu:88-152) evaluates CUDA's sinf / cosf;
+    its PTX carries them inline, so the interpreter reproduces the DEVICE's values.  The product's k_build_maps, compiled and executed
+    the same way, equals the reference kernel bit for bit (same library code, same contraction of k0*x + k1*y + k2*z); oracle-G and
+    the product's host twin use the host libm and stay within 1e-4 px of the kernel (the GPU tests allow 2e-3 px)."""
+    from oracle import ptx_product as PP
+    want = {k[len("build_warp_maps__"):]: gold[k] for k in gold.files if k.startswith("build_warp_maps__")}
+    assert len(want) == 2 * len(PC.MAP_PATCHES)
+    if PC.available():
+        for key, arr in PC.build_warp_maps_ptx(og).items():
+            assert _same(arr, want[key]), key
+    if PP.available():
+        for key, arr in PP.build_warp_maps(og).items():
+            assert _same(arr, want[key]), f"k_build_maps {key}"
+    for name, proj, view, dx, dy in PC.MAP_PATCHES:
+        K, R, scale, tl_x, tl_y, w, h = PC.map_patch_args(og, proj, view, dx, dy)
+        ox, oy = og.build_maps(proj, scale, K, R, tl_x, tl_y, w, h)
+        assert np.abs(ox - want[f"{name}_x"]).max() <= 1e-4 and np.abs(oy - want[f"{name}_y"]).max() <= 1e-4
+        assert np.count_nonzero(ox.view(np.uint32) == want[f"{name}_x"].view(np.uint32)) > ox.size // 2   # and most samples are identical
+
+
+def test_host_map_builder_equals_oracle(og, vsb):
+    """vsb_host_build_maps = the maps vsb_calibrate_rig builds on the host (pure host code, no device): bit-identical to oracle-G's
+    (same arithmetic, same libm), which is what makes everything downstream of the maps comparable bit for bit on the GPU."""
+    import ctypes as C
+    L = vsb.lib()
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    for proj in (0, 1):
+        for view in (0, 1, 3):
+            K, R = og.rig_camera(6, view, 640, 360, 90.0)
+            scale = np.float32(1280 / (2 * 3.1415926535897932384626))
+            roi = og.warp_roi(proj, scale, K, R, 640, 360)
+            w, h = roi[2], roi[3]
+            xm, ym = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
+            Kf, Rf = np.ascontiguousarray(K, np.float32).reshape(9), np.ascontiguousarray(R, np.float32).reshape(9)
+            assert L.vsb_host_build_maps(proj, C.c_float(scale), fp(Kf), fp(Rf), roi[0], roi[1], w, h, fp(xm), fp(ym)) == 0
+            ox, oy = og.build_maps(proj, scale, K, R, *roi)
+            assert _same(xm, ox) and _same(ym, oy), (proj, view)
 
 
 def test_interpreter_fma_is_correctly_rounded():

@@ -25,7 +25,7 @@ SYMBOLS = [
     "vsb_border_reflect_u8c3_to_s16c3", "vsb_pyr_down_s16c3", "vsb_pyr_up_s16c3", "vsb_pyr_down_f32",
     "vsb_add_src_weight_32f", "vsb_normalize_32f", "vsb_debug_read",
     "vsb_shard_set", "vsb_shard_info", "vsb_shard_rect", "vsb_get_plane",
-    "vsb_rig_camera", "vsb_voronoi_seams", "vsb_calibrate_rig", "vsb_rig_info_get", "vsb_get_config", "vsb_set_profiling", "vsb_get_profile",
+    "vsb_rig_camera", "vsb_voronoi_seams", "vsb_host_build_maps", "vsb_calibrate_rig", "vsb_rig_info_get", "vsb_get_config", "vsb_set_profiling", "vsb_get_profile",
     "vsb_set_formats", "vsb_nv12_to_bgr", "vsb_consumer_image_height", "vsb_consume",
     "vsb_calibrate_rig_device", "vsb_estimate_gains", "vsb_voronoi_seams_device", "vsb_dilate3x3_u8", "vsb_resize_linear_u8",
     "vsb_gain_compensator_feed", "vsb_shard_unique_id", "vsb_shard_init", "vsb_shard_compose", "vsb_shard_exchange_bytes",

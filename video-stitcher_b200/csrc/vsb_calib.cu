@@ -30,7 +30,9 @@ static inline uint8_t rni_sat_u8_host(float v)
 }
 
 // {Spherical,Cylindrical}Mapper::mapBackward with the device's contraction pattern, on the host
-// (sources/modules/stitching/src/cuda/build_warp_maps.cu:88-134)
+// (sources/modules/stitching/src/cuda/build_warp_maps.cu:88-134; the pattern is what nvcc emits for the reference's file, see
+// k_build_maps in vsb_primitives.cu: spherical = two rounded products subtracted, third term fused; cylindrical = second product
+// rounded, first and third fused).  Host libm sinf / cosf.
 static void host_build_maps(int proj, float scale, const float K[9], const float R[9], int tl_x, int tl_y, int w, int h,
                             float *xmap, float *ymap)
 {
@@ -39,22 +41,29 @@ static void host_build_maps(int proj, float scale, const float K[9], const float
     for (int dv = 0; dv < h; ++dv)
         for (int du = 0; du < w; ++du) {
             float u = (float)(tl_x + du), v = (float)(tl_y + dv);
-            float x_, y_, z_;
+            float x, y, z;
             if (proj == VSB_PROJ_SPHERICAL) {
                 v = v / scale; u = u / scale;
                 const float sinv = sinf(v);
-                x_ = sinv * sinf(u);
-                y_ = -cosf(v);
-                z_ = sinv * cosf(u);
+                const float x_ = sinv * sinf(u);
+                const float cosv = cosf(v);
+                const float z_ = sinv * cosf(u);
+                // (volatile: each product and the difference are rounded on their own whatever the host compiler's contraction setting)
+                volatile float x0 = x_ * k[0], x1 = cosv * k[1], y0 = x_ * k[3], y1 = cosv * k[4], z0 = x_ * k[6], z1 = cosv * k[7];
+                volatile float xs = x0 - x1, ys = y0 - y1, zs = z0 - z1;
+                x = std::fmaf(k[2], z_, xs);
+                y = std::fmaf(k[5], z_, ys);
+                z = std::fmaf(k[8], z_, zs);
             } else {
                 u = u / scale;
-                x_ = sinf(u);
-                y_ = v / scale;
-                z_ = cosf(u);
+                const float x_ = sinf(u);
+                const float y_ = v / scale;
+                const float z_ = cosf(u);
+                volatile float x1 = y_ * k[1], y1 = y_ * k[4], z1 = y_ * k[7];
+                x = std::fmaf(k[2], z_, std::fmaf(x_, k[0], x1));
+                y = std::fmaf(k[5], z_, std::fmaf(x_, k[3], y1));
+                z = std::fmaf(k[8], z_, std::fmaf(x_, k[6], z1));
             }
-            float x = std::fmaf(k[2], z_, std::fmaf(k[1], y_, k[0] * x_));
-            float y = std::fmaf(k[5], z_, std::fmaf(k[4], y_, k[3] * x_));
-            const float z = std::fmaf(k[8], z_, std::fmaf(k[7], y_, k[6] * x_));
             if (z > 0) { x = x / z; y = y / z; } else { x = y = -1.f; }
             xmap[(size_t)dv * w + du] = x;
             ymap[(size_t)dv * w + du] = y;
@@ -425,6 +434,14 @@ int vsb_rig_camera(int n_views, int i, int src_w, int src_h, double hfov_deg, fl
     const float r[9] = {(float)std::cos(rot), 0.f, (float)std::sin(rot), 0.f, 1.f, 0.f, (float)-std::sin(rot), 0.f, (float)std::cos(rot)};
     std::memcpy(K, k, sizeof(k));
     std::memcpy(R, r, sizeof(r));
+    return VSB_OK;
+}
+
+int vsb_host_build_maps(int projection, float scale, const float K[9], const float R[9], int tl_x, int tl_y, int w, int h, float *xmap, float *ymap)
+{
+    if (!K || !R || !xmap || !ymap || w <= 0 || h <= 0 || !(scale > 0) || (projection != VSB_PROJ_SPHERICAL && projection != VSB_PROJ_CYLINDRICAL))
+        return vsb::fail(VSB_ERR_INVALID, "host_build_maps: bad arguments");
+    vsb::host_build_maps(projection, scale, K, R, tl_x, tl_y, w, h, xmap, ymap);
     return VSB_OK;
 }
 

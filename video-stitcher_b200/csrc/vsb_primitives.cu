@@ -158,22 +158,28 @@ __global__ void k_build_maps(int proj, float scale, Mat3 k, int tl_u, int tl_v, 
     const int du = blockIdx.x * blockDim.x + threadIdx.x, dv = blockIdx.y * blockDim.y + threadIdx.y;
     if (du >= cols || dv >= rows) return;
     float u = (float)(tl_u + du), v = (float)(tl_v + dv);
-    float x_, y_, z_;
+    // What nvcc makes of  x = k[0]*x_ + k[1]*y_ + k[2]*z_  (read off the PTX of the reference's build_warp_maps.cu):
+    // spherical, where y_ = -cos(v): the negation is folded into a subtraction of two separately rounded products and only the
+    // third term is fused; cylindrical: the second product is rounded on its own, the first and the third are fused onto it.
+    float x, y, z;
     if (proj == VSB_PROJ_SPHERICAL) {
         v = __fdiv_rn(v, scale); u = __fdiv_rn(u, scale);
         const float sinv = sinf(v);
-        x_ = __fmul_rn(sinv, sinf(u));
-        y_ = -cosf(v);
-        z_ = __fmul_rn(sinv, cosf(u));
+        const float x_ = __fmul_rn(sinv, sinf(u));
+        const float cosv = cosf(v);
+        const float z_ = __fmul_rn(sinv, cosf(u));
+        x = __fmaf_rn(k.m[2], z_, __fsub_rn(__fmul_rn(x_, k.m[0]), __fmul_rn(cosv, k.m[1])));
+        y = __fmaf_rn(k.m[5], z_, __fsub_rn(__fmul_rn(x_, k.m[3]), __fmul_rn(cosv, k.m[4])));
+        z = __fmaf_rn(k.m[8], z_, __fsub_rn(__fmul_rn(x_, k.m[6]), __fmul_rn(cosv, k.m[7])));
     } else {
         u = __fdiv_rn(u, scale);
-        x_ = sinf(u);
-        y_ = __fdiv_rn(v, scale);
-        z_ = cosf(u);
+        const float x_ = sinf(u);
+        const float y_ = __fdiv_rn(v, scale);
+        const float z_ = cosf(u);
+        x = __fmaf_rn(k.m[2], z_, __fmaf_rn(x_, k.m[0], __fmul_rn(y_, k.m[1])));
+        y = __fmaf_rn(k.m[5], z_, __fmaf_rn(x_, k.m[3], __fmul_rn(y_, k.m[4])));
+        z = __fmaf_rn(k.m[8], z_, __fmaf_rn(x_, k.m[6], __fmul_rn(y_, k.m[7])));
     }
-    float x = __fmaf_rn(k.m[2], z_, __fmaf_rn(k.m[1], y_, __fmul_rn(k.m[0], x_)));
-    float y = __fmaf_rn(k.m[5], z_, __fmaf_rn(k.m[4], y_, __fmul_rn(k.m[3], x_)));
-    const float z = __fmaf_rn(k.m[8], z_, __fmaf_rn(k.m[7], y_, __fmul_rn(k.m[6], x_)));
     if (z > 0) { x = __fdiv_rn(x, z); y = __fdiv_rn(y, z); } else { x = y = -1.f; }
     *(float *)((char *)mx + (size_t)dv * pitch + (size_t)du * 4) = x;
     *(float *)((char *)my + (size_t)dv * pitch + (size_t)du * 4) = y;
