@@ -280,6 +280,61 @@ def cuda_resize_oracle(og, inp):
             "frame_down": og.cuda_resize_linear_u8(f, int(np.rint(f.shape[1] * s)), int(np.rint(f.shape[0] * s)), s, s)}
 
 
+# ---- the remap half of stitch_online + the head of feed_online as the reference runs it (360_stitcher/timed.cpp:84-100,
+#      S/src/blenders.cpp:711): cuda::remap (projection maps) -> convertTo(gain) -> cuda::remap (mesh maps) -> copyMakeBorder(REFLECT),
+#      four kernels in a row.  The product does this in two fused, table-driven kernels (K1 / K2, oracle/ptx_product.py).
+FUSED_GAIN = 1.03
+FUSED_BORDER = (5, 5, 9, 11)    # top, bottom, left, right
+
+
+def fused_inputs(rng):
+    inp = remap_inputs(rng)
+    dh, dw = inp["xmap"].shape
+    yy, xx = np.mgrid[0:dh, 0:dw].astype(np.float64)
+    # mesh maps: identity plus a smooth displacement of a few pixels (what the CPW mesh produces), reaching past every edge
+    inp["xmesh"] = (xx + 3.0 * np.sin(yy / 7.0) + 2.0 * np.cos(xx / 5.0) - 1.2 + 0.37 * rng.random((dh, dw))).astype(np.float32)
+    inp["ymesh"] = (yy + 2.5 * np.cos(xx / 6.0) - 1.5 * np.sin(yy / 4.0) + 0.8 + 0.41 * rng.random((dh, dw))).astype(np.float32)
+    # a camera frame whose rows are not a multiple of 4 bytes (51 px = 153 B, rows 156 B apart in the product's run): the word loads of
+    # windows at the very end of the buffer would leave it -- the product's table marks those entries and takes its coordinate-driven
+    # edge routine for them
+    inp["c3"] = np.ascontiguousarray(inp["c3"][:, :51])
+    sh, sw = inp["c3"].shape[:2]
+    inp["xmap"][1, 1] = sw - 0.5
+    inp["xmap"][3, 3], inp["ymap"][3, 3] = sw - 1.5, sh - 1.5
+    inp["xmap"][3, 4], inp["ymap"][3, 4] = sw - 1.25, sh - 1.0
+    inp["xmap"][3, 5], inp["ymap"][3, 5] = sw - 2.75, sh - 1.75
+    return {k: v for k, v in inp.items() if k != "c1"}
+
+
+def fused_ptx(inp):
+    sh, sw = inp["c3"].shape[:2]
+    dh, dw = inp["xmap"].shape
+    p1 = _remap("LinearFilterINS1_12BorderReaderINS0_7PtrStepI6uchar3EENS1_11BrdConstantI6float3", inp["c3"], inp["xmap"], inp["ymap"],
+                struct.pack("<iifff", sh, sw, 0.0, 0.0, 0.0))
+    k = [v for n, v in kernels("gpu_mat").items() if "transformSimple" in n and "ConvertorIhhfE" in n][0]
+    p2 = np.zeros_like(p1)
+    mem = P.Memory()
+    a_s, a_d = mem.add(p1), mem.add(p2)
+    P.launch(k, (_grid(dw * 3, 32), _grid(dh, 8)), (32, 8), [P.ptr_step(a_s, dw * 3), P.ptr_step(a_d, dw * 3), struct.pack("<ff", np.float32(FUSED_GAIN), 0.0), b"\0", P.i32(dh), P.i32(dw * 3)], mem)
+    q = _remap("LinearFilterINS1_12BorderReaderINS0_7PtrStepI6uchar3EENS1_11BrdConstantI6float3", p2, inp["xmesh"], inp["ymesh"],
+               struct.pack("<iifff", dh, dw, 0.0, 0.0, 0.0))
+    t, b, l, r = FUSED_BORDER
+    H, W = dh + t + b, dw + l + r
+    g0 = np.zeros((H, W, 3), np.uint8)
+    kb = P.find(kernels("copy_make_border"), "BrdBaseINS0_10BrdReflectENS0_7GlobPtrI6uchar3")
+    mem = P.Memory()
+    a_s, a_d = mem.add(q), mem.add(g0)
+    P.launch(kb, (_grid(W, 32), _grid(H, 8)), (32, 8), [struct.pack("<QQiiii", a_s, dw * 3, dh, dw, t, l), P.ptr_step(a_d, W * 3), b"\0", P.i32(H), P.i32(W)], mem)
+    return {"p": p2, "g0": g0}
+
+
+def fused_oracle(og, inp):
+    p = og.gain_u8(og.remap_linear_u8(inp["c3"], inp["xmap"], inp["ymap"]), np.float32(FUSED_GAIN))
+    q = og.remap_linear_u8(p, inp["xmesh"], inp["ymesh"])
+    t, b, l, r = FUSED_BORDER
+    return {"p": p, "g0": og.border_reflect_u8c3_to_s16(q, t, b, l, r).astype(np.uint8)}
+
+
 # ---- sources/modules/stitching/src/cuda/build_warp_maps.cu:88-152, 176-215 (32 x 8 threads; k_rinv / scale in __constant__ memory) ---------
 # Not in CASES: the kernel evaluates CUDA's sinf / cosf (inlined in its PTX, executed here as compiled), oracle-G the host libm's, so
 # oracle and kernel agree to a few 1e-5 px, not bit for bit.  What IS bit-exact against this kernel is the product's k_build_maps
@@ -322,6 +377,7 @@ CASES = {
     "gain": (gain_inputs, gain_ptx, gain_oracle, 1),
     "copy_make_border": (border_inputs, border_ptx, border_oracle, 6),
     "cuda_resize": (cuda_resize_inputs, cuda_resize_ptx, cuda_resize_oracle, 8),
+    "fused_remap": (fused_inputs, fused_ptx, fused_oracle, 9),
 }
 
 

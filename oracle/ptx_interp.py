@@ -98,8 +98,14 @@ class Module:
 
 
 class Kernel:
-    def __init__(self, name, params, body, shared, module=None, ret=None):
+    def __init__(self, name, params, body, shared, module=None, ret=None, local=None):
         self.name, self.params, self.shared = name, params, shared  # params: list of (name, size, align)
+        self.local_off, tot = {}, 0
+        for lname, lsize in (local or {}).items():
+            tot = (tot + 15) // 16 * 16
+            self.local_off[lname] = tot
+            tot += lsize
+        self.local_bytes = tot
         self.module = module or Module()
         self.ret = ret                                              # .func only: (name, size) of the return parameter
         self.instrs, self.labels = [], {}
@@ -171,7 +177,7 @@ def parse(ptx_text):
         return params
 
     def parse_body(btxt):
-        body, shared, cur = [], {}, ""
+        body, shared, local, cur = [], {}, {}, ""
         for line in btxt.split("\n"):
             line = line.strip()
             if not line or line in ("{", "}"):
@@ -191,20 +197,20 @@ def parse(ptx_text):
                 continue
             ml = re.match(r"\.local\s+\.align\s+\d+\s+\.b8\s+([\w$]+)\[(\d+)\];", stmt)
             if ml:
-                module.other_syms.add(ml.group(1))   # per-thread scratch of library slow paths (e.g. sinf's Payne-Hanek): addressable, never dereferenced here
+                local[ml.group(1)] = int(ml.group(2))   # per-thread arrays (spills, library scratch)
                 continue
             if stmt.startswith(".param"):
                 continue                      # a call sequence's parameter variable: created when it is written
             body.append(stmt)
-        return body, shared
+        return body, shared, local
 
     for m in re.finditer(r"\.func\s+(?:\(([^)]*)\)\s*)?([\w$]+)\s*\(([^)]*)\)\s*\{(.*?)\n\}", text, re.S):
         ret = parse_params(m.group(1))[0][:2] if m.group(1) else None
-        body, shared = parse_body(m.group(4))
-        module.funcs[m.group(2)] = Kernel(m.group(2), parse_params(m.group(3)), body, shared, module, ret)
-    for m in re.finditer(r"\.entry\s+([\w$]+)\s*\((.*?)\)\s*(?:\.maxntid[^\n{]*)?\{(.*?)\n\}", text, re.S):
-        body, shared = parse_body(m.group(3))
-        kernels[m.group(1)] = Kernel(m.group(1), parse_params(m.group(2)), body, shared, module)
+        body, shared, local = parse_body(m.group(4))
+        module.funcs[m.group(2)] = Kernel(m.group(2), parse_params(m.group(3)), body, shared, module, ret, local)
+    for m in re.finditer(r"\.entry\s+([\w$]+)\s*\(([^)]*)\)(?:\s*\.(?:maxntid|minnctapersm|reqntid|maxnreg)[^\n{]*)*\s*\{(.*?)\n\}", text, re.S):
+        body, shared, local = parse_body(m.group(3))
+        kernels[m.group(1)] = Kernel(m.group(1), parse_params(m.group(2)), body, shared, module, None, local)
     return kernels
 
 
@@ -216,6 +222,10 @@ def find(kernels, fragment):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # execution
+
+_PARAM_BASE = 1 << 60     # "address" of the kernel parameter block (a __grid_constant__ parameter read through a pointer)
+_LOCAL_BASE = 1 << 59     # per-activation local memory (.local depots: spilled arrays)
+
 
 class Memory:
     """Global memory: numpy buffers registered at fake base addresses (1 GiB apart)."""
@@ -258,6 +268,7 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
     of the return parameter for a .func."""
     R, lp = {}, {}
     retbuf = bytearray(kernel.ret[1]) if kernel.ret else bytearray()
+    local_mem = bytearray(kernel.local_bytes)
 
     def val(o, ty):
         """operand -> Python int (bit pattern / value) or np.float32 for f32"""
@@ -273,6 +284,10 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
             return shared_off[o]                 # shared-window offsets: ld.shared / st.shared name their space explicitly
         if o in kernel.module.const_off:
             return kernel.module.const_off[o][0]
+        if o in kernel.param_off:
+            return _PARAM_BASE + kernel.param_off[o]
+        if o in kernel.local_off:
+            return _LOCAL_BASE + kernel.local_off[o]
         if o in kernel.module.other_syms:
             return 0                             # .global / .local arrays of code paths the cases never take: any load there is out of bounds
         return int(o, 0)
@@ -289,8 +304,16 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
             if base in kernel.param_off:
                 p = kernel.param_off[base] + off
                 return int.from_bytes(params[p:p + n], "little")
+            if base.startswith("%"):             # the address of a parameter was taken: [%rd + off]
+                p = R[base] + off - _PARAM_BASE
+                assert 0 <= p and p + n <= len(params), "parameter access out of bounds"
+                return int.from_bytes(params[p:p + n], "little")
             return int.from_bytes(bytes(lp[base][off:off + n]), "little")
         a = (val(base, "u64") + off) & 0xFFFFFFFFFFFFFFFF
+        if space == "local" or _LOCAL_BASE <= a < _LOCAL_BASE + len(local_mem):
+            a -= _LOCAL_BASE
+            assert 0 <= a and a + n <= len(local_mem), "local access out of bounds"
+            return int.from_bytes(bytes(local_mem[a:a + n]), "little")
         if space == "const":
             cm = kernel.module.const_mem
             assert a + n <= len(cm), f"constant access out of bounds at {a}"
@@ -308,6 +331,11 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
             buf[off:off + n] = int(v & ((1 << (8 * n)) - 1)).to_bytes(n, "little")
             return
         a = (val(base, "u64") + off) & 0xFFFFFFFFFFFFFFFF
+        if space == "local" or _LOCAL_BASE <= a < _LOCAL_BASE + len(local_mem):
+            a -= _LOCAL_BASE
+            assert 0 <= a and a + n <= len(local_mem), "local access out of bounds"
+            local_mem[a:a + n] = int(v & ((1 << (8 * n)) - 1)).to_bytes(n, "little")
+            return
         if space == "shared":
             a &= 0xFFFFFFFF
             assert 0 <= a and a + n <= len(shared_mem), f"shared access out of bounds at {a}"
@@ -352,8 +380,16 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
             if name == "bra":
                 pc = kernel.labels[ops[-1]]
                 continue
-            if name == "bar":
-                yield
+            if name in ("bar", "barrier"):
+                yield "warp" if "warp" in op else "block"
+                continue
+            if name == "atom":                   # atom.global.<op>.b32 d, [a], b: threads run one after another between barriers, so plain read-modify-write
+                nbytes = _WIDTH[ty] // 8
+                old_v = ld(op[1], nbytes, ops[1])
+                b_ = _mask(val(ops[2], ty), _WIDTH[ty])
+                new_v = {"or": old_v | b_, "and": old_v & b_, "xor": old_v ^ b_, "add": old_v + b_, "exch": b_, "max": max(old_v, b_), "min": min(old_v, b_)}[op[2]]
+                st(op[1], nbytes, ops[1], new_v)
+                R[ops[0]] = old_v
                 continue
             if name == "ld":
                 space = op[1]
@@ -590,16 +626,29 @@ def launch(kernel, grid, block, params, mem):
                 shared_mem = bytearray(total)
                 threads = [_thread(kernel, blob, mem, shared_mem, shared_off, (bx, by, bz), block, grid, (tx, ty, tz))
                            for tz in range(block[2]) for ty in range(block[1]) for tx in range(block[0])]
-                live = threads
-                while live:
-                    nxt = []
-                    for t in live:
+                # A thread stops at a barrier and resumes when every live thread of its scope (the block for bar.sync, its warp for
+                # bar.warp.sync) has arrived at a barrier of the same kind or has exited.
+                n = len(threads)
+                state = ["run"] * n                                   # run | block | warp | done
+                while any(st_ != "done" for st_ in state):
+                    progressed = False
+                    for i_, t in enumerate(threads):
+                        if state[i_] != "run":
+                            continue
+                        progressed = True
                         try:
-                            next(t)
-                            nxt.append(t)   # stopped at a barrier
+                            state[i_] = next(t)
                         except StopIteration:
-                            pass
-                    live = nxt
+                            state[i_] = "done"
+                    if all(st_ in ("block", "done") for st_ in state):
+                        state = ["run" if st_ == "block" else st_ for st_ in state]
+                        progressed = progressed or any(st_ == "run" for st_ in state)
+                    for w0 in range(0, n, 32):
+                        ws = state[w0:w0 + 32]
+                        if any(st_ == "warp" for st_ in ws) and all(st_ in ("warp", "done") for st_ in ws):
+                            state[w0:w0 + 32] = ["run" if st_ == "warp" else st_ for st_ in ws]
+                            progressed = True
+                    assert progressed, "deadlock: threads wait at barriers that the others never reach"
 
 
 def ptr_step(base_addr, step_bytes):

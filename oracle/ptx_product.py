@@ -169,6 +169,103 @@ def cuda_resize(inp):
     return out
 
 
+# ---- the fused hot kernels K1 / K2 (vsb_pipeline.cu) with their tap-table builders, driven the way launch_front / vsb_set_mesh
+#      drive them: k_build_taps1 -> k_remap_stage1_tab<LANES = true> (remap #1 + gain -> zero-framed P), k_build_taps2 ->
+#      k_remap_stage2_tab (remap #2 + REFLECT border -> planar u8 G0).  Parameter blocks mirrored with ctypes (natural alignment,
+#      like nvcc lays the structs out); the sizes are checked against the PTX.
+import ctypes as C
+
+MAXV, MAX_BATCH = 16, 16
+
+
+class _TapTable(C.Structure):
+    _fields_ = [("off", C.c_uint64), ("w", C.c_uint64), ("plane", C.c_size_t), ("tab_pitch", C.c_int)]
+
+
+class _Stage1TabView(C.Structure):
+    _fields_ = [("tab", _TapTable), ("xmap", C.c_uint64), ("ymap", C.c_uint64), ("P", C.c_uint64), ("map_pitch", C.c_size_t), ("p_pitch", C.c_size_t),
+                ("p_frame_stride", C.c_size_t), ("w", C.c_int), ("h", C.c_int), ("src_w", C.c_int), ("src_h", C.c_int), ("gain", C.c_float)]
+
+
+class _Stage1TabParams(C.Structure):
+    _fields_ = [("tiles", C.c_uint64), ("v", _Stage1TabView * MAXV), ("src", C.c_uint64 * (MAX_BATCH * MAXV)), ("src_pitch", C.c_uint),
+                ("v0", C.c_int), ("n_views", C.c_int), ("n_frames", C.c_int), ("f0", C.c_int)]
+
+
+class _Stage2TabView(C.Structure):
+    _fields_ = [("tab", _TapTable), ("Pbase", C.c_uint64), ("G0", C.c_uint64), ("p_frame_stride", C.c_size_t), ("g0_frame_stride", C.c_size_t),
+                ("p_pitch", C.c_uint), ("bw", C.c_int), ("bh", C.c_int)]
+
+
+class _Stage2TabParams(C.Structure):
+    _fields_ = [("tiles", C.c_uint64), ("v", _Stage2TabView * MAXV), ("n_frames", C.c_int), ("f0", C.c_int)]
+
+
+def _align_up(v, a):
+    return (v + a - 1) // a * a
+
+
+def fused_remap(inp, lanes=True):
+    K = kernels("vsb_pipeline")
+    src, xmap, ymap, xmesh, ymesh = inp["c3"], inp["xmap"], inp["ymap"], inp["xmesh"], inp["ymesh"]
+    sh, sw = src.shape[:2]
+    h, w = xmap.shape
+    t, b, l, r = PC.FUSED_BORDER
+    bw, bh = w + l + r, h + t + b
+    src_pitch = _align_up(sw * 3, 4)                            # launch_front takes the table-driven kernels for 4-byte aligned rows
+    pitched = np.zeros((sh - 1) * src_pitch + sw * 3, np.uint8)   # exactly the bytes a caller owns: any read past them is an error here
+    for y in range(sh):
+        pitched[y * src_pitch:y * src_pitch + sw * 3] = src[y].reshape(-1)
+    src = pitched
+    # P with its zero frame (vsb_pipeline.cu: p_pitch / p_frame_stride / p_origin of vsb_init_view)
+    p_pitch = _align_up((w + 5) * 3 + 8, 16)
+    p_frame_stride = _align_up(p_pitch * (h + 2) + 16, 16)
+    p_origin = p_pitch + 12
+    P_alloc = np.zeros(p_frame_stride, np.uint8)
+    t1_pitch, t2_pitch = _align_up(w, 4), _align_up(bw, 4)
+    t1_off, t1_w = np.zeros(t1_pitch * h, np.int32), np.zeros(4 * t1_pitch * h, np.float32)
+    t2_off, t2_w = np.zeros(t2_pitch * bh, np.int32), np.zeros(4 * t2_pitch * bh, np.float32)
+    flag = np.zeros(1, np.int32)
+    G0 = np.full(3 * bw * bh, 0xEE, np.uint8)
+    tiles1 = np.array([0 | (tx << 8) | (ty << 20) for ty in range((h + 7) // 8) for tx in range((w + 127) // 128)], np.uint32)
+    tiles2 = np.array([0 | (tx << 8) | (ty << 20) for ty in range((bh + 7) // 8) for tx in range((bw + 127) // 128)], np.uint32)
+    mem = P.Memory()
+    a = {k: mem.add(v) for k, v in dict(src=src, xmap=xmap, ymap=ymap, xmesh=xmesh, ymesh=ymesh, P=P_alloc, t1o=t1_off, t1w=t1_w, t2o=t2_off, t2w=t2_w,
+                                        flag=flag, G0=G0, tiles1=tiles1, tiles2=tiles2).items()}
+    # ---- table of remap #1 (build_taps1) and the frame kernel (launch_front)
+    P.launch(P.find(K, "k_build_taps1"), _g(t1_pitch, h), (32, 8),
+             [_q(a["xmap"]), _q(a["ymap"]), _q(w * 4), _i(w), _i(h), _i(sw), _i(sh), struct.pack("<I", src_pitch), _q(a["t1o"]), _q(a["t1w"]), _q(t1_pitch * h), _i(t1_pitch), _i(0), _q(a["flag"])], mem)
+    p1 = _Stage1TabParams()
+    p1.tiles = a["tiles1"]
+    v = p1.v[0]
+    v.tab.off, v.tab.w, v.tab.plane, v.tab.tab_pitch = a["t1o"], a["t1w"], t1_pitch * h, t1_pitch
+    v.xmap, v.ymap, v.P, v.map_pitch, v.p_pitch, v.p_frame_stride = a["xmap"], a["ymap"], a["P"] + p_origin, w * 4, p_pitch, p_frame_stride
+    v.w, v.h, v.src_w, v.src_h, v.gain = w, h, sw, sh, PC.FUSED_GAIN
+    p1.src[0] = a["src"]
+    p1.src_pitch, p1.v0, p1.n_views, p1.n_frames, p1.f0 = src_pitch, 0, 1, 1, 0
+    k1 = P.find(K, "k_remap_stage1_tabILb1E" if lanes else "k_remap_stage1_tabILb0E")
+    assert C.sizeof(p1) == k1.params[0][1], (C.sizeof(p1), k1.params[0][1])
+    P.launch(k1, (len(tiles1),), (32, 8), [bytes(p1)], mem)
+    slow_entries = int(np.count_nonzero(t1_off < 0))
+    p_roi = np.stack([P_alloc[p_origin + y * p_pitch: p_origin + y * p_pitch + w * 3].reshape(w, 3) for y in range(h)])
+    frame_untouched = int(P_alloc.sum()) == int(p_roi.sum())      # K1 wrote the ROI only: the zero frame is intact
+    # ---- table of remap #2 (vsb_set_mesh) and the frame kernel
+    P.launch(P.find(K, "k_build_taps2"), _g(t2_pitch, bh), (32, 8),
+             [_q(a["xmesh"]), _q(a["ymesh"]), _q(w * 4), _i(w), _i(h), _i(bw), _i(bh), _i(t), _i(l), struct.pack("<I", p_pitch), struct.pack("<I", p_origin),
+              _q(a["t2o"]), _q(a["t2w"]), _q(t2_pitch * bh), _i(t2_pitch), _q(a["flag"])], mem)
+    p2 = _Stage2TabParams()
+    p2.tiles = a["tiles2"]
+    v2 = p2.v[0]
+    v2.tab.off, v2.tab.w, v2.tab.plane, v2.tab.tab_pitch = a["t2o"], a["t2w"], t2_pitch * bh, t2_pitch
+    v2.Pbase, v2.G0, v2.p_frame_stride, v2.g0_frame_stride, v2.p_pitch, v2.bw, v2.bh = a["P"], a["G0"], p_frame_stride, 3 * bw * bh, p_pitch, bw, bh
+    p2.n_frames, p2.f0 = 1, 0
+    k2 = P.find(K, "k_remap_stage2_tab")
+    assert C.sizeof(p2) == k2.params[0][1], (C.sizeof(p2), k2.params[0][1])
+    P.launch(k2, (len(tiles2),), (32, 8), [bytes(p2)], mem)
+    g0 = np.ascontiguousarray(G0.reshape(3, bh, bw).transpose(1, 2, 0))   # planar -> interleaved for the comparison
+    return {"p": p_roi, "g0": g0}, {"slow_entries": slow_entries, "zero_frame_intact": frame_untouched, "unsafe_flag": int(flag[0])}
+
+
 def build_warp_maps(og):
     out = {}
     k = P.find(kernels(), "k_build_maps")

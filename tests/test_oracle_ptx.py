@@ -63,11 +63,31 @@ def test_live_product_primitives_match_reference_kernels(gold, case):
     from oracle import ptx_product as PP
     if not PP.available():
         pytest.skip("nvcc not found")
+    if case == "fused_remap":
+        pytest.skip("covered by test_live_product_fused_remap_kernels_match_reference_chain")
     inp = PC.inputs_of(case)
     for key, arr in PP.RUNNERS[case](inp).items():
         assert _same(arr, gold[f"{case}__{key}"]), f"{case}/{key}"
     if case == "remap":   # vsb_warp's LINEAR / CONSTANT form (k_warp_remap<3>) is a second implementation of the same kernel
         assert _same(PP.remap_warp_linear_constant(inp), gold["remap__linear_constant_c3"])
+
+
+@pytest.mark.parametrize("lanes", [True, False])
+def test_live_product_fused_remap_kernels_match_reference_chain(gold, lanes):
+    """The product's two hot remap kernels as they ship -- k_build_taps1 + k_remap_stage1_tab<LANES> (K1: remap #1 + gain through the
+    tap table, denormal-scaled fma chain, lane-interleaved pixels transposed through shared memory, TAP_SLOW entries through the
+    edge routine) and k_build_taps2 + k_remap_stage2_tab (K2: remap #2 with the REFLECT border resolved in the table, zero-framed P,
+    planar u8 out) -- compiled from vsb_pipeline.cu and executed on the CPU, against the REFERENCE's four kernels for the same
+    stretch of the path (cuda::remap -> convertTo(gain) -> cuda::remap -> copyMakeBorder(REFLECT), 360_stitcher/timed.cpp:84-100,
+    S/src/blenders.cpp:711), executed the same way: identical bytes.  The camera frame is exactly as large as a caller's buffer,
+    so a window load past its end would be caught (the interpreter bounds-checks every access)."""
+    from oracle import ptx_product as PP
+    if not PP.available():
+        pytest.skip("nvcc not found")
+    got, info = PP.fused_remap(PC.inputs_of("fused_remap"), lanes)
+    assert _same(got["p"], gold["fused_remap__p"]), "K1: gain(remap #1)"
+    assert _same(got["g0"], gold["fused_remap__g0"]), "K2: border(remap #2)"
+    assert info["slow_entries"] >= 2 and info["zero_frame_intact"] and info["unsafe_flag"] == 0, info
 
 
 def test_map_builder_product_equals_reference_kernel_and_oracle_is_close(og, gold):
