@@ -1,0 +1,93 @@
+"""TEST INFRASTRUCTURE: one end-to-end run of the PRODUCT library on the emulated runtime (oracle/emu/runtime.py), compared with
+oracle-G.  Run as a module in its own process (the emulation build of the library is selected through VSB200_LIB before
+video-stitcher_b200/binding.py is imported):
+
+    python -m oracle.emu.run_case '{"n_views": 4, "src_w": 48, "src_h": 32, "pano_width": 192, "num_bands": 3}'
+
+Prints one JSON line: mismatch counts of the mesh maps, the warped views, the Gaussian levels the path materialises and the
+panorama, the kernels that were launched and the time spent interpreting them."""
+import collections
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    case = json.loads(sys.argv[1])
+    from oracle.emu import runtime as E
+    E.start()
+    os.environ["VSB200_LIB"] = os.path.join(E.BUILD, "libvsb200_emu.so")
+    import vsb200
+    from oracle import oracle as og
+    from oracle import pipeline as op
+    og.build()
+    B, S = vsb200.binding, vsb200.synth
+    assert B.LIB_PATH.endswith("libvsb200_emu.so")
+    n, sw, sh, pano, nb = case["n_views"], case["src_w"], case["src_h"], case["pano_width"], case["num_bands"]
+    F = int(case.get("frames", 1))
+    gains = S.gains(n)
+    t0 = time.time()
+    st = B.Stitcher(n, nb, True, F)
+    st.calibrate_rig(0, pano, sw, sh, 90.0, gains)          # the product's host calibration + its weight / plan kernels
+    info = st.rig_info()
+    for i in range(n):
+        mx, my = S.mesh(info.view_roi[i][2], info.view_roi[i][3])
+        st.set_mesh(i, mx.ctypes.data, my.ctypes.data, mx.shape[0], mx.shape[1])
+    t_cal = time.time() - t0
+    roi, _, _ = st.get_roi()
+    W, H = roi[2], roi[3]
+    frames = [[S.frame(i, f, sw, sh) for i in range(n)] for f in range(F)]
+    bufs = [E.Buffer(a) for fr in frames for a in fr]
+    outs = [E.Buffer(np.full((H, W, 3), -12345, np.int16)) for _ in range(F)]
+    n0 = len(E.stats()["launches"])
+    t0 = time.time()
+    st.compose([b.ptr for b in bufs], sw * 3, [o.ptr for o in outs], W * 6, 0)
+    t_compose = time.time() - t0
+    launched = [name for name, _, _ in E.stats()["launches"][n0:]]
+
+    orig = op.OracleRig(n, sw, sh, pano, num_bands=nb, enable_local=True, gains=gains)
+    for i in range(n):
+        orig.set_mesh(i, *S.mesh(*orig.sizes[i]))
+
+    def read(what, view, level, shape, dtype):
+        a = np.empty(shape, dtype)
+        st.debug_read(what, view, level, 0, a.ctypes.data, a.nbytes)
+        return a
+
+    res = collections.OrderedDict(error=E.stats().get("error"), roi_equal=bool(tuple(roi) == tuple(orig.roi_final)), mesh_maps=0, warped=0, gauss0=0, gauss2=0)
+    for i in range(n):
+        w, h = info.view_roi[i][2], info.view_roi[i][3]
+        g = st.view_geometry(i)
+        bw, bh = g["x_br"] - g["x_tl"], g["y_br"] - g["y_tl"]
+        res["mesh_maps"] += int(np.count_nonzero(read(4, i, 0, (h, w), np.float32).view(np.uint32) != orig.mesh_maps[i][0].view(np.uint32)))
+        res["mesh_maps"] += int(np.count_nonzero(read(5, i, 0, (h, w), np.float32).view(np.uint32) != orig.mesh_maps[i][1].view(np.uint32)))
+        done0 = read(7, i, 0, (bh, bw), np.uint8).astype(bool)
+        ov = orig.warp_view(i, frames[0][i])
+        crop = done0[g["top"]:g["top"] + h, g["left"]:g["left"] + w]
+        res["warped"] += int(np.count_nonzero(read(0, i, 0, (h, w, 3), np.uint8)[crop] != ov[crop]))
+        gk = og.border_reflect_u8c3_to_s16(ov, g["top"], g["bottom"], g["left"], g["right"])
+        res["gauss0"] += int(np.count_nonzero(read(1, i, 0, (bh, bw, 3), np.int16)[done0] != gk[done0]))
+        g2 = og.pyr_down_s16(og.pyr_down_s16(gk))
+        done2 = read(6, i, 0, (bh >> 2, bw >> 2), np.uint8).astype(bool)
+        res["gauss2"] += int(np.count_nonzero(read(1, i, 2, (bh >> 2, bw >> 2, 3), np.int16)[done2] != g2[done2]))
+    res["pano"] = 0
+    for f in range(F):
+        want, _ = orig.compose(frames[f])
+        res["pano"] += int(np.count_nonzero(outs[f].a != want))
+    res["pano_samples"] = int(F * H * W * 3)
+    res["pano_nonzero"] = int(np.count_nonzero(outs[0].a))
+    res["launched"] = [k.split("vsb")[-1][:28] for k in launched]
+    res["launch_count"] = st.last_launch_count()
+    res["calibration_launches"] = n0
+    res["seconds"] = {"calibrate_and_mesh": round(t_cal, 1), "compose": round(t_compose, 1)}
+    print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -55,16 +55,32 @@ def round_fraction_to_f32(q):
     return F32(sign * float(val))          # val is exactly representable: the conversions are exact
 
 
+def _exact_parts(x):
+    """finite float -> (m, e) with x == m * 2**e exactly, m an int"""
+    import math
+    m, e = math.frexp(x)
+    return int(m * 9007199254740992.0), e - 53      # 2**53: exact for every double
+
+
 def fma_f32(a, b, c):
-    a, b, c = F32(a), F32(b), F32(c)
-    if not (np.isfinite(a) and np.isfinite(b) and np.isfinite(c)):
+    """fma.rn.f32: a * b + c with ONE rounding.  a * b is exact in binary64 (48-bit product); when the binary64 sum is exact too
+    (TwoSum error 0) the result is one binary64 -> binary32 rounding, otherwise the sum is formed in integers and rounded once."""
+    fa, fb, fc = float(a), float(b), float(c)
+    p = fa * fb
+    s_ = p + fc
+    if s_ != s_ or s_ in (float("inf"), float("-inf")):
         with np.errstate(all="ignore"):
-            return F32(np.float64(a) * np.float64(b) + np.float64(c))
-    q = Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c))
-    if q == 0:  # sign of an exact zero: +0 unless both addends are -0 (round to nearest)
-        prod_neg = (np.signbit(a) != np.signbit(b))
-        return F32(-0.0) if (prod_neg and np.signbit(c)) else F32(0.0)
-    return round_fraction_to_f32(q)
+            return F32(s_)
+    bb = s_ - p
+    if (p - (s_ - bb)) + (fc - bb) == 0.0:
+        if s_ == 0.0:   # sign of an exact zero: +0 unless both addends are -0 (round to nearest)
+            import math
+            return F32(-0.0) if (math.copysign(1.0, p) < 0 and math.copysign(1.0, fc) < 0) else F32(0.0)
+        return F32(s_)
+    mp, ep = _exact_parts(p)
+    mc, ec = _exact_parts(fc)
+    e = min(ep, ec)
+    return round_fraction_to_f32(Fraction(mp << (ep - e)) * Fraction(2) ** e + Fraction(mc << (ec - e)) * Fraction(2) ** e)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -87,7 +103,7 @@ class Module:
     """Module-scope state: the .const bank (what cudaMemcpyToSymbol writes) and the names of .global / .local arrays."""
 
     def __init__(self):
-        self.const_off, self.const_mem, self.other_syms, self.funcs = {}, bytearray(), set(), {}
+        self.const_off, self.const_mem, self.other_syms, self.funcs, self.dyn_shared = {}, bytearray(), set(), {}, set()
 
     def set_const(self, fragment, data):
         hits = [n for n in self.const_off if fragment in n]
@@ -124,13 +140,29 @@ class Kernel:
             parts = line.split(None, 1)
             op = parts[0]
             ops = _split_operands(parts[1]) if len(parts) > 1 else []
-            self.instrs.append((guard, op.split("."), ops))
+            self.instrs.append((guard, op.split("."), [_decode_operand(o) for o in ops]))
         off, self.param_off = 0, {}
         for pname, size, align in params:
             off = (off + align - 1) // align * align
             self.param_off[pname] = off
             off += size
         self.param_bytes = off
+
+
+_INT_RE = re.compile(r"^-?(?:0[xX][0-9a-fA-F]+|\d+)U?$")
+_ADDR_RE = re.compile(r"^\[\s*([%\w$.]+)\s*(?:\+\s*(-?\w+))?\s*\]$")
+
+
+def _decode_operand(o):
+    """Literals and address operands are decoded once: ints stay ints, 0f... becomes a float32, [base+off] a tuple."""
+    if o.startswith("0f") or o.startswith("0F"):
+        return f32_from_bits(int(o[2:], 16))
+    if _INT_RE.match(o):
+        return int(o.rstrip("U"), 0)
+    m = _ADDR_RE.match(o)
+    if m:
+        return ("M", m.group(1), int(m.group(2), 0) if m.group(2) else 0)
+    return o
 
 
 def _split_operands(s):
@@ -163,6 +195,8 @@ def parse(ptx_text):
         module.const_off[cname] = (off, size)
     for m in re.finditer(r"^\.global\s+\.align\s+\d+\s+\.\w+\s+([\w$]+)", text, re.M):
         module.other_syms.add(m.group(1))
+    for m in re.finditer(r"^\.extern\s+\.shared\s+\.align\s+\d+\s+\.\w+\s+([\w$]+)\[\]", text, re.M):
+        module.dyn_shared.add(m.group(1))    # extern __shared__: starts where the kernel's static shared arrays end
     def parse_params(ptxt):
         params = []
         for p in ptxt.split(","):
@@ -182,6 +216,13 @@ def parse(ptx_text):
             line = line.strip()
             if not line or line in ("{", "}"):
                 continue
+            mb = re.match(r"^\{\s*(\.reg.*;.*)\}$", line)
+            if mb and not cur:                # an inline-asm scope on one line: its statements, minus the register declarations
+                for stmt in mb.group(1).split(";"):
+                    stmt = stmt.strip()
+                    if stmt and not stmt.startswith(".reg"):
+                        body.append(stmt + ";")
+                continue
             if not cur and (line.startswith(".reg") or line.startswith(".loc ") or line.startswith(".file") or line.startswith(".pragma")):
                 continue
             if not cur and line.endswith(":"):
@@ -191,9 +232,9 @@ def parse(ptx_text):
             if not cur.endswith(";"):
                 continue                      # a statement that continues on the next line (call argument lists)
             stmt, cur = cur, ""
-            ms = re.match(r"\.shared\s+\.align\s+(\d+)\s+\.b8\s+([\w$]+)\[(\d+)\];", stmt)
+            ms = re.match(r"\.shared\s+\.align\s+(\d+)\s+\.(\w+)\s+([\w$]+)(?:\[(\d+)\])?;", stmt)
             if ms:
-                shared[ms.group(2)] = int(ms.group(3))
+                shared[ms.group(3)] = _WIDTH[ms.group(2)] // 8 * (int(ms.group(4)) if ms.group(4) else 1)
                 continue
             ml = re.match(r"\.local\s+\.align\s+\d+\s+\.b8\s+([\w$]+)\[(\d+)\];", stmt)
             if ml:
@@ -223,6 +264,7 @@ def find(kernels, fragment):
 # ---------------------------------------------------------------------------------------------------------------------
 # execution
 
+TRACE = None              # debugging aid: a predicate on the special-register dict selects the threads whose instructions are printed
 _PARAM_BASE = 1 << 60     # "address" of the kernel parameter block (a __grid_constant__ parameter read through a pointer)
 _LOCAL_BASE = 1 << 59     # per-activation local memory (.local depots: spilled arrays)
 
@@ -256,6 +298,42 @@ class Memory:
         raw[off:off + n] = np.frombuffer(int(value & ((1 << (8 * n)) - 1)).to_bytes(n, "little"), dtype=np.uint8)
 
 
+class HostMemory:
+    """Global memory = this process's memory (the emulated runtime's "device" allocations are host allocations).  `regions()` returns
+    the current list of (base, size) allocations; every access must fall inside one of them."""
+
+    def __init__(self, regions):
+        import ctypes
+        self._ct, self._regions_fn, self._views, self._bases = ctypes, regions, [], []
+
+    def _refresh(self):
+        self._views = []
+        for base, size in self._regions_fn():
+            if size:
+                self._views.append((base, size, np.frombuffer((self._ct.c_ubyte * size).from_address(base), dtype=np.uint8)))
+        self._views.sort(key=lambda v: v[0])
+        self._bases = [v[0] for v in self._views]
+
+    def _find(self, addr, n):
+        import bisect
+        for attempt in range(2):
+            i = bisect.bisect_right(self._bases, addr) - 1
+            if i >= 0:
+                base, size, view = self._views[i]
+                if addr + n <= base + size:
+                    return view, addr - base
+            self._refresh()
+        raise AssertionError(f"access outside every allocation at {addr:#x} (+{n})")
+
+    def load(self, addr, n):
+        raw, off = self._find(addr, n)
+        return int.from_bytes(raw[off:off + n].tobytes(), "little")
+
+    def store(self, addr, n, value):
+        raw, off = self._find(addr, n)
+        raw[off:off + n] = np.frombuffer(int(value & ((1 << (8 * n)) - 1)).to_bytes(n, "little"), dtype=np.uint8)
+
+
 def _thread(kernel, params, mem, shared_mem, shared_off, ctaid, ntid, nctaid, tid):
     """Coroutine for one thread: yields at every bar.sync, returns at ret / the end of the body."""
     special = {"%tid.x": tid[0], "%tid.y": tid[1], "%tid.z": tid[2], "%ntid.x": ntid[0], "%ntid.y": ntid[1], "%ntid.z": ntid[2],
@@ -272,6 +350,10 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
 
     def val(o, ty):
         """operand -> Python int (bit pattern / value) or np.float32 for f32"""
+        if type(o) is not str:                   # a literal decoded at parse time
+            return F32(o) if (ty == "f32" and type(o) is int) else o
+        if o in R:
+            return R[o]
         if o in special:
             return special[o]
         if o.startswith("%"):
@@ -282,6 +364,8 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
             return F32(float(o))
         if o in shared_off:
             return shared_off[o]                 # shared-window offsets: ld.shared / st.shared name their space explicitly
+        if o in kernel.module.dyn_shared:
+            return shared_off["<dynamic>"]
         if o in kernel.module.const_off:
             return kernel.module.const_off[o][0]
         if o in kernel.param_off:
@@ -293,6 +377,8 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
         return int(o, 0)
 
     def addr_of(o):
+        if type(o) is tuple:
+            return o[1], o[2]
         inner = o.strip()[1:-1]
         m = re.match(r"^([%\w$.]+)\s*(?:\+\s*(-?\w+))?$", inner)
         base, off = m.group(1), int(m.group(2), 0) if m.group(2) else 0
@@ -359,6 +445,8 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
         while pc < n_instr:
             guard, op, ops = kernel.instrs[pc]
             pc += 1
+            if TRACE is not None and TRACE(special):
+                print("TRACE", pc - 1, guard, ".".join(op), ops, {o: R.get(o) for o in ops if o.startswith("%") and o in R})
             if guard is not None and bool(R[guard[0]]) == guard[1]:
                 continue
             name, ty = op[0], op[-1]
@@ -366,7 +454,7 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
                 return bytes(retbuf)
             if name == "call":
                 # call.uni (retval0), fname, (param0, param1, ...);   or   call.uni fname, (param0, ...);
-                has_ret = ops[0].startswith("(") and len(ops) == 3
+                has_ret = type(ops[0]) is str and ops[0].startswith("(") and len(ops) == 3
                 fname = ops[1] if has_ret else ops[0]
                 args = [a.strip() for a in ops[-1].strip("()").split(",") if a.strip()]
                 func = kernel.module.funcs[fname]
@@ -385,37 +473,47 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
                 continue
             if name == "atom":                   # atom.global.<op>.b32 d, [a], b: threads run one after another between barriers, so plain read-modify-write
                 nbytes = _WIDTH[ty] // 8
+                if ty == "f32":                  # atomicAdd(float *): one correctly rounded addition
+                    assert op[2] == "add"
+                    old_f = f32_from_bits(ld(op[1], 4, ops[1]))
+                    st(op[1], 4, ops[1], f32_bits(F32(old_f + val(ops[2], "f32"))))
+                    R[ops[0]] = old_f
+                    continue
                 old_v = ld(op[1], nbytes, ops[1])
                 b_ = _mask(val(ops[2], ty), _WIDTH[ty])
-                new_v = {"or": old_v | b_, "and": old_v & b_, "xor": old_v ^ b_, "add": old_v + b_, "exch": b_, "max": max(old_v, b_), "min": min(old_v, b_)}[op[2]]
+                if ty[0] == "s" and op[2] in ("min", "max"):
+                    sa, sb = _signed(old_v, _WIDTH[ty]), _signed(b_, _WIDTH[ty])
+                    new_v = _mask(min(sa, sb) if op[2] == "min" else max(sa, sb), _WIDTH[ty])
+                else:
+                    new_v = {"or": old_v | b_, "and": old_v & b_, "xor": old_v ^ b_, "add": old_v + b_, "exch": b_, "max": max(old_v, b_), "min": min(old_v, b_)}[op[2]]
                 st(op[1], nbytes, ops[1], new_v)
                 R[ops[0]] = old_v
                 continue
             if name == "ld":
                 space = op[1]
                 nbytes = _WIDTH[ty] // 8
-                if ops[0].startswith("{"):
+                if type(ops[0]) is str and ops[0].startswith("{"):
                     regs = [r.strip() for r in ops[0][1:-1].split(",")]
                     base, off = addr_of(ops[1])
                     for k, r in enumerate(regs):
-                        R[r] = to_reg(ty, ld(space, nbytes, f"[{base}+{off + k * nbytes}]"))
+                        R[r] = to_reg(ty, ld(space, nbytes, ("M", base, off + k * nbytes)))
                 else:
                     R[ops[0]] = to_reg(ty, ld(space, nbytes, ops[1]))
                 continue
             if name == "st":
                 nbytes = _WIDTH[ty] // 8
-                if ops[1].startswith("{"):
+                if type(ops[1]) is str and ops[1].startswith("{"):
                     regs = [r.strip() for r in ops[1][1:-1].split(",")]
                     base, off = addr_of(ops[0])
                     for k, r in enumerate(regs):
-                        st(op[1], nbytes, f"[{base}+{off + k * nbytes}]", from_reg(ty, val(r, ty)))
+                        st(op[1], nbytes, ("M", base, off + k * nbytes), from_reg(ty, val(r, ty)))
                 else:
                     st(op[1], nbytes, ops[0], from_reg(ty, val(ops[1], ty)))
                 continue
-            if name == "mov" and (ops[0].startswith("{") or ops[1].startswith("{")):
+            if name == "mov" and ((type(ops[0]) is str and ops[0].startswith("{")) or (type(ops[1]) is str and ops[1].startswith("{"))):
                 # pack / unpack: mov.b32 %r, {%rs_lo, %rs_hi};   mov.b32 {%rs_lo, %rs_hi}, %r;   (also b64 <-> two b32)
                 total = _WIDTH[ty]
-                if ops[1].startswith("{"):
+                if type(ops[1]) is str and ops[1].startswith("{"):
                     parts = [q_.strip() for q_ in ops[1][1:-1].split(",")]
                     w_ = total // len(parts)
                     v = 0
@@ -434,6 +532,8 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
                 continue
             if name in ("mov", "cvta"):
                 v = val(ops[1], ty)
+                if ty == "pred":                 # mov.pred %p, -1: any non-zero immediate is "true"
+                    v = int(bool(v))
                 if ty == "b32":                  # a bit cast when the register classes differ (%f <-> %r)
                     if ops[0].startswith("%f") and not isinstance(v, np.floating):
                         v = f32_from_bits(int(v))
@@ -445,6 +545,8 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
                 cmp_, a, b = op[1], val(ops[1], ty), val(ops[2], ty)
                 if ty in ("s16", "s32", "s64"):
                     a, b = _signed(a, _WIDTH[ty]), _signed(b, _WIDTH[ty])
+                elif ty != "f32":                # unsigned / bit types: immediates such as -3 mean their two's complement pattern
+                    a, b = _mask(a, _WIDTH[ty]), _mask(b, _WIDTH[ty])
                 if ty == "f32":
                     unordered = bool(np.isnan(a) or np.isnan(b))
                     table = {"eq": a == b, "ne": a != b, "lt": a < b, "le": a <= b, "gt": a > b, "ge": a >= b}
@@ -460,7 +562,7 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
                 R[ops[0]] = int(bool(res))
                 continue
             if ty == "pred":
-                a, b = R[ops[1]], (R[ops[2]] if len(ops) > 2 else 0)
+                a, b = int(bool(val(ops[1], "pred"))), (int(bool(val(ops[2], "pred"))) if len(ops) > 2 else 0)
                 R[ops[0]] = {"or": a | b, "and": a & b, "xor": a ^ b, "not": 1 - a}[name]
                 continue
             if name == "selp":
@@ -557,6 +659,54 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
                     acc += av * bv
                 R[ops[0]] = _mask(acc, 32)
                 continue
+            if name == "dp4a":                   # d = c + sum of the four byte products of a and b
+                at, bt = op[1], op[2]
+                a, b = _mask(val(ops[1], "b32"), 32), _mask(val(ops[2], "b32"), 32)
+                c = val(ops[3], "b32")
+                acc = _signed(c, 32) if (at[0] == "s" or bt[0] == "s") else _mask(c, 32)
+                for k_ in range(4):
+                    av, bv = (a >> (8 * k_)) & 0xFF, (b >> (8 * k_)) & 0xFF
+                    acc += (_signed(av, 8) if at[0] == "s" else av) * (_signed(bv, 8) if bt[0] == "s" else bv)
+                R[ops[0]] = _mask(acc, 32)
+                continue
+            if name == "bfe":                    # bit field extract: len bits of a from position pos (sign-extended for .s32)
+                bits_ = _WIDTH[ty]
+                a, pos, ln = _mask(val(ops[1], ty), bits_), _mask(val(ops[2], "u32"), 32) & 0xFF, _mask(val(ops[3], "u32"), 32) & 0xFF
+                if ln == 0:
+                    r = 0
+                else:
+                    field = (a >> min(pos, bits_)) & ((1 << min(ln, bits_)) - 1)
+                    if ty[0] == "s":
+                        top = min(pos + ln - 1, bits_ - 1)
+                        if (a >> top) & 1:
+                            field |= ((1 << bits_) - 1) & ~((1 << min(ln, bits_)) - 1)
+                    r = field
+                R[ops[0]] = _mask(r, bits_)
+                continue
+            if name == "bfind":                  # position of the most significant set bit (.shiftamt: the left shift that normalises it); 0xffffffff for 0
+                bits_ = _WIDTH[ty]
+                a = _mask(val(ops[1], ty), bits_)
+                if ty[0] == "s" and (a >> (bits_ - 1)):
+                    a = _mask(~a, bits_)
+                if a == 0:
+                    r = 0xFFFFFFFF
+                else:
+                    msb = a.bit_length() - 1
+                    r = (bits_ - 1 - msb) if "shiftamt" in op else msb
+                R[ops[0]] = r
+                continue
+            if name == "brev":
+                bits_ = _WIDTH[ty]
+                a = _mask(val(ops[1], ty), bits_)
+                R[ops[0]] = int(format(a, "0%db" % bits_)[::-1], 2)
+                continue
+            if name == "popc":
+                R[ops[0]] = bin(_mask(val(ops[1], ty), _WIDTH[ty])).count("1")
+                continue
+            if name == "clz":
+                bits_ = _WIDTH[ty]
+                R[ops[0]] = bits_ - _mask(val(ops[1], ty), bits_).bit_length()
+                continue
             if name == "shf":                    # funnel shift of {b, a} (b high), wrap mode
                 a, b, c = _mask(val(ops[1], "b32"), 32), _mask(val(ops[2], "b32"), 32), _mask(val(ops[3], "b32"), 32) & 31
                 pool = (b << 32) | a
@@ -605,7 +755,7 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
     return bytes(retbuf)
 
 
-def launch(kernel, grid, block, params, mem):
+def launch(kernel, grid, block, params, mem, dyn_smem=0):
     """params: one bytes object per kernel parameter (already in the parameter's binary layout)."""
     blob = bytearray(kernel.param_bytes)
     assert len(params) == len(kernel.params), (len(params), len(kernel.params))
@@ -620,6 +770,9 @@ def launch(kernel, grid, block, params, mem):
         total = (total + 15) // 16 * 16
         shared_off[sname] = total
         total += size
+    total = (total + 15) // 16 * 16
+    shared_off["<dynamic>"] = total
+    total += dyn_smem
     for bz in range(grid[2]):
         for by in range(grid[1]):
             for bx in range(grid[0]):

@@ -1,0 +1,47 @@
+"""CPU: the whole PRODUCT library, end to end, without a GPU.
+
+oracle/emu builds libvsb200_emu.so from the product's own object files and a stand-in CUDA runtime (device memory = host memory,
+streams inert); every kernel the product's host code launches -- calibration (weight pyramids, plans), vsb_set_mesh (splat /
+divide / upsample / tap table), and the frame path K1 K2 k_down2 k_down_tail k_coarse k_blend -- is executed by the PTX
+interpreter (oracle/ptx_interp.py) on the PTX of the same .cu files, compiled with the product's flags.  So this runs the shipped
+host logic (ROIs, seams, tile lists, launch sequences) and the shipped device code, and compares the panorama with oracle-G bit
+for bit -- the `-m gpu` parity test of a small rig, minus the hardware.  (k_down2 takes its plain-load form: no tensor-map encoder
+here, as on a driver without one; atomics are sequential; timing-dependent behaviour is not modelled.)"""
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(case):
+    if not (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        pytest.skip("nvcc not found (the emulation needs the product's PTX)")
+    env = {k: v for k, v in os.environ.items() if k != "VSB200_LIB"}
+    r = subprocess.run([sys.executable, "-m", "oracle.emu.run_case", json.dumps(case)], capture_output=True, text=True, timeout=1500, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+
+
+def test_product_library_end_to_end_on_the_emulated_runtime():
+    res = _run(dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3))
+    assert res["error"] is None, res["error"]
+    assert res["roi_equal"]
+    assert res["mesh_maps"] == 0, "vsb_set_mesh kernels vs oracle mesh -> map"
+    assert res["warped"] == 0 and res["gauss0"] == 0 and res["gauss2"] == 0, res
+    assert res["pano"] == 0 and res["pano_nonzero"] > res["pano_samples"] // 2, res
+    names = " ".join(res["launched"])
+    for k in ("k_remap_stage1_tab", "k_remap_stage2_tab", "k_down2", "k_down_tail", "k_coarse", "k_blend"):
+        assert k in names, (k, res["launched"])
+    assert res["launch_count"] in (6, 7)      # K1 K2 down2 down_tail coarse blend_seam (+ blend_int when a tile is interior)
+
+
+@pytest.mark.skipif(not os.environ.get("VSB_EMU_FULL"), reason="several minutes of interpretation: set VSB_EMU_FULL=1 (two frames, interior blend tiles)")
+def test_product_library_end_to_end_larger_rig():
+    res = _run(dict(n_views=4, src_w=96, src_h=64, pano_width=384, num_bands=3, frames=2))
+    assert res["error"] is None and res["pano"] == 0 and res["warped"] == 0 and res["gauss2"] == 0, res
+    assert "k_blend_int" in " ".join(res["launched"]), res["launched"]
