@@ -42,12 +42,20 @@ def main():
     t_cal = time.time() - t0
     roi, _, _ = st.get_roi()
     W, H = roi[2], roi[3]
-    frames = [[S.frame(i, f, sw, sh) for i in range(n)] for f in range(F)]
-    bufs = [E.Buffer(a) for fr in frames for a in fr]
-    outs = [E.Buffer(np.full((H, W, 3), -12345, np.int16)) for _ in range(F)]
+    wire = bool(case.get("wire"))       # NV12 frames in (converted inside remap #1's tap fetch), CV_8UC3 panoramas out
+    if wire:
+        st.set_formats(B.IN_NV12, B.OUT_U8C3)
+        nv = [[S.frame_nv12(i, f, sw, sh) for i in range(n)] for f in range(F)]
+        frames = [[og.nv12_to_bgr(a, sw, sh) for a in fr] for fr in nv]
+        bufs = [E.Buffer(a) for fr in nv for a in fr]
+        outs = [E.Buffer(np.full((H, W, 3), 0xAB, np.uint8)) for _ in range(F)]
+    else:
+        frames = [[S.frame(i, f, sw, sh) for i in range(n)] for f in range(F)]
+        bufs = [E.Buffer(a) for fr in frames for a in fr]
+        outs = [E.Buffer(np.full((H, W, 3), -12345, np.int16)) for _ in range(F)]
     n0 = len(E.stats()["launches"])
     t0 = time.time()
-    st.compose([b.ptr for b in bufs], sw * 3, [o.ptr for o in outs], W * 6, 0)
+    st.compose([b.ptr for b in bufs], sw if wire else sw * 3, [o.ptr for o in outs], W * (3 if wire else 6), 0)
     t_compose = time.time() - t0
     launched = [name for name, _, _ in E.stats()["launches"][n0:]]
 
@@ -79,6 +87,8 @@ def main():
     res["pano"] = 0
     for f in range(F):
         want, _ = orig.compose(frames[f])
+        if wire:
+            want = og.s16_to_u8(want)
         res["pano"] += int(np.count_nonzero(outs[f].a != want))
     res["pano_samples"] = int(F * H * W * 3)
     res["pano_nonzero"] = int(np.count_nonzero(outs[0].a))

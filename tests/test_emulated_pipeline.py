@@ -45,3 +45,12 @@ def test_product_library_end_to_end_larger_rig():
     res = _run(dict(n_views=4, src_w=96, src_h=64, pano_width=384, num_bands=3, frames=2))
     assert res["error"] is None and res["pano"] == 0 and res["warped"] == 0 and res["gauss2"] == 0, res
     assert "k_blend_int" in " ".join(res["launched"]), res["launched"]
+
+
+@pytest.mark.skipif(not os.environ.get("VSB_EMU_FULL"), reason="another minute and a half of interpretation: set VSB_EMU_FULL=1 (NV12 in, CV_8UC3 out)")
+def test_product_library_wire_formats_on_the_emulated_runtime():
+    """VSB_IN_NV12 / VSB_OUT_U8C3: the NV12 conversion fused into remap #1's tap fetch (k_remap_stage1_nv12) and the CV_8UC3 store of the
+    blend kernels, against og.nv12_to_bgr -> compose -> og.s16_to_u8."""
+    res = _run(dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3, wire=True))
+    assert res["error"] is None and res["pano"] == 0 and res["warped"] == 0, res
+    assert "k_remap_stage1_nv12" in " ".join(res["launched"]), res["launched"]
