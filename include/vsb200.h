@@ -87,7 +87,7 @@ int vsb_set_gain(vsb_stitcher *s, int i, float gain);
 
 /* ---- fixed-rig calibration (the static half of the path): calibrateCameras + warpImages,
  *      360_stitcher/calibration.cpp:28-249, generalised to N views (yaw_i = 2*pi*i/N, pitch = roll = 0), work_scale =
- *      compose_scale = 1, sphere radius = pano_width / 2*pi.  Host-side, runs once; computes K/R, seam-scale Voronoi
+ *      compose_scale = 1 (vsb_calibrate_rig_scaled below takes a compose_scale), sphere radius = pano_width / 2*pi.  Host-side, runs once; computes K/R, seam-scale Voronoi
  *      masks (VoronoiSeamFinder, S/src/seam_finders.cpp:72-162), compose-scale ROIs and maps, then calls
  *      vsb_prepare / vsb_init_view / vsb_set_maps / vsb_set_gain.  gains may be NULL (all 1). -------------------- */
 typedef struct vsb_rig_info {
@@ -126,6 +126,24 @@ int vsb_resize_linear_u8(const uint8_t *d_src, int sw, int sh, size_t src_pitch,
                          size_t dst_pitch, double fx, double fy, void *stream);
 int vsb_gain_compensator_feed(int n, const uint8_t *const *d_imgs, const uint8_t *const *d_masks, const int *sizes_wh,
                               const int *corners_xy, double *gains_out, void *stream);
+/* ---- compose_scale != 1 (A/calibration.cpp:137-205: COMPOSE_MEGAPIX; A/timed.cpp:74-81: the per-frame
+ *      cuda::resize(full_imgs[i], images[i], Size(), compose_scale, compose_scale, INTER_LINEAR) in front of remap #1).
+ *      vsb_compose_size: the sizes the reference derives from a compose_scale -- frame[2] = the frame remap #1 reads (the full
+ *      frame, or cvRound(full * scale) when |scale - 1| > 0.1: the reference's test for resizing at all, and the dsize cuda::resize
+ *      computes), which also sizes the blender (:159-178); map_src[2] = (int)(full * scale), the img_size its maps and masks are
+ *      ALWAYS built for (:203-204).  Where the two differ (cvRound != truncation -- e.g. the reference's default COMPOSE_MEGAPIX
+ *      = 1.4 on 1080p frames: 1578 vs 1577 columns -- or a scale within 0.1 of 1) the reference blends views whose maps were built
+ *      for a slightly different frame; this library reproduces that.  vsb_rig_camera_scaled: the rig camera after focal, ppx,
+ *      ppy *= compose_work_aspect (:168-172, doubles; work_scale = 1).  vsb_set_compose_scale (after vsb_set_maps; vsb_prepare
+ *      resets it to 1): the maps address frame[], the frames handed to vsb_feed / vsb_compose / vsb_submit_host are full_w x
+ *      full_h and go through the resize on the device first (bit-exact with the reference's kernel, CW/src/cuda/resize.cu:71-106).
+ *      vsb_calibrate_rig_scaled: vsb_calibrate_rig (on_device = 0) / vsb_calibrate_rig_device (1) at that compose_scale: warper
+ *      scale * (float)compose_scale, scaled cameras, ROIs / maps / masks as above, seam scale from the full frame. -------- */
+int vsb_compose_size(int full_w, int full_h, double compose_scale, int frame[2], int map_src[2], int *resized);
+int vsb_rig_camera_scaled(int n_views, int i, int src_w, int src_h, double hfov_deg, double compose_work_aspect, float K[9], float R[9]);
+int vsb_set_compose_scale(vsb_stitcher *s, double compose_scale, int full_w, int full_h);
+int vsb_calibrate_rig_scaled(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg,
+                             const float *gains, double compose_scale, int on_device);
 int vsb_rig_info_get(const vsb_stitcher *s, vsb_rig_info *out);
 int vsb_get_config(const vsb_stitcher *s, vsb_config *out);
 

@@ -152,6 +152,9 @@ public:
         check(vsb_set_maps(h_, i, (const float *)xmap.data, (const float *)ymap.data, xmap.cols, xmap.rows, xmap.step, 1, src.width, src.height));
     }
     void setGain(int i, double gain) { check(vsb_set_gain(h_, i, (float)gain)); }
+    /* compose_scale of stitch_online (A/timed.cpp:56,74-81): with a scale other than 1 the maps address the resized frame and
+       stitch_online / stitch resize the full_size frames on the device first (cuda::resize, INTER_LINEAR); call after setMaps */
+    void setComposeScale(double compose_scale, Size full_size) { check(vsb_set_compose_scale(h_, compose_scale, full_size.width, full_size.height)); }
     /* wire format in / consumer format out: VSB_IN_NV12 = the capture boards' NV12 frames (cv::cvtColor(CV_YUV2BGR_NV12),
        A/networking.cpp:46, runs on the device); VSB_OUT_U8C3 = the consumer's mat.convertTo(mat_8u, CV_8U) (A/timed.cpp:250)
        fused into blend(): gpuOut is then CV_8UC3 */

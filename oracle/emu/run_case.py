@@ -34,7 +34,13 @@ def main():
     gains = S.gains(n)
     t0 = time.time()
     st = B.Stitcher(n, nb, True, F)
-    st.calibrate_rig(0, pano, sw, sh, 90.0, gains)          # the product's host calibration + its weight / plan kernels
+    cs = float(case.get("compose_scale", 1.0))             # != 1: sw x sh are the full frames, resized on the device in front of remap #1
+    if cs != 1.0:
+        st.calibrate_rig_scaled(0, pano, sw, sh, cs, 90.0, gains, on_device=bool(case.get("device_calibration")))
+    elif case.get("device_calibration"):                   # every per-pixel loop of the calibration as kernels (maps differ from libm's by ulps)
+        st.calibrate_rig_device(0, pano, sw, sh, 90.0, gains)
+    else:
+        st.calibrate_rig(0, pano, sw, sh, 90.0, gains)      # the product's host calibration + its weight / plan kernels
     info = st.rig_info()
     for i in range(n):
         mx, my = S.mesh(info.view_roi[i][2], info.view_roi[i][3])
@@ -59,7 +65,7 @@ def main():
     t_compose = time.time() - t0
     launched = [name for name, _, _ in E.stats()["launches"][n0:]]
 
-    orig = op.OracleRig(n, sw, sh, pano, num_bands=nb, enable_local=True, gains=gains)
+    orig = op.OracleRig(n, sw, sh, pano, num_bands=nb, enable_local=True, gains=gains, compose_scale=cs)
     for i in range(n):
         orig.set_mesh(i, *S.mesh(*orig.sizes[i]))
 

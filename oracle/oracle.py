@@ -63,6 +63,14 @@ def rig_camera(n_views, i, src_w, src_h, hfov_deg=90.0):
     return K.reshape(3, 3), R.reshape(3, 3)
 
 
+def rig_camera_scaled(n_views, i, src_w, src_h, hfov_deg, compose_work_aspect):
+    """the camera after calibration.cpp:168-172 scaled focal / ppx / ppy by compose_work_aspect (doubles), as float K"""
+    K = np.zeros(9, np.float32)
+    R = np.zeros(9, np.float32)
+    lib().og_rig_camera_scaled(n_views, i, src_w, src_h, C.c_double(hfov_deg), C.c_double(compose_work_aspect), _p(K, C.c_float), _p(R, C.c_float))
+    return K.reshape(3, 3), R.reshape(3, 3)
+
+
 def projector(K, R):
     K = _f32(K).reshape(9)
     R = _f32(R).reshape(9)

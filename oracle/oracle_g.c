@@ -107,6 +107,18 @@ void og_rig_camera(int n_views, int i, int src_w, int src_h, double hfov_deg, fl
     R[6] = (float)-sin(rot); R[7] = 0.f; R[8] = (float)cos(rot);
 }
 
+/* the same camera after  cameras[i].focal *= compose_work_aspect; ppx *= ...; ppy *= ...  (A/calibration.cpp:168-172; doubles,
+ * work_scale = 1 so compose_work_aspect = compose_scale), then K().convertTo(CV_32F) (:175-176) */
+void og_rig_camera_scaled(int n_views, int i, int src_w, int src_h, double hfov_deg, double compose_work_aspect, float K[9], float R[9])
+{
+    const double PI = 3.1415926535897932384626;
+    og_rig_camera(n_views, i, src_w, src_h, hfov_deg, K, R);
+    double ppx = src_w / 2.0, ppy = src_h / 2.0;
+    double focal = (1.0 / tan(hfov_deg * PI / 180.0 * 0.5)) * ppx;
+    focal *= compose_work_aspect; ppx *= compose_work_aspect; ppy *= compose_work_aspect;
+    K[0] = (float)focal; K[2] = (float)ppx; K[4] = (float)(focal * 1.0); K[5] = (float)ppy;
+}
+
 static void mat3_mul_d(const float *a, const float *b, float *c)
 {
     for (int i = 0; i < 3; ++i)

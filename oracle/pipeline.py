@@ -1,7 +1,8 @@
 """Oracle-side restatement of the WHOLE path (calibration + per-frame compose), built from oracle-G primitives.
 
 TEST INFRASTRUCTURE ONLY (see oracle_g.h).  Mirrors, in reference order:
-  calibration : 360_stitcher/calibration.cpp:28-249  (calibrateCameras, warpImages) with work_scale = compose_scale = 1
+  calibration : 360_stitcher/calibration.cpp:28-249  (calibrateCameras, warpImages) with work_scale = 1; compose_scale = 1 unless
+                the rig is built with compose_scale= (then calibration.cpp:137-205 and the per-frame cuda::resize, timed.cpp:74-81)
   per frame   : 360_stitcher/timed.cpp:56-152        (stitch_online x N, stitch_one)
 """
 import math
@@ -36,8 +37,18 @@ def synthetic_mesh(W, H, rows=10, cols=10, phase=0.0):
 
 class OracleRig:
     def __init__(self, n_views, src_w, src_h, pano_width, projection=og.PROJ_SPHERICAL, num_bands=5,
-                 enable_local=True, gains=None, hfov_deg=90.0):
+                 enable_local=True, gains=None, hfov_deg=90.0, compose_scale=1.0):
         self.n, self.src_w, self.src_h = n_views, src_w, src_h
+        # compose_scale (calibration.cpp:137-205, timed.cpp:74-81), followed literally: when it is more than 0.1 away from 1 the frames
+        # are cuda::resize'd per frame to cvRound(full * scale) (:159-160 = the dsize cuda::resize computes) and the blender is sized
+        # from that; the maps and masks are ALWAYS built for (int)(full * scale) (:204); the cameras and the warper are always scaled.
+        # src_w x src_h stays the size of the caller's frames (full_img_size).
+        self.compose_scale = float(compose_scale)
+        self.scaled = abs(self.compose_scale - 1) > 1e-1          # the reference's own test, timed.cpp:75 / calibration.cpp:157
+        self.comp_w, self.comp_h = src_w, src_h                   # the frame remap #1 reads
+        if self.scaled:
+            self.comp_w, self.comp_h = int(np.rint(src_w * self.compose_scale)), int(np.rint(src_h * self.compose_scale))
+        self.map_src = (int(src_w * self.compose_scale), int(src_h * self.compose_scale))   # img_size of buildMaps / the mask warp
         self.projection, self.enable_local = projection, enable_local
         self.scale = np.float32(pano_width / (2.0 * 3.1415926535897932384626))
         self.gains = [1.0] * n_views if gains is None else [float(g) for g in gains]
@@ -64,13 +75,19 @@ class OracleRig:
         self.seam_masks, self.seam_corners, self.seam_sizes = seam_masks, seam_corners, seam_sizes
 
         # ---- compose scale: ROIs, prepare, maps, masks, init_gpu (calibration.cpp:137-246)
-        self.rois = [og.warp_roi(projection, self.scale, self.K[i], self.R[i], src_w, src_h) for i in range(n_views)]
-        self.corners = [r[:2] for r in self.rois]
-        self.sizes = [r[2:] for r in self.rois]
+        if self.compose_scale != 1.0:
+            # warper scale: warped_image_scale * static_cast<float>(compose_work_aspect) (:151); cameras: focal, ppx, ppy *= aspect (:168-172)
+            self.scale = np.float32(self.scale * np.float32(self.compose_scale))
+            self.K, self.R = zip(*[og.rig_camera_scaled(n_views, i, src_w, src_h, hfov_deg, self.compose_scale) for i in range(n_views)])
+        prep = [og.warp_roi(projection, self.scale, self.K[i], self.R[i], self.comp_w, self.comp_h) for i in range(n_views)]   # :176-178
+        self.rois = [og.warp_roi(projection, self.scale, self.K[i], self.R[i], *self.map_src) for i in range(n_views)]         # buildMaps' own roi
+        self.corners = [r[:2] for r in prep]                 # where the blender puts view i
+        self.prep_sizes = [r[2:] for r in prep]              # what prepare() sizes the panorama from
+        self.sizes = [r[2:] for r in self.rois]              # size of the maps, the masks and the warped views (= prep_sizes unless round != trunc)
         self.blender = og.Blender(num_bands)
-        self.blender.prepare(self.corners, self.sizes)
+        self.blender.prepare(self.corners, self.prep_sizes)
         self.xmaps, self.ymaps, self.masks = [], [], []
-        full = np.full((src_h, src_w), 255, np.uint8)
+        full = np.full((self.map_src[1], self.map_src[0]), 255, np.uint8)
         for i in range(n_views):
             xm, ym = og.build_maps(projection, self.scale, self.K[i], self.R[i], *self.rois[i])
             warped = og.remap_nearest_u8c1(full, xm, ym)
@@ -120,6 +137,8 @@ class OracleRig:
 
     def warp_view(self, i, img):
         """stitch_online up to (not including) feed_online: remap#1 -> gain -> remap#2 (timed.cpp:84-108)."""
+        if getattr(self, "scaled", False):   # cuda::resize(full, img, Size(), compose_scale, compose_scale, INTER_LINEAR), timed.cpp:74-77
+            img = og.cuda_resize_linear_u8(img, self.comp_w, self.comp_h, self.compose_scale, self.compose_scale)
         p = og.remap_linear_u8(img, self.xmaps[i], self.ymaps[i])
         p = og.gain_u8(p, np.float32(self.gains[i]))
         if self.enable_local:

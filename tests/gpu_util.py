@@ -30,22 +30,27 @@ class GpuRig:
     """Drives a vsb_stitcher for a rig; static inputs either from the oracle (inject) or from vsb_calibrate_rig."""
 
     def __init__(self, n_views, src_w, src_h, pano_width, projection=0, num_bands=5, enable_local=True, gains=None,
-                 max_batch=1, oracle_rig=None, device_calibration=False):
+                 max_batch=1, oracle_rig=None, device_calibration=False, compose_scale=1.0):
         self.n, self.src_w, self.src_h = n_views, src_w, src_h
         self.st = B.Stitcher(n_views, num_bands, enable_local, max_batch)
-        if device_calibration:
+        if compose_scale != 1.0 and oracle_rig is None:
+            self.st.calibrate_rig_scaled(projection, pano_width, src_w, src_h, compose_scale, 90.0, gains, on_device=device_calibration)
+        elif device_calibration:
             self.st.calibrate_rig_device(projection, pano_width, src_w, src_h, 90.0, gains)
         elif oracle_rig is None:
             self.st.calibrate_rig(projection, pano_width, src_w, src_h, 90.0, gains)
         else:
             r = oracle_rig
-            self.st.prepare(r.corners, r.sizes)
+            self.st.prepare(r.corners, getattr(r, "prep_sizes", r.sizes))
             for i in range(n_views):
                 m = np.ascontiguousarray(r.masks[i])
                 self.st.init_view(i, m.ctypes.data, m.shape[1], m.shape[0], m.shape[1], r.corners[i])
                 xm, ym = np.ascontiguousarray(r.xmaps[i]), np.ascontiguousarray(r.ymaps[i])
-                self.st.set_maps(i, xm.ctypes.data, ym.ctypes.data, xm.shape[1], xm.shape[0], xm.shape[1] * 4, src_w, src_h)
+                self.st.set_maps(i, xm.ctypes.data, ym.ctypes.data, xm.shape[1], xm.shape[0], xm.shape[1] * 4,
+                                 getattr(r, "comp_w", src_w), getattr(r, "comp_h", src_h))
                 self.st.set_gain(i, r.gains[i])
+            if compose_scale != 1.0:   # the low-level route: maps of the resized frame + vsb_set_compose_scale
+                self.st.set_compose_scale(compose_scale, src_w, src_h)
         self.roi_final, self.roi_padded, self.num_bands = self.st.get_roi()
         self.geom = [self.st.view_geometry(i) for i in range(n_views)]
         info = self.st.rig_info()

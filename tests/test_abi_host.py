@@ -96,6 +96,31 @@ def test_host_geometry_matches_oracle_and_reference(vsb, og, rig):
             assert len(row) == 1 and roi == tuple(int(v) for v in row[0, 6:])   # = the reference's warpRoi
 
 
+def test_compose_scale_sizes_and_cameras(vsb, og):
+    """compose_scale != 1 (A/calibration.cpp:137-205): the sizes the reference derives -- cvRound for the frame and the blender, (int)
+    for the maps, no resize within 0.1 of 1 -- and the scaled cameras, host side (no device needed), against the oracle's restatement."""
+    assert vsb.compose_size(1920, 1080, 1.0) == ((1920, 1080), (1920, 1080), False)
+    assert vsb.compose_size(1920, 1080, 0.5) == ((960, 540), (960, 540), True)
+    # COMPOSE_MEGAPIX = 1.4 on 1080p frames, the reference's default (A/defs.h:53): cvRound and (int) disagree in the width
+    cs = min(1.0, (1.4e6 / (1920 * 1080)) ** 0.5)
+    assert vsb.compose_size(1920, 1080, cs) == ((1578, 887), (1577, 887), True)
+    assert vsb.compose_size(1920, 1080, 0.95) == ((1920, 1080), (1824, 1026), False)    # cameras scaled, frames not (A/timed.cpp:75)
+    assert vsb.compose_size(101, 51, 0.5) == ((50, 26), (50, 25), True)                   # cvRound is round-half-even: 50.5 -> 50, 25.5 -> 26
+    lib = vsb.lib()
+    two = (C.c_int * 2)()
+    assert lib.vsb_compose_size(0, 10, C.c_double(0.5), two, two, None) == -1
+    assert lib.vsb_compose_size(10, 10, C.c_double(0.0), two, two, None) == -1
+    assert lib.vsb_compose_size(10, 10, C.c_double(0.5), None, two, None) == -1
+    assert lib.vsb_set_compose_scale(None, C.c_double(0.5), 10, 10) == -1
+    for (n, sw, sh, c) in ((6, 1920, 1080, cs), (4, 320, 240, 0.75), (12, 3840, 2160, 0.5)):
+        for i in range(n):
+            K, R = vsb.rig_camera_scaled(n, i, sw, sh, 90.0, c)
+            Ko, Ro = og.rig_camera_scaled(n, i, sw, sh, 90.0, c)
+            assert np.array_equal(np.float32(K), Ko.reshape(9)) and np.array_equal(np.float32(R), Ro.reshape(9))
+            K1, _ = vsb.rig_camera(n, i, sw, sh)
+            assert abs(K[0] - K1[0] * c) <= 1e-3 and abs(K[2] - K1[2] * c) <= 1e-3 and K[8] == 1.0
+
+
 def test_host_voronoi_matches_reference(vsb, og):
     from tests.golden import make_golden as G
     gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_cpu.npz"))

@@ -54,3 +54,14 @@ def test_product_library_wire_formats_on_the_emulated_runtime():
     res = _run(dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3, wire=True))
     assert res["error"] is None and res["pano"] == 0 and res["warped"] == 0, res
     assert "k_remap_stage1_nv12" in " ".join(res["launched"]), res["launched"]
+
+
+def test_product_library_compose_scale_on_the_emulated_runtime():
+    """compose_scale != 1 (A/calibration.cpp:137-205, A/timed.cpp:74-81) through the shipped library: vsb_calibrate_rig_scaled (scaled
+    cameras and warper, blender sized from cvRound(full * scale) = (49, 33), maps and masks built for (int)(full * scale) = (48, 32) --
+    the reference's own mismatch, reproduced) and the per-frame cuda::resize in front of remap #1 (k_prescale), bit-identical to oracle-G."""
+    res = _run(dict(n_views=4, src_w=61, src_h=41, pano_width=192, num_bands=3, compose_scale=0.8))
+    assert res["error"] is None and res["roi_equal"], res
+    assert res["mesh_maps"] == 0 and res["warped"] == 0 and res["gauss0"] == 0 and res["gauss2"] == 0, res
+    assert res["pano"] == 0 and res["pano_nonzero"] > res["pano_samples"] // 2, res
+    assert "k_prescale" in " ".join(res["launched"]), res["launched"]

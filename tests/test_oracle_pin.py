@@ -257,6 +257,37 @@ def test_live_pyramids_bordered_size(og):
     _ties_only(og.pyr_down_s16(a), vr.pyr_down(a, vr.T_S16C3), "pyrDown")
 
 
+def test_live_scaled_rig_geometry_vs_reference_projector(og):
+    """compose_scale != 1: the oracle's scaled rig (cameras * compose_work_aspect, warper scale * (float)aspect, sizes from cvRound /
+    (int), oracle/pipeline.py) put through the REFERENCE's own projector (warpers.cpp, compiled in place): same ROIs for the
+    blender sizes and for the maps, maps within the usual 2e-3 px; and the per-frame cuda::resize the scaled path adds equals the
+    reference's float gold (resizeImpl<uchar, LinearInterpolator>, CW/test/test_resize.cpp:54-74) on an explicit-scale case."""
+    vr = _vr()
+    from oracle import pipeline as op
+    for (n, sw, sh, pano, cs, proj) in ((4, 320, 240, 1024, 0.75, 0), (6, 1920, 1080, 3840, min(1.0, (1.4e6 / (1920 * 1080)) ** 0.5), 0), (5, 640, 480, 1600, 0.5, 1)):
+        scale = np.float32(np.float32(pano / (2.0 * 3.1415926535897932384626)) * np.float32(cs))
+        comp = (int(np.rint(sw * cs)), int(np.rint(sh * cs)))
+        msrc = (int(sw * cs), int(sh * cs))
+        for i in range(n):
+            K, R = og.rig_camera_scaled(n, i, sw, sh, 90.0, cs)
+            assert og.warp_roi(proj, scale, K, R, *comp) == vr.warp_roi(proj, scale, K, R, *comp)
+            roi = og.warp_roi(proj, scale, K, R, *msrc)
+            assert roi == vr.warp_roi(proj, scale, K, R, *msrc)
+            if i in (0, n // 2) and sw <= 640:
+                xm, ym = og.build_maps(proj, scale, K, R, *roi)
+                xr, yr, roi_r = vr.build_maps(proj, scale, K, R, *msrc)
+                assert tuple(roi_r) == roi
+                ok = ~((xm == -1) & (ym == -1)) & ~((xr == -1) & (yr == -1)) & (xr > -2) & (xr < msrc[0] + 1) & (yr > -2) & (yr < msrc[1] + 1)   # the part that addresses the frame
+                assert ok.sum() > 100 and np.abs(xm - xr)[ok].max() <= 2e-3 and np.abs(ym - yr)[ok].max() <= 2e-3
+    rig = op.OracleRig(4, 320, 240, 1024, num_bands=3, compose_scale=0.75)
+    assert (rig.comp_w, rig.comp_h) == (240, 180) and rig.scaled and rig.sizes == rig.prep_sizes
+    rig = op.OracleRig(4, 61, 41, 192, num_bands=3, compose_scale=0.8)          # cvRound (49, 33) vs (int) (48, 32)
+    assert (rig.comp_w, rig.comp_h) == (49, 33) and rig.map_src == (48, 32) and rig.masks[0].shape == tuple(rig.sizes[0][::-1])
+    src = G.resize_test_recipe(3)
+    want = vr.resize_gold_u8(src, 0.75, 0.75)
+    assert np.array_equal(og.cuda_resize_linear_u8(src, want.shape[1], want.shape[0], 0.75, 0.75), want)
+
+
 def test_live_small_rig_compose_vs_oracle_c(og):
     """Whole path, oracle-G vs the CPU compose on the reference's OpenCV (same static inputs): masks identical, pano close.
     Not a +-1 pin (fixed-point CPU remap + tie rounding) -- a gross-error tripwire."""

@@ -30,6 +30,7 @@ SYMBOLS = [
     "vsb_calibrate_rig_device", "vsb_estimate_gains", "vsb_voronoi_seams_device", "vsb_dilate3x3_u8", "vsb_resize_linear_u8",
     "vsb_gain_compensator_feed", "vsb_shard_unique_id", "vsb_shard_init", "vsb_shard_compose", "vsb_shard_exchange_bytes",
     "vsb_shard_plan", "vsb_shard_peer_bytes", "vsb_shard_pack", "vsb_shard_unpack", "vsb_feed_batch", "vsb_blend_batch",
+    "vsb_compose_size", "vsb_rig_camera_scaled", "vsb_set_compose_scale", "vsb_calibrate_rig_scaled",
 ]
 CONSUME_RGB, CONSUME_I420 = 0, 1
 IN_BGR8, IN_NV12 = 0, 1
@@ -92,6 +93,20 @@ def shard_unique_id():
     buf = (C.c_char * 128)()
     check(lib().vsb_shard_unique_id(buf))
     return bytes(buf.raw)
+
+
+def compose_size(full_w, full_h, compose_scale):
+    """-> (frame size remap #1 reads, img_size of the maps, whether the frames are resized)"""
+    frame, map_src, resized = (C.c_int * 2)(), (C.c_int * 2)(), C.c_int()
+    check(lib().vsb_compose_size(full_w, full_h, C.c_double(compose_scale), frame, map_src, C.byref(resized)))
+    return tuple(frame), tuple(map_src), bool(resized.value)
+
+
+def rig_camera_scaled(n_views, i, src_w, src_h, hfov_deg, compose_work_aspect):
+    K = (C.c_float * 9)()
+    R = (C.c_float * 9)()
+    check(lib().vsb_rig_camera_scaled(n_views, i, src_w, src_h, C.c_double(hfov_deg), C.c_double(compose_work_aspect), K, R))
+    return list(K), list(R)
 
 
 def rig_camera(n_views, i, src_w, src_h, hfov_deg=90.0):
@@ -161,6 +176,16 @@ class Stitcher:
         if gains is not None:
             g = (C.c_float * self.num_views)(*[float(v) for v in gains])
         check(lib().vsb_calibrate_rig_device(self._h, projection, pano_width, src_w, src_h, C.c_double(hfov_deg), g))
+
+    def calibrate_rig_scaled(self, projection, pano_width, src_w, src_h, compose_scale, hfov_deg=90.0, gains=None, on_device=False):
+        g = None
+        if gains is not None:
+            g = (C.c_float * self.num_views)(*[float(v) for v in gains])
+        check(lib().vsb_calibrate_rig_scaled(self._h, projection, pano_width, src_w, src_h, C.c_double(hfov_deg), g, C.c_double(compose_scale),
+                                             int(bool(on_device))))
+
+    def set_compose_scale(self, compose_scale, full_w, full_h):
+        check(lib().vsb_set_compose_scale(self._h, C.c_double(compose_scale), full_w, full_h))
 
     def estimate_gains(self, frame_ptrs, pitch, apply=False, stream=0):
         fp = (C.c_void_p * len(frame_ptrs))(*[int(p) for p in frame_ptrs])

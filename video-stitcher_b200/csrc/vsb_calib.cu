@@ -282,26 +282,14 @@ __global__ void k_dilate3x3(const uint8_t *__restrict__ src, int w, int h, uint8
     dst[(size_t)y * w + x] = (uint8_t)m;
 }
 
-// cuda::resize INTER_LINEAR on CV_8UC1 / CV_8UC3 (sources/modules/cudawarping/src/cuda/resize.cu:71-106): no half-pixel centre,
-// fp32 weights in the kernel's order, cvt.rni.sat.u8.  fx / fy are the factors the host wrapper passes (src/resize.cpp:76-105).
+// cuda::resize INTER_LINEAR on CV_8UC1 / CV_8UC3 (sources/modules/cudawarping/src/cuda/resize.cu:71-106); the per-sample
+// arithmetic is resize_linear_px (vsb_device.cuh).  fx / fy are the factors the host wrapper passes (src/resize.cpp:76-105).
 template <int CN>
 __global__ void k_resize_linear_u8(const uint8_t *__restrict__ src, int sw, int sh, size_t sp, uint8_t *__restrict__ dst, int dw, int dh, size_t dp, float fx, float fy)
 {
     const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y * blockDim.y + threadIdx.y;
     if (dx >= dw || dy >= dh) return;
-    const float sx = __fmul_rn((float)dx, fx), sy = __fmul_rn((float)dy, fy);
-    const int x1 = __float2int_rd(sx), y1 = __float2int_rd(sy), x2 = x1 + 1, y2 = y1 + 1;
-    const int x2r = min(x2, sw - 1), y2r = min(y2, sh - 1);
-    const float w11 = __fmul_rn(__fsub_rn((float)x2, sx), __fsub_rn((float)y2, sy)), w12 = __fmul_rn(__fsub_rn(sx, (float)x1), __fsub_rn((float)y2, sy));
-    const float w21 = __fmul_rn(__fsub_rn((float)x2, sx), __fsub_rn(sy, (float)y1)), w22 = __fmul_rn(__fsub_rn(sx, (float)x1), __fsub_rn(sy, (float)y1));
-#pragma unroll
-    for (int c = 0; c < CN; ++c) {
-        float o = __fmaf_rn((float)src[(size_t)y1 * sp + (size_t)x1 * CN + c], w11, 0.f);
-        o = __fmaf_rn((float)src[(size_t)y1 * sp + (size_t)x2r * CN + c], w12, o);
-        o = __fmaf_rn((float)src[(size_t)y2r * sp + (size_t)x1 * CN + c], w21, o);
-        o = __fmaf_rn((float)src[(size_t)y2r * sp + (size_t)x2r * CN + c], w22, o);
-        dst[(size_t)dy * dp + (size_t)dx * CN + c] = (uint8_t)rni_sat_u8(o);
-    }
+    resize_linear_px<CN>(src, sw, sh, sp, dst, dp, dx, dy, fx, fy);
 }
 
 __global__ void k_and_u8(uint8_t *__restrict__ a, const uint8_t *__restrict__ b, size_t n)
@@ -437,6 +425,40 @@ int vsb_rig_camera(int n_views, int i, int src_w, int src_h, double hfov_deg, fl
     return VSB_OK;
 }
 
+// The camera of vsb_rig_camera after A/calibration.cpp:168-172 (focal, ppx, ppy *= compose_work_aspect, in double; work_scale = 1) and
+// K().convertTo(CV_32F) (:175-176)
+int vsb_rig_camera_scaled(int n_views, int i, int src_w, int src_h, double hfov_deg, double compose_work_aspect, float K[9], float R[9])
+{
+    int r = vsb_rig_camera(n_views, i, src_w, src_h, hfov_deg, K, R);
+    if (r != VSB_OK) return r;
+    if (!(compose_work_aspect > 0)) return vsb::fail(VSB_ERR_INVALID, "rig_camera_scaled: compose_work_aspect must be > 0");
+    const double PI = 3.1415926535897932384626;
+    double ppx = src_w / 2.0, ppy = src_h / 2.0;
+    double focal = (1.0 / std::tan(hfov_deg * PI / 180.0 * 0.5)) * ppx;
+    focal *= compose_work_aspect; ppx *= compose_work_aspect; ppy *= compose_work_aspect;
+    K[0] = (float)focal; K[2] = (float)ppx; K[4] = (float)focal; K[5] = (float)ppy;
+    return VSB_OK;
+}
+
+// The sizes compose_scale implies, exactly as the reference derives them: frame[2] = the frame remap #1 reads -- the caller's
+// full frame, or cvRound(full * scale) when |scale - 1| > 0.1 (A/calibration.cpp:157-161; the same test decides the per-frame
+// cuda::resize, A/timed.cpp:75-77, whose dsize is that cvRound) -- which also sizes the blender (:176-178); map_src[2] = (int)(full *
+// scale), the img_size the maps and the warped masks are ALWAYS built for (:203-204).  For most scales the two agree; where they do
+// not (cvRound != truncation, or a scale within 0.1 of 1) the reference blends views whose maps were built for a slightly
+// different frame, and so does this library.
+int vsb_compose_size(int full_w, int full_h, double compose_scale, int frame[2], int map_src[2], int *resized)
+{
+    if (full_w <= 0 || full_h <= 0 || !(compose_scale > 0) || !frame || !map_src) return vsb::fail(VSB_ERR_INVALID, "compose_size: bad arguments");
+    const bool scaled = std::fabs(compose_scale - 1) > 1e-1;
+    frame[0] = scaled ? (int)std::nearbyint(full_w * compose_scale) : full_w;
+    frame[1] = scaled ? (int)std::nearbyint(full_h * compose_scale) : full_h;
+    map_src[0] = (int)(full_w * compose_scale);
+    map_src[1] = (int)(full_h * compose_scale);
+    if (resized) *resized = scaled ? 1 : 0;
+    if (frame[0] < 2 || frame[1] < 2 || map_src[0] < 2 || map_src[1] < 2) return vsb::fail(VSB_ERR_INVALID, "compose_size: compose_scale %g leaves no frame", compose_scale);
+    return VSB_OK;
+}
+
 int vsb_host_build_maps(int projection, float scale, const float K[9], const float R[9], int tl_x, int tl_y, int w, int h, float *xmap, float *ymap)
 {
     if (!K || !R || !xmap || !ymap || w <= 0 || h <= 0 || !(scale > 0) || (projection != VSB_PROJ_SPHERICAL && projection != VSB_PROJ_CYLINDRICAL))
@@ -452,15 +474,19 @@ int vsb_voronoi_seams(int n, const int *sizes_wh, const int *corners_xy, uint8_t
     return VSB_OK;
 }
 
-int vsb_calibrate_rig(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains)
+static int calibrate_rig_host(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains,
+                              double compose_scale)
 {
     using namespace vsb;
     if (!s || pano_width <= 0 || src_w <= 0 || src_h <= 0) return fail(VSB_ERR_INVALID, "calibrate_rig: bad arguments");
     vsb_config cfg;
     int r = vsb_get_config(s, &cfg);
     if (r != VSB_OK) return r;
+    int frame_sz[2], map_src[2];
+    r = vsb_compose_size(src_w, src_h, compose_scale, frame_sz, map_src, nullptr);
+    if (r != VSB_OK) return r;
     const int n = cfg.num_views;
-    const float scale = (float)(pano_width / (2.0 * 3.1415926535897932384626));  // sphere radius: pano_width px per 2*pi
+    float scale = (float)(pano_width / (2.0 * 3.1415926535897932384626));  // sphere radius: pano_width px per 2*pi
     std::vector<float> K(9 * n), R(9 * n);
     for (int i = 0; i < n; ++i) {
         r = vsb_rig_camera(n, i, src_w, src_h, hfov_deg, &K[9 * i], &R[9 * i]);
@@ -492,22 +518,34 @@ int vsb_calibrate_rig(vsb_stitcher *s, int projection, int pano_width, int src_w
         for (int i = 0; i < n; ++i) ptrs[i] = seam_masks[i].data();
         voronoi(n, seam_sizes.data(), seam_corners.data(), ptrs.data());
     }
-    // ---- compose scale (360_stitcher/calibration.cpp:137-246), compose_scale = 1
-    std::vector<int> corners(2 * n), sizes(2 * n);
+    // ---- compose scale (360_stitcher/calibration.cpp:137-246)
+    const int full_w = src_w, full_h = src_h;
+    if (compose_scale != 1.0) {
+        // warper scale: warped_image_scale * static_cast<float>(compose_work_aspect) (:151); cameras: focal, ppx, ppy *= aspect (:168-172)
+        scale = scale * static_cast<float>(compose_scale);
+        for (int i = 0; i < n; ++i) {
+            r = vsb_rig_camera_scaled(n, i, full_w, full_h, hfov_deg, compose_scale, &K[9 * i], &R[9 * i]);
+            if (r != VSB_OK) return r;
+        }
+    }
+    // corners + the sizes prepare() gets: warpRoi of the frame remap #1 reads (:176-178); maps and masks: img_size (:203-204, vsb_compose_size)
+    std::vector<int> corners(2 * n), sizes(2 * n), map_roi(4 * n);
     for (int i = 0; i < n; ++i) {
         int roi[4];
-        r = vsb_warp_roi(projection, scale, &K[9 * i], &R[9 * i], src_w, src_h, roi);
+        r = vsb_warp_roi(projection, scale, &K[9 * i], &R[9 * i], frame_sz[0], frame_sz[1], roi);
         if (r != VSB_OK) return r;
         corners[2 * i] = roi[0]; corners[2 * i + 1] = roi[1]; sizes[2 * i] = roi[2]; sizes[2 * i + 1] = roi[3];
+        r = vsb_warp_roi(projection, scale, &K[9 * i], &R[9 * i], map_src[0], map_src[1], &map_roi[4 * i]);
+        if (r != VSB_OK) return r;
     }
     r = vsb_prepare(s, corners.data(), sizes.data());
     if (r != VSB_OK) return r;
     for (int i = 0; i < n; ++i) {
-        const int w = sizes[2 * i], h = sizes[2 * i + 1];
+        const int w = map_roi[4 * i + 2], h = map_roi[4 * i + 3];
         std::vector<float> xm((size_t)w * h), ym((size_t)w * h);
-        host_build_maps(projection, scale, &K[9 * i], &R[9 * i], corners[2 * i], corners[2 * i + 1], w, h, xm.data(), ym.data());
+        host_build_maps(projection, scale, &K[9 * i], &R[9 * i], map_roi[4 * i], map_roi[4 * i + 1], w, h, xm.data(), ym.data());
         std::vector<uint8_t> warped((size_t)w * h), seam((size_t)w * h);
-        host_warp_full_mask(xm.data(), ym.data(), w, h, src_w, src_h, warped.data());
+        host_warp_full_mask(xm.data(), ym.data(), w, h, map_src[0], map_src[1], warped.data());
         const int sw = seam_sizes[2 * i], sh = seam_sizes[2 * i + 1];
         std::vector<uint8_t> dil(seam_masks[i].size());
         if (cfg.enable_local) dilate3x3(seam_masks[i].data(), sw, sh, dil.data());
@@ -516,11 +554,18 @@ int vsb_calibrate_rig(vsb_stitcher *s, int projection, int pano_width, int src_w
         for (size_t j = 0; j < seam.size(); ++j) seam[j] &= warped[j];
         r = vsb_init_view(s, i, seam.data(), w, h, (size_t)w, corners[2 * i], corners[2 * i + 1], 0);
         if (r != VSB_OK) return r;
-        r = vsb_set_maps(s, i, xm.data(), ym.data(), w, h, (size_t)w * 4, 0, src_w, src_h);
+        r = vsb_set_maps(s, i, xm.data(), ym.data(), w, h, (size_t)w * 4, 0, frame_sz[0], frame_sz[1]);   // cuda::remap tests against the frame it is given
         if (r != VSB_OK) return r;
         if (gains) { r = vsb_set_gain(s, i, gains[i]); if (r != VSB_OK) return r; }
     }
-    return vsb_note_rig(s, projection, scale, src_w, src_h);
+    r = vsb_set_compose_scale(s, compose_scale, full_w, full_h);
+    if (r != VSB_OK) return r;
+    return vsb_note_rig(s, projection, scale, full_w, full_h);
+}
+
+int vsb_calibrate_rig(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains)
+{
+    return calibrate_rig_host(s, projection, pano_width, src_w, src_h, hfov_deg, gains, 1.0);
 }
 
 // ---- device-side calibration entry points -------------------------------------------------------------------------------------
@@ -559,19 +604,23 @@ int vsb_resize_linear_u8(const uint8_t *d_src, int sw, int sh, size_t src_pitch,
 // reference (RotationWarperBase::detectResultRoi runs on the CPU there too: a walk along the image border).  The device evaluates
 // sinf / cosf itself, so the projection maps agree with the host path to ~1e-3 px, not bit for bit (the reference's own maps come
 // from the same kind of device code); everything downstream of the maps is exact.
-int vsb_calibrate_rig_device(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains)
+static int calibrate_rig_dev(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains,
+                             double compose_scale)
 {
     using namespace vsb;
     if (!s || pano_width <= 0 || src_w <= 0 || src_h <= 0) return fail(VSB_ERR_INVALID, "calibrate_rig_device: bad arguments");
     vsb_config cfg;
     int r = vsb_get_config(s, &cfg);
     if (r != VSB_OK) return r;
+    int frame_sz[2], map_src[2];
+    r = vsb_compose_size(src_w, src_h, compose_scale, frame_sz, map_src, nullptr);
+    if (r != VSB_OK) return r;
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(vsb_handle_device(s));
     struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev};
     const int n = cfg.num_views;
-    const float scale = (float)(pano_width / (2.0 * 3.1415926535897932384626));
+    float scale = (float)(pano_width / (2.0 * 3.1415926535897932384626));
     CalibState *cs = new CalibState();
     cs->n = n; cs->projection = projection; cs->src_w = src_w; cs->src_h = src_h;
     std::vector<float> K(9 * n), R(9 * n);
@@ -619,18 +668,27 @@ int vsb_calibrate_rig_device(vsb_stitcher *s, int projection, int pano_width, in
     }
     r = voronoi_device(n, seam_sizes.data(), seam_corners.data(), seam_masks.data(), st);
     if (r != VSB_OK) { free_seams(); return bail(r); }
-    // ---- compose scale (360_stitcher/calibration.cpp:137-246), compose_scale = 1
-    std::vector<int> corners(2 * n), sizes(2 * n);
+    // ---- compose scale (360_stitcher/calibration.cpp:137-246); the sizes as in calibrate_rig_host
+    const int full_w = src_w, full_h = src_h;
+    if (compose_scale != 1.0) {
+        scale = scale * static_cast<float>(compose_scale);
+        for (int i = 0; i < n; ++i) {
+            r = vsb_rig_camera_scaled(n, i, full_w, full_h, hfov_deg, compose_scale, &K[9 * i], &R[9 * i]);
+            if (r != VSB_OK) { free_seams(); return bail(r); }
+        }
+    }
+    std::vector<int> corners(2 * n), sizes(2 * n), map_roi(4 * n);
     for (int i = 0; i < n; ++i) {
         int roi[4];
-        r = vsb_warp_roi(projection, scale, &K[9 * i], &R[9 * i], src_w, src_h, roi);
+        r = vsb_warp_roi(projection, scale, &K[9 * i], &R[9 * i], frame_sz[0], frame_sz[1], roi);
+        if (r == VSB_OK) r = vsb_warp_roi(projection, scale, &K[9 * i], &R[9 * i], map_src[0], map_src[1], &map_roi[4 * i]);
         if (r != VSB_OK) { free_seams(); return bail(r); }
         corners[2 * i] = roi[0]; corners[2 * i + 1] = roi[1]; sizes[2 * i] = roi[2]; sizes[2 * i + 1] = roi[3];
     }
     r = vsb_prepare(s, corners.data(), sizes.data());
     if (r != VSB_OK) { free_seams(); return bail(r); }
     for (int i = 0; i < n && r == VSB_OK; ++i) {
-        const int w = sizes[2 * i], h = sizes[2 * i + 1], sw = seam_sizes[2 * i], sh = seam_sizes[2 * i + 1];
+        const int w = map_roi[4 * i + 2], h = map_roi[4 * i + 3], sw = seam_sizes[2 * i], sh = seam_sizes[2 * i + 1];
         const size_t mp = ((size_t)w * 4 + 15) / 16 * 16;
         float *xm = nullptr, *ym = nullptr;
         uint8_t *warped = nullptr, *seam = nullptr, *dil = nullptr;
@@ -638,9 +696,9 @@ int vsb_calibrate_rig_device(vsb_stitcher *s, int projection, int pano_width, in
             cudaMalloc(&seam, (size_t)w * h) != cudaSuccess || cudaMalloc(&dil, (size_t)sw * sh) != cudaSuccess)
             r = fail(VSB_ERR_NOMEM, "calibrate_rig_device: out of device memory");
         int roi2[4];
-        if (r == VSB_OK) r = vsb_build_maps(projection, scale, &K[9 * i], &R[9 * i], src_w, src_h, xm, ym, mp, roi2, st);
+        if (r == VSB_OK) r = vsb_build_maps(projection, scale, &K[9 * i], &R[9 * i], map_src[0], map_src[1], xm, ym, mp, roi2, st);
         if (r == VSB_OK) {
-            k_full_mask<<<grid2(w, h, b), b, 0, st>>>(xm, ym, mp, w, h, src_w, src_h, warped);
+            k_full_mask<<<grid2(w, h, b), b, 0, st>>>(xm, ym, mp, w, h, map_src[0], map_src[1], warped);
             const uint8_t *small = seam_masks[i];
             if (cfg.enable_local) { k_dilate3x3<<<grid2(sw, sh, b), b, 0, st>>>(seam_masks[i], sw, sh, dil); small = dil; }
             r = check_launch("mask kernels");
@@ -652,7 +710,7 @@ int vsb_calibrate_rig_device(vsb_stitcher *s, int projection, int pano_width, in
         }
         if (r == VSB_OK) r = check_cuda(cudaStreamSynchronize(st), "calibrate_rig_device");
         if (r == VSB_OK) r = vsb_init_view(s, i, seam, w, h, (size_t)w, corners[2 * i], corners[2 * i + 1], 1);
-        if (r == VSB_OK) r = vsb_set_maps(s, i, xm, ym, w, h, mp, 1, src_w, src_h);
+        if (r == VSB_OK) r = vsb_set_maps(s, i, xm, ym, w, h, mp, 1, frame_sz[0], frame_sz[1]);
         if (r == VSB_OK && gains) r = vsb_set_gain(s, i, gains[i]);
         cudaDeviceSynchronize();
         cudaFree(xm); cudaFree(ym); cudaFree(warped); cudaFree(seam); cudaFree(dil);
@@ -660,7 +718,24 @@ int vsb_calibrate_rig_device(vsb_stitcher *s, int projection, int pano_width, in
     free_seams();
     if (r != VSB_OK) return bail(r);
     vsb_attach_calib(s, cs, calib_state_free);
-    return vsb_note_rig(s, projection, scale, src_w, src_h);
+    r = vsb_set_compose_scale(s, compose_scale, full_w, full_h);
+    if (r != VSB_OK) return r;
+    return vsb_note_rig(s, projection, scale, full_w, full_h);
+}
+
+int vsb_calibrate_rig_device(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains)
+{
+    return calibrate_rig_dev(s, projection, pano_width, src_w, src_h, hfov_deg, gains, 1.0);
+}
+
+// Both calibrations with the reference's compose_scale (A/calibration.cpp:137-205): the cameras and the warper are scaled, the ROIs,
+// maps and masks are built for the scaled frame, and every frame handed to vsb_feed / vsb_compose / vsb_submit_host (still
+// src_w x src_h) goes through cuda::resize(..., Size(), compose_scale, compose_scale, INTER_LINEAR) first (A/timed.cpp:74-81).
+int vsb_calibrate_rig_scaled(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains,
+                             double compose_scale, int on_device)
+{
+    return on_device ? calibrate_rig_dev(s, projection, pano_width, src_w, src_h, hfov_deg, gains, compose_scale)
+                     : calibrate_rig_host(s, projection, pano_width, src_w, src_h, hfov_deg, gains, compose_scale);
 }
 
 // GainCompensator::feed (sources/modules/stitching/src/exposure_compensate.cpp:71-142) on warped images already on the device:

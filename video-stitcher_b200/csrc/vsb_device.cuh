@@ -35,6 +35,27 @@ __device__ __forceinline__ int rz_s16(float v)
 
 __device__ __forceinline__ int sat_s16(int v) { return max(-32768, min(32767, v)); }
 
+// One output sample of cuda::resize INTER_LINEAR on CV_8UC1 / CV_8UC3 (sources/modules/cudawarping/src/cuda/resize.cu:71-106): no
+// half-pixel centre, fp32 weights in the kernel's order, out += src * w (an fma on the device), cvt.rni.sat.u8.
+template <int CN>
+__device__ __forceinline__ void resize_linear_px(const uint8_t *__restrict__ src, int sw, int sh, size_t sp, uint8_t *__restrict__ dst, size_t dp,
+                                                 int dx, int dy, float fx, float fy)
+{
+    const float sx = __fmul_rn((float)dx, fx), sy = __fmul_rn((float)dy, fy);
+    const int x1 = __float2int_rd(sx), y1 = __float2int_rd(sy), x2 = x1 + 1, y2 = y1 + 1;
+    const int x2r = min(x2, sw - 1), y2r = min(y2, sh - 1);
+    const float w11 = __fmul_rn(__fsub_rn((float)x2, sx), __fsub_rn((float)y2, sy)), w12 = __fmul_rn(__fsub_rn(sx, (float)x1), __fsub_rn((float)y2, sy));
+    const float w21 = __fmul_rn(__fsub_rn((float)x2, sx), __fsub_rn(sy, (float)y1)), w22 = __fmul_rn(__fsub_rn(sx, (float)x1), __fsub_rn(sy, (float)y1));
+#pragma unroll
+    for (int c = 0; c < CN; ++c) {
+        float o = __fmaf_rn((float)src[(size_t)y1 * sp + (size_t)x1 * CN + c], w11, 0.f);
+        o = __fmaf_rn((float)src[(size_t)y1 * sp + (size_t)x2r * CN + c], w12, o);
+        o = __fmaf_rn((float)src[(size_t)y2r * sp + (size_t)x1 * CN + c], w21, o);
+        o = __fmaf_rn((float)src[(size_t)y2r * sp + (size_t)x2r * CN + c], w22, o);
+        dst[(size_t)dy * dp + (size_t)dx * CN + c] = (uint8_t)rni_sat_u8(o);
+    }
+}
+
 // round-half-even of v / 2^SH for two's-complement v (exact twin of cvt.rni on the exact fp32 value)
 template <int SH>
 __device__ __forceinline__ int rhe_shift(int v)

@@ -769,6 +769,25 @@ __global__ void __launch_bounds__(RM_BX *RM_BY) k_remap_stage2_tab(const __grid_
 // The capture boards send NV12 and the reference converts every received frame on the CPU with
 // cv::cvtColor(mat, mat, CV_YUV2BGR_NV12) before the upload (360_stitcher/networking.cpp:46, A/defs.h:10-17).  Here the NV12
 // frame is what crosses PCIe (half the bytes) and this kernel restates the integer BT.601 arithmetic of
+// compose_scale != 1: cuda::resize(full_img, img, Size(), compose_scale, compose_scale, INTER_LINEAR) of every camera frame of a
+// submission in one launch (A/timed.cpp:74-77; kernel sources/modules/cudawarping/src/cuda/resize.cu:71-106, arithmetic in
+// resize_linear_px).  blockIdx.z = frame * views + view; entries of views this rank does not own are null and skipped.
+struct PrescaleParams {
+    const uint8_t *src[MAX_BATCH * MAXV];
+    uint8_t *dst[MAX_BATCH * MAXV];
+    size_t pitch, dst_pitch;
+    int sw, sh, dw, dh;
+    float fx, fy;   // static_cast<float>(1.0 / compose_scale), as the host wrapper passes it (src/resize.cpp:104)
+};
+
+__global__ void __launch_bounds__(256) k_prescale(const __grid_constant__ PrescaleParams p)
+{
+    const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y;
+    const uint8_t *src = p.src[blockIdx.z];
+    if (dx >= p.dw || dy >= p.dh || !src) return;
+    resize_linear_px<3>(src, p.sw, p.sh, p.pitch, p.dst[blockIdx.z], p.dst_pitch, dx, dy, p.fx, p.fy);
+}
+
 // YUV420sp2RGB888Invoker<bIdx = 0, uIdx = 0> (sources/modules/imgproc/src/color.cpp:8741-8746, 8793-8818) bit for bit.
 // One thread = 4 pixels x 2 rows (two chroma pairs): three 32-bit loads, six 32-bit stores.
 struct Nv12Params {
@@ -790,6 +809,7 @@ __global__ void __launch_bounds__(256) k_nv12_to_bgr(const __grid_constant__ Nv1
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
     if (x0 >= p.w || y0 >= p.h) return;
     const uint8_t *src = p.src[blockIdx.z];
+    if (!src) return;  // a view another rank owns
     const uint8_t *y1 = src + (size_t)y0 * p.pitch + x0, *uv = src + (size_t)p.h * p.pitch + (size_t)(y0 >> 1) * p.pitch + x0;
     uint8_t *d = p.dst[blockIdx.z] + (size_t)y0 * p.dst_pitch + (size_t)x0 * 3;
     const int n = min(4, p.w - x0);  // w is even: n is 2 or 4
@@ -1286,6 +1306,13 @@ struct vsb_stitcher {
     uint8_t *nv_bgr = nullptr;          // [max_batch][num_views] BGR images, rows nv_pitch bytes apart
     size_t nv_pitch = 0, nv_stride = 0;
     int nv_w = 0, nv_h = 0;
+    // compose_scale != 1 (vsb_set_compose_scale): the caller's full_w x full_h frames go through cuda::resize into cs_buf first
+    bool prescale = false;
+    double compose_scale = 1.0;
+    int full_w = 0, full_h = 0, comp_w = 0, comp_h = 0;
+    uint8_t *cs_buf = nullptr;          // [max_batch][num_views] resized BGR frames, rows cs_pitch bytes apart
+    size_t cs_pitch = 0, cs_stride = 0;
+    int cs_w = 0, cs_h = 0;
     int *cons_tab = nullptr;            // consumer resize tables for (cons_w x cons_ih): xofs | yofs | ia | ib
     int cons_w = 0, cons_ih = 0;
     uint8_t *stage_nv12[vsb::HOST_DEPTH] = {};  // host path: device copy of the caller's NV12 frames
@@ -1960,13 +1987,50 @@ static int remap_variant()
     return v;
 }
 
+// size of the frames the caller hands in for view i: the size the maps address, or the full size when the frames are resized first
+static inline int frame_w(const vsb_stitcher *s, int i) { return s->prescale ? s->full_w : s->v[i].src_w; }
+static inline int frame_h(const vsb_stitcher *s, int i) { return s->prescale ? s->full_h : s->v[i].src_h; }
+
+// compose_scale != 1: resizes the caller's (or the NV12 stage's) BGR frames of views [v0, v1) into cs_buf and returns pointers to it
+static int launch_prescale(vsb_stitcher *s, int v0, int v1, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch, cudaStream_t st,
+                           const uint8_t **out_ptrs)
+{
+    const int n = v1 - v0, nv = s->cfg.num_views;
+    for (int i = v0; i < v1; ++i)
+        REQ(s->v[i].src_w == s->comp_w && s->v[i].src_h == s->comp_h, VSB_ERR_STATE,
+            "compose_scale: the maps of view %d address %dx%d frames, the scaled frame is %dx%d", i, s->v[i].src_w, s->v[i].src_h, s->comp_w, s->comp_h);
+    REQ(src_pitch >= (size_t)s->full_w * 3, VSB_ERR_INVALID, "compose_scale: pitch is smaller than a row of the %d-pixel-wide full frame", s->full_w);
+    if (!s->cs_buf || s->cs_w != s->comp_w || s->cs_h != s->comp_h) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(s->cs_buf); s->cs_buf = nullptr;
+        s->cs_pitch = align_up((size_t)s->comp_w * 3, 16);
+        s->cs_stride = align_up(s->cs_pitch * s->comp_h + 16, 256);
+        CK(cudaMalloc(&s->cs_buf, s->cs_stride * nv * s->cfg.max_batch));
+        s->cs_w = s->comp_w; s->cs_h = s->comp_h;
+    }
+    PrescaleParams p;
+    std::memset(&p, 0, sizeof(p));
+    for (int f = 0; f < n_frames; ++f)
+        for (int j = 0; j < n; ++j) {
+            p.src[f * n + j] = d_srcs[f * n + j];
+            p.dst[f * n + j] = s->cs_buf + s->cs_stride * ((size_t)(s->f0 + f) * nv + v0 + j);
+            out_ptrs[f * n + j] = p.dst[f * n + j];
+        }
+    p.pitch = src_pitch; p.dst_pitch = s->cs_pitch; p.sw = s->full_w; p.sh = s->full_h; p.dw = s->comp_w; p.dh = s->comp_h;
+    p.fx = p.fy = static_cast<float>(1.0 / s->compose_scale);
+    k_prescale<<<dim3((s->comp_w + 31) / 32, (s->comp_h + 7) / 8, n * n_frames), dim3(32, 8), 0, st>>>(p);
+    ++s->launches;
+    prof_stage(s, st, "prescale", 3.0 * ((double)s->full_w * s->full_h + (double)s->comp_w * s->comp_h) * n * n_frames);  // full frame in once, scaled frame out once
+    return check_launch("k_prescale");
+}
+
 // NV12 input: converts the caller's frames of views [v0, v1) into the handle's BGR staging and returns pointers to it
 static int launch_nv12(vsb_stitcher *s, int v0, int v1, int n_frames, const uint8_t *const *d_srcs, size_t src_pitch, cudaStream_t st,
                        const uint8_t **bgr_ptrs)
 {
     const int n = v1 - v0, nv = s->cfg.num_views;
-    const int w = s->v[v0].src_w, h = s->v[v0].src_h;
-    for (int i = v0; i < v1; ++i) REQ(s->v[i].src_w == w && s->v[i].src_h == h, VSB_ERR_INVALID, "NV12 input: all views must share one source size");
+    const int w = frame_w(s, v0), h = frame_h(s, v0);
+    for (int i = v0; i < v1; ++i) REQ(frame_w(s, i) == w && frame_h(s, i) == h, VSB_ERR_INVALID, "NV12 input: all views must share one source size");
     REQ((w & 1) == 0 && (h & 1) == 0, VSB_ERR_INVALID, "NV12 input: source width and height must be even (got %dx%d)", w, h);
     REQ(src_pitch >= (size_t)w, VSB_ERR_INVALID, "NV12 input: pitch is the Y-plane row pitch and must be >= width");
     if (!s->nv_bgr || s->nv_w != w || s->nv_h != h) {
@@ -2040,10 +2104,15 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
     int ws[MAXV], hs[MAXV];
     int r = sync_tile_lists(s);
     if (r != VSB_OK) return r;
-    const uint8_t *bgr_ptrs[MAX_BATCH * MAXV];
+    const uint8_t *bgr_ptrs[MAX_BATCH * MAXV], *cs_ptrs[MAX_BATCH * MAXV];
     bool nv12_fused = false;
     if (!(stages & FRONT_REMAP)) goto pyramid;
-    if (!warped && s->in_format == VSB_IN_NV12) {
+    if (!warped && s->in_format == VSB_IN_NV12 && s->prescale) {
+        // the resize reads BGR: convert at full size first (the reference's capture thread does, A/networking.cpp:46), then resize
+        r = launch_nv12(s, v0, v1, n_frames, d_srcs, src_pitch, st, bgr_ptrs);
+        if (r != VSB_OK) return r;
+        d_srcs = bgr_ptrs; src_pitch = s->nv_pitch;
+    } else if (!warped && s->in_format == VSB_IN_NV12) {
         // fused form: remap #1 converts its taps itself (k_remap_stage1_nv12), no BGR staging image.  Needs 2-byte aligned frames
         // and an even pitch (16-bit chroma loads), 31-bit offsets, and tables free of weights its scaled chain cannot take.
         static const bool want = [] { const char *e = std::getenv("VSB_NV12_FUSED"); return !e || std::atoi(e) != 0; }();
@@ -2062,6 +2131,11 @@ static int launch_front(vsb_stitcher *s, int v0, int v1, int n_frames, const uin
             if (r != VSB_OK) return r;
             d_srcs = bgr_ptrs; src_pitch = s->nv_pitch;
         }
+    }
+    if (!warped && s->prescale) {
+        r = launch_prescale(s, v0, v1, n_frames, d_srcs, src_pitch, st, cs_ptrs);
+        if (r != VSB_OK) return r;
+        d_srcs = cs_ptrs; src_pitch = s->cs_pitch;
     }
     if (!warped && nv12_fused) {
         int first = 0, count = 0;
@@ -2371,7 +2445,7 @@ int vsb_destroy(vsb_stitcher *s)
     cudaFree(s->d_coarse_desc); cudaFree(s->d_s1_tiles); cudaFree(s->d_s2_tiles); cudaFree(s->d_blend_lists);
     cudaFree(s->d_s1s_ids); cudaFree(s->d_s1s_tiles);
     for (int i = 0; i < MAXV; ++i) { cudaFree(s->d_send[i]); cudaFree(s->d_recv[i]); }
-    cudaFree(s->nv_bgr); cudaFree(s->cons_tab);
+    cudaFree(s->nv_bgr); cudaFree(s->cs_buf); cudaFree(s->cons_tab);
     for (int d = 0; d < HOST_DEPTH; ++d) { cudaFree(s->stage_src[d]); cudaFree(s->stage_out[d]); cudaFree(s->stage_nv12[d]); if (s->ev_host[d]) cudaEventDestroy(s->ev_host[d]); }
     for (int b = 0; b < 2; ++b)
         for (int p = 0; p < MAXV; ++p) { cudaFree(s->x_send[b][p]); cudaFree(s->x_recv[b][p]); }
@@ -2427,6 +2501,7 @@ int vsb_prepare(vsb_stitcher *s, const int *corners_xy, const int *sizes_wh)
     }
     s->stage_src_w = s->stage_src_h = 0; s->host_pending = 0;
     s->cons_w = s->cons_ih = 0;  // the consumer's resize tables depend on the panorama size
+    s->prescale = false; s->compose_scale = 1.0;  // a new geometry starts at compose_scale 1 (vsb_set_compose_scale after the maps)
     s->views_inited = 0; s->prepared = true; s->finalized = false;
     return VSB_OK;
 }
@@ -2922,8 +2997,8 @@ int vsb_submit_host(vsb_stitcher *s, int n_frames, const uint8_t *const *h_srcs,
     if (r != VSB_OK) return r;
     DeviceGuard g(s->device);
     const int n = s->cfg.num_views;
-    const int sw = s->v[0].src_w, sh = s->v[0].src_h;
-    for (int i = 1; i < n; ++i) REQ(s->v[i].src_w == sw && s->v[i].src_h == sh, VSB_ERR_INVALID, "submit_host: all views must share one source size");
+    const int sw = frame_w(s, 0), sh = frame_h(s, 0);  // (the full-size frame when compose_scale != 1)
+    for (int i = 1; i < n; ++i) REQ(frame_w(s, i) == sw && frame_h(s, i) == sh, VSB_ERR_INVALID, "submit_host: all views must share one source size");
     const bool nv12 = s->in_format == VSB_IN_NV12;
     const size_t opx = s->out_format == VSB_OUT_U8C3 ? 3 : 6;     // bytes per output pixel
     const size_t src_row = nv12 ? (size_t)sw : (size_t)sw * 3;    // bytes per source row, rows per source frame
@@ -3423,6 +3498,22 @@ int vsb_get_config(const vsb_stitcher *s, vsb_config *out)
 {
     REQ(s && out, VSB_ERR_INVALID, "get_config: null argument");
     *out = s->cfg;
+    return VSB_OK;
+}
+
+// compose_scale of the reference (A/timed.cpp:74-81, A/calibration.cpp:137-205).  The maps installed with vsb_set_maps address the
+// SCALED frame; the frames handed to vsb_feed / vsb_compose / vsb_submit_host are full_w x full_h and are resized on the device
+// first -- when |compose_scale - 1| > 0.1, the reference's own condition; otherwise the stage is off.  Takes effect with the next submission.
+int vsb_set_compose_scale(vsb_stitcher *s, double compose_scale, int full_w, int full_h)
+{
+    REQ(s, VSB_ERR_INVALID, "set_compose_scale: null handle");
+    if (compose_scale == 1.0) { s->prescale = false; s->compose_scale = 1.0; return VSB_OK; }
+    int frame[2], map_src[2], resized = 0;
+    int r = vsb_compose_size(full_w, full_h, compose_scale, frame, map_src, &resized);
+    if (r != VSB_OK) return r;
+    s->compose_scale = compose_scale;
+    s->prescale = resized != 0;   // within 0.1 of 1 the reference scales its cameras, not its frames (A/timed.cpp:75)
+    s->full_w = full_w; s->full_h = full_h; s->comp_w = frame[0]; s->comp_h = frame[1];
     return VSB_OK;
 }
 
