@@ -144,6 +144,20 @@ int vsb_rig_camera_scaled(int n_views, int i, int src_w, int src_h, double hfov_
 int vsb_set_compose_scale(vsb_stitcher *s, double compose_scale, int full_w, int full_h);
 int vsb_calibrate_rig_scaled(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg,
                              const float *gains, double compose_scale, int on_device);
+/* ---- modular wrap-around ROI (wrapAround, A/defs.h:25; A/meshwarper.cpp:93-102,620-626).  A camera that looks across +-pi gets
+ *      the reference's full-panorama-width ROI (RotationWarperBase::detectResultRoi): two image parts at the two ends of one
+ *      image, zeros between them -- four times the memory of its neighbours at 6 cameras, eight times at 12.  The split
+ *      calibration installs such a camera as TWO views, column windows of its warped image (margins and origins chosen so that
+ *      every pyramid level equals the full-width view's wherever a weight is non-zero: the panorama is the same bit for bit),
+ *      so no buffer is ever panorama-wide.  vsb_split_plan (host only) tells how many views a rig needs -- create the handle with
+ *      that num_views -- and which camera / columns each view shows; vsb_calibrate_rig_split is vsb_calibrate_rig for it (gains per
+ *      CAMERA).  Per frame the caller passes, for every VIEW, the frame of its camera (vsb_view_window); vsb_set_mesh on a window
+ *      view takes the camera's mesh.  Meshes must not move image content across the zero margin (3 * 2^num_bands + 8 px). ------ */
+int vsb_split_plan(int projection, int pano_width, int n_cameras, int src_w, int src_h, double hfov_deg, int num_bands, int *n_views,
+                   int *view_camera, int *view_x0, int *view_w);
+int vsb_calibrate_rig_split(vsb_stitcher *s, int projection, int pano_width, int n_cameras, int src_w, int src_h, double hfov_deg,
+                            const float *gains);
+int vsb_view_window(const vsb_stitcher *s, int view, int *camera, int *x0, int *full_w);
 int vsb_rig_info_get(const vsb_stitcher *s, vsb_rig_info *out);
 int vsb_get_config(const vsb_stitcher *s, vsb_config *out);
 

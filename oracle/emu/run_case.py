@@ -33,31 +33,37 @@ def main():
     F = int(case.get("frames", 1))
     gains = S.gains(n)
     t0 = time.time()
-    st = B.Stitcher(n, nb, True, F)
+    split = bool(case.get("split"))                        # cameras that wrap around +-pi become two views (vsb_calibrate_rig_split)
+    plan = B.split_plan(0, pano, n, sw, sh, nb) if split else [(i, 0, 0) for i in range(n)]
+    nv = len(plan)
+    st = B.Stitcher(nv, nb, True, F)
     cs = float(case.get("compose_scale", 1.0))             # != 1: sw x sh are the full frames, resized on the device in front of remap #1
-    if cs != 1.0:
+    if split:
+        st.calibrate_rig_split(0, pano, n, sw, sh, 90.0, gains)
+    elif cs != 1.0:
         st.calibrate_rig_scaled(0, pano, sw, sh, cs, 90.0, gains, on_device=bool(case.get("device_calibration")))
     elif case.get("device_calibration"):                   # every per-pixel loop of the calibration as kernels (maps differ from libm's by ulps)
         st.calibrate_rig_device(0, pano, sw, sh, 90.0, gains)
     else:
         st.calibrate_rig(0, pano, sw, sh, 90.0, gains)      # the product's host calibration + its weight / plan kernels
     info = st.rig_info()
-    for i in range(n):
-        mx, my = S.mesh(info.view_roi[i][2], info.view_roi[i][3])
-        st.set_mesh(i, mx.ctypes.data, my.ctypes.data, mx.shape[0], mx.shape[1])
+    win = [st.view_window(k) for k in range(nv)]            # (camera, x0, width of the camera's warped image) per view
+    for k in range(nv):
+        mx, my = S.mesh(win[k][2], info.view_roi[k][3])     # the mesh of the view's CAMERA
+        st.set_mesh(k, mx.ctypes.data, my.ctypes.data, mx.shape[0], mx.shape[1])
     t_cal = time.time() - t0
     roi, _, _ = st.get_roi()
     W, H = roi[2], roi[3]
     wire = bool(case.get("wire"))       # NV12 frames in (converted inside remap #1's tap fetch), CV_8UC3 panoramas out
     if wire:
         st.set_formats(B.IN_NV12, B.OUT_U8C3)
-        nv = [[S.frame_nv12(i, f, sw, sh) for i in range(n)] for f in range(F)]
-        frames = [[og.nv12_to_bgr(a, sw, sh) for a in fr] for fr in nv]
-        bufs = [E.Buffer(a) for fr in nv for a in fr]
+        nvf = [[S.frame_nv12(i, f, sw, sh) for i in range(n)] for f in range(F)]
+        frames = [[og.nv12_to_bgr(a, sw, sh) for a in fr] for fr in nvf]
+        bufs = [E.Buffer(fr[win[k][0]]) for fr in nvf for k in range(nv)]
         outs = [E.Buffer(np.full((H, W, 3), 0xAB, np.uint8)) for _ in range(F)]
     else:
         frames = [[S.frame(i, f, sw, sh) for i in range(n)] for f in range(F)]
-        bufs = [E.Buffer(a) for fr in frames for a in fr]
+        bufs = [E.Buffer(fr[win[k][0]]) for fr in frames for k in range(nv)]
         outs = [E.Buffer(np.full((H, W, 3), -12345, np.int16)) for _ in range(F)]
     n0 = len(E.stats()["launches"])
     t0 = time.time()
@@ -75,14 +81,18 @@ def main():
         return a
 
     res = collections.OrderedDict(error=E.stats().get("error"), roi_equal=bool(tuple(roi) == tuple(orig.roi_final)), mesh_maps=0, warped=0, gauss0=0, gauss2=0)
-    for i in range(n):
+    for i in range(nv):                                        # view i = columns [x0, x0 + w) of camera c's warped image
         w, h = info.view_roi[i][2], info.view_roi[i][3]
+        c, x0, _ = win[i]
         g = st.view_geometry(i)
         bw, bh = g["x_br"] - g["x_tl"], g["y_br"] - g["y_tl"]
-        res["mesh_maps"] += int(np.count_nonzero(read(4, i, 0, (h, w), np.float32).view(np.uint32) != orig.mesh_maps[i][0].view(np.uint32)))
-        res["mesh_maps"] += int(np.count_nonzero(read(5, i, 0, (h, w), np.float32).view(np.uint32) != orig.mesh_maps[i][1].view(np.uint32)))
+        omx = np.ascontiguousarray(orig.mesh_maps[c][0][:, x0:x0 + w] - np.float32(x0))   # (x - x0 in binary32, as the window kernel re-bases it)
+        omy = np.ascontiguousarray(orig.mesh_maps[c][1][:, x0:x0 + w])
+        gmx, gmy = read(4, i, 0, (h, w), np.float32), read(5, i, 0, (h, w), np.float32)
+        res["mesh_maps"] += int(np.count_nonzero((gmx.view(np.uint32) != omx.view(np.uint32)) & ~(np.isnan(gmx) & np.isnan(omx))))
+        res["mesh_maps"] += int(np.count_nonzero((gmy.view(np.uint32) != omy.view(np.uint32)) & ~(np.isnan(gmy) & np.isnan(omy))))
         done0 = read(7, i, 0, (bh, bw), np.uint8).astype(bool)
-        ov = orig.warp_view(i, frames[0][i])
+        ov = np.ascontiguousarray(orig.warp_view(c, frames[0][c])[:, x0:x0 + w])
         crop = done0[g["top"]:g["top"] + h, g["left"]:g["left"] + w]
         res["warped"] += int(np.count_nonzero(read(0, i, 0, (h, w, 3), np.uint8)[crop] != ov[crop]))
         gk = og.border_reflect_u8c3_to_s16(ov, g["top"], g["bottom"], g["left"], g["right"])
@@ -99,6 +109,7 @@ def main():
     res["pano_samples"] = int(F * H * W * 3)
     res["pano_nonzero"] = int(np.count_nonzero(outs[0].a))
     res["launched"] = [k.split("vsb")[-1][:28] for k in launched]
+    res["views"] = [list(p) for p in plan] if split else nv
     res["launch_count"] = st.last_launch_count()
     res["calibration_launches"] = n0
     res["seconds"] = {"calibrate_and_mesh": round(t_cal, 1), "compose": round(t_compose, 1)}

@@ -118,3 +118,32 @@ class GpuRig:
     def mesh_map(self, i, which):
         w, h = self.sizes[i]
         return self.read(4 + which, i, 0, (h, w), np.float32)
+
+
+class GpuSplitRig(GpuRig):
+    """vsb_calibrate_rig_split: cameras that wrap around +-pi are installed as two views (column windows of their warped image).
+    The interface stays per CAMERA: frames and meshes are given per camera and handed to every view of that camera."""
+
+    def __init__(self, n_views, src_w, src_h, pano_width, projection=0, num_bands=5, enable_local=True, gains=None, max_batch=1):
+        self.n_cameras, self.src_w, self.src_h = n_views, src_w, src_h
+        self.plan = B.split_plan(projection, pano_width, n_views, src_w, src_h, num_bands)
+        self.n = len(self.plan)
+        self.st = B.Stitcher(self.n, num_bands, enable_local, max_batch)
+        self.st.calibrate_rig_split(projection, pano_width, n_views, src_w, src_h, 90.0, gains)
+        self.roi_final, self.roi_padded, self.num_bands = self.st.get_roi()
+        self.geom = [self.st.view_geometry(k) for k in range(self.n)]
+        info = self.st.rig_info()
+        self.sizes = [(info.view_roi[k][2], info.view_roi[k][3]) for k in range(self.n)]
+        self.corners = [(info.view_roi[k][0], info.view_roi[k][1]) for k in range(self.n)]
+        self.win = [self.st.view_window(k) for k in range(self.n)]   # (camera, x0, width of the camera's warped image)
+
+    def set_camera_mesh(self, cam, mx, my):
+        for k in range(self.n):
+            if self.win[k][0] == cam:
+                self.set_mesh(k, mx, my)
+
+    def per_view(self, per_camera):
+        return [per_camera[self.win[k][0]] for k in range(self.n)]
+
+    def compose(self, frames_per_frame):
+        return super().compose([self.per_view(fr) for fr in frames_per_frame])

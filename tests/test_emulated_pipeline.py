@@ -18,17 +18,51 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(case):
+DEFAULT_CASES = {   # interpreted in parallel (one process each, ~70 s): started together by the first test that needs one
+    "base": dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3),
+    "compose_scale": dict(n_views=4, src_w=61, src_h=41, pano_width=192, num_bands=3, compose_scale=0.8),
+    "split": dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3, split=True),
+}
+_procs = {}
+
+
+def _spawn(case):
+    env = {k: v for k, v in os.environ.items() if k != "VSB200_LIB"}
+    return subprocess.Popen([sys.executable, "-m", "oracle.emu.run_case", json.dumps(case)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, env=env)
+
+
+def _collect(p):
+    try:
+        out, err = p.communicate(timeout=1500)
+    except subprocess.TimeoutExpired:
+        p.kill()
+        raise
+    assert p.returncode == 0, err[-3000:]
+    return json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+
+
+def _need_nvcc():
     if not (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
         pytest.skip("nvcc not found (the emulation needs the product's PTX)")
-    env = {k: v for k, v in os.environ.items() if k != "VSB200_LIB"}
-    r = subprocess.run([sys.executable, "-m", "oracle.emu.run_case", json.dumps(case)], capture_output=True, text=True, timeout=1500, cwd=ROOT, env=env)
-    assert r.returncode == 0, r.stderr[-3000:]
-    return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+
+
+def _run(case):
+    _need_nvcc()
+    return _collect(_spawn(case))
+
+
+def _default(name):
+    _need_nvcc()
+    if not _procs:
+        # build the emulation library once, before the processes race for it
+        subprocess.run([sys.executable, "-c", "from oracle.emu import runtime as E; E.start()"], cwd=ROOT, check=True, capture_output=True, timeout=900)
+        for k, case in DEFAULT_CASES.items():
+            _procs[k] = _spawn(case)
+    return _collect(_procs[name])
 
 
 def test_product_library_end_to_end_on_the_emulated_runtime():
-    res = _run(dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3))
+    res = _default("base")
     assert res["error"] is None, res["error"]
     assert res["roi_equal"]
     assert res["mesh_maps"] == 0, "vsb_set_mesh kernels vs oracle mesh -> map"
@@ -60,8 +94,22 @@ def test_product_library_compose_scale_on_the_emulated_runtime():
     """compose_scale != 1 (A/calibration.cpp:137-205, A/timed.cpp:74-81) through the shipped library: vsb_calibrate_rig_scaled (scaled
     cameras and warper, blender sized from cvRound(full * scale) = (49, 33), maps and masks built for (int)(full * scale) = (48, 32) --
     the reference's own mismatch, reproduced) and the per-frame cuda::resize in front of remap #1 (k_prescale), bit-identical to oracle-G."""
-    res = _run(dict(n_views=4, src_w=61, src_h=41, pano_width=192, num_bands=3, compose_scale=0.8))
+    res = _default("compose_scale")
     assert res["error"] is None and res["roi_equal"], res
     assert res["mesh_maps"] == 0 and res["warped"] == 0 and res["gauss0"] == 0 and res["gauss2"] == 0, res
     assert res["pano"] == 0 and res["pano_nonzero"] > res["pano_samples"] // 2, res
     assert "k_prescale" in " ".join(res["launched"]), res["launched"]
+
+
+def test_product_library_split_calibration_on_the_emulated_runtime():
+    """Modular wrap-around ROI (wrapAround, A/defs.h:25): vsb_calibrate_rig_split installs the camera that looks across +-pi as two
+    views -- column windows of its warped image, with the margin and origin rules of tests/test_oracle_wrap_split.py -- so no buffer
+    is panorama-wide; vsb_set_mesh on a window view takes the camera's mesh (k_mesh_upsample_win).  The panorama the shipped library
+    composes from the five views equals the UNSPLIT oracle's four-view panorama bit for bit; the per-view intermediates equal the
+    corresponding columns of the full-width view's."""
+    res = _default("split")
+    assert res["error"] is None and res["roi_equal"], res
+    assert len(res["views"]) == 5 and [v[0] for v in res["views"]] == [0, 1, 2, 2, 3], res["views"]
+    assert max(v[2] for v in res["views"]) < 192 // 2, res["views"]
+    assert res["mesh_maps"] == 0 and res["warped"] == 0 and res["gauss0"] == 0 and res["gauss2"] == 0, res
+    assert res["pano"] == 0 and res["pano_nonzero"] > res["pano_samples"] // 2, res

@@ -6,6 +6,8 @@ zero-extended by a margin of 3 * 2^num_bands (the REFLECT gap), the right part's
 the same panorama bit for bit,
 because Gaussian, Laplacian and weight levels of the sub-views equal the full-width view's wherever a weight is non-zero.
 (The product still allocates the full-width ROI and skips its empty tiles; this test pins the conditions a split has to meet.)"""
+import os
+
 import numpy as np
 import pytest
 
@@ -74,3 +76,46 @@ def test_wrapped_view_split_into_two_sub_views(rig_kw, nb, margin_units, exact):
         # cut at the content edge itself, the REFLECT border of the inner edge mirrors image content where the full-width view has
         # zeros: the split is NOT exact then (which makes the margin rule part of the design, not an implementation detail)
         assert not same
+
+
+FULL_SIZE = [((12, 3840, 2160, 15360), 5, 0)] if os.environ.get("VSB_ORACLE_FULL") else []   # config 4: 40 s on 16 threads, exact (opt-in)
+
+
+@pytest.mark.parametrize("rig_kw,nb,proj", [(RIG6, 5, 0), (RIG4, 3, 0), ((5, 256, 192, 800), 4, 1), ((2, 640, 360, 2011), 5, 0),
+                                            ((6, 1920, 1080, 3840), 5, 0)] + FULL_SIZE)   # the last one: BASELINE config 2 at full size
+def test_product_split_plan_is_exact_on_the_oracle(rig_kw, nb, proj):
+    """The plan the PRODUCT makes (vsb_split_plan, host code of vsb_calibrate_rig_split: which cameras to split, where to cut, the
+    margin, the origin of the right part) fed to the oracle's blender as crops of the full-width views: same panorama, bit for bit.
+    (The shipped library runs the same plan end to end in tests/test_emulated_pipeline.py and tests/test_gpu_vsb_wrap_split.py.)"""
+    og.build()
+    S, B = vsb200.synth, vsb200.binding
+    n, sw, sh, pano = rig_kw
+    rig = op.OracleRig(n, sw, sh, pano, projection=proj, num_bands=nb, enable_local=True, gains=S.gains(n))
+    plan = B.split_plan(proj, pano, n, sw, sh, nb)
+    assert len(plan) > n, "at least one camera of these rigs wraps"
+    W_pano = rig.roi_final[2]
+    for c, x0, w in plan:
+        assert x0 % (1 << rig.num_bands) == 0 and 0 < w <= rig.sizes[c][0] and x0 + w <= rig.sizes[c][0]
+        assert w <= W_pano // 2 + 2 or rig.sizes[c][0] < W_pano - 1, "no view of a split camera is panorama-wide any more"
+    for i in range(n):
+        rig.set_mesh(i, *S.mesh(*rig.sizes[i]))
+    frames = [S.frame(i, 0, sw, sh) for i in range(n)]
+    warped = [rig.warp_view(i, frames[i]) for i in range(n)]
+    for i in range(n):
+        rig.blender.feed_online(i, warped[i])
+    want, want_mask = rig.blender.blend()
+    b = og.Blender(nb)
+    b.prepare([(rig.corners[c][0] + x0, rig.corners[c][1]) for c, x0, w in plan], [(w, rig.sizes[c][1]) for c, x0, w in plan])
+    assert b.dst_roi() == rig.blender.dst_roi()
+    for c, x0, w in plan:
+        b.init_view(np.ascontiguousarray(rig.masks[c][:, x0:x0 + w]), (rig.corners[c][0] + x0, rig.corners[c][1]))
+    for k, (c, x0, w) in enumerate(plan):
+        # what the product's remap #2 makes of the window: the mesh map re-based to the window, reading the window of P (zeros outside)
+        p = og.gain_u8(og.remap_linear_u8(frames[c], rig.xmaps[c][:, x0:x0 + w], rig.ymaps[c][:, x0:x0 + w]), np.float32(rig.gains[c]))
+        mx = np.ascontiguousarray(rig.mesh_maps[c][0][:, x0:x0 + w] - np.float32(x0))
+        my = np.ascontiguousarray(rig.mesh_maps[c][1][:, x0:x0 + w])
+        q = og.remap_linear_u8(p, mx, my)
+        assert np.array_equal(q, warped[c][:, x0:x0 + w]), f"view {k}: remap #2 on the window"
+        b.feed_online(k, q)
+    got, got_mask = b.blend()
+    assert np.array_equal(got, want) and np.array_equal(got_mask, want_mask), int(np.count_nonzero(got != want))

@@ -31,6 +31,7 @@ SYMBOLS = [
     "vsb_gain_compensator_feed", "vsb_shard_unique_id", "vsb_shard_init", "vsb_shard_compose", "vsb_shard_exchange_bytes",
     "vsb_shard_plan", "vsb_shard_peer_bytes", "vsb_shard_pack", "vsb_shard_unpack", "vsb_feed_batch", "vsb_blend_batch",
     "vsb_compose_size", "vsb_rig_camera_scaled", "vsb_set_compose_scale", "vsb_calibrate_rig_scaled",
+    "vsb_split_plan", "vsb_calibrate_rig_split", "vsb_view_window",
 ]
 CONSUME_RGB, CONSUME_I420 = 0, 1
 IN_BGR8, IN_NV12 = 0, 1
@@ -93,6 +94,14 @@ def shard_unique_id():
     buf = (C.c_char * 128)()
     check(lib().vsb_shard_unique_id(buf))
     return bytes(buf.raw)
+
+
+def split_plan(projection, pano_width, n_cameras, src_w, src_h, num_bands, hfov_deg=90.0):
+    """-> [(camera, x0, width)] per view of the split calibration (cameras that wrap around +-pi become two views)"""
+    n = C.c_int()
+    cam, x0, w = (C.c_int * MAX_VIEWS)(), (C.c_int * MAX_VIEWS)(), (C.c_int * MAX_VIEWS)()
+    check(lib().vsb_split_plan(projection, pano_width, n_cameras, src_w, src_h, C.c_double(hfov_deg), num_bands, C.byref(n), cam, x0, w))
+    return [(cam[k], x0[k], w[k]) for k in range(n.value)]
 
 
 def compose_size(full_w, full_h, compose_scale):
@@ -183,6 +192,18 @@ class Stitcher:
             g = (C.c_float * self.num_views)(*[float(v) for v in gains])
         check(lib().vsb_calibrate_rig_scaled(self._h, projection, pano_width, src_w, src_h, C.c_double(hfov_deg), g, C.c_double(compose_scale),
                                              int(bool(on_device))))
+
+    def calibrate_rig_split(self, projection, pano_width, n_cameras, src_w, src_h, hfov_deg=90.0, gains=None):
+        g = None
+        if gains is not None:
+            g = (C.c_float * n_cameras)(*[float(v) for v in gains])
+        check(lib().vsb_calibrate_rig_split(self._h, projection, pano_width, n_cameras, src_w, src_h, C.c_double(hfov_deg), g))
+
+    def view_window(self, view):
+        """-> (camera, x0, full width of the camera's warped image)"""
+        cam, x0, fw = C.c_int(), C.c_int(), C.c_int()
+        check(lib().vsb_view_window(self._h, view, C.byref(cam), C.byref(x0), C.byref(fw)))
+        return cam.value, x0.value, fw.value
 
     def set_compose_scale(self, compose_scale, full_w, full_h):
         check(lib().vsb_set_compose_scale(self._h, C.c_double(compose_scale), full_w, full_h))

@@ -402,6 +402,55 @@ static int voronoi_device(int n, const int *sizes, const int *corners, uint8_t *
     return rc;
 }
 
+// ---- modular wrap-around ROI (wrapAround, 360_stitcher/defs.h:25; SURVEY.md section 7: "never allocate the full-width ROI") --------
+// A camera that looks across +-pi gets the reference's full-panorama-width ROI: its two parts sit at the two ends of one image
+// with zeros between them.  plan_parts replaces such a camera by TWO views -- the column ranges [0, a + m) and [b - m rounded down to a
+// multiple of 2^num_bands, w), where [a, b) is the widest run of columns no projection-map entry fills from the camera image and
+// m = 3 * 2^num_bands + 8 (the REFLECT gap of init_gpu, sources/modules/stitching/src/blenders.cpp:355, plus the reach of the mesh
+// remap).  With that margin and that origin the Gaussian, Laplacian and weight levels of the parts equal the full-width view's
+// wherever a weight is non-zero, so the panorama is the same bit for bit (a cut AT the content edge is not
+// exact).  A camera whose empty run is shorter than 4 m stays one view.
+struct ViewPart { int cam, x0, x1; };
+
+static int plan_parts(int projection, float scale, const float *K, const float *R, int n, int src_w, int src_h, int num_bands_cfg,
+                      const int *corners, const int *sizes, std::vector<ViewPart> &parts)
+{
+    int tlx = INT_MAX, tly = INT_MAX, brx = INT_MIN, bry = INT_MIN;
+    for (int i = 0; i < n; ++i) {
+        tlx = std::min(tlx, corners[2 * i]); tly = std::min(tly, corners[2 * i + 1]);
+        brx = std::max(brx, corners[2 * i] + sizes[2 * i]); bry = std::max(bry, corners[2 * i + 1] + sizes[2 * i + 1]);
+    }
+    const int W = brx - tlx, H = bry - tly;
+    // MultiBandBlender::prepare (sources/modules/stitching/src/blenders.cpp:237-247): bands limited by the panorama size
+    const int nb = std::min(num_bands_cfg, (int)std::ceil(std::log((double)std::max(W, H)) / std::log(2.0)));
+    const int unit = 1 << nb, m = 3 * unit + 8;
+    parts.clear();
+    for (int i = 0; i < n; ++i) {
+        const int w = sizes[2 * i], h = sizes[2 * i + 1];
+        if (w < W - 1) { parts.push_back({i, 0, w}); continue; }
+        std::vector<float> xm((size_t)w * h), ym((size_t)w * h);
+        host_build_maps(projection, scale, K + 9 * i, R + 9 * i, corners[2 * i], corners[2 * i + 1], w, h, xm.data(), ym.data());
+        std::vector<uint8_t> col(w, 0);
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                const int sx = f2i_rz(xm[(size_t)y * w + x]), sy = f2i_rz(ym[(size_t)y * w + x]);
+                if (sx >= 0 && sx < src_w && sy >= 0 && sy < src_h) col[x] = 1;
+            }
+        int best_a = -1, best_b = -1, run_start = -1;   // widest interior run [a, b) of empty columns between two filled ones
+        bool seen = false;
+        for (int x = 0; x < w; ++x) {
+            if (col[x]) {
+                if (seen && run_start >= 0 && x - run_start > best_b - best_a) { best_a = run_start; best_b = x; }
+                seen = true; run_start = -1;
+            } else if (seen && run_start < 0) run_start = x;
+        }
+        if (best_a < 0 || best_b - best_a <= 4 * m) { parts.push_back({i, 0, w}); continue; }
+        parts.push_back({i, 0, best_a + m});
+        parts.push_back({i, (best_b - m) / unit * unit, w});
+    }
+    return nb;
+}
+
 }  // namespace vsb
 
 
@@ -474,8 +523,10 @@ int vsb_voronoi_seams(int n, const int *sizes_wh, const int *corners_xy, uint8_t
     return VSB_OK;
 }
 
+// n_cameras = 0: one view per camera (cfg.num_views cameras).  n_cameras > 0: the split calibration -- cameras that wrap around +-pi
+// become two views (plan_parts), cfg.num_views must equal the number of parts (vsb_split_plan tells it before vsb_create).
 static int calibrate_rig_host(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains,
-                              double compose_scale)
+                              double compose_scale, int n_cameras = 0)
 {
     using namespace vsb;
     if (!s || pano_width <= 0 || src_w <= 0 || src_h <= 0) return fail(VSB_ERR_INVALID, "calibrate_rig: bad arguments");
@@ -485,7 +536,9 @@ static int calibrate_rig_host(vsb_stitcher *s, int projection, int pano_width, i
     int frame_sz[2], map_src[2];
     r = vsb_compose_size(src_w, src_h, compose_scale, frame_sz, map_src, nullptr);
     if (r != VSB_OK) return r;
-    const int n = cfg.num_views;
+    const bool split = n_cameras > 0;
+    const int n = split ? n_cameras : cfg.num_views;
+    if (split && (compose_scale != 1.0 || n > VSB_MAX_VIEWS)) return fail(VSB_ERR_INVALID, "calibrate_rig_split: bad arguments (compose_scale must be 1)");
     float scale = (float)(pano_width / (2.0 * 3.1415926535897932384626));  // sphere radius: pano_width px per 2*pi
     std::vector<float> K(9 * n), R(9 * n);
     for (int i = 0; i < n; ++i) {
@@ -538,6 +591,52 @@ static int calibrate_rig_host(vsb_stitcher *s, int projection, int pano_width, i
         r = vsb_warp_roi(projection, scale, &K[9 * i], &R[9 * i], map_src[0], map_src[1], &map_roi[4 * i]);
         if (r != VSB_OK) return r;
     }
+    if (split) {
+        // ---- the split calibration: the same per-camera products, installed as column windows of the cameras (plan_parts)
+        std::vector<ViewPart> parts;
+        plan_parts(projection, scale, K.data(), R.data(), n, src_w, src_h, cfg.num_bands, corners.data(), sizes.data(), parts);
+        const int nv = (int)parts.size();
+        if (nv != cfg.num_views)
+            return fail(VSB_ERR_INVALID, "calibrate_rig_split: this rig needs %d views (%d cameras, %d of them split), the handle has %d: size it with vsb_split_plan", nv, n, nv - n, cfg.num_views);
+        std::vector<int> vc(2 * nv), vs(2 * nv);
+        for (int k = 0; k < nv; ++k) {
+            const ViewPart &P = parts[k];
+            vc[2 * k] = corners[2 * P.cam] + P.x0; vc[2 * k + 1] = corners[2 * P.cam + 1];
+            vs[2 * k] = P.x1 - P.x0; vs[2 * k + 1] = sizes[2 * P.cam + 1];
+        }
+        r = vsb_prepare(s, vc.data(), vs.data());
+        if (r != VSB_OK) return r;
+        std::vector<float> xm, ym;
+        std::vector<uint8_t> warped, seam;
+        int have = -1;
+        for (int k = 0; k < nv; ++k) {
+            const ViewPart &P = parts[k];
+            const int i = P.cam, w = sizes[2 * i], h = sizes[2 * i + 1];
+            if (have != i) {   // the camera's full-width products (both parts of a camera are adjacent in the list)
+                xm.resize((size_t)w * h); ym.resize((size_t)w * h); warped.resize((size_t)w * h); seam.resize((size_t)w * h);
+                host_build_maps(projection, scale, &K[9 * i], &R[9 * i], corners[2 * i], corners[2 * i + 1], w, h, xm.data(), ym.data());
+                host_warp_full_mask(xm.data(), ym.data(), w, h, src_w, src_h, warped.data());
+                const int sw = seam_sizes[2 * i], sh = seam_sizes[2 * i + 1];
+                std::vector<uint8_t> dil(seam_masks[i].size());
+                if (cfg.enable_local) dilate3x3(seam_masks[i].data(), sw, sh, dil.data());
+                else dil = seam_masks[i];
+                resize_linear_u8(dil.data(), sw, sh, seam.data(), w, h);
+                for (size_t j = 0; j < seam.size(); ++j) seam[j] &= warped[j];
+                have = i;
+            }
+            const int pw = P.x1 - P.x0;
+            r = vsb_init_view(s, k, seam.data() + P.x0, pw, h, (size_t)w, vc[2 * k], vc[2 * k + 1], 0);
+            if (r != VSB_OK) return r;
+            r = vsb_set_maps(s, k, xm.data() + P.x0, ym.data() + P.x0, pw, h, (size_t)w * 4, 0, src_w, src_h);
+            if (r != VSB_OK) return r;
+            r = vsb_set_view_window(s, k, i, P.x0, w);
+            if (r != VSB_OK) return r;
+            if (gains) { r = vsb_set_gain(s, k, gains[i]); if (r != VSB_OK) return r; }
+        }
+        r = vsb_set_compose_scale(s, 1.0, src_w, src_h);
+        if (r != VSB_OK) return r;
+        return vsb_note_rig(s, projection, scale, src_w, src_h);
+    }
     r = vsb_prepare(s, corners.data(), sizes.data());
     if (r != VSB_OK) return r;
     for (int i = 0; i < n; ++i) {
@@ -566,6 +665,44 @@ static int calibrate_rig_host(vsb_stitcher *s, int projection, int pano_width, i
 int vsb_calibrate_rig(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains)
 {
     return calibrate_rig_host(s, projection, pano_width, src_w, src_h, hfov_deg, gains, 1.0);
+}
+
+// The views vsb_calibrate_rig_split makes of n_cameras cameras (host only, no device): view k is the column window
+// [view_x0[k], view_x0[k] + view_w[k]) of camera view_camera[k]'s warped image.  num_bands is the configured band count.
+int vsb_split_plan(int projection, int pano_width, int n_cameras, int src_w, int src_h, double hfov_deg, int num_bands, int *n_views,
+                   int *view_camera, int *view_x0, int *view_w)
+{
+    using namespace vsb;
+    if (n_cameras < 1 || n_cameras > VSB_MAX_VIEWS || pano_width <= 0 || src_w <= 0 || src_h <= 0 || num_bands < 1 || num_bands > VSB_MAX_BANDS || !n_views)
+        return fail(VSB_ERR_INVALID, "split_plan: bad arguments");
+    const int n = n_cameras;
+    const float scale = (float)(pano_width / (2.0 * 3.1415926535897932384626));
+    std::vector<float> K(9 * n), R(9 * n);
+    std::vector<int> corners(2 * n), sizes(2 * n);
+    for (int i = 0; i < n; ++i) {
+        int roi[4];
+        int r = vsb_rig_camera(n, i, src_w, src_h, hfov_deg, &K[9 * i], &R[9 * i]);
+        if (r == VSB_OK) r = vsb_warp_roi(projection, scale, &K[9 * i], &R[9 * i], src_w, src_h, roi);
+        if (r != VSB_OK) return r;
+        corners[2 * i] = roi[0]; corners[2 * i + 1] = roi[1]; sizes[2 * i] = roi[2]; sizes[2 * i + 1] = roi[3];
+    }
+    std::vector<ViewPart> parts;
+    plan_parts(projection, scale, K.data(), R.data(), n, src_w, src_h, num_bands, corners.data(), sizes.data(), parts);
+    *n_views = (int)parts.size();
+    if (*n_views > VSB_MAX_VIEWS) return fail(VSB_ERR_INVALID, "split_plan: %d views exceed VSB_MAX_VIEWS", *n_views);
+    for (int k = 0; k < *n_views; ++k) {
+        if (view_camera) view_camera[k] = parts[k].cam;
+        if (view_x0) view_x0[k] = parts[k].x0;
+        if (view_w) view_w[k] = parts[k].x1 - parts[k].x0;
+    }
+    return VSB_OK;
+}
+
+int vsb_calibrate_rig_split(vsb_stitcher *s, int projection, int pano_width, int n_cameras, int src_w, int src_h, double hfov_deg,
+                            const float *gains)
+{
+    if (n_cameras < 1) return vsb::fail(VSB_ERR_INVALID, "calibrate_rig_split: n_cameras must be >= 1");
+    return calibrate_rig_host(s, projection, pano_width, src_w, src_h, hfov_deg, gains, 1.0, n_cameras);
 }
 
 // ---- device-side calibration entry points -------------------------------------------------------------------------------------

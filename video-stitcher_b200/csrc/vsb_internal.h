@@ -47,3 +47,5 @@ extern "C" int vsb_note_rig(vsb_stitcher *s, int projection, float scale, int sr
 extern "C" void vsb_attach_calib(vsb_stitcher *s, void *state, void (*dtor)(void *));
 extern "C" void *vsb_get_calib(const vsb_stitcher *s);
 extern "C" int vsb_handle_device(const vsb_stitcher *s);
+// internal: marks a view as a column window of a camera's warped image (vsb_calibrate_rig_split)
+extern "C" int vsb_set_view_window(vsb_stitcher *s, int view, int camera, int x0, int full_w);

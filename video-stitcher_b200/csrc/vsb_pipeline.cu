@@ -1183,6 +1183,18 @@ __global__ void k_mesh_upsample(const float *__restrict__ wx, const float *__res
     *((float *)((char *)my + (size_t)v * pitch) + u) = custom_resize_at(wy, hw, hh, (size_t)hw * 4, W, H, u, v);
 }
 
+// m4 for a column window of the view (split calibration): columns [x0, x0 + w) of the W x H map, x coordinates re-based to the
+// window.  x - x0 is exact wherever the map points into or near the window (both are multiples of ulp(x) and the difference is the
+// smaller number), so floor and fraction -- all the remap uses -- are those of the full-width map; far outside it only has to stay outside.
+__global__ void k_mesh_upsample_win(const float *__restrict__ wx, const float *__restrict__ wy, int hw, int hh, int W, int H, int x0, int w,
+                                    float *mx, float *my, size_t pitch)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
+    if (u >= w || v >= H) return;
+    *((float *)((char *)mx + (size_t)v * pitch) + u) = __fsub_rn(custom_resize_at(wx, hw, hh, (size_t)hw * 4, W, H, u + x0, v), (float)x0);
+    *((float *)((char *)my + (size_t)v * pitch) + u) = custom_resize_at(wy, hw, hh, (size_t)hw * 4, W, H, u + x0, v);
+}
+
 // ============================================================================================ host side
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1193,6 +1205,7 @@ struct View {
     int roi_w = 0, roi_h = 0, tl_x = 0, tl_y = 0;
     int top = 0, bottom = 0, left = 0, right = 0, x_tl = 0, y_tl = 0, x_br = 0, y_br = 0, bw = 0, bh = 0;
     int src_w = 0, src_h = 0;
+    int cam = -1, win_x0 = 0, win_full_w = 0;  // split calibration: this view is columns [win_x0, win_x0 + roi_w) of camera cam's win_full_w-wide warped image (0: the whole image)
     float gain = 1.f;
     float *xmap = nullptr, *ymap = nullptr;
     size_t map_pitch = 0;
@@ -2685,7 +2698,10 @@ int vsb_set_mesh(vsb_stitcher *s, int i, const float *mesh_x, const float *mesh_
     REQ(rows >= 2 && cols >= 2 && rows * cols <= 4096, VSB_ERR_INVALID, "set_mesh: mesh must be between 2x2 and 4096 vertices");
     DeviceGuard g(s->device);
     View &V = s->v[i];
-    const int W = V.roi_w, H = V.roi_h, hw = W / 2, hh = H / 2;
+    // a window view (split calibration) takes the mesh of its CAMERA: the splat and the half-resolution table are those of the
+    // full-width image, only the window's columns of the map are written
+    const bool win = V.win_full_w > 0;
+    const int W = win ? V.win_full_w : V.roi_w, H = V.roi_h, hw = W / 2, hh = H / 2;
     REQ(hw >= 2 && hh >= 2, VSB_ERR_INVALID, "set_mesh: view too small");
     cudaStream_t st = s->mesh_stream;
     int target;
@@ -2710,7 +2726,8 @@ int vsb_set_mesh(vsb_stitcher *s, int i, const float *mesh_x, const float *mesh_
     const dim3 b(32, 8);
     k_mesh_splat<<<grid2d(W, H, b), b, 0, st>>>(d_mx, d_my, rows, cols, W, H, sum_x, sum_y, cnt);
     k_mesh_divide<<<(unsigned)((half + 255) / 256), 256, 0, st>>>(sum_x, sum_y, cnt, (int)half);
-    k_mesh_upsample<<<grid2d(W, H, b), b, 0, st>>>(sum_x, sum_y, hw, hh, W, H, V.mesh[target][0], V.mesh[target][1], V.map_pitch);
+    if (win) k_mesh_upsample_win<<<grid2d(V.roi_w, H, b), b, 0, st>>>(sum_x, sum_y, hw, hh, W, H, V.win_x0, V.roi_w, V.mesh[target][0], V.mesh[target][1], V.map_pitch);
+    else k_mesh_upsample<<<grid2d(W, H, b), b, 0, st>>>(sum_x, sum_y, hw, hh, W, H, V.mesh[target][0], V.mesh[target][1], V.map_pitch);
     {   // tap table of remap #2 for this mesh buffer (REFLECT border resolved, offsets into the zero-framed P)
         if (!V.t2_off[target]) {
             V.t2_pitch = (int)align_up((size_t)V.bw, 4);
@@ -2718,7 +2735,7 @@ int vsb_set_mesh(vsb_stitcher *s, int i, const float *mesh_x, const float *mesh_
             CK(cudaMalloc(&V.t2_off[target], V.t2_plane * sizeof(int)));
             CK(cudaMalloc(&V.t2_w[target], V.t2_plane * 4 * sizeof(float)));
         }
-        k_build_taps2<<<grid2d(V.t2_pitch, V.bh, b), b, 0, st>>>(V.mesh[target][0], V.mesh[target][1], V.map_pitch, W, H, V.bw, V.bh, V.top, V.left,
+        k_build_taps2<<<grid2d(V.t2_pitch, V.bh, b), b, 0, st>>>(V.mesh[target][0], V.mesh[target][1], V.map_pitch, V.roi_w, H, V.bw, V.bh, V.top, V.left,
                                                                  (unsigned)V.p_pitch, V.p_origin, V.t2_off[target], V.t2_w[target], V.t2_plane, V.t2_pitch, d_unsafe);
     }
     int r = check_launch("set_mesh kernels");
@@ -3514,6 +3531,30 @@ int vsb_set_compose_scale(vsb_stitcher *s, double compose_scale, int full_w, int
     s->compose_scale = compose_scale;
     s->prescale = resized != 0;   // within 0.1 of 1 the reference scales its cameras, not its frames (A/timed.cpp:75)
     s->full_w = full_w; s->full_h = full_h; s->comp_w = frame[0]; s->comp_h = frame[1];
+    return VSB_OK;
+}
+
+// split calibration (vsb_calibrate_rig_split): view `view` shows columns [x0, x0 + its width) of camera `camera`'s full_w-wide
+// warped image; vsb_set_mesh then takes the camera's mesh.  Internal (the calibration calls it after vsb_set_maps).
+int vsb_set_view_window(vsb_stitcher *s, int view, int camera, int x0, int full_w)
+{
+    REQ(s && view >= 0 && view < s->cfg.num_views && s->v[view].inited, VSB_ERR_INVALID, "set_view_window: bad view");
+    View &V = s->v[view];
+    REQ(camera >= 0 && x0 >= 0 && full_w >= x0 + V.roi_w, VSB_ERR_INVALID, "set_view_window: window outside the camera's image");
+    V.cam = camera;
+    const bool whole = x0 == 0 && full_w == V.roi_w;
+    V.win_x0 = whole ? 0 : x0; V.win_full_w = whole ? 0 : full_w;
+    return VSB_OK;
+}
+
+int vsb_view_window(const vsb_stitcher *s, int view, int *camera, int *x0, int *full_w)
+{
+    REQ(s && view >= 0 && view < s->cfg.num_views, VSB_ERR_INVALID, "view_window: bad view");
+    REQ(s->v[view].inited, VSB_ERR_STATE, "view_window: view %d is not initialised", view);
+    const View &V = s->v[view];
+    if (camera) *camera = V.cam >= 0 ? V.cam : view;
+    if (x0) *x0 = V.win_x0;
+    if (full_w) *full_w = V.win_full_w > 0 ? V.win_full_w : V.roi_w;
     return VSB_OK;
 }
 
