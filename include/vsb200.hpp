@@ -217,6 +217,29 @@ public:
         check(vsb_calibrate_rig_device(h_, projection, pano_width, src.width, src.height, hfov_deg, gains));
         next_view_ = n_;
     }
+    /* either calibration at the reference's compose_scale (calibration.cpp:137-205): scaled cameras and warper, the reference's
+       cvRound / (int) sizes; stitch_online / stitch then take FULL-size frames and resize them on the device first (timed.cpp:74-81) */
+    void calibrateRigScaled(int projection, int pano_width, Size src, double compose_scale, bool on_device = false, double hfov_deg = 90.0,
+                            const float *gains = 0)
+    {
+        check(vsb_calibrate_rig_scaled(h_, projection, pano_width, src.width, src.height, hfov_deg, gains, compose_scale, on_device ? 1 : 0));
+        next_view_ = n_;
+    }
+    /* wrapAround (defs.h:25) without a panorama-wide ROI: how many views a rig of n_cameras needs when every camera that looks across
+       +-pi is installed as two column windows of its warped image (construct the blender with that many views), and the calibration
+       that does it (gains per camera).  viewCamera(v) = the camera whose frame -- and whose mesh -- view v takes. */
+    static int splitViewCount(int projection, int pano_width, int n_cameras, Size src, int num_bands, double hfov_deg = 90.0)
+    {
+        int n = 0;
+        check(vsb_split_plan(projection, pano_width, n_cameras, src.width, src.height, hfov_deg, num_bands, &n, 0, 0, 0));
+        return n;
+    }
+    void calibrateRigSplit(int projection, int pano_width, int n_cameras, Size src, double hfov_deg = 90.0, const float *gains = 0)
+    {
+        check(vsb_calibrate_rig_split(h_, projection, pano_width, n_cameras, src.width, src.height, hfov_deg, gains));
+        next_view_ = n_;
+    }
+    int viewCamera(int view) const { int c = 0; check(vsb_view_window(h_, view, &c, 0, 0)); return c; }
     /* GainCompensator::feed + gains() (S/src/exposure_compensate.cpp:71-142,162-168) from the current camera frames, at run time;
        apply = true installs them (what A/timed.cpp:94 multiplies by) */
     std::vector<float> estimateGains(const std::vector<DeviceMat> &frames, bool apply, Stream stream = 0)

@@ -31,21 +31,22 @@ def main():
     assert B.LIB_PATH.endswith("libvsb200_emu.so")
     n, sw, sh, pano, nb = case["n_views"], case["src_w"], case["src_h"], case["pano_width"], case["num_bands"]
     F = int(case.get("frames", 1))
+    proj = int(case.get("projection", 0))                  # 0 spherical, 1 cylindrical
     gains = S.gains(n)
     t0 = time.time()
     split = bool(case.get("split"))                        # cameras that wrap around +-pi become two views (vsb_calibrate_rig_split)
-    plan = B.split_plan(0, pano, n, sw, sh, nb) if split else [(i, 0, 0) for i in range(n)]
+    plan = B.split_plan(proj, pano, n, sw, sh, nb) if split else [(i, 0, 0) for i in range(n)]
     nv = len(plan)
     st = B.Stitcher(nv, nb, True, F)
     cs = float(case.get("compose_scale", 1.0))             # != 1: sw x sh are the full frames, resized on the device in front of remap #1
     if split:
-        st.calibrate_rig_split(0, pano, n, sw, sh, 90.0, gains)
+        st.calibrate_rig_split(proj, pano, n, sw, sh, 90.0, gains)
     elif cs != 1.0:
-        st.calibrate_rig_scaled(0, pano, sw, sh, cs, 90.0, gains, on_device=bool(case.get("device_calibration")))
+        st.calibrate_rig_scaled(proj, pano, sw, sh, cs, 90.0, gains, on_device=bool(case.get("device_calibration")))
     elif case.get("device_calibration"):                   # every per-pixel loop of the calibration as kernels (maps differ from libm's by ulps)
-        st.calibrate_rig_device(0, pano, sw, sh, 90.0, gains)
+        st.calibrate_rig_device(proj, pano, sw, sh, 90.0, gains)
     else:
-        st.calibrate_rig(0, pano, sw, sh, 90.0, gains)      # the product's host calibration + its weight / plan kernels
+        st.calibrate_rig(proj, pano, sw, sh, 90.0, gains)   # the product's host calibration + its weight / plan kernels
     info = st.rig_info()
     win = [st.view_window(k) for k in range(nv)]            # (camera, x0, width of the camera's warped image) per view
     for k in range(nv):
@@ -71,7 +72,7 @@ def main():
     t_compose = time.time() - t0
     launched = [name for name, _, _ in E.stats()["launches"][n0:]]
 
-    orig = op.OracleRig(n, sw, sh, pano, num_bands=nb, enable_local=True, gains=gains, compose_scale=cs)
+    orig = op.OracleRig(n, sw, sh, pano, projection=proj, num_bands=nb, enable_local=True, gains=gains, compose_scale=cs)
     for i in range(n):
         orig.set_mesh(i, *S.mesh(*orig.sizes[i]))
 
@@ -117,4 +118,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except Exception:
+        from oracle.emu import runtime as E
+        print("emulated runtime error:", E.stats().get("error"), file=sys.stderr)
+        raise
