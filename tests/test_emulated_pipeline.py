@@ -113,3 +113,22 @@ def test_product_library_split_calibration_on_the_emulated_runtime():
     assert max(v[2] for v in res["views"]) < 192 // 2, res["views"]
     assert res["mesh_maps"] == 0 and res["warped"] == 0 and res["gauss0"] == 0 and res["gauss2"] == 0, res
     assert res["pano"] == 0 and res["pano_nonzero"] > res["pano_samples"] // 2, res
+
+
+@pytest.mark.skipif(not os.environ.get("VSB_EMU_FULL"), reason="a quarter of an hour of interpretation: set VSB_EMU_FULL=1 (view-sharded mode, 2 and 3 ranks)")
+@pytest.mark.parametrize("world,split", [(2, False), (3, True)])
+def test_view_sharded_mode_on_the_emulated_runtime(world, split):
+    """The north-star multi-GPU split without GPUs: `world` handles in one process (one per rank) on the emulated runtime -- shard
+    ownership and plan, front halves of the owned views, k_shard_copy pack, the per-peer messages handed over in-process (what
+    vsb_shard_compose's grouped ncclSend / ncclRecv moves), k_shard_copy unpack, strip blends -- and the strips summed are oracle-G's
+    panorama bit for bit.  With split=True the rig is calibrated with vsb_calibrate_rig_split (5 views from 4 cameras)."""
+    _need_nvcc()
+    case = dict(n_views=4, src_w=96, src_h=64, pano_width=512, num_bands=3, world=world, split=split)
+    env = {k: v for k, v in os.environ.items() if k != "VSB200_LIB"}
+    r = subprocess.run([sys.executable, "-m", "oracle.emu.run_shard_case", json.dumps(case)], capture_output=True, text=True, timeout=3000, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["error"] is None and res["roi_equal"] and res["pano"] == 0 and res["pano_nonzero"] > res["pano_samples"] // 2, res
+    assert len(res["ranks"]) == world and sum(x["send_bytes_per_frame"] for x in res["ranks"]) > 0 and res["shard_copy_launches"] >= 2, res
+    owned = sorted(v for x in res["ranks"] for v in x["owned"])
+    assert owned == list(range(5 if split else 4)), res["ranks"]
