@@ -22,6 +22,7 @@ DEFAULT_CASES = {   # interpreted in parallel (one process each, ~70 s): started
     "base": dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3),
     "compose_scale": dict(n_views=4, src_w=61, src_h=41, pano_width=192, num_bands=3, compose_scale=0.8),
     "split": dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3, split=True),
+    "wire": dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3, wire=True),
 }
 _procs = {}
 
@@ -81,11 +82,10 @@ def test_product_library_end_to_end_larger_rig():
     assert "k_blend_int" in " ".join(res["launched"]), res["launched"]
 
 
-@pytest.mark.skipif(not os.environ.get("VSB_EMU_FULL"), reason="another minute and a half of interpretation: set VSB_EMU_FULL=1 (NV12 in, CV_8UC3 out)")
 def test_product_library_wire_formats_on_the_emulated_runtime():
     """VSB_IN_NV12 / VSB_OUT_U8C3: the NV12 conversion fused into remap #1's tap fetch (k_remap_stage1_nv12) and the CV_8UC3 store of the
     blend kernels, against og.nv12_to_bgr -> compose -> og.s16_to_u8."""
-    res = _run(dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3, wire=True))
+    res = _default("wire")
     assert res["error"] is None and res["pano"] == 0 and res["warped"] == 0, res
     assert "k_remap_stage1_nv12" in " ".join(res["launched"]), res["launched"]
 
