@@ -533,7 +533,11 @@ def _run_sharded_body(args, cfg, rank, world, local_rank, replicas, dog):
             "parity_checked": bool(parity["bit_exact"]), "parity": parity,
             "shards": stats, "exchange_bytes_per_frame": xbytes,
             "exchange": {"bytes_per_frame": xbytes, "nvlink_GBps_per_gpu": xbytes * fps / world / 1e9},
-            "single_gpu_same_workload": single, "replicas": replicas})
+            "single_gpu_same_workload": single, "replicas": replicas,
+            "scale_note": ("BASELINE.json names a different workload per GPU count (config 2 on 1 GPU, config 3 = 4x the panorama pixels on 2 and 4, "
+                           "config 4 = 16x on 8): `value` is ONE frame stream of THIS line's workload sharded over all ranks (strong scaling). Its one-GPU "
+                           "counterpart is `single_gpu_same_workload` (measured in this run on rank 0), not the N=1 line of config 2; the frame-level-"
+                           "replicas rate of config 2 -- comparable with the N=1 line -- is under `replicas`.")})
     dog.done.set()
     torch.cuda.synchronize()
     os._exit(0)  # (a clean communicator teardown can itself wait on peers; everything is measured and printed)
