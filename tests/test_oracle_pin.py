@@ -288,6 +288,92 @@ def test_live_scaled_rig_geometry_vs_reference_projector(og):
     assert np.array_equal(og.cuda_resize_linear_u8(src, want.shape[1], want.shape[0], 0.75, 0.75), want)
 
 
+def test_live_tilted_cameras_roi_and_maps_vs_reference_projector(og):
+    """Cameras the fixed rig never produces -- pitch and roll, a pole of the sphere inside the image (SphericalWarper::detectResultRoi's
+    pole test, S/src/warpers.cpp:277-318), a camera looking straight up -- through oracle-G, the product's host ROI code
+    (vsb_warp_roi) and the REFERENCE's own projector (warpers.cpp compiled in place): identical ROIs, maps within 2e-3 px."""
+    vr = _vr()
+    import vsb200
+    B = vsb200.binding
+
+    def rot(yaw, pitch, roll):
+        cy, sy, cp, sp, cr, sr = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
+        Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        Rx = np.array([[1, 0, 0], [0, cp, -sp], [0, sp, cp]])
+        Rz = np.array([[cr, -sr, 0], [sr, cr, 0], [0, 0, 1]])
+        return (Rz @ Ry @ Rx).astype(np.float32)
+
+    sw, sh = 320, 240
+    K = np.array([[160.0, 0, 160.0], [0, 160.0, 120.0], [0, 0, 1]], np.float32)       # hfov 90 degrees
+    poles = 0
+    for proj in (0, 1):
+        for scale in (np.float32(163.0), np.float32(97.5)):
+            for (yaw, pitch, roll) in ((0.3, 0.4, 0.0), (2.9, -0.5, 0.2), (1.0, 1.2, 0.0), (0.0, np.pi / 2, 0.0), (3.1, -1.3, 0.7), (0.7, 0.0, 1.5)):
+                R = rot(yaw, pitch, roll)
+                want = vr.warp_roi(proj, scale, K, R, sw, sh)
+                assert og.warp_roi(proj, scale, K, R, sw, sh) == want, (proj, float(scale), yaw, pitch, roll)
+                assert B.warp_roi(proj, float(scale), [float(v) for v in K.reshape(9)], [float(v) for v in R.reshape(9)], sw, sh) == want
+                if proj == 0 and abs(pitch) > 1.0:
+                    poles += want[3] > 0.45 * np.pi * float(scale)          # a view over a pole is tall: it reaches the pole row
+                if want[2] * want[3] > 400000:
+                    continue
+                xm, ym = og.build_maps(proj, scale, K, R, *want)
+                xr, yr, roi_r = vr.build_maps(proj, scale, K, R, sw, sh)
+                assert tuple(roi_r) == want
+                ok = ~((xm == -1) & (ym == -1)) & ~((xr == -1) & (yr == -1)) & (xr > -2) & (xr < sw + 1) & (yr > -2) & (yr < sh + 1)
+                assert ok.sum() > 100 and np.abs(xm - xr)[ok].max() <= 2e-3 and np.abs(ym - yr)[ok].max() <= 2e-3, (proj, yaw, pitch, roll)
+    assert poles >= 2, "the pole branch of detectResultRoi was meant to be exercised"
+
+
+def test_live_voronoi_seams_on_ragged_layouts(og):
+    """VoronoiSeamFinder::find (S/src/seam_finders.cpp:72-162) on layouts the rig never produces: rectangles of different sizes at
+    random corners -- disjoint pairs, one view inside another, identical corners, one-pixel overlaps -- with holes in the masks:
+    oracle-G and the product's host seam finder (vsb_voronoi_seams) against the reference's own class, bit for bit."""
+    vr = _vr()
+    import ctypes as C
+    import vsb200
+    L = vsb200.binding.lib()
+    rng = np.random.default_rng(77)
+    layouts = 0
+    for trial in range(40):
+        n = int(rng.integers(2, 7))
+        sizes = [(int(rng.integers(1, 60)), int(rng.integers(1, 50))) for _ in range(n)]
+        corners = [(int(rng.integers(-40, 40)), int(rng.integers(-30, 30))) for _ in range(n)]
+        if trial % 5 == 0:
+            corners[1] = corners[0]                                            # identical corners
+        if trial % 7 == 0 and n > 2:
+            corners[2] = (corners[0][0] + sizes[0][0] - 1, corners[0][1])      # one column of overlap
+        base = []
+        for (w, h) in sizes:
+            m = np.full((h, w), 255, np.uint8)
+            if rng.random() < 0.5:
+                m[rng.random((h, w)) < 0.15] = 0                               # holes
+            base.append(m)
+        want = vr.voronoi_find(sizes, corners, [m.copy() for m in base])
+        got = og.voronoi_find(sizes, corners, [m.copy() for m in base])
+        mine = [m.copy() for m in base]
+        sz = np.ascontiguousarray(np.array(sizes, np.int32).reshape(-1))
+        co = np.ascontiguousarray(np.array(corners, np.int32).reshape(-1))
+        ptrs = (C.c_void_p * n)(*[m.ctypes.data for m in mine])
+        assert L.vsb_voronoi_seams(n, sz.ctypes.data_as(C.POINTER(C.c_int)), co.ctypes.data_as(C.POINTER(C.c_int)), ptrs) == 0
+        for i in range(n):
+            assert np.array_equal(got[i], want[i]), (trial, i, "oracle-G")
+            assert np.array_equal(mine[i], want[i]), (trial, i, "vsb_voronoi_seams")
+        layouts += any(not np.array_equal(want[i], base[i]) for i in range(n))
+    assert layouts > 20, "most layouts must have overlaps the seam finder cuts"
+
+
+def test_live_gain_compensator_on_other_layouts(og):
+    """GainCompensator::feed (S/src/exposure_compensate.cpp:79-147) beyond the one committed input: 4 to 9 views, ring and chain
+    layouts, masks with holes, a pair without overlap -- oracle-G against the reference's own class, float64, bit for bit."""
+    vr = _vr()
+    for seed, n in ((1, 4), (2, 5), (3, 7), (4, 9), (5, 6)):
+        imgs, masks, corners, sizes = G.gain_input(seed=seed, n=n)
+        if seed == 5:
+            corners = [(c[0] + (400 if i == n - 1 else 0), c[1]) for i, c in enumerate(corners)]   # the last view overlaps nobody
+        assert np.array_equal(og.gain_compensator_feed(imgs, masks, corners, sizes), vr.gain_compensator_feed(imgs, masks, corners, sizes)), (seed, n)
+
+
 def test_live_small_rig_compose_vs_oracle_c(og):
     """Whole path, oracle-G vs the CPU compose on the reference's OpenCV (same static inputs): masks identical, pano close.
     Not a +-1 pin (fixed-point CPU remap + tie rounding) -- a gross-error tripwire."""
