@@ -2714,10 +2714,15 @@ int vsb_set_mesh(vsb_stitcher *s, int i, const float *mesh_x, const float *mesh_
         if (s->last_compose_valid) CK(cudaStreamWaitEvent(st, s->last_compose, 0));
     }
     const size_t half = (size_t)hw * hh;
-    if (!V.mesh_scratch) CK(cudaMalloc(&V.mesh_scratch, sizeof(float) * (3 * half + 2 * 4096 + 1)));
+    // scratch: half-resolution accumulators + the vertex mesh.  A window view's accumulators are those of the panorama-wide image
+    // it was cut from, which the split calibration exists not to keep: they come from the stream-ordered pool for this call only
+    float *scratch = V.mesh_scratch;
+    if (win) CK(cudaMallocAsync((void **)&scratch, sizeof(float) * (3 * half + 2 * 4096 + 1), st));
+    else if (!scratch) { CK(cudaMalloc(&V.mesh_scratch, sizeof(float) * (3 * half + 2 * 4096 + 1))); scratch = V.mesh_scratch; }
+    struct PoolScratch { float *p; cudaStream_t st; ~PoolScratch() { if (p) cudaFreeAsync(p, st); } } pool_scratch{win ? scratch : nullptr, st};
     for (int c = 0; c < 2; ++c)
         if (!V.mesh[target][c]) CK(cudaMalloc(&V.mesh[target][c], V.map_pitch * H));
-    float *sum_x = V.mesh_scratch, *sum_y = sum_x + half, *cnt = sum_y + half, *d_mx = cnt + half, *d_my = d_mx + 4096;
+    float *sum_x = scratch, *sum_y = sum_x + half, *cnt = sum_y + half, *d_mx = cnt + half, *d_my = d_mx + 4096;
     int *d_unsafe = (int *)(d_my + 4096);
     CK(cudaMemcpyAsync(d_mx, mesh_x, sizeof(float) * rows * cols, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_my, mesh_y, sizeof(float) * rows * cols, cudaMemcpyHostToDevice, st));
