@@ -121,6 +121,31 @@ def test_compose_scale_sizes_and_cameras(vsb, og):
             assert abs(K[0] - K1[0] * c) <= 1e-3 and abs(K[2] - K1[2] * c) <= 1e-3 and K[8] == 1.0
 
 
+@pytest.mark.parametrize("rig,views", [((6, 1920, 1080, 3840), 7), ((6, 3840, 2160, 7680), 7), ((12, 3840, 2160, 15360), 15), ((2, 1280, 720, 4021), 3)])
+def test_split_plan_of_the_baseline_configs(vsb, og, rig, views):
+    """vsb_split_plan (host only) on BASELINE.json's configs: which cameras wrap around +-pi, where they are cut, and that afterwards no
+    view is panorama-wide (the point of the split: config 4 has three panorama-wide views, 15360 columns each, without it)."""
+    n, sw, sh, pano = rig
+    plan = vsb.split_plan(0, pano, n, sw, sh, 5)
+    assert len(plan) == views and sorted(set(c for c, _, _ in plan)) == list(range(n))
+    scale = np.float32(pano / (2.0 * 3.1415926535897932384626))
+    rois = [og.warp_roi(0, scale, *og.rig_camera(n, i, sw, sh), sw, sh) for i in range(n)]
+    W = max(r[0] + r[2] for r in rois) - min(r[0] for r in rois)
+    whole = [c for c, x0, w in plan if (x0, w) == (0, rois[c][2])]
+    parts = [(c, x0, w) for c, x0, w in plan if (x0, w) != (0, rois[c][2])]
+    assert len(parts) == 2 * (views - n) and all(rois[c][2] >= W - 1 for c, _, _ in parts) and all(rois[c][2] < W - 1 for c in whole)
+    for c, x0, w in parts:
+        assert x0 % 32 == 0 and x0 + w <= rois[c][2] and w < 0.3 * W + 240, (c, x0, w)
+    for c in set(c for c, _, _ in parts):
+        (_, a0, aw), (_, b0, bw) = [p for p in parts if p[0] == c]
+        assert a0 == 0 and b0 + bw == rois[c][2] and b0 - aw > 4 * (3 * 32 + 8), "the two windows are the two ends of the image, far apart"
+    lib = vsb.lib()
+    nv = C.c_int()
+    assert lib.vsb_split_plan(0, pano, 0, sw, sh, C.c_double(90.0), 5, C.byref(nv), None, None, None) == -1
+    assert lib.vsb_split_plan(0, pano, n, sw, sh, C.c_double(90.0), 9, C.byref(nv), None, None, None) == -1
+    assert lib.vsb_calibrate_rig_split(None, 0, pano, n, sw, sh, C.c_double(90.0), None) == -1
+
+
 def test_host_voronoi_matches_reference(vsb, og):
     from tests.golden import make_golden as G
     gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_cpu.npz"))
