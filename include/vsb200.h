@@ -150,13 +150,14 @@ int vsb_calibrate_rig_scaled(vsb_stitcher *s, int projection, int pano_width, in
  *      calibration installs such a camera as TWO views, column windows of its warped image (margins and origins chosen so that
  *      every pyramid level equals the full-width view's wherever a weight is non-zero: the panorama is the same bit for bit),
  *      so no buffer is ever panorama-wide.  vsb_split_plan (host only) tells how many views a rig needs -- create the handle with
- *      that num_views -- and which camera / columns each view shows; vsb_calibrate_rig_split is vsb_calibrate_rig for it (gains per
+ *      that num_views -- and which camera / columns each view shows; vsb_calibrate_rig_split is vsb_calibrate_rig (on_device = 0) or
+ *      vsb_calibrate_rig_device (1; vsb_estimate_gains then installs each camera's gain on all of its views) for it (gains per
  *      CAMERA).  Per frame the caller passes, for every VIEW, the frame of its camera (vsb_view_window); vsb_set_mesh on a window
  *      view takes the camera's mesh.  Meshes must not move image content across the zero margin (3 * 2^num_bands + 8 px). ------ */
 int vsb_split_plan(int projection, int pano_width, int n_cameras, int src_w, int src_h, double hfov_deg, int num_bands, int *n_views,
                    int *view_camera, int *view_x0, int *view_w);
 int vsb_calibrate_rig_split(vsb_stitcher *s, int projection, int pano_width, int n_cameras, int src_w, int src_h, double hfov_deg,
-                            const float *gains);
+                            const float *gains, int on_device);
 int vsb_view_window(const vsb_stitcher *s, int view, int *camera, int *x0, int *full_w);
 int vsb_rig_info_get(const vsb_stitcher *s, vsb_rig_info *out);
 int vsb_get_config(const vsb_stitcher *s, vsb_config *out);

@@ -234,9 +234,9 @@ public:
         check(vsb_split_plan(projection, pano_width, n_cameras, src.width, src.height, hfov_deg, num_bands, &n, 0, 0, 0));
         return n;
     }
-    void calibrateRigSplit(int projection, int pano_width, int n_cameras, Size src, double hfov_deg = 90.0, const float *gains = 0)
+    void calibrateRigSplit(int projection, int pano_width, int n_cameras, Size src, bool on_device = false, double hfov_deg = 90.0, const float *gains = 0)
     {
-        check(vsb_calibrate_rig_split(h_, projection, pano_width, n_cameras, src.width, src.height, hfov_deg, gains));
+        check(vsb_calibrate_rig_split(h_, projection, pano_width, n_cameras, src.width, src.height, hfov_deg, gains, on_device ? 1 : 0));
         next_view_ = n_;
     }
     int viewCamera(int view) const { int c = 0; check(vsb_view_window(h_, view, &c, 0, 0)); return c; }

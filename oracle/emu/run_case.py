@@ -40,7 +40,7 @@ def main():
     st = B.Stitcher(nv, nb, True, F)
     cs = float(case.get("compose_scale", 1.0))             # != 1: sw x sh are the full frames, resized on the device in front of remap #1
     if split:
-        st.calibrate_rig_split(proj, pano, n, sw, sh, 90.0, gains)
+        st.calibrate_rig_split(proj, pano, n, sw, sh, 90.0, gains, on_device=bool(case.get("device_calibration")))
     elif cs != 1.0:
         st.calibrate_rig_scaled(proj, pano, sw, sh, cs, 90.0, gains, on_device=bool(case.get("device_calibration")))
     elif case.get("device_calibration"):                   # every per-pixel loop of the calibration as kernels (maps differ from libm's by ulps)
@@ -107,6 +107,8 @@ def main():
         if wire:
             want = og.s16_to_u8(want)
         res["pano"] += int(np.count_nonzero(outs[f].a != want))
+    import hashlib
+    res["pano_sha256"] = hashlib.sha256(b"".join(np.ascontiguousarray(o.a).tobytes() for o in outs)).hexdigest()[:16]
     res["pano_samples"] = int(F * H * W * 3)
     res["pano_nonzero"] = int(np.count_nonzero(outs[0].a))
     res["launched"] = [k.split("vsb")[-1][:28] for k in launched]

@@ -360,8 +360,12 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
             return R[o]
         if o.startswith("0f") or o.startswith("0F"):
             return f32_from_bits(int(o[2:], 16))
+        if o.startswith("0d") or o.startswith("0D"):
+            return struct.unpack("<d", int(o[2:], 16).to_bytes(8, "little"))[0]
         if ty == "f32":
             return F32(float(o))
+        if ty == "f64":
+            return float(o)
         if o in shared_off:
             return shared_off[o]                 # shared-window offsets: ld.shared / st.shared name their space explicitly
         if o in kernel.module.dyn_shared:
@@ -433,11 +437,15 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
         """raw little-endian integer from memory -> register value"""
         if ty == "f32":
             return f32_from_bits(raw)
+        if ty == "f64":
+            return struct.unpack("<d", int(raw).to_bytes(8, "little"))[0]
         return _mask(raw, _WIDTH[ty])
 
     def from_reg(ty, v):
         if ty == "f32":
             return f32_bits(v)
+        if ty == "f64":
+            return int.from_bytes(struct.pack("<d", float(v)), "little")
         return _mask(int(v), _WIDTH[ty])
 
     pc, n_instr = 0, len(kernel.instrs)
@@ -545,9 +553,9 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
                 cmp_, a, b = op[1], val(ops[1], ty), val(ops[2], ty)
                 if ty in ("s16", "s32", "s64"):
                     a, b = _signed(a, _WIDTH[ty]), _signed(b, _WIDTH[ty])
-                elif ty != "f32":                # unsigned / bit types: immediates such as -3 mean their two's complement pattern
+                elif ty not in ("f32", "f64"):   # unsigned / bit types: immediates such as -3 mean their two's complement pattern
                     a, b = _mask(a, _WIDTH[ty]), _mask(b, _WIDTH[ty])
-                if ty == "f32":
+                if ty in ("f32", "f64"):
                     unordered = bool(np.isnan(a) or np.isnan(b))
                     table = {"eq": a == b, "ne": a != b, "lt": a < b, "le": a <= b, "gt": a > b, "ge": a >= b}
                     if cmp_ in ("nan", "num"):
@@ -572,7 +580,7 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
                 dst_t, src_t = op[-2], op[-1]
                 v = val(ops[1], src_t)
                 mods = op[1:-2]
-                if src_t == "f32" and dst_t != "f32":       # float -> integer (rounding mode in mods, saturating at the type's range)
+                if src_t == "f32" and dst_t not in ("f32", "f64"):   # float -> integer (rounding mode in mods, saturating at the type's range)
                     bits = _WIDTH[dst_t]
                     lo, hi = (-(1 << (bits - 1)), (1 << (bits - 1)) - 1) if dst_t[0] == "s" else (0, (1 << bits) - 1)
                     if np.isnan(v):
@@ -594,6 +602,14 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
                             raise NotImplementedError(op)
                         r = min(max(r, lo), hi)
                     R[ops[0]] = _mask(r, bits)
+                elif dst_t == "f64" and src_t == "f32":     # widening: exact
+                    R[ops[0]] = float(v)
+                elif dst_t == "f64" and src_t != "f64":     # integer -> binary64: Python rounds int -> float to nearest even (exact below 2^53)
+                    iv = _signed(v, _WIDTH[src_t]) if src_t[0] == "s" else _mask(v, _WIDTH[src_t])
+                    R[ops[0]] = float(iv)
+                elif dst_t == "f32" and src_t == "f64":     # narrowing, round to nearest even
+                    assert "rn" in mods, "only cvt.rn.f32.f64 is modelled"
+                    R[ops[0]] = F32(v)
                 elif dst_t == "f32" and src_t != "f32":     # integer -> float, round to nearest even
                     iv = _signed(v, _WIDTH[src_t]) if src_t[0] == "s" else _mask(v, _WIDTH[src_t])
                     R[ops[0]] = round_fraction_to_f32(Fraction(iv))
@@ -602,6 +618,36 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
                 else:                                       # integer -> integer: sign- or zero-extend, then truncate
                     iv = _signed(v, _WIDTH[src_t]) if src_t[0] == "s" else _mask(v, _WIDTH[src_t])
                     R[ops[0]] = _mask(iv, _WIDTH[dst_t])
+                continue
+            if ty == "f64":                      # binary64: Python floats are IEEE doubles; +, -, *, / and sqrt are correctly rounded (rn)
+                import math
+                a = float(val(ops[1], "f64"))
+                b = float(val(ops[2], "f64")) if len(ops) > 2 else None
+                assert name in ("neg", "abs", "mov") or "rn" in op or name in ("min", "max"), f"only round-to-nearest binary64 is modelled: {op}"
+                if name == "add":
+                    r = a + b
+                elif name == "sub":
+                    r = a - b
+                elif name == "mul":
+                    r = a * b
+                elif name == "div":
+                    r = (a / b) if b != 0 else (math.nan if (a == 0 or a != a) else math.copysign(math.inf, a) * math.copysign(1.0, b))
+                elif name == "sqrt":
+                    r = math.sqrt(a) if a >= 0 else math.nan
+                elif name == "neg":
+                    r = -a
+                elif name == "abs":
+                    r = abs(a)
+                elif name == "fma":
+                    c = float(val(ops[3], "f64"))
+                    if any(x != x or x in (math.inf, -math.inf) for x in (a, b, c)):
+                        r = a * b + c
+                    else:
+                        fr = Fraction(a) * Fraction(b) + Fraction(c)
+                        r = fr.numerator / fr.denominator if fr != 0 else (a * b + c)   # int / int true division rounds correctly
+                else:
+                    raise NotImplementedError(op)
+                R[ops[0]] = r
                 continue
             if ty == "f32":
                 a = val(ops[1], "f32")

@@ -98,4 +98,7 @@ else:
     if not picks or "wire" in picks:
         T.test_split_wire_formats_and_wrong_view_count(fake_torch, og)
         print("ok: test_split_wire_formats_and_wrong_view_count", round(time.time() - t0), "s", flush=True)
+    if not picks or "device" in picks:
+        T.test_split_on_the_device_calibration_and_gain_refresh(fake_torch, og)
+        print("ok: test_split_on_the_device_calibration_and_gain_refresh", round(time.time() - t0), "s", flush=True)
 print("done", round(time.time() - t0), "s")

@@ -124,12 +124,13 @@ class GpuSplitRig(GpuRig):
     """vsb_calibrate_rig_split: cameras that wrap around +-pi are installed as two views (column windows of their warped image).
     The interface stays per CAMERA: frames and meshes are given per camera and handed to every view of that camera."""
 
-    def __init__(self, n_views, src_w, src_h, pano_width, projection=0, num_bands=5, enable_local=True, gains=None, max_batch=1):
+    def __init__(self, n_views, src_w, src_h, pano_width, projection=0, num_bands=5, enable_local=True, gains=None, max_batch=1,
+                 device_calibration=False):
         self.n_cameras, self.src_w, self.src_h = n_views, src_w, src_h
         self.plan = B.split_plan(projection, pano_width, n_views, src_w, src_h, num_bands)
         self.n = len(self.plan)
         self.st = B.Stitcher(self.n, num_bands, enable_local, max_batch)
-        self.st.calibrate_rig_split(projection, pano_width, n_views, src_w, src_h, 90.0, gains)
+        self.st.calibrate_rig_split(projection, pano_width, n_views, src_w, src_h, 90.0, gains, on_device=device_calibration)
         self.roi_final, self.roi_padded, self.num_bands = self.st.get_roi()
         self.geom = [self.st.view_geometry(k) for k in range(self.n)]
         info = self.st.rig_info()

@@ -143,7 +143,7 @@ def test_split_plan_of_the_baseline_configs(vsb, og, rig, views):
     nv = C.c_int()
     assert lib.vsb_split_plan(0, pano, 0, sw, sh, C.c_double(90.0), 5, C.byref(nv), None, None, None) == -1
     assert lib.vsb_split_plan(0, pano, n, sw, sh, C.c_double(90.0), 9, C.byref(nv), None, None, None) == -1
-    assert lib.vsb_calibrate_rig_split(None, 0, pano, n, sw, sh, C.c_double(90.0), None) == -1
+    assert lib.vsb_calibrate_rig_split(None, 0, pano, n, sw, sh, C.c_double(90.0), None, 0) == -1
 
 
 def test_host_voronoi_matches_reference(vsb, og):

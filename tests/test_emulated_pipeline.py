@@ -132,3 +132,18 @@ def test_view_sharded_mode_on_the_emulated_runtime(world, split):
     assert len(res["ranks"]) == world and sum(x["send_bytes_per_frame"] for x in res["ranks"]) > 0 and res["shard_copy_launches"] >= 2, res
     owned = sorted(v for x in res["ranks"] for v in x["owned"])
     assert owned == list(range(5 if split else 4)), res["ranks"]
+
+
+def test_device_gain_estimation_on_the_emulated_runtime():
+    """vsb_gain_compensator_feed on the emulated runtime: k_gain_pairs -- binary64 sums in the reference's summation order, interpreted
+    from the product's PTX -- and the host LU solve give the gains of the REFERENCE's own GainCompensator class (committed in
+    tests/golden/reference_cpu.npz from oracle/_ref), bit for bit, float64."""
+    import numpy as np
+    _need_nvcc()
+    env = {k: v for k, v in os.environ.items() if k != "VSB200_LIB"}
+    r = subprocess.run([sys.executable, "-m", "oracle.emu.run_gain_case"], capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["rc"] == 0 and res["error"] is None and any("k_gain_pairs" in k for k in res["launched"]), res
+    want = np.load(os.path.join(ROOT, "tests", "golden", "reference_cpu.npz"))["gain_compensator"]
+    assert [float.fromhex(h) for h in res["gains_hex"]] == [float(v) for v in want]

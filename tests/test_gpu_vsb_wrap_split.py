@@ -96,3 +96,31 @@ def test_split_wire_formats_and_wrong_view_count(cuda, og):
     with pytest.raises(B.VsbError) as e:
         st.calibrate_rig_split(0, kw["pano_width"], n, sw, sh, 90.0, gains)
     assert f"needs {grig.n} views" in str(e.value)
+
+
+def test_split_on_the_device_calibration_and_gain_refresh(cuda, og):
+    """vsb_calibrate_rig_split(on_device = 1): the device calibration's products installed as windows.  Its panorama equals the UNSPLIT
+    device calibration's bit for bit (both build the same maps and seams with the device's sinf / cosf), and vsb_estimate_gains --
+    one gain per CAMERA -- installs each gain on both views of a split camera."""
+    import vsb200
+    from tests.gpu_util import GpuRig, GpuSplitRig, dev, stream
+    S = vsb200.synth
+    kw = dict(CASES["small4"])
+    n, sw, sh = kw["n_views"], kw["src_w"], kw["src_h"]
+    gains = S.gains(n)
+    whole = GpuRig(gains=gains, device_calibration=True, **kw)
+    split = GpuSplitRig(gains=gains, device_calibration=True, **kw)
+    assert split.n == n + 1 and split.roi_final == whole.roi_final
+    for c in range(n):
+        mx, my = S.mesh(*whole.sizes[c])
+        whole.set_mesh(c, mx, my)
+        split.set_camera_mesh(c, mx, my)
+    frames = [S.frame(i, 1, sw, sh) for i in range(n)]
+    _eq(split.compose([frames])[0], whole.compose([frames])[0], "split vs unsplit device calibration")
+    dim = [np.clip(f.astype(np.float32) * (0.8 if i in (1, 2) else 1.0), 0, 255).astype(np.uint8) for i, f in enumerate(frames)]
+    srcs = [dev(f) for f in dim]
+    ptrs = [t.data_ptr() for t in srcs]
+    g_whole = whole.st.estimate_gains(ptrs, sw * 3, apply=True, stream=stream())[:n]
+    g_split = split.st.estimate_gains(ptrs, sw * 3, apply=True, stream=stream())[:n]
+    assert g_whole == g_split and g_whole[1] > g_whole[0], (g_whole, g_split)
+    _eq(split.compose([dim])[0], whole.compose([dim])[0], "after the run-time gain refresh (camera 2 is the split one)")

@@ -193,11 +193,11 @@ class Stitcher:
         check(lib().vsb_calibrate_rig_scaled(self._h, projection, pano_width, src_w, src_h, C.c_double(hfov_deg), g, C.c_double(compose_scale),
                                              int(bool(on_device))))
 
-    def calibrate_rig_split(self, projection, pano_width, n_cameras, src_w, src_h, hfov_deg=90.0, gains=None):
+    def calibrate_rig_split(self, projection, pano_width, n_cameras, src_w, src_h, hfov_deg=90.0, gains=None, on_device=False):
         g = None
         if gains is not None:
             g = (C.c_float * n_cameras)(*[float(v) for v in gains])
-        check(lib().vsb_calibrate_rig_split(self._h, projection, pano_width, n_cameras, src_w, src_h, C.c_double(hfov_deg), g))
+        check(lib().vsb_calibrate_rig_split(self._h, projection, pano_width, n_cameras, src_w, src_h, C.c_double(hfov_deg), g, int(bool(on_device))))
 
     def view_window(self, view):
         """-> (camera, x0, full width of the camera's warped image)"""

@@ -698,11 +698,15 @@ int vsb_split_plan(int projection, int pano_width, int n_cameras, int src_w, int
     return VSB_OK;
 }
 
+static int calibrate_rig_dev(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains,
+                             double compose_scale, int n_cameras = 0);
+
 int vsb_calibrate_rig_split(vsb_stitcher *s, int projection, int pano_width, int n_cameras, int src_w, int src_h, double hfov_deg,
-                            const float *gains)
+                            const float *gains, int on_device)
 {
     if (n_cameras < 1) return vsb::fail(VSB_ERR_INVALID, "calibrate_rig_split: n_cameras must be >= 1");
-    return calibrate_rig_host(s, projection, pano_width, src_w, src_h, hfov_deg, gains, 1.0, n_cameras);
+    return on_device ? calibrate_rig_dev(s, projection, pano_width, src_w, src_h, hfov_deg, gains, 1.0, n_cameras)
+                     : calibrate_rig_host(s, projection, pano_width, src_w, src_h, hfov_deg, gains, 1.0, n_cameras);
 }
 
 // ---- device-side calibration entry points -------------------------------------------------------------------------------------
@@ -742,7 +746,7 @@ int vsb_resize_linear_u8(const uint8_t *d_src, int sw, int sh, size_t src_pitch,
 // sinf / cosf itself, so the projection maps agree with the host path to ~1e-3 px, not bit for bit (the reference's own maps come
 // from the same kind of device code); everything downstream of the maps is exact.
 static int calibrate_rig_dev(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains,
-                             double compose_scale)
+                             double compose_scale, int n_cameras)
 {
     using namespace vsb;
     if (!s || pano_width <= 0 || src_w <= 0 || src_h <= 0) return fail(VSB_ERR_INVALID, "calibrate_rig_device: bad arguments");
@@ -756,7 +760,9 @@ static int calibrate_rig_dev(vsb_stitcher *s, int projection, int pano_width, in
     cudaGetDevice(&prev);
     cudaSetDevice(vsb_handle_device(s));
     struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev};
-    const int n = cfg.num_views;
+    const bool split = n_cameras > 0;   // cameras that wrap around +-pi become two views, as in calibrate_rig_host
+    const int n = split ? n_cameras : cfg.num_views;
+    if (split && (compose_scale != 1.0 || n > VSB_MAX_VIEWS)) return fail(VSB_ERR_INVALID, "calibrate_rig_split: bad arguments (compose_scale must be 1)");
     float scale = (float)(pano_width / (2.0 * 3.1415926535897932384626));
     CalibState *cs = new CalibState();
     cs->n = n; cs->projection = projection; cs->src_w = src_w; cs->src_h = src_h;
@@ -822,9 +828,27 @@ static int calibrate_rig_dev(vsb_stitcher *s, int projection, int pano_width, in
         if (r != VSB_OK) { free_seams(); return bail(r); }
         corners[2 * i] = roi[0]; corners[2 * i + 1] = roi[1]; sizes[2 * i] = roi[2]; sizes[2 * i + 1] = roi[3];
     }
-    r = vsb_prepare(s, corners.data(), sizes.data());
+    // the views: one per camera, or (split) the column windows plan_parts makes of the cameras that wrap around
+    std::vector<ViewPart> parts;
+    if (split) plan_parts(projection, scale, K.data(), R.data(), n, src_w, src_h, cfg.num_bands, corners.data(), sizes.data(), parts);
+    else for (int i = 0; i < n; ++i) parts.push_back({i, 0, map_roi[4 * i + 2]});
+    const int nv = (int)parts.size();
+    if (nv != cfg.num_views) {
+        free_seams();
+        return bail(fail(VSB_ERR_INVALID, "calibrate_rig_split: this rig needs %d views (%d cameras, %d of them split), the handle has %d: size it with vsb_split_plan", nv, n, nv - n, cfg.num_views));
+    }
+    if (split) {
+        std::vector<int> vc(2 * nv), vs(2 * nv);
+        for (int k = 0; k < nv; ++k) {
+            vc[2 * k] = corners[2 * parts[k].cam] + parts[k].x0; vc[2 * k + 1] = corners[2 * parts[k].cam + 1];
+            vs[2 * k] = parts[k].x1 - parts[k].x0; vs[2 * k + 1] = sizes[2 * parts[k].cam + 1];
+        }
+        r = vsb_prepare(s, vc.data(), vs.data());
+    } else {
+        r = vsb_prepare(s, corners.data(), sizes.data());
+    }
     if (r != VSB_OK) { free_seams(); return bail(r); }
-    for (int i = 0; i < n && r == VSB_OK; ++i) {
+    for (int i = 0, k = 0; i < n && r == VSB_OK; ++i) {
         const int w = map_roi[4 * i + 2], h = map_roi[4 * i + 3], sw = seam_sizes[2 * i], sh = seam_sizes[2 * i + 1];
         const size_t mp = ((size_t)w * 4 + 15) / 16 * 16;
         float *xm = nullptr, *ym = nullptr;
@@ -846,9 +870,13 @@ static int calibrate_rig_dev(vsb_stitcher *s, int projection, int pano_width, in
             }
         }
         if (r == VSB_OK) r = check_cuda(cudaStreamSynchronize(st), "calibrate_rig_device");
-        if (r == VSB_OK) r = vsb_init_view(s, i, seam, w, h, (size_t)w, corners[2 * i], corners[2 * i + 1], 1);
-        if (r == VSB_OK) r = vsb_set_maps(s, i, xm, ym, w, h, mp, 1, frame_sz[0], frame_sz[1]);
-        if (r == VSB_OK && gains) r = vsb_set_gain(s, i, gains[i]);
+        for (; k < nv && parts[k].cam == i && r == VSB_OK; ++k) {   // the camera's view(s): windows of its mask and maps, in place
+            const int x0 = parts[k].x0, pw = parts[k].x1 - x0;
+            r = vsb_init_view(s, k, seam + x0, pw, h, (size_t)w, corners[2 * i] + x0, corners[2 * i + 1], 1);
+            if (r == VSB_OK) r = vsb_set_maps(s, k, xm + x0, ym + x0, pw, h, mp, 1, frame_sz[0], frame_sz[1]);
+            if (r == VSB_OK && split) r = vsb_set_view_window(s, k, i, x0, w);
+            if (r == VSB_OK && gains) r = vsb_set_gain(s, k, gains[i]);
+        }
         cudaDeviceSynchronize();
         cudaFree(xm); cudaFree(ym); cudaFree(warped); cudaFree(seam); cudaFree(dil);
     }
@@ -975,9 +1003,17 @@ int vsb_estimate_gains(vsb_stitcher *s, const uint8_t *const *d_frames, size_t p
     cleanup();
     if (r != VSB_OK) return r;
     std::vector<double> &bb = g;
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n; ++i)
         if (gains_out) gains_out[i] = (float)bb[i];
-        if (apply) { r = vsb_set_gain(s, i, (float)bb[i]); if (r != VSB_OK) return r; }
+    if (apply) {   // one gain per CAMERA, installed on each of its views (a camera split by vsb_calibrate_rig_split has two)
+        vsb_config cfg;
+        r = vsb_get_config(s, &cfg);
+        for (int k = 0; k < cfg.num_views && r == VSB_OK; ++k) {
+            int cam = k;
+            r = vsb_view_window(s, k, &cam, nullptr, nullptr);
+            if (r == VSB_OK && cam >= 0 && cam < n) r = vsb_set_gain(s, k, (float)bb[cam]);
+        }
+        if (r != VSB_OK) return r;
     }
     return VSB_OK;
 }
