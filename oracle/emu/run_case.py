@@ -107,6 +107,16 @@ def main():
         if wire:
             want = og.s16_to_u8(want)
         res["pano"] += int(np.count_nonzero(outs[f].a != want))
+    if wire:   # the consumer epilogue on the device (vsb_consume: fixed-point cv::resize + BGR2RGB / letter-boxed BGR2YUV_I420, A/timed.cpp:254-315)
+        want_u8 = og.s16_to_u8(orig.compose(frames[0])[0])
+        ow, oh = 96, 64
+        ih = og.consumer_image_height(W, H, ow, oh, True)
+        rgb = E.Buffer(np.full((ih, ow, 3), 0xCD, np.uint8))
+        st.consume(outs[0].ptr, W * 3, ow, oh, B.CONSUME_RGB, rgb.ptr, ow * 3)
+        res["consume_rgb"] = int(np.count_nonzero(rgb.a != og.consume(want_u8, ow, oh, 0)))
+        yuv = E.Buffer(np.full(ow * oh * 3 // 2, 0xCD, np.uint8))
+        st.consume(outs[0].ptr, W * 3, ow, oh, B.CONSUME_I420, yuv.ptr, ow)
+        res["consume_i420"] = int(np.count_nonzero(yuv.a != og.consume(want_u8, ow, oh, 1).reshape(-1)))
     import hashlib
     res["pano_sha256"] = hashlib.sha256(b"".join(np.ascontiguousarray(o.a).tobytes() for o in outs)).hexdigest()[:16]
     res["pano_samples"] = int(F * H * W * 3)

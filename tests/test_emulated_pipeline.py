@@ -27,9 +27,10 @@ DEFAULT_CASES = {   # interpreted in parallel (one process each, ~70 s): started
 _procs = {}
 
 
-def _spawn(case):
+def _spawn(case, module="oracle.emu.run_case"):
     env = {k: v for k, v in os.environ.items() if k != "VSB200_LIB"}
-    return subprocess.Popen([sys.executable, "-m", "oracle.emu.run_case", json.dumps(case)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, env=env)
+    cmd = [sys.executable, "-m", module] + ([json.dumps(case)] if case is not None else [])
+    return subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, env=env)
 
 
 def _collect(p):
@@ -59,6 +60,7 @@ def _default(name):
         subprocess.run([sys.executable, "-c", "from oracle.emu import runtime as E; E.start()"], cwd=ROOT, check=True, capture_output=True, timeout=900)
         for k, case in DEFAULT_CASES.items():
             _procs[k] = _spawn(case)
+        _procs["voronoi"] = _spawn(None, "oracle.emu.run_voronoi_case")
     return _collect(_procs[name])
 
 
@@ -88,6 +90,23 @@ def test_product_library_wire_formats_on_the_emulated_runtime():
     res = _default("wire")
     assert res["error"] is None and res["pano"] == 0 and res["warped"] == 0, res
     assert "k_remap_stage1_nv12" in " ".join(res["launched"]), res["launched"]
+    # ... and the consumer epilogue on that CV_8UC3 panorama (vsb_consume: the reference's fixed-point cv::resize, then BGR2RGB or the
+    # letter-boxed BGR2YUV_I420 frame the encoder is fed, A/timed.cpp:254-315) against og.consume
+    assert res["consume_rgb"] == 0 and res["consume_i420"] == 0, res
+
+
+def test_device_seam_finder_on_the_emulated_runtime():
+    """vsb_voronoi_seams_device (k_vor_columns + k_vor_decide, interpreted from the product's PTX) on the seam-scale masks of a 6-view
+    rig: the masks it leaves are the ones the REFERENCE's own VoronoiSeamFinder leaves (tests/golden/reference_cpu.npz), bit for bit."""
+    import hashlib
+    import numpy as np
+    res = _default("voronoi")
+    assert res["rc"] == 0 and res["error"] is None and set(res["values"]) <= {0, 255}, res
+    assert any("k_vor_columns" in k for k in res["launched"]) and any("k_vor_decide" in k for k in res["launched"]), res["launched"]
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_cpu.npz"))
+    n, _, _, pano, proj = res["rig"]
+    want = [hashlib.sha256(np.ascontiguousarray(gold[f"voronoi_{n}_{pano}_{proj}_{i}"]).tobytes()).hexdigest() for i in range(n)]
+    assert res["packed_sha256"] == want
 
 
 def test_product_library_compose_scale_on_the_emulated_runtime():
