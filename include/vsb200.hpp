@@ -244,10 +244,13 @@ public:
        apply = true installs them (what A/timed.cpp:94 multiplies by) */
     std::vector<float> estimateGains(const std::vector<DeviceMat> &frames, bool apply, Stream stream = 0)
     {
-        if ((int)frames.size() != n_) throw Error(VSB_ERR_INVALID, "vsb200: estimateGains: one frame per view");
-        std::vector<const uint8_t *> fp(n_);
-        for (int i = 0; i < n_; ++i) { fp[i] = (const uint8_t *)frames[i].data; if (frames[i].step != frames[0].step) throw Error(VSB_ERR_INVALID, "vsb200: estimateGains: frames must share one pitch"); }
-        std::vector<float> g(n_);
+        /* one frame per CAMERA (= per view, unless calibrateRigSplit made two views of a camera) */
+        int n_cam = 0;
+        for (int v = 0; v < n_; ++v) n_cam = viewCamera(v) + 1 > n_cam ? viewCamera(v) + 1 : n_cam;
+        if ((int)frames.size() != n_cam) throw Error(VSB_ERR_INVALID, "vsb200: estimateGains: one frame per camera");
+        std::vector<const uint8_t *> fp(n_cam);
+        for (int i = 0; i < n_cam; ++i) { fp[i] = (const uint8_t *)frames[i].data; if (frames[i].step != frames[0].step) throw Error(VSB_ERR_INVALID, "vsb200: estimateGains: frames must share one pitch"); }
+        std::vector<float> g(n_cam);
         check(vsb_estimate_gains(h_, fp.data(), frames[0].step, g.data(), apply ? 1 : 0, stream));
         return g;
     }
