@@ -374,6 +374,21 @@ def test_live_gain_compensator_on_other_layouts(og):
         assert np.array_equal(og.gain_compensator_feed(imgs, masks, corners, sizes), vr.gain_compensator_feed(imgs, masks, corners, sizes)), (seed, n)
 
 
+def test_live_pyramids_on_degenerate_shapes(og):
+    """pyrDown / pyrUp on planes of one or two rows / columns and other tiny shapes (where every sample is a border sample: the
+    top levels of a 7-band pyramid look like this): the oracle's border index rules against the reference's CPU pyramids, exact
+    through the half-up twins, ties only through the CUDA rounding."""
+    vr = _vr()
+    rng = np.random.default_rng(3)
+    for shape in ((1, 1), (1, 7), (7, 1), (2, 2), (3, 5), (5, 3), (4, 64), (2, 9), (9, 2), (3, 3), (1, 2), (2, 1)):
+        a = rng.integers(-300, 600, shape + (3,)).astype(np.int16)
+        assert np.array_equal(og.pyr_down_s16_halfup(a), vr.pyr_down(a, vr.T_S16C3)), shape
+        assert np.array_equal(og.pyr_up_s16_halfup(a), vr.pyr_up(a, vr.T_S16C3)), shape
+        # CUDA rounding (half-even) against the CPU's (half-up): exact .5 ties differ by one, nothing else (too few samples for a rate)
+        assert np.abs(og.pyr_down_s16(a).astype(int) - vr.pyr_down(a, vr.T_S16C3)).max() <= 1, shape
+        assert np.abs(og.pyr_up_s16(a).astype(int) - vr.pyr_up(a, vr.T_S16C3)).max() <= 1, shape
+
+
 def test_live_small_rig_compose_vs_oracle_c(og):
     """Whole path, oracle-G vs the CPU compose on the reference's OpenCV (same static inputs): masks identical, pano close.
     Not a +-1 pin (fixed-point CPU remap + tie rounding) -- a gross-error tripwire."""
