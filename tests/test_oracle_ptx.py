@@ -146,3 +146,34 @@ def test_interpreter_fma_is_correctly_rounded():
     assert float(P.round_fraction_to_f32(__import__("fractions").Fraction(2 ** 24 + 3))) == 2.0 ** 24 + 4
     assert float(P.fma_f32(np.float32(2.0 ** -100), np.float32(2.0 ** -40), np.float32(0))) == 2.0 ** -140
     assert P.fma_f32(np.float32(3.0), np.float32(2.0), np.float32(-6.0)) == 0 and not np.signbit(P.fma_f32(np.float32(3.0), np.float32(2.0), np.float32(-6.0)))
+
+
+def test_live_reference_pyramid_kernels_on_degenerate_shapes(og):
+    """The reference's pyrDown<short3> / pyrUp<short3> kernels (interpreted PTX) on planes where every sample is a border sample --
+    one row, one column, 2 x 2 ... (the top levels of a deep pyramid) -- against oracle-G's border index rules: bit for bit."""
+    if not PC.available():
+        pytest.skip("oracle/_ref/ptx not built (needs /root/reference and nvcc: make -C oracle -f ref_ptx.mk)")
+    rng = np.random.default_rng(41)
+    for shape in ((1, 1), (1, 7), (7, 1), (2, 2), (3, 5), (5, 3), (2, 9), (9, 2), (3, 3), (1, 2), (2, 1), (4, 33)):
+        a = rng.integers(-300, 600, shape + (3,)).astype(np.int16)
+        assert _same(PC._pyr_down("pyrDownI6short3", a, 6), og.pyr_down_s16(a)), f"pyrDown {shape}"
+        assert _same(PC.pyr_up_ptx({"s16": a})["s16"], og.pyr_up_s16(a)), f"pyrUp {shape}"
+    for shape in ((1, 1), (1, 5), (6, 1), (2, 2), (3, 4)):
+        w = rng.random(shape).astype(np.float32)
+        assert _same(PC._pyr_down("pyrDownIfNS", w, 4), og.pyr_down_f32(w)), f"pyrDown<float> {shape}"
+
+
+def test_live_product_pyramid_primitives_on_degenerate_shapes():
+    """The PRODUCT's pyramid primitives (vsb_pyr_down_s16c3 / vsb_pyr_up_s16c3 / vsb_pyr_down_f32, compiled to PTX with the product's
+    flags) against the REFERENCE's kernels on the same degenerate planes, both interpreted: identical bytes."""
+    from oracle import ptx_product as PP
+    if not PC.available() or not PP.available():
+        pytest.skip("needs oracle/_ref/ptx (reference kernels) and nvcc (product PTX)")
+    rng = np.random.default_rng(43)
+    for shape in ((1, 1), (1, 7), (7, 1), (2, 2), (3, 5), (5, 3), (2, 9), (1, 2), (2, 1)):
+        a = rng.integers(-300, 600, shape + (3,)).astype(np.int16)
+        w = rng.random(shape).astype(np.float32)
+        mine = PP.pyr_down({"s16": a, "f32": w})
+        assert _same(mine["s16"], PC._pyr_down("pyrDownI6short3", a, 6)), f"pyrDown {shape}"
+        assert _same(mine["f32"], PC._pyr_down("pyrDownIfNS", w, 4)), f"pyrDown<float> {shape}"
+        assert _same(PP.pyr_up({"s16": a})["s16"], PC.pyr_up_ptx({"s16": a})["s16"]), f"pyrUp {shape}"
