@@ -92,21 +92,26 @@ def main():
         gmx, gmy = read(4, i, 0, (h, w), np.float32), read(5, i, 0, (h, w), np.float32)
         res["mesh_maps"] += int(np.count_nonzero((gmx.view(np.uint32) != omx.view(np.uint32)) & ~(np.isnan(gmx) & np.isnan(omx))))
         res["mesh_maps"] += int(np.count_nonzero((gmy.view(np.uint32) != omy.view(np.uint32)) & ~(np.isnan(gmy) & np.isnan(omy))))
-        done0 = read(7, i, 0, (bh, bw), np.uint8).astype(bool)
+        fast = nb >= 3                                         # below 3 bands the generic per-level kernels run and every sample is computed
+        done0 = read(7, i, 0, (bh, bw), np.uint8).astype(bool) if fast else np.ones((bh, bw), bool)
         ov = np.ascontiguousarray(orig.warp_view(c, frames[0][c])[:, x0:x0 + w])
         crop = done0[g["top"]:g["top"] + h, g["left"]:g["left"] + w]
         res["warped"] += int(np.count_nonzero(read(0, i, 0, (h, w, 3), np.uint8)[crop] != ov[crop]))
         gk = og.border_reflect_u8c3_to_s16(ov, g["top"], g["bottom"], g["left"], g["right"])
         res["gauss0"] += int(np.count_nonzero(read(1, i, 0, (bh, bw, 3), np.int16)[done0] != gk[done0]))
         g2 = og.pyr_down_s16(og.pyr_down_s16(gk))
-        done2 = read(6, i, 0, (bh >> 2, bw >> 2), np.uint8).astype(bool)
-        res["gauss2"] += int(np.count_nonzero(read(1, i, 2, (bh >> 2, bw >> 2, 3), np.int16)[done2] != g2[done2]))
+        done2 = read(6, i, 0, (bh >> 2, bw >> 2), np.uint8).astype(bool) if fast else np.ones((bh >> 2, bw >> 2), bool)
+        if nb >= 2:
+            res["gauss2"] += int(np.count_nonzero(read(1, i, 2, (bh >> 2, bw >> 2, 3), np.int16)[done2] != g2[done2]))
     res["pano"] = 0
     for f in range(F):
         want, _ = orig.compose(frames[f])
         if wire:
             want = og.s16_to_u8(want)
         res["pano"] += int(np.count_nonzero(outs[f].a != want))
+        if os.environ.get("VSB_EMU_DUMP"):               # debugging aid: the two panoramas side by side
+            np.save(os.environ["VSB_EMU_DUMP"] + f"_got{f}.npy", outs[f].a)
+            np.save(os.environ["VSB_EMU_DUMP"] + f"_want{f}.npy", want)
     if wire:   # the consumer epilogue on the device (vsb_consume: fixed-point cv::resize + BGR2RGB / letter-boxed BGR2YUV_I420, A/timed.cpp:254-315)
         want_u8 = og.s16_to_u8(orig.compose(frames[0])[0])
         ow, oh = 96, 64

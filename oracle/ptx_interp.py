@@ -500,13 +500,22 @@ def _frame(kernel, params, mem, shared_mem, shared_off, special):
             if name == "ld":
                 space = op[1]
                 nbytes = _WIDTH[ty] // 8
+
+                def widen(reg, v):
+                    # a signed load narrower than its destination register is sign-extended to the register's width (ld.shared.s16 %r5, ...:
+                    # PTX ISA, "ld": the loaded value is converted to the destination register's size)
+                    if ty in ("s8", "s16", "s32") and type(reg) is str:
+                        rw = 64 if reg.startswith("%rd") else (16 if reg.startswith("%rs") else (32 if reg.startswith("%r") else 0))
+                        if rw > _WIDTH[ty]:
+                            return _mask(_signed(v, _WIDTH[ty]), rw)
+                    return v
                 if type(ops[0]) is str and ops[0].startswith("{"):
                     regs = [r.strip() for r in ops[0][1:-1].split(",")]
                     base, off = addr_of(ops[1])
                     for k, r in enumerate(regs):
-                        R[r] = to_reg(ty, ld(space, nbytes, ("M", base, off + k * nbytes)))
+                        R[r] = widen(r, to_reg(ty, ld(space, nbytes, ("M", base, off + k * nbytes))))
                 else:
-                    R[ops[0]] = to_reg(ty, ld(space, nbytes, ops[1]))
+                    R[ops[0]] = widen(ops[0], to_reg(ty, ld(space, nbytes, ops[1])))
                 continue
             if name == "st":
                 nbytes = _WIDTH[ty] // 8

@@ -23,6 +23,7 @@ DEFAULT_CASES = {   # interpreted in parallel (one process each, ~70 s): started
     "compose_scale": dict(n_views=4, src_w=61, src_h=41, pano_width=192, num_bands=3, compose_scale=0.8),
     "split": dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3, split=True),
     "wire": dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3, wire=True),
+    "bands2": dict(n_views=4, src_w=48, src_h=24, pano_width=192, num_bands=2),
 }
 _procs = {}
 
@@ -166,3 +167,12 @@ def test_device_gain_estimation_on_the_emulated_runtime():
     assert res["rc"] == 0 and res["error"] is None and any("k_gain_pairs" in k for k in res["launched"]), res
     want = np.load(os.path.join(ROOT, "tests", "golden", "reference_cpu.npz"))["gain_compensator"]
     assert [float.fromhex(h) for h in res["gains_hex"]] == [float(v) for v in want]
+
+
+def test_generic_path_below_three_bands_on_the_emulated_runtime():
+    """num_bands = 2: the generic per-level kernels (k_pyr_down<u8> / <s16>, k_legacy_blend_collapse: Laplacian, weighted add,
+    normalise, collapse, mask and crop of every level in one kernel) instead of the fused fast path -- bit-identical to oracle-G."""
+    res = _default("bands2")
+    assert res["error"] is None and res["roi_equal"] and res["warped"] == 0 and res["gauss0"] == 0 and res["gauss2"] == 0, res
+    assert res["pano"] == 0 and res["pano_nonzero"] > res["pano_samples"] // 2, res
+    assert "k_legacy_blend_collapse" in " ".join(res["launched"]) and res["launch_count"] == 5, res["launched"]
