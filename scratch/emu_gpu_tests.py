@@ -6,6 +6,7 @@ process in parallel, e.g.  for c in small4 cyl5 nolocal6 wire; do python scratch
 
     python scratch/emu_gpu_tests.py scale [case ...]     tests/test_gpu_vsb_compose_scale.py
     python scratch/emu_gpu_tests.py split [case ...]     tests/test_gpu_vsb_wrap_split.py
+    python scratch/emu_gpu_tests.py parity [case ...]    the calibration tests of tests/test_gpu_parity.py
 """
 import os
 import sys
@@ -84,6 +85,21 @@ if which == "scale":
     if not picks or "wire" in picks:
         T.test_scaled_wire_formats_and_host_path(fake_torch, og)
         print("ok: test_scaled_wire_formats_and_host_path", round(time.time() - t0), "s", flush=True)
+elif which == "parity":
+    # the calibration tests of tests/test_gpu_parity.py (host and device calibration were restructured for compose_scale / the split)
+    import tests.test_gpu_parity as T
+    T.CASES.update({
+        "small4": dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3, enable_local=True),
+        "small6_nolocal": dict(n_views=4, src_w=48, src_h=36, pano_width=192, num_bands=3, enable_local=False),
+        "cyl5": dict(n_views=4, src_w=48, src_h=36, pano_width=208, num_bands=3, enable_local=True, projection=1),
+    })
+    for case in (picks or ["small4", "small6_nolocal", "cyl5"]):
+        if case in ("small4", "small6_nolocal", "cyl5"):
+            T.test_calibration_products_match_oracle(fake_torch, og, case)
+            print("ok: test_calibration_products_match_oracle", case, round(time.time() - t0), "s", flush=True)
+    if not picks or "device" in picks:
+        T.test_device_calibration_products_and_compose(fake_torch, og, "small6_nolocal")
+        print("ok: test_device_calibration_products_and_compose small6_nolocal", round(time.time() - t0), "s", flush=True)
 else:
     import tests.test_gpu_vsb_wrap_split as T
     T.CASES.update({
