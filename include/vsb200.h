@@ -159,6 +159,17 @@ int vsb_split_plan(int projection, int pano_width, int n_cameras, int src_w, int
 int vsb_calibrate_rig_split(vsb_stitcher *s, int projection, int pano_width, int n_cameras, int src_w, int src_h, double hfov_deg,
                             const float *gains, int on_device);
 int vsb_view_window(const vsb_stitcher *s, int view, int *camera, int *x0, int *full_w);
+/* ---- stitch_calib with its own constants (A/calibration.cpp:256-305; A/defs.h:51-53: WORK_MEGAPIX 0.6, SEAM_MEAGPIX 0.01,
+ *      COMPOSE_MEGAPIX 1.4).  vsb_ref_scales: work_scale / compose_scale = min(1, sqrt(MEGAPIX * 1e6 / area)) (negative: 1).
+ *      vsb_rig_camera_work: calibrateCameras at a work scale (ppx = w * work_scale / 2, focal = ppx / tan(hfov / 2), doubles), then
+ *      focal, ppx, ppy *= aspect.  vsb_calibrate_rig_megapix: the calibration with the sphere radius the REFERENCE uses --
+ *      warped_image_scale = (float)cameras[0].focal at work scale, seam_work_aspect = seam_scale / work_scale, compose_work_aspect =
+ *      compose_scale / work_scale -- instead of a pano_width; with (0.6, 1.4) it is the reference's default panorama, frames resized
+ *      on the device as vsb_calibrate_rig_scaled does. ------------------------------------------------------------------------ */
+int vsb_ref_scales(int src_w, int src_h, double work_megapix, double compose_megapix, double *work_scale, double *compose_scale);
+int vsb_rig_camera_work(int n_views, int i, int src_w, int src_h, double hfov_deg, double work_scale, double aspect, float K[9], float R[9]);
+int vsb_calibrate_rig_megapix(vsb_stitcher *s, int projection, int src_w, int src_h, double hfov_deg, const float *gains,
+                              double work_megapix, double compose_megapix, int on_device);
 int vsb_rig_info_get(const vsb_stitcher *s, vsb_rig_info *out);
 int vsb_get_config(const vsb_stitcher *s, vsb_config *out);
 

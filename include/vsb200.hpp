@@ -225,6 +225,13 @@ public:
         check(vsb_calibrate_rig_scaled(h_, projection, pano_width, src.width, src.height, hfov_deg, gains, compose_scale, on_device ? 1 : 0));
         next_view_ = n_;
     }
+    /* stitch_calib with its own WORK_MEGAPIX / COMPOSE_MEGAPIX constants (defs.h:51-53): the reference's default panorama geometry */
+    void calibrateRigMegapix(int projection, Size src, double work_megapix = 0.6, double compose_megapix = 1.4, bool on_device = false,
+                             double hfov_deg = 90.0, const float *gains = 0)
+    {
+        check(vsb_calibrate_rig_megapix(h_, projection, src.width, src.height, hfov_deg, gains, work_megapix, compose_megapix, on_device ? 1 : 0));
+        next_view_ = n_;
+    }
     /* wrapAround (defs.h:25) without a panorama-wide ROI: how many views a rig of n_cameras needs when every camera that looks across
        +-pi is installed as two column windows of its warped image (construct the blender with that many views), and the calibration
        that does it (gains per camera).  viewCamera(v) = the camera whose frame -- and whose mesh -- view v takes. */

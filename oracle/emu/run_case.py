@@ -39,7 +39,13 @@ def main():
     nv = len(plan)
     st = B.Stitcher(nv, nb, True, F)
     cs = float(case.get("compose_scale", 1.0))             # != 1: sw x sh are the full frames, resized on the device in front of remap #1
-    if split:
+    ws = 1.0
+    if case.get("megapix"):                                # stitch_calib's own scales: [WORK_MEGAPIX, COMPOSE_MEGAPIX]; pano_width is ignored (0)
+        wm, cm = case["megapix"]
+        ws, cs = op.ref_scales(sw, sh, wm, cm)
+        pano = 0
+        st.calibrate_rig_megapix(proj, sw, sh, wm, cm, 90.0, gains, on_device=bool(case.get("device_calibration")))
+    elif split:
         st.calibrate_rig_split(proj, pano, n, sw, sh, 90.0, gains, on_device=bool(case.get("device_calibration")))
     elif cs != 1.0:
         st.calibrate_rig_scaled(proj, pano, sw, sh, cs, 90.0, gains, on_device=bool(case.get("device_calibration")))
@@ -72,7 +78,7 @@ def main():
     t_compose = time.time() - t0
     launched = [name for name, _, _ in E.stats()["launches"][n0:]]
 
-    orig = op.OracleRig(n, sw, sh, pano, projection=proj, num_bands=nb, enable_local=True, gains=gains, compose_scale=cs)
+    orig = op.OracleRig(n, sw, sh, pano, projection=proj, num_bands=nb, enable_local=True, gains=gains, compose_scale=cs, work_scale=ws)
     for i in range(n):
         orig.set_mesh(i, *S.mesh(*orig.sizes[i]))
 

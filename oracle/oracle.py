@@ -71,6 +71,14 @@ def rig_camera_scaled(n_views, i, src_w, src_h, hfov_deg, compose_work_aspect):
     return K.reshape(3, 3), R.reshape(3, 3)
 
 
+def rig_camera_work(n_views, i, src_w, src_h, hfov_deg, work_scale, aspect):
+    """calibrateCameras at a work scale, then focal / ppx / ppy *= aspect (doubles), as float K"""
+    K = np.zeros(9, np.float32)
+    R = np.zeros(9, np.float32)
+    lib().og_rig_camera_work(n_views, i, src_w, src_h, C.c_double(hfov_deg), C.c_double(work_scale), C.c_double(aspect), _p(K, C.c_float), _p(R, C.c_float))
+    return K.reshape(3, 3), R.reshape(3, 3)
+
+
 def projector(K, R):
     K = _f32(K).reshape(9)
     R = _f32(R).reshape(9)

@@ -119,6 +119,19 @@ void og_rig_camera_scaled(int n_views, int i, int src_w, int src_h, double hfov_
     K[0] = (float)focal; K[2] = (float)ppx; K[4] = (float)(focal * 1.0); K[5] = (float)ppy;
 }
 
+/* calibrateCameras at a work scale (A/calibration.cpp:54-60: ppx = (full.width * work_scale) / 2, focal = focal_tmp * ppx, doubles),
+ * then focal, ppx, ppy *= aspect (:168-172: compose_work_aspect = compose_scale / work_scale; 1 for the work-scale camera itself) and
+ * K().convertTo(CV_32F).  work_scale = aspect = 1 gives og_rig_camera; work_scale = 1 gives og_rig_camera_scaled. */
+void og_rig_camera_work(int n_views, int i, int src_w, int src_h, double hfov_deg, double work_scale, double aspect, float K[9], float R[9])
+{
+    const double PI = 3.1415926535897932384626;
+    og_rig_camera(n_views, i, src_w, src_h, hfov_deg, K, R);
+    double ppx = (src_w * work_scale) / 2.0, ppy = (src_h * work_scale) / 2.0;
+    double focal = (1.0 / tan(hfov_deg * PI / 180.0 * 0.5)) * ppx;
+    focal *= aspect; ppx *= aspect; ppy *= aspect;
+    K[0] = (float)focal; K[2] = (float)ppx; K[4] = (float)(focal * 1.0); K[5] = (float)ppy;
+}
+
 static void mat3_mul_d(const float *a, const float *b, float *c)
 {
     for (int i = 0; i < 3; ++i)

@@ -24,6 +24,7 @@ enum { OG_PROJ_SPHERICAL = 0, OG_PROJ_CYLINDRICAL = 1 };
 
 /* ---------------------------------------------------------------- camera rig + projector */
 void og_rig_camera(int n_views, int i, int src_w, int src_h, double hfov_deg, float K[9], float R[9]);
+void og_rig_camera_work(int n_views, int i, int src_w, int src_h, double hfov_deg, double work_scale, double aspect, float K[9], float R[9]);
 void og_rig_camera_scaled(int n_views, int i, int src_w, int src_h, double hfov_deg, double compose_work_aspect, float K[9], float R[9]);
 void og_projector(const float K[9], const float R[9], float k_rinv[9], float r_kinv[9], float rinv[9]);
 /* roi = {tl_x, tl_y, width, height} with width = br_x - tl_x + 1 (size of the maps buildMaps makes) */

@@ -35,10 +35,25 @@ def synthetic_mesh(W, H, rows=10, cols=10, phase=0.0):
     return (mx + dx.astype(np.float32)).astype(np.float32), (my + dy.astype(np.float32)).astype(np.float32)
 
 
+def ref_scales(src_w, src_h, work_megapix=0.6, compose_megapix=1.4):
+    """work_scale and compose_scale as stitch_calib / warpImages derive them (calibration.cpp:270-277,140-143; defaults A/defs.h:51-53):
+    min(1, sqrt(MEGAPIX * 1e6 / area)), a negative MEGAPIX meaning scale 1."""
+    area = src_w * src_h
+    ws = 1.0 if work_megapix < 0 else min(1.0, math.sqrt(work_megapix * 1e6 / area))
+    cs = 1.0 if compose_megapix <= 0 else min(1.0, math.sqrt(compose_megapix * 1e6 / area))
+    return ws, cs
+
+
 class OracleRig:
     def __init__(self, n_views, src_w, src_h, pano_width, projection=og.PROJ_SPHERICAL, num_bands=5,
-                 enable_local=True, gains=None, hfov_deg=90.0, compose_scale=1.0):
+                 enable_local=True, gains=None, hfov_deg=90.0, compose_scale=1.0, work_scale=1.0):
+        """pano_width > 0: the sphere radius is pano_width / 2 pi (this repository's parametrisation; work_scale must be 1).
+        pano_width = 0: the reference's own -- warped_image_scale = (float)cameras[0].focal at work scale (stitch_calib,
+        calibration.cpp:283-289), which with work_scale / compose_scale from WORK_MEGAPIX / COMPOSE_MEGAPIX (ref_scales below) is
+        stitch_calib's default geometry."""
         self.n, self.src_w, self.src_h = n_views, src_w, src_h
+        self.work_scale = float(work_scale)
+        assert pano_width > 0 or pano_width == 0, pano_width
         # compose_scale (calibration.cpp:137-205, timed.cpp:74-81), followed literally: when it is more than 0.1 away from 1 the frames
         # are cuda::resize'd per frame to cvRound(full * scale) (:159-160 = the dsize cuda::resize computes) and the blender is sized
         # from that; the maps and masks are ALWAYS built for (int)(full * scale) (:204); the cameras and the warper are always scaled.
@@ -50,15 +65,17 @@ class OracleRig:
             self.comp_w, self.comp_h = int(np.rint(src_w * self.compose_scale)), int(np.rint(src_h * self.compose_scale))
         self.map_src = (int(src_w * self.compose_scale), int(src_h * self.compose_scale))   # img_size of buildMaps / the mask warp
         self.projection, self.enable_local = projection, enable_local
-        self.scale = np.float32(pano_width / (2.0 * 3.1415926535897932384626))
         self.gains = [1.0] * n_views if gains is None else [float(g) for g in gains]
-        self.K, self.R = zip(*[og.rig_camera(n_views, i, src_w, src_h, hfov_deg) for i in range(n_views)])
+        # cameras at work scale (calibrateCameras, calibration.cpp:28-68); warped_image_scale (:283)
+        self.K, self.R = zip(*[og.rig_camera_work(n_views, i, src_w, src_h, hfov_deg, self.work_scale, 1.0) for i in range(n_views)])
+        self.scale = np.float32(pano_width / (2.0 * 3.1415926535897932384626)) if pano_width > 0 else np.float32(self.K[0][0, 0])
 
         # ---- seam scale: warp all-255 masks (NEAREST / CONSTANT), Voronoi (calibration.cpp:92-135)
         seam_scale = min(1.0, math.sqrt(SEAM_MEGAPIX * 1e6 / (src_w * src_h)))
+        seam_work_aspect = seam_scale / self.work_scale                                  # :280
         seam_w, seam_h = int(np.rint(src_w * seam_scale)), int(np.rint(src_h * seam_scale))
-        seam_warp_scale = np.float32(float(self.scale) * seam_scale)
-        swa = np.float32(seam_scale)
+        seam_warp_scale = np.float32(float(self.scale) * seam_work_aspect)                # static_cast<float>(warped_image_scale * seam_work_aspect), :103
+        swa = np.float32(seam_work_aspect)
         seam_masks, seam_corners, seam_sizes = [], [], []
         self.seam_scale, self.seam_size, self.seam_maps = seam_scale, (seam_w, seam_h), []
         ones = np.full((seam_h, seam_w), 255, np.uint8)
@@ -75,10 +92,11 @@ class OracleRig:
         self.seam_masks, self.seam_corners, self.seam_sizes = seam_masks, seam_corners, seam_sizes
 
         # ---- compose scale: ROIs, prepare, maps, masks, init_gpu (calibration.cpp:137-246)
-        if self.compose_scale != 1.0:
+        compose_work_aspect = self.compose_scale / self.work_scale                        # :148
+        if compose_work_aspect != 1.0:
             # warper scale: warped_image_scale * static_cast<float>(compose_work_aspect) (:151); cameras: focal, ppx, ppy *= aspect (:168-172)
-            self.scale = np.float32(self.scale * np.float32(self.compose_scale))
-            self.K, self.R = zip(*[og.rig_camera_scaled(n_views, i, src_w, src_h, hfov_deg, self.compose_scale) for i in range(n_views)])
+            self.scale = np.float32(self.scale * np.float32(compose_work_aspect))
+            self.K, self.R = zip(*[og.rig_camera_work(n_views, i, src_w, src_h, hfov_deg, self.work_scale, compose_work_aspect) for i in range(n_views)])
         prep = [og.warp_roi(projection, self.scale, self.K[i], self.R[i], self.comp_w, self.comp_h) for i in range(n_views)]   # :176-178
         self.rois = [og.warp_roi(projection, self.scale, self.K[i], self.R[i], *self.map_src) for i in range(n_views)]         # buildMaps' own roi
         self.corners = [r[:2] for r in prep]                 # where the blender puts view i

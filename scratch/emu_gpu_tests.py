@@ -82,6 +82,11 @@ if which == "scale":
     if not picks or "device" in picks:
         T.test_scaled_device_calibration_and_low_level_route(fake_torch, og)
         print("ok: test_scaled_device_calibration_and_low_level_route", round(time.time() - t0), "s", flush=True)
+    T.REF_RIG, T.REF_MEGAPIX = (4, 64, 40, 3), (0.0015, 0.0016)
+    for dev_cal in (False, True):
+        if not picks or ("megapix_dev" if dev_cal else "megapix") in picks:
+            T.test_reference_default_scales_at_1080p(fake_torch, og, dev_cal)
+            print("ok: test_reference_default_scales_at_1080p on_device =", dev_cal, round(time.time() - t0), "s", flush=True)
     if not picks or "wire" in picks:
         T.test_scaled_wire_formats_and_host_path(fake_torch, og)
         print("ok: test_scaled_wire_formats_and_host_path", round(time.time() - t0), "s", flush=True)

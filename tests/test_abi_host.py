@@ -146,6 +146,28 @@ def test_split_plan_of_the_baseline_configs(vsb, og, rig, views):
     assert lib.vsb_calibrate_rig_split(None, 0, pano, n, sw, sh, C.c_double(90.0), None, 0) == -1
 
 
+def test_reference_scales_and_work_scale_cameras(vsb, og):
+    """vsb_ref_scales / vsb_rig_camera_work (host only): stitch_calib's work_scale and compose_scale from its MEGAPIX constants, and the
+    cameras of calibrateCameras at a work scale, against the oracle's restatement; the special cases reduce to the existing functions."""
+    from oracle import pipeline as op
+    assert vsb.ref_scales(1920, 1080) == op.ref_scales(1920, 1080) == ((0.6e6 / (1920 * 1080)) ** 0.5, (1.4e6 / (1920 * 1080)) ** 0.5)
+    assert vsb.ref_scales(640, 480, -1.0, -1.0) == (1.0, 1.0) and vsb.ref_scales(320, 240) == (1.0, 1.0)          # small frames: min(1, .)
+    assert vsb.lib().vsb_ref_scales(0, 10, C.c_double(0.6), C.c_double(1.4), None, None) == -1
+    ws, cs = vsb.ref_scales(1920, 1080)
+    for (n, sw, sh) in ((6, 1920, 1080), (4, 320, 240), (12, 3840, 2160)):
+        for i in range(n):
+            for (w_, a_) in ((1.0, 1.0), (ws, 1.0), (ws, cs / ws), (1.0, 0.75)):
+                K, R = vsb.rig_camera_work(n, i, sw, sh, 90.0, w_, a_)
+                Ko, Ro = og.rig_camera_work(n, i, sw, sh, 90.0, w_, a_)
+                assert np.array_equal(np.float32(K), Ko.reshape(9)) and np.array_equal(np.float32(R), Ro.reshape(9))
+            assert vsb.rig_camera_work(n, i, sw, sh, 90.0, 1.0, 1.0) == vsb.rig_camera(n, i, sw, sh)
+            assert vsb.rig_camera_work(n, i, sw, sh, 90.0, 1.0, 0.75) == vsb.rig_camera_scaled(n, i, sw, sh, 90.0, 0.75)
+    # the reference's default panorama of 6 x 1080p (WORK 0.6, COMPOSE 1.4): sphere radius = the work-scale focal length x compose_work_aspect
+    rig = op.OracleRig(6, 1920, 1080, 0, num_bands=5, compose_scale=cs, work_scale=ws)
+    assert abs(float(rig.scale) - 960.0 * cs) < 0.05 and (rig.comp_w, rig.comp_h) == (1578, 887) and rig.map_src == (1577, 887)
+    assert rig.roi_final[2] in range(4950, 4960) and rig.num_bands == 5
+
+
 def test_host_voronoi_matches_reference(vsb, og):
     from tests.golden import make_golden as G
     gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_cpu.npz"))

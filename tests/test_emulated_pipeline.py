@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 DEFAULT_CASES = {   # interpreted in parallel (one process each, ~70 s): started together by the first test that needs one
     "base": dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3),
-    "compose_scale": dict(n_views=4, src_w=61, src_h=41, pano_width=192, num_bands=3, compose_scale=0.8),
+    "megapix": dict(n_views=4, src_w=64, src_h=40, pano_width=0, num_bands=3, megapix=[0.0015, 0.0016]),
     "split": dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3, split=True),
     "wire": dict(n_views=4, src_w=48, src_h=32, pano_width=192, num_bands=3, wire=True),
     "bands2": dict(n_views=4, src_w=48, src_h=24, pano_width=192, num_bands=2),
@@ -110,11 +110,13 @@ def test_device_seam_finder_on_the_emulated_runtime():
     assert res["packed_sha256"] == want
 
 
-def test_product_library_compose_scale_on_the_emulated_runtime():
-    """compose_scale != 1 (A/calibration.cpp:137-205, A/timed.cpp:74-81) through the shipped library: vsb_calibrate_rig_scaled (scaled
-    cameras and warper, blender sized from cvRound(full * scale) = (49, 33), maps and masks built for (int)(full * scale) = (48, 32) --
-    the reference's own mismatch, reproduced) and the per-frame cuda::resize in front of remap #1 (k_prescale), bit-identical to oracle-G."""
-    res = _default("compose_scale")
+def test_product_library_reference_scales_on_the_emulated_runtime():
+    """stitch_calib's own scales through the shipped library (vsb_calibrate_rig_megapix; A/calibration.cpp:256-305,137-205, A/timed.cpp:74-81):
+    work_scale 0.765 and compose_scale 0.791 from (scaled-down) WORK / COMPOSE_MEGAPIX constants, cameras at work scale, warped_image_scale
+    = (float)cameras[0].focal, seam_work_aspect and compose_work_aspect as ratios; blender sized from cvRound(full * scale) = (51, 32), maps
+    and masks built for (int)(full * scale) = (50, 31) -- the reference's own mismatch, reproduced -- and the per-frame cuda::resize in
+    front of remap #1 (k_prescale): bit-identical to oracle-G."""
+    res = _default("megapix")
     assert res["error"] is None and res["roi_equal"], res
     assert res["mesh_maps"] == 0 and res["warped"] == 0 and res["gauss0"] == 0 and res["gauss2"] == 0, res
     assert res["pano"] == 0 and res["pano_nonzero"] > res["pano_samples"] // 2, res
@@ -176,3 +178,11 @@ def test_generic_path_below_three_bands_on_the_emulated_runtime():
     assert res["error"] is None and res["roi_equal"] and res["warped"] == 0 and res["gauss0"] == 0 and res["gauss2"] == 0, res
     assert res["pano"] == 0 and res["pano_nonzero"] > res["pano_samples"] // 2, res
     assert "k_legacy_blend_collapse" in " ".join(res["launched"]) and res["launch_count"] == 5, res["launched"]
+
+
+@pytest.mark.skipif(not os.environ.get("VSB_EMU_FULL"), reason="another minute of interpretation: set VSB_EMU_FULL=1 (compose_scale with a pano_width)")
+def test_product_library_compose_scale_on_the_emulated_runtime():
+    """vsb_calibrate_rig_scaled: compose_scale 0.8 on 61 x 41 frames with this repository's pano_width parametrisation (work_scale 1)."""
+    res = _run(dict(n_views=4, src_w=61, src_h=41, pano_width=192, num_bands=3, compose_scale=0.8))
+    assert res["error"] is None and res["roi_equal"] and res["pano"] == 0 and res["warped"] == 0 and res["mesh_maps"] == 0, res
+    assert "k_prescale" in " ".join(res["launched"]), res["launched"]

@@ -144,3 +144,63 @@ def test_scaled_wire_formats_and_host_path(cuda, og):
     d_out = torch.full((H, W, 3), 0xAB, dtype=torch.uint8, device="cuda")
     grig.st.compose([t.data_ptr() for t in d_nv], sw, [d_out.data_ptr()], W * 3, stream())
     _eq(host(d_out), og.s16_to_u8(orig.compose(bgr)[0]), "NV12 in -> resize -> compose -> CV_8UC3 out")
+
+
+REF_RIG, REF_MEGAPIX = (6, 1920, 1080, 5), (0.6, 1.4)   # (cameras, frame width, frame height, bands), (WORK_MEGAPIX, COMPOSE_MEGAPIX) of A/defs.h:51-53
+
+
+@pytest.mark.parametrize("on_device", [False, True])
+def test_reference_default_scales_at_1080p(cuda, og, on_device):
+    """vsb_calibrate_rig_megapix(0.6, 1.4): stitch_calib's defaults on 6 x 1080p -- work_scale 0.538, compose_scale 0.822, sphere radius
+    = the work-scale focal length x compose_work_aspect (a 4955-wide panorama), 1578 x 887 frames against 1577 x 887 maps.  Host
+    calibration: bit-exact against oracle-G.  Device calibration: the same geometry, panorama equal to oracle-G's from the device's own
+    products (as for every device calibration; its maps differ from libm's by ulps)."""
+    import torch
+    import vsb200
+    from oracle import pipeline as op
+    from tests.gpu_util import dev, host, stream
+    B, S = vsb200.binding, vsb200.synth
+    n, sw, sh, nb = REF_RIG
+    gains = S.gains(n)
+    ws, cs = B.ref_scales(sw, sh, *REF_MEGAPIX)
+    orig = op.OracleRig(n, sw, sh, 0, num_bands=nb, enable_local=True, gains=gains, compose_scale=cs, work_scale=ws)
+    st = B.Stitcher(n, nb, True, 1)
+    st.calibrate_rig_megapix(0, sw, sh, REF_MEGAPIX[0], REF_MEGAPIX[1], 90.0, gains, on_device=on_device)
+    roi, rpad, bands = st.get_roi()
+    assert tuple(roi) == tuple(orig.roi_final) and tuple(rpad) == tuple(orig.roi_padded) and bands == orig.num_bands
+    info = st.rig_info()
+    assert abs(info.scale - float(orig.scale)) == 0.0
+    xmaps, ymaps, masks = [], [], []
+    for i in range(n):
+        w, h = info.view_roi[i][2], info.view_roi[i][3]
+        assert (w, h) == tuple(orig.sizes[i]) and (info.view_roi[i][0], info.view_roi[i][1]) == tuple(orig.corners[i])
+        assert st.view_geometry(i) == orig.blender.view_geom(i)
+        a = np.empty((h, w), np.float32); st.debug_read(8, i, 0, 0, a.ctypes.data, a.nbytes)
+        b = np.empty((h, w), np.float32); st.debug_read(9, i, 0, 0, b.ctypes.data, b.nbytes)
+        g = st.view_geometry(i)
+        bw, bh = g["x_br"] - g["x_tl"], g["y_br"] - g["y_tl"]
+        w0 = np.empty((bh, bw), np.float32); st.debug_read(2, i, 0, 0, w0.ctypes.data, w0.nbytes)
+        m = np.rint(w0[g["top"]:g["top"] + h, g["left"]:g["left"] + w] * 255).astype(np.uint8)
+        if on_device:
+            inside = (orig.xmaps[i] > -2) & (orig.xmaps[i] < orig.comp_w + 1) & (orig.ymaps[i] > -2) & (orig.ymaps[i] < orig.comp_h + 1) & ~((orig.xmaps[i] == -1) & (orig.ymaps[i] == -1))
+            assert np.abs(a - orig.xmaps[i])[inside].max() <= 2e-3 and np.abs(b - orig.ymaps[i])[inside].max() <= 2e-3
+        else:
+            _eq(a, orig.xmaps[i], f"x projection map view {i}")
+            _eq(b, orig.ymaps[i], f"y projection map view {i}")
+            _eq(m, orig.masks[i], f"seam mask view {i}")
+        xmaps.append(a); ymaps.append(b); masks.append(m)
+    ref = orig
+    if on_device:   # oracle-G on the device's own products: everything downstream of the maps is exact
+        ref = op.OracleRig.from_products(sw, sh, orig.corners, orig.prep_sizes, xmaps, ymaps, masks, nb, True, orig.gains)
+        ref.sizes = [tuple(z) for z in orig.sizes]
+        ref.scaled, ref.compose_scale, ref.comp_w, ref.comp_h = True, orig.compose_scale, orig.comp_w, orig.comp_h
+    for i in range(n):
+        mx, my = S.mesh(*orig.sizes[i])
+        ref.set_mesh(i, mx, my)
+        st.set_mesh(i, mx.ctypes.data, my.ctypes.data, mx.shape[0], mx.shape[1])
+    frames = [S.frame(i, 0, sw, sh) for i in range(n)]
+    srcs = [dev(f) for f in frames]
+    W, H = roi[2], roi[3]
+    out = torch.full((H, W, 3), -12345, dtype=torch.int16, device="cuda")
+    st.compose([t.data_ptr() for t in srcs], sw * 3, [out.data_ptr()], W * 6, stream())
+    _eq(host(out), ref.compose(frames)[0], "panorama at the reference's default scales")

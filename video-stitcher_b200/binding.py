@@ -32,6 +32,7 @@ SYMBOLS = [
     "vsb_shard_plan", "vsb_shard_peer_bytes", "vsb_shard_pack", "vsb_shard_unpack", "vsb_feed_batch", "vsb_blend_batch",
     "vsb_compose_size", "vsb_rig_camera_scaled", "vsb_set_compose_scale", "vsb_calibrate_rig_scaled",
     "vsb_split_plan", "vsb_calibrate_rig_split", "vsb_view_window",
+    "vsb_ref_scales", "vsb_rig_camera_work", "vsb_calibrate_rig_megapix",
 ]
 CONSUME_RGB, CONSUME_I420 = 0, 1
 IN_BGR8, IN_NV12 = 0, 1
@@ -102,6 +103,19 @@ def split_plan(projection, pano_width, n_cameras, src_w, src_h, num_bands, hfov_
     cam, x0, w = (C.c_int * MAX_VIEWS)(), (C.c_int * MAX_VIEWS)(), (C.c_int * MAX_VIEWS)()
     check(lib().vsb_split_plan(projection, pano_width, n_cameras, src_w, src_h, C.c_double(hfov_deg), num_bands, C.byref(n), cam, x0, w))
     return [(cam[k], x0[k], w[k]) for k in range(n.value)]
+
+
+def ref_scales(src_w, src_h, work_megapix=0.6, compose_megapix=1.4):
+    ws, cs = C.c_double(), C.c_double()
+    check(lib().vsb_ref_scales(src_w, src_h, C.c_double(work_megapix), C.c_double(compose_megapix), C.byref(ws), C.byref(cs)))
+    return ws.value, cs.value
+
+
+def rig_camera_work(n_views, i, src_w, src_h, hfov_deg, work_scale, aspect):
+    K = (C.c_float * 9)()
+    R = (C.c_float * 9)()
+    check(lib().vsb_rig_camera_work(n_views, i, src_w, src_h, C.c_double(hfov_deg), C.c_double(work_scale), C.c_double(aspect), K, R))
+    return list(K), list(R)
 
 
 def compose_size(full_w, full_h, compose_scale):
@@ -204,6 +218,14 @@ class Stitcher:
         cam, x0, fw = C.c_int(), C.c_int(), C.c_int()
         check(lib().vsb_view_window(self._h, view, C.byref(cam), C.byref(x0), C.byref(fw)))
         return cam.value, x0.value, fw.value
+
+    def calibrate_rig_megapix(self, projection, src_w, src_h, work_megapix=0.6, compose_megapix=1.4, hfov_deg=90.0, gains=None, on_device=False):
+        """stitch_calib with its own constants: the reference's default panorama geometry"""
+        g = None
+        if gains is not None:
+            g = (C.c_float * self.num_views)(*[float(v) for v in gains])
+        check(lib().vsb_calibrate_rig_megapix(self._h, projection, src_w, src_h, C.c_double(hfov_deg), g, C.c_double(work_megapix),
+                                              C.c_double(compose_megapix), int(bool(on_device))))
 
     def set_compose_scale(self, compose_scale, full_w, full_h):
         check(lib().vsb_set_compose_scale(self._h, C.c_double(compose_scale), full_w, full_h))

@@ -489,6 +489,33 @@ int vsb_rig_camera_scaled(int n_views, int i, int src_w, int src_h, double hfov_
     return VSB_OK;
 }
 
+// calibrateCameras at a work scale (A/calibration.cpp:54-60: ppx = (full.width * work_scale) / 2, focal = focal_tmp * ppx, in double),
+// then focal, ppx, ppy *= aspect (:168-172: compose_work_aspect = compose_scale / work_scale; 1 for the work-scale camera itself) and
+// K().convertTo(CV_32F).  work_scale = aspect = 1 is vsb_rig_camera, work_scale = 1 is vsb_rig_camera_scaled.
+int vsb_rig_camera_work(int n_views, int i, int src_w, int src_h, double hfov_deg, double work_scale, double aspect, float K[9], float R[9])
+{
+    int r = vsb_rig_camera(n_views, i, src_w, src_h, hfov_deg, K, R);
+    if (r != VSB_OK) return r;
+    if (!(work_scale > 0) || !(aspect > 0)) return vsb::fail(VSB_ERR_INVALID, "rig_camera_work: work_scale and aspect must be > 0");
+    const double PI = 3.1415926535897932384626;
+    double ppx = (src_w * work_scale) / 2.0, ppy = (src_h * work_scale) / 2.0;
+    double focal = (1.0 / std::tan(hfov_deg * PI / 180.0 * 0.5)) * ppx;
+    focal *= aspect; ppx *= aspect; ppy *= aspect;
+    K[0] = (float)focal; K[2] = (float)ppx; K[4] = (float)focal; K[5] = (float)ppy;
+    return VSB_OK;
+}
+
+// work_scale and compose_scale as stitch_calib / warpImages derive them from WORK_MEGAPIX / COMPOSE_MEGAPIX (A/calibration.cpp:270-277,
+// 140-143; defaults 0.6 / 1.4, A/defs.h:51-53): min(1, sqrt(MEGAPIX * 1e6 / area)); a negative value means scale 1.
+int vsb_ref_scales(int src_w, int src_h, double work_megapix, double compose_megapix, double *work_scale, double *compose_scale)
+{
+    if (src_w <= 0 || src_h <= 0) return vsb::fail(VSB_ERR_INVALID, "ref_scales: bad frame size");
+    const double area = (double)(src_w * src_h);
+    if (work_scale) *work_scale = work_megapix < 0 ? 1.0 : std::min(1.0, std::sqrt(work_megapix * 1e6 / area));
+    if (compose_scale) *compose_scale = compose_megapix <= 0 ? 1.0 : std::min(1.0, std::sqrt(compose_megapix * 1e6 / area));
+    return VSB_OK;
+}
+
 // The sizes compose_scale implies, exactly as the reference derives them: frame[2] = the frame remap #1 reads -- the caller's
 // full frame, or cvRound(full * scale) when |scale - 1| > 0.1 (A/calibration.cpp:157-161; the same test decides the per-frame
 // cuda::resize, A/timed.cpp:75-77, whose dsize is that cvRound) -- which also sizes the blender (:176-178); map_src[2] = (int)(full *
@@ -525,11 +552,14 @@ int vsb_voronoi_seams(int n, const int *sizes_wh, const int *corners_xy, uint8_t
 
 // n_cameras = 0: one view per camera (cfg.num_views cameras).  n_cameras > 0: the split calibration -- cameras that wrap around +-pi
 // become two views (plan_parts), cfg.num_views must equal the number of parts (vsb_split_plan tells it before vsb_create).
+// pano_width > 0: sphere radius pano_width / 2 pi (work_scale must be 1).  pano_width = 0: the reference's own warped_image_scale =
+// (float)cameras[0].focal at work_scale (stitch_calib, A/calibration.cpp:283-289).
 static int calibrate_rig_host(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains,
-                              double compose_scale, int n_cameras = 0)
+                              double compose_scale, int n_cameras = 0, double work_scale = 1.0)
 {
     using namespace vsb;
-    if (!s || pano_width <= 0 || src_w <= 0 || src_h <= 0) return fail(VSB_ERR_INVALID, "calibrate_rig: bad arguments");
+    if (!s || pano_width < 0 || src_w <= 0 || src_h <= 0 || !(work_scale > 0) || (pano_width > 0 && work_scale != 1.0))
+        return fail(VSB_ERR_INVALID, "calibrate_rig: bad arguments");
     vsb_config cfg;
     int r = vsb_get_config(s, &cfg);
     if (r != VSB_OK) return r;
@@ -539,17 +569,19 @@ static int calibrate_rig_host(vsb_stitcher *s, int projection, int pano_width, i
     const bool split = n_cameras > 0;
     const int n = split ? n_cameras : cfg.num_views;
     if (split && (compose_scale != 1.0 || n > VSB_MAX_VIEWS)) return fail(VSB_ERR_INVALID, "calibrate_rig_split: bad arguments (compose_scale must be 1)");
-    float scale = (float)(pano_width / (2.0 * 3.1415926535897932384626));  // sphere radius: pano_width px per 2*pi
     std::vector<float> K(9 * n), R(9 * n);
-    for (int i = 0; i < n; ++i) {
-        r = vsb_rig_camera(n, i, src_w, src_h, hfov_deg, &K[9 * i], &R[9 * i]);
+    for (int i = 0; i < n; ++i) {   // the cameras at work scale (for work_scale = 1 exactly vsb_rig_camera's)
+        r = vsb_rig_camera_work(n, i, src_w, src_h, hfov_deg, work_scale, 1.0, &K[9 * i], &R[9 * i]);
         if (r != VSB_OK) return r;
     }
+    float scale = pano_width > 0 ? (float)(pano_width / (2.0 * 3.1415926535897932384626))  // sphere radius: pano_width px per 2*pi
+                                 : K[0];                                                     // warped_image_scale = (float)cameras[0].focal
     // ---- seam scale (360_stitcher/calibration.cpp:92-135; SEAM_MEAGPIX = 0.01, 360_stitcher/defs.h:52)
     const double seam_scale = std::min(1.0, std::sqrt(0.01 * 1e6 / ((double)src_w * src_h)));
+    const double seam_work_aspect = seam_scale / work_scale;   // :280
     const int seam_w = (int)std::nearbyint(src_w * seam_scale), seam_h = (int)std::nearbyint(src_h * seam_scale);
-    const float seam_warp_scale = static_cast<float>(scale * seam_scale);
-    const float swa = (float)seam_scale;
+    const float seam_warp_scale = static_cast<float>(scale * seam_work_aspect);
+    const float swa = (float)seam_work_aspect;
     std::vector<std::vector<uint8_t>> seam_masks(n);
     std::vector<int> seam_sizes(2 * n), seam_corners(2 * n);
     for (int i = 0; i < n; ++i) {
@@ -573,11 +605,12 @@ static int calibrate_rig_host(vsb_stitcher *s, int projection, int pano_width, i
     }
     // ---- compose scale (360_stitcher/calibration.cpp:137-246)
     const int full_w = src_w, full_h = src_h;
-    if (compose_scale != 1.0) {
+    const double compose_work_aspect = compose_scale / work_scale;   // :148
+    if (compose_work_aspect != 1.0) {
         // warper scale: warped_image_scale * static_cast<float>(compose_work_aspect) (:151); cameras: focal, ppx, ppy *= aspect (:168-172)
-        scale = scale * static_cast<float>(compose_scale);
+        scale = scale * static_cast<float>(compose_work_aspect);
         for (int i = 0; i < n; ++i) {
-            r = vsb_rig_camera_scaled(n, i, full_w, full_h, hfov_deg, compose_scale, &K[9 * i], &R[9 * i]);
+            r = vsb_rig_camera_work(n, i, full_w, full_h, hfov_deg, work_scale, compose_work_aspect, &K[9 * i], &R[9 * i]);
             if (r != VSB_OK) return r;
         }
     }
@@ -664,6 +697,7 @@ static int calibrate_rig_host(vsb_stitcher *s, int projection, int pano_width, i
 
 int vsb_calibrate_rig(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains)
 {
+    if (pano_width <= 0) return vsb::fail(VSB_ERR_INVALID, "calibrate_rig: bad arguments");
     return calibrate_rig_host(s, projection, pano_width, src_w, src_h, hfov_deg, gains, 1.0);
 }
 
@@ -699,12 +733,12 @@ int vsb_split_plan(int projection, int pano_width, int n_cameras, int src_w, int
 }
 
 static int calibrate_rig_dev(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains,
-                             double compose_scale, int n_cameras = 0);
+                             double compose_scale, int n_cameras = 0, double work_scale = 1.0);
 
 int vsb_calibrate_rig_split(vsb_stitcher *s, int projection, int pano_width, int n_cameras, int src_w, int src_h, double hfov_deg,
                             const float *gains, int on_device)
 {
-    if (n_cameras < 1) return vsb::fail(VSB_ERR_INVALID, "calibrate_rig_split: n_cameras must be >= 1");
+    if (n_cameras < 1 || pano_width <= 0) return vsb::fail(VSB_ERR_INVALID, "calibrate_rig_split: n_cameras must be >= 1, pano_width > 0");
     return on_device ? calibrate_rig_dev(s, projection, pano_width, src_w, src_h, hfov_deg, gains, 1.0, n_cameras)
                      : calibrate_rig_host(s, projection, pano_width, src_w, src_h, hfov_deg, gains, 1.0, n_cameras);
 }
@@ -746,10 +780,11 @@ int vsb_resize_linear_u8(const uint8_t *d_src, int sw, int sh, size_t src_pitch,
 // sinf / cosf itself, so the projection maps agree with the host path to ~1e-3 px, not bit for bit (the reference's own maps come
 // from the same kind of device code); everything downstream of the maps is exact.
 static int calibrate_rig_dev(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains,
-                             double compose_scale, int n_cameras)
+                             double compose_scale, int n_cameras, double work_scale)
 {
     using namespace vsb;
-    if (!s || pano_width <= 0 || src_w <= 0 || src_h <= 0) return fail(VSB_ERR_INVALID, "calibrate_rig_device: bad arguments");
+    if (!s || pano_width < 0 || src_w <= 0 || src_h <= 0 || !(work_scale > 0) || (pano_width > 0 && work_scale != 1.0))
+        return fail(VSB_ERR_INVALID, "calibrate_rig_device: bad arguments");
     vsb_config cfg;
     int r = vsb_get_config(s, &cfg);
     if (r != VSB_OK) return r;
@@ -763,21 +798,22 @@ static int calibrate_rig_dev(vsb_stitcher *s, int projection, int pano_width, in
     const bool split = n_cameras > 0;   // cameras that wrap around +-pi become two views, as in calibrate_rig_host
     const int n = split ? n_cameras : cfg.num_views;
     if (split && (compose_scale != 1.0 || n > VSB_MAX_VIEWS)) return fail(VSB_ERR_INVALID, "calibrate_rig_split: bad arguments (compose_scale must be 1)");
-    float scale = (float)(pano_width / (2.0 * 3.1415926535897932384626));
     CalibState *cs = new CalibState();
     cs->n = n; cs->projection = projection; cs->src_w = src_w; cs->src_h = src_h;
     std::vector<float> K(9 * n), R(9 * n);
-    for (int i = 0; i < n; ++i) {
-        r = vsb_rig_camera(n, i, src_w, src_h, hfov_deg, &K[9 * i], &R[9 * i]);
+    for (int i = 0; i < n; ++i) {   // the cameras at work scale; scales as in calibrate_rig_host
+        r = vsb_rig_camera_work(n, i, src_w, src_h, hfov_deg, work_scale, 1.0, &K[9 * i], &R[9 * i]);
         if (r != VSB_OK) { calib_state_free(cs); return r; }
     }
+    float scale = pano_width > 0 ? (float)(pano_width / (2.0 * 3.1415926535897932384626)) : K[0];
     cudaStream_t st = nullptr;  // calibration time: the default stream, synchronised at the end of every phase
     const dim3 b(32, 8);
     auto bail = [&](int code) { cudaDeviceSynchronize(); calib_state_free(cs); return code; };
     // ---- seam scale (360_stitcher/calibration.cpp:92-135)
     const double seam_scale = std::min(1.0, std::sqrt(0.01 * 1e6 / ((double)src_w * src_h)));
     const int seam_w = (int)std::nearbyint(src_w * seam_scale), seam_h = (int)std::nearbyint(src_h * seam_scale);
-    const float seam_warp_scale = static_cast<float>(scale * seam_scale), swa = (float)seam_scale;
+    const double seam_work_aspect = seam_scale / work_scale;
+    const float seam_warp_scale = static_cast<float>(scale * seam_work_aspect), swa = (float)seam_work_aspect;
     cs->seam_scale = seam_scale; cs->seam_w = seam_w; cs->seam_h = seam_h; cs->seam_warp_scale = seam_warp_scale;
     std::vector<int> seam_sizes(2 * n), seam_corners(2 * n);
     std::vector<uint8_t *> seam_masks(n, nullptr);
@@ -813,10 +849,11 @@ static int calibrate_rig_dev(vsb_stitcher *s, int projection, int pano_width, in
     if (r != VSB_OK) { free_seams(); return bail(r); }
     // ---- compose scale (360_stitcher/calibration.cpp:137-246); the sizes as in calibrate_rig_host
     const int full_w = src_w, full_h = src_h;
-    if (compose_scale != 1.0) {
-        scale = scale * static_cast<float>(compose_scale);
+    const double compose_work_aspect = compose_scale / work_scale;
+    if (compose_work_aspect != 1.0) {
+        scale = scale * static_cast<float>(compose_work_aspect);
         for (int i = 0; i < n; ++i) {
-            r = vsb_rig_camera_scaled(n, i, full_w, full_h, hfov_deg, compose_scale, &K[9 * i], &R[9 * i]);
+            r = vsb_rig_camera_work(n, i, full_w, full_h, hfov_deg, work_scale, compose_work_aspect, &K[9 * i], &R[9 * i]);
             if (r != VSB_OK) { free_seams(); return bail(r); }
         }
     }
@@ -890,15 +927,31 @@ static int calibrate_rig_dev(vsb_stitcher *s, int projection, int pano_width, in
 
 int vsb_calibrate_rig_device(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains)
 {
+    if (pano_width <= 0) return vsb::fail(VSB_ERR_INVALID, "calibrate_rig_device: bad arguments");
     return calibrate_rig_dev(s, projection, pano_width, src_w, src_h, hfov_deg, gains, 1.0);
 }
 
 // Both calibrations with the reference's compose_scale (A/calibration.cpp:137-205): the cameras and the warper are scaled, the ROIs,
 // maps and masks are built for the scaled frame, and every frame handed to vsb_feed / vsb_compose / vsb_submit_host (still
 // src_w x src_h) goes through cuda::resize(..., Size(), compose_scale, compose_scale, INTER_LINEAR) first (A/timed.cpp:74-81).
+// stitch_calib with its own constants (A/calibration.cpp:256-305; A/defs.h:51-53): work_scale from WORK_MEGAPIX, compose_scale from
+// COMPOSE_MEGAPIX (vsb_ref_scales), the cameras of calibrateCameras at work scale, warped_image_scale = (float)cameras[0].focal,
+// seam_work_aspect = seam_scale / work_scale, compose_work_aspect = compose_scale / work_scale -- the reference's default panorama
+// geometry, which a pano_width cannot express (the sphere radius is a float derived from the focal length, not from an integer width).
+int vsb_calibrate_rig_megapix(vsb_stitcher *s, int projection, int src_w, int src_h, double hfov_deg, const float *gains,
+                              double work_megapix, double compose_megapix, int on_device)
+{
+    double ws = 1.0, cs = 1.0;
+    int r = vsb_ref_scales(src_w, src_h, work_megapix, compose_megapix, &ws, &cs);
+    if (r != VSB_OK) return r;
+    return on_device ? calibrate_rig_dev(s, projection, 0, src_w, src_h, hfov_deg, gains, cs, 0, ws)
+                     : calibrate_rig_host(s, projection, 0, src_w, src_h, hfov_deg, gains, cs, 0, ws);
+}
+
 int vsb_calibrate_rig_scaled(vsb_stitcher *s, int projection, int pano_width, int src_w, int src_h, double hfov_deg, const float *gains,
                              double compose_scale, int on_device)
 {
+    if (pano_width <= 0) return vsb::fail(VSB_ERR_INVALID, "calibrate_rig_scaled: bad arguments");
     return on_device ? calibrate_rig_dev(s, projection, pano_width, src_w, src_h, hfov_deg, gains, compose_scale)
                      : calibrate_rig_host(s, projection, pano_width, src_w, src_h, hfov_deg, gains, compose_scale);
 }
