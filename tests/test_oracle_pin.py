@@ -279,6 +279,16 @@ def test_live_scaled_rig_geometry_vs_reference_projector(og):
                 assert tuple(roi_r) == roi
                 ok = ~((xm == -1) & (ym == -1)) & ~((xr == -1) & (yr == -1)) & (xr > -2) & (xr < msrc[0] + 1) & (yr > -2) & (yr < msrc[1] + 1)   # the part that addresses the frame
                 assert ok.sum() > 100 and np.abs(xm - xr)[ok].max() <= 2e-3 and np.abs(ym - yr)[ok].max() <= 2e-3
+    # stitch_calib's default scales on 6 x 1080p (WORK 0.6, COMPOSE 1.4): cameras at work scale x compose_work_aspect, sphere radius from
+    # the work-scale focal length -- the oracle rig's ROIs are the reference projector's
+    ws, cs = op.ref_scales(1920, 1080)
+    rig = op.OracleRig(6, 1920, 1080, 0, num_bands=5, compose_scale=cs, work_scale=ws)
+    for i in range(6):
+        K, R = og.rig_camera_work(6, i, 1920, 1080, 90.0, ws, cs / ws)
+        assert np.array_equal(K, rig.K[i]) and np.array_equal(R, rig.R[i])
+        prep = vr.warp_roi(0, rig.scale, K, R, rig.comp_w, rig.comp_h)
+        assert (prep[:2], prep[2:]) == (tuple(rig.corners[i]), tuple(rig.prep_sizes[i]))
+        assert vr.warp_roi(0, rig.scale, K, R, *rig.map_src)[2:] == tuple(rig.sizes[i])
     rig = op.OracleRig(4, 320, 240, 1024, num_bands=3, compose_scale=0.75)
     assert (rig.comp_w, rig.comp_h) == (240, 180) and rig.scaled and rig.sizes == rig.prep_sizes
     rig = op.OracleRig(4, 61, 41, 192, num_bands=3, compose_scale=0.8)          # cvRound (49, 33) vs (int) (48, 32)
