@@ -16,7 +16,11 @@ out = {}
 for name, kw in (("small4", dict(n_views=4, src_w=320, src_h=240, pano_width=1024, num_bands=3, enable_local=True)),
                  ("cyl5", dict(n_views=5, src_w=256, src_h=192, pano_width=800, num_bands=4, enable_local=True, projection=1)),
                  # the rig bench.py composes view-sharded on N GPUs to verify parity inside the scaling run ("parity_checked")
-                 ("shard6", dict(n_views=6, src_w=480, src_h=270, pano_width=1536, num_bands=4, enable_local=True))):
+                 ("shard6", dict(n_views=6, src_w=480, src_h=270, pano_width=1536, num_bands=4, enable_local=True)),
+                 # compose_scale != 1 (exact sizes; the reference's cvRound / (int) mismatch): the two panoramas a B200 reproduced through
+                 # the C ABI in round 2 (profiles/r02_hw_check_compose_scale_and_split.log; same hashes in scratch/runs_r02/r2v_expected.json)
+                 ("scale_small4", dict(n_views=4, src_w=320, src_h=240, pano_width=1024, num_bands=3, enable_local=True, compose_scale=0.75)),
+                 ("scale_mismatch6", dict(n_views=6, src_w=322, src_h=182, pano_width=960, num_bands=4, enable_local=True, compose_scale=0.8))):
     rig = op.OracleRig(gains=S.gains(kw["n_views"]), **kw)
     for i in range(kw["n_views"]):
         rig.set_mesh(i, *S.mesh(*rig.sizes[i]))

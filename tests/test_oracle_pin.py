@@ -64,7 +64,7 @@ def test_consumer_epilogue_exact(og, gold):
 
 
 def test_whole_path_known_answers(og):
-    """Whole-path KAT: oracle-G's panoramas of three small rigs hash to the committed values (tests/golden/make_compose_hashes.py).
+    """Whole-path KAT: oracle-G's panoramas of five small rigs hash to the committed values (tests/golden/make_compose_hashes.py).
     The GPU parity suite was green against exactly this oracle, so a drift of the restatement cannot go unnoticed."""
     import hashlib
     import json
@@ -74,7 +74,10 @@ def test_whole_path_known_answers(og):
     want = json.load(open(os.path.join(os.path.dirname(GOLD), "oracle_compose_hashes.json")))
     cases = {"small4": dict(n_views=4, src_w=320, src_h=240, pano_width=1024, num_bands=3, enable_local=True),
              "cyl5": dict(n_views=5, src_w=256, src_h=192, pano_width=800, num_bands=4, enable_local=True, projection=1),
-             "shard6": dict(n_views=6, src_w=480, src_h=270, pano_width=1536, num_bands=4, enable_local=True)}  # bench.py's in-run parity rig
+             "shard6": dict(n_views=6, src_w=480, src_h=270, pano_width=1536, num_bands=4, enable_local=True),   # bench.py's in-run parity rig
+             # compose_scale != 1: the two panoramas a B200 reproduced through the C ABI (profiles/r02_hw_check_compose_scale_and_split.log)
+             "scale_small4": dict(n_views=4, src_w=320, src_h=240, pano_width=1024, num_bands=3, enable_local=True, compose_scale=0.75),
+             "scale_mismatch6": dict(n_views=6, src_w=322, src_h=182, pano_width=960, num_bands=4, enable_local=True, compose_scale=0.8)}
     for name, kw in cases.items():
         rig = op.OracleRig(gains=S.gains(kw["n_views"]), **kw)
         for i in range(kw["n_views"]):
